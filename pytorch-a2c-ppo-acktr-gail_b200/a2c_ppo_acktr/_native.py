@@ -1,0 +1,119 @@
+"""ctypes binding of liba2cb.so (C ABI declared in include/a2cb.h).
+
+There is deliberately no CPU or eager-PyTorch fallback: if the shared library is
+missing, or a tensor handed to a kernel wrapper does not live on a CUDA device,
+the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "liba2cb.so")
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_f64 = ctypes.c_double
+c_f32 = ctypes.c_float
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class GatherField(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_i64)]
+
+
+_SIGNATURES = {
+    "a2cb_abi_version": (c_int, []),
+    "a2cb_last_error": (ctypes.c_char_p, []),
+    "a2cb_launch_count": (c_i64, []),
+    "a2cb_returns_scan": (c_int, [c_void_p] * 6 + [c_int, c_i64, c_f64, c_f64, c_int, c_int, c_int, c_void_p]),
+    "a2cb_gather_rows": (c_int, [ctypes.POINTER(GatherField), c_int, c_void_p, c_i64, c_int, c_i64, c_i64, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads liba2cb.so once; raises if it has not been built (python build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                "liba2cb.so not found at %s -- build it with `python __graft_entry__.py` or "
+                "`python pytorch-a2c-ppo-acktr-gail_b200/build.py`; there is no CPU fallback" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise NativeError("%s failed (%d): %s" % (what, rc, lib().a2cb_last_error().decode()))
+
+
+def launch_count():
+    return int(lib().a2cb_launch_count())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def dptr(t, dtype=None, name="tensor"):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise NativeError("%s must be a CUDA tensor (got %s); the update path has no CPU fallback"
+                          % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise NativeError("%s must be %s (got %s)" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise NativeError("%s must be contiguous" % name)
+    return c_void_p(t.data_ptr())
+
+
+# ---------------------------------------------------------------------------
+# thin wrappers
+# ---------------------------------------------------------------------------
+def returns_scan(rewards, value_preds, returns, masks, bad_masks, next_value, gamma, gae_lambda,
+                 use_gae, use_proper_time_limits, schedule=0):
+    T, N = rewards.shape[0], rewards.shape[1]
+    f32 = torch.float32
+    ptrs = [dptr(rewards, f32, "rewards"), dptr(value_preds, f32, "value_preds"),
+            dptr(returns, f32, "returns"), dptr(masks, f32, "masks"),
+            dptr(bad_masks, f32, "bad_masks"), dptr(next_value, f32, "next_value")]
+    with torch.cuda.device(rewards.device):
+        rc = lib().a2cb_returns_scan(
+            *ptrs, T, N, float(gamma), float(gae_lambda), int(bool(use_gae)),
+            int(bool(use_proper_time_limits)), int(schedule), stream_ptr(rewards.device))
+    check(rc, "a2cb_returns_scan")
+
+
+def gather_rows(pairs, idx, n_out_rows, mode=0, E=0, N=0):
+    """pairs: list of (src, dst) tensors; rows are dim 0 of the flattened [rows, ...] views."""
+    arr = (GatherField * len(pairs))()
+    for i, (src, dst) in enumerate(pairs):
+        if src.dtype != dst.dtype:
+            raise NativeError("gather_rows: dtype mismatch")
+        row_bytes = dst[0].numel() * dst.element_size() if dst.shape[0] else 0
+        if dst.shape[0] == 0:
+            row_bytes = src[0].numel() * src.element_size()
+        arr[i].src = dptr(src, name="gather src").value
+        arr[i].dst = dptr(dst, name="gather dst").value
+        arr[i].row_bytes = row_bytes
+    dev = pairs[0][0].device
+    idx_p = dptr(idx, torch.int64, "idx")
+    with torch.cuda.device(dev):
+        rc = lib().a2cb_gather_rows(arr, len(pairs), idx_p, int(n_out_rows),
+                                    int(mode), int(E), int(N), stream_ptr(dev))
+    check(rc, "a2cb_gather_rows")

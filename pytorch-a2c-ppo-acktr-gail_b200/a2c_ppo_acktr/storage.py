@@ -1,0 +1,167 @@
+"""Rollout buffer with the reference's public surface, backed by sm_100a kernels.
+
+Drop-in for `a2c_ppo_acktr.storage.RolloutStorage` (reference storage.py:9-202):
+same constructor, same public tensor attributes ([T(+1), N, ...] layout), same
+`insert / after_update / compute_returns / feed_forward_generator /
+recurrent_generator` signatures, same assertion messages, same consumption of the
+global CPU RNG (one `randperm` per epoch, drawn when the generator is first
+advanced).  `compute_returns` is one reverse-scan kernel instead of a Python loop
+over time; the generators are one fused gather launch per minibatch instead of
+eight `aten::index` calls.
+
+One opt-in extension: `obs_dtype=torch.uint8` stores Atari frames as bytes (a
+quarter of the HBM footprint and gather traffic); the policy kernels normalise
+bytes to fp32/255 while loading.  The default (fp32) keeps the reference contract.
+"""
+import torch
+
+from . import _native
+
+
+def _space_is_discrete(action_space):
+    # duck-typed by class NAME, exactly as the reference does (storage.py:19,24)
+    return action_space.__class__.__name__ == 'Discrete'
+
+
+class RolloutStorage(object):
+    _MOVABLE = ('obs', 'recurrent_hidden_states', 'rewards', 'value_preds', 'returns',
+                'action_log_probs', 'actions', 'masks', 'bad_masks')
+
+    def __init__(self, num_steps, num_processes, obs_shape, action_space,
+                 recurrent_hidden_state_size, obs_dtype=torch.float32):
+        T, N = num_steps, num_processes
+        self.obs = torch.zeros(T + 1, N, *obs_shape, dtype=obs_dtype)
+        self.recurrent_hidden_states = torch.zeros(T + 1, N, recurrent_hidden_state_size)
+        self.rewards = torch.zeros(T, N, 1)
+        self.value_preds = torch.zeros(T + 1, N, 1)
+        self.returns = torch.zeros(T + 1, N, 1)
+        self.action_log_probs = torch.zeros(T, N, 1)
+        if _space_is_discrete(action_space):
+            self.actions = torch.zeros(T, N, 1, dtype=torch.int64)
+        else:
+            self.actions = torch.zeros(T, N, action_space.shape[0])
+        self.masks = torch.ones(T + 1, N, 1)
+        # 0 where an episode ended because of a time limit rather than a true terminal
+        self.bad_masks = torch.ones(T + 1, N, 1)
+
+        self.num_steps = T
+        self.step = 0
+        self._idx_cache = None
+
+    # -- placement ---------------------------------------------------------
+    def to(self, device):
+        for name in self._MOVABLE:
+            setattr(self, name, getattr(self, name).to(device))
+
+    # -- actor-side writes (reference storage.py:46-64) --------------------------
+    def insert(self, obs, recurrent_hidden_states, actions, action_log_probs,
+               value_preds, rewards, masks, bad_masks):
+        t = self.step
+        self.obs[t + 1].copy_(obs)
+        self.recurrent_hidden_states[t + 1].copy_(recurrent_hidden_states)
+        self.masks[t + 1].copy_(masks)
+        self.bad_masks[t + 1].copy_(bad_masks)
+        self.actions[t].copy_(actions)
+        self.action_log_probs[t].copy_(action_log_probs)
+        self.value_preds[t].copy_(value_preds)
+        self.rewards[t].copy_(rewards)
+        self.step = (t + 1) % self.num_steps
+
+    def after_update(self):
+        for buf in (self.obs, self.recurrent_hidden_states, self.masks, self.bad_masks):
+            buf[0].copy_(buf[-1])
+
+    # -- (1) returns / GAE: one reverse-scan kernel (reference storage.py:66-105) --
+    def compute_returns(self, next_value, use_gae, gamma, gae_lambda,
+                        use_proper_time_limits=True, schedule=0):
+        nv = next_value.detach().to(dtype=torch.float32).reshape(-1).contiguous()
+        if nv.numel() != self.rewards.size(1):
+            raise ValueError("next_value must hold one value per process")
+        _native.returns_scan(self.rewards, self.value_preds, self.returns, self.masks,
+                             self.bad_masks, nv, gamma, gae_lambda, use_gae,
+                             use_proper_time_limits, schedule)
+
+    # -- (2) minibatch generators -------------------------------------------------
+    def _flat_sources(self, advantages):
+        """[T*N, ...] views in the order of the yielded 8-tuple."""
+        T, N = self.rewards.size()[0:2]
+        srcs = [
+            self.obs[:-1].view(T * N, *self.obs.size()[2:]),
+            self.recurrent_hidden_states[:-1].view(T * N, self.recurrent_hidden_states.size(-1)),
+            self.actions.view(T * N, self.actions.size(-1)),
+            self.value_preds[:-1].view(T * N, 1),
+            self.returns[:-1].view(T * N, 1),
+            self.masks[:-1].view(T * N, 1),
+            self.action_log_probs.view(T * N, 1),
+        ]
+        if advantages is not None:
+            adv = advantages
+            if adv.dtype != torch.float32 or not adv.is_contiguous():
+                adv = adv.to(torch.float32).contiguous()
+            srcs.append(adv.view(T * N, 1))
+        return srcs
+
+    def feed_forward_generator(self, advantages, num_mini_batch=None, mini_batch_size=None):
+        num_steps, num_processes = self.rewards.size()[0:2]
+        batch_size = num_processes * num_steps
+
+        if mini_batch_size is None:
+            assert batch_size >= num_mini_batch, (
+                "PPO requires the number of processes ({}) "
+                "* number of steps ({}) = {} "
+                "to be greater than or equal to the number of PPO mini batches ({})."
+                "".format(num_processes, num_steps, num_processes * num_steps,
+                          num_mini_batch))
+            mini_batch_size = batch_size // num_mini_batch
+
+        # SubsetRandomSampler(range(B)) draws exactly one randperm(B) from the global
+        # CPU generator when iteration starts; BatchSampler(drop_last=True) cuts it into
+        # consecutive chunks (reference storage.py:122-125).
+        perm = torch.randperm(batch_size)
+        dev = self.rewards.device
+        perm_dev = perm.to(dev, non_blocking=False)
+        srcs = self._flat_sources(advantages)
+        for k in range(batch_size // mini_batch_size):
+            idx = perm_dev[k * mini_batch_size:(k + 1) * mini_batch_size]
+            outs = [torch.empty((mini_batch_size,) + tuple(s.shape[1:]), dtype=s.dtype, device=dev)
+                    for s in srcs]
+            _native.gather_rows(list(zip(srcs, outs)), idx, mini_batch_size, mode=0)
+            if advantages is None:
+                outs.append(None)
+            yield tuple(outs)
+
+    def recurrent_generator(self, advantages, num_mini_batch):
+        num_processes = self.rewards.size(1)
+        assert num_processes >= num_mini_batch, (
+            "PPO requires the number of processes ({}) "
+            "to be greater than or equal to the number of "
+            "PPO mini batches ({}).".format(num_processes, num_mini_batch))
+        E = num_processes // num_mini_batch
+        T, N = self.num_steps, num_processes
+        perm = torch.randperm(num_processes)
+        dev = self.rewards.device
+        perm_dev = perm.to(dev)
+        srcs = self._flat_sources(advantages)
+        hidden_src = self.recurrent_hidden_states[0]            # [N, H]: state at t = 0 only
+        for start in range(0, N, E):
+            if start + E > N:
+                # the reference walks perm[start + offset] past its end here
+                # (storage.py:154,165 with N % num_mini_batch != 0)
+                raise IndexError("index {} is out of bounds for dimension 0 with size {}".format(N, N))
+            env = perm_dev[start:start + E]
+            outs = []
+            pairs = []
+            for i, s in enumerate(srcs):
+                if i == 1:
+                    outs.append(None)
+                    continue
+                o = torch.empty((T * E,) + tuple(s.shape[1:]), dtype=s.dtype, device=dev)
+                outs.append(o)
+                pairs.append((s, o))
+            _native.gather_rows(pairs, env, T * E, mode=1, E=E, N=N)
+            h = torch.empty((E, hidden_src.size(-1)), dtype=hidden_src.dtype, device=dev)
+            _native.gather_rows([(hidden_src, h)], env, E, mode=0)
+            outs[1] = h
+            if advantages is None:
+                outs.append(None)
+            yield tuple(outs)

@@ -1,0 +1,74 @@
+"""Shared helpers of the test-suite: golden loading, rollout reconstruction, fingerprints."""
+import json
+import os
+
+import numpy as np
+import torch
+
+import synthetic
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SAMPLE = 16
+
+
+def load(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+def summary(t):
+    f = t.detach().cpu().reshape(-1).double()
+    n = f.numel()
+    pos = torch.linspace(0, n - 1, min(SAMPLE, n)).long()
+    return np.concatenate([[f.sum().item(), f.norm().item(), float(n)], f[pos].numpy()])
+
+
+def case_config(case):
+    cfg = json.loads(str(case["config"]))
+    cfg["obs_shape"] = tuple(cfg["obs_shape"])
+    cfg["action"] = tuple(cfg["action"])
+    return cfg
+
+
+def hidden_size_of(cfg):
+    if not cfg["recurrent"]:
+        return 1
+    return 512 if len(cfg["obs_shape"]) == 3 else 64
+
+
+def rollout_from_case(case, cfg, obs_uint8=False, device="cpu"):
+    """Rebuilds the rollout the golden file was produced from: frames/signals from the
+    counter-based generator, policy outputs (actions, log-probs, values) from the file."""
+    obs, rewards, masks, bad = synthetic.rollout_inputs(cfg, seed=0, obs_uint8=obs_uint8)
+    T, N = cfg["T"], cfg["N"]
+    H = hidden_size_of(cfg)
+    ro = {
+        "obs": torch.from_numpy(obs),
+        "rewards": torch.from_numpy(rewards),
+        "masks": torch.from_numpy(masks),
+        "bad_masks": torch.from_numpy(bad),
+        "actions": torch.from_numpy(case["ro_actions"]),
+        "action_log_probs": torch.from_numpy(case["ro_action_log_probs"]),
+        "value_preds": torch.from_numpy(case["ro_value_preds"]).clone(),
+        "next_value": torch.from_numpy(case["ro_next_value"]),
+        "returns": torch.zeros(T + 1, N, 1),
+    }
+    if cfg["recurrent"]:
+        ro["recurrent_hidden_states"] = torch.from_numpy(case["ro_recurrent_hidden_states"])
+    else:
+        ro["recurrent_hidden_states"] = torch.zeros(T + 1, N, H)
+    assert abs(ro["obs"].double().sum().item() - float(case["obs_sum"])) < 1e-3, "synthetic frames drifted"
+    return {k: v.to(device) for k, v in ro.items()}
+
+
+def assert_summary_close(got, want, rtol, atol, what="", elem_frac=0.0):
+    """Compares two `summary` fingerprints (sum, norm, n, samples).
+    elem_frac widens the per-sample tolerance by that fraction of the tensor's RMS value."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert got[2] == want[2], "%s: element count %s != %s" % (what, got[2], want[2])
+    n = want[2]
+    # the L2 norm bounds a sum's rounding noise: |sum err| <= sqrt(n) * |elem err|
+    scale = max(want[1], 1e-30)
+    assert abs(got[1] - want[1]) <= rtol * scale + atol, "%s: norm %r vs %r" % (what, got[1], want[1])
+    assert abs(got[0] - want[0]) <= ((rtol + elem_frac) * scale + atol) * np.sqrt(n), "%s: sum %r vs %r" % (what, got[0], want[0])
+    np.testing.assert_allclose(got[3:], want[3:], rtol=rtol, atol=atol + (rtol + elem_frac) * scale / np.sqrt(n), err_msg=what)
