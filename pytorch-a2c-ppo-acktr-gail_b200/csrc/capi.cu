@@ -43,8 +43,8 @@ int a2cb_returns_scan(const float* rewards, float* value_preds, float* returns, 
                       const float* bad_masks, const float* next_value, int32_t T, int64_t N,
                       double gamma, double gae_lambda, int32_t use_gae,
                       int32_t use_proper_time_limits, int32_t schedule, a2cb_stream_t stream) {
-    A2CB_REQUIRE(rewards && value_preds && returns && masks && next_value, "returns_scan: null pointer");
-    A2CB_REQUIRE(!use_proper_time_limits || bad_masks, "returns_scan: bad_masks required");
+    A2CB_REQUIRE((T == 0 || rewards) && value_preds && returns && (T == 0 || masks) && next_value, "returns_scan: null pointer");
+    A2CB_REQUIRE(T == 0 || !use_proper_time_limits || bad_masks, "returns_scan: bad_masks required");
     A2CB_REQUIRE(T >= 0 && N >= 0 && schedule >= 0 && schedule <= 2, "returns_scan: bad T/N/schedule");
     if (N == 0) return A2CB_OK;
     return returns_scan(rewards, value_preds, returns, masks, bad_masks, next_value, T, (long)N, gamma,
