@@ -75,6 +75,160 @@ typedef struct {
 int a2cb_gather_rows(const a2cb_gather_field_t* fields, int32_t n_fields, const int64_t* idx,
                      int64_t n_out_rows, int32_t mode, int64_t E, int64_t N, a2cb_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * (3) affine-indexed GEMM engine: conv / linear / GRU forward, dgrad and wgrad
+ *     reference call sites: a2c_ppo_acktr/model.py:176-180,185,190 (CNNBase),
+ *     model.py:209-218 (MLPBase), model.py:113,153-155 (GRU), distributions.py:69-72,
+ *     83-87 (heads) and their autograd backward; also kfac.py:29-64,216-227.
+ *
+ *   C[rowC(i) + colC(j)] = epi( alpha * sum_r A[rowA(i) + redA(r)] * B[redB(r) + colB(j)] )
+ *
+ * Each map is a 3-digit affine map: off(i) = q0*s0 + q1*s1 + q2*s2 with q0 = i / d1,
+ * q1 = (i % d1) / d2, q2 = i % d2 (element units).  gather_row / gather_red optionally
+ * replace q0 of rowA / redA by a lookup in a device int64 list (minibatch rows of the
+ * rollout buffer), which fuses the observation gather (storage.py:127) and -- with
+ * a_dtype = 1 -- the uint8 -> fp32 / 255 normalisation (model.py:190) into the load.
+ * epi: + bias, activation, ReLU/tanh-derivative masking, optional accumulate.
+ * With splits > 1 raw partial sums are written at C + s * split_stride for
+ * a2cb_reduce_splits to fold.  ones_row appends a logical all-ones row M to A whose
+ * outputs (column sums of B = bias gradients) go to C_ones[j * ones_stride].
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    int64_t d1, d2;
+    int64_t s0, s1, s2;
+} a2cb_affine3_t;
+
+typedef struct {
+    const void* A;
+    const float* B;
+    float* C;
+    float* C_ones;
+    const float* bias;
+    const float* mask;
+    const int64_t* gather_row;
+    const int64_t* gather_red;
+    int64_t M, N, K;
+    a2cb_affine3_t rowA, rowC, rowM;
+    a2cb_affine3_t redA, redB;
+    a2cb_affine3_t colB, colC, colM;
+    int32_t a_dtype;    /* 0 fp32, 1 uint8 / 255.0f, 2 fp32 / 255.0f */
+    int32_t ones_row;
+    int64_t ones_stride;
+    int32_t bias_mode;  /* 0 none, 1 bias[j], 2 bias[i] */
+    int32_t act;        /* 0 none, 1 relu, 2 tanh */
+    int32_t mask_mode;  /* 0 none, 1 *= (mask > 0), 2 *= (1 - mask^2) */
+    int32_t accumulate;
+    float alpha;
+    int32_t batch;      /* 1..4 problems sharing the maps, base offsets below */
+    int64_t batch_offA[4], batch_offB[4], batch_offC[4], batch_offM[4];
+    int32_t splits;
+    int32_t vecA;       /* 0 scalar, 1 four consecutive r contiguous+aligned, 2 four consecutive rows */
+    int64_t split_stride;
+    int32_t vecB;       /* 0 scalar, 1 four consecutive columns contiguous+aligned */
+    int32_t tile;       /* 0 auto, else column tile 32 / 64 / 128 */
+} a2cb_gemm_t;
+
+int a2cb_gemm(const a2cb_gemm_t* desc, a2cb_stream_t stream);
+/* dst[e] (+)= sum_{s < splits} src[s * stride + e],  e in [0, count) */
+int a2cb_reduce_splits(float* dst, const float* src, int64_t count, int64_t stride, int32_t splits,
+                       int32_t accumulate, a2cb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * (4) fused loss epilogue                a2c_ppo_acktr/algo/ppo.py:35-37,61-77,86-88
+ *                                         algo/a2c_acktr.py:48-51,55-64
+ *                                         distributions.py:18-44, model.py:76-77
+ * One thread per row: Categorical / DiagGaussian log-prob + entropy from the head outputs
+ * z[b] = (value, logits[A] | mean[A]); PPO clipped surrogate + (clipped) value loss, or the
+ * A2C / Fisher-sample losses; analytic gradient dz of
+ *     total = c_v * value_loss + action_loss - c_e * entropy
+ * and the three loss means (warp-shuffle + fixed-order block reduction, deterministic).
+ * Rollout fields are read through the minibatch index list idx (NULL = identity), which
+ * fuses the narrow-field gathers of storage.py:131-140.  inv_B = 1 / global minibatch size.
+ * ------------------------------------------------------------------------- */
+#define A2CB_MAX_ACTIONS 32
+typedef struct {
+    const float* z;
+    const float* logstd;
+    const int64_t* idx;
+    const void* actions;      /* int64 [rows, act_stride] (Categorical) | fp32 [rows, act_stride] */
+    const float* old_logp;
+    const float* old_value;
+    const float* returns;
+    const float* adv;
+    const float* noise;
+    float* dz;
+    float* dlogstd;
+    float* logp_out;
+    float* ent_out;
+    float* loss_out;          /* [3] value_loss, action_loss, dist_entropy of this minibatch */
+    float* loss_accum;        /* [3] running sums over minibatches */
+    float* scratch;           /* a2cb_loss_scratch_floats(B) floats, zeroed once by the caller */
+    int32_t B, A;
+    int32_t z_stride, dz_stride;
+    int32_t act_stride, dlogstd_stride;
+    int32_t dist;             /* 0 Categorical, 1 DiagGaussian */
+    int32_t mode;             /* 0 PPO, 1 A2C, 2 Fisher sample (ACKTR), 3 forward only,
+                                 4 VJP: old_value / old_logp hold dL/dvalue, dL/dlogp per row, noise[0] = dL/d(mean entropy) */
+    int32_t use_clipped_value_loss;
+    float clip, c_v, c_e;
+    float inv_B;
+    int32_t pad_;
+} a2cb_loss_t;
+
+int a2cb_loss_epilogue(const a2cb_loss_t* desc, a2cb_stream_t stream);
+int64_t a2cb_loss_scratch_floats(int32_t B);
+
+/* advantage statistics (ppo.py:35-37): moments[0..2] = (sum, sum of squares, count) of
+ * returns - value_preds over n rows, fp64 (all-reduce them across ranks when sharded);
+ * scratch: 2*128 doubles + 1 counter word, zeroed once.  a2cb_adv_normalize then writes
+ * adv = (x - mean) / (unbiased_std + 1e-5). */
+int a2cb_adv_moments(const float* returns, const float* value_preds, int64_t n, double* scratch,
+                     double* moments, a2cb_stream_t stream);
+int a2cb_adv_normalize(const float* returns, const float* value_preds, int64_t n, const double* moments,
+                       float* adv, a2cb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * clip_grad_norm_ + optimiser step over the flat parameter buffer
+ *     a2c_ppo_acktr/algo/ppo.py:79-84, algo/a2c_acktr.py:70-78, algo/kfac.py:139-142,241
+ * a2cb_grad_norm: norm_out[0] = ||g||_2, norm_out[1] = ||g||_2^2  (scratch: 148 doubles + counter).
+ * a2cb_optim_step: kind 0 Adam, 1 RMSprop (b2 = alpha), 2 SGD with momentum (b1 = momentum).
+ *   lr_eff = lr / (1 - b1^t) for Adam, lr otherwise; omb1/omb2 = 1-b1 / 1-b2 rounded from
+ *   double; bc2_sqrt = sqrt(1 - b2^t).  max_norm > 0 rescales g by min(1, max_norm/(norm+1e-6))
+ *   in place first (reading norm[0] on the device: no host sync).
+ * ------------------------------------------------------------------------- */
+int a2cb_grad_norm(const float* grads, int64_t n, double* scratch, float* norm_out, a2cb_stream_t stream);
+int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, float* state2, int64_t n,
+                    const float* norm, float lr_eff, float eps, float b1, float b2, float omb1, float omb2,
+                    float bc2_sqrt, float max_norm, int32_t first_step, a2cb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Op lists: one minibatch step of PPO.update / A2C_ACKTR.update (forward GEMMs, loss
+ * epilogue, backward GEMMs, split-K folds, clip + optimiser) is a short list of the
+ * descriptors above; a2cb_run_ops launches them back to back on `stream` from C, so the
+ * per-minibatch Python cost is one call (ppo.py:51-88 is ~200 Python-dispatched kernels).
+ * Ops flagged A2CB_OP_RUNTIME_IDX get their minibatch index list (gather_row / gather_red /
+ * loss idx) replaced by the `idx` argument, so one list serves every minibatch of an epoch.
+ * ------------------------------------------------------------------------- */
+#define A2CB_OP_GEMM 1
+#define A2CB_OP_REDUCE 2
+#define A2CB_OP_LOSS 3
+#define A2CB_OP_GRAD_NORM 4
+#define A2CB_OP_OPTIM 5
+#define A2CB_OP_FILL 6
+#define A2CB_OP_RUNTIME_IDX 1
+
+typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate; } a2cb_reduce_t;
+typedef struct { const float* grads; int64_t n; double* scratch; float* norm_out; } a2cb_grad_norm_t;
+typedef struct {
+    float* params; float* grads; float* state1; float* state2; int64_t n; const float* norm;
+    int32_t kind; int32_t first_step;
+    float lr_eff, eps, b1, b2, omb1, omb2, bc2_sqrt, max_norm;
+} a2cb_optim_t;
+typedef struct { void* dst; int64_t bytes; int32_t value; int32_t pad_; } a2cb_fill_t;
+typedef struct { int32_t kind; int32_t flags; const void* desc; } a2cb_op_t;
+
+int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

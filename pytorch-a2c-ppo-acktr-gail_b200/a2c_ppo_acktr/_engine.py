@@ -1,0 +1,636 @@
+"""Execution engine: turns a policy + batch shape into op lists for liba2cb.so and runs them.
+
+Host-side only (no tensor math): owns the activation / gradient arenas, resolves the
+symbolic plans of `_plans.py` into `a2cb_gemm_t` descriptors holding device pointers,
+and assembles the per-minibatch programs
+
+    forward GEMMs -> fused loss epilogue -> backward GEMMs -> split-K folds -> clip + optimiser
+
+that `a2cb_run_ops` launches from C in one call.  torch is used for device memory only.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _native
+from . import _plans as P
+
+c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+OP_GEMM, OP_REDUCE, OP_LOSS, OP_GRAD_NORM, OP_OPTIM, OP_FILL = 1, 2, 3, 4, 5, 6
+RUNTIME_IDX = 1
+SENTINEL = 1          # non-NULL placeholder for "use the runtime minibatch index list"
+
+
+class LossDesc(ctypes.Structure):
+    """Mirror of a2cb_loss_t."""
+    _fields_ = [
+        ("z", c_vp), ("logstd", c_vp), ("idx", c_vp), ("actions", c_vp), ("old_logp", c_vp),
+        ("old_value", c_vp), ("returns", c_vp), ("adv", c_vp), ("noise", c_vp), ("dz", c_vp),
+        ("dlogstd", c_vp), ("logp_out", c_vp), ("ent_out", c_vp), ("loss_out", c_vp), ("loss_accum", c_vp),
+        ("scratch", c_vp),
+        ("B", c_i32), ("A", c_i32), ("z_stride", c_i32), ("dz_stride", c_i32), ("act_stride", c_i32),
+        ("dlogstd_stride", c_i32), ("dist", c_i32), ("mode", c_i32), ("use_clipped_value_loss", c_i32),
+        ("clip", c_f32), ("c_v", c_f32), ("c_e", c_f32), ("inv_B", c_f32), ("pad_", c_i32),
+    ]
+
+
+class ReduceDesc(ctypes.Structure):
+    _fields_ = [("dst", c_vp), ("src", c_vp), ("count", c_i64), ("stride", c_i64), ("splits", c_i32),
+                ("accumulate", c_i32)]
+
+
+class GradNormDesc(ctypes.Structure):
+    _fields_ = [("grads", c_vp), ("n", c_i64), ("scratch", c_vp), ("norm_out", c_vp)]
+
+
+class OptimDesc(ctypes.Structure):
+    _fields_ = [("params", c_vp), ("grads", c_vp), ("state1", c_vp), ("state2", c_vp), ("n", c_i64),
+                ("norm", c_vp), ("kind", c_i32), ("first_step", c_i32),
+                ("lr_eff", c_f32), ("eps", c_f32), ("b1", c_f32), ("b2", c_f32), ("omb1", c_f32), ("omb2", c_f32),
+                ("bc2_sqrt", c_f32), ("max_norm", c_f32)]
+
+
+class FillDesc(ctypes.Structure):
+    _fields_ = [("dst", c_vp), ("bytes", c_i64), ("value", c_i32), ("pad_", c_i32)]
+
+
+class Op(ctypes.Structure):
+    _fields_ = [("kind", c_i32), ("flags", c_i32), ("desc", c_vp)]
+
+
+_native.register({
+    "a2cb_gemm": (c_i32, [ctypes.POINTER(P.GemmDesc), c_vp]),
+    "a2cb_reduce_splits": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp]),
+    "a2cb_loss_epilogue": (c_i32, [ctypes.POINTER(LossDesc), c_vp]),
+    "a2cb_loss_scratch_floats": (c_i64, [c_i32]),
+    "a2cb_adv_moments": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "a2cb_adv_normalize": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "a2cb_grad_norm": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "a2cb_optim_step": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp] + [c_f32] * 8 + [c_i32, c_vp]),
+    "a2cb_run_ops": (c_i32, [ctypes.POINTER(Op), c_i32, c_vp, c_vp]),
+})
+
+
+def _aff(t):
+    return P.Affine3(*t)
+
+
+class Arena(object):
+    """Named flat device buffers."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def bind(self, name, tensor):
+        self.bufs[name] = tensor
+
+    def ensure(self, name, numel, dtype=torch.float32):
+        t = self.bufs.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.zeros(max(int(numel), 1), dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t
+
+    def ptr(self, ref):
+        """(name, element offset) -> device address."""
+        if ref is None:
+            return None
+        name, off = ref
+        t = self.bufs[name]
+        assert 0 <= off <= t.numel(), (name, off, t.numel())
+        return t.data_ptr() + off * t.element_size()
+
+
+def resolve(plan, arena):
+    """Plan (symbolic) -> a2cb_gemm_t with device pointers."""
+    g = P.GemmDesc()
+    g.A, g.B, g.C = arena.ptr(plan.A), arena.ptr(plan.B), arena.ptr(plan.C)
+    g.C_ones = arena.ptr(plan.ones)
+    g.bias = arena.ptr(plan.bias)
+    g.mask = arena.ptr(plan.mask)
+    g.gather_row = SENTINEL if plan.gather_row else None
+    g.gather_red = SENTINEL if plan.gather_red else None
+    g.M, g.N, g.K = plan.M, plan.N, plan.K
+    g.rowA, g.rowC, g.rowM = _aff(plan.rowA), _aff(plan.rowC), _aff(plan.rowM)
+    g.redA, g.redB = _aff(plan.redA), _aff(plan.redB)
+    g.colB, g.colC, g.colM = _aff(plan.colB), _aff(plan.colC), _aff(plan.colM)
+    g.a_dtype = int(plan.a_u8)
+    g.ones_row = 1 if plan.ones is not None else 0
+    g.ones_stride = plan.ones_stride
+    g.bias_mode, g.act, g.mask_mode, g.accumulate = plan.bias_mode, plan.act, plan.mask_mode, plan.accumulate
+    g.alpha = plan.alpha
+    g.batch = plan.batch
+    for z in range(4):
+        g.batch_offA[z], g.batch_offB[z] = plan.batch_offA[z], plan.batch_offB[z]
+        g.batch_offC[z], g.batch_offM[z] = plan.batch_offC[z], plan.batch_offM[z]
+    g.splits, g.split_stride = plan.splits, plan.split_stride
+    g.vecA, g.vecB, g.tile = plan.vecA, plan.vecB, plan.tile
+    return g
+
+
+def choose_splits(rows, cols, red):
+    """Split the reduction so that a weight-gradient GEMM with a tiny output fills 148 SMs."""
+    tiles = ((rows + 127) // 128) * ((cols + 63) // 64 if cols > 32 else 1)
+    ktiles = (red + 15) // 16
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return int(max(1, min(want, ktiles // 8 if ktiles >= 16 else 1, 256)))
+
+
+class Program(object):
+    """An op list plus everything it must keep alive."""
+
+    def __init__(self, device):
+        self.device = device
+        self.entries = []          # (kind, flags, ctypes struct)
+        self.flops = 0
+        self._arr = None
+
+    def add(self, kind, desc, flags=0):
+        self.entries.append((kind, flags, desc))
+        self._arr = None
+        return desc
+
+    def add_plan(self, plan, arena):
+        flags = RUNTIME_IDX if (plan.gather_row or plan.gather_red) else 0
+        self.add(OP_GEMM, resolve(plan, arena), flags)
+        self.flops += plan.flops
+        if plan.splits > 1:
+            dst = plan.split_dst
+            r = ReduceDesc(arena.ptr((dst[0], dst[1])), arena.ptr(plan.C), dst[2], plan.split_stride, plan.splits,
+                           plan.accumulate)
+            self.add(OP_REDUCE, r)
+
+    def extend(self, other):
+        self.entries.extend(other.entries)
+        self.flops += other.flops
+        self._arr = None
+
+    def finalize(self):
+        arr = (Op * len(self.entries))()
+        for i, (kind, flags, desc) in enumerate(self.entries):
+            arr[i].kind, arr[i].flags = kind, flags
+            arr[i].desc = ctypes.addressof(desc)
+        self._arr = arr
+        return self
+
+    def __len__(self):
+        return len(self.entries)
+
+    def n_launches(self):
+        return len(self.entries)
+
+    def run(self, idx=None):
+        if self._arr is None:
+            self.finalize()
+        idx_p = _native.dptr(idx, torch.int64, "idx") if idx is not None else c_vp(0)
+        with torch.cuda.device(self.device):
+            rc = _native.lib().a2cb_run_ops(self._arr, len(self.entries), idx_p, _native.stream_ptr(self.device))
+        _native.check(rc, "a2cb_run_ops")
+
+
+# ---------------------------------------------------------------------------
+# parameter layout
+# ---------------------------------------------------------------------------
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class ParamLayout(object):
+    """Flat fp32 layout of all parameters: each layer is [weight | bias] (so a split-K weight
+    gradient and its bias gradient are one contiguous span), segment starts 16 B aligned.
+    `entries`: reference state_dict key -> (offset, shape)."""
+
+    def __init__(self, spec):
+        self.spec = spec
+        self.entries = {}
+        self.layers = {}
+        off = 0
+
+        def layer(name, wkey, wshape, bkey, bshape):
+            nonlocal off
+            off = _pad4(off)
+            wn = int(math.prod(wshape))
+            self.entries[wkey] = (off, tuple(wshape))
+            self.entries[bkey] = (off + wn, tuple(bshape))
+            self.layers[name] = (off, off + wn)
+            off += wn + int(math.prod(bshape))
+
+        H, A = spec.hidden, spec.num_actions
+        if spec.cnn:
+            C = spec.obs_shape[0]
+            layer("conv1", "base.main.0.weight", (32, C, 8, 8), "base.main.0.bias", (32,))
+            layer("conv2", "base.main.2.weight", (64, 32, 4, 4), "base.main.2.bias", (64,))
+            layer("conv3", "base.main.4.weight", (32, 64, 3, 3), "base.main.4.bias", (32,))
+            layer("fc", "base.main.7.weight", (H, 32 * 7 * 7), "base.main.7.bias", (H,))
+            gru_in = H
+        else:
+            gru_in = spec.obs_shape[0]
+            d_in = H if spec.recurrent else spec.obs_shape[0]
+            layer("actor0", "base.actor.0.weight", (H, d_in), "base.actor.0.bias", (H,))
+            layer("actor2", "base.actor.2.weight", (H, H), "base.actor.2.bias", (H,))
+            layer("critic0", "base.critic.0.weight", (H, d_in), "base.critic.0.bias", (H,))
+            layer("critic2", "base.critic.2.weight", (H, H), "base.critic.2.bias", (H,))
+        if spec.recurrent:
+            off = _pad4(off)
+            self.layers["gru"] = (off, off + 3 * H * gru_in)
+            self.entries["base.gru.weight_ih_l0"] = (off, (3 * H, gru_in)); off += 3 * H * gru_in
+            self.entries["base.gru.weight_hh_l0"] = (off, (3 * H, H)); off += 3 * H * H
+            self.entries["base.gru.bias_ih_l0"] = (off, (3 * H,)); off += 3 * H
+            self.entries["base.gru.bias_hh_l0"] = (off, (3 * H,)); off += 3 * H
+        # heads: [critic_linear.weight (1,H) | head weight (A,H) | critic_linear.bias | head bias]
+        off = _pad4(off)
+        hw = "dist.linear" if spec.action_kind == "discrete" else "dist.fc_mean"
+        self.entries["base.critic_linear.weight"] = (off, (1, H))
+        self.entries[hw + ".weight"] = (off + H, (A, H))
+        self.entries["base.critic_linear.bias"] = (off + (1 + A) * H, (1,))
+        self.entries[hw + ".bias"] = (off + (1 + A) * H + 1, (A,))
+        self.layers["heads"] = (off, off + (1 + A) * H)
+        off += (1 + A) * H + 1 + A
+        if spec.action_kind == "box":
+            off = _pad4(off)
+            self.entries["dist.logstd._bias"] = (off, (A, 1))
+            self.layers["logstd"] = (off, off)
+            off += A
+        self.total = _pad4(off)
+
+
+# ---------------------------------------------------------------------------
+# network plans
+# ---------------------------------------------------------------------------
+class NetBuilder(object):
+    """Builds forward / backward plan lists for one policy spec and one batch size."""
+
+    def __init__(self, spec, layout, B, obs_buf, obs_code, gather, tag):
+        self.spec, self.L, self.B = spec, layout, B
+        self.obs = obs_buf          # arena name of the observation source
+        self.obs_code = obs_code    # a_dtype of the first layer: 0 raw fp32, 1 uint8/255, 2 fp32/255
+        self.gather = gather
+        self.t = tag                # arena name prefix for this batch size's buffers
+        self.sizes = {}             # arena buffer name -> numel (fp32)
+        H, A = spec.hidden, spec.num_actions
+        self.zs = 1 + A
+        if spec.cnn:
+            C = spec.obs_shape[0]
+            assert spec.obs_shape[1:] == (84, 84), "CNNBase geometry is the reference's 84x84 (model.py:176-180)"
+            self.c1 = P.Conv("conv1", C, 84, 84, 8, 4, 32, in_layout="nchw", needs_dgrad=False)
+            self.c2 = P.Conv("conv2", 32, 20, 20, 4, 2, 64)
+            self.c3 = P.Conv("conv3", 64, 9, 9, 3, 1, 32)
+            self.fc = P.Linear("fc", 1568, H, in_perm=P.aff(7 * 32, 32, 7, 1, 49))
+        self.heads = P.Linear("heads", H, 1 + A)
+
+    def n(self, name):
+        return self.t + name
+
+    def buf(self, name, numel):
+        self.sizes[self.n(name)] = int(numel)
+        return (self.n(name), 0)
+
+    def wb(self, layer):
+        w, b = self.L.layers[layer]
+        return ("P", w), ("P", b)
+
+    def gwb(self, layer):
+        w, b = self.L.layers[layer]
+        return ("G", w), ("G", b)
+
+    # ---- CNN ----
+    def cnn_forward(self):
+        B, s = self.B, self.spec
+        c1, c2, c3 = self.c1, self.c2, self.c3
+        a1, a2, a3 = self.buf("a1", B * c1.out_row), self.buf("a2", B * c2.out_row), self.buf("a3", B * c3.out_row)
+        h, z = self.buf("h", B * s.hidden), self.buf("z", B * self.zs)
+        plans = [
+            P.conv_forward(c1, B, (self.obs, 0), *self.wb("conv1"), a1, a_u8=self.obs_code, gather=self.gather),
+            P.conv_forward(c2, B, a1, *self.wb("conv2"), a2),
+            P.conv_forward(c3, B, a2, *self.wb("conv3"), a3),
+            P.linear_forward(self.fc, B, a3, *self.wb("fc"), h, act=P.ACT_RELU),
+        ]
+        return plans, h
+
+    def cnn_backward(self, feat_grad):
+        """feat_grad: gradient w.r.t. the trunk output h, already masked by relu'."""
+        B = self.B
+        c1, c2, c3 = self.c1, self.c2, self.c3
+        a1, a2, a3 = (self.n("a1"), 0), (self.n("a2"), 0), (self.n("a3"), 0)
+        g3, g2, g1 = self.buf("g3", B * c3.gout_row), self.buf("g2", B * c2.gout_row), self.buf("g1", B * c1.gout_row)
+        plans = [
+            P.linear_wgrad(self.fc, B, a3, feat_grad, *self.gwb("fc")),
+            P.linear_dgrad(self.fc, B, feat_grad, ("P", self.L.layers["fc"][0]), g3, mask=a3, mask_mode=1,
+                           row_out=P.plain(c3.gout_row), col_out=P.aff(7 * 32, 32, c3.pw * 32, 32, 1),
+                           gx_base=c3.gout_base, mask_row=P.plain(1568), mask_col=P.plain(1)),
+        ]
+        for cv, src, g, gprev, prev, a_prev in ((c3, a2, g3, g2, c2, a2), (c2, a1, g2, g1, c1, a1)):
+            sp = choose_splits(cv.K + 1, cv.cout, B * cv.oh * cv.ow)
+            part = self.buf("part_" + cv.name, sp * (cv.cout * cv.K + cv.cout)) if sp > 1 else None
+            plans.append(P.conv_wgrad(cv, B, src, g, *self.gwb(cv.name), splits=sp, partial=part))
+            plans.append(P.conv_dgrad(cv, B, g, ("P", self.L.layers[cv.name][0]), gprev,
+                                      (prev.gout_row, prev.pw, prev.gout_base), mask=a_prev))
+        sp = choose_splits(c1.K + 1, c1.cout, B * c1.oh * c1.ow)
+        part = self.buf("part_conv1", sp * (c1.cout * c1.K + c1.cout)) if sp > 1 else None
+        plans.append(P.conv_wgrad(c1, B, (self.obs, 0), g1, *self.gwb("conv1"), a_u8=self.obs_code,
+                                  gather=self.gather, splits=sp, partial=part))
+        return plans
+
+    # ---- MLP ----
+    def mlp_forward(self):
+        B, s = self.B, self.spec
+        H, d = s.hidden, s.obs_shape[0]
+        x = (self.obs, 0)
+        ha1, ha2 = self.buf("ha1", B * H), self.buf("ha2", B * H)
+        hc1, hc2 = self.buf("hc1", B * H), self.buf("hc2", B * H)
+        z = self.buf("z", B * self.zs)
+        l0a, l2a = P.Linear("actor0", d, H), P.Linear("actor2", H, H)
+        l0c, l2c = P.Linear("critic0", d, H), P.Linear("critic2", H, H)
+        self.mlp_layers = (l0a, l2a, l0c, l2c)
+        p0a = P.linear_forward(l0a, B, x, *self.wb("actor0"), ha1, act=P.ACT_TANH)
+        p0c = P.linear_forward(l0c, B, x, *self.wb("critic0"), hc1, act=P.ACT_TANH)
+        for p in (p0a, p0c):
+            p.gather_row = self.gather
+            p.vecA = 1 if d % 4 == 0 else 0
+        plans = [p0c, P.linear_forward(l2c, B, hc1, *self.wb("critic2"), hc2, act=P.ACT_TANH),
+                 p0a, P.linear_forward(l2a, B, ha1, *self.wb("actor2"), ha2, act=P.ACT_TANH)]
+        return plans, (hc2, ha2)
+
+    def mlp_heads_forward(self, hc2, ha2):
+        B, H, A = self.B, self.spec.hidden, self.spec.num_actions
+        w0, b0 = self.L.layers["heads"]
+        z = (self.n("z"), 0)
+        crit = P.Linear("critic_linear", H, 1)
+        mean = P.Linear("head", H, A)
+        return [P.linear_forward(crit, B, hc2, ("P", w0), ("P", b0), z, y_stride=self.zs),
+                P.linear_forward(mean, B, ha2, ("P", w0 + H), ("P", b0 + 1), (z[0], 1), y_stride=self.zs)]
+
+    def mlp_backward(self):
+        B, H, A, d = self.B, self.spec.hidden, self.spec.num_actions, self.spec.obs_shape[0]
+        l0a, l2a, l0c, l2c = self.mlp_layers
+        w0, b0 = self.L.layers["heads"]
+        dz = (self.n("dz"), 0)
+        ha1, ha2, hc1, hc2 = [(self.n(k), 0) for k in ("ha1", "ha2", "hc1", "hc2")]
+        gc2, gc1 = self.buf("gc2", B * H), self.buf("gc1", B * H)
+        ga2, ga1 = self.buf("ga2", B * H), self.buf("ga1", B * H)
+        crit = P.Linear("critic_linear", H, 1)
+        mean = P.Linear("head", H, A)
+        x = (self.obs, 0)
+        plans = [
+            P.linear_wgrad(crit, B, hc2, dz, ("G", w0), ("G", b0), gy_stride=self.zs),
+            P.linear_dgrad(crit, B, dz, ("P", w0), gc2, mask=hc2, mask_mode=2, gy_stride=self.zs),
+            P.linear_wgrad(l2c, B, hc1, gc2, *self.gwb("critic2")),
+            P.linear_dgrad(l2c, B, gc2, ("P", self.L.layers["critic2"][0]), gc1, mask=hc1, mask_mode=2),
+            P.linear_wgrad(l0c, B, x, gc1, *self.gwb("critic0")),
+            P.linear_wgrad(mean, B, ha2, (dz[0], 1), ("G", w0 + H), ("G", b0 + 1), gy_stride=self.zs),
+            P.linear_dgrad(mean, B, (dz[0], 1), ("P", w0 + H), ga2, mask=ha2, mask_mode=2, gy_stride=self.zs),
+            P.linear_wgrad(l2a, B, ha1, ga2, *self.gwb("actor2")),
+            P.linear_dgrad(l2a, B, ga2, ("P", self.L.layers["actor2"][0]), ga1, mask=ha1, mask_mode=2),
+            P.linear_wgrad(l0a, B, x, ga1, *self.gwb("actor0")),
+        ]
+        for p in (plans[4], plans[9]):
+            p.gather_red = self.gather
+            p.vecA = 0          # gathered rows: row-contiguity of x across the batch index does not apply
+        return plans
+
+    # ---- heads (CNN: one [1+A, H] matrix on the shared feature) ----
+    def cnn_heads_forward(self, h):
+        w, b = self.wb("heads")
+        return [P.linear_forward(self.heads, self.B, h, w, b, (self.n("z"), 0))]
+
+    def cnn_heads_backward(self, h):
+        B, H = self.B, self.spec.hidden
+        dz = self.buf("dz", B * self.zs)
+        gh = self.buf("gh", B * H)
+        gw, gb = self.gwb("heads")
+        return [P.linear_wgrad(self.heads, B, h, dz, gw, gb),
+                P.linear_dgrad(self.heads, B, dz, ("P", self.L.layers["heads"][0]), gh, mask=h, mask_mode=1)], gh
+
+    def forward_plans(self):
+        if self.spec.cnn:
+            plans, h = self.cnn_forward()
+            return plans + self.cnn_heads_forward(h)
+        plans, (hc2, ha2) = self.mlp_forward()
+        return plans + self.mlp_heads_forward(hc2, ha2)
+
+    def backward_plans(self):
+        if self.spec.cnn:
+            hp, gh = self.cnn_heads_backward((self.n("h"), 0))
+            return hp + self.cnn_backward(gh)
+        self.buf("dz", self.B * self.zs)
+        return self.mlp_backward()
+
+
+# ---------------------------------------------------------------------------
+# runtime: caches programs per batch shape and runs them
+# ---------------------------------------------------------------------------
+class PolicyRuntime(object):
+    MAX_CACHE = 96
+
+    def __init__(self, spec, layout, flat, flat_grad):
+        self.spec, self.L = spec, layout
+        self.dev = flat.device
+        if self.dev.type != "cuda":
+            raise _native.NativeError("the policy lives on %s: move it to a CUDA device "
+                                      "(the update path has no CPU fallback)" % self.dev)
+        _native.lib()
+        self.arena = Arena(self.dev)
+        self.arena.bind("P", flat)
+        self.arena.bind("G", flat_grad)
+        self.cache = {}
+        self.forward_token = 0
+        self.keep = {}
+        self.zs = 1 + spec.num_actions
+
+    # -- helpers ------------------------------------------------------------
+    def obs_code(self, obs):
+        if obs.dtype == torch.uint8:
+            if not self.spec.cnn:
+                raise _native.NativeError("uint8 observations are only meaningful for the CNN trunk")
+            return 1
+        if obs.dtype != torch.float32:
+            raise _native.NativeError("observations must be float32 or uint8 (got %s)" % obs.dtype)
+        return 2 if self.spec.cnn else 0
+
+    def _remember(self, key, value):
+        if len(self.cache) >= self.MAX_CACHE:
+            self.cache.pop(next(iter(self.cache)))
+        self.cache[key] = value
+        return value
+
+    def _alloc(self, builder):
+        for name, numel in builder.sizes.items():
+            self.arena.ensure(name, numel)
+
+    def loss_scratch(self, B):
+        n = int(_native.lib().a2cb_loss_scratch_floats(B))
+        return self.arena.ensure("loss_scratch_%d" % B, n)
+
+    def logstd_ref(self):
+        if self.spec.action_kind != "box":
+            return None
+        return ("P", self.L.entries["dist.logstd._bias"][0])
+
+    # -- forward only -------------------------------------------------------
+    def forward(self, obs, hxs, masks, keep_for_backward=False):
+        if self.spec.recurrent:
+            raise _native.NativeError("recurrent (GRU) policies are not built yet in this round")
+        if not obs.is_cuda:
+            raise _native.NativeError("observations must be CUDA tensors; there is no CPU fallback")
+        obs = obs.contiguous()
+        B = obs.shape[0]
+        if tuple(obs.shape[1:]) != self.spec.obs_shape:
+            raise ValueError("expected observations of shape [B, %s], got %s" % (self.spec.obs_shape, tuple(obs.shape)))
+        code = self.obs_code(obs)
+        key = ("fwd", B, obs.data_ptr(), code)
+        ent = self.cache.get(key)
+        self.arena.bind("obs_in", obs.view(-1))
+        if ent is None:
+            nb = NetBuilder(self.spec, self.L, B, "obs_in", code, False, "b%d_" % B)
+            plans = nb.forward_plans()
+            self._alloc(nb)
+            prog = Program(self.dev)
+            for p in plans:
+                prog.add_plan(p, self.arena)
+            ent = self._remember(key, (prog.finalize(), nb))
+        prog, nb = ent
+        self.keep["obs"] = obs
+        prog.run()
+        self.forward_token += 1
+        z = self.arena.bufs["b%d_z" % B][:B * self.zs].view(B, self.zs)
+        return {"z": z, "hxs": hxs, "builder": nb}
+
+    def _loss_desc(self, B, tag, mode, actions, **kw):
+        s = self.spec
+        d = LossDesc()
+        d.z = self.arena.ptr((tag + "z", 0))
+        d.logstd = self.arena.ptr(self.logstd_ref())
+        d.actions = actions.data_ptr()
+        d.act_stride = actions.shape[-1]
+        d.B, d.A = B, s.num_actions
+        d.z_stride = d.dz_stride = self.zs
+        d.dlogstd_stride = 1
+        d.dist = 0 if s.action_kind == "discrete" else 1
+        d.mode = mode
+        d.inv_B = 1.0 / B
+        d.scratch = self.loss_scratch(B).data_ptr()
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+
+    def _check_actions(self, B, action):
+        s = self.spec
+        want = torch.int64 if s.action_kind == "discrete" else torch.float32
+        if not action.is_cuda:
+            raise _native.NativeError("actions must be CUDA tensors")
+        a = action.to(want).contiguous().view(B, -1)
+        if s.action_kind == "box" and a.shape[1] != s.num_actions:
+            raise ValueError("action dimension mismatch")
+        return a
+
+    def head_stats(self, B, action):
+        """log-prob [B] and mean entropy (0-dim) of `action` under the last forward of batch B."""
+        a = self._check_actions(B, action)
+        out = self.arena.ensure("b%d_stats" % B, 2 * B + 4)
+        d = self._loss_desc(B, "b%d_" % B, 3, a, logp_out=out.data_ptr(), loss_out=out.data_ptr() + 8 * B)
+        self.keep["stats_actions"] = a
+        with torch.cuda.device(self.dev):
+            rc = _native.lib().a2cb_loss_epilogue(ctypes.byref(d), _native.stream_ptr(self.dev))
+        _native.check(rc, "a2cb_loss_epilogue")
+        return {"logp": out[:B], "entropy": out[2 * B + 2]}
+
+    # -- VJP for the autograd bridge -----------------------------------------
+    def backward_vjp(self, B, action, g_value, g_logp, g_ent):
+        a = self._check_actions(B, action)
+        tag = "b%d_" % B
+        obs = self.keep["obs"]
+        code = self.obs_code(obs)
+        key = ("bwd", B, obs.data_ptr(), code)
+        ent = self.cache.get(key)
+        self.arena.bind("obs_in", obs.view(-1))
+        if ent is None:
+            nb = NetBuilder(self.spec, self.L, B, "obs_in", code, False, tag)
+            nb.forward_plans()
+            plans = nb.backward_plans()
+            self._alloc(nb)
+            prog = Program(self.dev)
+            for p in plans:
+                prog.add_plan(p, self.arena)
+            ent = self._remember(key, prog.finalize())
+        prog = ent
+        d = self._loss_desc(B, tag, 4, a, old_value=g_value.data_ptr(), old_logp=g_logp.data_ptr(),
+                            noise=g_ent.data_ptr(), dz=self.arena.ptr((tag + "dz", 0)))
+        if self.spec.action_kind == "box":
+            d.dlogstd = self.arena.ptr(("G", self.L.entries["dist.logstd._bias"][0]))
+        with torch.cuda.device(self.dev):
+            rc = _native.lib().a2cb_loss_epilogue(ctypes.byref(d), _native.stream_ptr(self.dev))
+        _native.check(rc, "a2cb_loss_epilogue")
+        prog.run()
+        return self.arena.bufs["G"]
+
+    # -- fused training step --------------------------------------------------
+    def train_program(self, storage, mbs, mode, hyper, adv=None, noise=None, loss_accum=None, use_idx=True,
+                      with_backward=True):
+        """Op list of one minibatch step reading rows of `storage` through the runtime index list:
+        forward -> loss epilogue (mode) -> backward.  Optimiser ops are appended by the caller."""
+        s = self.spec
+        T, N = storage.rewards.shape[0], storage.rewards.shape[1]
+        obs_flat = storage.obs[:-1].view(T * N, *storage.obs.shape[2:])
+        code = self.obs_code(obs_flat)
+        self.arena.bind("obs_st", obs_flat.view(-1))
+        tag = "t%d_" % mbs
+        nb = NetBuilder(s, self.L, mbs, "obs_st", code, use_idx, tag)
+        fwd = nb.forward_plans()
+        bwd = nb.backward_plans() if with_backward else []
+        if not with_backward:
+            nb.buf("dz", mbs * self.zs)
+        self._alloc(nb)
+        prog = Program(self.dev)
+        for p in fwd:
+            prog.add_plan(p, self.arena)
+        acts = storage.actions.view(T * N, -1)
+        lo = self.arena.ensure(tag + "loss_out", 4)
+        d = self._loss_desc(mbs, tag, mode, acts,
+                            old_logp=storage.action_log_probs.data_ptr(),
+                            old_value=storage.value_preds.data_ptr(),
+                            returns=storage.returns.data_ptr(),
+                            dz=self.arena.ptr((tag + "dz", 0)),
+                            loss_out=lo.data_ptr(),
+                            clip=float(hyper.get("clip_param", 0.0)), c_v=float(hyper["value_loss_coef"]),
+                            c_e=float(hyper["entropy_coef"]),
+                            use_clipped_value_loss=int(bool(hyper.get("use_clipped_value_loss", True))))
+        d.idx = SENTINEL if use_idx else None
+        if adv is not None:
+            d.adv = adv.data_ptr()
+        if noise is not None:
+            d.noise = noise.data_ptr()
+        if loss_accum is not None:
+            d.loss_accum = loss_accum.data_ptr()
+        if "inv_B" in hyper:
+            d.inv_B = float(hyper["inv_B"])
+        if s.action_kind == "box":
+            d.dlogstd = self.arena.ptr(("G", self.L.entries["dist.logstd._bias"][0]))
+        prog.add(OP_LOSS, d, RUNTIME_IDX if use_idx else 0)
+        for p in bwd:
+            prog.add_plan(p, self.arena)
+        prog.loss_desc = d
+        prog.loss_out = lo
+        prog.builder = nb
+        return prog
+
+    def add_optimizer_ops(self, prog, kind, state1, state2, max_norm):
+        n = self.L.total
+        scratch = self.arena.ensure("norm_scratch", 2 * (148 + 2), torch.float64)
+        norm = self.arena.ensure("grad_norm", 4)
+        clip = max_norm is not None and max_norm > 0
+        if clip:
+            prog.add(OP_GRAD_NORM, GradNormDesc(self.arena.bufs["G"].data_ptr(), n, scratch.data_ptr(), norm.data_ptr()))
+        o = OptimDesc()
+        o.params, o.grads = self.arena.bufs["P"].data_ptr(), self.arena.bufs["G"].data_ptr()
+        o.state1 = state1.data_ptr()
+        o.state2 = state2.data_ptr() if state2 is not None else None
+        o.n = n
+        o.norm = norm.data_ptr()
+        o.kind = kind
+        o.max_norm = float(max_norm) if clip else 0.0
+        prog.add(OP_OPTIM, o)
+        prog.optim_desc = o
+        return o

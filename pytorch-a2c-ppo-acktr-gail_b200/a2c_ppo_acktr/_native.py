@@ -36,6 +36,24 @@ _SIGNATURES = {
 }
 
 _lib = None
+_applied = set()
+
+
+def register(signatures):
+    """Adds ctypes signatures (used by _engine for the descriptor-taking entry points)."""
+    _SIGNATURES.update(signatures)
+    if _lib is not None:
+        _apply_signatures(_lib)
+
+
+def _apply_signatures(l):
+    for name, (res, args) in _SIGNATURES.items():
+        if name in _applied:
+            continue
+        fn = getattr(l, name)
+        fn.restype = res
+        fn.argtypes = args
+        _applied.add(name)
 
 
 def lib():
@@ -47,10 +65,7 @@ def lib():
                 "liba2cb.so not found at %s -- build it with `python __graft_entry__.py` or "
                 "`python pytorch-a2c-ppo-acktr-gail_b200/build.py`; there is no CPU fallback" % LIB_PATH)
         l = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in _SIGNATURES.items():
-            fn = getattr(l, name)
-            fn.restype = res
-            fn.argtypes = args
+        _apply_signatures(l)
         _lib = l
     return _lib
 

@@ -2,6 +2,8 @@
 #include "../../include/a2cb.h"
 #include "common.cuh"
 #include "decls.cuh"
+#include "gemm.cuh"
+#include "loss.cuh"
 
 #include <atomic>
 #include <stdarg.h>
@@ -58,6 +60,101 @@ int a2cb_gather_rows(const a2cb_gather_field_t* fields, int32_t n_fields, const 
     static_assert(sizeof(a2cb_gather_field_t) == sizeof(GatherField), "layout");
     return gather_rows(reinterpret_cast<const GatherField*>(fields), n_fields, idx, (long)n_out_rows, mode,
                        (long)E, (long)N, (cudaStream_t)stream);
+}
+
+int a2cb_gemm(const a2cb_gemm_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc, "gemm: null descriptor");
+    static_assert(sizeof(a2cb_gemm_t) == sizeof(GemmDesc), "a2cb_gemm_t and GemmDesc must share a layout");
+    return gemm(*reinterpret_cast<const GemmDesc*>(desc), (cudaStream_t)stream);
+}
+
+int a2cb_reduce_splits(float* dst, const float* src, int64_t count, int64_t stride, int32_t splits,
+                       int32_t accumulate, a2cb_stream_t stream) {
+    A2CB_REQUIRE(dst && src && count >= 0 && splits >= 1, "reduce_splits: bad argument");
+    return reduce_splits(dst, src, (long)count, (long)stride, splits, accumulate, (cudaStream_t)stream);
+}
+
+int a2cb_loss_epilogue(const a2cb_loss_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc, "loss: null descriptor");
+    static_assert(sizeof(a2cb_loss_t) == sizeof(LossDesc), "a2cb_loss_t and LossDesc must share a layout");
+    static_assert(A2CB_MAX_ACTIONS == kMaxActions, "max actions");
+    return loss_epilogue(*reinterpret_cast<const LossDesc*>(desc), (cudaStream_t)stream);
+}
+int64_t a2cb_loss_scratch_floats(int32_t B) { return loss_scratch_floats(B); }
+
+int a2cb_adv_moments(const float* returns, const float* value_preds, int64_t n, double* scratch,
+                     double* moments, a2cb_stream_t stream) {
+    return adv_moments(returns, value_preds, (long)n, scratch, moments, (cudaStream_t)stream);
+}
+int a2cb_adv_normalize(const float* returns, const float* value_preds, int64_t n, const double* moments,
+                       float* adv, a2cb_stream_t stream) {
+    return adv_normalize(returns, value_preds, (long)n, moments, adv, (cudaStream_t)stream);
+}
+
+int a2cb_grad_norm(const float* grads, int64_t n, double* scratch, float* norm_out, a2cb_stream_t stream) {
+    return grad_norm(grads, (long)n, scratch, norm_out, (cudaStream_t)stream);
+}
+int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, float* state2, int64_t n,
+                    const float* norm, float lr_eff, float eps, float b1, float b2, float omb1, float omb2,
+                    float bc2_sqrt, float max_norm, int32_t first_step, a2cb_stream_t stream) {
+    return optim_step(kind, params, grads, state1, state2, (long)n, norm, lr_eff, eps, b1, b2, omb1, omb2,
+                      bc2_sqrt, max_norm, first_step, (cudaStream_t)stream);
+}
+
+int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream) {
+    A2CB_REQUIRE(n_ops >= 0 && (n_ops == 0 || ops), "run_ops: bad op list");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n_ops; ++i) {
+        const a2cb_op_t& op = ops[i];
+        const bool rt = (op.flags & A2CB_OP_RUNTIME_IDX) != 0;
+        A2CB_REQUIRE(op.desc, "run_ops: op %d has no descriptor", i);
+        A2CB_REQUIRE(!rt || idx, "run_ops: op %d wants a runtime index list but none was given", i);
+        int rc = A2CB_OK;
+        switch (op.kind) {
+            case A2CB_OP_GEMM: {
+                GemmDesc g = *reinterpret_cast<const GemmDesc*>(op.desc);
+                if (rt) {
+                    if (g.gather_row) g.gather_row = idx;
+                    if (g.gather_red) g.gather_red = idx;
+                }
+                rc = gemm(g, st);
+                break;
+            }
+            case A2CB_OP_REDUCE: {
+                const a2cb_reduce_t& r = *reinterpret_cast<const a2cb_reduce_t*>(op.desc);
+                rc = reduce_splits(r.dst, r.src, (long)r.count, (long)r.stride, r.splits, r.accumulate, st);
+                break;
+            }
+            case A2CB_OP_LOSS: {
+                LossDesc d = *reinterpret_cast<const LossDesc*>(op.desc);
+                if (rt) d.idx = idx;
+                rc = loss_epilogue(d, st);
+                break;
+            }
+            case A2CB_OP_GRAD_NORM: {
+                const a2cb_grad_norm_t& n = *reinterpret_cast<const a2cb_grad_norm_t*>(op.desc);
+                rc = grad_norm(n.grads, (long)n.n, n.scratch, n.norm_out, st);
+                break;
+            }
+            case A2CB_OP_OPTIM: {
+                const a2cb_optim_t& o = *reinterpret_cast<const a2cb_optim_t*>(op.desc);
+                rc = optim_step(o.kind, o.params, o.grads, o.state1, o.state2, (long)o.n, o.norm, o.lr_eff, o.eps,
+                                o.b1, o.b2, o.omb1, o.omb2, o.bc2_sqrt, o.max_norm, o.first_step, st);
+                break;
+            }
+            case A2CB_OP_FILL: {
+                const a2cb_fill_t& f = *reinterpret_cast<const a2cb_fill_t*>(op.desc);
+                cudaError_t e = cudaMemsetAsync(f.dst, f.value, (size_t)f.bytes, st);
+                if (e != cudaSuccess) { set_error("run_ops: memset: %s", cudaGetErrorString(e)); rc = A2CB_ERR_CUDA; }
+                break;
+            }
+            default:
+                set_error("run_ops: unknown op kind %d at %d", op.kind, i);
+                return A2CB_ERR_INVALID;
+        }
+        if (rc != A2CB_OK) return rc;
+    }
+    return A2CB_OK;
 }
 
 }  // extern "C"

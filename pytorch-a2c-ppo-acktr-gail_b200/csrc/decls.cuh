@@ -15,4 +15,25 @@ struct GatherField { const void* src; void* dst; long row_bytes; };
 int gather_rows(const GatherField* fields, int n_fields, const int64_t* idx, long n_rows, int mode,
                 long E, long N, cudaStream_t st);
 
+// gemm.cu
+struct GemmDesc;
+int gemm(const GemmDesc& g, cudaStream_t st);
+int reduce_splits(float* dst, const float* src, long count, long stride, int splits, int accumulate,
+                  cudaStream_t st);
+
+// loss.cu
+struct LossDesc;
+int loss_epilogue(const LossDesc& d, cudaStream_t st);
+long loss_scratch_floats(int B);
+int adv_moments(const float* returns, const float* values, long n, double* scratch, double* moments,
+                cudaStream_t st);
+int adv_normalize(const float* returns, const float* values, long n, const double* moments, float* adv,
+                  cudaStream_t st);
+
+// optim.cu
+int grad_norm(const float* g, long n, double* scratch, float* norm_out, cudaStream_t st);
+int optim_step(int kind, float* p, float* g, float* s1, float* s2, long n, const float* norm,
+               float lr_eff, float eps, float b1, float b2, float omb1, float omb2, float bc2_sqrt,
+               float max_norm, int first_step, cudaStream_t st);
+
 }  // namespace a2cb

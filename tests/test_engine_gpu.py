@@ -1,0 +1,235 @@
+"""GPU: the affine-indexed GEMM engine, the fused loss epilogue and the optimiser kernels
+(all through the C ABI) against the numpy emulator / torch fp32 references."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from a2c_ppo_acktr import _engine, _native  # noqa: E402
+from a2c_ppo_acktr import _plans as P  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def run_plan(plan, bufs, idx=None):
+    """Runs one plan on the GPU on copies of the numpy buffers; returns the updated buffers."""
+    arena = _engine.Arena(torch.device(DEV))
+    for k, v in bufs.items():
+        arena.bind(k, torch.from_numpy(v.copy()).to(DEV))
+    prog = _engine.Program(torch.device(DEV))
+    prog.add_plan(plan, arena)
+    prog.run(torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(DEV) if idx is not None else None)
+    torch.cuda.synchronize()
+    return {k: arena.bufs[k].cpu().numpy() for k in bufs}
+
+
+def rand_affine(rng, n, max_off):
+    """A random injective-enough 3-digit map for n indices."""
+    d2 = int(rng.integers(1, 5))
+    d1 = d2 * int(rng.integers(1, 4))
+    s2 = int(rng.integers(1, 4))
+    s1 = s2 * d2 + int(rng.integers(0, 3))
+    s0 = s1 * (d1 // d2) + int(rng.integers(0, 5))
+    return (d1, d2, s0, s1, s2), ((n - 1) // d1) * s0 + ((d1 - 1) // d2) * s1 + (d2 - 1) * s2 + 1
+
+
+@pytest.mark.parametrize("M,N,K,tile", [(1, 1, 1, 0), (129, 7, 33, 0), (300, 33, 70, 64), (257, 130, 19, 128),
+                                        (64, 64, 64, 32), (500, 96, 128, 0)])
+@pytest.mark.parametrize("variant", ["plain", "epilogue", "ones", "batch"])
+def test_gemm_random_maps_vs_emulator(M, N, K, tile, variant):
+    rng = np.random.default_rng(M * 1000 + N * 10 + K)
+    rowA, spanRA = rand_affine(rng, M, 0)
+    redA, spanKA = rand_affine(rng, K, 0)
+    redB, spanKB = rand_affine(rng, K, 0)
+    colB, spanCB = rand_affine(rng, N, 0)
+    # output map must be injective: plain row-major with padding
+    ldc = N + int(rng.integers(0, 3))
+    rowC, colC = P.plain(ldc), P.plain(1)
+    nb = 3 if variant == "batch" else 1
+    bufs = {
+        "A": rng.standard_normal(spanRA + spanKA + 64 * nb).astype(np.float32),
+        "B": rng.standard_normal(spanKB + spanCB + 64 * nb).astype(np.float32),
+        "C": np.zeros(M * ldc * nb + 8, np.float32),
+        "bias": rng.standard_normal(max(M, N)).astype(np.float32),
+        "mask": rng.standard_normal(M * ldc).astype(np.float32),
+        "ones": np.zeros(N * 2, np.float32),
+    }
+    kw = dict(tile=tile)
+    if variant == "epilogue":
+        kw.update(bias=("bias", 0), bias_mode=1 + (M % 2), act=P.ACT_RELU if N % 2 else P.ACT_TANH,
+                  mask=("mask", 0), mask_mode=1 + (K % 2), rowM=rowC, colM=colC, alpha=0.5)
+    if variant == "ones":
+        kw.update(ones=("ones", 1), ones_stride=2 if N > 1 else 1)
+    if variant == "batch":
+        kw.update(batch=3, batch_offA=[0, 17, 40, 0], batch_offB=[0, 5, 64, 0], batch_offC=[0, M * ldc, 2 * M * ldc, 0])
+    plan = P.Plan("t", ("A", 0), ("B", 0), ("C", 0), M, N, K, rowA, redA, redB, colB, rowC, colC, **kw)
+    want = {k: v.copy() for k, v in bufs.items()}
+    P.emulate(plan, want)
+    got = run_plan(plan, bufs)
+    np.testing.assert_allclose(got["C"], want["C"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(got["ones"], want["ones"], rtol=2e-5, atol=2e-5)
+
+
+def test_gemm_split_k_and_reduce():
+    rng = np.random.default_rng(5)
+    M, N, K, splits = 70, 33, 1000, 7
+    span = M * N + N
+    bufs = {"A": rng.standard_normal(M * K).astype(np.float32), "B": rng.standard_normal(K * N).astype(np.float32),
+            "part": np.zeros(splits * span, np.float32), "G": np.full(span + 5, 3.0, np.float32)}
+    plan = P.Plan("t", ("A", 0), ("B", 0), ("part", 0), M, N, K, P.plain(K), P.plain(1), P.plain(N), P.plain(1),
+                  P.plain(N), P.plain(1), ones=("part", M * N), splits=splits, split_stride=span,
+                  split_dst=("G", 5, span))
+    got = run_plan(plan, bufs)
+    A = bufs["A"].reshape(M, K).astype(np.float64)
+    B = bufs["B"].reshape(K, N).astype(np.float64)
+    np.testing.assert_allclose(got["G"][5:5 + M * N].reshape(M, N), A @ B, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(got["G"][5 + M * N:], B.sum(0), rtol=1e-5, atol=1e-4)
+    assert np.all(got["G"][:5] == 3.0)
+
+
+@pytest.mark.parametrize("obs_dtype", [torch.uint8, torch.float32])
+def test_cnn_forward_backward_vs_torch(obs_dtype):
+    """Whole CNN trunk + heads through the engine (gathered rows, fused /255) vs torch autograd."""
+    from a2c_ppo_acktr.model import Policy
+
+    class Discrete(object):
+        n = 6
+    torch.manual_seed(1)
+    pol = Policy((4, 84, 84), Discrete())
+    sd = {k: v.clone() for k, v in pol.state_dict().items()}
+    # non-zero biases so that the bias paths are exercised
+    g = torch.Generator().manual_seed(3)
+    for k in sd:
+        if k.endswith("bias"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+    pol.load_state_dict(sd)
+    pol.to(DEV)
+    rows, B = 11, 5
+    obs_u8 = torch.randint(0, 256, (rows, 4, 84, 84), generator=g, dtype=torch.uint8)
+    idx = torch.tensor([7, 0, 3, 10, 3])
+    action = torch.randint(0, 6, (B, 1), generator=g)
+    # torch reference on CPU
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = obs_u8[idx].float() / 255.0
+    a = F.relu(F.conv2d(x, ref["base.main.0.weight"], ref["base.main.0.bias"], stride=4))
+    a = F.relu(F.conv2d(a, ref["base.main.2.weight"], ref["base.main.2.bias"], stride=2))
+    a = F.relu(F.conv2d(a, ref["base.main.4.weight"], ref["base.main.4.bias"], stride=1))
+    h = F.relu(F.linear(a.reshape(B, -1), ref["base.main.7.weight"], ref["base.main.7.bias"]))
+    value = F.linear(h, ref["base.critic_linear.weight"], ref["base.critic_linear.bias"])
+    logits = F.linear(h, ref["dist.linear.weight"], ref["dist.linear.bias"])
+    dist = torch.distributions.Categorical(logits=logits)
+    logp = dist.log_prob(action.squeeze(-1)).unsqueeze(-1)
+    ent = dist.entropy().mean()
+    cv, cl, ce = torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g), 0.7
+    ((value * cv).sum() + (logp * cl).sum() + ce * ent).backward()
+
+    obs_dev = (obs_u8 if obs_dtype == torch.uint8 else obs_u8.float())[idx].to(DEV)
+    v2, lp2, ent2, _ = pol.evaluate_actions(obs_dev, torch.zeros(B, 1, device=DEV), torch.ones(B, 1, device=DEV),
+                                            action.to(DEV))
+    tol = dict(rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(v2.detach().cpu().numpy(), value.detach().numpy(), **tol)
+    np.testing.assert_allclose(lp2.detach().cpu().numpy(), logp.detach().numpy(), **tol)
+    np.testing.assert_allclose(ent2.item(), ent.item(), **tol)
+    for p in pol.parameters():
+        p.grad.zero_()
+    ((v2 * cv.to(DEV)).sum() + (lp2 * cl.to(DEV)).sum() + ce * ent2).backward()
+    for k, p in pol.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref[k].grad.numpy(), rtol=2e-4, atol=2e-5, err_msg=k)
+
+
+def test_mlp_forward_backward_vs_torch():
+    from a2c_ppo_acktr.model import Policy
+
+    class Box(object):
+        shape = (3,)
+    torch.manual_seed(1)
+    pol = Policy((11,), Box())
+    g = torch.Generator().manual_seed(4)
+    sd = {k: v.clone() for k, v in pol.state_dict().items()}
+    for k in sd:
+        if k.endswith("bias"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
+    pol.load_state_dict(sd)
+    pol.to(DEV)
+    B = 9
+    obs = torch.randn(B, 11, generator=g)
+    action = torch.randn(B, 3, generator=g)
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    hc = torch.tanh(F.linear(obs, ref["base.critic.0.weight"], ref["base.critic.0.bias"]))
+    hc = torch.tanh(F.linear(hc, ref["base.critic.2.weight"], ref["base.critic.2.bias"]))
+    ha = torch.tanh(F.linear(obs, ref["base.actor.0.weight"], ref["base.actor.0.bias"]))
+    ha = torch.tanh(F.linear(ha, ref["base.actor.2.weight"], ref["base.actor.2.bias"]))
+    value = F.linear(hc, ref["base.critic_linear.weight"], ref["base.critic_linear.bias"])
+    mean = F.linear(ha, ref["dist.fc_mean.weight"], ref["dist.fc_mean.bias"])
+    std = (torch.zeros_like(mean) + ref["dist.logstd._bias"].t().view(1, -1)).exp()
+    dist = torch.distributions.Normal(mean, std)
+    logp = dist.log_prob(action).sum(-1, keepdim=True)
+    ent = dist.entropy().sum(-1).mean()
+    cv, cl, ce = torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g), -0.3
+    ((value * cv).sum() + (logp * cl).sum() + ce * ent).backward()
+    v2, lp2, ent2, _ = pol.evaluate_actions(obs.to(DEV), torch.zeros(B, 1, device=DEV), torch.ones(B, 1, device=DEV),
+                                            action.to(DEV))
+    tol = dict(rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(v2.detach().cpu().numpy(), value.detach().numpy(), **tol)
+    np.testing.assert_allclose(lp2.detach().cpu().numpy(), logp.detach().numpy(), **tol)
+    np.testing.assert_allclose(ent2.item(), ent.item(), **tol)
+    for p in pol.parameters():
+        p.grad.zero_()
+    ((v2 * cv.to(DEV)).sum() + (lp2 * cl.to(DEV)).sum() + ce * ent2).backward()
+    for k, p in pol.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), ref[k].grad.numpy(), rtol=2e-4, atol=2e-5, err_msg=k)
+
+
+@pytest.mark.parametrize("kind", ["adam", "rmsprop"])
+def test_optimizer_step_vs_torch(kind):
+    n = 10007
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=g)
+    ref = p0.clone().requires_grad_(True)
+    opt = (torch.optim.Adam([ref], lr=2.5e-4, eps=1e-5) if kind == "adam"
+           else torch.optim.RMSprop([ref], 7e-4, eps=1e-5, alpha=0.99))
+    p = p0.clone().to(DEV)
+    s1, s2 = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    scratch = torch.zeros(160, dtype=torch.float64, device=DEV)
+    norm = torch.zeros(4, device=DEV)
+    lib = _native.lib()
+    for t in range(1, 4):
+        grad = torch.randn(n, generator=g) * (3.0 if t == 2 else 0.001)
+        ref.grad = grad.clone()
+        tn = torch.nn.utils.clip_grad_norm_([ref], 0.5)
+        opt.step()
+        gd = grad.clone().to(DEV)
+        st = _native.stream_ptr(torch.device(DEV))
+        _native.check(lib.a2cb_grad_norm(gd.data_ptr(), n, scratch.data_ptr(), norm.data_ptr(), st), "norm")
+        if kind == "adam":
+            bc1, bc2 = 1 - 0.9 ** t, 1 - 0.999 ** t
+            args = (0, 2.5e-4 / bc1, 1e-5, 0.9, 0.999, 1 - 0.9, 1 - 0.999, math.sqrt(bc2))
+        else:
+            args = (1, 7e-4, 1e-5, 0.0, 0.99, 1.0, 1 - 0.99, 1.0)
+        _native.check(lib.a2cb_optim_step(args[0], p.data_ptr(), gd.data_ptr(), s1.data_ptr(), s2.data_ptr(), n,
+                                          norm.data_ptr(), *args[1:], 0.5, int(t == 1), st), "optim")
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(norm[0].item(), float(tn), rtol=1e-6)
+        np.testing.assert_allclose(gd.cpu().numpy(), ref.grad.numpy(), rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(p.cpu().numpy(), ref.detach().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_adv_normalize_vs_torch():
+    g = torch.Generator().manual_seed(2)
+    for n in (7, 1024, 40001):
+        ret, val = torch.randn(n, generator=g) * 3 + 1, torch.randn(n, generator=g)
+        adv = ret - val
+        want = (adv - adv.mean()) / (adv.std() + 1e-5)
+        rd, vd = ret.to(DEV), val.to(DEV)
+        out = torch.zeros(n, device=DEV)
+        scratch = torch.zeros(2 * 128 + 2, dtype=torch.float64, device=DEV)
+        mom = torch.zeros(4, dtype=torch.float64, device=DEV)
+        lib, st = _native.lib(), _native.stream_ptr(torch.device(DEV))
+        _native.check(lib.a2cb_adv_moments(rd.data_ptr(), vd.data_ptr(), n, scratch.data_ptr(), mom.data_ptr(), st), "m")
+        _native.check(lib.a2cb_adv_normalize(rd.data_ptr(), vd.data_ptr(), n, mom.data_ptr(), out.data_ptr(), st), "n")
+        np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)

