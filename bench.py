@@ -1,0 +1,485 @@
+"""Benchmark of the rollout-batch policy-update hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3]
+
+One "step" = one pass of the hot path over one synthetic rollout:
+    RolloutStorage.compute_returns -> PPO.update -> after_update        (reference main.py:157-162)
+`value` is update transitions/s with the rollout already resident in HBM; `e2e` is the
+same metric through the public a2c_ppo_acktr API with HOST buffers: every step copies the
+rollout from pinned host memory to the device storage and reads the three losses back.
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the
+reference (oracle/) on the host cores with the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pytorch-a2c-ppo-acktr-gail_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import synthetic  # noqa: E402
+
+
+class Discrete(object):
+    def __init__(self, n):
+        self.n = n
+
+
+class Box(object):
+    def __init__(self, d):
+        self.shape = (d,)
+
+
+def space(action):
+    kind, n = action
+    return Discrete(n) if kind == "discrete" else Box(n)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor_burst=p["bf16_tflops"], tensor_sustained=p["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ---------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                c, m = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.2:
+                sm.append(c)
+                smax.append(m)
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        if not sm:
+            for ts, line in self.lines[-3:]:
+                parts = [p.strip() for p in line.split(",")]
+                try:
+                    sm.append(float(parts[0]))
+                    smax.append(float(parts[1]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# workload construction
+# ---------------------------------------------------------------------------
+def workload_config(name):
+    cfg = dict(synthetic.CONFIGS[name])
+    cfg["name"] = name
+    return cfg
+
+
+def host_rollout(cfg, policy_act, policy_value, hidden, env_range=None, N_total=None):
+    """Synthetic rollout on the host (pinned), policy-consistent (actions from Policy.act)."""
+    ro = synthetic.make_rollout(cfg, policy_act, policy_value, hidden, seed=0, env_range=env_range,
+                                N_total=N_total, obs_uint8=(cfg["kind"] == "atari"))
+    return ro
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from a2c_ppo_acktr import _native, algo
+    from a2c_ppo_acktr.model import Policy
+    from a2c_ppo_acktr.storage import RolloutStorage
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs a torchrun launch with %d ranks" % (args.gpus, args.gpus))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = workload_config(args.workload)
+    T, Nloc = cfg["T"], cfg["N"]                    # weak scaling: every rank owns cfg["N"] environments
+    N_total = Nloc * world
+    env_range = (rank * Nloc, (rank + 1) * Nloc)
+
+    torch.manual_seed(1)
+    policy = Policy(cfg["obs_shape"], space(cfg["action"]), base_kwargs={"recurrent": cfg["recurrent"]})
+    policy.to(dev)
+    H = policy.recurrent_hidden_state_size
+    obs_dtype = torch.uint8 if cfg["kind"] == "atari" else torch.float32
+
+    # ---- synthetic rollout: frames on the host, policy outputs from Policy.act on the device ----
+    torch.manual_seed(2 + rank)
+    obs_np, rew_np, mask_np, bad_np = synthetic.rollout_inputs(cfg, 0, env_range, N_total, obs_uint8=(obs_dtype == torch.uint8))
+    host = {
+        "obs": torch.from_numpy(obs_np).pin_memory(),
+        "rewards": torch.from_numpy(rew_np).pin_memory(),
+        "masks": torch.from_numpy(mask_np).pin_memory(),
+        "bad_masks": torch.from_numpy(bad_np).pin_memory(),
+    }
+    st = RolloutStorage(T, Nloc, cfg["obs_shape"], space(cfg["action"]), H, obs_dtype=obs_dtype)
+    st.to(dev)
+    for k in ("obs", "rewards", "masks", "bad_masks"):
+        getattr(st, k).copy_(host[k])
+    with torch.no_grad():
+        for t in range(T):
+            v, a, lp, h = policy.act(st.obs[t], st.recurrent_hidden_states[t], st.masks[t])
+            st.value_preds[t].copy_(v)
+            st.actions[t].copy_(a)
+            st.action_log_probs[t].copy_(lp)
+            st.recurrent_hidden_states[t + 1].copy_(h)
+        next_value = policy.get_value(st.obs[T], st.recurrent_hidden_states[T], st.masks[T]).clone()
+    for k in ("actions", "action_log_probs", "value_preds", "recurrent_hidden_states"):
+        host[k] = getattr(st, k).cpu().pin_memory()
+    host["next_value"] = next_value.cpu().pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    if cfg["algo"] == "ppo":
+        agent = algo.PPO(policy, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
+                         cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"], max_grad_norm=cfg["max_grad_norm"])
+    else:
+        agent = algo.A2C_ACKTR(policy, cfg["value_loss_coef"], cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"],
+                               alpha=cfg["alpha"], max_grad_norm=cfg["max_grad_norm"])
+    if world > 1:
+        agent.set_distributed(world, rank, env_range, N_total)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def upload():
+        for k in ("obs", "rewards", "masks", "bad_masks", "actions", "action_log_probs", "value_preds",
+                  "recurrent_hidden_states"):
+            getattr(st, k).copy_(host[k], non_blocking=True)
+        return host["next_value"].to(dev, non_blocking=True)
+
+    def hot_path(nv):
+        st.compute_returns(nv, cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"], cfg["use_proper_time_limits"])
+        out = agent.update(st)
+        st.after_update()
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, e2e):
+        """Device-timed steps (CUDA events on the launching stream), L2 flushed between steps."""
+        total_ms = 0.0
+        losses = None
+        for i in range(n_steps):
+            torch.manual_seed(7 + i)
+            if not e2e:
+                nv = upload()                                  # restore the rollout (params keep training)
+            flush.zero_()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if e2e:
+                nv = upload()
+            losses = hot_path(nv)                              # update() ends with the D2H of the losses
+            e1.record()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            total_ms += ms.item()
+        return total_ms, losses
+
+    timed(args.warmup, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    t0 = time.time()
+    l0 = _native.launch_count()
+    total_ms, losses = timed(args.steps, False)
+    launches = _native.launch_count() - l0
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    timed(1, True)
+    e2e_ms, _ = timed(args.steps, True)
+
+    transitions = T * Nloc * world
+    ms_per_step = total_ms / args.steps
+    value = transitions / (ms_per_step / 1e3)
+    e2e_value = transitions / (e2e_ms / args.steps / 1e3)
+
+    out = None
+    if rank == 0:
+        pk = peaks()
+        roof, kernels = kernel_roofline(agent, st, cfg, dev, pk) if world == 1 else (None, None)
+        scan = scan_roofline(dev, pk) if world == 1 else None
+        out = {
+            "metric": "PPO update transitions/sec" if cfg["algo"] == "ppo" else "A2C update transitions/sec",
+            "value": value, "unit": "transitions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (cfg["name"], describe(cfg)), "envs_per_gpu": Nloc, "num_steps": T,
+                       "obs": "uint8 4x84x84" if obs_dtype == torch.uint8 else "fp32", "l2": "flushed between steps (256 MiB write)",
+                       "step": "compute_returns + update + after_update"},
+            "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 12},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "losses": [float(x) for x in losses],
+        }
+        if roof:
+            out["roofline"] = roof
+            out["kernels"] = kernels
+        if scan:
+            out["scan"] = scan
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(cfg, steps=3)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+def describe(cfg):
+    if cfg["algo"] == "ppo":
+        return ("PPO %s, %d steps x %d procs per GPU, %d epochs x %d minibatches, clip %.2g%s"
+                % ("CNNBase" if len(cfg["obs_shape"]) == 3 else "MLPBase", cfg["T"], cfg["N"], cfg["ppo_epoch"],
+                   cfg["num_mini_batch"], cfg["clip_param"], ", GRU" if cfg["recurrent"] else ""))
+    return "%s %s, %d steps x %d procs" % (cfg["algo"].upper(), "CNNBase", cfg["T"], cfg["N"])
+
+
+# ---------------------------------------------------------------------------
+# per-kernel timing (CUDA events around every op of one minibatch program)
+# ---------------------------------------------------------------------------
+def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
+    from a2c_ppo_acktr import _engine
+    prog = getattr(agent, "_prog", None)
+    if prog is None:
+        return None, None
+    T, N = cfg["T"], cfg["N"]
+    mbs = prog.builder.B
+    names, flops = [], []
+    for kind, flags, desc in prog.entries:
+        if kind == _engine.OP_GEMM:
+            names.append("gemm")
+            flops.append(2.0 * desc.M * desc.N * desc.K * desc.batch)
+        else:
+            names.append({2: "reduce_splits", 3: "loss_epilogue", 4: "grad_norm", 5: "optim_step"}.get(kind, "op%d" % kind))
+            flops.append(0.0)
+    # label GEMMs by their plan
+    labels = []
+    gi = 0
+    plan_names = [p for p in getattr(prog, "plan_names", [])]
+    for i, n in enumerate(names):
+        if n == "gemm" and gi < len(plan_names):
+            labels.append(plan_names[gi])
+            gi += 1
+        else:
+            labels.append(n)
+    singles = []
+    for kind, flags, desc in prog.entries:
+        p = _engine.Program(dev)
+        p.add(kind, desc, flags)
+        singles.append(p.finalize())
+    idx = torch.randperm(T * N)[:mbs].to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    times = np.zeros(len(singles))
+    for r in range(reps + 2):
+        flush.zero_()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(singles) + 1)]
+        evs[0].record()
+        for i, p in enumerate(singles):
+            p.run(idx)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        if r >= 2:
+            times += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(len(singles))])
+    times /= reps
+    total = times.sum()
+    rows = []
+    for lab, t, f in zip(labels, times, flops):
+        rows.append({"op": lab, "ms": float(t), "share": float(t / total), "tflops": float(f / t / 1e9) if f else None})
+    top = int(np.argmax(times))
+    peak = pk["tensor_sustained"]
+    roof = {"bound": "tensor", "kernel": "gemm_kernel (%s)" % labels[top], "achieved": rows[top]["tflops"],
+            "peak": peak, "unit": "TFLOP/s", "frac": (rows[top]["tflops"] or 0.0) / peak, "traffic": None,
+            "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside the step; fp32 SIMT engine, "
+                           "no TF32 peak is published for this pool)",
+            "share_of_step": rows[top]["share"], "launch_ms": rows[top]["ms"]}
+    return roof, rows
+
+
+def scan_roofline(dev, pk):
+    """GAE scan HBM GB/s on a [128, 2^20] sweep (config-sized scans are launch-bound: 20 KB..5 MB)."""
+    from a2c_ppo_acktr import _native
+    T, N = 128, 1 << 20
+    r = torch.randn(T, N, 1, device=dev)
+    v = torch.randn(T + 1, N, 1, device=dev)
+    m = (torch.rand(T + 1, N, 1, device=dev) > 0.01).float()
+    b = torch.ones(T + 1, N, 1, device=dev)
+    out = torch.zeros(T + 1, N, 1, device=dev)
+    nv = torch.randn(N, device=dev)
+    ts = []
+    for i in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _native.returns_scan(r, v, out, m, b, nv, 0.99, 0.95, True, True, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ms = float(np.mean(ts))
+    gbs = 20.0 * T * N / ms / 1e6
+    return {"kernel": "returns_scan_env_kernel<GAE,PTL,4,4>", "shape": [T, N], "bytes_per_transition": 20,
+            "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "ms": ms,
+            "note": "inputs 2.7 GB > L2"}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference on the host cores
+# ---------------------------------------------------------------------------
+def cpu_update_once(cfg, state):
+    from oracle import returns as o_ret
+    from oracle import update as o_upd
+    ro, p, spec = state["ro"], state["p"], state["spec"]
+    t0 = time.perf_counter()
+    ret, vp = o_ret.compute_returns(ro["rewards"].numpy(), ro["value_preds"].numpy(), ro["masks"].numpy(),
+                                    ro["bad_masks"].numpy(), ro["next_value"].numpy(), cfg["use_gae"], cfg["gamma"],
+                                    cfg["gae_lambda"], cfg["use_proper_time_limits"])
+    ro["returns"] = torch.from_numpy(ret)
+    ro["value_preds"] = torch.from_numpy(vp)
+    if cfg["algo"] == "ppo":
+        out = o_upd.ppo_update(p, spec, ro, cfg, optimizer=state.get("opt"))
+    else:
+        out = o_upd.a2c_update(p, spec, ro, cfg, optimizer=state.get("opt"))
+    state["opt"] = out[3]
+    for k in ("obs", "recurrent_hidden_states", "masks", "bad_masks"):       # after_update
+        ro[k][0].copy_(ro[k][-1])
+    return time.perf_counter() - t0, out[:3]
+
+
+def cpu_state(cfg):
+    from oracle import policy as o_pol
+    from oracle import update as o_upd
+    spec = o_pol.Spec(cfg["obs_shape"], cfg["action"], cfg["recurrent"])
+    p0 = o_pol.init_params(spec, seed=1)
+    torch.manual_seed(2)
+    with torch.no_grad():
+        ro = synthetic.make_rollout(cfg, lambda o, h, m: o_pol.act(p0, spec, o, h, m),
+                                    lambda o, h, m: o_pol.get_value(p0, spec, o, h, m), spec.hidden_state_size, seed=0)
+    return {"ro": ro, "p": o_upd.make_leaf_params(p0), "spec": spec}
+
+
+def cpu_baseline(cfg, steps=3, warmup=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = cpu_state(cfg)
+    ts = []
+    for i in range(warmup + steps):
+        torch.manual_seed(7 + i)
+        dt, _ = cpu_update_once(cfg, state)
+        if i >= warmup:
+            ts.append(dt)
+    tr = cfg["T"] * cfg["N"]
+    return {"value": tr / float(np.mean(ts)), "unit": "transitions/s", "cores": cores, "kind": "port",
+            "sample": "%d full %s updates (%d transitions each) of the oracle port (torch %s CPU, %d threads), "
+                      "mean %.3f s/update" % (steps, cfg["name"], tr, torch.__version__, cores, float(np.mean(ts)))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload_config(args.workload)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = cpu_state(cfg)
+    ts, losses = [], None
+    for i in range(args.warmup + args.steps):
+        torch.manual_seed(7 + i)
+        dt, losses = cpu_update_once(cfg, state)
+        if i >= args.warmup:
+            ts.append(dt)
+    tr = cfg["T"] * cfg["N"]
+    val = tr / float(np.mean(ts))
+    sample = "%d full %s updates of the oracle port of the reference (torch %s CPU, %d threads)" % (
+        args.steps, cfg["name"], torch.__version__, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "PPO update transitions/sec" if cfg["algo"] == "ppo" else "A2C update transitions/sec",
+        "value": val, "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(ts)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (cfg["name"], describe(cfg)), "envs_per_gpu": cfg["N"], "num_steps": cfg["T"],
+                   "step": "compute_returns + update + after_update"},
+        "cpu_baseline": {"value": val, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "losses": [float(x) for x in losses],
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -124,14 +124,16 @@ typedef struct {
     int32_t splits;
     int32_t vecA;       /* 0 scalar, 1 four consecutive r contiguous+aligned, 2 four consecutive rows */
     int64_t split_stride;
-    int32_t vecB;       /* 0 scalar, 1 four consecutive columns contiguous+aligned */
-    int32_t tile;       /* 0 auto, else column tile 32 / 64 / 128 */
+    int32_t vecB;       /* 0 scalar, 1 four consecutive columns contiguous+aligned, 2 four consecutive r */
+    int32_t tile;       /* 0 auto, else tile: 32 / 64 / 128 (128 x tile) or 65 (64 x 64) */
 } a2cb_gemm_t;
 
 int a2cb_gemm(const a2cb_gemm_t* desc, a2cb_stream_t stream);
-/* dst[e] (+)= sum_{s < splits} src[s * stride + e],  e in [0, count) */
+/* dst[e] (+)= act( sum_{s < splits} src[s * stride + e] + bias[e % ncols] ),  e in [0, count)
+ * (bias may be NULL; act: 0 none, 1 relu, 2 tanh) */
 int a2cb_reduce_splits(float* dst, const float* src, int64_t count, int64_t stride, int32_t splits,
-                       int32_t accumulate, a2cb_stream_t stream);
+                       int32_t accumulate, const float* bias, int32_t ncols, int32_t act,
+                       a2cb_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * (4) fused loss epilogue                a2c_ppo_acktr/algo/ppo.py:35-37,61-77,86-88
@@ -217,7 +219,8 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_FILL 6
 #define A2CB_OP_RUNTIME_IDX 1
 
-typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate; } a2cb_reduce_t;
+typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
+                 const float* bias; int32_t ncols; int32_t act; } a2cb_reduce_t;
 typedef struct { const float* grads; int64_t n; double* scratch; float* norm_out; } a2cb_grad_norm_t;
 typedef struct {
     float* params; float* grads; float* state1; float* state2; int64_t n; const float* norm;

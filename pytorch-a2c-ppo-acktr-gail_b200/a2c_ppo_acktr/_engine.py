@@ -38,7 +38,7 @@ class LossDesc(ctypes.Structure):
 
 class ReduceDesc(ctypes.Structure):
     _fields_ = [("dst", c_vp), ("src", c_vp), ("count", c_i64), ("stride", c_i64), ("splits", c_i32),
-                ("accumulate", c_i32)]
+                ("accumulate", c_i32), ("bias", c_vp), ("ncols", c_i32), ("act", c_i32)]
 
 
 class GradNormDesc(ctypes.Structure):
@@ -62,7 +62,7 @@ class Op(ctypes.Structure):
 
 _native.register({
     "a2cb_gemm": (c_i32, [ctypes.POINTER(P.GemmDesc), c_vp]),
-    "a2cb_reduce_splits": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp]),
+    "a2cb_reduce_splits": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
     "a2cb_loss_epilogue": (c_i32, [ctypes.POINTER(LossDesc), c_vp]),
     "a2cb_loss_scratch_floats": (c_i64, [c_i32]),
     "a2cb_adv_moments": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -131,6 +131,14 @@ def resolve(plan, arena):
     return g
 
 
+def forward_splits(M, N, K):
+    """Split-K for a forward GEMM whose output grid alone cannot occupy the machine (small batches)."""
+    tiles = ((M + 63) // 64) * ((N + 63) // 64)
+    ktiles = (K + 15) // 16
+    want = (148 + tiles - 1) // tiles
+    return int(max(1, min(want, ktiles // 8 if ktiles >= 16 else 1, 32)))
+
+
 def choose_splits(rows, cols, red):
     """Split the reduction so that a weight-gradient GEMM with a tiny output fills 148 SMs."""
     tiles = ((rows + 127) // 128) * ((cols + 63) // 64 if cols > 32 else 1)
@@ -146,6 +154,7 @@ class Program(object):
         self.device = device
         self.entries = []          # (kind, flags, ctypes struct)
         self.flops = 0
+        self.plan_names = []
         self._arr = None
 
     def add(self, kind, desc, flags=0):
@@ -156,11 +165,12 @@ class Program(object):
     def add_plan(self, plan, arena):
         flags = RUNTIME_IDX if (plan.gather_row or plan.gather_red) else 0
         self.add(OP_GEMM, resolve(plan, arena), flags)
+        self.plan_names.append(plan.name)
         self.flops += plan.flops
         if plan.splits > 1:
             dst = plan.split_dst
             r = ReduceDesc(arena.ptr((dst[0], dst[1])), arena.ptr(plan.C), dst[2], plan.split_stride, plan.splits,
-                           plan.accumulate)
+                           plan.accumulate, arena.ptr(plan.split_bias), plan.N, plan.split_act)
             self.add(OP_REDUCE, r)
 
     def extend(self, other):
@@ -278,7 +288,7 @@ class NetBuilder(object):
             self.c1 = P.Conv("conv1", C, 84, 84, 8, 4, 32, in_layout="nchw", needs_dgrad=False)
             self.c2 = P.Conv("conv2", 32, 20, 20, 4, 2, 64)
             self.c3 = P.Conv("conv3", 64, 9, 9, 3, 1, 32)
-            self.fc = P.Linear("fc", 1568, H, in_perm=P.aff(7 * 32, 32, 7, 1, 49))
+            self.fc = P.Linear("fc", 1568, H)     # a3 is kept in NCHW-flatten order: no permutation
         self.heads = P.Linear("heads", H, 1 + A)
 
     def n(self, name):
@@ -302,11 +312,13 @@ class NetBuilder(object):
         c1, c2, c3 = self.c1, self.c2, self.c3
         a1, a2, a3 = self.buf("a1", B * c1.out_row), self.buf("a2", B * c2.out_row), self.buf("a3", B * c3.out_row)
         h, z = self.buf("h", B * s.hidden), self.buf("z", B * self.zs)
+        sp = forward_splits(B, s.hidden, 1568)
+        part = self.buf("part_fc_fwd", sp * B * s.hidden) if sp > 1 else None
         plans = [
             P.conv_forward(c1, B, (self.obs, 0), *self.wb("conv1"), a1, a_u8=self.obs_code, gather=self.gather),
             P.conv_forward(c2, B, a1, *self.wb("conv2"), a2),
-            P.conv_forward(c3, B, a2, *self.wb("conv3"), a3),
-            P.linear_forward(self.fc, B, a3, *self.wb("fc"), h, act=P.ACT_RELU),
+            P.conv_forward(c3, B, a2, *self.wb("conv3"), a3, out_layout="nchw"),
+            P.linear_forward(self.fc, B, a3, *self.wb("fc"), h, act=P.ACT_RELU, splits=sp, partial=part),
         ]
         return plans, h
 
@@ -319,7 +331,7 @@ class NetBuilder(object):
         plans = [
             P.linear_wgrad(self.fc, B, a3, feat_grad, *self.gwb("fc")),
             P.linear_dgrad(self.fc, B, feat_grad, ("P", self.L.layers["fc"][0]), g3, mask=a3, mask_mode=1,
-                           row_out=P.plain(c3.gout_row), col_out=P.aff(7 * 32, 32, c3.pw * 32, 32, 1),
+                           row_out=P.plain(c3.gout_row), col_out=P.aff(49, 7, 1, c3.pw * 32, 32),
                            gx_base=c3.gout_base, mask_row=P.plain(1568), mask_col=P.plain(1)),
         ]
         for cv, src, g, gprev, prev, a_prev in ((c3, a2, g3, g2, c2, a2), (c2, a1, g2, g1, c1, a1)):
@@ -394,7 +406,9 @@ class NetBuilder(object):
     # ---- heads (CNN: one [1+A, H] matrix on the shared feature) ----
     def cnn_heads_forward(self, h):
         w, b = self.wb("heads")
-        return [P.linear_forward(self.heads, self.B, h, w, b, (self.n("z"), 0))]
+        sp = forward_splits(self.B, self.zs, self.spec.hidden)
+        part = self.buf("part_heads_fwd", sp * self.B * self.zs) if sp > 1 else None
+        return [P.linear_forward(self.heads, self.B, h, w, b, (self.n("z"), 0), splits=sp, partial=part)]
 
     def cnn_heads_backward(self, h):
         B, H = self.B, self.spec.hidden

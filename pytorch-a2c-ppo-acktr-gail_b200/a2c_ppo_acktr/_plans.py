@@ -96,6 +96,8 @@ class Plan(object):
         self.splits = kw.pop("splits", 1)
         self.split_stride = kw.pop("split_stride", 0)
         self.split_dst = kw.pop("split_dst", None)  # where reduce_splits folds the partials: (buffer, offset, count)
+        self.split_bias = kw.pop("split_bias", None)  # epilogue applied by the fold: bias[e % N] ...
+        self.split_act = kw.pop("split_act", ACT_NONE)  # ... and activation
         self.vecA = kw.pop("vecA", 0)
         self.vecB = kw.pop("vecB", 0)
         self.alpha = kw.pop("alpha", 1.0)
@@ -214,11 +216,19 @@ class Conv(object):
         return aff(self.oh * self.ow, self.ow, self.gout_row, self.pw * self.cout, self.cout)
 
 
-def conv_forward(cv, B, src, w, b, dst, act=ACT_RELU, a_u8=False, gather=False):
-    return Plan(cv.name + ".fwd", src, w, dst, B * cv.oh * cv.ow, cv.cout, cv.K,
-                rowA=cv.row_in(), redA=cv.red_in(), redB=cv.red_weight(), colB=plain(cv.K),
-                rowC=plain(cv.cout), colC=plain(1), bias=b, bias_mode=1, act=act, a_u8=a_u8,
-                gather_row=gather, vecA=1 if cv.vec_ok() else 0)
+def conv_forward(cv, B, src, w, b, dst, act=ACT_RELU, a_u8=False, gather=False, out_layout="nhwc"):
+    """out_layout 'nchw' writes [B, Cout, OH, OW] (the order the reference's Flatten() feeds main.7)."""
+    p = cv.oh * cv.ow
+    if out_layout == "nhwc":
+        rowC, colC = plain(cv.cout), plain(1)
+    else:
+        rowC, colC = aff(p, 1, cv.cout * p, 1, 0), plain(p)
+    wk = cv.red_weight()
+    return Plan(cv.name + ".fwd", src, w, dst, B * p, cv.cout, cv.K,
+                rowA=cv.row_in(), redA=cv.red_in(), redB=wk, colB=plain(cv.K),
+                rowC=rowC, colC=colC, bias=b, bias_mode=1, act=act, a_u8=a_u8,
+                gather_row=gather, vecA=1 if cv.vec_ok() else 0,
+                vecB=2 if (wk == plain(1) and cv.K % 4 == 0) else 0)
 
 
 def conv_wgrad(cv, B, src, gout, dw, db, a_u8=False, gather=False, splits=1, partial=None):
@@ -282,11 +292,19 @@ class Linear(object):
         self.in_perm = in_perm or plain(1)
 
 
-def linear_forward(ln, B, x, w, b, y, act=ACT_NONE, x_stride=None, y_stride=None):
-    return Plan(ln.name + ".fwd", x, w, y, B, ln.d_out, ln.d_in,
+def linear_forward(ln, B, x, w, b, y, act=ACT_NONE, x_stride=None, y_stride=None, splits=1, partial=None):
+    kw = {}
+    C, bias, bias_mode, gact = y, b, (1 if b is not None else 0), act
+    if splits > 1:
+        assert (y_stride or ln.d_out) == ln.d_out, "split-K forward needs a dense [B, d_out] output"
+        C, bias, bias_mode, gact = partial, None, 0, ACT_NONE
+        kw = dict(splits=splits, split_stride=B * ln.d_out, split_dst=(y[0], y[1], B * ln.d_out),
+                  split_bias=b, split_act=act)
+    return Plan(ln.name + ".fwd", x, w, C, B, ln.d_out, ln.d_in,
                 rowA=plain(x_stride or ln.d_in), redA=plain(1), redB=ln.in_perm, colB=plain(ln.d_in),
-                rowC=plain(y_stride or ln.d_out), colC=plain(1), bias=b, bias_mode=1 if b is not None else 0,
-                act=act, vecA=1 if (ln.d_in % 4 == 0 and (x_stride or ln.d_in) % 4 == 0) else 0)
+                rowC=plain(y_stride or ln.d_out), colC=plain(1), bias=bias, bias_mode=bias_mode,
+                act=gact, vecA=1 if (ln.d_in % 4 == 0 and (x_stride or ln.d_in) % 4 == 0) else 0,
+                vecB=2 if (ln.in_perm == plain(1) and ln.d_in % 4 == 0 and w[1] % 4 == 0) else 0, **kw)
 
 
 def linear_dgrad(ln, B, gy, w, gx, mask=None, mask_mode=0, gy_stride=None, col_out=None, row_out=None,

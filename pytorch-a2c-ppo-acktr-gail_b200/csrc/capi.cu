@@ -69,9 +69,10 @@ int a2cb_gemm(const a2cb_gemm_t* desc, a2cb_stream_t stream) {
 }
 
 int a2cb_reduce_splits(float* dst, const float* src, int64_t count, int64_t stride, int32_t splits,
-                       int32_t accumulate, a2cb_stream_t stream) {
+                       int32_t accumulate, const float* bias, int32_t ncols, int32_t act, a2cb_stream_t stream) {
     A2CB_REQUIRE(dst && src && count >= 0 && splits >= 1, "reduce_splits: bad argument");
-    return reduce_splits(dst, src, (long)count, (long)stride, splits, accumulate, (cudaStream_t)stream);
+    return reduce_splits(dst, src, (long)count, (long)stride, splits, accumulate, bias, ncols, act,
+                         (cudaStream_t)stream);
 }
 
 int a2cb_loss_epilogue(const a2cb_loss_t* desc, a2cb_stream_t stream) {
@@ -122,7 +123,7 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             }
             case A2CB_OP_REDUCE: {
                 const a2cb_reduce_t& r = *reinterpret_cast<const a2cb_reduce_t*>(op.desc);
-                rc = reduce_splits(r.dst, r.src, (long)r.count, (long)r.stride, r.splits, r.accumulate, st);
+                rc = reduce_splits(r.dst, r.src, (long)r.count, (long)r.stride, r.splits, r.accumulate, r.bias, r.ncols, r.act, st);
                 break;
             }
             case A2CB_OP_LOSS: {

@@ -19,7 +19,7 @@ int gather_rows(const GatherField* fields, int n_fields, const int64_t* idx, lon
 struct GemmDesc;
 int gemm(const GemmDesc& g, cudaStream_t st);
 int reduce_splits(float* dst, const float* src, long count, long stride, int splits, int accumulate,
-                  cudaStream_t st);
+                  const float* bias, int ncols, int act, cudaStream_t st);
 
 // loss.cu
 struct LossDesc;

@@ -163,6 +163,10 @@ gemm_kernel(const GemmDesc g) {
                     const int jl = (s % (BN / 4)) * 4, r = s / (BN / 4);
                     if (k0 + r < kend && cvalid[jl])
                         v = __ldg(reinterpret_cast<const float4*>(Bb + kB[buf][r] + cB[jl]));
+                } else if (g.vecB == 2) {
+                    const int jl = s % BN, r = (s / BN) * 4;
+                    if (k0 + r < kend && cvalid[jl])
+                        v = __ldg(reinterpret_cast<const float4*>(Bb + kB[buf][r] + cB[jl]));
                 } else {
                     const int jl = s % BN, r0 = s / BN;
                     float t4[4];
@@ -205,6 +209,10 @@ gemm_kernel(const GemmDesc g) {
                 if (g.vecB == 1) {
                     const int jl = (s % (BN / 4)) * 4, r = s / (BN / 4);
                     *reinterpret_cast<float4*>(&Bs[nb][r][jl]) = v;
+                } else if (g.vecB == 2) {
+                    const int jl = s % BN, r = (s / BN) * 4;
+                    Bs[nb][r + 0][jl] = v.x; Bs[nb][r + 1][jl] = v.y;
+                    Bs[nb][r + 2][jl] = v.z; Bs[nb][r + 3][jl] = v.w;
                 } else {
                     const int jl = s % BN, r0 = s / BN;
                     Bs[nb][r0][jl] = v.x; Bs[nb][r0 + kBK / 4][jl] = v.y;
@@ -316,31 +324,45 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
     A2CB_REQUIRE(g.vecA != 1 || g.K % 4 == 0, "gemm: vecA=1 needs K %% 4 == 0");
     A2CB_REQUIRE(g.vecA != 2 || g.M % 4 == 0, "gemm: vecA=2 needs M %% 4 == 0");
     A2CB_REQUIRE(g.vecB != 1 || g.N % 4 == 0, "gemm: vecB=1 needs N %% 4 == 0");
+    A2CB_REQUIRE(g.vecB != 2 || g.K % 4 == 0, "gemm: vecB=2 needs K %% 4 == 0");
     if (g.M + g.ones_row == 0 || g.N == 0) return A2CB_OK;
     int bn = g.tile;
-    if (bn == 0) bn = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
+    if (bn == 0) {
+        bn = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
+        // small problems: prefer 64x64 tiles over 128x128 when the big tile would leave most SMs idle
+        const long Mtot = g.M + g.ones_row;
+        const long big = ((Mtot + 127) / 128) * ((g.N + 127) / 128) * g.batch * g.splits;
+        if (bn == 128 && big < kNumSM) bn = 65;
+    }
     if (bn == 32) launch_tile<128, 32, 4, 4>(g, st);
     else if (bn == 64) launch_tile<128, 64, 8, 4>(g, st);
+    else if (bn == 65) launch_tile<64, 64, 4, 4>(g, st);
     else if (bn == 128) launch_tile<128, 128, 8, 8>(g, st);
     else { set_error("gemm: unsupported tile %d", bn); return A2CB_ERR_UNSUPPORTED; }
     return check_launch("gemm");
 }
 
-// dst[e] (+)= sum_s src[s * stride + e]   for e in [0, count): folds split-K partials.
+// dst[e] (+)= act( sum_s src[s * stride + e] + bias[e % ncols] )  for e in [0, count): folds split-K
+// partials (fixed order, deterministic) and applies the epilogue the split GEMM could not.
 __global__ void __launch_bounds__(256)
 reduce_splits_kernel(float* __restrict__ dst, const float* __restrict__ src, long count, long stride,
-                     int splits, int accumulate) {
+                     int splits, int accumulate, const float* __restrict__ bias, int ncols, int act) {
     const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count) return;
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += __ldg(src + (long)k * stride + e);
+    if (bias) s += __ldg(bias + (e % ncols));
+    if (act == 1) s = fmaxf(s, 0.f);
+    else if (act == 2) s = tanhf(s);
     dst[e] = accumulate ? dst[e] + s : s;
 }
 
 int reduce_splits(float* dst, const float* src, long count, long stride, int splits, int accumulate,
-                  cudaStream_t st) {
+                  const float* bias, int ncols, int act, cudaStream_t st) {
     if (count == 0) return A2CB_OK;
-    reduce_splits_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(dst, src, count, stride, splits, accumulate);
+    A2CB_REQUIRE(!bias || ncols > 0, "reduce_splits: bias needs ncols");
+    reduce_splits_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(dst, src, count, stride, splits, accumulate,
+                                                                          bias, ncols, act);
     return check_launch("reduce_splits");
 }
 

@@ -41,7 +41,7 @@ def test_cnn_trunk_plans_match_torch(u8):
     c1 = P.Conv("conv1", 4, 84, 84, 8, 4, 32, in_layout="nchw", needs_dgrad=False)
     c2 = P.Conv("conv2", 32, 20, 20, 4, 2, 64)
     c3 = P.Conv("conv3", 64, 9, 9, 3, 1, 32)
-    fc = P.Linear("fc", 1568, 512, in_perm=P.aff(7 * 32, 32, 7, 1, 49))
+    fc = P.Linear("fc", 1568, 512)
     # flat parameter / gradient buffers: [w | b] per layer
     offs, o = {}, 0
     for name, w, b in zip(["c1", "c2", "c3", "fc"], ws, bs):
@@ -68,7 +68,7 @@ def test_cnn_trunk_plans_match_torch(u8):
     fwd = [
         P.conv_forward(c1, Bn, ("obs", 0), *wb("c1"), ("a1", 0), a_u8=adt, gather=True),
         P.conv_forward(c2, Bn, ("a1", 0), *wb("c2"), ("a2", 0)),
-        P.conv_forward(c3, Bn, ("a2", 0), *wb("c3"), ("a3", 0)),
+        P.conv_forward(c3, Bn, ("a2", 0), *wb("c3"), ("a3", 0), out_layout="nchw"),
         P.linear_forward(fc, Bn, ("a3", 0), *wb("fc"), ("h", 0), act=P.ACT_RELU),
     ]
     for p in fwd:
@@ -76,14 +76,14 @@ def test_cnn_trunk_plans_match_torch(u8):
     tol = dict(rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(bufs["a1"].reshape(Bn, 20, 20, 32), nhwc(a1).detach().numpy(), **tol)
     np.testing.assert_allclose(bufs["a2"].reshape(Bn, 9, 9, 64), nhwc(a2).detach().numpy(), **tol)
-    np.testing.assert_allclose(bufs["a3"].reshape(Bn, 7, 7, 32), nhwc(a3).detach().numpy(), **tol)
+    np.testing.assert_allclose(bufs["a3"].reshape(Bn, 32, 7, 7), a3.detach().numpy(), **tol)
     np.testing.assert_allclose(bufs["h"].reshape(Bn, 512), h.detach().numpy(), **tol)
 
     bufs["gh"][:] = (R * (h > 0)).detach().numpy().ravel()
     bwd = [
         P.linear_wgrad(fc, Bn, ("a3", 0), ("gh", 0), *gwb("fc")),
         P.linear_dgrad(fc, Bn, ("gh", 0), ("P", offs["fc"][0]), ("g3", 0), mask=("a3", 0), mask_mode=1,
-                       row_out=P.plain(c3.gout_row), col_out=P.aff(7 * 32, 32, c3.pw * 32, 32, 1),
+                       row_out=P.plain(c3.gout_row), col_out=P.aff(49, 7, 1, c3.pw * 32, 32),
                        gx_base=c3.gout_base, mask_row=P.plain(1568), mask_col=P.plain(1)),
         P.conv_wgrad(c3, Bn, ("a2", 0), ("g3", 0), *gwb("c3")),
         P.conv_dgrad(c3, Bn, ("g3", 0), ("P", offs["c3"][0]), ("g2", 0),
