@@ -174,7 +174,7 @@ typedef struct {
     int32_t use_clipped_value_loss;
     float clip, c_v, c_e;
     float inv_B;
-    int32_t pad_;
+    int32_t n_valid;          /* rows [n_valid, B) are padding of a sharded minibatch; < 0: all valid */
 } a2cb_loss_t;
 
 int a2cb_loss_epilogue(const a2cb_loss_t* desc, a2cb_stream_t stream);

@@ -32,7 +32,7 @@ class LossDesc(ctypes.Structure):
         ("scratch", c_vp),
         ("B", c_i32), ("A", c_i32), ("z_stride", c_i32), ("dz_stride", c_i32), ("act_stride", c_i32),
         ("dlogstd_stride", c_i32), ("dist", c_i32), ("mode", c_i32), ("use_clipped_value_loss", c_i32),
-        ("clip", c_f32), ("c_v", c_f32), ("c_e", c_f32), ("inv_B", c_f32), ("pad_", c_i32),
+        ("clip", c_f32), ("c_v", c_f32), ("c_e", c_f32), ("inv_B", c_f32), ("n_valid", c_i32),
     ]
 
 
@@ -525,6 +525,7 @@ class PolicyRuntime(object):
         d.dist = 0 if s.action_kind == "discrete" else 1
         d.mode = mode
         d.inv_B = 1.0 / B
+        d.n_valid = -1
         d.scratch = self.loss_scratch(B).data_ptr()
         for k, v in kw.items():
             setattr(d, k, v)

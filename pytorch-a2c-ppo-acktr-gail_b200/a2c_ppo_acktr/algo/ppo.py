@@ -14,28 +14,36 @@ reference storage.py:122-125 -- so identical seeds give identical minibatches.
 """
 import torch
 
-from .. import _native
+from .. import _dist, _native
 from .optim import FlatAdam
 
 
-def _adv_normalize(rt, rollouts, allreduce=None):
-    """(returns - value_preds - mean) / (unbiased std + 1e-5) over all T*N rows (ppo.py:35-37)."""
+def _adv_moments(rt, rollouts):
+    """fp64 (sum, sum of squares, count) of returns - value_preds over this buffer's T*N rows."""
     T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
-    n = T * N
-    adv = rt.arena.ensure("adv", n)
     scratch = rt.arena.ensure("adv_scratch", 2 * 128 + 2, torch.float64)
     moments = rt.arena.ensure("adv_moments", 4, torch.float64)
-    lib = _native.lib()
-    st = _native.stream_ptr(rt.dev)
     with torch.cuda.device(rt.dev):
-        _native.check(lib.a2cb_adv_moments(_native.dptr(rollouts.returns, torch.float32, "returns"),
-                                           _native.dptr(rollouts.value_preds, torch.float32, "value_preds"),
-                                           n, scratch.data_ptr(), moments.data_ptr(), st), "a2cb_adv_moments")
-        if allreduce is not None:
-            allreduce(moments)
-        _native.check(lib.a2cb_adv_normalize(rollouts.returns.data_ptr(), rollouts.value_preds.data_ptr(), n,
-                                             moments.data_ptr(), adv.data_ptr(), st), "a2cb_adv_normalize")
+        _native.check(_native.lib().a2cb_adv_moments(
+            _native.dptr(rollouts.returns, torch.float32, "returns"),
+            _native.dptr(rollouts.value_preds, torch.float32, "value_preds"),
+            T * N, scratch.data_ptr(), moments.data_ptr(), _native.stream_ptr(rt.dev)), "a2cb_adv_moments")
+    return moments
+
+
+def _adv_apply(rt, rollouts, moments):
+    """(x - mean) / (unbiased std + 1e-5) from (possibly all-reduced) moments (ppo.py:35-37)."""
+    T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+    adv = rt.arena.ensure("adv", T * N)
+    with torch.cuda.device(rt.dev):
+        _native.check(_native.lib().a2cb_adv_normalize(
+            rollouts.returns.data_ptr(), rollouts.value_preds.data_ptr(), T * N, moments.data_ptr(),
+            adv.data_ptr(), _native.stream_ptr(rt.dev)), "a2cb_adv_normalize")
     return adv
+
+
+def _adv_normalize(rt, rollouts):
+    return _adv_apply(rt, rollouts, _adv_moments(rt, rollouts))
 
 
 class PPO():
@@ -63,21 +71,36 @@ class PPO():
         self._prog = None
         self.last_launches = 0
         self.step_hook = None      # optional callable(step_index) after each optimiser step (tests)
+        self.shard = None          # _dist.ShardInfo when the rollout is sharded over ranks
 
-    def _program(self, rt, rollouts, mbs, adv, accum):
+    def set_distributed(self, world, rank, env_range, n_total):
+        """Declares that `rollouts` passed to update() hold environments [env_range) of a global
+        rollout of n_total environments, one shard per rank of the default process group."""
+        self.shard = _dist.ShardInfo(world, rank, env_range[0], env_range[1], n_total) if world > 1 else None
+        self._prog_key = None
+
+    def _program(self, rt, rollouts, mbs, adv, accum, inv_B=None):
+        """(forward + loss + backward) program and the (clip + Adam) program.  Unsharded they are one
+        op list; sharded they are separated by the gradient all-reduce."""
         key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(),
                rollouts.value_preds.data_ptr(), rollouts.action_log_probs.data_ptr(), adv.data_ptr(),
-               accum.data_ptr(), mbs, self.clip_param, self.value_loss_coef, self.entropy_coef,
+               accum.data_ptr(), mbs, inv_B, self.clip_param, self.value_loss_coef, self.entropy_coef,
                self.use_clipped_value_loss, self.max_grad_norm)
         if key != self._prog_key:
+            from .. import _engine
             hyper = dict(clip_param=self.clip_param, value_loss_coef=self.value_loss_coef,
                          entropy_coef=self.entropy_coef, use_clipped_value_loss=self.use_clipped_value_loss)
+            if inv_B is not None:
+                hyper["inv_B"] = inv_B
             prog = rt.train_program(rollouts, mbs, 0, hyper, adv=adv, loss_accum=accum)
             self.optimizer._ensure_state()
-            rt.add_optimizer_ops(prog, 0, self.optimizer.state1, self.optimizer.state2, self.max_grad_norm)
+            opt = prog if self.shard is None else _engine.Program(rt.dev)
+            opt.optim_desc = rt.add_optimizer_ops(opt, 0, self.optimizer.state1, self.optimizer.state2,
+                                                  self.max_grad_norm)
             prog.finalize()
-            self._prog, self._prog_key = prog, key
-        return self._prog
+            opt.finalize()
+            self._prog, self._opt_prog, self._prog_key = prog, opt, key
+        return self._prog, self._opt_prog
 
     def update(self, rollouts):
         policy = self.actor_critic
@@ -91,13 +114,15 @@ class PPO():
             "* number of steps ({}) = {} "
             "to be greater than or equal to the number of PPO mini batches ({})."
             "".format(N, T, N * T, self.num_mini_batch))
+        if self.shard is not None:
+            return self._update_sharded(rt, rollouts)
         mbs = batch_size // self.num_mini_batch
         n_mb = batch_size // mbs
 
         adv = _adv_normalize(rt, rollouts)
         accum = rt.arena.ensure("loss_accum", 4)
         accum.zero_()
-        prog = self._program(rt, rollouts, mbs, adv, accum)
+        prog, _ = self._program(rt, rollouts, mbs, adv, accum)
         launches0 = _native.launch_count()
         for _ in range(self.ppo_epoch):
             perm = torch.randperm(batch_size).to(rt.dev)
@@ -109,4 +134,57 @@ class PPO():
         self.last_launches = _native.launch_count() - launches0
         num_updates = self.ppo_epoch * self.num_mini_batch
         sums = accum[:3].cpu()          # the update's only device->host synchronisation
+        return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
+
+    def _update_sharded(self, rt, rollouts):
+        gen = self.sharded_steps(rt, rollouts)
+        try:
+            while True:
+                _dist.all_reduce_sum(next(gen))
+        except StopIteration as done:
+            return done.value
+
+    def sharded_steps(self, rt, rollouts):
+        """Same update on an environment shard (see _dist.py): global permutation, own rows only,
+        gradient all-reduce before the (redundant, identical) clip + Adam step.  Written as a
+        generator that yields every tensor that must be sum-all-reduced in place, so that the
+        collective can be real NCCL (`_update_sharded`) or, in single-GPU tests, an emulation that
+        steps several ranks in lock-step."""
+        sh = self.shard
+        T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+        assert n_loc == sh.n_local, "rollouts hold %d environments, the shard declares %d" % (n_loc, sh.n_local)
+        batch_global = T * sh.n_total
+        assert batch_global >= self.num_mini_batch
+        mbs_g = batch_global // self.num_mini_batch
+        n_mb = batch_global // mbs_g
+        cap = getattr(self, "_cap", None) or _dist.default_capacity(mbs_g, sh)
+
+        moments = _adv_moments(rt, rollouts)
+        yield moments
+        adv = _adv_apply(rt, rollouts, moments)
+        accum = rt.arena.ensure("loss_accum", 4)
+        accum.zero_()
+        grads = rt.arena.bufs["G"]
+        launches0 = _native.launch_count()
+        for _ in range(self.ppo_epoch):
+            perm = torch.randperm(batch_global).numpy()            # identical on every rank (same CPU seed)
+            idx_np, counts = _dist.shard_epoch(perm, mbs_g, n_mb, sh, cap)
+            if idx_np.shape[1] > cap:
+                cap = (idx_np.shape[1] + 3) // 4 * 4
+                idx_np, counts = _dist.shard_epoch(perm, mbs_g, n_mb, sh, cap)
+            self._cap = cap
+            prog, opt = self._program(rt, rollouts, cap, adv, accum, inv_B=1.0 / mbs_g)
+            idx = torch.from_numpy(idx_np).to(rt.dev)
+            for k in range(n_mb):
+                prog.loss_desc.n_valid = int(counts[k])
+                prog.run(idx[k])
+                yield grads
+                self.optimizer.configure(opt.optim_desc)
+                opt.run()
+                if self.step_hook is not None:
+                    self.step_hook(self.optimizer.step_count)
+        self.last_launches = _native.launch_count() - launches0
+        yield accum
+        num_updates = self.ppo_epoch * self.num_mini_batch
+        sums = accum[:3].cpu()
         return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)

@@ -35,7 +35,13 @@ loss_kernel(const LossDesc d) {
 #pragma unroll
     for (int a = 0; a < kMaxActions; ++a) dls[a] = 0.f;
 
-    if (b < d.B) {
+    const int n_valid = d.n_valid < 0 ? d.B : d.n_valid;
+    if (b < d.B && b >= n_valid && d.dz) {
+        // padding row of a sharded minibatch: contributes nothing
+        float* dz = d.dz + (long)b * d.dz_stride;
+        for (int j = 0; j <= A; ++j) dz[j] = 0.f;
+    }
+    if (b < n_valid) {
         const long src = d.idx ? (long)d.idx[b] : (long)b;
         const float* z = d.z + (long)b * d.z_stride;
         const float v = z[0];

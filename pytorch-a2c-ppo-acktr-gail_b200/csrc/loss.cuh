@@ -31,7 +31,7 @@ struct LossDesc {
     int32_t use_clipped_value_loss;
     float clip, c_v, c_e;
     float inv_B;               // 1 / (global minibatch size)
-    int32_t pad_;
+    int32_t n_valid;           // rows [n_valid, B) are padding (dz = 0, no loss); < 0: all B rows valid
 };
 
 }  // namespace a2cb

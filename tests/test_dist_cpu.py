@@ -1,0 +1,83 @@
+"""CPU-only: host logic of the environment-sharded update, incl. a world_size-2 gloo run."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from a2c_ppo_acktr import _dist
+
+
+def test_shard_rows_partition_property():
+    T, N = 6, 10
+    perm = torch.randperm(T * N).numpy()
+    shards = [_dist.ShardInfo(3, r, lo, hi, N) for r, (lo, hi) in enumerate([(0, 3), (3, 7), (7, 10)])]
+    got = []
+    for sh in shards:
+        loc = _dist.shard_rows(perm, sh)
+        t, n = loc // sh.n_local, loc % sh.n_local
+        got.append(t * N + n + sh.lo)
+    merged = np.concatenate(got)
+    assert sorted(merged.tolist()) == sorted(perm.tolist())
+    # order inside a shard follows the global permutation
+    for sh, g in zip(shards, got):
+        owned = [x for x in perm.tolist() if sh.lo <= x % N < sh.hi]
+        assert g.tolist() == owned
+
+
+def test_shard_epoch_padding_and_capacity():
+    sh = _dist.ShardInfo(2, 1, 4, 8, 8)
+    perm = torch.randperm(128 * 8).numpy()
+    cap = _dist.default_capacity(256, sh)
+    idx, counts = _dist.shard_epoch(perm, 256, 4, sh, cap)
+    assert idx.shape[0] == 4 and idx.shape[1] >= counts.max() and idx.shape[1] % 4 == 0
+    assert counts.sum() == 128 * 4
+    for k in range(4):
+        assert not idx[k, counts[k]:].any()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    T, N = 16, 6
+    g = torch.Generator().manual_seed(0)
+    returns, values = torch.randn(T, N, generator=g), torch.randn(T, N, generator=g)
+    lo, hi = (0, 3) if rank == 0 else (3, 6)
+    sh = _dist.ShardInfo(world, rank, lo, hi, N)
+    x = (returns - values)[:, lo:hi].double()
+    moments = torch.tensor([x.sum(), (x * x).sum(), float(x.numel())], dtype=torch.float64)
+    _dist.all_reduce_sum(moments)                      # the 3-double exchange of the sharded update
+    mean = moments[0] / moments[2]
+    std = ((moments[1] - moments[2] * mean * mean) / (moments[2] - 1)).sqrt()
+    ref = (returns - values)
+    ok = abs(mean.item() - ref.mean().item()) < 1e-6 and abs(std.item() - ref.std().item()) < 1e-6
+    # gradient exchange: each rank contributes the rows it owns; the sum equals the global batch
+    torch.manual_seed(7)
+    perm = torch.randperm(T * N).numpy()
+    rows = _dist.shard_rows(perm[:24], sh)
+    w = torch.arange(T * N, dtype=torch.float64).view(T, N)[:, lo:hi].reshape(-1)
+    part = torch.tensor([w[rows].sum()], dtype=torch.float64)
+    _dist.all_reduce_sum(part)
+    want = torch.arange(T * N, dtype=torch.float64)[perm[:24]].sum()
+    ok = ok and abs(part.item() - want.item()) < 1e-9
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_moments_and_partition():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] and out[1]

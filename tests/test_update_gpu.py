@@ -161,3 +161,69 @@ def test_policy_pickle_roundtrip(tmp_path):
     a = pol.act(obs, torch.zeros(4, 1, device=DEV), torch.ones(4, 1, device=DEV), deterministic=True)
     b = pol2.act(obs, torch.zeros(4, 1, device=DEV), torch.ones(4, 1, device=DEV), deterministic=True)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def _sharded_lockstep(name, world, obs_uint8=True):
+    """Runs `world` emulated ranks of the environment-sharded PPO update in lock-step on ONE GPU;
+    every tensor the ranks would all-reduce over NCCL is summed here by hand."""
+    case = helpers.load("update_" + name)
+    cfg = helpers.case_config(case)
+    ro = helpers.rollout_from_case(case, cfg, obs_uint8=obs_uint8)
+    N = cfg["N"]
+    per = N // world
+    ranks = []
+    for r in range(world):
+        lo, hi = r * per, (r + 1) * per
+        torch.manual_seed(1)
+        pol = Policy(cfg["obs_shape"], space(cfg["action"]), base_kwargs={"recurrent": False}).to(DEV)
+        st = RolloutStorage(cfg["T"], per, cfg["obs_shape"], space(cfg["action"]), 1,
+                            obs_dtype=torch.uint8 if obs_uint8 else torch.float32)
+        for nme in ("obs", "recurrent_hidden_states", "rewards", "value_preds", "action_log_probs", "actions",
+                    "masks", "bad_masks"):
+            getattr(st, nme).copy_(ro[nme][:, lo:hi])
+        st.to(DEV)
+        st.compute_returns(ro["next_value"][lo:hi].to(DEV), cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"],
+                           cfg["use_proper_time_limits"], schedule=1)
+        agent = algo.PPO(pol, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
+                         cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"], max_grad_norm=cfg["max_grad_norm"],
+                         use_clipped_value_loss=cfg.get("use_clipped_value_loss", True))
+        agent.set_distributed(world, r, (lo, hi), N)
+        torch.manual_seed(7)
+        ranks.append(dict(pol=pol, st=st, agent=agent, rng=torch.get_rng_state(),
+                          gen=agent.sharded_steps(pol.runtime(), st)))
+    results = [None] * world
+    while any(r["gen"] is not None for r in ranks):
+        pend = []
+        for i, r in enumerate(ranks):
+            torch.set_rng_state(r["rng"])          # every rank has its own copy of the CPU generator
+            try:
+                pend.append(next(r["gen"]))
+            except StopIteration as done:
+                results[i] = done.value
+                r["gen"] = None
+            r["rng"] = torch.get_rng_state()
+        if pend:
+            assert len(pend) == world
+            total = torch.stack([t.clone() for t in pend]).sum(0)
+            for t in pend:
+                t.copy_(total)
+    return case, cfg, ranks, results
+
+
+@pytest.mark.parametrize("name,world", [("C3s", 2), ("C3u", 4), ("C3", 4), ("C1s", 1)])
+def test_sharded_update_equals_single_device(name, world):
+    if name == "C1s":
+        pytest.skip("N = 1 cannot be sharded")
+    case, cfg, ranks, results = _sharded_lockstep(name, world)
+    full = name == "C3"
+    for res in results:
+        np.testing.assert_allclose(np.array(res), case["losses"], rtol=2e-4 if full else 1e-4, atol=2e-6)
+    # parameters stay bit-identical across ranks ...
+    p0 = dict(ranks[0]["pol"].named_parameters())
+    for r in ranks[1:]:
+        for k, p in r["pol"].named_parameters():
+            assert torch.equal(p, p0[k]), k
+    # ... and equal the single-device reference result up to summation order
+    for k, p in p0.items():
+        helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2 if full else 1e-4, atol=1e-6,
+                                     what="final " + k, elem_frac=0.1 if full else 0.0)
