@@ -125,10 +125,20 @@ typedef struct {
     int32_t vecA;       /* 0 scalar, 1 four consecutive r contiguous+aligned, 2 four consecutive rows */
     int64_t split_stride;
     int32_t vecB;       /* 0 scalar, 1 four consecutive columns contiguous+aligned, 2 four consecutive r */
-    int32_t tile;       /* 0 auto, else tile: 32 / 64 / 128 (128 x tile) or 65 (64 x 64) */
+    int32_t tile;       /* 0 auto, else SIMT tile: 32 / 64 / 128 (128 x tile) or 65 (64 x 64); 1000 / 1001 force engine */
+    int32_t tc_chunk;   /* tensor-core engine: k-blocks (32 reduction indices each) accumulated in TMEM before
+                           the partial sum is drained into fp32 registers (the tensor core's accumulator
+                           truncates; short chains keep long, cancelling reductions exact enough).  0 = 8 */
+    int32_t pad_;
 } a2cb_gemm_t;
 
 int a2cb_gemm(const a2cb_gemm_t* desc, a2cb_stream_t stream);
+/* Engine behind a2cb_gemm: 1 = tcgen05 tensor cores (3xTF32 split operands, chunked fp32 TMEM
+ * accumulation) wherever supported; 0 = exact-fp32 SIMT engine; 2 (default) = per-descriptor choice
+ * from measured crossover points.  Also A2CB_GEMM=simt|tc|auto, or per descriptor tile = 1000 (force
+ * tensor cores) / 1001 (force SIMT). */
+int a2cb_set_gemm_mode(int32_t mode);
+int a2cb_get_gemm_mode(void);
 /* dst[e] (+)= act( sum_{s < splits} src[s * stride + e] + bias[e % ncols] ),  e in [0, count)
  * (bias may be NULL; act: 0 none, 1 relu, 2 tanh) */
 int a2cb_reduce_splits(float* dst, const float* src, int64_t count, int64_t stride, int32_t splits,

@@ -128,6 +128,7 @@ def resolve(plan, arena):
         g.batch_offC[z], g.batch_offM[z] = plan.batch_offC[z], plan.batch_offM[z]
     g.splits, g.split_stride = plan.splits, plan.split_stride
     g.vecA, g.vecB, g.tile = plan.vecA, plan.vecB, plan.tile
+    g.tc_chunk = plan.tc_chunk
     return g
 
 

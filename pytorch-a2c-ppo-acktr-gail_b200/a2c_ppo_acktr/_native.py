@@ -31,6 +31,8 @@ _SIGNATURES = {
     "a2cb_abi_version": (c_int, []),
     "a2cb_last_error": (ctypes.c_char_p, []),
     "a2cb_launch_count": (c_i64, []),
+    "a2cb_set_gemm_mode": (c_int, [c_int]),
+    "a2cb_get_gemm_mode": (c_int, []),
     "a2cb_returns_scan": (c_int, [c_void_p] * 6 + [c_int, c_i64, c_f64, c_f64, c_int, c_int, c_int, c_void_p]),
     "a2cb_gather_rows": (c_int, [ctypes.POINTER(GatherField), c_int, c_void_p, c_i64, c_int, c_i64, c_i64, c_void_p]),
 }
@@ -73,6 +75,11 @@ def lib():
 def check(rc, what):
     if rc != 0:
         raise NativeError("%s failed (%d): %s" % (what, rc, lib().a2cb_last_error().decode()))
+
+
+def set_gemm_mode(mode):
+    """0: exact-fp32 SIMT engine; 1: tcgen05 3xTF32 engine everywhere; 2: automatic choice (default)."""
+    check(lib().a2cb_set_gemm_mode(int(mode)), "a2cb_set_gemm_mode")
 
 
 def launch_count():

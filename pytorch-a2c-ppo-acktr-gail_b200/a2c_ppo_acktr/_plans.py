@@ -42,10 +42,14 @@ class GemmDesc(ctypes.Structure):
         ("alpha", c_f32), ("batch", c_i32),
         ("batch_offA", c_i64 * 4), ("batch_offB", c_i64 * 4), ("batch_offC", c_i64 * 4), ("batch_offM", c_i64 * 4),
         ("splits", c_i32), ("vecA", c_i32), ("split_stride", c_i64), ("vecB", c_i32), ("tile", c_i32),
+        ("tc_chunk", c_i32), ("pad_", c_i32),
     ]
 
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+# Weight gradients sum long, heavily cancelling series: keep their tensor-core accumulation chains short
+# (2 k-blocks = 64 reduction indices per TMEM chain, then an fp32 round-to-nearest add in registers).
+WGRAD_CHUNK = 2
 
 
 def aff(d1, d2, s0, s1, s2):
@@ -103,6 +107,7 @@ class Plan(object):
         self.alpha = kw.pop("alpha", 1.0)
         self.accumulate = kw.pop("accumulate", 0)
         self.tile = kw.pop("tile", 0)
+        self.tc_chunk = kw.pop("tc_chunk", 0)
         self.flops = 2 * self.M * self.N * self.K * self.batch
         assert not kw, kw
 
@@ -247,7 +252,7 @@ def conv_wgrad(cv, B, src, gout, dw, db, a_u8=False, gather=False, splits=1, par
     return Plan(cv.name + ".wgrad", src, (gout[0], gout[1] + cv.gout_base), C, cv.K, cv.cout, B * cv.oh * cv.ow,
                 rowA=cv.red_in(), redA=cv.row_in(), redB=cv.row_gout(), colB=plain(1),
                 rowC=row_w, colC=plain(cv.K), ones=ones, ones_stride=1, a_u8=a_u8, gather_red=gather,
-                vecA=vecA, vecB=1 if cv.cout % 4 == 0 else 0, **kw)
+                vecA=vecA, vecB=1 if cv.cout % 4 == 0 else 0, tc_chunk=WGRAD_CHUNK, **kw)
 
 
 def conv_dgrad(cv, B, gout, w, gin, gin_geom, mask):
@@ -334,4 +339,5 @@ def linear_wgrad(ln, B, x, gy, dw, db, x_stride=None, gy_stride=None, splits=1, 
                 rowA=plain(1), redA=plain(xs), redB=plain(gs), colB=plain(1),
                 rowC=ln.in_perm, colC=plain(ln.d_in), ones=ones if db is not None else None, ones_stride=1,
                 vecA=2 if (ln.d_in % 4 == 0 and xs % 4 == 0) else 0,
-                vecB=1 if (ln.d_out % 4 == 0 and gs % 4 == 0) else 0, accumulate=accumulate, **kw)
+                vecB=1 if (ln.d_out % 4 == 0 and gs % 4 == 0) else 0, accumulate=accumulate,
+                tc_chunk=WGRAD_CHUNK, **kw)

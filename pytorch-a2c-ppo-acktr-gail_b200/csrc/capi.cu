@@ -68,6 +68,13 @@ int a2cb_gemm(const a2cb_gemm_t* desc, a2cb_stream_t stream) {
     return gemm(*reinterpret_cast<const GemmDesc*>(desc), (cudaStream_t)stream);
 }
 
+int a2cb_set_gemm_mode(int32_t mode) {
+    A2CB_REQUIRE(mode >= 0 && mode <= 2, "set_gemm_mode: 0 (fp32 SIMT), 1 (tcgen05 3xTF32) or 2 (auto)");
+    set_gemm_mode(mode);
+    return A2CB_OK;
+}
+int a2cb_get_gemm_mode(void) { return gemm_mode(); }
+
 int a2cb_reduce_splits(float* dst, const float* src, int64_t count, int64_t stride, int32_t splits,
                        int32_t accumulate, const float* bias, int32_t ncols, int32_t act, a2cb_stream_t stream) {
     A2CB_REQUIRE(dst && src && count >= 0 && splits >= 1, "reduce_splits: bad argument");

@@ -18,6 +18,11 @@ int gather_rows(const GatherField* fields, int n_fields, const int64_t* idx, lon
 // gemm.cu
 struct GemmDesc;
 int gemm(const GemmDesc& g, cudaStream_t st);
+int gemm_mode();
+void set_gemm_mode(int m);
+// gemm_tc.cu
+bool gemm_tc_supported(const GemmDesc& g);
+int gemm_tc(const GemmDesc& g, cudaStream_t st);
 int reduce_splits(float* dst, const float* src, long count, long stride, int splits, int accumulate,
                   const float* bias, int ncols, int act, cudaStream_t st);
 

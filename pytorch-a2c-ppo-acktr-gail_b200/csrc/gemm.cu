@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "decls.cuh"
 #include "gemm.cuh"
+#include <stdlib.h>
 
 namespace a2cb {
 
@@ -310,6 +311,28 @@ static void launch_tile(const GemmDesc& g, cudaStream_t st) {
     else gemm_kernel<BM, BN, TM, TN, 0><<<grid, kNT, 0, st>>>(g);
 }
 
+// 0: fp32 SIMT engine only; 1: tensor-core (tcgen05, 3xTF32) engine wherever it applies;
+// 2 (default): per-descriptor choice between the two from measured crossover points.
+static int g_gemm_mode = -1;
+int gemm_mode() {
+    if (g_gemm_mode < 0) {
+        const char* e = getenv("A2CB_GEMM");
+        g_gemm_mode = 2;
+        if (e && (e[0] == 's' || e[0] == 'S')) g_gemm_mode = 0;
+        else if (e && (e[0] == 't' || e[0] == 'T')) g_gemm_mode = 1;
+    }
+    return g_gemm_mode;
+}
+void set_gemm_mode(int m) { g_gemm_mode = (m < 0 || m > 2) ? 2 : m; }
+
+// Measured on B200 (tools/layer_bench.py, profiles/): with skinny outputs (N <= 64 channels) and
+// reduction-contiguous operands the tensor-core engine wins from a few thousand rows upwards; the
+// transposed-loader shapes (weight gradients) and the wide fc layers are still faster on the SIMT
+// engine, whose split-K partials also keep their long reductions in round-to-nearest fp32.
+static bool prefer_tc(const GemmDesc& g) {
+    return g.vecA != 2 && g.vecB != 1 && g.N <= 64 && g.N >= 16 && g.M >= 4096 && g.K >= 64;
+}
+
 int gemm(const GemmDesc& g, cudaStream_t st) {
     A2CB_REQUIRE(g.A && g.B && g.C, "gemm: null operand");
     A2CB_REQUIRE(g.M >= 0 && g.N >= 0 && g.K >= 0, "gemm: negative extent");
@@ -326,7 +349,11 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
     A2CB_REQUIRE(g.vecB != 1 || g.N % 4 == 0, "gemm: vecB=1 needs N %% 4 == 0");
     A2CB_REQUIRE(g.vecB != 2 || g.K % 4 == 0, "gemm: vecB=2 needs K %% 4 == 0");
     if (g.M + g.ones_row == 0 || g.N == 0) return A2CB_OK;
-    int bn = g.tile;
+    if (g.tile != 1001 && gemm_tc_supported(g)) {
+        const int mode = gemm_mode();
+        if (g.tile == 1000 || mode == 1 || (mode == 2 && prefer_tc(g))) return gemm_tc(g, st);
+    }
+    int bn = g.tile >= 1000 ? 0 : g.tile;
     if (bn == 0) {
         bn = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
         // small problems: prefer 64x64 tiles over 128x128 when the big tile would leave most SMs idle

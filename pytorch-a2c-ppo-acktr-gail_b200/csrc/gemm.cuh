@@ -38,6 +38,8 @@ struct GemmDesc {
     int64_t split_stride;
     int32_t vecB;         // 0 scalar, 1 four consecutive columns contiguous & aligned
     int32_t tile;         // 0 auto, else preferred BN (32 / 64 / 128)
+    int32_t tc_chunk;     // tensor-core engine: k-blocks (of 32) per TMEM accumulation chain, 0 = default 8
+    int32_t pad_;
 };
 
 }  // namespace a2cb

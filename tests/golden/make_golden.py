@@ -36,6 +36,17 @@ def summary(t):
     return np.concatenate([[f.sum().item(), f.norm().item(), float(n)], f[pos].numpy()])
 
 
+DENSE = 4096
+
+
+def dense(t):
+    """DENSE strided values of a tensor (fp32) -- enough for a rel-L2 estimate of large tensors."""
+    f = t.detach().reshape(-1).float()
+    n = f.numel()
+    pos = torch.linspace(0, n - 1, min(DENSE, n)).long()
+    return f[pos].numpy().copy()
+
+
 def space(action):
     kind, n = action
     return Discrete(n) if kind == "discrete" else Box(n)
@@ -269,11 +280,14 @@ def case_update(name):
     out["losses"] = np.array([vl, al, ent], dtype=np.float64)
     for k, v in first["grads"].items():
         out["step1_grad_" + k] = summary(v)
+        out["step1_graddense_" + k] = dense(v)
     for k, v in first["params"].items():
         out["step1_param_" + k] = summary(v)
+        out["step1_paramdense_" + k] = dense(v)
     small = sum(p.numel() for p in pol.parameters()) < 20000
     for k, v in pol.state_dict().items():
         out["final_" + k] = summary(v)
+        out["finaldense_" + k] = dense(v)
         if small:
             out["finalfull_" + k] = v.numpy().copy()
     # second update on the same storage (optimizer state carried over)

@@ -23,6 +23,28 @@ def summary(t):
     return np.concatenate([[f.sum().item(), f.norm().item(), float(n)], f[pos].numpy()])
 
 
+DENSE = 4096
+
+
+def dense(t):
+    f = t.detach().cpu().reshape(-1).float()
+    n = f.numel()
+    pos = torch.linspace(0, n - 1, min(DENSE, n)).long()
+    return f[pos].numpy().copy()
+
+
+def rel_l2(case, prefix, named):
+    """rel-L2 distance ||got - want|| / ||want|| over the dense samples of ALL tensors together
+    (the parameter-vector metric of SURVEY.md section 8c)."""
+    num = den = 0.0
+    for k, v in named.items():
+        want = case[prefix + k].astype(np.float64)
+        got = dense(v).astype(np.float64)
+        num += float(((got - want) ** 2).sum())
+        den += float((want ** 2).sum())
+    return (num / max(den, 1e-300)) ** 0.5
+
+
 def case_config(case):
     cfg = json.loads(str(case["config"]))
     cfg["obs_shape"] = tuple(cfg["obs_shape"])

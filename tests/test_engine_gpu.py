@@ -16,6 +16,14 @@ from a2c_ppo_acktr import _plans as P  # noqa: E402
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=["tcgen05", "simt"], autouse=True)
+def gemm_engine(request):
+    """Every test of this file runs on both engines behind a2cb_gemm."""
+    _native.set_gemm_mode(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    _native.set_gemm_mode(2)
+
+
 def run_plan(plan, bufs, idx=None):
     """Runs one plan on the GPU on copies of the numpy buffers; returns the updated buffers."""
     arena = _engine.Arena(torch.device(DEV))
@@ -41,7 +49,7 @@ def rand_affine(rng, n, max_off):
 @pytest.mark.parametrize("M,N,K,tile", [(1, 1, 1, 0), (129, 7, 33, 0), (300, 33, 70, 64), (257, 130, 19, 128),
                                         (64, 64, 64, 32), (500, 96, 128, 0)])
 @pytest.mark.parametrize("variant", ["plain", "epilogue", "ones", "batch"])
-def test_gemm_random_maps_vs_emulator(M, N, K, tile, variant):
+def test_gemm_random_maps_vs_emulator(M, N, K, tile, variant, gemm_engine):
     rng = np.random.default_rng(M * 1000 + N * 10 + K)
     rowA, spanRA = rand_affine(rng, M, 0)
     redA, spanKA = rand_affine(rng, K, 0)
@@ -71,8 +79,10 @@ def test_gemm_random_maps_vs_emulator(M, N, K, tile, variant):
     want = {k: v.copy() for k, v in bufs.items()}
     P.emulate(plan, want)
     got = run_plan(plan, bufs)
-    np.testing.assert_allclose(got["C"], want["C"], rtol=2e-5, atol=2e-5)
-    np.testing.assert_allclose(got["ones"], want["ones"], rtol=2e-5, atol=2e-5)
+    # 3xTF32 drops the lo*lo term and rounds lo to 11 bits: ~2^-21 per product, sums of K = 128 N(0,1) products
+    atol = 1e-4 if gemm_engine == "tcgen05" else 2e-5
+    np.testing.assert_allclose(got["C"], want["C"], rtol=2e-5, atol=atol)
+    np.testing.assert_allclose(got["ones"], want["ones"], rtol=2e-5, atol=atol)
 
 
 def test_gemm_split_k_and_reduce():
