@@ -227,6 +227,9 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_GRAD_NORM 4
 #define A2CB_OP_OPTIM 5
 #define A2CB_OP_FILL 6
+#define A2CB_OP_GRU_INIT 7
+#define A2CB_OP_GRU_FWD 8
+#define A2CB_OP_GRU_BWD 9
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -241,6 +244,33 @@ typedef struct { void* dst; int64_t bytes; int32_t value; int32_t pad_; } a2cb_f
 typedef struct { int32_t kind; int32_t flags; const void* desc; } a2cb_op_t;
 
 int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * GRU recurrence of NNBase._forward_gru        a2c_ppo_acktr/model.py:111-166 (+ nn.GRU, :89-95)
+ * Gate kernels for one time-step of a [T, N] sequence (rows time-major t*N + n); the two matmuls
+ * (gi for all rows, gh per step) are a2cb_gemm descriptors in the same op list.  Episode boundaries
+ * are handled by multiplying the carried state with masks[t] inside the kernels (equivalent to the
+ * reference's per-segment cuDNN calls, without its host sync at model.py:133-137).
+ *   which = A2CB_OP_GRU_INIT: hm[0] = h0 * mask[0]
+ *           A2CB_OP_GRU_FWD : step t forward (saves r, z, n when non-NULL), writes hm[t+1]
+ *           A2CB_OP_GRU_BWD : step t backward-through-time: dgi[t], dgh[t], dcarry = dh * z
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    const float* gi;
+    const float* gh;
+    float* hm;
+    const float* h0;
+    const float* masks;
+    const int64_t* idx;
+    float* out;
+    float* r; float* z; float* n;
+    const float* dout;
+    float* dgi; float* dgh;
+    float* dcarry;
+    int32_t T, N, H, t;
+} a2cb_gru_t;
+
+int a2cb_gru_op(int32_t which, const a2cb_gru_t* desc, a2cb_stream_t stream);
 
 #ifdef __cplusplus
 }

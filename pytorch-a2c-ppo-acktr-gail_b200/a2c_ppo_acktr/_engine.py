@@ -19,6 +19,7 @@ from . import _plans as P
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
 OP_GEMM, OP_REDUCE, OP_LOSS, OP_GRAD_NORM, OP_OPTIM, OP_FILL = 1, 2, 3, 4, 5, 6
+OP_GRU_INIT, OP_GRU_FWD, OP_GRU_BWD = 7, 8, 9
 RUNTIME_IDX = 1
 SENTINEL = 1          # non-NULL placeholder for "use the runtime minibatch index list"
 
@@ -56,6 +57,20 @@ class FillDesc(ctypes.Structure):
     _fields_ = [("dst", c_vp), ("bytes", c_i64), ("value", c_i32), ("pad_", c_i32)]
 
 
+class GruDesc(ctypes.Structure):
+    """Mirror of a2cb_gru_t."""
+    _fields_ = [("gi", c_vp), ("gh", c_vp), ("hm", c_vp), ("h0", c_vp), ("masks", c_vp), ("idx", c_vp),
+                ("out", c_vp), ("r", c_vp), ("z", c_vp), ("n", c_vp), ("dout", c_vp), ("dgi", c_vp), ("dgh", c_vp),
+                ("dcarry", c_vp), ("T", c_i32), ("N", c_i32), ("H", c_i32), ("t", c_i32)]
+
+
+class RawOp(object):
+    """A non-GEMM op in a plan list: kind + symbolic fields resolved against the arena."""
+
+    def __init__(self, kind, fields, ints, runtime_idx=False, name="op"):
+        self.kind, self.fields, self.ints, self.runtime_idx, self.name = kind, fields, ints, runtime_idx, name
+
+
 class Op(ctypes.Structure):
     _fields_ = [("kind", c_i32), ("flags", c_i32), ("desc", c_vp)]
 
@@ -70,6 +85,7 @@ _native.register({
     "a2cb_grad_norm": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "a2cb_optim_step": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp] + [c_f32] * 8 + [c_i32, c_vp]),
     "a2cb_run_ops": (c_i32, [ctypes.POINTER(Op), c_i32, c_vp, c_vp]),
+    "a2cb_gru_op": (c_i32, [c_i32, ctypes.POINTER(GruDesc), c_vp]),
 })
 
 
@@ -164,6 +180,16 @@ class Program(object):
         return desc
 
     def add_plan(self, plan, arena):
+        if isinstance(plan, RawOp):
+            d = GruDesc()
+            for k, ref in plan.fields.items():
+                setattr(d, k, arena.ptr(ref))
+            for k, v in plan.ints.items():
+                setattr(d, k, v)
+            if plan.runtime_idx:
+                d.idx = SENTINEL
+            self.add(plan.kind, d, RUNTIME_IDX if plan.runtime_idx else 0)
+            return
         flags = RUNTIME_IDX if (plan.gather_row or plan.gather_red) else 0
         self.add(OP_GEMM, resolve(plan, arena), flags)
         self.plan_names.append(plan.name)
@@ -274,8 +300,13 @@ class ParamLayout(object):
 class NetBuilder(object):
     """Builds forward / backward plan lists for one policy spec and one batch size."""
 
-    def __init__(self, spec, layout, B, obs_buf, obs_code, gather, tag):
+    def __init__(self, spec, layout, B, obs_buf, obs_code, gather, tag, seq=None, masks=("masks_in", 0),
+                 hxs=("hxs_in", 0), keep_gates=True):
         self.spec, self.L, self.B = spec, layout, B
+        # recurrent policies see the batch as a [T, N] sequence, rows time-major (model.py:119-126)
+        self.seqT, self.seqN = seq if seq is not None else (1, B)
+        assert self.seqT * self.seqN == B
+        self.masks_ref, self.hxs_ref, self.keep_gates = masks, hxs, keep_gates
         self.obs = obs_buf          # arena name of the observation source
         self.obs_code = obs_code    # a_dtype of the first layer: 0 raw fp32, 1 uint8/255, 2 fp32/255
         self.gather = gather
@@ -348,10 +379,12 @@ class NetBuilder(object):
         return plans
 
     # ---- MLP ----
-    def mlp_forward(self):
+    def mlp_forward(self, x=None, d_in=None):
         B, s = self.B, self.spec
-        H, d = s.hidden, s.obs_shape[0]
-        x = (self.obs, 0)
+        H = s.hidden
+        from_obs = x is None
+        d = d_in if d_in is not None else s.obs_shape[0]
+        x = x if x is not None else (self.obs, 0)
         ha1, ha2 = self.buf("ha1", B * H), self.buf("ha2", B * H)
         hc1, hc2 = self.buf("hc1", B * H), self.buf("hc2", B * H)
         z = self.buf("z", B * self.zs)
@@ -361,7 +394,7 @@ class NetBuilder(object):
         p0a = P.linear_forward(l0a, B, x, *self.wb("actor0"), ha1, act=P.ACT_TANH)
         p0c = P.linear_forward(l0c, B, x, *self.wb("critic0"), hc1, act=P.ACT_TANH)
         for p in (p0a, p0c):
-            p.gather_row = self.gather
+            p.gather_row = self.gather and from_obs
             p.vecA = 1 if d % 4 == 0 else 0
         plans = [p0c, P.linear_forward(l2c, B, hc1, *self.wb("critic2"), hc2, act=P.ACT_TANH),
                  p0a, P.linear_forward(l2a, B, ha1, *self.wb("actor2"), ha2, act=P.ACT_TANH)]
@@ -376,8 +409,11 @@ class NetBuilder(object):
         return [P.linear_forward(crit, B, hc2, ("P", w0), ("P", b0), z, y_stride=self.zs),
                 P.linear_forward(mean, B, ha2, ("P", w0 + H), ("P", b0 + 1), (z[0], 1), y_stride=self.zs)]
 
-    def mlp_backward(self):
-        B, H, A, d = self.B, self.spec.hidden, self.spec.num_actions, self.spec.obs_shape[0]
+    def mlp_backward(self, x=None, d_in=None, gx=None):
+        """gx: optional buffer receiving the gradient w.r.t. the trunk input (recurrent MLP)."""
+        B, H, A = self.B, self.spec.hidden, self.spec.num_actions
+        from_obs = x is None
+        d = d_in if d_in is not None else self.spec.obs_shape[0]
         l0a, l2a, l0c, l2c = self.mlp_layers
         w0, b0 = self.L.layers["heads"]
         dz = (self.n("dz"), 0)
@@ -386,7 +422,7 @@ class NetBuilder(object):
         ga2, ga1 = self.buf("ga2", B * H), self.buf("ga1", B * H)
         crit = P.Linear("critic_linear", H, 1)
         mean = P.Linear("head", H, A)
-        x = (self.obs, 0)
+        x = x if x is not None else (self.obs, 0)
         plans = [
             P.linear_wgrad(crit, B, hc2, dz, ("G", w0), ("G", b0), gy_stride=self.zs),
             P.linear_dgrad(crit, B, dz, ("P", w0), gc2, mask=hc2, mask_mode=2, gy_stride=self.zs),
@@ -400,9 +436,63 @@ class NetBuilder(object):
             P.linear_wgrad(l0a, B, x, ga1, *self.gwb("actor0")),
         ]
         for p in (plans[4], plans[9]):
-            p.gather_red = self.gather
-            p.vecA = 0          # gathered rows: row-contiguity of x across the batch index does not apply
+            p.gather_red = self.gather and from_obs
+            if self.gather and from_obs:
+                p.vecA = 0      # gathered rows: row-contiguity of x across the batch index does not apply
+        if gx is not None:
+            plans.append(P.linear_dgrad(l0c, B, gc1, ("P", self.L.layers["critic0"][0]), gx))
+            plans.append(P.linear_dgrad(l0a, B, ga1, ("P", self.L.layers["actor0"][0]), gx, accumulate=1))
         return plans
+
+    # ---- GRU (model.py:111-166) ----
+    def gru_forward(self, x, d_in):
+        """x: (buffer, offset) of the [B, d_in] input rows.  Returns (ops, output ref)."""
+        B, H, T, N = self.B, self.spec.hidden, self.seqT, self.seqN
+        e = self.L.entries
+        wih, whh = ("P", e["base.gru.weight_ih_l0"][0]), ("P", e["base.gru.weight_hh_l0"][0])
+        bih, bhh = ("P", e["base.gru.bias_ih_l0"][0]), ("P", e["base.gru.bias_hh_l0"][0])
+        gi, gh = self.buf("gru_gi", B * 3 * H), self.buf("gru_gh", B * 3 * H)
+        hm, out = self.buf("gru_hm", B * H), self.buf("gru_out", B * H)
+        fields = dict(gi=gi, gh=gh, hm=hm, masks=self.masks_ref, out=out)
+        if self.keep_gates:
+            fields.update(r=self.buf("gru_r", B * H), z=self.buf("gru_z", B * H), n=self.buf("gru_n", B * H))
+        self.gru_in = P.Linear("gru_ih", d_in, 3 * H)
+        self.gru_hh = P.Linear("gru_hh", H, 3 * H)
+        ops = [P.linear_forward(self.gru_in, B, x, wih, bih, gi),
+               RawOp(OP_GRU_INIT, dict(hm=hm, h0=self.hxs_ref, masks=self.masks_ref), dict(T=T, N=N, H=H, t=0),
+                     self.gather, "gru.init")]
+        for t in range(T):
+            ops.append(P.linear_forward(self.gru_hh, N, (hm[0], t * N * H), whh, bhh, (gh[0], t * N * 3 * H)))
+            ops[-1].name = "gru_hh.fwd"
+            ops.append(RawOp(OP_GRU_FWD, fields, dict(T=T, N=N, H=H, t=t), self.gather, "gru.gates"))
+        return ops, out
+
+    def gru_backward(self, x, d_in, dout, dx=None, dx_mask=None):
+        """dout: gradient w.r.t. the GRU outputs [B, H].  Writes the GRU parameter gradients and, when
+        dx is given, the gradient w.r.t. the input rows (masked by relu' of dx_mask)."""
+        B, H, T, N = self.B, self.spec.hidden, self.seqT, self.seqN
+        e = self.L.entries
+        whh, wih = ("P", e["base.gru.weight_hh_l0"][0]), ("P", e["base.gru.weight_ih_l0"][0])
+        dgi, dgh = self.buf("gru_dgi", B * 3 * H), self.buf("gru_dgh", B * 3 * H)
+        dcarry = self.buf("gru_dcarry", N * H)
+        names = ("gi", "gh", "hm", "out", "r", "z", "n")
+        fields = {k: (self.n("gru_" + k), 0) for k in names}
+        fields.update(masks=self.masks_ref, dout=dout, dgi=dgi, dgh=dgh, dcarry=dcarry)
+        ops = []
+        for t in range(T - 1, -1, -1):
+            ops.append(RawOp(OP_GRU_BWD, fields, dict(T=T, N=N, H=H, t=t), self.gather, "gru.gates_bwd"))
+            if t > 0:
+                p = P.linear_dgrad(self.gru_hh, N, (dgh[0], t * N * 3 * H), whh, dcarry, accumulate=1)
+                p.name = "gru_hh.dgrad"
+                ops.append(p)
+        hm = (self.n("gru_hm"), 0)
+        ops.append(P.linear_wgrad(self.gru_hh, B, hm, dgh, ("G", e["base.gru.weight_hh_l0"][0]),
+                                  ("G", e["base.gru.bias_hh_l0"][0])))
+        ops.append(P.linear_wgrad(self.gru_in, B, x, dgi, ("G", e["base.gru.weight_ih_l0"][0]),
+                                  ("G", e["base.gru.bias_ih_l0"][0])))
+        if dx is not None:
+            ops.append(P.linear_dgrad(self.gru_in, B, dgi, wih, dx, mask=dx_mask, mask_mode=1 if dx_mask else 0))
+        return ops
 
     # ---- heads (CNN: one [1+A, H] matrix on the shared feature) ----
     def cnn_heads_forward(self, h):
@@ -411,26 +501,54 @@ class NetBuilder(object):
         part = self.buf("part_heads_fwd", sp * self.B * self.zs) if sp > 1 else None
         return [P.linear_forward(self.heads, self.B, h, w, b, (self.n("z"), 0), splits=sp, partial=part)]
 
-    def cnn_heads_backward(self, h):
+    def cnn_heads_backward(self, h, relu_mask=True):
         B, H = self.B, self.spec.hidden
         dz = self.buf("dz", B * self.zs)
         gh = self.buf("gh", B * H)
         gw, gb = self.gwb("heads")
         return [P.linear_wgrad(self.heads, B, h, dz, gw, gb),
-                P.linear_dgrad(self.heads, B, dz, ("P", self.L.layers["heads"][0]), gh, mask=h, mask_mode=1)], gh
+                P.linear_dgrad(self.heads, B, dz, ("P", self.L.layers["heads"][0]), gh,
+                               mask=h if relu_mask else None, mask_mode=1 if relu_mask else 0)], gh
 
     def forward_plans(self):
-        if self.spec.cnn:
+        s = self.spec
+        if s.cnn:
             plans, h = self.cnn_forward()
+            if s.recurrent:
+                gops, feat = self.gru_forward(h, s.hidden)
+                return plans + gops + self.cnn_heads_forward(feat)
             return plans + self.cnn_heads_forward(h)
+        if s.recurrent:
+            gops, feat = self.gru_forward((self.obs, 0), s.obs_shape[0])
+            # the GRU reads the (possibly gathered) observation rows itself; the trunks read its output
+            gops[0].gather_row = self.gather
+            gops[0].vecA = 1 if s.obs_shape[0] % 4 == 0 else 0
+            plans, (hc2, ha2) = self.mlp_forward(x=feat, d_in=s.hidden)
+            return gops + plans + self.mlp_heads_forward(hc2, ha2)
         plans, (hc2, ha2) = self.mlp_forward()
         return plans + self.mlp_heads_forward(hc2, ha2)
 
     def backward_plans(self):
-        if self.spec.cnn:
-            hp, gh = self.cnn_heads_backward((self.n("h"), 0))
+        s = self.spec
+        if s.cnn:
+            h = (self.n("h"), 0)
+            if s.recurrent:
+                feat = (self.n("gru_out"), 0)
+                hp, gfeat = self.cnn_heads_backward(feat, relu_mask=False)
+                gx = self.buf("gru_dx", self.B * s.hidden)
+                return hp + self.gru_backward(h, s.hidden, gfeat, dx=gx, dx_mask=h) + self.cnn_backward(gx)
+            hp, gh = self.cnn_heads_backward(h)
             return hp + self.cnn_backward(gh)
         self.buf("dz", self.B * self.zs)
+        if s.recurrent:
+            feat = (self.n("gru_out"), 0)
+            gfeat = self.buf("gru_dout", self.B * s.hidden)
+            plans = self.mlp_backward(x=feat, d_in=s.hidden, gx=gfeat)
+            gb = self.gru_backward((self.obs, 0), s.obs_shape[0], gfeat)
+            w = gb[-1]                       # dW_ih reads the (possibly gathered) observation rows
+            w.gather_red = self.gather
+            w.vecA = 0 if self.gather else w.vecA
+            return plans + gb
         return self.mlp_backward()
 
 
@@ -485,21 +603,39 @@ class PolicyRuntime(object):
         return ("P", self.L.entries["dist.logstd._bias"][0])
 
     # -- forward only -------------------------------------------------------
-    def forward(self, obs, hxs, masks, keep_for_backward=False):
-        if self.spec.recurrent:
-            raise _native.NativeError("recurrent (GRU) policies are not built yet in this round")
+    def _bind_inputs(self, obs, hxs, masks):
+        """Binds the caller's tensors into the arena; returns (B, seq, key part)."""
         if not obs.is_cuda:
             raise _native.NativeError("observations must be CUDA tensors; there is no CPU fallback")
         obs = obs.contiguous()
         B = obs.shape[0]
         if tuple(obs.shape[1:]) != self.spec.obs_shape:
             raise ValueError("expected observations of shape [B, %s], got %s" % (self.spec.obs_shape, tuple(obs.shape)))
-        code = self.obs_code(obs)
-        key = ("fwd", B, obs.data_ptr(), code)
-        ent = self.cache.get(key)
         self.arena.bind("obs_in", obs.view(-1))
+        self.keep["obs"] = obs
+        seq, extra = None, ()
+        if self.spec.recurrent:
+            N = hxs.shape[0]
+            if B % N != 0:
+                raise ValueError("batch of %d rows is not a whole number of %d-environment steps" % (B, N))
+            hx = hxs.detach().to(torch.float32).contiguous()
+            mk = masks.detach().to(torch.float32).contiguous().view(-1)
+            if not (hx.is_cuda and mk.is_cuda):
+                raise _native.NativeError("recurrent state and masks must be CUDA tensors")
+            self.arena.bind("hxs_in", hx.view(-1))
+            self.arena.bind("masks_in", mk)
+            self.keep["hxs"], self.keep["masks"] = hx, mk
+            seq, extra = (B // N, N), (hx.data_ptr(), mk.data_ptr(), N)
+        return obs, B, seq, extra
+
+    def forward(self, obs, hxs, masks, keep_for_backward=False):
+        obs, B, seq, extra = self._bind_inputs(obs, hxs, masks)
+        code = self.obs_code(obs)
+        key = ("fwd", B, obs.data_ptr(), code, bool(keep_for_backward)) + extra
+        ent = self.cache.get(key)
         if ent is None:
-            nb = NetBuilder(self.spec, self.L, B, "obs_in", code, False, "b%d_" % B)
+            nb = NetBuilder(self.spec, self.L, B, "obs_in", code, False, "b%d_" % B, seq=seq,
+                            keep_gates=keep_for_backward or not self.spec.recurrent)
             plans = nb.forward_plans()
             self._alloc(nb)
             prog = Program(self.dev)
@@ -507,11 +643,15 @@ class PolicyRuntime(object):
                 prog.add_plan(p, self.arena)
             ent = self._remember(key, (prog.finalize(), nb))
         prog, nb = ent
-        self.keep["obs"] = obs
         prog.run()
         self.forward_token += 1
         z = self.arena.bufs["b%d_z" % B][:B * self.zs].view(B, self.zs)
-        return {"z": z, "hxs": hxs, "builder": nb}
+        out_h = hxs
+        if self.spec.recurrent:
+            T, N = seq
+            H = self.spec.hidden
+            out_h = self.arena.bufs["b%d_gru_out" % B][(T - 1) * N * H:T * N * H].view(N, H).clone()
+        return {"z": z, "hxs": out_h, "builder": nb, "seq": seq}
 
     def _loss_desc(self, B, tag, mode, actions, **kw):
         s = self.spec
@@ -559,11 +699,15 @@ class PolicyRuntime(object):
         tag = "b%d_" % B
         obs = self.keep["obs"]
         code = self.obs_code(obs)
-        key = ("bwd", B, obs.data_ptr(), code)
+        seq, extra = None, ()
+        if self.spec.recurrent:
+            hx, mk = self.keep["hxs"], self.keep["masks"]
+            seq, extra = (B // hx.shape[0], hx.shape[0]), (hx.data_ptr(), mk.data_ptr(), hx.shape[0])
+        key = ("bwd", B, obs.data_ptr(), code) + extra
         ent = self.cache.get(key)
         self.arena.bind("obs_in", obs.view(-1))
         if ent is None:
-            nb = NetBuilder(self.spec, self.L, B, "obs_in", code, False, tag)
+            nb = NetBuilder(self.spec, self.L, B, "obs_in", code, False, tag, seq=seq)
             nb.forward_plans()
             plans = nb.backward_plans()
             self._alloc(nb)
@@ -584,7 +728,7 @@ class PolicyRuntime(object):
 
     # -- fused training step --------------------------------------------------
     def train_program(self, storage, mbs, mode, hyper, adv=None, noise=None, loss_accum=None, use_idx=True,
-                      with_backward=True):
+                      with_backward=True, seq=None):
         """Op list of one minibatch step reading rows of `storage` through the runtime index list:
         forward -> loss epilogue (mode) -> backward.  Optimiser ops are appended by the caller."""
         s = self.spec
@@ -593,7 +737,18 @@ class PolicyRuntime(object):
         code = self.obs_code(obs_flat)
         self.arena.bind("obs_st", obs_flat.view(-1))
         tag = "t%d_" % mbs
-        nb = NetBuilder(s, self.L, mbs, "obs_st", code, use_idx, tag)
+        kw = {}
+        if s.recurrent:
+            # rows of the minibatch are time-major (t * E + e); masks come from the rollout buffer through
+            # the row list, the initial state from `hxs_mb` (filled per minibatch by the caller)
+            assert seq is not None and seq[0] * seq[1] == mbs
+            self.arena.bind("masks_st", storage.masks.view(-1))
+            if use_idx:
+                self.arena.ensure("hxs_mb", seq[1] * s.hidden)
+            else:
+                self.arena.bind("hxs_mb", storage.recurrent_hidden_states[0].contiguous().view(-1))
+            kw = dict(seq=seq, masks=("masks_st", 0), hxs=("hxs_mb", 0))
+        nb = NetBuilder(s, self.L, mbs, "obs_st", code, use_idx, tag, **kw)
         fwd = nb.forward_plans()
         bwd = nb.backward_plans() if with_backward else []
         if not with_backward:

@@ -34,15 +34,15 @@ class A2C_ACKTR():
     def update(self, rollouts):
         policy = self.actor_critic
         rt = policy.runtime()
-        if policy.is_recurrent:
-            raise _native.NativeError("recurrent A2C is not built yet in this round")
         T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         B = T * N
         key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(), B,
+               rollouts.masks.data_ptr(), rollouts.recurrent_hidden_states.data_ptr(),
                self.value_loss_coef, self.entropy_coef, self.max_grad_norm)
         if key != self._prog_key:
             hyper = dict(value_loss_coef=self.value_loss_coef, entropy_coef=self.entropy_coef)
-            prog = rt.train_program(rollouts, B, 1, hyper, use_idx=False)
+            prog = rt.train_program(rollouts, B, 1, hyper, use_idx=False,
+                                    seq=(T, N) if policy.is_recurrent else None)
             self.optimizer._ensure_state()
             rt.add_optimizer_ops(prog, 1, self.optimizer.state1, None, self.max_grad_norm)
             prog.finalize()

@@ -79,12 +79,12 @@ class PPO():
         self.shard = _dist.ShardInfo(world, rank, env_range[0], env_range[1], n_total) if world > 1 else None
         self._prog_key = None
 
-    def _program(self, rt, rollouts, mbs, adv, accum, inv_B=None):
+    def _program(self, rt, rollouts, mbs, adv, accum, inv_B=None, seq=None):
         """(forward + loss + backward) program and the (clip + Adam) program.  Unsharded they are one
         op list; sharded they are separated by the gradient all-reduce."""
         key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(),
                rollouts.value_preds.data_ptr(), rollouts.action_log_probs.data_ptr(), adv.data_ptr(),
-               accum.data_ptr(), mbs, inv_B, self.clip_param, self.value_loss_coef, self.entropy_coef,
+               accum.data_ptr(), mbs, inv_B, seq, rollouts.masks.data_ptr(), self.clip_param, self.value_loss_coef, self.entropy_coef,
                self.use_clipped_value_loss, self.max_grad_norm)
         if key != self._prog_key:
             from .. import _engine
@@ -92,7 +92,7 @@ class PPO():
                          entropy_coef=self.entropy_coef, use_clipped_value_loss=self.use_clipped_value_loss)
             if inv_B is not None:
                 hyper["inv_B"] = inv_B
-            prog = rt.train_program(rollouts, mbs, 0, hyper, adv=adv, loss_accum=accum)
+            prog = rt.train_program(rollouts, mbs, 0, hyper, adv=adv, loss_accum=accum, seq=seq)
             self.optimizer._ensure_state()
             opt = prog if self.shard is None else _engine.Program(rt.dev)
             opt.optim_desc = rt.add_optimizer_ops(opt, 0, self.optimizer.state1, self.optimizer.state2,
@@ -105,9 +105,11 @@ class PPO():
     def update(self, rollouts):
         policy = self.actor_critic
         rt = policy.runtime()
-        if policy.is_recurrent:
-            raise _native.NativeError("recurrent PPO is not built yet in this round")
         T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+        if policy.is_recurrent:
+            if self.shard is not None:
+                raise _native.NativeError("sharded recurrent PPO is not built yet")
+            return self._update_recurrent(rt, rollouts)
         batch_size = T * N
         assert batch_size >= self.num_mini_batch, (
             "PPO requires the number of processes ({}) "
@@ -134,6 +136,40 @@ class PPO():
         self.last_launches = _native.launch_count() - launches0
         num_updates = self.ppo_epoch * self.num_mini_batch
         sums = accum[:3].cpu()          # the update's only device->host synchronisation
+        return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
+
+    def _update_recurrent(self, rt, rollouts):
+        """Recurrent minibatches are whole environments (reference storage.py:145-202): one
+        randperm(N) per epoch, chunks of E = N // num_mini_batch environments, rows time-major."""
+        T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+        assert N >= self.num_mini_batch, (
+            "PPO requires the number of processes ({}) "
+            "to be greater than or equal to the number of "
+            "PPO mini batches ({}).".format(N, self.num_mini_batch))
+        E = N // self.num_mini_batch
+        adv = _adv_normalize(rt, rollouts)
+        accum = rt.arena.ensure("loss_accum", 4)
+        accum.zero_()
+        prog, _ = self._program(rt, rollouts, T * E, adv, accum, seq=(T, E))
+        hxs_mb = rt.arena.bufs["hxs_mb"][:E * rt.spec.hidden].view(E, rt.spec.hidden)
+        h0 = rollouts.recurrent_hidden_states[0]
+        t_off = (torch.arange(T, device=rt.dev, dtype=torch.int64) * N).view(T, 1)
+        launches0 = _native.launch_count()
+        for _ in range(self.ppo_epoch):
+            perm = torch.randperm(N)
+            for start in range(0, N, E):
+                if start + E > N:
+                    raise IndexError("index {} is out of bounds for dimension 0 with size {}".format(N, N))
+                env = perm[start:start + E].to(rt.dev)
+                rows = (t_off + env.view(1, E)).reshape(-1).contiguous()
+                _native.gather_rows([(h0, hxs_mb)], env, E)
+                self.optimizer.configure(prog.optim_desc)
+                prog.run(rows)
+                if self.step_hook is not None:
+                    self.step_hook(self.optimizer.step_count)
+        self.last_launches = _native.launch_count() - launches0
+        num_updates = self.ppo_epoch * self.num_mini_batch
+        sums = accum[:3].cpu()
         return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
 
     def _update_sharded(self, rt, rollouts):

@@ -226,7 +226,7 @@ class Policy(nn.Module):
                     std = self.dist.logstd._bias.detach().t().exp().expand_as(mean)
                     action = torch.normal(mean, std)
             stats = rt.head_stats(z.shape[0], action)
-        return z[:, 0:1].clone(), action, stats["logp"].view(-1, 1), out["hxs"]
+        return z[:, 0:1].clone(), action, stats["logp"].view(-1, 1).clone(), out["hxs"]
 
     def get_value(self, inputs, rnn_hxs, masks):
         with torch.no_grad():
@@ -244,7 +244,7 @@ class Policy(nn.Module):
         with torch.no_grad():
             out = rt.forward(inputs, rnn_hxs, masks)
             stats = rt.head_stats(out["z"].shape[0], action)
-        return out["z"][:, 0:1].clone(), stats["logp"].view(-1, 1), stats["entropy"], out["hxs"]
+        return out["z"][:, 0:1].clone(), stats["logp"].view(-1, 1).clone(), stats["entropy"].clone(), out["hxs"]
 
 
 class _EvaluateActions(torch.autograd.Function):

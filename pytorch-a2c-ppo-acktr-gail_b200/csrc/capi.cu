@@ -4,6 +4,7 @@
 #include "decls.cuh"
 #include "gemm.cuh"
 #include "loss.cuh"
+#include "gru.cuh"
 
 #include <atomic>
 #include <stdarg.h>
@@ -109,6 +110,12 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
                       bc2_sqrt, max_norm, first_step, (cudaStream_t)stream);
 }
 
+int a2cb_gru_op(int32_t which, const a2cb_gru_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc && which >= A2CB_OP_GRU_INIT && which <= A2CB_OP_GRU_BWD, "gru_op: bad argument");
+    static_assert(sizeof(a2cb_gru_t) == sizeof(GruDesc), "a2cb_gru_t and GruDesc must share a layout");
+    return gru_op(which - A2CB_OP_GRU_INIT, *reinterpret_cast<const GruDesc*>(desc), (cudaStream_t)stream);
+}
+
 int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream) {
     A2CB_REQUIRE(n_ops >= 0 && (n_ops == 0 || ops), "run_ops: bad op list");
     cudaStream_t st = (cudaStream_t)stream;
@@ -154,6 +161,14 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
                 const a2cb_fill_t& f = *reinterpret_cast<const a2cb_fill_t*>(op.desc);
                 cudaError_t e = cudaMemsetAsync(f.dst, f.value, (size_t)f.bytes, st);
                 if (e != cudaSuccess) { set_error("run_ops: memset: %s", cudaGetErrorString(e)); rc = A2CB_ERR_CUDA; }
+                break;
+            }
+            case A2CB_OP_GRU_INIT:
+            case A2CB_OP_GRU_FWD:
+            case A2CB_OP_GRU_BWD: {
+                GruDesc d = *reinterpret_cast<const GruDesc*>(op.desc);
+                if (rt) d.idx = idx;
+                rc = gru_op(op.kind - A2CB_OP_GRU_INIT, d, st);
                 break;
             }
             default:

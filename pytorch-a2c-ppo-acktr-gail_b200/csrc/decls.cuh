@@ -41,4 +41,8 @@ int optim_step(int kind, float* p, float* g, float* s1, float* s2, long n, const
                float lr_eff, float eps, float b1, float b2, float omb1, float omb2, float bc2_sqrt,
                float max_norm, int first_step, cudaStream_t st);
 
+// gru.cu
+struct GruDesc;
+int gru_op(int which, const GruDesc& d, cudaStream_t st);   // which: 0 init, 1 forward step, 2 backward step
+
 }  // namespace a2cb

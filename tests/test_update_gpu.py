@@ -42,7 +42,7 @@ def space(action):
     return Discrete(n) if kind == "discrete" else Box(n)
 
 
-@pytest.mark.parametrize("tag", ["cnn", "mlp", "mlp_disc"])
+@pytest.mark.parametrize("tag", ["cnn", "mlp", "mlp_disc", "cnn_gru", "mlp_gru"])
 def test_policy_init_and_forward_vs_golden(tag):
     g = helpers.load("policy")
     pc = POLICY_CASES[tag]
@@ -59,7 +59,12 @@ def test_policy_init_and_forward_vs_golden(tag):
     np.testing.assert_allclose(lp.detach().cpu().numpy(), g[tag + "_logp"], **tol)
     np.testing.assert_allclose(ent.item(), g[tag + "_entropy"], **tol)
     hx1 = torch.from_numpy(g[tag + "_act_hxs_in"]).to(DEV)
-    v1, a1, lp1, _ = pol.act(obs.to(DEV), hx1, masks.to(DEV), deterministic=True)
+    v1, a1, lp1, h1 = pol.act(obs.to(DEV), hx1, masks.to(DEV), deterministic=True)
+    if pc["recurrent"]:
+        # final hidden state of the [T, N] sequence and of the single step (model.py:111-166)
+        _, _, _, h2 = pol.evaluate_actions(obs.to(DEV), hxs, masks.to(DEV), action.to(DEV))
+        np.testing.assert_allclose(h2.detach().cpu().numpy(), g[tag + "_hxs_out"], **tol)
+        np.testing.assert_allclose(h1.cpu().numpy(), g[tag + "_act_hxs_out"], **tol)
     np.testing.assert_allclose(v1.cpu().numpy(), g[tag + "_act_value"], **tol)
     np.testing.assert_allclose(a1.cpu().numpy(), g[tag + "_act_action"], **tol)
     np.testing.assert_allclose(lp1.cpu().numpy(), g[tag + "_act_logp"], **tol)
@@ -100,7 +105,7 @@ def build(case_name, obs_uint8):
     return case, cfg, pol, st, agent
 
 
-SMALL = ["C1s", "C3s", "C3u", "C2", "C2g"]
+SMALL = ["C1s", "C3s", "C3u", "C2", "C2g", "C5s"]
 FULL = ["C1", "C3"]
 
 
@@ -128,6 +133,7 @@ def test_update_vs_reference_golden(name, obs_uint8, gemm_engine):
     # per-entry allowance of 0.5% of the tensor's RMS value.
     tc = gemm_engine == "tcgen05"
     ef = 5e-3 if tc else 0.0
+    rt1 = 5e-4 if tc else 1e-4      # per-TENSOR fingerprints (scalars like critic_linear.bias cancel heavily)
     # losses: 1e-4 relative with an absolute floor (action_loss ~ 0 with normalised advantages)
     np.testing.assert_allclose(np.array([vl, al, ent]), case["losses"], rtol=2e-4 if full else 1e-4, atol=2e-6)
     if first:
@@ -140,17 +146,17 @@ def test_update_vs_reference_golden(name, obs_uint8, gemm_engine):
         assert helpers.rel_l2(case, "step1_paramdense_", first["params"]) <= 1e-4
         for k, v in first["grads"].items():
             helpers.assert_summary_close(helpers.summary(v), case["step1_grad_" + k],
-                                         rtol=5e-3 if (tc and full) else 1e-4, atol=1e-7,
+                                         rtol=5e-3 if (tc and full) else rt1, atol=1e-7,
                                          what="step-1 grad " + k, elem_frac=2e-2 if (tc and full) else ef)
         for k, v in first["params"].items():
-            helpers.assert_summary_close(helpers.summary(v), case["step1_param_" + k], rtol=1e-4, atol=1e-7,
+            helpers.assert_summary_close(helpers.summary(v), case["step1_param_" + k], rtol=rt1, atol=1e-7,
                                          what="step-1 param " + k, elem_frac=ef)
     # end of update: tight for <= 4 steps; full-size runs sit at the oracle's own noise floor
     # (reference vs itself: 1e-4..3e-4 rel-L2), so those use the looser bound
     rl2 = helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters()))
     assert rl2 <= (2e-3 if full else 1e-4), rl2
     for k, p in pol.named_parameters():
-        helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2 if full else 1e-4,
+        helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2 if full else rt1,
                                      atol=1e-6, what="final " + k, elem_frac=0.1 if full else ef)
     if not full:
         st.after_update()
