@@ -139,10 +139,11 @@ int a2cb_gemm(const a2cb_gemm_t* desc, a2cb_stream_t stream);
  * tensor cores) / 1001 (force SIMT). */
 int a2cb_set_gemm_mode(int32_t mode);
 int a2cb_get_gemm_mode(void);
-/* dst[e] (+)= act( sum_{s < splits} src[s * stride + e] + bias[e % ncols] ),  e in [0, count)
- * (bias may be NULL; act: 0 none, 1 relu, 2 tanh) */
+/* dst[e] = (accumulate ? beta * dst[e] : 0) + act( sum_{s < splits} src[s * stride + e] + bias[e % ncols] ),
+ * e in [0, count)  (bias may be NULL; act: 0 none, 1 relu, 2 tanh).  With beta = stat_decay this is also
+ * the KFAC running average m <- decay * m + (1 - decay) * new (kfac.py:67-71). */
 int a2cb_reduce_splits(float* dst, const float* src, int64_t count, int64_t stride, int32_t splits,
-                       int32_t accumulate, const float* bias, int32_t ncols, int32_t act,
+                       int32_t accumulate, const float* bias, int32_t ncols, int32_t act, float beta,
                        a2cb_stream_t stream);
 
 /* ---------------------------------------------------------------------------
@@ -206,7 +207,8 @@ int a2cb_adv_normalize(const float* returns, const float* value_preds, int64_t n
  * a2cb_optim_step: kind 0 Adam, 1 RMSprop (b2 = alpha), 2 SGD with momentum (b1 = momentum).
  *   lr_eff = lr / (1 - b1^t) for Adam, lr otherwise; omb1/omb2 = 1-b1 / 1-b2 rounded from
  *   double; bc2_sqrt = sqrt(1 - b2^t).  max_norm > 0 rescales g by min(1, max_norm/(norm+1e-6))
- *   in place first (reading norm[0] on the device: no host sync).
+ *   in place first (reading norm[0] on the device: no host sync); max_norm < 0 rescales g by
+ *   norm[0] itself (the KFAC trust-region factor nu).
  * ------------------------------------------------------------------------- */
 int a2cb_grad_norm(const float* grads, int64_t n, double* scratch, float* norm_out, a2cb_stream_t stream);
 int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, float* state2, int64_t n,
@@ -233,7 +235,7 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
-                 const float* bias; int32_t ncols; int32_t act; } a2cb_reduce_t;
+                 const float* bias; int32_t ncols; int32_t act; float beta; int32_t pad_; } a2cb_reduce_t;
 typedef struct { const float* grads; int64_t n; double* scratch; float* norm_out; } a2cb_grad_norm_t;
 typedef struct {
     float* params; float* grads; float* state1; float* state2; int64_t n; const float* norm;
@@ -271,6 +273,26 @@ typedef struct {
 } a2cb_gru_t;
 
 int a2cb_gru_op(int32_t which, const a2cb_gru_t* desc, a2cb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * (5) ACKTR / KFAC helpers                              a2c_ppo_acktr/algo/kfac.py
+ * The factor products (compute_cov_a / compute_cov_g, kfac.py:29-64) and the preconditioning chain
+ * (kfac.py:216-227) are a2cb_gemm descriptors (implicit im2col, running average folded into
+ * a2cb_reduce_splits with beta = stat_decay).  These entry points cover the rest:
+ *   a2cb_spatial_sum: s[b,c] = sum_p g[b,p,c] over a (haloed) NHWC gradient image  (kfac.py:59-61)
+ *   a2cb_kfac_scale:  v[i,j] /= d_g[i] * d_a[j] + damping (d_a NULL -> 1)          (kfac.py:223-225)
+ *   a2cb_kfac_nu:     out[0] = nu = min(1, sqrt(kl_clip / sum(v * grad * lr^2)))   (kfac.py:229-234)
+ *                     (scratch: 148 doubles + counter, zeroed once; a2cb_optim_step with max_norm < 0
+ *                     then scales by norm[0] = nu before the SGD-momentum step, kfac.py:236-241)
+ *   a2cb_frames_to_f32: dst = src / div as fp32 (uint8 or fp32 source)
+ * ------------------------------------------------------------------------- */
+int a2cb_spatial_sum(float* out, const float* in, int32_t B, int32_t P, int32_t C, int32_t ow, int64_t img_stride,
+                     int64_t pitch, a2cb_stream_t stream);
+int a2cb_kfac_scale(float* v, const float* dg, const float* da, int32_t rows, int32_t cols, float damping,
+                    a2cb_stream_t stream);
+int a2cb_kfac_nu(const float* v, const float* grads, int64_t n, double* scratch, float* out, float lr, float kl_clip,
+                 a2cb_stream_t stream);
+int a2cb_frames_to_f32(float* dst, const void* src, int64_t n, int32_t src_is_u8, float div, a2cb_stream_t stream);
 
 #ifdef __cplusplus
 }

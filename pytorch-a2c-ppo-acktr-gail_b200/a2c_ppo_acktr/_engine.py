@@ -39,7 +39,8 @@ class LossDesc(ctypes.Structure):
 
 class ReduceDesc(ctypes.Structure):
     _fields_ = [("dst", c_vp), ("src", c_vp), ("count", c_i64), ("stride", c_i64), ("splits", c_i32),
-                ("accumulate", c_i32), ("bias", c_vp), ("ncols", c_i32), ("act", c_i32)]
+                ("accumulate", c_i32), ("bias", c_vp), ("ncols", c_i32), ("act", c_i32), ("beta", c_f32),
+                ("pad_", c_i32)]
 
 
 class GradNormDesc(ctypes.Structure):
@@ -77,7 +78,11 @@ class Op(ctypes.Structure):
 
 _native.register({
     "a2cb_gemm": (c_i32, [ctypes.POINTER(P.GemmDesc), c_vp]),
-    "a2cb_reduce_splits": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp]),
+    "a2cb_reduce_splits": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32, c_i32, c_f32, c_vp]),
+    "a2cb_spatial_sum": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_vp]),
+    "a2cb_kfac_scale": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),
+    "a2cb_kfac_nu": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_f32, c_vp]),
+    "a2cb_frames_to_f32": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp]),
     "a2cb_loss_epilogue": (c_i32, [ctypes.POINTER(LossDesc), c_vp]),
     "a2cb_loss_scratch_floats": (c_i64, [c_i32]),
     "a2cb_adv_moments": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -136,7 +141,8 @@ def resolve(plan, arena):
     g.a_dtype = int(plan.a_u8)
     g.ones_row = 1 if plan.ones is not None else 0
     g.ones_stride = plan.ones_stride
-    g.bias_mode, g.act, g.mask_mode, g.accumulate = plan.bias_mode, plan.act, plan.mask_mode, plan.accumulate
+    g.bias_mode, g.act, g.mask_mode = plan.bias_mode, plan.act, plan.mask_mode
+    g.accumulate = plan.accumulate if plan.splits == 1 else 0      # split-K: the fold accumulates instead
     g.alpha = plan.alpha
     g.batch = plan.batch
     for z in range(4):
@@ -197,7 +203,7 @@ class Program(object):
         if plan.splits > 1:
             dst = plan.split_dst
             r = ReduceDesc(arena.ptr((dst[0], dst[1])), arena.ptr(plan.C), dst[2], plan.split_stride, plan.splits,
-                           plan.accumulate, arena.ptr(plan.split_bias), plan.N, plan.split_act)
+                           plan.accumulate, arena.ptr(plan.split_bias), plan.N, plan.split_act, plan.split_beta, 0)
             self.add(OP_REDUCE, r)
 
     def extend(self, other):
@@ -786,6 +792,45 @@ class PolicyRuntime(object):
         prog.loss_out = lo
         prog.builder = nb
         return prog
+
+    def acktr_programs(self, storage, hyper, noise):
+        """ACKTR's three passes over the FULL batch (reference a2c_acktr.py:38-72) as separate programs:
+        forward;  Fisher-sample loss + data-gradient-only backward (feeds the g-statistics);
+        main A2C loss + full backward.  Frames are read from the fp32/255 copy `obs_f32`."""
+        s = self.spec
+        T, N = storage.rewards.shape[0], storage.rewards.shape[1]
+        B = T * N
+        tag = "t%d_" % B
+        nb = NetBuilder(s, self.L, B, "obs_f32", 0, False, tag)
+        fwd = nb.forward_plans()
+        bwd = nb.backward_plans()
+        self._alloc(nb)
+        acts = storage.actions.view(B, -1)
+        lo = self.arena.ensure(tag + "loss_out", 4)
+        lo_f = self.arena.ensure(tag + "loss_out_fisher", 4)
+
+        def loss(mode, out):
+            return self._loss_desc(B, tag, mode, acts, returns=storage.returns.data_ptr(),
+                                   dz=self.arena.ptr((tag + "dz", 0)), loss_out=out.data_ptr(),
+                                   c_v=float(hyper["value_loss_coef"]), c_e=float(hyper["entropy_coef"]),
+                                   noise=noise.data_ptr())
+        progs = {}
+        progs["fwd"] = Program(self.dev)
+        for p in fwd:
+            progs["fwd"].add_plan(p, self.arena)
+        progs["fisher"] = Program(self.dev)
+        progs["fisher"].add(OP_LOSS, loss(2, lo_f))
+        for p in bwd:
+            if not p.name.endswith(".wgrad"):
+                progs["fisher"].add_plan(p, self.arena)
+        progs["main"] = Program(self.dev)
+        progs["main"].add(OP_LOSS, loss(1, lo))
+        for p in bwd:
+            progs["main"].add_plan(p, self.arena)
+        for p in progs.values():
+            p.finalize()
+        progs["loss_out"] = lo
+        return progs
 
     def add_optimizer_ops(self, prog, kind, state1, state2, max_norm):
         n = self.L.total

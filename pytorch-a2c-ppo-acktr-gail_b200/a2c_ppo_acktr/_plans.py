@@ -102,6 +102,7 @@ class Plan(object):
         self.split_dst = kw.pop("split_dst", None)  # where reduce_splits folds the partials: (buffer, offset, count)
         self.split_bias = kw.pop("split_bias", None)  # epilogue applied by the fold: bias[e % N] ...
         self.split_act = kw.pop("split_act", ACT_NONE)  # ... and activation
+        self.split_beta = kw.pop("split_beta", 1.0)     # fold computes beta * dst + sum when accumulate
         self.vecA = kw.pop("vecA", 0)
         self.vecB = kw.pop("vecB", 0)
         self.alpha = kw.pop("alpha", 1.0)

@@ -1,11 +1,15 @@
-"""A2C update (and, in a later round, ACKTR) executed on the sm_100a engine.
+"""A2C and ACKTR updates executed on the sm_100a engine.
 
-Drop-in for `a2c_ppo_acktr.algo.A2C_ACKTR` (reference algo/a2c_acktr.py:9-80): one
-full-batch forward / loss / backward over all T*N rows, gradient clipping and RMSprop.
+Drop-in for `a2c_ppo_acktr.algo.A2C_ACKTR` (reference algo/a2c_acktr.py:9-80): one full-batch
+forward / loss / backward over all T*N rows, then either gradient clipping + RMSprop (A2C) or the
+Fisher-sampling backward + KFAC step (ACKTR, algo/kfac.py).
 """
+import math
+
 import torch
 
 from .. import _native
+from .kfac import KFACOptimizer
 from .optim import FlatRMSprop
 
 
@@ -25,8 +29,9 @@ class A2C_ACKTR():
         self.entropy_coef = entropy_coef
         self.max_grad_norm = max_grad_norm
         if acktr:
-            raise _native.NativeError("ACKTR (KFAC) is not built yet in this round")
-        self.optimizer = FlatRMSprop(actor_critic, lr, eps=eps, alpha=alpha)
+            self.optimizer = KFACOptimizer(actor_critic)
+        else:
+            self.optimizer = FlatRMSprop(actor_critic, lr, eps=eps, alpha=alpha)
         self._prog_key = None
         self._prog = None
         self.last_launches = 0
@@ -36,6 +41,8 @@ class A2C_ACKTR():
         rt = policy.runtime()
         T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         B = T * N
+        if self.acktr:
+            return self._update_acktr(rt, rollouts)
         key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(), B,
                rollouts.masks.data_ptr(), rollouts.recurrent_hidden_states.data_ptr(),
                self.value_loss_coef, self.entropy_coef, self.max_grad_norm)
@@ -53,4 +60,42 @@ class A2C_ACKTR():
         prog.run()
         self.last_launches = _native.launch_count() - launches0
         out = prog.loss_out[:3].cpu()
+        return out[0].item(), out[1].item(), out[2].item()
+
+    def _update_acktr(self, rt, rollouts):
+        """reference a2c_acktr.py:38-80 with acktr=True."""
+        opt = self.optimizer
+        T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+        B = T * N
+        lib, st = _native.lib(), _native.stream_ptr(rt.dev)
+        obs_flat = rollouts.obs[:-1].view(B, -1)
+        obs_f32 = rt.arena.ensure("obs_f32", obs_flat.numel())
+        _native.check(lib.a2cb_frames_to_f32(obs_f32.data_ptr(), _native.dptr(obs_flat, name="obs"), obs_flat.numel(),
+                                             int(obs_flat.dtype == torch.uint8), 255.0, st), "a2cb_frames_to_f32")
+        # value noise of the Fisher sample: drawn on the CPU from the global generator, as the
+        # reference does (a2c_acktr.py:58-60), then uploaded
+        noise = rt.arena.ensure("kfac_noise", B)
+        use_fisher = opt.steps % opt.Ts == 0
+        if use_fisher:
+            noise.copy_(torch.randn(T, N, 1).view(-1), non_blocking=False)
+        key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(), B,
+               self.value_loss_coef, self.entropy_coef)
+        if key != self._prog_key:
+            hyper = dict(value_loss_coef=self.value_loss_coef, entropy_coef=self.entropy_coef)
+            self._prog = rt.acktr_programs(rollouts, hyper, noise)
+            self._prog_key = key
+        progs = self._prog
+        opt._build(rt, rollouts)
+        launches0 = _native.launch_count()
+        progs["fwd"].run()
+        opt.accumulate_a(rt)
+        if use_fisher:
+            opt.acc_stats = True
+            progs["fisher"].run()
+            opt.accumulate_g(rt)
+            opt.acc_stats = False
+        progs["main"].run()
+        opt.step(rt)
+        self.last_launches = _native.launch_count() - launches0
+        out = progs["loss_out"][:3].cpu()
         return out[0].item(), out[1].item(), out[2].item()

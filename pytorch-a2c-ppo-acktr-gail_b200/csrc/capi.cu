@@ -77,9 +77,10 @@ int a2cb_set_gemm_mode(int32_t mode) {
 int a2cb_get_gemm_mode(void) { return gemm_mode(); }
 
 int a2cb_reduce_splits(float* dst, const float* src, int64_t count, int64_t stride, int32_t splits,
-                       int32_t accumulate, const float* bias, int32_t ncols, int32_t act, a2cb_stream_t stream) {
+                       int32_t accumulate, const float* bias, int32_t ncols, int32_t act, float beta,
+                       a2cb_stream_t stream) {
     A2CB_REQUIRE(dst && src && count >= 0 && splits >= 1, "reduce_splits: bad argument");
-    return reduce_splits(dst, src, (long)count, (long)stride, splits, accumulate, bias, ncols, act,
+    return reduce_splits(dst, src, (long)count, (long)stride, splits, accumulate, bias, ncols, act, beta,
                          (cudaStream_t)stream);
 }
 
@@ -110,6 +111,22 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
                       bc2_sqrt, max_norm, first_step, (cudaStream_t)stream);
 }
 
+int a2cb_spatial_sum(float* out, const float* in, int32_t B, int32_t P, int32_t C, int32_t ow, int64_t img_stride,
+                     int64_t pitch, a2cb_stream_t stream) {
+    return spatial_sum(out, in, B, P, C, ow, (long)img_stride, (long)pitch, (cudaStream_t)stream);
+}
+int a2cb_kfac_scale(float* v, const float* dg, const float* da, int32_t rows, int32_t cols, float damping,
+                    a2cb_stream_t stream) {
+    return kfac_scale(v, dg, da, rows, cols, damping, (cudaStream_t)stream);
+}
+int a2cb_kfac_nu(const float* v, const float* grads, int64_t n, double* scratch, float* out, float lr, float kl_clip,
+                 a2cb_stream_t stream) {
+    return kfac_nu(v, grads, (long)n, scratch, out, lr, kl_clip, (cudaStream_t)stream);
+}
+int a2cb_frames_to_f32(float* dst, const void* src, int64_t n, int32_t src_is_u8, float div, a2cb_stream_t stream) {
+    return frames_to_f32(dst, src, (long)n, src_is_u8, div, (cudaStream_t)stream);
+}
+
 int a2cb_gru_op(int32_t which, const a2cb_gru_t* desc, a2cb_stream_t stream) {
     A2CB_REQUIRE(desc && which >= A2CB_OP_GRU_INIT && which <= A2CB_OP_GRU_BWD, "gru_op: bad argument");
     static_assert(sizeof(a2cb_gru_t) == sizeof(GruDesc), "a2cb_gru_t and GruDesc must share a layout");
@@ -137,7 +154,7 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             }
             case A2CB_OP_REDUCE: {
                 const a2cb_reduce_t& r = *reinterpret_cast<const a2cb_reduce_t*>(op.desc);
-                rc = reduce_splits(r.dst, r.src, (long)r.count, (long)r.stride, r.splits, r.accumulate, r.bias, r.ncols, r.act, st);
+                rc = reduce_splits(r.dst, r.src, (long)r.count, (long)r.stride, r.splits, r.accumulate, r.bias, r.ncols, r.act, r.beta, st);
                 break;
             }
             case A2CB_OP_LOSS: {

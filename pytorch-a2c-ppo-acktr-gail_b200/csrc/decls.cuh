@@ -24,7 +24,7 @@ void set_gemm_mode(int m);
 bool gemm_tc_supported(const GemmDesc& g);
 int gemm_tc(const GemmDesc& g, cudaStream_t st);
 int reduce_splits(float* dst, const float* src, long count, long stride, int splits, int accumulate,
-                  const float* bias, int ncols, int act, cudaStream_t st);
+                  const float* bias, int ncols, int act, float beta, cudaStream_t st);
 
 // loss.cu
 struct LossDesc;
@@ -40,6 +40,14 @@ int grad_norm(const float* g, long n, double* scratch, float* norm_out, cudaStre
 int optim_step(int kind, float* p, float* g, float* s1, float* s2, long n, const float* norm,
                float lr_eff, float eps, float b1, float b2, float omb1, float omb2, float bc2_sqrt,
                float max_norm, int first_step, cudaStream_t st);
+
+// kfac.cu
+int spatial_sum(float* out, const float* in, int B, int P, int C, int ow, long img_stride, long pitch,
+                cudaStream_t st);
+int kfac_scale(float* v, const float* dg, const float* da, int rows, int cols, float damping, cudaStream_t st);
+int kfac_nu(const float* v, const float* g, long n, double* scratch, float* out, float lr, float kl_clip,
+            cudaStream_t st);
+int frames_to_f32(float* dst, const void* src, long n, int src_is_u8, float div, cudaStream_t st);
 
 // gru.cu
 struct GruDesc;

@@ -369,11 +369,11 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
     return check_launch("gemm");
 }
 
-// dst[e] (+)= act( sum_s src[s * stride + e] + bias[e % ncols] )  for e in [0, count): folds split-K
+// dst[e] = (accumulate ? beta * dst[e] : 0) + act( sum_s src[s * stride + e] + bias[e % ncols] )  for e in [0, count): folds split-K
 // partials (fixed order, deterministic) and applies the epilogue the split GEMM could not.
 __global__ void __launch_bounds__(256)
 reduce_splits_kernel(float* __restrict__ dst, const float* __restrict__ src, long count, long stride,
-                     int splits, int accumulate, const float* __restrict__ bias, int ncols, int act) {
+                     int splits, int accumulate, const float* __restrict__ bias, int ncols, int act, float beta) {
     const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count) return;
     float s = 0.f;
@@ -381,15 +381,15 @@ reduce_splits_kernel(float* __restrict__ dst, const float* __restrict__ src, lon
     if (bias) s += __ldg(bias + (e % ncols));
     if (act == 1) s = fmaxf(s, 0.f);
     else if (act == 2) s = tanhf(s);
-    dst[e] = accumulate ? dst[e] + s : s;
+    dst[e] = accumulate ? beta * dst[e] + s : s;
 }
 
 int reduce_splits(float* dst, const float* src, long count, long stride, int splits, int accumulate,
-                  const float* bias, int ncols, int act, cudaStream_t st) {
+                  const float* bias, int ncols, int act, float beta, cudaStream_t st) {
     if (count == 0) return A2CB_OK;
     A2CB_REQUIRE(!bias || ncols > 0, "reduce_splits: bias needs ncols");
     reduce_splits_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(dst, src, count, stride, splits, accumulate,
-                                                                          bias, ncols, act);
+                                                                          bias, ncols, act, beta);
     return check_launch("reduce_splits");
 }
 

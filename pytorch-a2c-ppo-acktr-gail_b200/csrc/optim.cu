@@ -77,10 +77,11 @@ optim_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
                   float* __restrict__ s2, long n, const float* __restrict__ norm, OptimArgs a) {
     float coef = 1.f;
     if (a.max_norm > 0.f) coef = fminf(1.f, a.max_norm / (norm[0] + 1e-6f));
+    else if (a.max_norm < 0.f) coef = norm[0];              // KFAC: norm[0] holds nu (kfac.py:234-239)
     const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     float gi = g[e];
-    if (a.max_norm > 0.f) { gi = __fmul_rn(gi, coef); g[e] = gi; }
+    if (a.max_norm != 0.f) { gi = __fmul_rn(gi, coef); g[e] = gi; }
     float pi = p[e];
     if (KIND == 0) {
         float m = s1[e], v = s2[e];
@@ -109,7 +110,7 @@ int optim_step(int kind, float* p, float* g, float* s1, float* s2, long n, const
     A2CB_REQUIRE(p && g && n >= 0, "optim_step: null pointer");
     A2CB_REQUIRE(kind >= 0 && kind <= 2, "optim_step: kind");
     A2CB_REQUIRE(s1 && (kind != 0 || s2), "optim_step: missing optimiser state");
-    A2CB_REQUIRE(max_norm <= 0.f || norm, "optim_step: clipping needs the norm buffer");
+    A2CB_REQUIRE(max_norm == 0.f || norm, "optim_step: clipping needs the norm buffer");
     if (n == 0) return A2CB_OK;
     OptimArgs a{lr_eff, eps, b1, b2, omb1, omb2, bc2_sqrt, max_norm, first_step};
     const unsigned grid = (unsigned)((n + 255) / 256);

@@ -213,7 +213,20 @@ UPDATE_CASES = {
     "C2g": ("C2", dict(T=6, N=3, use_gae=True, use_proper_time_limits=True)),
     "C1": ("C1", dict()),
     "C3": ("C3", dict()),
+    "C4s": ("C4", dict(T=4, N=4)),
+    "C4": ("C4", dict()),
 }
+
+
+def plain_name(k):
+    """KFACOptimizer rewrites the module tree (SplitBias, kfac.py:101-108): map its parameter names
+    back to the original ones so that ACKTR fixtures use the same keys as every other case."""
+    return k.replace(".module.weight", ".weight").replace(".add_bias._bias", ".bias")
+
+
+def plain_value(k, v):
+    return v.reshape(-1) if k.endswith(".add_bias._bias") else v
+
 
 
 def build_ref_rollout(cfg, pol, seed=0):
@@ -253,7 +266,9 @@ def case_update(name):
     for k, v in pol.state_dict().items():
         out["init_" + k] = summary(v)
 
-    if cfg["algo"] == "ppo":
+    if cfg["algo"] == "acktr":
+        agent = REF["algo.a2c_acktr"].A2C_ACKTR(pol, cfg["value_loss_coef"], cfg["entropy_coef"], acktr=True)
+    elif cfg["algo"] == "ppo":
         agent = REF["algo.ppo"].PPO(pol, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"],
                                     cfg["value_loss_coef"], cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"],
                                     max_grad_norm=cfg["max_grad_norm"],
@@ -268,16 +283,25 @@ def case_update(name):
 
     def step_hook(*a, **k):
         if "grads" not in first:
-            first["grads"] = {n: p.grad.detach().clone() for n, p in pol.named_parameters()}
+            first["grads"] = {plain_name(n): plain_value(n, p.grad.detach().clone()) for n, p in pol.named_parameters()}
         r = orig_step(*a, **k)
         if "params" not in first:
-            first["params"] = {n: p.detach().clone() for n, p in pol.named_parameters()}
+            first["params"] = {plain_name(n): plain_value(n, p.detach().clone()) for n, p in pol.named_parameters()}
         return r
 
     agent.optimizer.step = step_hook
     torch.manual_seed(7)
     vl, al, ent = agent.update(st)
     out["losses"] = np.array([vl, al, ent], dtype=np.float64)
+    if cfg["algo"] == "acktr":
+        # running Kronecker factors after the first update, keyed by the parameter each module owns
+        names = {id(p): plain_name(n) for n, p in pol.named_parameters()}
+        for mod in agent.optimizer.modules:
+            key = names[id(next(mod.parameters()))]
+            out["maa_" + key] = summary(agent.optimizer.m_aa[mod])
+            out["mgg_" + key] = summary(agent.optimizer.m_gg[mod])
+            out["maadense_" + key] = dense(agent.optimizer.m_aa[mod])
+            out["mggdense_" + key] = dense(agent.optimizer.m_gg[mod])
     for k, v in first["grads"].items():
         out["step1_grad_" + k] = summary(v)
         out["step1_graddense_" + k] = dense(v)
@@ -285,7 +309,8 @@ def case_update(name):
         out["step1_param_" + k] = summary(v)
         out["step1_paramdense_" + k] = dense(v)
     small = sum(p.numel() for p in pol.parameters()) < 20000
-    for k, v in pol.state_dict().items():
+    for k0, v0 in pol.state_dict().items():
+        k, v = plain_name(k0), plain_value(k0, v0)
         out["final_" + k] = summary(v)
         out["finaldense_" + k] = dense(v)
         if small:

@@ -259,3 +259,45 @@ def test_sharded_update_equals_single_device(name, world, gemm_engine):
     for k, p in p0.items():
         helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2 if full else 1e-4, atol=1e-6,
                                      what="final " + k, elem_frac=0.1 if full else ef)
+
+
+@pytest.mark.parametrize("obs_uint8", [True, False])
+@pytest.mark.parametrize("name", ["C4s", "C4"])
+def test_acktr_update_vs_reference_golden(name, obs_uint8, gemm_engine):
+    """ACKTR (reference a2c_acktr.py + kfac.py): running Kronecker factors, preconditioned step and
+    losses of two consecutive updates against the reference.  Eigenvectors are not unique,
+    so only factors, parameters and losses are compared."""
+    case = helpers.load("update_" + name)
+    cfg = helpers.case_config(case)
+    torch.manual_seed(1)
+    pol = Policy(cfg["obs_shape"], space(cfg["action"])).to(DEV)
+    ro = helpers.rollout_from_case(case, cfg, obs_uint8=obs_uint8)
+    st = RolloutStorage(cfg["T"], cfg["N"], cfg["obs_shape"], space(cfg["action"]), 1,
+                        obs_dtype=torch.uint8 if obs_uint8 else torch.float32)
+    for nme in ("obs", "recurrent_hidden_states", "rewards", "value_preds", "action_log_probs", "actions", "masks",
+                "bad_masks"):
+        getattr(st, nme).copy_(ro[nme])
+    st.to(DEV)
+    st.compute_returns(ro["next_value"].to(DEV), cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"],
+                       cfg["use_proper_time_limits"], schedule=1)
+    agent = algo.A2C_ACKTR(pol, cfg["value_loss_coef"], cfg["entropy_coef"], acktr=True)
+    torch.manual_seed(7)
+    got = agent.update(st)
+    np.testing.assert_allclose(np.array(got), case["losses"], rtol=1e-4, atol=2e-6)
+    opt = agent.optimizer
+    tc = gemm_engine == "tcgen05"
+    for m in opt.modules:
+        for kind, fname in (("maa", m.aa), ("mgg", m.gg)):
+            f = opt.factors[fname]
+            want = case["%sdense_%s" % (kind, m.key)].astype(np.float64)
+            gotf = helpers.dense(f["m"]).astype(np.float64)
+            err = np.linalg.norm(gotf - want) / max(np.linalg.norm(want), 1e-30)
+            # g-factors inherit the ReLU-mask sensitivity of the backward pass on the tensor-core engine
+            assert err <= (5e-3 if (tc and kind == "mgg") else 2e-4), (kind, m.key, err)
+    rl2 = helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters()))
+    assert rl2 <= 1e-4, rl2
+    st.after_update()
+    torch.manual_seed(8)
+    got2 = agent.update(st)
+    np.testing.assert_allclose(np.array(got2), case["losses2"], rtol=5e-4, atol=5e-6)
+    assert opt.steps == 2
