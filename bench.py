@@ -117,9 +117,16 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------
 # workload construction
 # ---------------------------------------------------------------------------
+ENVS_OVERRIDE = 0
+
+
 def workload_config(name):
     cfg = dict(synthetic.CONFIGS[name])
     cfg["name"] = name
+    if name == "C5":
+        cfg["N"] = 256          # one GPU's shard of the 2048 environments (256 envs / GPU)
+    if ENVS_OVERRIDE:
+        cfg["N"] = ENVS_OVERRIDE
     return cfg
 
 
@@ -187,6 +194,8 @@ def run_ours(args):
     if cfg["algo"] == "ppo":
         agent = algo.PPO(policy, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
                          cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"], max_grad_norm=cfg["max_grad_norm"])
+    elif cfg["algo"] == "acktr":
+        agent = algo.A2C_ACKTR(policy, cfg["value_loss_coef"], cfg["entropy_coef"], acktr=True)
     else:
         agent = algo.A2C_ACKTR(policy, cfg["value_loss_coef"], cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"],
                                alpha=cfg["alpha"], max_grad_norm=cfg["max_grad_norm"])
@@ -260,7 +269,7 @@ def run_ours(args):
         roof, kernels = kernel_roofline(agent, st, cfg, dev, pk) if world == 1 else (None, None)
         scan = scan_roofline(dev, pk) if world == 1 else None
         out = {
-            "metric": "PPO update transitions/sec" if cfg["algo"] == "ppo" else "A2C update transitions/sec",
+            "metric": "%s update transitions/sec" % cfg["algo"].upper(),
             "value": value, "unit": "transitions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -301,17 +310,22 @@ def describe(cfg):
 def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
     from a2c_ppo_acktr import _engine
     prog = getattr(agent, "_prog", None)
+    if isinstance(prog, dict):           # ACKTR keeps three programs; profile the main fwd/bwd pass
+        prog = prog.get("main")
     if prog is None:
         return None, None
     T, N = cfg["T"], cfg["N"]
-    mbs = prog.builder.B
+    mbs = prog.builder.B if hasattr(prog, "builder") else T * N
+    if cfg.get("recurrent"):
+        return None, None                # recurrent programs need per-minibatch state set up by update()
     names, flops = [], []
     for kind, flags, desc in prog.entries:
         if kind == _engine.OP_GEMM:
             names.append("gemm")
             flops.append(2.0 * desc.M * desc.N * desc.K * desc.batch)
         else:
-            names.append({2: "reduce_splits", 3: "loss_epilogue", 4: "grad_norm", 5: "optim_step"}.get(kind, "op%d" % kind))
+            names.append({2: "reduce_splits", 3: "loss_epilogue", 4: "grad_norm", 5: "optim_step", 7: "gru_init",
+                          8: "gru_gates", 9: "gru_gates_bwd"}.get(kind, "op%d" % kind))
             flops.append(0.0)
     # label GEMMs by their plan
     labels = []
@@ -397,6 +411,11 @@ def cpu_update_once(cfg, state):
     ro["value_preds"] = torch.from_numpy(vp)
     if cfg["algo"] == "ppo":
         out = o_upd.ppo_update(p, spec, ro, cfg, optimizer=state.get("opt"))
+    elif cfg["algo"] == "acktr":
+        from oracle import kfac as o_kfac
+        if "opt" not in state:
+            state["opt"] = o_kfac.KFACState()
+        out = o_kfac.acktr_update(p, ro, cfg, state["opt"]) + (state["opt"],)
     else:
         out = o_upd.a2c_update(p, spec, ro, cfg, optimizer=state.get("opt"))
     state["opt"] = out[3]
@@ -452,7 +471,7 @@ def run_reference(args):
     sample = "%d full %s updates of the oracle port of the reference (torch %s CPU, %d threads)" % (
         args.steps, cfg["name"], torch.__version__, cores)
     print(json.dumps({
-        "impl": "reference", "metric": "PPO update transitions/sec" if cfg["algo"] == "ppo" else "A2C update transitions/sec",
+        "impl": "reference", "metric": "%s update transitions/sec" % cfg["algo"].upper(),
         "value": val, "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(ts)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -472,7 +491,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--envs", type=int, default=0, help="override the number of environments per GPU")
     args = ap.parse_args()
+    global ENVS_OVERRIDE
+    ENVS_OVERRIDE = args.envs
     if args.impl == "reference":
         run_reference(args)
     else:

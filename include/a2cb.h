@@ -40,6 +40,9 @@ const char* a2cb_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench.py's
  * "gpu_launches" evidence). */
 int64_t a2cb_launch_count(void);
+/* Bookkeeping for launches that happen through a replayed CUDA graph (captured launches are counted
+ * when recorded; the host wrapper subtracts them once and adds them back per replay). */
+void a2cb_add_launches(int64_t n);
 
 /* ---------------------------------------------------------------------------
  * (1) RolloutStorage.compute_returns              a2c_ppo_acktr/storage.py:66-105
@@ -241,6 +244,8 @@ typedef struct {
     float* params; float* grads; float* state1; float* state2; int64_t n; const float* norm;
     int32_t kind; int32_t first_step;
     float lr_eff, eps, b1, b2, omb1, omb2, bc2_sqrt, max_norm;
+    const float* dyn;   /* optional DEVICE scalars {lr_eff, bc2_sqrt, first_step}: they override the fields above,
+                           so a CUDA graph holding a whole epoch of optimiser steps is replayed without re-capture */
 } a2cb_optim_t;
 typedef struct { void* dst; int64_t bytes; int32_t value; int32_t pad_; } a2cb_fill_t;
 typedef struct { int32_t kind; int32_t flags; const void* desc; } a2cb_op_t;

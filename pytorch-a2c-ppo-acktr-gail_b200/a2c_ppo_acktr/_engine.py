@@ -51,7 +51,7 @@ class OptimDesc(ctypes.Structure):
     _fields_ = [("params", c_vp), ("grads", c_vp), ("state1", c_vp), ("state2", c_vp), ("n", c_i64),
                 ("norm", c_vp), ("kind", c_i32), ("first_step", c_i32),
                 ("lr_eff", c_f32), ("eps", c_f32), ("b1", c_f32), ("b2", c_f32), ("omb1", c_f32), ("omb2", c_f32),
-                ("bc2_sqrt", c_f32), ("max_norm", c_f32)]
+                ("bc2_sqrt", c_f32), ("max_norm", c_f32), ("dyn", c_vp)]
 
 
 class FillDesc(ctypes.Structure):

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "a2cb_abi_version": (c_int, []),
     "a2cb_last_error": (ctypes.c_char_p, []),
     "a2cb_launch_count": (c_i64, []),
+    "a2cb_add_launches": (None, [c_i64]),
     "a2cb_set_gemm_mode": (c_int, [c_int]),
     "a2cb_get_gemm_mode": (c_int, []),
     "a2cb_returns_scan": (c_int, [c_void_p] * 6 + [c_int, c_i64, c_f64, c_f64, c_int, c_int, c_int, c_void_p]),

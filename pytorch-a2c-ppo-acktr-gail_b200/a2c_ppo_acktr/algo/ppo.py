@@ -72,6 +72,10 @@ class PPO():
         self.last_launches = 0
         self.step_hook = None      # optional callable(step_index) after each optimiser step (tests)
         self.shard = None          # _dist.ShardInfo when the rollout is sharded over ranks
+        # One CUDA graph holds a whole epoch (num_mini_batch x ~20 kernels): the minibatch indices and the
+        # per-step Adam scalars live in device buffers that are refreshed before each replay.
+        self.use_cuda_graph = True
+        self._graph = None
 
     def set_distributed(self, world, rank, env_range, n_total):
         """Declares that `rollouts` passed to update() hold environments [env_range) of a global
@@ -126,9 +130,14 @@ class PPO():
         accum.zero_()
         prog, _ = self._program(rt, rollouts, mbs, adv, accum)
         launches0 = _native.launch_count()
+        graphed = self.use_cuda_graph and self.step_hook is None
         for _ in range(self.ppo_epoch):
-            perm = torch.randperm(batch_size).to(rt.dev)
+            perm = torch.randperm(batch_size)
+            if graphed and self._epoch_graph(rt, prog, mbs, n_mb, perm):
+                continue
+            perm = perm.to(rt.dev)
             for k in range(n_mb):
+                prog.optim_desc.dyn = None
                 self.optimizer.configure(prog.optim_desc)
                 prog.run(perm[k * mbs:(k + 1) * mbs])
                 if self.step_hook is not None:
@@ -137,6 +146,44 @@ class PPO():
         num_updates = self.ppo_epoch * self.num_mini_batch
         sums = accum[:3].cpu()          # the update's only device->host synchronisation
         return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
+
+    def _epoch_graph(self, rt, prog, mbs, n_mb, perm):
+        """Replays one epoch as a CUDA graph.  Returns False the first time a program is seen (that epoch
+        runs eagerly, which also warms every kernel up); the graph is captured before the next one."""
+        key = (id(prog), mbs, n_mb)
+        g = self._graph
+        if g is None or g["key"] != key:
+            if g is not None and g.get("pending") == key:
+                idx_buf = torch.zeros(n_mb * mbs, dtype=torch.int64, device=rt.dev)
+                dyn_buf = torch.zeros(n_mb, 4, dtype=torch.float32, device=rt.dev)
+                graph = torch.cuda.CUDAGraph()
+                n0 = _native.launch_count()
+                torch.cuda.synchronize(rt.dev)
+                with torch.cuda.graph(graph):
+                    for k in range(n_mb):
+                        prog.optim_desc.dyn = dyn_buf.data_ptr() + 16 * k
+                        prog.run(idx_buf[k * mbs:(k + 1) * mbs])
+                prog.optim_desc.dyn = None
+                self._graph = g = dict(key=key, graph=graph, idx=idx_buf, dyn=dyn_buf,
+                                       launches=_native.launch_count() - n0,
+                                       host_dyn=torch.zeros(n_mb, 4).pin_memory(),
+                                       host_idx=torch.zeros(n_mb * mbs, dtype=torch.int64).pin_memory())
+                _native.lib().a2cb_add_launches(-g["launches"])          # capture recorded, did not run, them
+            else:
+                self._graph = dict(key=None, pending=key)
+                return False
+        opt = self.optimizer
+        hd = g["host_dyn"]
+        for k in range(n_mb):
+            opt.step_count += 1
+            sc = opt.scalars()
+            hd[k, 0], hd[k, 1], hd[k, 2] = sc["lr_eff"], sc["bc2_sqrt"], float(sc["first_step"])
+        g["host_idx"].copy_(perm[:n_mb * mbs])
+        g["idx"].copy_(g["host_idx"], non_blocking=True)
+        g["dyn"].copy_(hd, non_blocking=True)
+        g["graph"].replay()
+        _native.lib().a2cb_add_launches(g["launches"])
+        return True
 
     def _update_recurrent(self, rt, rollouts):
         """Recurrent minibatches are whole environments (reference storage.py:145-202): one

@@ -41,6 +41,7 @@ extern "C" {
 int a2cb_abi_version(void) { return A2CB_ABI_VERSION; }
 const char* a2cb_last_error(void) { return g_err; }
 int64_t a2cb_launch_count(void) { return g_launches.load(); }
+void a2cb_add_launches(int64_t n) { g_launches.fetch_add(n); }
 
 int a2cb_returns_scan(const float* rewards, float* value_preds, float* returns, const float* masks,
                       const float* bad_masks, const float* next_value, int32_t T, int64_t N,
@@ -108,7 +109,7 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
                     const float* norm, float lr_eff, float eps, float b1, float b2, float omb1, float omb2,
                     float bc2_sqrt, float max_norm, int32_t first_step, a2cb_stream_t stream) {
     return optim_step(kind, params, grads, state1, state2, (long)n, norm, lr_eff, eps, b1, b2, omb1, omb2,
-                      bc2_sqrt, max_norm, first_step, (cudaStream_t)stream);
+                      bc2_sqrt, max_norm, first_step, nullptr, (cudaStream_t)stream);
 }
 
 int a2cb_spatial_sum(float* out, const float* in, int32_t B, int32_t P, int32_t C, int32_t ow, int64_t img_stride,
@@ -171,7 +172,7 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             case A2CB_OP_OPTIM: {
                 const a2cb_optim_t& o = *reinterpret_cast<const a2cb_optim_t*>(op.desc);
                 rc = optim_step(o.kind, o.params, o.grads, o.state1, o.state2, (long)o.n, o.norm, o.lr_eff, o.eps,
-                                o.b1, o.b2, o.omb1, o.omb2, o.bc2_sqrt, o.max_norm, o.first_step, st);
+                                o.b1, o.b2, o.omb1, o.omb2, o.bc2_sqrt, o.max_norm, o.first_step, o.dyn, st);
                 break;
             }
             case A2CB_OP_FILL: {

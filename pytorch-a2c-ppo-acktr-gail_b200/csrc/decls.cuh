@@ -39,7 +39,7 @@ int adv_normalize(const float* returns, const float* values, long n, const doubl
 int grad_norm(const float* g, long n, double* scratch, float* norm_out, cudaStream_t st);
 int optim_step(int kind, float* p, float* g, float* s1, float* s2, long n, const float* norm,
                float lr_eff, float eps, float b1, float b2, float omb1, float omb2, float bc2_sqrt,
-               float max_norm, int first_step, cudaStream_t st);
+               float max_norm, int first_step, const float* dyn, cudaStream_t st);
 
 // kfac.cu
 int spatial_sum(float* out, const float* in, int B, int P, int C, int ow, long img_stride, long pitch,

@@ -23,7 +23,6 @@
 
 namespace a2cb {
 
-constexpr int kBK = 16;
 constexpr int kNT = 256;
 
 __device__ __forceinline__ long affine_eval(const Affine3& a, long i, const int64_t* gather) {
@@ -55,7 +54,7 @@ __device__ __forceinline__ float4 load_a4(const void* A, long off) {
     return v;
 }
 
-template <int BM, int BN, int TM, int TN, int A_U8>
+template <int BM, int BN, int TM, int TN, int A_U8, int kBK>
 __global__ void __launch_bounds__(kNT)
 gemm_kernel(const GemmDesc g) {
     static_assert((BM / TM) * (BN / TN) == kNT, "thread tiling");
@@ -302,13 +301,13 @@ gemm_kernel(const GemmDesc g) {
     }
 }
 
-template <int BM, int BN, int TM, int TN>
+template <int BM, int BN, int TM, int TN, int kBK>
 static void launch_tile(const GemmDesc& g, cudaStream_t st) {
     const long Mtot = g.M + (g.ones_row ? 1 : 0);
     dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((Mtot + BM - 1) / BM), (unsigned)(g.batch * g.splits));
-    if (g.a_dtype == 1) gemm_kernel<BM, BN, TM, TN, 1><<<grid, kNT, 0, st>>>(g);
-    else if (g.a_dtype == 2) gemm_kernel<BM, BN, TM, TN, 2><<<grid, kNT, 0, st>>>(g);
-    else gemm_kernel<BM, BN, TM, TN, 0><<<grid, kNT, 0, st>>>(g);
+    if (g.a_dtype == 1) gemm_kernel<BM, BN, TM, TN, 1, kBK><<<grid, kNT, 0, st>>>(g);
+    else if (g.a_dtype == 2) gemm_kernel<BM, BN, TM, TN, 2, kBK><<<grid, kNT, 0, st>>>(g);
+    else gemm_kernel<BM, BN, TM, TN, 0, kBK><<<grid, kNT, 0, st>>>(g);
 }
 
 // 0: fp32 SIMT engine only; 1: tensor-core (tcgen05, 3xTF32) engine wherever it applies;
@@ -361,10 +360,12 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
         const long big = ((Mtot + 127) / 128) * ((g.N + 127) / 128) * g.batch * g.splits;
         if (bn == 128 && big < kNumSM) bn = 65;
     }
-    if (bn == 32) launch_tile<128, 32, 4, 4>(g, st);
-    else if (bn == 64) launch_tile<128, 64, 8, 4>(g, st);
-    else if (bn == 65) launch_tile<64, 64, 4, 4>(g, st);
-    else if (bn == 128) launch_tile<128, 128, 8, 8>(g, st);
+    // deeper k-tiles (32) for the narrow tiles: half the barriers / offset stagings per reduction
+    // element on latency-bound shapes; the 128x128 tile keeps 16 to stay inside 48 KiB of static smem
+    if (bn == 32) launch_tile<128, 32, 4, 4, 32>(g, st);
+    else if (bn == 64) launch_tile<128, 64, 8, 4, 16>(g, st);
+    else if (bn == 65) launch_tile<64, 64, 4, 4, 32>(g, st);
+    else if (bn == 128) launch_tile<128, 128, 8, 8, 16>(g, st);
     else { set_error("gemm: unsupported tile %d", bn); return A2CB_ERR_UNSUPPORTED; }
     return check_launch("gemm");
 }

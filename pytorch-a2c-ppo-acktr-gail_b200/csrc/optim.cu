@@ -69,12 +69,15 @@ struct OptimArgs {
     float bc2_sqrt;      // Adam: sqrt(1 - b2^t)
     float max_norm;      // <= 0: no clipping
     int first_step;      // SGD momentum: buf = g
+    const float* dyn;    // optional device scalars {lr_eff, bc2_sqrt, first_step} overriding the fields
+                         // above, so that a CUDA graph of many optimiser steps needs no re-capture
 };
 
 template <int KIND>   // 0 Adam, 1 RMSprop, 2 SGD-momentum
 __global__ void __launch_bounds__(256)
 optim_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ s1,
                   float* __restrict__ s2, long n, const float* __restrict__ norm, OptimArgs a) {
+    if (a.dyn) { a.lr_eff = a.dyn[0]; a.bc2_sqrt = a.dyn[1]; a.first_step = a.dyn[2] != 0.f; }
     float coef = 1.f;
     if (a.max_norm > 0.f) coef = fminf(1.f, a.max_norm / (norm[0] + 1e-6f));
     else if (a.max_norm < 0.f) coef = norm[0];              // KFAC: norm[0] holds nu (kfac.py:234-239)
@@ -106,13 +109,13 @@ optim_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
 
 int optim_step(int kind, float* p, float* g, float* s1, float* s2, long n, const float* norm,
                float lr_eff, float eps, float b1, float b2, float omb1, float omb2, float bc2_sqrt,
-               float max_norm, int first_step, cudaStream_t st) {
+               float max_norm, int first_step, const float* dyn, cudaStream_t st) {
     A2CB_REQUIRE(p && g && n >= 0, "optim_step: null pointer");
     A2CB_REQUIRE(kind >= 0 && kind <= 2, "optim_step: kind");
     A2CB_REQUIRE(s1 && (kind != 0 || s2), "optim_step: missing optimiser state");
     A2CB_REQUIRE(max_norm == 0.f || norm, "optim_step: clipping needs the norm buffer");
     if (n == 0) return A2CB_OK;
-    OptimArgs a{lr_eff, eps, b1, b2, omb1, omb2, bc2_sqrt, max_norm, first_step};
+    OptimArgs a{lr_eff, eps, b1, b2, omb1, omb2, bc2_sqrt, max_norm, first_step, dyn};
     const unsigned grid = (unsigned)((n + 255) / 256);
     if (kind == 0) optim_step_kernel<0><<<grid, 256, 0, st>>>(p, g, s1, s2, n, norm, a);
     else if (kind == 1) optim_step_kernel<1><<<grid, 256, 0, st>>>(p, g, s1, s2, n, norm, a);

@@ -171,3 +171,34 @@ def test_update_matches_reference(name):
     for k, v in p.items():
         helpers.assert_summary_close(helpers.summary(v), case["final_" + k], rtol=1e-2 if full else 2e-4,
                                      atol=1e-6, what="param " + k, elem_frac=0.1 if full else 0.0)
+
+
+@pytest.mark.parametrize("name", ["C4s", "C4"])
+def test_acktr_oracle_matches_reference(name):
+    """oracle/kfac.py (functional KFAC) against the reference's hook-based KFACOptimizer."""
+    from oracle import kfac
+    case = helpers.load("update_" + name)
+    cfg = helpers.case_config(case)
+    spec = policy.Spec(cfg["obs_shape"], cfg["action"], cfg["recurrent"])
+    p0 = policy.init_params(spec, seed=1)
+    ro = helpers.rollout_from_case(case, cfg)
+    ret, vp = returns.compute_returns(ro["rewards"].numpy(), ro["value_preds"].numpy(), ro["masks"].numpy(),
+                                      ro["bad_masks"].numpy(), ro["next_value"].numpy(), cfg["use_gae"],
+                                      cfg["gamma"], cfg["gae_lambda"], cfg["use_proper_time_limits"])
+    ro["returns"], ro["value_preds"] = torch.from_numpy(ret), torch.from_numpy(vp)
+    p = update.make_leaf_params(p0)
+    st = kfac.KFACState()
+    torch.manual_seed(7)
+    got = kfac.acktr_update(p, ro, cfg, st)
+    np.testing.assert_allclose(np.array(got), case["losses"], rtol=1e-4, atol=2e-6)
+    for k in p:
+        for kind, m in (("maa", st.m_aa), ("mgg", st.m_gg)):
+            want = case["%sdense_%s" % (kind, k)].astype(np.float64)
+            g = helpers.dense(m[k]).astype(np.float64)
+            assert np.linalg.norm(g - want) <= 1e-4 * max(np.linalg.norm(want), 1e-30), (kind, k)
+    assert helpers.rel_l2(case, "finaldense_", p) <= 1e-4
+    for k in ("obs", "recurrent_hidden_states", "masks", "bad_masks"):
+        ro[k][0].copy_(ro[k][-1])
+    torch.manual_seed(8)
+    got2 = kfac.acktr_update(p, ro, cfg, st)
+    np.testing.assert_allclose(np.array(got2), case["losses2"], rtol=5e-4, atol=5e-6)
