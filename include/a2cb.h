@@ -189,6 +189,8 @@ typedef struct {
     float clip, c_v, c_e;
     float inv_B;
     int32_t n_valid;          /* rows [n_valid, B) are padding of a sharded minibatch; < 0: all valid */
+    int32_t valid_mod;        /* > 0: row b is valid iff (b % valid_mod) < n_valid (recurrent, padded per env) */
+    int32_t pad2_;
 } a2cb_loss_t;
 
 int a2cb_loss_epilogue(const a2cb_loss_t* desc, a2cb_stream_t stream);

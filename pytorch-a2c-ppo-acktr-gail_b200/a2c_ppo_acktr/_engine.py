@@ -33,7 +33,7 @@ class LossDesc(ctypes.Structure):
         ("scratch", c_vp),
         ("B", c_i32), ("A", c_i32), ("z_stride", c_i32), ("dz_stride", c_i32), ("act_stride", c_i32),
         ("dlogstd_stride", c_i32), ("dist", c_i32), ("mode", c_i32), ("use_clipped_value_loss", c_i32),
-        ("clip", c_f32), ("c_v", c_f32), ("c_e", c_f32), ("inv_B", c_f32), ("n_valid", c_i32),
+        ("clip", c_f32), ("c_v", c_f32), ("c_e", c_f32), ("inv_B", c_f32), ("n_valid", c_i32), ("valid_mod", c_i32), ("pad2_", c_i32),
     ]
 
 
@@ -793,7 +793,7 @@ class PolicyRuntime(object):
         prog.builder = nb
         return prog
 
-    def acktr_programs(self, storage, hyper, noise):
+    def acktr_programs(self, storage, hyper, noise, inv_B=None):
         """ACKTR's three passes over the FULL batch (reference a2c_acktr.py:38-72) as separate programs:
         forward;  Fisher-sample loss + data-gradient-only backward (feeds the g-statistics);
         main A2C loss + full backward.  Frames are read from the fp32/255 copy `obs_f32`."""
@@ -810,10 +810,13 @@ class PolicyRuntime(object):
         lo_f = self.arena.ensure(tag + "loss_out_fisher", 4)
 
         def loss(mode, out):
-            return self._loss_desc(B, tag, mode, acts, returns=storage.returns.data_ptr(),
-                                   dz=self.arena.ptr((tag + "dz", 0)), loss_out=out.data_ptr(),
-                                   c_v=float(hyper["value_loss_coef"]), c_e=float(hyper["entropy_coef"]),
-                                   noise=noise.data_ptr())
+            d = self._loss_desc(B, tag, mode, acts, returns=storage.returns.data_ptr(),
+                                dz=self.arena.ptr((tag + "dz", 0)), loss_out=out.data_ptr(),
+                                c_v=float(hyper["value_loss_coef"]), c_e=float(hyper["entropy_coef"]),
+                                noise=noise.data_ptr())
+            if inv_B is not None:
+                d.inv_B = float(inv_B)          # sharded: loss terms are local sums over the GLOBAL batch size
+            return d
         progs = {}
         progs["fwd"] = Program(self.dev)
         for p in fwd:

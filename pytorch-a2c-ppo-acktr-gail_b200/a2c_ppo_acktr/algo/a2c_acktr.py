@@ -8,7 +8,7 @@ import math
 
 import torch
 
-from .. import _native
+from .. import _dist, _native
 from .kfac import KFACOptimizer
 from .optim import FlatRMSprop
 
@@ -35,6 +35,15 @@ class A2C_ACKTR():
         self._prog_key = None
         self._prog = None
         self.last_launches = 0
+        self.shard = None
+
+    def set_distributed(self, world, rank, env_range, n_total):
+        """Environment-sharded ACKTR: per-update factor increments and the gradient are all-reduced
+        (SURVEY.md section 8e); every rank then performs the identical KFAC step."""
+        if not self.acktr and world > 1:
+            raise _native.NativeError("sharded A2C is not built; use PPO or ACKTR")
+        self.shard = _dist.ShardInfo(world, rank, env_range[0], env_range[1], n_total) if world > 1 else None
+        self._prog_key = None
 
     def update(self, rollouts):
         policy = self.actor_critic
@@ -63,8 +72,21 @@ class A2C_ACKTR():
         return out[0].item(), out[1].item(), out[2].item()
 
     def _update_acktr(self, rt, rollouts):
-        """reference a2c_acktr.py:38-80 with acktr=True."""
+        gen = self.acktr_steps(rt, rollouts)
+        try:
+            while True:
+                t = next(gen)
+                if self.shard is not None:
+                    _dist.all_reduce_sum(t)
+        except StopIteration as done:
+            return done.value
+
+    def acktr_steps(self, rt, rollouts):
+        """reference a2c_acktr.py:38-80 with acktr=True.  Generator: yields every tensor that must be
+        sum-all-reduced when the rollout is sharded (nothing is yielded on a single device)."""
         opt = self.optimizer
+        sh = self.shard
+        world = sh.world if sh is not None else 1
         T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         B = T * N
         lib, st = _native.lib(), _native.stream_ptr(rt.dev)
@@ -77,15 +99,19 @@ class A2C_ACKTR():
         noise = rt.arena.ensure("kfac_noise", B)
         use_fisher = opt.steps % opt.Ts == 0
         if use_fisher:
-            noise.copy_(torch.randn(T, N, 1).view(-1), non_blocking=False)
+            if sh is None:
+                noise.copy_(torch.randn(T, N, 1).view(-1), non_blocking=False)
+            else:       # drawn for the GLOBAL batch (same seed on every rank), this shard's columns kept
+                full = torch.randn(T, sh.n_total, 1)
+                noise.copy_(full[:, sh.lo:sh.hi].contiguous().view(-1), non_blocking=False)
         key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(), B,
-               self.value_loss_coef, self.entropy_coef)
+               self.value_loss_coef, self.entropy_coef, world)
         if key != self._prog_key:
             hyper = dict(value_loss_coef=self.value_loss_coef, entropy_coef=self.entropy_coef)
-            self._prog = rt.acktr_programs(rollouts, hyper, noise)
+            self._prog = rt.acktr_programs(rollouts, hyper, noise, inv_B=1.0 / (B * world))
             self._prog_key = key
         progs = self._prog
-        opt._build(rt, rollouts)
+        opt._build(rt, rollouts, world)
         launches0 = _native.launch_count()
         progs["fwd"].run()
         opt.accumulate_a(rt)
@@ -94,8 +120,17 @@ class A2C_ACKTR():
             progs["fisher"].run()
             opt.accumulate_g(rt)
             opt.acc_stats = False
+        if sh is not None:
+            for fname, f in opt.factors.items():      # ~15.6 MB of factor statistics per update (CNN)
+                if fname != "one":
+                    yield f["m"]
         progs["main"].run()
+        if sh is not None:
+            yield rt.arena.bufs["G"]
         opt.step(rt)
         self.last_launches = _native.launch_count() - launches0
-        out = progs["loss_out"][:3].cpu()
+        lo = progs["loss_out"]
+        if sh is not None:
+            yield lo
+        out = lo[:3].cpu()
         return out[0].item(), out[1].item(), out[2].item()

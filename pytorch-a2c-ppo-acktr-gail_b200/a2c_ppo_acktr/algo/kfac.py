@@ -64,12 +64,17 @@ class KFACOptimizer(object):
                                       d=torch.zeros(n, device=dev))
         return self.factors[name]
 
-    def _build(self, rt, rollouts):
-        """Programs for the factor statistics and the preconditioning chain (built once per buffer set)."""
+    def _build(self, rt, rollouts, world=1):
+        """Programs for the factor statistics and the preconditioning chain (built once per buffer set).
+        world > 1: this rank holds 1/world of the batch; factor scales use the GLOBAL batch size and the
+        running-average weight of the old value is divided by world, so that the SUM over ranks of the
+        locally folded factors is decay * m + (1 - decay) * new (the caller all-reduces them)."""
         spec, L, dev = rt.spec, rt.L, rt.dev
         T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         B = T * N
-        key = (id(rt), rollouts.obs.data_ptr(), B)
+        Bg = B * world
+        self.world = world
+        key = (id(rt), rollouts.obs.data_ptr(), B, world)
         if self._built_for == key:
             return
         A, H = spec.num_actions, spec.hidden
@@ -115,31 +120,31 @@ class KFACOptimizer(object):
                 rowC, colC = P.aff(k * c, c, k * cv.K, cv.K, k * k * cv.K), P.aff(k * c, c, k, 1, k * k)
             v = cv.vec_ok()
             a_plans.append(factor_plan("aa_" + name, cv.K, src, src, cv.red_in(), cv.row_in(), cv.row_in(), cv.red_in(),
-                                       rowC, colC, B * Pn, 1.0 / (B * float(Pn) ** 2), 2 if v else 0, 1 if v else 0))
+                                       rowC, colC, B * Pn, 1.0 / (Bg * float(Pn) ** 2), 2 if v else 0, 1 if v else 0))
             g = (gbufs[name][0], gbufs[name][1] + cv.gout_base)
             g_plans.append(factor_plan("gg_" + name, cv.cout, g, g, P.plain(1), cv.row_gout(), cv.row_gout(), P.plain(1),
-                                       P.plain(cv.cout), P.plain(1), B * Pn, float(B * Pn), 2, 1))
+                                       P.plain(cv.cout), P.plain(1), B * Pn, float(Bg * Pn), 2, 1))
             s = buf("s_" + name, B * cv.cout)
             self._spatial.append((s, gbufs[name][0], cv))
             g_plans.append(factor_plan("ggb_" + name, cv.cout, ("kfac_s_" + name, 0), ("kfac_s_" + name, 0), P.plain(1),
                                        P.plain(cv.cout), P.plain(cv.cout), P.plain(1), P.plain(cv.cout), P.plain(1), B,
-                                       float(B), 2, 1))
+                                       float(Bg), 2, 1))
             self.modules.append(_Module(wk, cv.cout, cv.K, "aa_" + name, "gg_" + name))
             self.modules.append(_Module(bk, cv.cout, 1, "one", "ggb_" + name))
         # fc: input a3 (NCHW-flatten order == the reference's), output gradient gh
         a_plans.append(factor_plan("aa_fc", 1568, (tag + "a3", 0), (tag + "a3", 0), P.plain(1), P.plain(1568),
-                                   P.plain(1568), P.plain(1), P.plain(1568), P.plain(1), B, 1.0 / B, 2, 1))
+                                   P.plain(1568), P.plain(1), P.plain(1568), P.plain(1), B, 1.0 / Bg, 2, 1))
         g_plans.append(factor_plan("gg_fc", H, (tag + "gh", 0), (tag + "gh", 0), P.plain(1), P.plain(H), P.plain(H),
-                                   P.plain(1), P.plain(H), P.plain(1), B, float(B), 2, 1))
+                                   P.plain(1), P.plain(H), P.plain(1), B, float(Bg), 2, 1))
         self.modules.append(_Module("base.main.7.weight", H, 1568, "aa_fc", "gg_fc"))
         self.modules.append(_Module("base.main.7.bias", H, 1, "one", "gg_fc"))
         # heads share their input h
         a_plans.append(factor_plan("aa_heads", H, (tag + "h", 0), (tag + "h", 0), P.plain(1), P.plain(H), P.plain(H),
-                                   P.plain(1), P.plain(H), P.plain(1), B, 1.0 / B, 2, 1))
+                                   P.plain(1), P.plain(H), P.plain(1), B, 1.0 / Bg, 2, 1))
         g_plans.append(factor_plan("gg_critic", 1, (tag + "dz", 0), (tag + "dz", 0), P.plain(1), P.plain(zs), P.plain(zs),
-                                   P.plain(1), P.plain(1), P.plain(1), B, float(B), 0, 0))
+                                   P.plain(1), P.plain(1), P.plain(1), B, float(Bg), 0, 0))
         g_plans.append(factor_plan("gg_dist", A, (tag + "dz", 1), (tag + "dz", 1), P.plain(1), P.plain(zs), P.plain(zs),
-                                   P.plain(1), P.plain(A), P.plain(1), B, float(B), 0, 0))
+                                   P.plain(1), P.plain(A), P.plain(1), B, float(Bg), 0, 0))
         hw = "dist.linear"
         self.modules.append(_Module("base.critic_linear.weight", 1, H, "aa_heads", "gg_critic"))
         self.modules.append(_Module("base.critic_linear.bias", 1, 1, "one", "gg_critic"))
@@ -228,7 +233,7 @@ class KFACOptimizer(object):
         """Running average m <- decay m + (1 - decay) new; m = new on the very first update."""
         first = self.steps == 0
         w_new = 1.0 if first else (1.0 - self.stat_decay)
-        beta = 0.0 if first else self.stat_decay
+        beta = 0.0 if first else self.stat_decay / getattr(self, "world", 1)
         gi = 0
         for kind, flags, desc in prog.entries:
             if kind == _engine.OP_GEMM:

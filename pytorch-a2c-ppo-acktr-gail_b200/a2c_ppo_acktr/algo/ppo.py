@@ -112,7 +112,7 @@ class PPO():
         T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         if policy.is_recurrent:
             if self.shard is not None:
-                raise _native.NativeError("sharded recurrent PPO is not built yet")
+                return self._drive(self.sharded_recurrent_steps(rt, rollouts))
             return self._update_recurrent(rt, rollouts)
         batch_size = T * N
         assert batch_size >= self.num_mini_batch, (
@@ -220,12 +220,56 @@ class PPO():
         return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
 
     def _update_sharded(self, rt, rollouts):
-        gen = self.sharded_steps(rt, rollouts)
+        return self._drive(self.sharded_steps(rt, rollouts))
+
+    @staticmethod
+    def _drive(gen):
         try:
             while True:
                 _dist.all_reduce_sum(next(gen))
         except StopIteration as done:
             return done.value
+
+    def sharded_recurrent_steps(self, rt, rollouts):
+        """Recurrent PPO on an environment shard.  Whole environments are the unit of a recurrent
+        minibatch and every rank owns the same number of them, so the global minibatch k is the union
+        over ranks of the k-th chunk of each rank's LOCAL environment permutation: perfectly balanced,
+        nothing padded, no frame or hidden state ever leaves its GPU.  (A single-device run fed the same
+        environment sets gives the same result; the partition is stratified by rank, not one global
+        randperm.)  Yields the tensors to sum-all-reduce, like `sharded_steps`."""
+        sh = self.shard
+        T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+        assert n_loc == sh.n_local and n_loc >= self.num_mini_batch
+        E = n_loc // self.num_mini_batch
+        E_global = E * sh.world
+        moments = _adv_moments(rt, rollouts)
+        yield moments
+        adv = _adv_apply(rt, rollouts, moments)
+        accum = rt.arena.ensure("loss_accum", 4)
+        accum.zero_()
+        prog, opt = self._program(rt, rollouts, T * E, adv, accum, inv_B=1.0 / (T * E_global), seq=(T, E))
+        hxs_mb = rt.arena.bufs["hxs_mb"][:E * rt.spec.hidden].view(E, rt.spec.hidden)
+        h0 = rollouts.recurrent_hidden_states[0]
+        t_off = (torch.arange(T, device=rt.dev, dtype=torch.int64) * n_loc).view(T, 1)
+        grads = rt.arena.bufs["G"]
+        launches0 = _native.launch_count()
+        for _ in range(self.ppo_epoch):
+            perm = torch.randperm(n_loc)                      # same seed on every rank -> same local order
+            for start in range(0, E * self.num_mini_batch, E):
+                env = perm[start:start + E].to(rt.dev)
+                rows = (t_off + env.view(1, E)).reshape(-1).contiguous()
+                _native.gather_rows([(h0, hxs_mb)], env, E)
+                prog.run(rows)
+                yield grads
+                self.optimizer.configure(opt.optim_desc)
+                opt.run()
+                if self.step_hook is not None:
+                    self.step_hook(self.optimizer.step_count)
+        self.last_launches = _native.launch_count() - launches0
+        yield accum
+        num_updates = self.ppo_epoch * self.num_mini_batch
+        sums = accum[:3].cpu()
+        return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
 
     def sharded_steps(self, rt, rollouts):
         """Same update on an environment shard (see _dist.py): global permutation, own rows only,

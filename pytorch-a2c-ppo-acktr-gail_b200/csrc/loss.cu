@@ -35,13 +35,15 @@ loss_kernel(const LossDesc d) {
 #pragma unroll
     for (int a = 0; a < kMaxActions; ++a) dls[a] = 0.f;
 
-    const int n_valid = d.n_valid < 0 ? d.B : d.n_valid;
-    if (b < d.B && b >= n_valid && d.dz) {
+    // padding rows of a sharded minibatch: rows [n_valid, B), or -- time-major recurrent batches padded
+    // per environment -- rows whose environment slot (b % valid_mod) is >= n_valid
+    const bool row_valid = d.n_valid < 0 ? true : (d.valid_mod > 0 ? (b % d.valid_mod) < d.n_valid : b < d.n_valid);
+    if (b < d.B && !row_valid && d.dz) {
         // padding row of a sharded minibatch: contributes nothing
         float* dz = d.dz + (long)b * d.dz_stride;
         for (int j = 0; j <= A; ++j) dz[j] = 0.f;
     }
-    if (b < n_valid) {
+    if (b < d.B && row_valid) {
         const long src = d.idx ? (long)d.idx[b] : (long)b;
         const float* z = d.z + (long)b * d.z_stride;
         const float v = z[0];

@@ -32,6 +32,8 @@ struct LossDesc {
     float clip, c_v, c_e;
     float inv_B;               // 1 / (global minibatch size)
     int32_t n_valid;           // rows [n_valid, B) are padding (dz = 0, no loss); < 0: all B rows valid
+    int32_t valid_mod;         // > 0: row b is valid iff (b % valid_mod) < n_valid (time-major recurrent batches)
+    int32_t pad2_;
 };
 
 }  // namespace a2cb

@@ -34,7 +34,7 @@ def main():
     dev = torch.device("cuda", lr)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
-    name = "C3"
+    name = os.environ.get("A2CB_DIST_CASE", "C3")
     case = helpers.load("update_" + name)
     cfg = helpers.case_config(case)
     ro = helpers.rollout_from_case(case, cfg, obs_uint8=True)
@@ -49,8 +49,11 @@ def main():
     st.to(dev)
     st.compute_returns(ro["next_value"][lo:hi].to(dev), cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"],
                        cfg["use_proper_time_limits"], schedule=1)
-    agent = algo.PPO(pol, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
-                     cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"], max_grad_norm=cfg["max_grad_norm"])
+    if cfg["algo"] == "acktr":
+        agent = algo.A2C_ACKTR(pol, cfg["value_loss_coef"], cfg["entropy_coef"], acktr=True)
+    else:
+        agent = algo.PPO(pol, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
+                         cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"], max_grad_norm=cfg["max_grad_norm"])
     agent.set_distributed(world, rank, (lo, hi), cfg["N"])
     torch.manual_seed(7)
     losses = agent.update(st)
@@ -61,9 +64,10 @@ def main():
     assert torch.equal(flat, ref), "parameters diverged across ranks"
     for k, p in pol.named_parameters():
         helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2, atol=1e-6, what=k, elem_frac=0.1)
+    assert helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters())) <= 2e-3
     dist.barrier()
     if rank == 0:
-        print("dist_check ok: world=%d losses=%s" % (world, losses))
+        print("dist_check ok: case=%s world=%d losses=%s" % (name, world, losses))
     dist.destroy_process_group()
 
 

@@ -301,3 +301,109 @@ def test_acktr_update_vs_reference_golden(name, obs_uint8, gemm_engine):
     got2 = agent.update(st)
     np.testing.assert_allclose(np.array(got2), case["losses2"], rtol=5e-4, atol=5e-6)
     assert opt.steps == 2
+
+
+def _lockstep(ranks):
+    """Steps generator-based sharded updates of several emulated ranks in lock-step on one GPU, summing
+    every yielded tensor across ranks (what NCCL all-reduce does on real hardware)."""
+    results = [None] * len(ranks)
+    while any(r["gen"] is not None for r in ranks):
+        pend = []
+        for i, r in enumerate(ranks):
+            torch.set_rng_state(r["rng"])
+            try:
+                pend.append(next(r["gen"]))
+            except StopIteration as done:
+                results[i] = done.value
+                r["gen"] = None
+            r["rng"] = torch.get_rng_state()
+        if pend:
+            assert len(pend) == len(ranks)
+            total = torch.stack([t.clone() for t in pend]).sum(0)
+            for t in pend:
+                t.copy_(total)
+    return results
+
+
+@pytest.mark.parametrize("name,world", [("C4s", 2), ("C4", 4)])
+def test_sharded_acktr_equals_single_device(name, world, gemm_engine):
+    case = helpers.load("update_" + name)
+    cfg = helpers.case_config(case)
+    ro = helpers.rollout_from_case(case, cfg, obs_uint8=True)
+    per = cfg["N"] // world
+    ranks = []
+    for r in range(world):
+        lo, hi = r * per, (r + 1) * per
+        torch.manual_seed(1)
+        pol = Policy(cfg["obs_shape"], space(cfg["action"])).to(DEV)
+        st = RolloutStorage(cfg["T"], per, cfg["obs_shape"], space(cfg["action"]), 1, obs_dtype=torch.uint8)
+        for nme in ("obs", "recurrent_hidden_states", "rewards", "value_preds", "action_log_probs", "actions",
+                    "masks", "bad_masks"):
+            getattr(st, nme).copy_(ro[nme][:, lo:hi])
+        st.to(DEV)
+        st.compute_returns(ro["next_value"][lo:hi].to(DEV), cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"],
+                           cfg["use_proper_time_limits"], schedule=1)
+        agent = algo.A2C_ACKTR(pol, cfg["value_loss_coef"], cfg["entropy_coef"], acktr=True)
+        agent.set_distributed(world, r, (lo, hi), cfg["N"])
+        torch.manual_seed(7)
+        ranks.append(dict(pol=pol, st=st, agent=agent, rng=torch.get_rng_state(),
+                          gen=agent.acktr_steps(pol.runtime(), st)))
+    results = _lockstep(ranks)
+    for res in results:
+        np.testing.assert_allclose(np.array(res), case["losses"], rtol=1e-4, atol=2e-6)
+    p0 = dict(ranks[0]["pol"].named_parameters())
+    for r in ranks[1:]:
+        for k, p in r["pol"].named_parameters():
+            assert torch.equal(p, p0[k]), k
+    assert helpers.rel_l2(case, "finaldense_", p0) <= 1e-4
+
+
+def test_sharded_recurrent_ppo_equals_single_device(gemm_engine, monkeypatch):
+    """Recurrent PPO on 2 emulated ranks vs ONE device fed the same environment sets per minibatch."""
+    case = helpers.load("update_C5s")
+    cfg = helpers.case_config(case)
+    world, N = 2, cfg["N"]
+    per = N // world
+    ro = helpers.rollout_from_case(case, cfg, obs_uint8=True)
+
+    def make(lo, hi):
+        torch.manual_seed(1)
+        pol = Policy(cfg["obs_shape"], space(cfg["action"]), base_kwargs={"recurrent": True}).to(DEV)
+        st = RolloutStorage(cfg["T"], hi - lo, cfg["obs_shape"], space(cfg["action"]), 512, obs_dtype=torch.uint8)
+        for nme in ("obs", "recurrent_hidden_states", "rewards", "value_preds", "action_log_probs", "actions",
+                    "masks", "bad_masks"):
+            getattr(st, nme).copy_(ro[nme][:, lo:hi])
+        st.to(DEV)
+        st.compute_returns(ro["next_value"][lo:hi].to(DEV), cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"],
+                           cfg["use_proper_time_limits"], schedule=1)
+        agent = algo.PPO(pol, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
+                         cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"], max_grad_norm=cfg["max_grad_norm"])
+        return pol, st, agent
+
+    ranks = []
+    for r in range(world):
+        pol, st, agent = make(r * per, (r + 1) * per)
+        agent.set_distributed(world, r, (r * per, (r + 1) * per), N)
+        torch.manual_seed(7)
+        ranks.append(dict(pol=pol, st=st, agent=agent, rng=torch.get_rng_state(),
+                          gen=agent.sharded_recurrent_steps(pol.runtime(), st)))
+    sharded = _lockstep(ranks)
+    # single device, with the global permutation the stratified scheme implies
+    nmb, E = cfg["num_mini_batch"], per // cfg["num_mini_batch"]
+    torch.manual_seed(7)
+    perms = []
+    for _ in range(cfg["ppo_epoch"]):
+        lp = torch.randperm(per)
+        perms.append(torch.cat([torch.cat([r * per + lp[k * E:(k + 1) * E] for r in range(world)]) for k in range(nmb)]))
+    pol, st, agent = make(0, N)
+    it = iter(perms)
+    real = torch.randperm
+    monkeypatch.setattr(torch, "randperm", lambda n, *a, **k: next(it) if n == N else real(n, *a, **k))
+    single = agent.update(st)
+    monkeypatch.undo()
+    np.testing.assert_allclose(np.array(sharded[0]), np.array(single), rtol=1e-4, atol=2e-6)
+    p1 = dict(pol.named_parameters())
+    for k, p in ranks[0]["pol"].named_parameters():
+        d = (p - p1[k]).double().norm() / p1[k].double().norm().clamp_min(1e-30)
+        assert d <= 2e-4, (k, d.item())
+        assert torch.equal(p, dict(ranks[1]["pol"].named_parameters())[k])
