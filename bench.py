@@ -316,8 +316,6 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
         return None, None
     T, N = cfg["T"], cfg["N"]
     mbs = prog.builder.B if hasattr(prog, "builder") else T * N
-    if cfg.get("recurrent"):
-        return None, None                # recurrent programs need per-minibatch state set up by update()
     names, flops = [], []
     for kind, flags, desc in prog.entries:
         if kind == _engine.OP_GEMM:
@@ -342,7 +340,17 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
         p = _engine.Program(dev)
         p.add(kind, desc, flags)
         singles.append(p.finalize())
-    idx = torch.randperm(T * N)[:mbs].to(dev)
+    if cfg.get("recurrent"):
+        # a recurrent minibatch = E whole environments, rows time-major; initial state gathered per minibatch
+        from a2c_ppo_acktr import _native as nat
+        E = mbs // T
+        rt = agent.actor_critic.runtime()
+        env = torch.randperm(N)[:E].to(dev)
+        idx = ((torch.arange(T, device=dev, dtype=torch.int64) * N).view(T, 1) + env.view(1, E)).reshape(-1).contiguous()
+        hxs_mb = rt.arena.bufs["hxs_mb"][:E * rt.spec.hidden].view(E, rt.spec.hidden)
+        nat.gather_rows([(st.recurrent_hidden_states[0], hxs_mb)], env, E)
+    else:
+        idx = torch.randperm(T * N)[:mbs].to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     times = np.zeros(len(singles))
     for r in range(reps + 2):
@@ -357,17 +365,26 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
             times += np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(len(singles))])
     times /= reps
     total = times.sum()
-    rows = []
+    # aggregate by op label (a recurrent program repeats the per-time-step ops T times)
+    agg = {}
     for lab, t, f in zip(labels, times, flops):
-        rows.append({"op": lab, "ms": float(t), "share": float(t / total), "tflops": float(f / t / 1e9) if f else None})
-    top = int(np.argmax(times))
+        a = agg.setdefault(lab, [0.0, 0.0, 0])
+        a[0] += t; a[1] += f; a[2] += 1
+    rows = [{"op": lab, "launches": a[2], "ms": float(a[0]), "share": float(a[0] / total),
+             "tflops": float(a[1] / a[0] / 1e9) if a[1] else None} for lab, a in agg.items()]
+    rows.sort(key=lambda r: -r["ms"])
+    gemm_rows = [r for r in rows if r["tflops"] is not None]
+    top = gemm_rows[0]
+    from a2c_ppo_acktr import _native as nat
     peak = pk["tensor_sustained"]
-    roof = {"bound": "tensor", "kernel": "gemm_kernel (%s)" % labels[top], "achieved": rows[top]["tflops"],
-            "peak": peak, "unit": "TFLOP/s", "frac": (rows[top]["tflops"] or 0.0) / peak, "traffic": None,
-            "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside the step; fp32 SIMT engine, "
-                           "no TF32 peak is published for this pool)",
-            "share_of_step": rows[top]["share"], "launch_ms": rows[top]["ms"]}
-    return roof, rows
+    roof = {"bound": "tensor", "kernel": "a2cb::gemm_tc_kernel / gemm_kernel (%s)" % top["op"],
+            "achieved": top["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": top["tflops"] / peak, "traffic": None,
+            "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step); algorithmic fp32 "
+                           "flops: the tensor-core engine spends 3 TF32 MMAs per product (3xTF32), so <= 1/3 of a "
+                           "TF32 peak (no TF32 figure is published for this pool) is attainable",
+            "share_of_step": top["share"], "launch_ms": top["ms"] / top["launches"], "launches_per_step": top["launches"],
+            "step_program_ms": float(total), "gemm_engine_mode": int(nat.lib().a2cb_get_gemm_mode())}
+    return roof, rows[:24]
 
 
 def scan_roofline(dev, pk):
@@ -424,6 +441,15 @@ def cpu_update_once(cfg, state):
     return time.perf_counter() - t0, out[:3]
 
 
+def cpu_sample_config(cfg):
+    """Bounded CPU sample: workloads with more than 4096 transitions per update are timed on a reduced
+    number of environments (the per-transition cost of the reference path does not depend on it)."""
+    c = dict(cfg)
+    if c["T"] * c["N"] > 4096 and c["N"] > 1:
+        c["N"] = max(c.get("num_mini_batch", 1) * 4, 2048 // c["T"])
+    return c
+
+
 def cpu_state(cfg):
     from oracle import policy as o_pol
     from oracle import update as o_upd
@@ -439,6 +465,10 @@ def cpu_state(cfg):
 def cpu_baseline(cfg, steps=3, warmup=1):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    full = cfg
+    cfg = cpu_sample_config(cfg)
+    if cfg["T"] * cfg["N"] > 2048:
+        steps = 2
     state = cpu_state(cfg)
     ts = []
     for i in range(warmup + steps):
@@ -447,16 +477,18 @@ def cpu_baseline(cfg, steps=3, warmup=1):
         if i >= warmup:
             ts.append(dt)
     tr = cfg["T"] * cfg["N"]
+    what = "full" if cfg["N"] == full["N"] else "reduced (%d of %d environments)" % (cfg["N"], full["N"])
     return {"value": tr / float(np.mean(ts)), "unit": "transitions/s", "cores": cores, "kind": "port",
-            "sample": "%d full %s updates (%d transitions each) of the oracle port (torch %s CPU, %d threads), "
-                      "mean %.3f s/update" % (steps, cfg["name"], tr, torch.__version__, cores, float(np.mean(ts)))}
+            "sample": "%d %s %s updates (%d transitions each) of the oracle port (torch %s CPU, %d threads), "
+                      "mean %.3f s/update" % (steps, what, cfg["name"], tr, torch.__version__, cores, float(np.mean(ts)))}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = workload_config(args.workload)
+    full = workload_config(args.workload)
+    cfg = cpu_sample_config(full)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     state = cpu_state(cfg)
@@ -468,15 +500,16 @@ def run_reference(args):
             ts.append(dt)
     tr = cfg["T"] * cfg["N"]
     val = tr / float(np.mean(ts))
-    sample = "%d full %s updates of the oracle port of the reference (torch %s CPU, %d threads)" % (
-        args.steps, cfg["name"], torch.__version__, cores)
+    what = "full" if cfg["N"] == full["N"] else "reduced (%d of %d environments per GPU)" % (cfg["N"], full["N"])
+    sample = "%d %s %s updates (%d transitions each) of the oracle port of the reference (torch %s CPU, %d threads)" % (
+        args.steps, what, cfg["name"], tr, torch.__version__, cores)
     print(json.dumps({
         "impl": "reference", "metric": "%s update transitions/sec" % cfg["algo"].upper(),
         "value": val, "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(ts)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (cfg["name"], describe(cfg)), "envs_per_gpu": cfg["N"], "num_steps": cfg["T"],
-                   "step": "compute_returns + update + after_update"},
+        "config": {"workload": "%s: %s" % (full["name"], describe(full)), "envs_per_gpu": full["N"], "num_steps": full["T"],
+                   "step": "compute_returns + update + after_update", "cpu_sample_envs": cfg["N"]},
         "cpu_baseline": {"value": val, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "losses": [float(x) for x in losses],
@@ -489,7 +522,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C3", choices=sorted(synthetic.CONFIGS))
+    ap.add_argument("--workload", default="C5", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--envs", type=int, default=0, help="override the number of environments per GPU")
     args = ap.parse_args()

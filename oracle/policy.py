@@ -116,12 +116,16 @@ def gru_forward(p, x, hxs, masks):
     T = x.shape[0] // N
     xs = x.view(T, N, -1)
     ms = masks.view(T, N, 1)
-    h = hxs
+    # Like the reference (model.py:129-157): run the fused aten GRU over every stretch of steps in
+    # which no environment resets, multiplying the carried state by the mask at the stretch start.
+    w = [p["base.gru.weight_ih_l0"], p["base.gru.weight_hh_l0"], p["base.gru.bias_ih_l0"], p["base.gru.bias_hh_l0"]]
+    cuts = [0] + [t for t in range(1, T) if bool((ms[t] == 0.0).any())] + [T]
+    h = hxs.unsqueeze(0)
     outs = []
-    for t in range(T):
-        h = gru_cell(p, xs[t], h * ms[t])
-        outs.append(h)
-    return torch.cat(outs, 0), h
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        y, h = torch._VF.gru(xs[a:b], h * ms[a].view(1, N, 1), w, True, 1, 0.0, False, False, False)
+        outs.append(y)
+    return torch.cat(outs, 0).view(T * N, -1), h.squeeze(0)
 
 
 def base_forward(p, spec, obs, hxs, masks):

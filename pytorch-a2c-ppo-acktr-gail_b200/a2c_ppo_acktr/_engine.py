@@ -467,8 +467,11 @@ class NetBuilder(object):
         ops = [P.linear_forward(self.gru_in, B, x, wih, bih, gi),
                RawOp(OP_GRU_INIT, dict(hm=hm, h0=self.hxs_ref, masks=self.masks_ref), dict(T=T, N=N, H=H, t=0),
                      self.gather, "gru.init")]
+        sp = forward_splits(N, 3 * H, H)          # the per-step GEMM is tiny (M = environments): split K
+        part = self.buf("part_gru_hh_fwd", sp * N * 3 * H) if sp > 1 else None
         for t in range(T):
-            ops.append(P.linear_forward(self.gru_hh, N, (hm[0], t * N * H), whh, bhh, (gh[0], t * N * 3 * H)))
+            ops.append(P.linear_forward(self.gru_hh, N, (hm[0], t * N * H), whh, bhh, (gh[0], t * N * 3 * H),
+                                        splits=sp, partial=part))
             ops[-1].name = "gru_hh.fwd"
             ops.append(RawOp(OP_GRU_FWD, fields, dict(T=T, N=N, H=H, t=t), self.gather, "gru.gates"))
         return ops, out
@@ -485,10 +488,13 @@ class NetBuilder(object):
         fields = {k: (self.n("gru_" + k), 0) for k in names}
         fields.update(masks=self.masks_ref, dout=dout, dgi=dgi, dgh=dgh, dcarry=dcarry)
         ops = []
+        sp = forward_splits(N, H, 3 * H)
+        part = self.buf("part_gru_hh_dgrad", sp * N * H) if sp > 1 else None
         for t in range(T - 1, -1, -1):
             ops.append(RawOp(OP_GRU_BWD, fields, dict(T=T, N=N, H=H, t=t), self.gather, "gru.gates_bwd"))
             if t > 0:
-                p = P.linear_dgrad(self.gru_hh, N, (dgh[0], t * N * 3 * H), whh, dcarry, accumulate=1)
+                p = P.linear_dgrad(self.gru_hh, N, (dgh[0], t * N * 3 * H), whh, dcarry, accumulate=1,
+                                   splits=sp, partial=part)
                 p.name = "gru_hh.dgrad"
                 ops.append(p)
         hm = (self.n("gru_hm"), 0)

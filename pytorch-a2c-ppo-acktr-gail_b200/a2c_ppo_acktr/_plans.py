@@ -314,16 +314,23 @@ def linear_forward(ln, B, x, w, b, y, act=ACT_NONE, x_stride=None, y_stride=None
 
 
 def linear_dgrad(ln, B, gy, w, gx, mask=None, mask_mode=0, gy_stride=None, col_out=None, row_out=None,
-                 gx_base=0, accumulate=0, mask_row=None, mask_col=None):
+                 gx_base=0, accumulate=0, mask_row=None, mask_col=None, splits=1, partial=None):
     """gx[b, k] = mask * sum_n gy[b, n] W[n, perm(k)].  col_out/row_out let the result land in a
-    haloed NHWC gradient buffer."""
+    haloed NHWC gradient buffer.  splits > 1 (dense [B, d_in] output, no mask): split-K partials folded
+    (and, with accumulate, added onto gx) by reduce_splits -- for the tiny per-time-step GRU GEMMs."""
     gs = gy_stride or ln.d_out
-    return Plan(ln.name + ".dgrad", gy, w, (gx[0], gx[1] + gx_base), B, ln.d_in, ln.d_out,
+    kw = {}
+    C = (gx[0], gx[1] + gx_base)
+    if splits > 1:
+        assert mask is None and row_out is None and col_out is None and gx_base == 0
+        kw = dict(splits=splits, split_stride=B * ln.d_in, split_dst=(gx[0], gx[1], B * ln.d_in))
+        C = partial
+    return Plan(ln.name + ".dgrad", gy, w, C, B, ln.d_in, ln.d_out,
                 rowA=plain(gs), redA=plain(1), redB=plain(ln.d_in), colB=ln.in_perm,
                 rowC=row_out or plain(ln.d_in), colC=col_out or plain(1),
                 rowM=mask_row or plain(ln.d_in), colM=mask_col or plain(1), mask=mask, mask_mode=mask_mode,
                 accumulate=accumulate, vecA=1 if (ln.d_out % 4 == 0 and gs % 4 == 0) else 0,
-                vecB=1 if (ln.in_perm == plain(1) and ln.d_in % 4 == 0) else 0)
+                vecB=1 if (ln.in_perm == plain(1) and ln.d_in % 4 == 0) else 0, **kw)
 
 
 def linear_wgrad(ln, B, x, gy, dw, db, x_stride=None, gy_stride=None, splits=1, partial=None, accumulate=0):
