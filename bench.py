@@ -323,7 +323,7 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
             flops.append(2.0 * desc.M * desc.N * desc.K * desc.batch)
         else:
             names.append({2: "reduce_splits", 3: "loss_epilogue", 4: "grad_norm", 5: "optim_step", 7: "gru_init",
-                          8: "gru_gates", 9: "gru_gates_bwd"}.get(kind, "op%d" % kind))
+                          8: "gru_gates", 9: "gru_gates_bwd", 10: "bias_pixel_sum"}.get(kind, "op%d" % kind))
             flops.append(0.0)
     # label GEMMs by their plan
     labels = []

@@ -237,6 +237,7 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_GRU_INIT 7
 #define A2CB_OP_GRU_FWD 8
 #define A2CB_OP_GRU_BWD 9
+#define A2CB_OP_SPATIAL_SUM 10
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -250,6 +251,7 @@ typedef struct {
                            so a CUDA graph holding a whole epoch of optimiser steps is replayed without re-capture */
 } a2cb_optim_t;
 typedef struct { void* dst; int64_t bytes; int32_t value; int32_t pad_; } a2cb_fill_t;
+typedef struct { float* out; const float* in; int64_t img_stride; int64_t pitch; int32_t B, P, C, ow; } a2cb_spatial_sum_t;
 typedef struct { int32_t kind; int32_t flags; const void* desc; } a2cb_op_t;
 
 int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream);

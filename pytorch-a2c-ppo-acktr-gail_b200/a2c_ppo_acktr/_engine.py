@@ -19,7 +19,7 @@ from . import _plans as P
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
 OP_GEMM, OP_REDUCE, OP_LOSS, OP_GRAD_NORM, OP_OPTIM, OP_FILL = 1, 2, 3, 4, 5, 6
-OP_GRU_INIT, OP_GRU_FWD, OP_GRU_BWD = 7, 8, 9
+OP_GRU_INIT, OP_GRU_FWD, OP_GRU_BWD, OP_SPATIAL_SUM = 7, 8, 9, 10
 RUNTIME_IDX = 1
 SENTINEL = 1          # non-NULL placeholder for "use the runtime minibatch index list"
 
@@ -65,11 +65,17 @@ class GruDesc(ctypes.Structure):
                 ("dcarry", c_vp), ("T", c_i32), ("N", c_i32), ("H", c_i32), ("t", c_i32)]
 
 
+class SpatialSumDesc(ctypes.Structure):
+    _fields_ = [("out", c_vp), ("in_", c_vp), ("img_stride", c_i64), ("pitch", c_i64), ("B", c_i32), ("P", c_i32),
+                ("C", c_i32), ("ow", c_i32)]
+
+
 class RawOp(object):
     """A non-GEMM op in a plan list: kind + symbolic fields resolved against the arena."""
 
-    def __init__(self, kind, fields, ints, runtime_idx=False, name="op"):
+    def __init__(self, kind, fields, ints, runtime_idx=False, name="op", struct=None):
         self.kind, self.fields, self.ints, self.runtime_idx, self.name = kind, fields, ints, runtime_idx, name
+        self.struct = struct
 
 
 class Op(ctypes.Structure):
@@ -187,7 +193,7 @@ class Program(object):
 
     def add_plan(self, plan, arena):
         if isinstance(plan, RawOp):
-            d = GruDesc()
+            d = (plan.struct or GruDesc)()
             for k, ref in plan.fields.items():
                 setattr(d, k, arena.ptr(ref))
             for k, v in plan.ints.items():
@@ -195,6 +201,7 @@ class Program(object):
             if plan.runtime_idx:
                 d.idx = SENTINEL
             self.add(plan.kind, d, RUNTIME_IDX if plan.runtime_idx else 0)
+            self.plan_names_all = getattr(self, "plan_names_all", [])
             return
         flags = RUNTIME_IDX if (plan.gather_row or plan.gather_red) else 0
         self.add(OP_GEMM, resolve(plan, arena), flags)
@@ -373,16 +380,34 @@ class NetBuilder(object):
                            gx_base=c3.gout_base, mask_row=P.plain(1568), mask_col=P.plain(1)),
         ]
         for cv, src, g, gprev, prev, a_prev in ((c3, a2, g3, g2, c2, a2), (c2, a1, g2, g1, c1, a1)):
-            sp = choose_splits(cv.K + 1, cv.cout, B * cv.oh * cv.ow)
-            part = self.buf("part_" + cv.name, sp * (cv.cout * cv.K + cv.cout)) if sp > 1 else None
-            plans.append(P.conv_wgrad(cv, B, src, g, *self.gwb(cv.name), splits=sp, partial=part))
+            plans += self.conv_wgrad_ops(cv, src, g)
             plans.append(P.conv_dgrad(cv, B, g, ("P", self.L.layers[cv.name][0]), gprev,
                                       (prev.gout_row, prev.pw, prev.gout_base), mask=a_prev))
-        sp = choose_splits(c1.K + 1, c1.cout, B * c1.oh * c1.ow)
-        part = self.buf("part_conv1", sp * (c1.cout * c1.K + c1.cout)) if sp > 1 else None
-        plans.append(P.conv_wgrad(c1, B, (self.obs, 0), g1, *self.gwb("conv1"), a_u8=self.obs_code,
-                                  gather=self.gather, splits=sp, partial=part))
+        plans += self.conv_wgrad_ops(c1, (self.obs, 0), g1, a_u8=self.obs_code, gather=self.gather)
         return plans
+
+    def conv_wgrad_ops(self, cv, src, g, a_u8=False, gather=False):
+        """Weight (+ bias) gradient of one conv layer.  The bias gradient is normally the logical ones row
+        of the same GEMM; when the patch size K is a multiple of the 128-row tile that row would cost a
+        whole extra tile row of CTAs (conv1: +50%), so it is computed as a pixel sum + batch fold instead."""
+        B = self.B
+        wref, bref = self.gwb(cv.name)
+        fused_bias = cv.K % 128 != 0
+        rows = cv.K + (1 if fused_bias else 0)
+        sp = choose_splits(rows, cv.cout, B * cv.oh * cv.ow)
+        span = cv.cout * cv.K + (cv.cout if fused_bias else 0)
+        part = self.buf("part_" + cv.name, sp * span) if sp > 1 else None
+        ops = [P.conv_wgrad(cv, B, src, g, wref, bref if fused_bias else None, a_u8=a_u8, gather=gather,
+                            splits=sp, partial=part)]
+        if not fused_bias:
+            s = self.buf("bsum_" + cv.name, B * cv.cout)
+            ops.append(RawOp(OP_SPATIAL_SUM, {"out": s, "in_": (g[0], g[1] + cv.gout_base)},
+                             dict(img_stride=cv.gout_row, pitch=cv.pw * cv.cout, B=B, P=cv.oh * cv.ow, C=cv.cout,
+                                  ow=cv.ow), False, cv.name + ".bias_psum", SpatialSumDesc))
+            ops.append(RawOp(OP_REDUCE, {"dst": bref, "src": s},
+                             dict(count=cv.cout, stride=cv.cout, splits=B, accumulate=0, ncols=0, act=0, beta=1.0),
+                             False, cv.name + ".bias_fold", ReduceDesc))
+        return ops
 
     # ---- MLP ----
     def mlp_forward(self, x=None, d_in=None):
@@ -830,7 +855,7 @@ class PolicyRuntime(object):
         progs["fisher"] = Program(self.dev)
         progs["fisher"].add(OP_LOSS, loss(2, lo_f))
         for p in bwd:
-            if not p.name.endswith(".wgrad"):
+            if not (p.name.endswith(".wgrad") or ".bias_" in p.name):     # data gradients only
                 progs["fisher"].add_plan(p, self.arena)
         progs["main"] = Program(self.dev)
         progs["main"].add(OP_LOSS, loss(1, lo))

@@ -246,10 +246,12 @@ def conv_wgrad(cv, B, src, gout, dw, db, a_u8=False, gather=False, splits=1, par
     kw = {}
     C, ones = dw, db
     if splits > 1:
-        span = cv.cout * cv.K + cv.cout
-        C, ones = (partial[0], partial[1]), (partial[0], partial[1] + cv.cout * cv.K)
+        span = cv.cout * cv.K + (cv.cout if db is not None else 0)
+        C = (partial[0], partial[1])
+        ones = (partial[0], partial[1] + cv.cout * cv.K) if db is not None else None
         kw = dict(splits=splits, split_stride=span, split_dst=(dw[0], dw[1], span))
-        assert db[1] == dw[1] + cv.cout * cv.K and db[0] == dw[0], "bias must follow the weight in the flat buffer"
+        assert db is None or (db[1] == dw[1] + cv.cout * cv.K and db[0] == dw[0]), \
+            "bias must follow the weight in the flat buffer"
     return Plan(cv.name + ".wgrad", src, (gout[0], gout[1] + cv.gout_base), C, cv.K, cv.cout, B * cv.oh * cv.ow,
                 rowA=cv.red_in(), redA=cv.row_in(), redB=cv.row_gout(), colB=plain(1),
                 rowC=row_w, colC=plain(cv.K), ones=ones, ones_stride=1, a_u8=a_u8, gather_red=gather,

@@ -181,6 +181,11 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
                 if (e != cudaSuccess) { set_error("run_ops: memset: %s", cudaGetErrorString(e)); rc = A2CB_ERR_CUDA; }
                 break;
             }
+            case A2CB_OP_SPATIAL_SUM: {
+                const a2cb_spatial_sum_t& q = *reinterpret_cast<const a2cb_spatial_sum_t*>(op.desc);
+                rc = spatial_sum(q.out, q.in, q.B, q.P, q.C, q.ow, (long)q.img_stride, (long)q.pitch, st);
+                break;
+            }
             case A2CB_OP_GRU_INIT:
             case A2CB_OP_GRU_FWD:
             case A2CB_OP_GRU_BWD: {

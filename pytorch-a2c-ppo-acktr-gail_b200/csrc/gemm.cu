@@ -36,10 +36,13 @@ __device__ __forceinline__ long affine_eval(const Affine3& a, long i, const int6
 }
 
 // ADT: 0 fp32 as is, 1 uint8 / 255, 2 fp32 / 255 (frames kept as fp32 0..255, reference layout).
-// True IEEE division, so the value equals torch's `inputs / 255.0` bit for bit (model.py:190).
+// ADT 2 uses true IEEE division, so the operand equals torch's `inputs / 255.0` bit for bit
+// (model.py:190).  ADT 1 keeps the byte as an exact integer-valued float and folds the 1/255 into
+// the epilogue scale: sum(v w) / 255 instead of sum(fl(v / 255) w) -- equal to <= 1 ulp per
+// product, no division per element, and exact in TF32 for the tensor-core engine.
 template <int ADT>
 __device__ __forceinline__ float load_a1(const void* A, long off) {
-    if (ADT == 1) return (float)__ldg(reinterpret_cast<const uint8_t*>(A) + off) / 255.0f;
+    if (ADT == 1) return (float)__ldg(reinterpret_cast<const uint8_t*>(A) + off);
     const float v = __ldg(reinterpret_cast<const float*>(A) + off);
     return ADT == 2 ? v / 255.0f : v;
 }
@@ -47,7 +50,7 @@ template <int ADT>
 __device__ __forceinline__ float4 load_a4(const void* A, long off) {
     if (ADT == 1) {
         const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(A) + off));
-        return make_float4((float)u.x / 255.0f, (float)u.y / 255.0f, (float)u.z / 255.0f, (float)u.w / 255.0f);
+        return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
     }
     float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(A) + off));
     if (ADT == 2) { v.x /= 255.0f; v.y /= 255.0f; v.z /= 255.0f; v.w /= 255.0f; }
@@ -281,11 +284,11 @@ gemm_kernel(const GemmDesc g) {
         for (int n = 0; n < TN; ++n) {
             const int jl = tx * TN + n;
             if (!cvalid[jl]) continue;
-            float v = acc[m][n] * g.alpha;
-            if (fl == 1) {
-                g.C_ones[(long)split * g.split_stride + (j0 + jl) * g.ones_stride] = v;
+            if (fl == 1) {       // logical all-ones row: never a byte operand, no 1/255
+                g.C_ones[(long)split * g.split_stride + (j0 + jl) * g.ones_stride] = acc[m][n] * g.alpha;
                 continue;
             }
+            float v = acc[m][n] * (A_U8 == 1 ? g.alpha / 255.0f : g.alpha);
             float* dst = Cb + rC[il] + cC[jl];
             if (final_pass) {
                 if (g.bias_mode == 1) v += __ldg(g.bias + j0 + jl);

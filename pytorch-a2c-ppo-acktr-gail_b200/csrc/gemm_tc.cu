@@ -46,9 +46,11 @@ __device__ __forceinline__ long tc_affine(const Affine3& a, long i, const int64_
     return g0 * a.s0 + (long)q1 * a.s1 + (long)q2 * a.s2;
 }
 
+// ADT 1 (uint8 frames): the byte stays an exact integer-valued float -- exact in TF32, so the A
+// operand needs no lo part and one of the three MMAs disappears; 1/255 is folded into the epilogue.
 template <int ADT>
 __device__ __forceinline__ float tc_load1(const void* A, long off) {
-    if (ADT == 1) return (float)__ldg(reinterpret_cast<const uint8_t*>(A) + off) / 255.0f;
+    if (ADT == 1) return (float)__ldg(reinterpret_cast<const uint8_t*>(A) + off);
     const float v = __ldg(reinterpret_cast<const float*>(A) + off);
     return ADT == 2 ? v / 255.0f : v;
 }
@@ -56,7 +58,7 @@ template <int ADT>
 __device__ __forceinline__ float4 tc_load4(const void* A, long off) {
     if (ADT == 1) {
         const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(A) + off));
-        return make_float4((float)u.x / 255.0f, (float)u.y / 255.0f, (float)u.z / 255.0f, (float)u.w / 255.0f);
+        return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
     }
     float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(A) + off));
     if (ADT == 2) { v.x /= 255.0f; v.y /= 255.0f; v.z /= 255.0f; v.w /= 255.0f; }
@@ -284,11 +286,15 @@ gemm_tc_kernel(const GemmDesc g) {
             int row, kc;
             if (g.vecA == 2) { row = (s >> 5) * 4 + (lane & 3); kc = (s & (TBK - 1)) >> 2; }
             else { row = rowb + 8 * (q & 1); kc = kcb + 4 * (q >> 1); }
-            float4 hi, lo;
-            split4(a_reg[q], hi, lo);
             const uint32_t o = tile_off(row, kc);
-            *reinterpret_cast<float4*>(Ah + o) = hi;
-            *reinterpret_cast<float4*>(Al + o) = lo;
+            if (ADT == 1) {
+                *reinterpret_cast<float4*>(Ah + o) = a_reg[q];     // bytes (and the ones row) are exact in TF32
+            } else {
+                float4 hi, lo;
+                split4(a_reg[q], hi, lo);
+                *reinterpret_cast<float4*>(Ah + o) = hi;
+                *reinterpret_cast<float4*>(Al + o) = lo;
+            }
         }
 #pragma unroll
         for (int q = 0; q < B_NV; ++q) {
@@ -373,8 +379,9 @@ gemm_tc_kernel(const GemmDesc g) {
 #pragma unroll
             for (int ks = 0; ks < TBK / 8; ++ks) {
                 const uint32_t o = ks * 256;                 // two 128-byte core matrices per K = 8 step
-                umma_tf32(d, umma_desc(al + o), umma_desc(bh + o), idesc, (!chain_start || ks > 0) ? 1u : 0u);
-                umma_tf32(d, umma_desc(ah + o), umma_desc(bl + o), idesc, 1u);
+                const uint32_t acc0 = (!chain_start || ks > 0) ? 1u : 0u;
+                if (ADT != 1) umma_tf32(d, umma_desc(al + o), umma_desc(bh + o), idesc, acc0);
+                umma_tf32(d, umma_desc(ah + o), umma_desc(bl + o), idesc, ADT != 1 ? 1u : acc0);
                 umma_tf32(d, umma_desc(ah + o), umma_desc(bh + o), idesc, 1u);
             }
             tc_commit(&mbar[s]);
@@ -399,11 +406,11 @@ gemm_tc_kernel(const GemmDesc g) {
         for (int n = 0; n < HALF; ++n) {
             const int jl = (warp >> 2) * HALF + n;
             if (!cvalid[jl]) continue;
-            float x = acc[n] * g.alpha;
             if (fl == 1) {
-                g.C_ones[(long)split * g.split_stride + (j0 + jl) * g.ones_stride] = x;
+                g.C_ones[(long)split * g.split_stride + (j0 + jl) * g.ones_stride] = acc[n] * g.alpha;
                 continue;
             }
+            float x = acc[n] * (ADT == 1 ? g.alpha / 255.0f : g.alpha);
             float* dst = Cb + rC[il] + cC[jl];
             if (final_pass) {
                 if (g.bias_mode == 1) x += __ldg(g.bias + j0 + jl);

