@@ -130,13 +130,6 @@ def workload_config(name):
     return cfg
 
 
-def host_rollout(cfg, policy_act, policy_value, hidden, env_range=None, N_total=None):
-    """Synthetic rollout on the host (pinned), policy-consistent (actions from Policy.act)."""
-    ro = synthetic.make_rollout(cfg, policy_act, policy_value, hidden, seed=0, env_range=env_range,
-                                N_total=N_total, obs_uint8=(cfg["kind"] == "atari"))
-    return ro
-
-
 def run_ours(args):
     import torch.distributed as dist
     from a2c_ppo_acktr import _native, algo
@@ -221,7 +214,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n_steps, e2e):
+    def timed(n_steps, e2e, profile_once=False):
         """Device-timed steps (CUDA events on the launching stream), L2 flushed between steps."""
         total_ms = 0.0
         losses = None
@@ -232,11 +225,17 @@ def run_ours(args):
             flush.zero_()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            prof = profile_once and not e2e and i == 0 and os.environ.get("A2CB_PROFILE_STEP") == "1"
+            if prof:
+                torch.cuda.profiler.start()                    # ncu --profile-from-start off: one timed step
             e0.record()
             if e2e:
                 nv = upload()
             losses = hot_path(nv)                              # update() ends with the D2H of the losses
             e1.record()
+            if prof:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.stop()
             barrier()
             ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
             if world > 1:
@@ -251,7 +250,7 @@ def run_ours(args):
     time.sleep(0.25)
     t0 = time.time()
     l0 = _native.launch_count()
-    total_ms, losses = timed(args.steps, False)
+    total_ms, losses = timed(args.steps, False, profile_once=True)
     launches = _native.launch_count() - l0
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
@@ -323,7 +322,7 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
             flops.append(2.0 * desc.M * desc.N * desc.K * desc.batch)
         else:
             names.append({2: "reduce_splits", 3: "loss_epilogue", 4: "grad_norm", 5: "optim_step", 7: "gru_init",
-                          8: "gru_gates", 9: "gru_gates_bwd", 10: "bias_pixel_sum"}.get(kind, "op%d" % kind))
+                          8: "gru_gates", 9: "gru_gates_bwd", 10: "bias_pixel_sum", 11: "weight_prep"}.get(kind, "op%d" % kind))
             flops.append(0.0)
     # label GEMMs by their plan
     labels = []

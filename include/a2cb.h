@@ -133,9 +133,16 @@ typedef struct {
                            the partial sum is drained into fp32 registers (the tensor core's accumulator
                            truncates; short chains keep long, cancelling reductions exact enough).  0 = 8 */
     int32_t pad_;
+    const float* B_image; /* optional image of B produced by a2cb_gemm_prep_b (weights: once per optimiser step);
+                             the tensor-core engine then loads B with one TMA bulk copy per k-block */
 } a2cb_gemm_t;
 
 int a2cb_gemm(const a2cb_gemm_t* desc, a2cb_stream_t stream);
+/* Writes desc->B_image: for every (batch, column tile, k-block) the B tile split into hi = tf32(b),
+ * lo = tf32(b - hi) and laid out exactly as the tensor-core engine wants it in shared memory
+ * (8-row x 16-byte core matrices, K-major).  a2cb_gemm_b_image_floats gives the buffer size. */
+int a2cb_gemm_prep_b(const a2cb_gemm_t* desc, a2cb_stream_t stream);
+int64_t a2cb_gemm_b_image_floats(const a2cb_gemm_t* desc);
 /* Engine behind a2cb_gemm: 1 = tcgen05 tensor cores (3xTF32 split operands, chunked fp32 TMEM
  * accumulation) wherever supported; 0 = exact-fp32 SIMT engine; 2 (default) = per-descriptor choice
  * from measured crossover points.  Also A2CB_GEMM=simt|tc|auto, or per descriptor tile = 1000 (force
@@ -238,6 +245,7 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_GRU_FWD 8
 #define A2CB_OP_GRU_BWD 9
 #define A2CB_OP_SPATIAL_SUM 10
+#define A2CB_OP_GEMM_PREP_B 11
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -268,7 +276,7 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
  * ------------------------------------------------------------------------- */
 typedef struct {
     const float* gi;
-    const float* gh;
+    float* gh;
     float* hm;
     const float* h0;
     const float* masks;
@@ -278,7 +286,11 @@ typedef struct {
     const float* dout;
     float* dgi; float* dgh;
     float* dcarry;
+    const float* gh_part;   /* optional split-K partials [gh_splits][N,3H] of this step's hm W_hh^T: folded (+ gh_bias) */
+    const float* gh_bias;   /*   by the forward gate kernel itself, which then also writes gh                        */
+    const float* dc_part;   /* optional split-K partials [dc_splits][N,H] of dgh_{t+1} W_hh, folded by the backward kernel */
     int32_t T, N, H, t;
+    int32_t gh_splits, dc_splits;
 } a2cb_gru_t;
 
 int a2cb_gru_op(int32_t which, const a2cb_gru_t* desc, a2cb_stream_t stream);

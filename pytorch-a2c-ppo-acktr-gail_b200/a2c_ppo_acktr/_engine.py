@@ -19,7 +19,7 @@ from . import _plans as P
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
 OP_GEMM, OP_REDUCE, OP_LOSS, OP_GRAD_NORM, OP_OPTIM, OP_FILL = 1, 2, 3, 4, 5, 6
-OP_GRU_INIT, OP_GRU_FWD, OP_GRU_BWD, OP_SPATIAL_SUM = 7, 8, 9, 10
+OP_GRU_INIT, OP_GRU_FWD, OP_GRU_BWD, OP_SPATIAL_SUM, OP_GEMM_PREP_B = 7, 8, 9, 10, 11
 RUNTIME_IDX = 1
 SENTINEL = 1          # non-NULL placeholder for "use the runtime minibatch index list"
 
@@ -62,7 +62,8 @@ class GruDesc(ctypes.Structure):
     """Mirror of a2cb_gru_t."""
     _fields_ = [("gi", c_vp), ("gh", c_vp), ("hm", c_vp), ("h0", c_vp), ("masks", c_vp), ("idx", c_vp),
                 ("out", c_vp), ("r", c_vp), ("z", c_vp), ("n", c_vp), ("dout", c_vp), ("dgi", c_vp), ("dgh", c_vp),
-                ("dcarry", c_vp), ("T", c_i32), ("N", c_i32), ("H", c_i32), ("t", c_i32)]
+                ("dcarry", c_vp), ("gh_part", c_vp), ("gh_bias", c_vp), ("dc_part", c_vp),
+                ("T", c_i32), ("N", c_i32), ("H", c_i32), ("t", c_i32), ("gh_splits", c_i32), ("dc_splits", c_i32)]
 
 
 class SpatialSumDesc(ctypes.Structure):
@@ -84,6 +85,8 @@ class Op(ctypes.Structure):
 
 _native.register({
     "a2cb_gemm": (c_i32, [ctypes.POINTER(P.GemmDesc), c_vp]),
+    "a2cb_gemm_prep_b": (c_i32, [ctypes.POINTER(P.GemmDesc), c_vp]),
+    "a2cb_gemm_b_image_floats": (c_i64, [ctypes.POINTER(P.GemmDesc)]),
     "a2cb_reduce_splits": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32, c_i32, c_f32, c_vp]),
     "a2cb_spatial_sum": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_vp]),
     "a2cb_kfac_scale": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_f32, c_vp]),
@@ -157,7 +160,15 @@ def resolve(plan, arena):
     g.splits, g.split_stride = plan.splits, plan.split_stride
     g.vecA, g.vecB, g.tile = plan.vecA, plan.vecB, plan.tile
     g.tc_chunk = plan.tc_chunk
+    g.B_image = arena.ptr(plan.b_image)
     return g
+
+
+def wants_b_image(plan):
+    """B operand = network weights (flat parameter buffer) of a GEMM the auto-selection sends to the
+    tensor-core engine (mirrors prefer_tc in csrc/gemm.cu)."""
+    return (plan.B[0] == "P" and plan.vecA != 2 and plan.M >= 2048 and plan.K >= 64 and plan.tile < 1000
+            and not plan.a_u8 == 99)
 
 
 def forward_splits(M, N, K):
@@ -204,10 +215,22 @@ class Program(object):
             self.plan_names_all = getattr(self, "plan_names_all", [])
             return
         flags = RUNTIME_IDX if (plan.gather_row or plan.gather_red) else 0
-        self.add(OP_GEMM, resolve(plan, arena), flags)
+        if plan.b_image is None and wants_b_image(plan):
+            # weights feeding a tensor-core GEMM: pre-tile + pre-split them once per step (they change with
+            # every optimiser step) so that every CTA fetches its B blocks by TMA instead of gathering them
+            bn = 32 if plan.N <= 32 else (64 if plan.N <= 64 else 128)
+            floats = plan.batch * ((plan.N + bn - 1) // bn) * ((plan.K + 31) // 32) * 2 * bn * 32
+            self._n_images = getattr(self, "_n_images", 0) + 1
+            name = "bimg_%x_%d" % (id(self) & 0xFFFFFF, self._n_images)
+            arena.ensure(name, floats)
+            plan.b_image = (name, 0)
+        desc = resolve(plan, arena)
+        if plan.b_image is not None:
+            self.add(OP_GEMM_PREP_B, desc, 0)
+        self.add(OP_GEMM, desc, flags)
         self.plan_names.append(plan.name)
         self.flops += plan.flops
-        if plan.splits > 1:
+        if plan.splits > 1 and plan.split_dst is not None:
             dst = plan.split_dst
             r = ReduceDesc(arena.ptr((dst[0], dst[1])), arena.ptr(plan.C), dst[2], plan.split_stride, plan.splits,
                            plan.accumulate, arena.ptr(plan.split_bias), plan.N, plan.split_act, plan.split_beta, 0)
@@ -494,11 +517,18 @@ class NetBuilder(object):
                      self.gather, "gru.init")]
         sp = forward_splits(N, 3 * H, H)          # the per-step GEMM is tiny (M = environments): split K
         part = self.buf("part_gru_hh_fwd", sp * N * 3 * H) if sp > 1 else None
+        ints = dict(T=T, N=N, H=H)
+        if sp > 1:      # the gate kernel folds the split-K partials itself (no separate fold launch per step)
+            fields.update(gh_part=part, gh_bias=bhh)
+            ints.update(gh_splits=sp)
         for t in range(T):
-            ops.append(P.linear_forward(self.gru_hh, N, (hm[0], t * N * H), whh, bhh, (gh[0], t * N * 3 * H),
-                                        splits=sp, partial=part))
-            ops[-1].name = "gru_hh.fwd"
-            ops.append(RawOp(OP_GRU_FWD, fields, dict(T=T, N=N, H=H, t=t), self.gather, "gru.gates"))
+            p = P.linear_forward(self.gru_hh, N, (hm[0], t * N * H), whh, bhh, (gh[0], t * N * 3 * H),
+                                 splits=sp, partial=part)
+            p.name = "gru_hh.fwd"
+            if sp > 1:
+                p.split_dst = None
+            ops.append(p)
+            ops.append(RawOp(OP_GRU_FWD, fields, dict(ints, t=t), self.gather, "gru.gates"))
         return ops, out
 
     def gru_backward(self, x, d_in, dout, dx=None, dx_mask=None):
@@ -515,11 +545,17 @@ class NetBuilder(object):
         ops = []
         sp = forward_splits(N, H, 3 * H)
         part = self.buf("part_gru_hh_dgrad", sp * N * H) if sp > 1 else None
+        ints = dict(T=T, N=N, H=H)
+        if sp > 1:
+            fields.update(dc_part=part)
+            ints.update(dc_splits=sp)
         for t in range(T - 1, -1, -1):
-            ops.append(RawOp(OP_GRU_BWD, fields, dict(T=T, N=N, H=H, t=t), self.gather, "gru.gates_bwd"))
+            ops.append(RawOp(OP_GRU_BWD, fields, dict(ints, t=t), self.gather, "gru.gates_bwd"))
             if t > 0:
                 p = P.linear_dgrad(self.gru_hh, N, (dgh[0], t * N * 3 * H), whh, dcarry, accumulate=1,
                                    splits=sp, partial=part)
+                if sp > 1:
+                    p.split_dst = None      # folded by the next (earlier-in-time) backward gate kernel
                 p.name = "gru_hh.dgrad"
                 ops.append(p)
         hm = (self.n("gru_hm"), 0)

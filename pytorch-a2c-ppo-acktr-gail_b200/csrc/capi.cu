@@ -70,6 +70,14 @@ int a2cb_gemm(const a2cb_gemm_t* desc, a2cb_stream_t stream) {
     return gemm(*reinterpret_cast<const GemmDesc*>(desc), (cudaStream_t)stream);
 }
 
+int a2cb_gemm_prep_b(const a2cb_gemm_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc, "gemm_prep_b: null descriptor");
+    return gemm_prep_b(*reinterpret_cast<const GemmDesc*>(desc), (cudaStream_t)stream);
+}
+int64_t a2cb_gemm_b_image_floats(const a2cb_gemm_t* desc) {
+    return desc ? gemm_b_image_floats(*reinterpret_cast<const GemmDesc*>(desc)) : 0;
+}
+
 int a2cb_set_gemm_mode(int32_t mode) {
     A2CB_REQUIRE(mode >= 0 && mode <= 2, "set_gemm_mode: 0 (fp32 SIMT), 1 (tcgen05 3xTF32) or 2 (auto)");
     set_gemm_mode(mode);
@@ -179,6 +187,10 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
                 const a2cb_fill_t& f = *reinterpret_cast<const a2cb_fill_t*>(op.desc);
                 cudaError_t e = cudaMemsetAsync(f.dst, f.value, (size_t)f.bytes, st);
                 if (e != cudaSuccess) { set_error("run_ops: memset: %s", cudaGetErrorString(e)); rc = A2CB_ERR_CUDA; }
+                break;
+            }
+            case A2CB_OP_GEMM_PREP_B: {
+                rc = gemm_prep_b(*reinterpret_cast<const GemmDesc*>(op.desc), st);
                 break;
             }
             case A2CB_OP_SPATIAL_SUM: {

@@ -23,6 +23,8 @@ void set_gemm_mode(int m);
 // gemm_tc.cu
 bool gemm_tc_supported(const GemmDesc& g);
 int gemm_tc(const GemmDesc& g, cudaStream_t st);
+int gemm_prep_b(const GemmDesc& g, cudaStream_t st);
+long gemm_b_image_floats(const GemmDesc& g);
 int reduce_splits(float* dst, const float* src, long count, long stride, int splits, int accumulate,
                   const float* bias, int ncols, int act, float beta, cudaStream_t st);
 

@@ -332,6 +332,7 @@ void set_gemm_mode(int m) { g_gemm_mode = (m < 0 || m > 2) ? 2 : m; }
 // transposed-loader shapes (weight gradients) and the wide fc layers are still faster on the SIMT
 // engine, whose split-K partials also keep their long reductions in round-to-nearest fp32.
 static bool prefer_tc(const GemmDesc& g) {
+    if (g.B_image) return g.vecA != 2 && g.M >= 2048 && g.K >= 64;      // B arrives by TMA: loaders only feed A
     return g.vecA != 2 && g.vecB != 1 && g.N <= 64 && g.N >= 16 && g.M >= 4096 && g.K >= 64;
 }
 

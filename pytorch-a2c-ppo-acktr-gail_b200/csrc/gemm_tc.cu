@@ -151,6 +151,7 @@ gemm_tc_kernel(const GemmDesc g) {
     __shared__ unsigned char rflag[TBM];
     __shared__ unsigned char cvalid[BN];
     __shared__ __align__(8) uint64_t mbar[TSTAGES];
+    __shared__ __align__(8) uint64_t bbar[TSTAGES];      // TMA arrival of a pre-tiled B block
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -172,7 +173,7 @@ gemm_tc_kernel(const GemmDesc g) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 32) {
-        for (int s = 0; s < TSTAGES; ++s) tc_mbar_init(&mbar[s], 1);
+        for (int s = 0; s < TSTAGES; ++s) { tc_mbar_init(&mbar[s], 1); tc_mbar_init(&bbar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int t = tid; t < TBM; t += TNT) {
@@ -208,6 +209,11 @@ gemm_tc_kernel(const GemmDesc g) {
         }
     };
 
+    // pre-tiled B image: [batch][column tile][k-block][hi | lo][BN x 32 floats in tile_off order]
+    const bool has_image = g.B_image != nullptr;
+    const long n_ctiles = (g.N + BN - 1) / BN;
+    const float* Bimg = has_image
+        ? g.B_image + ((long)batch * n_ctiles + blockIdx.x) * ktiles * (2 * BN * TBK) : nullptr;
     float4 a_reg[A_NV], b_reg[B_NV];
     static_assert(A_NV == 4, "row-fast A mapping assumes 4 slots per thread");
     const int rowb = 16 * warp + (lane & 7), kcb = lane >> 3;   // row-fast A slots of this thread
@@ -249,6 +255,7 @@ gemm_tc_kernel(const GemmDesc g) {
             }
             a_reg[q] = v;
         }
+        if (has_image) return;
 #pragma unroll
         for (int q = 0; q < B_NV; ++q) {
             const int s = tid + q * TNT;
@@ -296,6 +303,7 @@ gemm_tc_kernel(const GemmDesc g) {
                 *reinterpret_cast<float4*>(Al + o) = lo;
             }
         }
+        if (has_image) return;
 #pragma unroll
         for (int q = 0; q < B_NV; ++q) {
             const int s = tid + q * TNT;
@@ -366,12 +374,25 @@ gemm_tc_kernel(const GemmDesc g) {
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
         }
+        if (has_image && tid == 0) {
+            // stage s is free (its last MMAs were waited for above): fetch this k-block's B (hi | lo) with
+            // ONE TMA bulk copy; it lands while the warps convert and store the A tile
+            const uint32_t bytes = 2 * B_TILE;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem(&bbar[s])), "r"(bytes)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    tc_smem(tc_dyn + s * STAGE + 2 * A_TILE)),
+                "l"(Bimg + (kbeg / TBK + kb) * (2 * BN * TBK)), "r"(bytes), "r"(tc_smem(&bbar[s]))
+                : "memory");
+        }
         store_tile(s);
         if (kb + 1 < nkb) load_tile((kb + 1) & 1, kbeg + (long)(kb + 1) * TBK);
         stage_red(kb & 1, kbeg + (long)(kb + 2) * TBK);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
+            if (has_image) tc_mbar_wait(&bbar[s], (uint32_t)((kb / TSTAGES) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ah = tc_smem(tc_dyn + s * STAGE), al = ah + A_TILE, bh = al + A_TILE, bl = bh + B_TILE;
             const uint32_t d = tmem_d + (uint32_t)(((kb / CH) & 1) * BN);
@@ -451,6 +472,64 @@ static int launch_tc(const GemmDesc& g, cudaStream_t st) {
     else if (g.a_dtype == 2) gemm_tc_kernel<BN, 2><<<grid, TNT, smem, st>>>(g);
     else gemm_tc_kernel<BN, 0><<<grid, TNT, smem, st>>>(g);
     return check_launch("gemm_tc");
+}
+
+// ---------------------------------------------------------------------------
+// B image: weights are the same for every CTA of a GEMM and change once per optimiser step, so their
+// gather (PyTorch [out, in, kh, kw] order -> engine K order), hi/lo split and UMMA tiling are done ONCE
+// here instead of in every CTA and every k-block.
+// ---------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(256)
+gemm_prep_b_kernel(const GemmDesc g, float* __restrict__ img) {
+    const long ktiles = (g.K + TBK - 1) / TBK;
+    const long n_ctiles = (g.N + BN - 1) / BN;
+    const long chunks = (long)g.batch * n_ctiles * ktiles * BN * TKC;       // 16-byte (row, kc) chunks
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= chunks) return;
+    const int kc = (int)(e % TKC);
+    const int col = (int)((e / TKC) % BN);
+    const long blk = e / ((long)TKC * BN);                                   // (batch, ctile, kb)
+    const long kb = blk % ktiles;
+    const long ct = (blk / ktiles) % n_ctiles;
+    const int z = (int)(blk / (ktiles * n_ctiles));
+    const long j = ct * BN + col;
+    const float* Bb = g.B + g.batch_offB[z];
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (j < g.N) {
+        const long cb = tc_affine(g.colB, j, nullptr);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const long r = kb * TBK + kc * 4 + c;
+            if (r < g.K) v[c] = __ldg(Bb + tc_affine(g.redB, r, nullptr) + cb);
+        }
+    }
+    float4 hi, lo;
+    split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+    float* dst = img + blk * (2 * BN * TBK);
+    const uint32_t o = tile_off(col, kc) / 4;
+    *reinterpret_cast<float4*>(dst + o) = hi;
+    *reinterpret_cast<float4*>(dst + BN * TBK + o) = lo;
+}
+
+static int tc_bn(const GemmDesc& g) { return g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128); }
+
+long gemm_b_image_floats(const GemmDesc& g) {
+    const int bn = tc_bn(g);
+    return (long)g.batch * ((g.N + bn - 1) / bn) * ((g.K + TBK - 1) / TBK) * 2 * bn * TBK;
+}
+
+int gemm_prep_b(const GemmDesc& g, cudaStream_t st) {
+    A2CB_REQUIRE(g.B && g.B_image, "gemm_prep_b: B and B_image required");
+    const int bn = tc_bn(g);
+    const long chunks = gemm_b_image_floats(g) / 8;
+    if (chunks == 0) return A2CB_OK;
+    const unsigned grid = (unsigned)((chunks + 255) / 256);
+    float* img = const_cast<float*>(g.B_image);
+    if (bn == 32) gemm_prep_b_kernel<32><<<grid, 256, 0, st>>>(g, img);
+    else if (bn == 64) gemm_prep_b_kernel<64><<<grid, 256, 0, st>>>(g, img);
+    else gemm_prep_b_kernel<128><<<grid, 256, 0, st>>>(g, img);
+    return check_launch("gemm_prep_b");
 }
 
 // Shapes the tensor-core path accepts; everything else stays on the fp32 SIMT engine.

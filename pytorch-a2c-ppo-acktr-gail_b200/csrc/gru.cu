@@ -41,11 +41,24 @@ gru_fwd_kernel(const GruDesc d) {
     const int t = d.t;
     const long row = (long)t * d.N + n;
     const float* gi = d.gi + row * 3 * H;
-    const float* gh = d.gh + row * 3 * H;
+    float* gh = d.gh + row * 3 * H;
+    float ghr, ghz, ghn;
+    if (d.gh_part) {
+        // fold the split-K partials of this step's hm_t W_hh^T (fixed order) and add b_hh
+        ghr = d.gh_bias[k]; ghz = d.gh_bias[H + k]; ghn = d.gh_bias[2 * H + k];
+        const long stride = (long)d.N * 3 * H;
+        const float* p = d.gh_part + (long)n * 3 * H;
+        float sr = 0.f, sz = 0.f, sn = 0.f;
+        for (int s = 0; s < d.gh_splits; ++s, p += stride) { sr += p[k]; sz += p[H + k]; sn += p[2 * H + k]; }
+        ghr += sr; ghz += sz; ghn += sn;
+        gh[k] = ghr; gh[H + k] = ghz; gh[2 * H + k] = ghn;       // kept for the backward pass
+    } else {
+        ghr = gh[k]; ghz = gh[H + k]; ghn = gh[2 * H + k];
+    }
     const float hm = d.hm[row * H + k];
-    const float r = sigmoidf_(gi[k] + gh[k]);
-    const float z = sigmoidf_(gi[H + k] + gh[H + k]);
-    const float nn = tanhf(gi[2 * H + k] + r * gh[2 * H + k]);
+    const float r = sigmoidf_(gi[k] + ghr);
+    const float z = sigmoidf_(gi[H + k] + ghz);
+    const float nn = tanhf(gi[2 * H + k] + r * ghn);
     const float h = (1.f - z) * nn + z * hm;
     d.out[row * H + k] = h;
     if (d.r) { d.r[row * H + k] = r; d.z[row * H + k] = z; d.n[row * H + k] = nn; }
@@ -63,7 +76,16 @@ gru_bwd_kernel(const GruDesc d) {
     const int t = d.t;
     const long row = (long)t * d.N + n;
     float dh = d.dout[row * H + k];
-    if (t + 1 < d.T) dh += d.dcarry[e] * row_mask(d, t + 1, n);
+    if (t + 1 < d.T) {
+        float c = d.dcarry[e];
+        if (d.dc_part) {
+            const long stride = (long)d.N * H;
+            float s = 0.f;
+            for (int q = 0; q < d.dc_splits; ++q) s += d.dc_part[q * stride + e];
+            c += s;
+        }
+        dh += c * row_mask(d, t + 1, n);
+    }
     const float r = d.r[row * H + k], z = d.z[row * H + k], nn = d.n[row * H + k];
     const float hm = d.hm[row * H + k];
     const float ghn = d.gh[row * 3 * H + 2 * H + k];

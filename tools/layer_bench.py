@@ -50,7 +50,7 @@ def main():
             if kind == _engine.OP_GEMM:
                 labels.append(prog.plan_names[gi]); gi += 1
             else:
-                labels.append({2: "reduce_splits", 3: "loss", 4: "grad_norm", 5: "optim"}[kind])
+                labels.append({2: "reduce_splits", 3: "loss", 4: "grad_norm", 5: "optim", 10: "bias_psum", 11: "weight_prep"}.get(kind, "op%d" % kind))
         idx = torch.randperm(T * N)[:B].to(dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         for eng in engines:
