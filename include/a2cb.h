@@ -246,6 +246,8 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_GRU_BWD 9
 #define A2CB_OP_SPATIAL_SUM 10
 #define A2CB_OP_GEMM_PREP_B 11
+#define A2CB_OP_GRU_SEQ_FWD 12
+#define A2CB_OP_GRU_SEQ_BWD 13
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -294,6 +296,14 @@ typedef struct {
 } a2cb_gru_t;
 
 int a2cb_gru_op(int32_t which, const a2cb_gru_t* desc, a2cb_stream_t stream);
+
+/* Whole-sequence GRU in ONE cooperative (persistent) launch per direction: every CTA keeps its slice of
+ * W_hh in shared memory for all T steps and the CTAs meet at a grid barrier once per step.  Same buffers
+ * as the per-step ops (gi must already hold x W_ih^T + b_ih; backward leaves dgi / dgh for the weight-
+ * gradient GEMMs).  a2cb_gru_seq_supported says whether all CTAs of an [N, H] problem can be co-resident. */
+typedef struct { a2cb_gru_t d; const float* W_hh; const float* b_hh; } a2cb_gru_seq_t;
+int a2cb_gru_seq(int32_t backward, const a2cb_gru_seq_t* desc, a2cb_stream_t stream);
+int a2cb_gru_seq_supported(int32_t N, int32_t H);
 
 /* ---------------------------------------------------------------------------
  * (5) ACKTR / KFAC helpers                              a2c_ppo_acktr/algo/kfac.py

@@ -20,6 +20,7 @@ c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctyp
 
 OP_GEMM, OP_REDUCE, OP_LOSS, OP_GRAD_NORM, OP_OPTIM, OP_FILL = 1, 2, 3, 4, 5, 6
 OP_GRU_INIT, OP_GRU_FWD, OP_GRU_BWD, OP_SPATIAL_SUM, OP_GEMM_PREP_B = 7, 8, 9, 10, 11
+OP_GRU_SEQ_FWD, OP_GRU_SEQ_BWD = 12, 13
 RUNTIME_IDX = 1
 SENTINEL = 1          # non-NULL placeholder for "use the runtime minibatch index list"
 
@@ -71,6 +72,19 @@ class SpatialSumDesc(ctypes.Structure):
                 ("C", c_i32), ("ow", c_i32)]
 
 
+class GruSeqDesc(ctypes.Structure):
+    """Mirror of a2cb_gru_seq_t: the per-step descriptor + the recurrent weights."""
+    _fields_ = GruDesc._fields_ + [("W_hh", c_vp), ("b_hh", c_vp)]
+
+
+def gru_seq_supported(N, H):
+    """Persistent whole-sequence GRU kernel usable?  (A2CB_GRU=steps forces the per-step path.)"""
+    import os
+    if os.environ.get("A2CB_GRU", "") == "steps":
+        return False
+    return bool(_native.lib().a2cb_gru_seq_supported(int(N), int(H)))
+
+
 class RawOp(object):
     """A non-GEMM op in a plan list: kind + symbolic fields resolved against the arena."""
 
@@ -100,6 +114,8 @@ _native.register({
     "a2cb_optim_step": (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp] + [c_f32] * 8 + [c_i32, c_vp]),
     "a2cb_run_ops": (c_i32, [ctypes.POINTER(Op), c_i32, c_vp, c_vp]),
     "a2cb_gru_op": (c_i32, [c_i32, ctypes.POINTER(GruDesc), c_vp]),
+    "a2cb_gru_seq": (c_i32, [c_i32, c_vp, c_vp]),
+    "a2cb_gru_seq_supported": (c_i32, [c_i32, c_i32]),
 })
 
 
@@ -512,6 +528,12 @@ class NetBuilder(object):
             fields.update(r=self.buf("gru_r", B * H), z=self.buf("gru_z", B * H), n=self.buf("gru_n", B * H))
         self.gru_in = P.Linear("gru_ih", d_in, 3 * H)
         self.gru_hh = P.Linear("gru_hh", H, 3 * H)
+        self.gru_persistent = gru_seq_supported(N, H)
+        if self.gru_persistent:
+            # whole recurrence in one cooperative launch (csrc/gru_persistent.cu)
+            f2 = dict(fields, h0=self.hxs_ref, W_hh=whh, b_hh=bhh)
+            return [P.linear_forward(self.gru_in, B, x, wih, bih, gi),
+                    RawOp(OP_GRU_SEQ_FWD, f2, dict(T=T, N=N, H=H, t=0), self.gather, "gru.seq_fwd", GruSeqDesc)], out
         ops = [P.linear_forward(self.gru_in, B, x, wih, bih, gi),
                RawOp(OP_GRU_INIT, dict(hm=hm, h0=self.hxs_ref, masks=self.masks_ref), dict(T=T, N=N, H=H, t=0),
                      self.gather, "gru.init")]
@@ -543,6 +565,10 @@ class NetBuilder(object):
         fields = {k: (self.n("gru_" + k), 0) for k in names}
         fields.update(masks=self.masks_ref, dout=dout, dgi=dgi, dgh=dgh, dcarry=dcarry)
         ops = []
+        if getattr(self, "gru_persistent", False):
+            f2 = dict(fields, W_hh=whh)
+            f2.pop("dcarry")
+            ops.append(RawOp(OP_GRU_SEQ_BWD, f2, dict(T=T, N=N, H=H, t=0), self.gather, "gru.seq_bwd", GruSeqDesc))
         sp = forward_splits(N, H, 3 * H)
         part = self.buf("part_gru_hh_dgrad", sp * N * H) if sp > 1 else None
         ints = dict(T=T, N=N, H=H)
@@ -550,6 +576,8 @@ class NetBuilder(object):
             fields.update(dc_part=part)
             ints.update(dc_splits=sp)
         for t in range(T - 1, -1, -1):
+            if getattr(self, "gru_persistent", False):
+                break
             ops.append(RawOp(OP_GRU_BWD, fields, dict(ints, t=t), self.gather, "gru.gates_bwd"))
             if t > 0:
                 p = P.linear_dgrad(self.gru_hh, N, (dgh[0], t * N * 3 * H), whh, dcarry, accumulate=1,

@@ -142,6 +142,13 @@ int a2cb_gru_op(int32_t which, const a2cb_gru_t* desc, a2cb_stream_t stream) {
     return gru_op(which - A2CB_OP_GRU_INIT, *reinterpret_cast<const GruDesc*>(desc), (cudaStream_t)stream);
 }
 
+int a2cb_gru_seq(int32_t backward, const a2cb_gru_seq_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc, "gru_seq: null descriptor");
+    return gru_persistent(backward != 0, *reinterpret_cast<const GruDesc*>(&desc->d), desc->W_hh, desc->b_hh,
+                          (cudaStream_t)stream);
+}
+int a2cb_gru_seq_supported(int32_t N, int32_t H) { return gru_persistent_supported(N, H) ? 1 : 0; }
+
 int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream) {
     A2CB_REQUIRE(n_ops >= 0 && (n_ops == 0 || ops), "run_ops: bad op list");
     cudaStream_t st = (cudaStream_t)stream;
@@ -196,6 +203,14 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             case A2CB_OP_SPATIAL_SUM: {
                 const a2cb_spatial_sum_t& q = *reinterpret_cast<const a2cb_spatial_sum_t*>(op.desc);
                 rc = spatial_sum(q.out, q.in, q.B, q.P, q.C, q.ow, (long)q.img_stride, (long)q.pitch, st);
+                break;
+            }
+            case A2CB_OP_GRU_SEQ_FWD:
+            case A2CB_OP_GRU_SEQ_BWD: {
+                const a2cb_gru_seq_t& q = *reinterpret_cast<const a2cb_gru_seq_t*>(op.desc);
+                GruDesc d = *reinterpret_cast<const GruDesc*>(&q.d);
+                if (rt) d.idx = idx;
+                rc = gru_persistent(op.kind == A2CB_OP_GRU_SEQ_BWD, d, q.W_hh, q.b_hh, st);
                 break;
             }
             case A2CB_OP_GRU_INIT:

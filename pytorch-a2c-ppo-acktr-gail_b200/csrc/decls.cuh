@@ -55,4 +55,8 @@ int frames_to_f32(float* dst, const void* src, long n, int src_is_u8, float div,
 struct GruDesc;
 int gru_op(int which, const GruDesc& d, cudaStream_t st);   // which: 0 init, 1 forward step, 2 backward step
 
+// gru_persistent.cu
+bool gru_persistent_supported(int N, int H);
+int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st);
+
 }  // namespace a2cb
