@@ -315,25 +315,23 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
         return None, None
     T, N = cfg["T"], cfg["N"]
     mbs = prog.builder.B if hasattr(prog, "builder") else T * N
-    names, flops = [], []
-    for kind, flags, desc in prog.entries:
-        if kind == _engine.OP_GEMM:
-            names.append("gemm")
-            flops.append(2.0 * desc.M * desc.N * desc.K * desc.batch)
-        else:
-            names.append({2: "reduce_splits", 3: "loss_epilogue", 4: "grad_norm", 5: "optim_step", 7: "gru_init",
-                          8: "gru_gates", 9: "gru_gates_bwd", 10: "bias_pixel_sum", 11: "weight_prep"}.get(kind, "op%d" % kind))
-            flops.append(0.0)
-    # label GEMMs by their plan
-    labels = []
-    gi = 0
+    kind_names = {2: "reduce_splits", 3: "loss_epilogue", 4: "grad_norm", 5: "optim_step", 7: "gru_init",
+                  8: "gru_gates", 9: "gru_gates_bwd", 10: "bias_pixel_sum", 11: "weight_prep", 12: "gru.seq_fwd",
+                  13: "gru.seq_bwd", 16: "lo_plane", 17: "weight_image", 18: "frames_s2d", 19: "bias_colsum"}
+    labels, flops = [], []
     plan_names = [p for p in getattr(prog, "plan_names", [])]
-    for i, n in enumerate(names):
-        if n == "gemm" and gi < len(plan_names):
-            labels.append(plan_names[gi])
+    gi = 0
+    for (kind, flags, desc), (lab, fl) in zip(prog.entries, prog.labels):
+        if kind == _engine.OP_GEMM:
+            labels.append(plan_names[gi] if gi < len(plan_names) else "gemm")
             gi += 1
+            flops.append(2.0 * desc.M * desc.N * desc.K * desc.batch)
+        elif kind in (14, 15):              # TMA-fed tensor-core engine: labelled by layer
+            labels.append(lab)
+            flops.append(fl)
         else:
-            labels.append(n)
+            labels.append(kind_names.get(kind, lab or "op%d" % kind))
+            flops.append(0.0)
     singles = []
     for kind, flags, desc in prog.entries:
         p = _engine.Program(dev)
@@ -376,7 +374,9 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
     top = gemm_rows[0]
     from a2c_ppo_acktr import _native as nat
     peak = pk["tensor_sustained"]
-    roof = {"bound": "tensor", "kernel": "a2cb::gemm_tc_kernel / gemm_kernel (%s)" % top["op"],
+    tcx_ops = any(kind in (14, 15) for kind, _, _ in prog.entries)
+    roof = {"bound": "tensor", "kernel": ("a2cb::tcx_fwd_kernel / tcx_wgrad_kernel (%s)" if tcx_ops else
+                                          "a2cb::gemm_tc_kernel / gemm_kernel (%s)") % top["op"],
             "achieved": top["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": top["tflops"] / peak, "traffic": None,
             "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step); algorithmic fp32 "
                            "flops: the tensor-core engine spends 3 TF32 MMAs per product (3xTF32), so <= 1/3 of a "

@@ -157,6 +157,97 @@ int a2cb_reduce_splits(float* dst, const float* src, int64_t count, int64_t stri
                        a2cb_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * (3b) TMA-fed tensor-core engine: CNNBase / Linear forward, data and weight gradients
+ *      reference call sites: a2c_ppo_acktr/model.py:176-180,185,190 (CNNBase), model.py:113
+ *      (GRU input product) and their autograd backward.
+ *
+ * Operands are fp32 tensors stored as TWO planes, x and lo = x - trunc_tf32(x); the tensor core ignores
+ * the 13 low mantissa bits of a kind::tf32 operand, so x itself is the "hi" operand and three MMAs
+ * (x*w_hi + lo*w_hi + x*w_lo) reproduce the fp32 product to ~2^-20.  Activations are NHWC; a
+ * convolution is a sum over filter taps of [pixels x C_in] x [C_in x C_out] products whose pixel box is one
+ * multi-dimensional TMA box of a strided 5-D view (dimension 0 = channels, 32 per box).
+ *
+ *   a2cb_tcx_fwd:   out[o_base + sum_d (base_d + i_d) o_stride[d] + n] =
+ *                       epi( alpha * sum_kb sum_{c<32} A[box(kb)][row i][c] * B[n][kb_b[kb] + c] )
+ *                   epi: + bias[n], relu, relu' masking; optionally also writes the lo plane of out.
+ *   a2cb_tcx_wgrad: partial[split][row_off[m] + n col_stride] = alpha * sum_rows A[row][m] * Bm[row][n]
+ *                   (m = g 128 + 32 j + c: channel c of box j of accumulator group g), reduction over
+ *                   row tiles split across CTAs; fold the splits with a2cb_reduce_splits.
+ * ------------------------------------------------------------------------- */
+#define A2CB_TCX_MAX_KB 64
+#define A2CB_TCX_MAX_G 8
+typedef struct {
+    const float* x;
+    const float* lo;      /* NULL: x is exact in TF32 (uint8 frames) */
+    int64_t dim[5];       /* extents, innermost (channels) first */
+    int64_t stride[5];    /* elements; stride[0] = 1 */
+    int32_t box[5];       /* box[0] = 32 */
+    int32_t pad_;
+} a2cb_tcx_view_t;
+/* tile t -> (tq, tr) = (t / t_div, t % t_div); base[tr_dim] += tr * tr_step; base[tq_dim] += tq * tq_step */
+typedef struct { int32_t n_tiles, t_div, tr_dim, tr_step, tq_dim, tq_step; } a2cb_tcx_tiling_t;
+typedef struct {
+    a2cb_tcx_view_t A;
+    const float* B;       /* weight image [b_rows = N][b_cols], reduction index contiguous (a2cb_tcx_prep_weights) */
+    const float* B_lo;
+    int64_t b_rows, b_cols;
+    int32_t n_kb;
+    int32_t chain;        /* k-blocks per TMEM accumulation chain (the tensor core's accumulator truncates) */
+    int16_t kb_a[A2CB_TCX_MAX_KB][4];
+    int32_t kb_b[A2CB_TCX_MAX_KB];
+    a2cb_tcx_tiling_t tiles;
+    float* out;
+    float* out_lo;
+    const float* mask;
+    const float* bias;
+    int64_t o_stride[5];
+    int64_t o_base;
+    int32_t o_ext[5];
+    int32_t N;
+    float alpha;
+    int32_t act;
+} a2cb_tcx_fwd_t;
+typedef struct {
+    a2cb_tcx_view_t A;
+    a2cb_tcx_view_t Bm;
+    int32_t G, nbb;
+    int16_t ga[A2CB_TCX_MAX_G][4][4];
+    int16_t gb[8][4];
+    a2cb_tcx_tiling_t rows;
+    int32_t splits, chain;
+    int32_t ot_a, ot_b, ot_a_step, ot_b_step;
+    float* partial;
+    int64_t split_stride;
+    const int32_t* row_off;
+    int64_t col_stride;
+    int32_t n_cols;
+    float alpha;
+} a2cb_tcx_wgrad_t;
+int a2cb_tcx_fwd(const a2cb_tcx_fwd_t* desc, a2cb_stream_t stream);
+int a2cb_tcx_wgrad(const a2cb_tcx_wgrad_t* desc, a2cb_stream_t stream);
+/* lo[i] = x[i] - trunc_tf32(x[i]), n a multiple of 4 */
+int a2cb_tcx_lo_plane(float* lo, const float* x, int64_t n, a2cb_stream_t stream);
+/* img[n][k] = src[ntab[n] + ktab[k]] (0 where a table entry is negative), img_lo = its lo plane: weights in
+ * the reference's PyTorch layouts -> the reduction-contiguous images a2cb_tcx_fwd reads (once per optimiser
+ * step).  ntab [N], ktab [K]: device int32 element offsets. */
+int a2cb_tcx_prep_weights(float* img, float* img_lo, const float* src, int64_t N, int64_t K, const int32_t* ntab,
+                          const int32_t* ktab, a2cb_stream_t stream);
+/* frames [*, C, H, W] (uint8 or fp32; rows through idx, NULL = identity) -> fp32 space-to-depth
+ * [B, H/S, W/S, C*S*S], channel (c, dy, dx): fuses the minibatch gather of storage.py:127 with the layout
+ * change that turns the stride-S first convolution into a stride-1 one.  out_lo optional. */
+int a2cb_tcx_s2d(float* out, float* out_lo, const void* frames, int32_t src_is_u8, const int64_t* idx, int32_t B,
+                 int32_t C, int32_t H, int32_t W, int32_t S, a2cb_stream_t stream);
+/* part[blk][c] = partial column sums of x[rows][C] (row pitch in elements); a2cb_tcx_colsum_blocks(rows)
+ * partials, folded by a2cb_reduce_splits: bias gradients */
+int a2cb_tcx_colsum(float* part, const float* x, int64_t rows, int32_t C, int64_t pitch, a2cb_stream_t stream);
+int a2cb_tcx_colsum_blocks(int64_t rows);
+/* sizeof of a2cb_tcx_fwd_t (0), a2cb_tcx_wgrad_t (1), a2cb_tcx_view_t (2) as compiled: lets a binding check its mirror */
+int a2cb_tcx_sizeof(int32_t which);
+/* hardware-semantics knobs of the MN-major (weight-gradient) path, for probing: UMMA layout type, stride
+ * between K atoms, start-address advance per K = 8 step, CUtensorMapSwizzle of the boxes */
+int a2cb_tcx_set_knobs(int32_t mn_layout_type, int32_t mn_sbo_bytes, int32_t mn_kstep_bytes, int32_t mn_tma_swizzle);
+
+/* ---------------------------------------------------------------------------
  * (4) fused loss epilogue                a2c_ppo_acktr/algo/ppo.py:35-37,61-77,86-88
  *                                         algo/a2c_acktr.py:48-51,55-64
  *                                         distributions.py:18-44, model.py:76-77
@@ -248,6 +339,12 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_GEMM_PREP_B 11
 #define A2CB_OP_GRU_SEQ_FWD 12
 #define A2CB_OP_GRU_SEQ_BWD 13
+#define A2CB_OP_TCX_FWD 14
+#define A2CB_OP_TCX_WGRAD 15
+#define A2CB_OP_TCX_LO 16
+#define A2CB_OP_TCX_PREP 17
+#define A2CB_OP_TCX_S2D 18
+#define A2CB_OP_TCX_COLSUM 19
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -262,6 +359,10 @@ typedef struct {
 } a2cb_optim_t;
 typedef struct { void* dst; int64_t bytes; int32_t value; int32_t pad_; } a2cb_fill_t;
 typedef struct { float* out; const float* in; int64_t img_stride; int64_t pitch; int32_t B, P, C, ow; } a2cb_spatial_sum_t;
+typedef struct { float* lo; const float* x; int64_t n; } a2cb_tcx_lo_t;
+typedef struct { float* img; float* img_lo; const float* src; int64_t N, K; const int32_t* ntab; const int32_t* ktab; } a2cb_tcx_prep_t;
+typedef struct { float* out; float* out_lo; const void* frames; const int64_t* idx; int32_t src_is_u8, B, C, H, W, S; } a2cb_tcx_s2d_t;
+typedef struct { float* part; const float* x; int64_t rows; int64_t pitch; int32_t C; int32_t pad_; } a2cb_tcx_colsum_t;
 typedef struct { int32_t kind; int32_t flags; const void* desc; } a2cb_op_t;
 
 int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream);

@@ -10,6 +10,7 @@ that `a2cb_run_ops` launches from C in one call.  torch is used for device memor
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -209,16 +210,23 @@ class Program(object):
     def __init__(self, device):
         self.device = device
         self.entries = []          # (kind, flags, ctypes struct)
+        self.labels = []           # (label or None, flops) per entry -- bench.py's per-op table
         self.flops = 0
         self.plan_names = []
         self._arr = None
 
-    def add(self, kind, desc, flags=0):
+    def add(self, kind, desc, flags=0, label=None, flops=0.0):
         self.entries.append((kind, flags, desc))
+        self.labels.append((label, flops))
         self._arr = None
         return desc
 
     def add_plan(self, plan, arena):
+        from . import _tcx
+        if isinstance(plan, _tcx.TcxOp):
+            self.add(plan.kind, plan.make(arena), RUNTIME_IDX if plan.runtime_idx else 0, label=plan.name, flops=plan.flops)
+            self.flops += plan.flops
+            return
         if isinstance(plan, RawOp):
             d = (plan.struct or GruDesc)()
             for k, ref in plan.fields.items():
@@ -227,7 +235,7 @@ class Program(object):
                 setattr(d, k, v)
             if plan.runtime_idx:
                 d.idx = SENTINEL
-            self.add(plan.kind, d, RUNTIME_IDX if plan.runtime_idx else 0)
+            self.add(plan.kind, d, RUNTIME_IDX if plan.runtime_idx else 0, label=plan.name)
             self.plan_names_all = getattr(self, "plan_names_all", [])
             return
         flags = RUNTIME_IDX if (plan.gather_row or plan.gather_red) else 0
@@ -254,6 +262,7 @@ class Program(object):
 
     def extend(self, other):
         self.entries.extend(other.entries)
+        self.labels.extend(other.labels)
         self.flops += other.flops
         self._arr = None
 
@@ -353,7 +362,7 @@ class NetBuilder(object):
     """Builds forward / backward plan lists for one policy spec and one batch size."""
 
     def __init__(self, spec, layout, B, obs_buf, obs_code, gather, tag, seq=None, masks=("masks_in", 0),
-                 hxs=("hxs_in", 0), keep_gates=True):
+                 hxs=("hxs_in", 0), keep_gates=True, allow_tcx=True):
         self.spec, self.L, self.B = spec, layout, B
         # recurrent policies see the batch as a [T, N] sequence, rows time-major (model.py:119-126)
         self.seqT, self.seqN = seq if seq is not None else (1, B)
@@ -374,6 +383,13 @@ class NetBuilder(object):
             self.c3 = P.Conv("conv3", 64, 9, 9, 3, 1, 32)
             self.fc = P.Linear("fc", 1568, H)     # a3 is kept in NCHW-flatten order: no permutation
         self.heads = P.Linear("heads", H, 1 + A)
+        # CNN trunk (+ the GRU's input product) on the TMA-fed tensor-core engine (csrc/tcx.cu) unless the exact
+        # fp32 SIMT engine was requested; other geometries stay on the affine-indexed engine
+        self.tcx = None
+        if (allow_tcx and spec.cnn and spec.obs_shape[0] == 4 and H % 256 == 0 and obs_code in (1, 2)
+                and _native.lib().a2cb_get_gemm_mode() != 0 and os.environ.get("A2CB_TCX", "1") != "0"):
+            from . import _tcx
+            self.tcx = _tcx.CnnNet(self)
 
     def n(self, name):
         return self.t + name
@@ -395,6 +411,9 @@ class NetBuilder(object):
         B, s = self.B, self.spec
         c1, c2, c3 = self.c1, self.c2, self.c3
         a1, a2, a3 = self.buf("a1", B * c1.out_row), self.buf("a2", B * c2.out_row), self.buf("a3", B * c3.out_row)
+        if self.tcx is not None:
+            self.buf("z", B * self.zs)
+            return self.tcx.forward()
         h, z = self.buf("h", B * s.hidden), self.buf("z", B * self.zs)
         sp = forward_splits(B, s.hidden, 1568)
         part = self.buf("part_fc_fwd", sp * B * s.hidden) if sp > 1 else None
@@ -406,9 +425,16 @@ class NetBuilder(object):
         ]
         return plans, h
 
-    def cnn_backward(self, feat_grad):
-        """feat_grad: gradient w.r.t. the trunk output h, already masked by relu'."""
+    def cnn_backward(self, feat_grad, feat_grad_lo=None):
+        """feat_grad: gradient w.r.t. the trunk output h, already masked by relu' (feat_grad_lo: its lo plane when
+        the TMA-fed engine produced it)."""
         B = self.B
+        if self.tcx is not None:
+            from . import _tcx
+            if feat_grad_lo is not None:
+                return self.tcx.backward(feat_grad, feat_grad_lo)
+            lo = self.buf("feat_grad_lo", B * self.spec.hidden)
+            return [_tcx.lo_op("lo_plane", feat_grad, lo, B * self.spec.hidden)] + self.tcx.backward(feat_grad, lo)
         c1, c2, c3 = self.c1, self.c2, self.c3
         a1, a2, a3 = (self.n("a1"), 0), (self.n("a2"), 0), (self.n("a3"), 0)
         g3, g2, g1 = self.buf("g3", B * c3.gout_row), self.buf("g2", B * c2.gout_row), self.buf("g1", B * c1.gout_row)
@@ -529,12 +555,15 @@ class NetBuilder(object):
         self.gru_in = P.Linear("gru_ih", d_in, 3 * H)
         self.gru_hh = P.Linear("gru_hh", H, 3 * H)
         self.gru_persistent = gru_seq_supported(N, H)
+        in_prod = [P.linear_forward(self.gru_in, B, x, wih, bih, gi)]
+        if self.tcx is not None and d_in == H:
+            in_prod = self.tcx.gru_ih_forward(gi)
         if self.gru_persistent:
             # whole recurrence in one cooperative launch (csrc/gru_persistent.cu)
             f2 = dict(fields, h0=self.hxs_ref, W_hh=whh, b_hh=bhh)
-            return [P.linear_forward(self.gru_in, B, x, wih, bih, gi),
+            return in_prod + [
                     RawOp(OP_GRU_SEQ_FWD, f2, dict(T=T, N=N, H=H, t=0), self.gather, "gru.seq_fwd", GruSeqDesc)], out
-        ops = [P.linear_forward(self.gru_in, B, x, wih, bih, gi),
+        ops = in_prod + [
                RawOp(OP_GRU_INIT, dict(hm=hm, h0=self.hxs_ref, masks=self.masks_ref), dict(T=T, N=N, H=H, t=0),
                      self.gather, "gru.init")]
         sp = forward_splits(N, 3 * H, H)          # the per-step GEMM is tiny (M = environments): split K
@@ -566,8 +595,7 @@ class NetBuilder(object):
         fields.update(masks=self.masks_ref, dout=dout, dgi=dgi, dgh=dgh, dcarry=dcarry)
         ops = []
         if getattr(self, "gru_persistent", False):
-            f2 = dict(fields, W_hh=whh)
-            f2.pop("dcarry")
+            f2 = dict(fields, W_hh=whh)          # dcarry doubles as the kernel's carry workspace for N > 64
             ops.append(RawOp(OP_GRU_SEQ_BWD, f2, dict(T=T, N=N, H=H, t=0), self.gather, "gru.seq_bwd", GruSeqDesc))
         sp = forward_splits(N, H, 3 * H)
         part = self.buf("part_gru_hh_dgrad", sp * N * H) if sp > 1 else None
@@ -587,6 +615,8 @@ class NetBuilder(object):
                 p.name = "gru_hh.dgrad"
                 ops.append(p)
         hm = (self.n("gru_hm"), 0)
+        if self.tcx is not None and d_in == H and dx is not None and dx_mask is not None:
+            return ops + self.tcx.gru_backward(dgi, dgh, hm, dx, (dx[0] + "_lo", dx[1]))
         ops.append(P.linear_wgrad(self.gru_hh, B, hm, dgh, ("G", e["base.gru.weight_hh_l0"][0]),
                                   ("G", e["base.gru.bias_hh_l0"][0])))
         ops.append(P.linear_wgrad(self.gru_in, B, x, dgi, ("G", e["base.gru.weight_ih_l0"][0]),
@@ -637,7 +667,8 @@ class NetBuilder(object):
                 feat = (self.n("gru_out"), 0)
                 hp, gfeat = self.cnn_heads_backward(feat, relu_mask=False)
                 gx = self.buf("gru_dx", self.B * s.hidden)
-                return hp + self.gru_backward(h, s.hidden, gfeat, dx=gx, dx_mask=h) + self.cnn_backward(gx)
+                gx_lo = self.buf("gru_dx_lo", self.B * s.hidden) if self.tcx is not None else None
+                return hp + self.gru_backward(h, s.hidden, gfeat, dx=gx, dx_mask=h) + self.cnn_backward(gx, gx_lo)
             hp, gh = self.cnn_heads_backward(h)
             return hp + self.cnn_backward(gh)
         self.buf("dz", self.B * self.zs)
@@ -948,3 +979,6 @@ class PolicyRuntime(object):
         prog.add(OP_OPTIM, o)
         prog.optim_desc = o
         return o
+
+
+from . import _tcx  # noqa: E402,F401  (registers the a2cb_tcx_* entry points; imports this module lazily)

@@ -1,0 +1,445 @@
+"""Host-side descriptors of the TMA-fed tensor-core engine (csrc/tcx.cu): ctypes mirrors of
+`a2cb_tcx_*_t` (include/a2cb.h) and small builders for the views / tilings the CNN layers use.
+Pure integer bookkeeping -- no tensor math happens here."""
+import ctypes
+
+from . import _native
+from . import _plans as P
+
+c_i16, c_i32, c_i64, c_f32, c_vp = ctypes.c_int16, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+MAX_KB, MAX_G = 64, 8
+OOB = 30000          # coordinate offset that pushes a box completely out of bounds (TMA zero-fills it)
+
+
+class View(ctypes.Structure):
+    _fields_ = [("x", c_vp), ("lo", c_vp), ("dim", c_i64 * 5), ("stride", c_i64 * 5), ("box", c_i32 * 5), ("pad_", c_i32)]
+
+
+class Tiling(ctypes.Structure):
+    _fields_ = [("n_tiles", c_i32), ("t_div", c_i32), ("tr_dim", c_i32), ("tr_step", c_i32), ("tq_dim", c_i32),
+                ("tq_step", c_i32)]
+
+
+class FwdDesc(ctypes.Structure):
+    _fields_ = [("A", View), ("B", c_vp), ("B_lo", c_vp), ("b_rows", c_i64), ("b_cols", c_i64), ("n_kb", c_i32),
+                ("chain", c_i32), ("kb_a", (c_i16 * 4) * MAX_KB), ("kb_b", c_i32 * MAX_KB), ("tiles", Tiling),
+                ("out", c_vp), ("out_lo", c_vp), ("mask", c_vp), ("bias", c_vp), ("o_stride", c_i64 * 5),
+                ("o_base", c_i64), ("o_ext", c_i32 * 5), ("N", c_i32), ("alpha", c_f32), ("act", c_i32)]
+
+
+class WgradDesc(ctypes.Structure):
+    _fields_ = [("A", View), ("Bm", View), ("G", c_i32), ("nbb", c_i32), ("ga", ((c_i16 * 4) * 4) * MAX_G),
+                ("gb", (c_i16 * 4) * 8), ("rows", Tiling), ("splits", c_i32), ("chain", c_i32), ("ot_a", c_i32),
+                ("ot_b", c_i32), ("ot_a_step", c_i32), ("ot_b_step", c_i32), ("partial", c_vp), ("split_stride", c_i64),
+                ("row_off", c_vp), ("col_stride", c_i64), ("n_cols", c_i32), ("alpha", c_f32)]
+
+
+class LoDesc(ctypes.Structure):
+    _fields_ = [("lo", c_vp), ("x", c_vp), ("n", c_i64)]
+
+
+class PrepDesc(ctypes.Structure):
+    _fields_ = [("img", c_vp), ("img_lo", c_vp), ("src", c_vp), ("N", c_i64), ("K", c_i64), ("ntab", c_vp), ("ktab", c_vp)]
+
+
+class S2dDesc(ctypes.Structure):
+    _fields_ = [("out", c_vp), ("out_lo", c_vp), ("frames", c_vp), ("idx", c_vp), ("src_is_u8", c_i32), ("B", c_i32),
+                ("C", c_i32), ("H", c_i32), ("W", c_i32), ("S", c_i32)]
+
+
+class ColsumDesc(ctypes.Structure):
+    _fields_ = [("part", c_vp), ("x", c_vp), ("rows", c_i64), ("pitch", c_i64), ("C", c_i32), ("pad_", c_i32)]
+
+
+_native.register({
+    "a2cb_tcx_fwd": (c_i32, [ctypes.POINTER(FwdDesc), c_vp]),
+    "a2cb_tcx_wgrad": (c_i32, [ctypes.POINTER(WgradDesc), c_vp]),
+    "a2cb_tcx_lo_plane": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    "a2cb_tcx_prep_weights": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "a2cb_tcx_s2d": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "a2cb_tcx_colsum": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
+    "a2cb_tcx_colsum_blocks": (c_i32, [c_i64]),
+    "a2cb_tcx_sizeof": (c_i32, [c_i32]),
+    "a2cb_tcx_set_knobs": (c_i32, [c_i32, c_i32, c_i32, c_i32]),
+})
+
+
+def view(x_ptr, lo_ptr, dims, strides, box):
+    """5-D view, innermost first; shorter tuples are padded with unit dimensions."""
+    v = View()
+    v.x, v.lo = x_ptr, lo_ptr
+    dims, strides, box = list(dims), list(strides), list(box)
+    while len(dims) < 5:
+        strides.append(strides[-1] * dims[-1])
+        dims.append(1)
+        box.append(1)
+    assert strides[0] == 1 and box[0] == 32
+    for d in range(5):
+        v.dim[d], v.stride[d], v.box[d] = dims[d], strides[d], box[d]
+    return v
+
+
+def tiling(n_tiles, tr_dim, tr_step, t_div=None, tq_dim=4, tq_step=0):
+    t = Tiling()
+    t.n_tiles, t.t_div = n_tiles, (t_div if t_div else n_tiles)
+    t.tr_dim, t.tr_step, t.tq_dim, t.tq_step = tr_dim, tr_step, tq_dim, tq_step
+    return t
+
+
+# ---------------------------------------------------------------------------------------------------
+# op builders (symbolic: buffer references are (arena name, element offset) pairs resolved at program
+# build time, exactly like the GEMM plans of _plans.py)
+# ---------------------------------------------------------------------------------------------------
+OP_TCX_FWD, OP_TCX_WGRAD, OP_TCX_LO, OP_TCX_PREP, OP_TCX_S2D, OP_TCX_COLSUM = 14, 15, 16, 17, 18, 19
+
+
+class TcxOp(object):
+    """One launch of the TMA-fed engine in a plan list."""
+
+    def __init__(self, kind, make, name, runtime_idx=False, flops=0.0):
+        self.kind, self.make, self.name, self.runtime_idx, self.flops = kind, make, name, runtime_idx, flops
+
+
+def _itab(arena, name, values):
+    import numpy as np
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(np.asarray(values, dtype=np.int32))).to(arena.device)
+    arena.bind(name, t)
+    return t.data_ptr()
+
+
+def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tiles, out, out_lo, o_stride, o_ext, N,
+           alpha=1.0, bias=None, act=0, mask=None, chain=4, o_base=0, flops=0.0):
+    assert len(kbs) <= MAX_KB, (name, len(kbs))
+
+    def make(arena):
+        d = FwdDesc()
+        d.A = view(arena.ptr(A), arena.ptr(A_lo), dims, strides, box)
+        d.B, d.B_lo = arena.ptr((img, 0)), arena.ptr((img + "_lo", 0))
+        d.b_rows, d.b_cols = img_rows, img_cols
+        d.n_kb, d.chain = len(kbs), chain
+        for i, (a, b) in enumerate(kbs):
+            for j in range(4):
+                d.kb_a[i][j] = a[j]
+            d.kb_b[i] = b
+        d.tiles = tiles
+        d.out, d.out_lo = arena.ptr(out), arena.ptr(out_lo)
+        d.mask, d.bias = arena.ptr(mask), arena.ptr(bias)
+        os_, oe = list(o_stride) + [0] * (5 - len(o_stride)), list(o_ext) + [1] * (5 - len(o_ext))
+        for i in range(5):
+            d.o_stride[i], d.o_ext[i] = os_[i], oe[i]
+        d.o_base, d.N, d.alpha, d.act = o_base, N, alpha, act
+        return d
+    return TcxOp(OP_TCX_FWD, make, name, flops=flops)
+
+
+def wgrad_op(name, A, A_lo, a_dims, a_strides, a_box, Bm, Bm_lo, b_dims, b_strides, b_box, groups, b_boxes, rows, splits,
+             chain, ot_a, ot_b, ot_a_step, ot_b_step, partial, split_stride, row_off, col_stride, n_cols, alpha=1.0,
+             flops=0.0):
+    """groups: per accumulator group, 4 coordinate-offset tuples (dims 0..3); b_boxes: per 32-channel box of Bm one
+    tuple; row_off: list of ot_a * G * 128 element offsets (-1 = unused accumulator row)."""
+    G = len(groups)
+    assert 1 <= G <= MAX_G and all(len(g) == 4 for g in groups) and len(row_off) == ot_a * G * 128
+
+    def make(arena):
+        d = WgradDesc()
+        d.A = view(arena.ptr(A), arena.ptr(A_lo), a_dims, a_strides, a_box)
+        d.Bm = view(arena.ptr(Bm), arena.ptr(Bm_lo), b_dims, b_strides, b_box)
+        d.G, d.nbb = G, len(b_boxes)
+        for g, boxes in enumerate(groups):
+            for j, c in enumerate(boxes):
+                for k in range(4):
+                    d.ga[g][j][k] = c[k]
+        for j, c in enumerate(b_boxes):
+            for k in range(4):
+                d.gb[j][k] = c[k]
+        d.rows, d.splits, d.chain = rows, splits, chain
+        d.ot_a, d.ot_b, d.ot_a_step, d.ot_b_step = ot_a, ot_b, ot_a_step, ot_b_step
+        d.partial, d.split_stride = arena.ptr(partial), split_stride
+        d.row_off = _itab(arena, partial[0] + "_rowoff", row_off)
+        d.col_stride, d.n_cols, d.alpha = col_stride, n_cols, alpha
+        return d
+    return TcxOp(OP_TCX_WGRAD, make, name, flops=flops)
+
+
+def lo_op(name, x, lo, n):
+    def make(arena):
+        return LoDesc(arena.ptr(lo), arena.ptr(x), n)
+    return TcxOp(OP_TCX_LO, make, name)
+
+
+def prep_op(name, img, src, N, K, ntab, ktab):
+    def make(arena):
+        return PrepDesc(arena.ptr((img, 0)), arena.ptr((img + "_lo", 0)), arena.ptr(src), N, K,
+                        _itab(arena, img + "_ntab", ntab), _itab(arena, img + "_ktab", ktab))
+    return TcxOp(OP_TCX_PREP, make, name)
+
+
+def colsum_op(name, part, x, rows, C, pitch):
+    def make(arena):
+        return ColsumDesc(arena.ptr(part), arena.ptr(x), rows, pitch, C, 0)
+    return TcxOp(OP_TCX_COLSUM, make, name)
+
+
+def colsum_blocks(rows):
+    # mirrors tcx_colsum_blocks (csrc/tcx_aux.cu)
+    return int(min((rows + 255) // 256, 148 * 2))
+
+
+def split_rows(n_rt, want_ctas):
+    """(splits, row tiles per split) with no empty split."""
+    per = max(1, -(-n_rt // max(1, want_ctas)))
+    return -(-n_rt // per), per
+
+
+class CnnNet(object):
+    """CNNBase (reference model.py:169-195: conv 8x8/4 -> 4x4/2 -> 3x3/1 -> fc, ReLU after each) and the GRU's
+    input product on the TMA-fed engine.  Activations are NHWC planes (x, lo); the frames are re-laid out once per
+    minibatch as a 21 x 21 x 64 space-to-depth tensor so that conv1 is a 2 x 2 stride-1 convolution."""
+
+    def __init__(self, nb):
+        self.nb = nb
+        self.B, self.H = nb.B, nb.spec.hidden
+        self.frames_lo = nb.obs_code != 1          # fp32 frames are not exact in TF32: they get a lo plane too
+
+    # -- small helpers ------------------------------------------------------------------------------
+    def buf2(self, name, numel):
+        """x plane + lo plane."""
+        return self.nb.buf(name, numel), self.nb.buf(name + "_lo", numel)
+
+    def image(self, name, rows, cols):
+        self.nb.buf(name, rows * cols)
+        self.nb.buf(name + "_lo", rows * cols)
+        return self.nb.n(name)
+
+    def P(self, key):
+        return ("P", self.nb.L.entries[key][0])
+
+    def G(self, key):
+        return ("G", self.nb.L.entries[key][0])
+
+    # -- forward --------------------------------------------------------------------------------------
+    def forward(self):
+        nb, B, H = self.nb, self.B, self.H
+        ops = []
+        x0 = nb.buf("x0", B * 441 * 64)
+        x0_lo = nb.buf("x0_lo", B * 441 * 64) if self.frames_lo else None
+        (a1, a1_lo), (a2, a2_lo) = self.buf2("a1", B * 400 * 32), self.buf2("a2", B * 81 * 64)
+        (a3, a3_lo), (h, h_lo) = self.buf2("a3", B * 49 * 32), self.buf2("h", B * H)
+        self.refs = dict(x0=x0, x0_lo=x0_lo, a1=a1, a1_lo=a1_lo, a2=a2, a2_lo=a2_lo, a3=a3, a3_lo=a3_lo, h=h, h_lo=h_lo)
+
+        # ---- weight images (weights change with every optimiser step) ----
+        w1, w2, w3, wf = self.image("img_c1", 32, 256), self.image("img_c2", 64, 512), self.image("img_c3", 32, 576), \
+            self.image("img_fc", H, 1568)
+        # conv1: k = (by, bx | c, dy, dx) -> W[out, c, 4 by + dy, 4 bx + dx]
+        k1 = [c * 64 + (4 * by + dy) * 8 + 4 * bx + dx for by in range(2) for bx in range(2) for c in range(4)
+              for dy in range(4) for dx in range(4)]
+        k2 = [c * 16 + ky * 4 + kx for ky in range(4) for kx in range(4) for c in range(32)]
+        k3 = [c * 9 + ky * 3 + kx for ky in range(3) for kx in range(3) for c in range(64)]
+        self.fc_perm = [c * 49 + y * 7 + x for y in range(7) for x in range(7) for c in range(32)]   # NHWC -> NCHW flatten
+        ops += [prep_op("weight_image", w1, self.P("base.main.0.weight"), 32, 256, [n * 256 for n in range(32)], k1),
+                prep_op("weight_image", w2, self.P("base.main.2.weight"), 64, 512, [n * 512 for n in range(64)], k2),
+                prep_op("weight_image", w3, self.P("base.main.4.weight"), 32, 576, [n * 576 for n in range(32)], k3),
+                prep_op("weight_image", wf, self.P("base.main.7.weight"), H, 1568, [n * 1568 for n in range(H)], self.fc_perm)]
+
+        # ---- frames -> space-to-depth ----
+        frames, is_u8, gather = (nb.obs, 0), nb.obs_code == 1, nb.gather
+
+        def make_s2d(arena):
+            return S2dDesc(arena.ptr(x0), arena.ptr(x0_lo), arena.ptr(frames), None, 1 if is_u8 else 0, B, 4, 84, 84, 4)
+        ops.append(TcxOp(OP_TCX_S2D, make_s2d, "frames_s2d", runtime_idx=gather))
+
+        # ---- conv1: 2 x 2 taps x 64 channels, tile = 12 output rows of one image ----
+        kbs = [((c0, bx, by, 0), (by * 2 + bx) * 64 + c0) for by in range(2) for bx in range(2) for c0 in (0, 32)]
+        ops.append(fwd_op("conv1.fwd", x0, x0_lo, (64, 21, 21, B), (1, 64, 64 * 21, 64 * 441), (32, 20, 12, 1), w1, 32, 256,
+                          kbs, tiling(2 * B, 2, 12, t_div=2, tq_dim=3, tq_step=1), a1, a1_lo, (0, 32, 640, 12800),
+                          (0, 20, 20, B), 32, alpha=1.0 / 255.0, bias=self.P("base.main.0.bias"), act=1,
+                          flops=2.0 * B * 400 * 32 * 256))
+        # ---- conv2 (stride 2): parity view (px|c, X, py, Y, n) of a1, tile = 3 images ----
+        kbs = [(((kx % 2) * 32, kx // 2, ky % 2, ky // 2), (ky * 4 + kx) * 32) for ky in range(4) for kx in range(4)]
+        k = 3
+        ops.append(fwd_op("conv2.fwd", a1, a1_lo, (64, 10, 2, 10, B), (1, 64, 640, 1280, 12800), (32, 9, 1, 9, k), w2, 64, 512,
+                          kbs, tiling(-(-B // k), 4, k), a2, a2_lo, (0, 64, 0, 576, 5184), (0, 9, 1, 9, B), 64,
+                          bias=self.P("base.main.2.bias"), act=1, flops=2.0 * B * 81 * 64 * 512))
+        # ---- conv3: tile = 5 images ----
+        kbs = [((c0, kx, ky, 0), (ky * 3 + kx) * 64 + c0) for ky in range(3) for kx in range(3) for c0 in (0, 32)]
+        k = 5
+        ops.append(fwd_op("conv3.fwd", a2, a2_lo, (64, 9, 9, B), (1, 64, 576, 5184), (32, 7, 7, k), w3, 32, 576, kbs,
+                          tiling(-(-B // k), 3, k), a3, a3_lo, (0, 32, 224, 1568), (0, 7, 7, B), 32,
+                          bias=self.P("base.main.4.bias"), act=1, chain=6, flops=2.0 * B * 49 * 32 * 576))
+        # ---- fc ----
+        ops.append(self.linear_fwd("fc.fwd", a3, a3_lo, 1568, wf, H, h, h_lo, bias=self.P("base.main.7.bias"), act=1))
+        return ops, h
+
+    def linear_fwd(self, name, x, x_lo, K, img, N, out, out_lo, bias=None, act=0, mask=None):
+        B = self.B
+        R = 256 if B > 4096 else 128
+        kbs = [((32 * i, 0, 0, 0), 32 * i) for i in range(K // 32)]
+        return fwd_op(name, x, x_lo, (K, B), (1, K), (32, R), img, N, K, kbs, tiling(-(-B // R), 1, R), out, out_lo,
+                      (0, N), (0, B), N, bias=bias, act=act, mask=mask, chain=8, flops=2.0 * B * N * K)
+
+    def gru_ih_forward(self, gi):
+        """gi = h W_ih^T + b_ih for all rows (model.py:113 / torch GRU input product)."""
+        H = self.H
+        wi = self.image("img_gih", 3 * H, H)
+        r = self.refs
+        return [prep_op("weight_image", wi, self.P("base.gru.weight_ih_l0"), 3 * H, H, [n * H for n in range(3 * H)],
+                        list(range(H))),
+                self.linear_fwd("gru_ih.fwd", r["h"], r["h_lo"], H, wi, 3 * H, gi, None, bias=self.P("base.gru.bias_ih_l0"))]
+
+    # -- backward -------------------------------------------------------------------------------------
+    def bias_grad(self, name, x, rows, C, dst):
+        nb = self.nb
+        blocks = colsum_blocks(rows)
+        part = nb.buf("bpart_" + name, blocks * C)
+        from ._engine import RawOp, ReduceDesc, OP_REDUCE
+        return [colsum_op(name + ".bias_colsum", part, x, rows, C, C),
+                RawOp(OP_REDUCE, {"dst": dst, "src": part},
+                      dict(count=C, stride=C, splits=blocks, accumulate=0, ncols=0, act=0, beta=1.0), False,
+                      name + ".bias_fold", ReduceDesc)]
+
+    def fold(self, name, part, dst, count, splits):
+        from ._engine import RawOp, ReduceDesc, OP_REDUCE
+        return RawOp(OP_REDUCE, {"dst": dst, "src": part},
+                     dict(count=count, stride=count, splits=splits, accumulate=0, ncols=0, act=0, beta=1.0), False,
+                     name + ".fold", ReduceDesc)
+
+    def linear_wgrad(self, name, x, x_lo, K, gy, gy_lo, N, dst, perm=None):
+        """dW[n][perm(k)] = sum_rows gy[row, n] x[row, k]."""
+        B = self.B
+        R = 32
+        ot_a, ot_b = -(-K // 128), -(-N // 256)
+        n_rt = -(-B // R)
+        splits, per = split_rows(n_rt, max(1, 160 // (ot_a * ot_b)))
+        part = self.nb.buf("wpart_" + name, splits * N * K)
+        row_off = []
+        for f in range(ot_a * 128):
+            row_off.append(-1 if f >= K else (perm[f] if perm is not None else f))
+        groups = [[(32 * j, 0, 0, 0) for j in range(4)]]
+        b_boxes = [(32 * j, 0, 0, 0) for j in range(8)]
+        op = wgrad_op(name, x, x_lo, (K, B), (1, K), (32, R), gy, gy_lo, (N, B), (1, N), (32, R), groups, b_boxes,
+                      tiling(n_rt, 1, R), splits, 16, ot_a, ot_b, 128, 256, part, N * K, row_off, K, N,
+                      flops=2.0 * B * N * K)
+        return [op, self.fold(name, part, dst, N * K, splits)]
+
+    def backward(self, gh, gh_lo):
+        """gh: gradient w.r.t. the trunk output h (already masked by relu'), both planes."""
+        nb, B, H, r = self.nb, self.B, self.H, self.refs
+        ops = []
+        (g3, g3_lo), (g2, g2_lo), (g1, g1_lo) = self.buf2("g3", B * 49 * 32), self.buf2("g2", B * 81 * 64), \
+            self.buf2("g1", B * 400 * 32)
+        # ---- data-gradient weight images ----
+        wfd, w3d, w2d = self.image("img_fc_d", 1568, H), self.image("img_c3_d", 64, 288), self.image("img_c2_d", 32, 1024)
+        ops += [prep_op("weight_image", wfd, self.P("base.main.7.weight"), 1568, H, self.fc_perm, [k * 1568 for k in range(H)]),
+                # [ci][(ky, kx | co)] = W3[co, ci, ky, kx]
+                prep_op("weight_image", w3d, self.P("base.main.4.weight"), 64, 288, [ci * 9 for ci in range(64)],
+                        [co * 576 + ky * 3 + kx for ky in range(3) for kx in range(3) for co in range(32)]),
+                # [ci][(py, px | b, a | co)] = W2[co, ci, py + 2 b, px + 2 a]
+                prep_op("weight_image", w2d, self.P("base.main.2.weight"), 32, 1024, [ci * 16 for ci in range(32)],
+                        [co * 512 + (py + 2 * b) * 4 + (px + 2 * a) for py in range(2) for px in range(2)
+                         for b in range(2) for a in range(2) for co in range(64)])]
+        # ---- fc ----
+        ops += self.linear_wgrad("fc.wgrad", r["a3"], r["a3_lo"], 1568, gh, gh_lo, H, self.G("base.main.7.weight"),
+                                 perm=self.fc_perm)
+        ops += self.bias_grad("fc", gh, B, H, self.G("base.main.7.bias"))
+        ops.append(self.linear_fwd("fc.dgrad", gh, gh_lo, H, wfd, 1568, g3, g3_lo, mask=r["a3"]))
+        # ---- conv3 ----
+        ops += self.conv3_wgrad(g3, g3_lo)
+        ops += self.bias_grad("conv3", g3, B * 49, 32, self.G("base.main.4.bias"))
+        kbs = [((0, -kx, -ky, 0), (ky * 3 + kx) * 32) for ky in range(3) for kx in range(3)]
+        k = 3
+        ops.append(fwd_op("conv3.dgrad", g3, g3_lo, (32, 7, 7, B), (1, 32, 224, 1568), (32, 9, 9, k), w3d, 64, 288, kbs,
+                          tiling(-(-B // k), 3, k), g2, g2_lo, (0, 64, 576, 5184), (0, 9, 9, B), 64, mask=r["a2"], chain=5,
+                          flops=2.0 * B * 49 * 32 * 576))
+        # ---- conv2 ----
+        ops += self.conv2_wgrad(g2, g2_lo)
+        ops += self.bias_grad("conv2", g2, B * 81, 64, self.G("base.main.2.bias"))
+        k = 2
+        for py in range(2):
+            for px in range(2):
+                cls = py * 2 + px
+                kbs = [((c0, -a, -b, 0), cls * 256 + (b * 2 + a) * 64 + c0) for b in range(2) for a in range(2)
+                       for c0 in (0, 32)]
+                ops.append(fwd_op("conv2.dgrad", g2, g2_lo, (64, 9, 9, B), (1, 64, 576, 5184), (32, 10, 10, k), w2d, 32, 1024,
+                                  kbs, tiling(-(-B // k), 3, k), g1, g1_lo, (0, 64, 1280, 12800), (0, 10, 10, B), 32,
+                                  mask=r["a1"], o_base=(py * 20 + px) * 32, flops=2.0 * B * 81 * 64 * 512 / 4))
+        # ---- conv1 ----
+        ops += self.conv1_wgrad(g1, g1_lo)
+        ops += self.bias_grad("conv1", g1, B * 400, 32, self.G("base.main.0.bias"))
+        return ops
+
+    def conv3_wgrad(self, g3, g3_lo):
+        B, r = self.B, self.refs
+        groups, row_off = [], []
+        for g in range(5):
+            boxes = []
+            for j in range(4):
+                tap = 2 * g + j // 2
+                boxes.append(((j % 2) * 32, tap % 3, tap // 3, 0) if tap < 9 else (0, 0, 0, OOB))
+                row_off += [(((j % 2) * 32 + c) * 9 + tap) if tap < 9 else -1 for c in range(32)]
+            groups.append(boxes)
+        splits, per = split_rows(B, 148)
+        part = self.nb.buf("wpart_conv3", splits * 32 * 576)
+        op = wgrad_op("conv3.wgrad", r["a2"], r["a2_lo"], (64, 9, 9, B), (1, 64, 576, 5184), (32, 7, 7, 1), g3, g3_lo,
+                      (32, 7, 7, B), (1, 32, 224, 1568), (32, 7, 7, 1), groups, [(0, 0, 0, 0)], tiling(B, 3, 1), splits, 8,
+                      1, 1, 0, 0, part, 32 * 576, row_off, 576, 32, flops=2.0 * B * 49 * 32 * 576)
+        return [op, self.fold("conv3.wgrad", part, self.G("base.main.4.weight"), 32 * 576, splits)]
+
+    def conv2_wgrad(self, g2, g2_lo):
+        B, r = self.B, self.refs
+        groups, row_off = [], []
+        for ky in range(4):
+            boxes = []
+            for kx in range(4):
+                boxes.append(((kx % 2) * 32, kx // 2, ky % 2, ky // 2))
+                row_off += [c * 16 + ky * 4 + kx for c in range(32)]
+            groups.append(boxes)
+        n_rt = 2 * B                                   # half images: 5 output rows x 9
+        splits, per = split_rows(n_rt, 148)
+        part = self.nb.buf("wpart_conv2", splits * 64 * 512)
+        op = wgrad_op("conv2.wgrad", r["a1"], r["a1_lo"], (64, 10, 2, 10, B), (1, 64, 640, 1280, 12800), (32, 9, 1, 5, 1),
+                      g2, g2_lo, (64, 9, 1, 9, B), (1, 64, 64, 576, 5184), (32, 9, 1, 5, 1), groups,
+                      [(0, 0, 0, 0), (32, 0, 0, 0)], tiling(n_rt, 3, 5, t_div=2, tq_dim=4, tq_step=1), splits, 8, 1, 1, 0, 0,
+                      part, 64 * 512, row_off, 512, 64, flops=2.0 * B * 81 * 64 * 512)
+        return [op, self.fold("conv2.wgrad", part, self.G("base.main.2.weight"), 64 * 512, splits)]
+
+    def conv1_wgrad(self, g1, g1_lo):
+        B, r = self.B, self.refs
+        groups, row_off = [], []
+        for g in range(2):
+            boxes = []
+            for j in range(4):
+                by, bx = g, j // 2
+                boxes.append(((j % 2) * 32, bx, by, 0))
+                for cl in range(32):
+                    cc = (j % 2) * 32 + cl
+                    c, dy, dx = cc // 16, (cc // 4) % 4, cc % 4
+                    row_off.append(c * 64 + (4 * by + dy) * 8 + 4 * bx + dx)
+            groups.append(boxes)
+        yr = 2 if self.frames_lo else 4                 # output rows per row tile
+        n_rt = (20 // yr) * B
+        splits, per = split_rows(n_rt, 148)
+        part = self.nb.buf("wpart_conv1", splits * 32 * 256)
+        op = wgrad_op("conv1.wgrad", r["x0"], r["x0_lo"], (64, 21, 21, B), (1, 64, 64 * 21, 64 * 441), (32, 20, yr, 1), g1, g1_lo,
+                      (32, 20, 20, B), (1, 32, 640, 12800), (32, 20, yr, 1), groups, [(0, 0, 0, 0)],
+                      tiling(n_rt, 2, yr, t_div=20 // yr, tq_dim=3, tq_step=1), splits, 6 if yr == 4 else 12, 1, 1, 0, 0, part,
+                      32 * 256, row_off, 256, 32, alpha=1.0 / 255.0, flops=2.0 * B * 400 * 32 * 256)
+        return [op, self.fold("conv1.wgrad", part, self.G("base.main.0.weight"), 32 * 256, splits)]
+
+    # -- GRU linear parts (the recurrence itself is csrc/gru_persistent.cu) ---------------------------
+    def gru_backward(self, dgi, dgh, hm, gx, gx_lo):
+        """Weight / bias gradients of both GRU matrices and the gradient w.r.t. the GRU input (masked by relu' of h)."""
+        nb, B, H, r = self.nb, self.B, self.H, self.refs
+        dgi_lo, dgh_lo, hm_lo = nb.buf("gru_dgi_lo", B * 3 * H), nb.buf("gru_dgh_lo", B * 3 * H), nb.buf("gru_hm_lo", B * H)
+        wid = self.image("img_gih_d", H, 3 * H)
+        ops = [lo_op("lo_plane", dgi, dgi_lo, B * 3 * H), lo_op("lo_plane", dgh, dgh_lo, B * 3 * H),
+               lo_op("lo_plane", hm, hm_lo, B * H)]
+        ops += self.linear_wgrad("gru_hh.wgrad", hm, hm_lo, H, dgh, dgh_lo, 3 * H, self.G("base.gru.weight_hh_l0"))
+        ops += self.bias_grad("gru_hh", dgh, B, 3 * H, self.G("base.gru.bias_hh_l0"))
+        ops += self.linear_wgrad("gru_ih.wgrad", r["h"], r["h_lo"], H, dgi, dgi_lo, 3 * H, self.G("base.gru.weight_ih_l0"))
+        ops += self.bias_grad("gru_ih", dgi, B, 3 * H, self.G("base.gru.bias_ih_l0"))
+        ops.append(prep_op("weight_image", wid, self.P("base.gru.weight_ih_l0"), H, 3 * H, list(range(H)),
+                           [k * H for k in range(3 * H)]))
+        ops.append(self.linear_fwd("gru_ih.dgrad", dgi, dgi_lo, 3 * H, wid, H, gx, gx_lo, mask=r["h"]))
+        return ops

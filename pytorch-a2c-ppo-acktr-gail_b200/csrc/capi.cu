@@ -5,6 +5,7 @@
 #include "gemm.cuh"
 #include "loss.cuh"
 #include "gru.cuh"
+#include "tcx.cuh"
 
 #include <atomic>
 #include <stdarg.h>
@@ -149,6 +150,40 @@ int a2cb_gru_seq(int32_t backward, const a2cb_gru_seq_t* desc, a2cb_stream_t str
 }
 int a2cb_gru_seq_supported(int32_t N, int32_t H) { return gru_persistent_supported(N, H) ? 1 : 0; }
 
+int a2cb_tcx_fwd(const a2cb_tcx_fwd_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc, "tcx_fwd: null descriptor");
+    static_assert(sizeof(a2cb_tcx_fwd_t) == sizeof(TcxFwd), "a2cb_tcx_fwd_t out of sync with TcxFwd");
+    return tcx_fwd(*reinterpret_cast<const TcxFwd*>(desc), (cudaStream_t)stream);
+}
+int a2cb_tcx_wgrad(const a2cb_tcx_wgrad_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc, "tcx_wgrad: null descriptor");
+    static_assert(sizeof(a2cb_tcx_wgrad_t) == sizeof(TcxWgrad), "a2cb_tcx_wgrad_t out of sync with TcxWgrad");
+    return tcx_wgrad(*reinterpret_cast<const TcxWgrad*>(desc), (cudaStream_t)stream);
+}
+int a2cb_tcx_lo_plane(float* lo, const float* x, int64_t n, a2cb_stream_t stream) {
+    return tcx_lo_plane(lo, x, (long)n, (cudaStream_t)stream);
+}
+int a2cb_tcx_prep_weights(float* img, float* img_lo, const float* src, int64_t N, int64_t K, const int32_t* ntab,
+                          const int32_t* ktab, a2cb_stream_t stream) {
+    return tcx_prep_weights(img, img_lo, src, (long)N, (long)K, ntab, ktab, (cudaStream_t)stream);
+}
+int a2cb_tcx_s2d(float* out, float* out_lo, const void* frames, int32_t src_is_u8, const int64_t* idx, int32_t B,
+                 int32_t C, int32_t H, int32_t W, int32_t S, a2cb_stream_t stream) {
+    return tcx_s2d(out, out_lo, frames, src_is_u8, idx, B, C, H, W, S, (cudaStream_t)stream);
+}
+int a2cb_tcx_colsum(float* part, const float* x, int64_t rows, int32_t C, int64_t pitch, a2cb_stream_t stream) {
+    return tcx_colsum(part, x, (long)rows, C, (long)pitch, (cudaStream_t)stream);
+}
+int a2cb_tcx_sizeof(int32_t which) {
+    return which == 0 ? (int)sizeof(TcxFwd) : which == 1 ? (int)sizeof(TcxWgrad) : (int)sizeof(TcxView);
+}
+int a2cb_tcx_colsum_blocks(int64_t rows) { return tcx_colsum_blocks((long)rows); }
+int a2cb_tcx_set_knobs(int32_t mn_layout_type, int32_t mn_sbo_bytes, int32_t mn_kstep_bytes, int32_t mn_tma_swizzle) {
+    TcxKnobs k = {mn_layout_type, mn_sbo_bytes, mn_kstep_bytes, mn_tma_swizzle};
+    tcx_set_knobs(k);
+    return A2CB_OK;
+}
+
 int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream) {
     A2CB_REQUIRE(n_ops >= 0 && (n_ops == 0 || ops), "run_ops: bad op list");
     cudaStream_t st = (cudaStream_t)stream;
@@ -211,6 +246,32 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
                 GruDesc d = *reinterpret_cast<const GruDesc*>(&q.d);
                 if (rt) d.idx = idx;
                 rc = gru_persistent(op.kind == A2CB_OP_GRU_SEQ_BWD, d, q.W_hh, q.b_hh, st);
+                break;
+            }
+            case A2CB_OP_TCX_FWD:
+                rc = tcx_fwd(*reinterpret_cast<const TcxFwd*>(op.desc), st);
+                break;
+            case A2CB_OP_TCX_WGRAD:
+                rc = tcx_wgrad(*reinterpret_cast<const TcxWgrad*>(op.desc), st);
+                break;
+            case A2CB_OP_TCX_LO: {
+                const a2cb_tcx_lo_t& q = *reinterpret_cast<const a2cb_tcx_lo_t*>(op.desc);
+                rc = tcx_lo_plane(q.lo, q.x, (long)q.n, st);
+                break;
+            }
+            case A2CB_OP_TCX_PREP: {
+                const a2cb_tcx_prep_t& q = *reinterpret_cast<const a2cb_tcx_prep_t*>(op.desc);
+                rc = tcx_prep_weights(q.img, q.img_lo, q.src, (long)q.N, (long)q.K, q.ntab, q.ktab, st);
+                break;
+            }
+            case A2CB_OP_TCX_S2D: {
+                const a2cb_tcx_s2d_t& q = *reinterpret_cast<const a2cb_tcx_s2d_t*>(op.desc);
+                rc = tcx_s2d(q.out, q.out_lo, q.frames, q.src_is_u8, rt ? idx : q.idx, q.B, q.C, q.H, q.W, q.S, st);
+                break;
+            }
+            case A2CB_OP_TCX_COLSUM: {
+                const a2cb_tcx_colsum_t& q = *reinterpret_cast<const a2cb_tcx_colsum_t*>(op.desc);
+                rc = tcx_colsum(q.part, q.x, (long)q.rows, q.C, (long)q.pitch, st);
                 break;
             }
             case A2CB_OP_GRU_INIT:

@@ -59,4 +59,19 @@ int gru_op(int which, const GruDesc& d, cudaStream_t st);   // which: 0 init, 1 
 bool gru_persistent_supported(int N, int H);
 int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st);
 
+// tcx.cu / tcx_aux.cu
+struct TcxFwd;
+struct TcxWgrad;
+struct TcxKnobs;
+int tcx_fwd(const TcxFwd& p, cudaStream_t st);
+int tcx_wgrad(const TcxWgrad& p, cudaStream_t st);
+void tcx_set_knobs(const TcxKnobs& k);
+int tcx_lo_plane(float* lo, const float* x, long n, cudaStream_t st);
+int tcx_prep_weights(float* img, float* img_lo, const float* src, long N, long K, const int32_t* ntab,
+                     const int32_t* ktab, cudaStream_t st);
+int tcx_s2d(float* out, float* out_lo, const void* frames, int src_is_u8, const int64_t* idx, int B, int C, int H, int W,
+            int S, cudaStream_t st);
+int tcx_colsum(float* part, const float* x, long rows, int C, long pitch, cudaStream_t st);
+int tcx_colsum_blocks(long rows);
+
 }  // namespace a2cb

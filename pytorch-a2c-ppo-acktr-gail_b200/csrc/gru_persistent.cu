@@ -2,13 +2,14 @@
 //
 // The per-step formulation (gru.cu + one tiny GEMM per step) is launch- and latency-bound: at the
 // C5 minibatch shape (T = 128, N = 64 environments, H = 512) the 2 x 128 sequential GEMMs of
-// 0.1 GFLOP each cost ~18 us apiece although they are ~1 us of math.  Here every CTA owns KB = 8
-// hidden units for one block of 64 environments and keeps ITS slice of W_hh resident in shared
-// memory for all T steps (forward: the 3 x 8 gate rows, 48 KiB; backward: the 8 columns, 48 KiB);
-// per step it streams the previous state (forward) / the gate gradients (backward) of its
-// environment block from L2 through a padded shared-memory tile, does the matmul slice, applies the
-// gate math in registers, and meets the other CTAs at one grid-wide barrier.  Episode boundaries are
-// handled by the mask multiply, exactly as in gru.cu (reference model.py:111-166).
+// 0.1 GFLOP each cost ~18 us apiece although they are ~1.5 us of fp32 math.  Here CTA b owns 4 hidden
+// units for ALL environments and keeps its slice of W_hh (12 gate rows forward, 4 columns backward,
+// 24 KiB) resident in shared memory for all T steps; H / 4 = 128 CTAs, one per SM.  Per step a warp
+// takes 8 environments, its lanes split the reduction dimension, operands stream from L2 with
+// coalesced ld.global.cg float4 (no shared-memory staging, no bank conflicts), partial sums are
+// transpose-reduced with shuffles so that lane 4 r + j finishes (environment r, unit j), and the
+// CTAs meet at ONE grid barrier per step.  Episode boundaries are the mask multiply, exactly as in
+// gru.cu (reference model.py:111-166).
 //
 // Same buffers and the same saved quantities as the per-step path, so either path can feed the
 // weight-gradient GEMMs and the tests compare both against the reference goldens.
@@ -22,10 +23,11 @@ namespace cg = cooperative_groups;
 
 namespace a2cb {
 
-constexpr int PG_KB = 8;        // hidden units per CTA
-constexpr int PG_RB = 64;       // environments per CTA
-constexpr int PG_NT = 256;      // threads: (row = tid % 64) x (unit pair = tid / 64)
-constexpr int PG_KC = 64;       // reduction chunk staged in shared memory
+constexpr int PG_KB = 4;        // hidden units per CTA  (H / 4 CTAs: 128 for the 512-unit GRU)
+constexpr int PG_RW = 8;        // environments per warp
+constexpr int PG_NW = 8;        // warps per CTA -> 64 environments per pass
+constexpr int PG_RB = PG_RW * PG_NW;
+constexpr int PG_NT = 32 * PG_NW;
 
 __device__ __forceinline__ float pg_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -35,198 +37,264 @@ __device__ __forceinline__ float pg_mask(const GruDesc& d, int t, int n) {
     return d.masks[src];
 }
 
-// Loads src[(row0 + r) * ld + k0 + k] for r < 64, k < PG_KC into tile[k][r] (transposed, padded).
-__device__ __forceinline__ void pg_load_tile(float (*tile)[PG_RB + 1], const float* __restrict__ src, long ld,
-                                             int row0, int nrows, int k0, int tid) {
-    // 64 rows x 16 float4 per chunk; consecutive lanes take consecutive float4 of one row (coalesced)
+__device__ __forceinline__ float pg_dot4(const float4 a, const float4 b, float acc) {
+    acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+    acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    return acc;
+}
+
+// Butterfly "transpose-reduce": every lane enters with NV partial sums v[0..NV) (NV = 32 * PER) of the
+// same NV outputs and leaves with the complete sums of outputs lane * PER + i in v[i], i < PER.  Each of
+// the five halving rounds exchanges the half a lane does not keep with its xor-partner.
+template <int NV>
+__device__ __forceinline__ void pg_reduce(float* v, int lane) {
 #pragma unroll
-    for (int q = 0; q < (PG_RB * PG_KC / 4) / PG_NT; ++q) {
-        const int s = tid + q * PG_NT;
-        const int r = s / (PG_KC / 4), k4 = (s % (PG_KC / 4)) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nrows) v = *reinterpret_cast<const float4*>(src + (long)(row0 + r) * ld + k0 + k4);
-        tile[k4 + 0][r] = v.x; tile[k4 + 1][r] = v.y; tile[k4 + 2][r] = v.z; tile[k4 + 3][r] = v.w;
+    for (int s = 0; s < 5; ++s) {
+        const int half = NV >> (s + 1);                      // values kept after this round
+        const int off = 16 >> s;
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float a = v[i], b = v[i + half];
+            const float send = upper ? a : b;
+            const float keep = upper ? b : a;
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
-// forward
+// forward: CTA b owns hidden units kb = 4 b .. 4 b + 3 (12 gate rows of W_hh resident in shared memory).
+// Per step and per block of 64 environments: warp w takes 8 environments, its lanes split the reduction
+// (lane l: k = 4 l .. 4 l + 3 of every 128), hm_t comes straight from L2 (ld.global.cg, coalesced float4,
+// 8 independent loads in flight per lane), the 96 partial sums are transpose-reduced so that lane
+// l = 4 r + j ends up with the three gate pre-activations of (environment r, unit j) and applies the gate
+// math.  One grid barrier per step.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(PG_NT)
 gru_persistent_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh) {
     extern __shared__ __align__(16) float pg_smem[];
     const int H = d.H;
-    float* Ws = pg_smem;                                            // [3 * KB][H]: rows (unit j, gate g) -> j * 3 + g
-    float (*tile)[PG_RB + 1] = reinterpret_cast<float (*)[PG_RB + 1]>(pg_smem + 3 * PG_KB * H);
+    float* Ws = pg_smem;                                            // [j * 3 + g][H]
     cg::grid_group grid = cg::this_grid();
 
-    const int tid = threadIdx.x;
-    const int kb = blockIdx.x * PG_KB;                              // first hidden unit of this CTA
-    const int row0 = blockIdx.y * PG_RB;
-    const int nrows = min(PG_RB, d.N - row0);
-    const int r = tid % PG_RB, up = tid / PG_RB;                    // this thread: env row r, units 2*up, 2*up + 1
-
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kb = blockIdx.x * PG_KB;
     for (int e = tid; e < 3 * PG_KB * H; e += PG_NT) {
         const int c = e / H, k = e - c * H;
         const int j = c / 3, g = c - j * 3;
         Ws[e] = Whh[(long)(g * H + kb + j) * H + k];
     }
-    float bias[6];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        const int j = 2 * up + c / 3, g = c % 3;
-        bias[c] = bhh[g * H + kb + j];
+    const int rl = lane >> 2, jl = lane & 3;                        // this lane's (environment, unit) after the reduce
+    const int ku = kb + jl;
+    const float b_r = bhh[ku], b_z = bhh[H + ku], b_n = bhh[2 * H + ku];
+    const int nblk = (d.N + PG_RB - 1) / PG_RB;
+
+    // hm_0 = h0 * mask_0 for this CTA's units
+    for (int e = tid; e < d.N * PG_KB; e += PG_NT) {
+        const int n = e / PG_KB, k = kb + (e - n * PG_KB);
+        d.hm[(long)n * H + k] = d.h0[(long)n * H + k] * pg_mask(d, 0, n);
     }
-    // hm_0 = h0 * mask_0 for this CTA's units (every CTA writes its own columns of hm[0])
-    if (r < nrows) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int k = kb + 2 * up + u;
-            d.hm[(long)(row0 + r) * H + k] = d.h0[(long)(row0 + r) * H + k] * pg_mask(d, 0, row0 + r);
-        }
-    }
-    __threadfence();
+    __syncthreads();
     grid.sync();
 
     for (int t = 0; t < d.T; ++t) {
         const float* hm_t = d.hm + (long)t * d.N * H;
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int k0 = 0; k0 < H; k0 += PG_KC) {
-            __syncthreads();
-            pg_load_tile(tile, hm_t, H, row0, nrows, k0, tid);
-            __syncthreads();
-            const float* w = Ws + (long)(6 * up) * H + k0;
-#pragma unroll 4
-            for (int k = 0; k < PG_KC; k += 4) {
-                const float h0v = tile[k][r], h1v = tile[k + 1][r], h2v = tile[k + 2][r], h3v = tile[k + 3][r];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) {
-                    const float4 wv = *reinterpret_cast<const float4*>(w + (long)c * H + k);
-                    acc[c] = fmaf(h0v, wv.x, acc[c]); acc[c] = fmaf(h1v, wv.y, acc[c]);
-                    acc[c] = fmaf(h2v, wv.z, acc[c]); acc[c] = fmaf(h3v, wv.w, acc[c]);
-                }
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int r0 = blk * PG_RB + warp * PG_RW;
+            const int my = r0 + rl;                                 // the environment this lane finishes
+            const bool live = my < d.N;
+            const long row = (long)t * d.N + my;
+            float gi_r = 0.f, gi_z = 0.f, gi_n = 0.f, hprev = 0.f, mnext = 0.f;
+            if (live) {                                             // issued early, consumed after the matmul
+                const float* gi = d.gi + row * 3 * H;
+                gi_r = __ldg(gi + ku); gi_z = __ldg(gi + H + ku); gi_n = __ldg(gi + 2 * H + ku);
+                hprev = __ldcg(hm_t + (long)my * H + ku);
+                mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, my) : 0.f;
             }
-        }
-        if (r < nrows) {
-            const long row = (long)t * d.N + row0 + r;
-            const float* gi = d.gi + row * 3 * H;
-            const float mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, row0 + r) : 0.f;
+            float acc[PG_RW * 12];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int k = kb + 2 * up + u;
-                const float ghr = acc[3 * u + 0] + bias[3 * u + 0];
-                const float ghz = acc[3 * u + 1] + bias[3 * u + 1];
-                const float ghn = acc[3 * u + 2] + bias[3 * u + 2];
-                const float hm = hm_t[(long)(row0 + r) * H + k];
-                const float rr = pg_sigmoid(gi[k] + ghr);
-                const float zz = pg_sigmoid(gi[H + k] + ghz);
-                const float nn = tanhf(gi[2 * H + k] + rr * ghn);
-                const float h = (1.f - zz) * nn + zz * hm;
-                d.out[row * H + k] = h;
+            for (int i = 0; i < PG_RW * 12; ++i) acc[i] = 0.f;
+            // two register sets of 8 float4: the loads of chunk i + 1 are in flight while chunk i is multiplied
+            float4 ha[PG_RW], hb[PG_RW];
+            auto load_h = [&](float4* h, int k0) {
+#pragma unroll
+                for (int r = 0; r < PG_RW; ++r) {
+                    const int n = min(r0 + r, d.N - 1);
+                    h[r] = __ldcg(reinterpret_cast<const float4*>(hm_t + (long)n * H + k0 + 4 * lane));
+                }
+            };
+            auto mul_h = [&](const float4* h, int k0) {
+#pragma unroll
+                for (int c = 0; c < 12; ++c) {
+                    const float4 w = *reinterpret_cast<const float4*>(Ws + c * H + k0 + 4 * lane);
+#pragma unroll
+                    for (int r = 0; r < PG_RW; ++r) acc[r * 12 + c] = pg_dot4(h[r], w, acc[r * 12 + c]);
+                }
+            };
+            load_h(ha, 0);
+            for (int k0 = 0; k0 < H; k0 += 256) {
+                if (k0 + 128 < H) load_h(hb, k0 + 128);
+                mul_h(ha, k0);
+                if (k0 + 256 < H) load_h(ha, k0 + 256);
+                if (k0 + 128 < H) mul_h(hb, k0 + 128);
+            }
+            pg_reduce<PG_RW * 12>(acc, lane);                      // acc[0..2] = (r, z, n) sums of (rl, jl)
+            if (live) {
+                const float ghr = acc[0] + b_r, ghz = acc[1] + b_z, ghn = acc[2] + b_n;
+                const float rr = pg_sigmoid(gi_r + ghr);
+                const float zz = pg_sigmoid(gi_z + ghz);
+                const float nn = tanhf(gi_n + rr * ghn);
+                const float h = (1.f - zz) * nn + zz * hprev;
+                d.out[row * H + ku] = h;
                 if (d.r) {
-                    d.r[row * H + k] = rr; d.z[row * H + k] = zz; d.n[row * H + k] = nn;
-                    d.gh[row * 3 * H + 2 * H + k] = ghn;             // the only part of gh the backward pass reads
+                    d.r[row * H + ku] = rr; d.z[row * H + ku] = zz; d.n[row * H + ku] = nn;
+                    d.gh[row * 3 * H + 2 * H + ku] = ghn;            // the only part of gh the backward pass reads
                 }
-                if (t + 1 < d.T) d.hm[(row + d.N) * H + k] = h * mnext;
+                if (t + 1 < d.T) __stcg(d.hm + (row + d.N) * H + ku, h * mnext);
             }
         }
-        if (t + 1 < d.T) {
-            __threadfence();
-            grid.sync();
-        }
+        if (t + 1 < d.T) grid.sync();
     }
 }
 
 // ---------------------------------------------------------------------------
-// backward through time
+// backward through time: CTA b owns the same 4 units; its columns of W_hh (all 3H gate rows) stay in
+// shared memory.  Phase A (element-wise gate gradients of its units, needs the carry it computed itself),
+// grid barrier, phase B (carry = dh z + dgh_t W_hh restricted to its units, lanes split the 3H-long
+// reduction, 32 partial sums transpose-reduced to one per lane).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(PG_NT)
-gru_persistent_bwd_kernel(const GruDesc d, const float* __restrict__ Whh) {
+gru_persistent_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws) {
     extern __shared__ __align__(16) float pg_smem[];
-    const int H = d.H;
-    float* Wc = pg_smem;                                            // [3H][KB]: W_hh[c][kb + j]
-    float (*tile)[PG_RB + 1] = reinterpret_cast<float (*)[PG_RB + 1]>(pg_smem + 3 * H * PG_KB);
+    const int H = d.H, H3 = 3 * d.H;
+    float* Wc = pg_smem;     // [(c / 128) * 4 + c % 4][lane = (c % 128) / 4][4 units]: conflict-free float4 per lane
     cg::grid_group grid = cg::this_grid();
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kb = blockIdx.x * PG_KB;
-    const int row0 = blockIdx.y * PG_RB;
-    const int nrows = min(PG_RB, d.N - row0);
-    const int r = tid % PG_RB, up = tid / PG_RB;
-
-    for (int e = tid; e < 3 * H * PG_KB; e += PG_NT) {
+    for (int e = tid; e < H3 * PG_KB; e += PG_NT) {
         const int c = e / PG_KB, j = e - c * PG_KB;
-        Wc[e] = Whh[(long)c * H + kb + j];
+        const int it = c >> 7, l = (c & 127) >> 2, q = c & 3;
+        Wc[(((it * 4 + q) * 32) + l) * 4 + j] = Whh[(long)c * H + kb + j];
     }
-    float carry[2] = {0.f, 0.f};          // d loss / d hm_{t+1} for this thread's (row, 2 units)
+    __syncthreads();
+    const int rl = lane >> 2, jl = lane & 3;
+    const int ku = kb + jl;
+    const int nblk = (d.N + PG_RB - 1) / PG_RB;
+    // carry of (environment, unit): one per lane per environment block; blocks beyond the first spill to a
+    // small global workspace slice private to this CTA
+    float carry0 = 0.f;
+
+    struct PhaseA { float dout, r, z, n, hm, ghn, mnext; };
+    auto load_a = [&](int t, int my) {
+        PhaseA a;
+        const long row = (long)t * d.N + my;
+        a.dout = d.dout[row * H + ku];
+        a.r = d.r[row * H + ku]; a.z = d.z[row * H + ku]; a.n = d.n[row * H + ku];
+        a.hm = d.hm[row * H + ku];
+        a.ghn = d.gh[row * 3 * H + 2 * H + ku];
+        a.mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, my) : 0.f;
+        return a;
+    };
+    const int my0 = warp * PG_RW + rl;                       // this lane's environment in block 0
+    PhaseA pre = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (my0 < d.N) pre = load_a(d.T - 1, my0);
 
     for (int t = d.T - 1; t >= 0; --t) {
-        const long row = (long)t * d.N + row0 + r;
-        float dhz[2] = {0.f, 0.f};
-        // ---- phase A: gate gradients of this CTA's units ----
-        if (r < nrows) {
-            const float mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, row0 + r) : 0.f;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int k = kb + 2 * up + u;
-                float dh = d.dout[row * H + k];
-                if (t + 1 < d.T) dh += carry[u] * mnext;
-                const float rr = d.r[row * H + k], zz = d.z[row * H + k], nn = d.n[row * H + k];
-                const float hm = d.hm[row * H + k];
-                const float ghn = d.gh[row * 3 * H + 2 * H + k];
-                const float dn_pre = dh * (1.f - zz) * (1.f - nn * nn);
-                const float dz_pre = dh * (hm - nn) * zz * (1.f - zz);
-                const float dr_pre = dn_pre * ghn * rr * (1.f - rr);
-                float* dgi = d.dgi + row * 3 * H;
-                float* dgh = d.dgh + row * 3 * H;
-                dgi[k] = dr_pre; dgi[H + k] = dz_pre; dgi[2 * H + k] = dn_pre;
-                dgh[k] = dr_pre; dgh[H + k] = dz_pre; dgh[2 * H + k] = dn_pre * rr;
-                dhz[u] = dh * zz;
+        // ---- phase A ----
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int my = blk * PG_RB + warp * PG_RW + rl;
+            if (my >= d.N) continue;
+            const long row = (long)t * d.N + my;
+            const PhaseA a = blk == 0 ? pre : load_a(t, my);   // block 0 was prefetched before the last barrier
+            float dh = a.dout;
+            if (t + 1 < d.T) {
+                const float c = blk == 0 ? carry0 : carry_ws[((long)blockIdx.x * d.N + my) * PG_KB + jl];
+                dh += c * a.mnext;
             }
+            const float dn_pre = dh * (1.f - a.z) * (1.f - a.n * a.n);
+            const float dz_pre = dh * (a.hm - a.n) * a.z * (1.f - a.z);
+            const float dr_pre = dn_pre * a.ghn * a.r * (1.f - a.r);
+            float* dgi = d.dgi + row * 3 * H;
+            float* dgh = d.dgh + row * 3 * H;
+            dgi[ku] = dr_pre; dgi[H + ku] = dz_pre; dgi[2 * H + ku] = dn_pre;
+            __stcg(dgh + ku, dr_pre); __stcg(dgh + H + ku, dz_pre); __stcg(dgh + 2 * H + ku, dn_pre * a.r);
+            const float dhz = dh * a.z;
+            if (blk == 0) carry0 = dhz;
+            else carry_ws[((long)blockIdx.x * d.N + my) * PG_KB + jl] = dhz;
         }
         if (t == 0) break;                 // the gradient w.r.t. the initial state is not needed
-        __threadfence();
+        if (my0 < d.N) pre = load_a(t - 1, my0);               // in flight across the barrier and phase B
         grid.sync();
-        // ---- phase B: carry[u] = dh * z + (dgh_t W_hh)[row, unit] over all 3H gate columns ----
-        const float* dgh_t = d.dgh + (long)t * d.N * 3 * H;
-        float acc0 = 0.f, acc1 = 0.f;
-        for (int c0 = 0; c0 < 3 * H; c0 += PG_KC) {
-            __syncthreads();
-            pg_load_tile(tile, dgh_t, 3 * H, row0, nrows, c0, tid);
-            __syncthreads();
-            const float* w = Wc + (long)c0 * PG_KB + 2 * up;
-#pragma unroll 8
-            for (int c = 0; c < PG_KC; ++c) {
-                const float g = tile[c][r];
-                const float2 wv = *reinterpret_cast<const float2*>(w + c * PG_KB);
-                acc0 = fmaf(g, wv.x, acc0);
-                acc1 = fmaf(g, wv.y, acc1);
+        // ---- phase B ----
+        const float* dgh_t = d.dgh + (long)t * d.N * H3;
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int r0 = blk * PG_RB + warp * PG_RW;
+            float acc[PG_RW * PG_KB];
+#pragma unroll
+            for (int i = 0; i < PG_RW * PG_KB; ++i) acc[i] = 0.f;
+            float4 ga[PG_RW], gb[PG_RW];
+            auto load_g = [&](float4* g, int it) {
+#pragma unroll
+                for (int r = 0; r < PG_RW; ++r) {
+                    const int n = min(r0 + r, d.N - 1);
+                    g[r] = __ldcg(reinterpret_cast<const float4*>(dgh_t + (long)n * H3 + it * 128 + 4 * lane));
+                }
+            };
+            auto mul_g = [&](const float4* g, int it) {
+                const float4* wp = reinterpret_cast<const float4*>(Wc) + (it * 4) * 32 + lane;
+                const float4 w0 = wp[0], w1 = wp[32], w2 = wp[64], w3 = wp[96];
+#pragma unroll
+                for (int r = 0; r < PG_RW; ++r) {
+                    float* a = acc + r * PG_KB;
+                    a[0] = fmaf(g[r].x, w0.x, a[0]); a[1] = fmaf(g[r].x, w0.y, a[1]);
+                    a[2] = fmaf(g[r].x, w0.z, a[2]); a[3] = fmaf(g[r].x, w0.w, a[3]);
+                    a[0] = fmaf(g[r].y, w1.x, a[0]); a[1] = fmaf(g[r].y, w1.y, a[1]);
+                    a[2] = fmaf(g[r].y, w1.z, a[2]); a[3] = fmaf(g[r].y, w1.w, a[3]);
+                    a[0] = fmaf(g[r].z, w2.x, a[0]); a[1] = fmaf(g[r].z, w2.y, a[1]);
+                    a[2] = fmaf(g[r].z, w2.z, a[2]); a[3] = fmaf(g[r].z, w2.w, a[3]);
+                    a[0] = fmaf(g[r].w, w3.x, a[0]); a[1] = fmaf(g[r].w, w3.y, a[1]);
+                    a[2] = fmaf(g[r].w, w3.z, a[2]); a[3] = fmaf(g[r].w, w3.w, a[3]);
+                }
+            };
+            const int nit = H3 / 128;
+            load_g(ga, 0);
+            for (int it = 0; it < nit; it += 2) {
+                if (it + 1 < nit) load_g(gb, it + 1);
+                mul_g(ga, it);
+                if (it + 2 < nit) load_g(ga, it + 2);
+                if (it + 1 < nit) mul_g(gb, it + 1);
+            }
+            pg_reduce<PG_RW * PG_KB>(acc, lane);                   // acc[0] = sum of (rl, jl)
+            const int my = r0 + rl;
+            if (my < d.N) {
+                if (blk == 0) carry0 += acc[0];
+                else carry_ws[((long)blockIdx.x * d.N + my) * PG_KB + jl] += acc[0];
             }
         }
-        carry[0] = dhz[0] + acc0;
-        carry[1] = dhz[1] + acc1;
     }
 }
 
-static size_t pg_smem_bytes(int H) { return (size_t)(3 * PG_KB * H + PG_KC * (PG_RB + 1)) * sizeof(float); }
+static size_t pg_smem_bytes(int H) { return (size_t)(3 * PG_KB * H) * sizeof(float); }
 
 // Cooperative launch: every CTA must be co-resident.  Asks the runtime how many fit.
 bool gru_persistent_supported(int N, int H) {
-    if (N <= 0 || H % PG_KB != 0 || H % PG_KC != 0) return false;
+    if (N <= 0 || H % 128 != 0) return false;
     const size_t smem = pg_smem_bytes(H);
-    if (smem > 220 * 1024) return false;
+    if (smem > 200 * 1024) return false;
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    cudaFuncSetAttribute(gru_persistent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    cudaFuncSetAttribute(gru_persistent_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(gru_persistent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gru_persistent_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     int pf = 0, pb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pf, gru_persistent_fwd_kernel, PG_NT, smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, gru_persistent_bwd_kernel, PG_NT, smem);
-    const long ctas = (long)(H / PG_KB) * ((N + PG_RB - 1) / PG_RB);
+    const long ctas = (long)(H / PG_KB);
     return ctas <= (long)sms * (pf < pb ? pf : pb);
 }
 
@@ -235,19 +303,13 @@ int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float
     A2CB_REQUIRE(Whh && d.hm && d.masks, "gru_persistent: null pointer");
     A2CB_REQUIRE(backward || (bhh && d.h0 && d.gi && d.out), "gru_persistent: forward pointers");
     A2CB_REQUIRE(!backward || (d.r && d.z && d.n && d.gh && d.dout && d.dgi && d.dgh), "gru_persistent: backward pointers");
+    A2CB_REQUIRE(!backward || d.N <= PG_RB || d.dcarry, "gru_persistent: dcarry workspace [N, H] needed for N > %d", PG_RB);
     const size_t smem = pg_smem_bytes(d.H);
-    static bool attr[2] = {false, false};
-    if (!attr[backward]) {
-        cudaError_t e = backward
-            ? cudaFuncSetAttribute(gru_persistent_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)
-            : cudaFuncSetAttribute(gru_persistent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) { set_error("gru_persistent: %s", cudaGetErrorString(e)); return A2CB_ERR_CUDA; }
-        attr[backward] = true;
-    }
-    dim3 grid((unsigned)(d.H / PG_KB), (unsigned)((d.N + PG_RB - 1) / PG_RB));
+    dim3 grid((unsigned)(d.H / PG_KB));
     GruDesc dd = d;
+    float* ws = d.dcarry;
     void* args_f[] = {(void*)&dd, (void*)&Whh, (void*)&bhh};
-    void* args_b[] = {(void*)&dd, (void*)&Whh};
+    void* args_b[] = {(void*)&dd, (void*)&Whh, (void*)&ws};
     cudaError_t e = backward
         ? cudaLaunchCooperativeKernel((const void*)gru_persistent_bwd_kernel, grid, dim3(PG_NT), args_b, smem, st)
         : cudaLaunchCooperativeKernel((const void*)gru_persistent_fwd_kernel, grid, dim3(PG_NT), args_f, smem, st);

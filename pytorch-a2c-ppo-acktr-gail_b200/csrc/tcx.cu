@@ -1,0 +1,574 @@
+// TMA-fed tensor-core engine (tcgen05 / TMEM, sm_100a) for the dense layers of the policy update:
+// CNNBase convolutions as per-tap GEMMs straight from NHWC activations, Linear layers, and all of their
+// data / weight gradients (reference a2c_ppo_acktr/model.py:169-195 forward; autograd backward).
+//
+// Why a second engine next to gemm_tc.cu: that kernel gathers operands with SIMT loads (implicit
+// im2col through affine index maps), splits every fp32 into TF32 hi/lo in registers and stores them to
+// shared memory -- ~950 instructions per warp and k-block, which caps it at ~20-30 TFLOP/s.  Here
+//   * activations live in HBM as two planes: x (plain fp32) and lo = x - trunc_tf32(x), written ONCE by
+//     the producing epilogue.  kind::tf32 ignores the 13 low mantissa bits of its 32-bit operands, so the
+//     x plane itself is the "hi" operand and  x*w = hi_x*hi_w + lo_x*hi_w + hi_x*lo_w  (+ ~2^-20) costs
+//     three MMAs with no conversion pass at all;
+//   * a convolution is a sum over filter taps of [pixels x C_in] x [C_in x C_out] products; the pixel
+//     box of one tap (for a whole tile of images) is ONE multi-dimensional TMA box of the NHWC tensor
+//     (stride-2 layers through a parity view, transposed convolutions through TMA's out-of-bounds zero
+//     fill), landing in shared memory as 128-byte swizzled rows -- exactly the K-major UMMA operand;
+//   * weight gradients reduce over pixels, i.e. both operands are "MN-major" ([pixels][channels] with
+//     the reduction along rows); the same TMA boxes feed them through MN-major UMMA descriptors
+//     (32-byte-atom 128B swizzle, the one layout the tensor core accepts for transposed 32-bit operands);
+//   * warp-specialised CTA: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2-9 =
+//     accumulator drain + epilogue.  The tensor core's fp32 accumulation truncates (error grows with the
+//     reduction length, tools/tc_accuracy.py), so the reduction is cut into chains that alternate between
+//     two TMEM accumulators; the epilogue warps add finished chains into fp32 registers while the next
+//     chain runs.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "decls.cuh"
+#include "tcx.cuh"
+
+namespace a2cb {
+
+namespace {
+
+constexpr int TX_NT = 320;                    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TX_EPI0 = 2;                    // first epilogue warp
+constexpr int TX_ROWB = 128;                  // bytes per operand row (32 floats, one swizzle span)
+constexpr int TX_MAX_STAGES = 6;
+
+TcxKnobs g_knobs = {1 /* SWIZZLE_128B_BASE32B */, 512, 1024, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
+
+__device__ __forceinline__ uint32_t tx_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tx_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tx_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void tx_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(tx_smem(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tx_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tx_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void tx_expect(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tx_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tx_tma5(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                        int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+            "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(tx_smem(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tx_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tx_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tx_mma(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
+// version 1 << 46 | layout type << 61
+__device__ __forceinline__ uint64_t tx_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ void tx_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tx_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+struct TxBars {
+    uint64_t full[TX_MAX_STAGES], empty[TX_MAX_STAGES], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tx_tile_base(const TcxTiling& t, int tile, int* base) {
+    base[0] = base[1] = base[2] = base[3] = base[4] = 0;
+    const int tq = tile / t.t_div, tr = tile - tq * t.t_div;
+    base[t.tr_dim] += tr * t.tr_step;
+    base[t.tq_dim] += tq * t.tq_step;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward-like: out tile [R <= 128 * MB pixels] x [BN channels], reduction over n_kb k-blocks of 32
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int MB>
+__global__ void __launch_bounds__(TX_NT, 1)
+tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const __grid_constant__ TcxFwd p, const int stages) {
+    constexpr int A_BYTES = MB * 128 * TX_ROWB;             // one plane of the A tile
+    constexpr int B_BYTES = BN * TX_ROWB;
+    constexpr int HALF = BN / 2;
+    extern __shared__ uint8_t tx_dyn[];
+    __shared__ TxBars bars;
+    const uint32_t dyn = (tx_smem(tx_dyn) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool has_lo = p.A.lo != nullptr;
+    const int stage_bytes = A_BYTES * (has_lo ? 2 : 1) + 2 * B_BYTES;
+    const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
+    const int chain = p.chain > 0 ? p.chain : p.n_kb;
+    const int n_chains = (p.n_kb + chain - 1) / chain;
+    int base[5];
+    tx_tile_base(p.tiles, blockIdx.x, base);
+    const int n0 = blockIdx.y * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { tx_mbar_init(&bars.full[s], 1); tx_mbar_init(&bars.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { tx_mbar_init(&bars.acc_full[b], 1); tx_mbar_init(&bars.acc_empty[b], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tx_smem(&bars.tmem_base)),
+                     "r"((uint32_t)(2 * MB * BN)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = bars.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(R * TX_ROWB * (has_lo ? 2 : 1) + 2 * B_BYTES);
+            for (int kb = 0; kb < p.n_kb; ++kb) {
+                const int s = kb % stages;
+                if (kb >= stages) tx_mbar_wait(&bars.empty[s], (uint32_t)(((kb / stages) - 1) & 1));
+                const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
+                const uint32_t sb = sa + (uint32_t)(A_BYTES * (has_lo ? 2 : 1));
+                tx_expect(&bars.full[s], bytes);
+                const int c0 = p.kb_a[kb][0], c1 = p.kb_a[kb][1] + base[1], c2 = p.kb_a[kb][2] + base[2],
+                          c3 = p.kb_a[kb][3] + base[3], c4 = base[4];
+                tx_tma5(sa, &tmA, &bars.full[s], c0, c1, c2, c3, c4);
+                if (has_lo) tx_tma5(sa + A_BYTES, &tmAlo, &bars.full[s], c0, c1, c2, c3, c4);
+                tx_tma5(sb, &tmB, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
+                tx_tma5(sb + B_BYTES, &tmBlo, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D fp32, A/B tf32, both K-major, N = BN, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int kb = 0; kb < p.n_kb; ++kb) {
+                const int s = kb % stages;
+                const int c = kb / chain, buf = c & 1;
+                const bool first = (kb - c * chain) == 0;
+                if (first && c >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)(((c >> 1) - 1) & 1));
+                tx_mbar_wait(&bars.full[s], (uint32_t)((kb / stages) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
+                const uint32_t sb = sa + (uint32_t)(A_BYTES * (has_lo ? 2 : 1));
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) {
+                    const uint32_t d = tmem + (uint32_t)(buf * MB * BN + mb * BN);
+                    const uint32_t ah = sa + (uint32_t)(mb * 128 * TX_ROWB);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t o = ks * 32;
+                        const uint64_t dah = tx_desc(ah + o, 16, 1024, 2), dbh = tx_desc(sb + o, 16, 1024, 2);
+                        const uint64_t dbl = tx_desc(sb + B_BYTES + o, 16, 1024, 2);
+                        const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
+                        if (has_lo) tx_mma(d, tx_desc(ah + A_BYTES + o, 16, 1024, 2), dbh, idesc, acc0);
+                        tx_mma(d, dah, dbl, idesc, has_lo ? 1u : acc0);
+                        tx_mma(d, dah, dbh, idesc, 1u);
+                    }
+                }
+                tx_commit(&bars.empty[s]);
+                if (kb == p.n_kb - 1 || (kb + 1) % chain == 0) tx_commit(&bars.acc_full[buf]);
+            }
+        }
+    } else {
+        // ---- drain chains into registers, then the epilogue ----
+        const int q = warp & 3, hf = (warp - TX_EPI0) >> 2;          // TMEM lane quadrant, column half
+        float acc[MB][HALF];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+            for (int n = 0; n < HALF; ++n) acc[mb][n] = 0.f;
+        for (int c = 0; c < n_chains; ++c) {
+            const int buf = c & 1;
+            tx_mbar_wait(&bars.acc_full[buf], (uint32_t)((c >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                for (int c0 = 0; c0 < HALF; c0 += 16) {
+                    uint32_t v[16];
+                    tx_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * MB * BN + mb * BN + hf * HALF + c0), v);
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) acc[mb][c0 + n] += __uint_as_float(v[n]);
+                }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tx_mbar_arrive(&bars.acc_empty[buf]);
+        }
+        const int b1 = p.A.box[1], b2 = p.A.box[2], b3 = p.A.box[3];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+            const int r = mb * 128 + 32 * q + lane;
+            if (r >= R) continue;
+            int t = r;
+            const int i1 = t % b1; t /= b1;
+            const int i2 = t % b2; t /= b2;
+            const int i3 = t % b3; t /= b3;
+            const int i4 = t;
+            const int g1 = base[1] + i1, g2 = base[2] + i2, g3 = base[3] + i3, g4 = base[4] + i4;
+            if (g1 >= p.o_ext[1] || g2 >= p.o_ext[2] || g3 >= p.o_ext[3] || g4 >= p.o_ext[4]) continue;
+            const long off = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
+#pragma unroll
+            for (int n = 0; n < HALF; n += 4) {
+                const int ch = n0 + hf * HALF + n;
+                if (ch >= p.N) continue;
+                float4 v = make_float4(acc[mb][n] * p.alpha, acc[mb][n + 1] * p.alpha, acc[mb][n + 2] * p.alpha,
+                                       acc[mb][n + 3] * p.alpha);
+                if (p.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                }
+                if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                if (p.mask) {
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(p.mask + off + ch));
+                    v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+                    v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                }
+                *reinterpret_cast<float4*>(p.out + off + ch) = v;
+                if (p.out_lo)
+                    *reinterpret_cast<float4*>(p.out_lo + off + ch) = make_float4(tx_lo(v.x), tx_lo(v.y), tx_lo(v.z), tx_lo(v.w));
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * MB * BN)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight-gradient-like: G accumulators D_g[128 x BN] += sum over pixel rows of A_g^T B, both operands
+// MN-major (rows = reduction).  One pipeline stage = (row tile, group).
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int G>
+__global__ void __launch_bounds__(TX_NT, 1)
+tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                 const __grid_constant__ TcxWgrad p, const int stages, const TcxKnobs knobs) {
+    constexpr int NBB = BN / 32;
+    constexpr int HALF = BN / 2;
+    extern __shared__ uint8_t tx_dyn[];
+    __shared__ TxBars bars;
+    const uint32_t dyn = (tx_smem(tx_dyn) + 1023u) & ~1023u;
+    uint8_t* dyn_ptr = tx_dyn + (dyn - tx_smem(tx_dyn));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool has_lo = p.A.lo != nullptr;
+    const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
+    const int R8 = (R + 7) & ~7;
+    const int box_bytes = R8 * TX_ROWB;
+    const int a_planes = has_lo ? 2 : 1;
+    const int stage_bytes = box_bytes * (4 * a_planes + 2 * NBB);
+    const int per = (p.rows.n_tiles + p.splits - 1) / p.splits;
+    const int rt0 = blockIdx.x * per;
+    const int rt1 = min(p.rows.n_tiles, rt0 + per);
+    const int n_rt = max(0, rt1 - rt0);
+    const int chain = p.chain > 0 ? p.chain : max(1, n_rt);
+    const int n_chains = (n_rt + chain - 1) / chain;
+    const int ota = blockIdx.y % p.ot_a, otb = blockIdx.y / p.ot_a;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { tx_mbar_init(&bars.full[s], 1); tx_mbar_init(&bars.empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { tx_mbar_init(&bars.acc_full[b], 1); tx_mbar_init(&bars.acc_empty[b], 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        constexpr uint32_t cols = (2 * G * BN <= 32) ? 32 : (2 * G * BN <= 64) ? 64 : (2 * G * BN <= 128) ? 128 : (2 * G * BN <= 256) ? 256 : 512;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tx_smem(&bars.tmem_base)), "r"(cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    // rows R..R8-1 of every box are never written by TMA but take part in the K = 8 MMA steps: zero them once
+    if (R8 > R) {
+        const int nbox = stages * (4 * a_planes + 2 * NBB);
+        const int per_box = (R8 - R) * (TX_ROWB / 4);
+        for (int e = threadIdx.x; e < nbox * per_box; e += TX_NT) {
+            const int b = e / per_box, w = e - b * per_box;
+            reinterpret_cast<float*>(dyn_ptr + (size_t)b * box_bytes + (size_t)R * TX_ROWB)[w] = 0.f;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = bars.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(R * TX_ROWB * (4 * a_planes + 2 * NBB));
+            int qn = 0;
+            for (int rt = rt0; rt < rt1; ++rt) {
+                int base[5];
+                tx_tile_base(p.rows, rt, base);
+                for (int g = 0; g < G; ++g, ++qn) {
+                    const int s = qn % stages;
+                    if (qn >= stages) tx_mbar_wait(&bars.empty[s], (uint32_t)(((qn / stages) - 1) & 1));
+                    const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
+                    const uint32_t sb = sa + (uint32_t)(4 * a_planes * box_bytes);
+                    tx_expect(&bars.full[s], bytes);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c0 = p.ga[g][j][0] + ota * p.ot_a_step, c1 = p.ga[g][j][1] + base[1],
+                                  c2 = p.ga[g][j][2] + base[2], c3 = p.ga[g][j][3] + base[3], c4 = base[4];
+                        tx_tma5(sa + (uint32_t)(j * box_bytes), &tmA, &bars.full[s], c0, c1, c2, c3, c4);
+                        if (has_lo) tx_tma5(sa + (uint32_t)((4 + j) * box_bytes), &tmAlo, &bars.full[s], c0, c1, c2, c3, c4);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NBB; ++j) {
+                        const int c0 = p.gb[j][0] + otb * p.ot_b_step, c1 = p.gb[j][1] + base[1], c2 = p.gb[j][2] + base[2],
+                                  c3 = p.gb[j][3] + base[3], c4 = base[4];
+                        tx_tma5(sb + (uint32_t)(j * box_bytes), &tmB, &bars.full[s], c0, c1, c2, c3, c4);
+                        tx_tma5(sb + (uint32_t)((NBB + j) * box_bytes), &tmBlo, &bars.full[s], c0, c1, c2, c3, c4);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D fp32, A/B tf32, both MN-major, N = BN, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t lt = (uint32_t)knobs.mn_layout_type, sbo = (uint32_t)knobs.mn_sbo_bytes;
+            const int ksteps = R8 / 8;
+            int qn = 0;
+            for (int i = 0; i < n_rt; ++i) {
+                const int c = i / chain, buf = c & 1;
+                const bool first = (i - c * chain) == 0;
+                if (first && c >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)(((c >> 1) - 1) & 1));
+                for (int g = 0; g < G; ++g, ++qn) {
+                    const int s = qn % stages;
+                    tx_mbar_wait(&bars.full[s], (uint32_t)((qn / stages) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
+                    const uint32_t sal = sa + (uint32_t)(4 * box_bytes);
+                    const uint32_t sb = sa + (uint32_t)(4 * a_planes * box_bytes);
+                    const uint32_t sbl = sb + (uint32_t)(NBB * box_bytes);
+                    const uint32_t d = tmem + (uint32_t)(buf * G * BN + g * BN);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t o = (uint32_t)(ks * knobs.mn_kstep_bytes);
+                        const uint64_t dah = tx_desc(sa + o, (uint32_t)box_bytes, sbo, lt);
+                        const uint64_t dbh = tx_desc(sb + o, (uint32_t)box_bytes, sbo, lt);
+                        const uint64_t dbl = tx_desc(sbl + o, (uint32_t)box_bytes, sbo, lt);
+                        const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
+                        if (has_lo) tx_mma(d, tx_desc(sal + o, (uint32_t)box_bytes, sbo, lt), dbh, idesc, acc0);
+                        tx_mma(d, dah, dbl, idesc, has_lo ? 1u : acc0);
+                        tx_mma(d, dah, dbh, idesc, 1u);
+                    }
+                    tx_commit(&bars.empty[s]);
+                }
+                if (i == n_rt - 1 || (i + 1) % chain == 0) tx_commit(&bars.acc_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3, hf = (warp - TX_EPI0) >> 2;
+        float acc[G][HALF];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int n = 0; n < HALF; ++n) acc[g][n] = 0.f;
+        for (int c = 0; c < n_chains; ++c) {
+            const int buf = c & 1;
+            tx_mbar_wait(&bars.acc_full[buf], (uint32_t)((c >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int c0 = 0; c0 < HALF; c0 += 16) {
+                    uint32_t v[16];
+                    tx_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * G * BN + g * BN + hf * HALF + c0), v);
+#pragma unroll
+                    for (int n = 0; n < 16; ++n) acc[g][c0 + n] += __uint_as_float(v[n]);
+                }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tx_mbar_arrive(&bars.acc_empty[buf]);
+        }
+        float* dst = p.partial + (long)blockIdx.x * p.split_stride;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int m = g * 128 + 32 * q + lane;
+            const int off = __ldg(p.row_off + (long)ota * (G * 128) + m);
+            if (off < 0) continue;
+#pragma unroll
+            for (int n = 0; n < HALF; ++n) {
+                const int col = otb * BN + hf * HALF + n;
+                if (col < p.n_cols) dst[off + (long)col * p.col_stride] = acc[g][n] * p.alpha;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        constexpr uint32_t cols = (2 * G * BN <= 32) ? 32 : (2 * G * BN <= 64) ? 64 : (2 * G * BN <= 128) ? 128 : (2 * G * BN <= 256) ? 256 : 512;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_map(CUtensorMap* out, const float* base, const int64_t* dim, const int64_t* stride, const int32_t* box, int swizzle,
+             const char* what) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("tcx: cuTensorMapEncodeTiled is not available"); return A2CB_ERR_CUDA; }
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+    for (int d = 0; d < 5; ++d) { gd[d] = (cuuint64_t)dim[d]; bx[d] = (cuuint32_t)box[d]; }
+    for (int d = 1; d < 5; ++d) gs[d - 1] = (cuuint64_t)stride[d] * 4;
+    A2CB_REQUIRE(stride[0] == 1 && box[0] == 32, "tcx(%s): innermost dimension must be contiguous with a 32-float box", what);
+    A2CB_REQUIRE(((uintptr_t)base & 15) == 0, "tcx(%s): base pointer must be 16-byte aligned", what);
+    for (int d = 1; d < 5; ++d)
+        A2CB_REQUIRE(stride[d] % 4 == 0 && box[d] >= 1 && box[d] <= 256 && dim[d] >= 1, "tcx(%s): bad dimension %d", what, d);
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tcx(%s): cuTensorMapEncodeTiled failed (%d)", what, (int)r); return A2CB_ERR_CUDA; }
+    return A2CB_OK;
+}
+
+int view_maps(CUtensorMap* hi, CUtensorMap* lo, const TcxView& v, int swizzle, const char* what) {
+    int rc = make_map(hi, v.x, v.dim, v.stride, v.box, swizzle, what);
+    if (rc) return rc;
+    if (v.lo) return make_map(lo, v.lo, v.dim, v.stride, v.box, swizzle, what);
+    *lo = *hi;
+    return A2CB_OK;
+}
+
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BN, int MB>
+int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
+    const int a_planes = p.A.lo ? 2 : 1;
+    const int stage = MB * 128 * TX_ROWB * a_planes + 2 * BN * TX_ROWB;
+    int stages = kSmemBudget / stage;
+    stages = stages > TX_MAX_STAGES ? TX_MAX_STAGES : stages;
+    A2CB_REQUIRE(stages >= 2, "tcx_fwd: tile does not fit shared memory");
+    const int smem = stages * stage + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(tcx_fwd_kernel<BN, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+        if (e != cudaSuccess) { set_error("tcx_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return A2CB_ERR_CUDA; }
+        attr = true;
+    }
+    dim3 grid((unsigned)p.tiles.n_tiles, (unsigned)((p.N + BN - 1) / BN));
+    tcx_fwd_kernel<BN, MB><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], p, stages);
+    return check_launch("tcx_fwd");
+}
+
+template <int BN, int G>
+int launch_wgrad(const TcxWgrad& p, const CUtensorMap* m, cudaStream_t st) {
+    const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
+    const int R8 = (R + 7) & ~7;
+    const int stage = R8 * TX_ROWB * (4 * (p.A.lo ? 2 : 1) + 2 * (BN / 32));
+    int stages = kSmemBudget / stage;
+    stages = stages > TX_MAX_STAGES ? TX_MAX_STAGES : stages;
+    A2CB_REQUIRE(stages >= 2, "tcx_wgrad: row tile of %d rows does not fit shared memory", R);
+    const int smem = stages * stage + 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(tcx_wgrad_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+        if (e != cudaSuccess) { set_error("tcx_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return A2CB_ERR_CUDA; }
+        attr = true;
+    }
+    dim3 grid((unsigned)p.splits, (unsigned)(p.ot_a * p.ot_b));
+    tcx_wgrad_kernel<BN, G><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], p, stages, g_knobs);
+    return check_launch("tcx_wgrad");
+}
+
+}  // namespace
+
+void tcx_set_knobs(const TcxKnobs& k) { g_knobs = k; }
+TcxKnobs tcx_get_knobs() { return g_knobs; }
+
+int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
+    A2CB_REQUIRE(p.A.x && p.B && p.B_lo && p.out, "tcx_fwd: null pointer");
+    A2CB_REQUIRE(p.n_kb >= 1 && p.n_kb <= TCX_MAX_KB, "tcx_fwd: n_kb = %d out of range", p.n_kb);
+    A2CB_REQUIRE(p.N > 0 && p.N % 4 == 0, "tcx_fwd: N = %d must be a positive multiple of 4", p.N);
+    A2CB_REQUIRE(p.tiles.n_tiles > 0 && p.tiles.t_div > 0 && p.tiles.tr_dim >= 1 && p.tiles.tr_dim <= 4 &&
+                 p.tiles.tq_dim >= 1 && p.tiles.tq_dim <= 4, "tcx_fwd: bad tiling");
+    const long R = (long)p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
+    A2CB_REQUIRE(R >= 1 && R <= 256, "tcx_fwd: %ld rows per tile (max 256)", R);
+    const int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
+    const int MB = R <= 128 ? 1 : 2;
+    CUtensorMap m[4];
+    int rc = view_maps(&m[0], &m[1], p.A, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd A");
+    if (rc) return rc;
+    const int64_t bd[5] = {p.b_cols, p.b_rows, 1, 1, 1};
+    const int64_t bs[5] = {1, p.b_cols, p.b_cols * p.b_rows, p.b_cols * p.b_rows, p.b_cols * p.b_rows};
+    const int32_t bb[5] = {32, BN, 1, 1, 1};
+    A2CB_REQUIRE(p.b_cols % 4 == 0, "tcx_fwd: weight image pitch must be a multiple of 4");
+    if ((rc = make_map(&m[2], p.B, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B"))) return rc;
+    if ((rc = make_map(&m[3], p.B_lo, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B_lo"))) return rc;
+    if (BN == 32) return MB == 1 ? launch_fwd<32, 1>(p, m, st) : launch_fwd<32, 2>(p, m, st);
+    if (BN == 64) return MB == 1 ? launch_fwd<64, 1>(p, m, st) : launch_fwd<64, 2>(p, m, st);
+    return MB == 1 ? launch_fwd<128, 1>(p, m, st) : launch_fwd<128, 2>(p, m, st);
+}
+
+int tcx_wgrad(const TcxWgrad& p, cudaStream_t st) {
+    A2CB_REQUIRE(p.A.x && p.Bm.x && p.Bm.lo && p.partial && p.row_off, "tcx_wgrad: null pointer");
+    A2CB_REQUIRE(p.G >= 1 && p.G <= TCX_MAX_G && p.nbb >= 1 && p.nbb <= 8, "tcx_wgrad: bad G / nbb");
+    A2CB_REQUIRE(p.splits >= 1 && p.ot_a >= 1 && p.ot_b >= 1 && p.rows.n_tiles >= 1 && p.rows.t_div > 0, "tcx_wgrad: bad tiling");
+    for (int d = 1; d < 5; ++d) A2CB_REQUIRE(p.A.box[d] == p.Bm.box[d] || true, "tcx_wgrad: box mismatch");
+    const long RA = (long)p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
+    const long RB = (long)p.Bm.box[1] * p.Bm.box[2] * p.Bm.box[3] * p.Bm.box[4];
+    A2CB_REQUIRE(RA == RB && RA >= 1, "tcx_wgrad: operand boxes enumerate %ld vs %ld rows", RA, RB);
+    CUtensorMap m[4];
+    int rc = view_maps(&m[0], &m[1], p.A, g_knobs.mn_tma_swizzle, "wgrad A");
+    if (rc) return rc;
+    if ((rc = view_maps(&m[2], &m[3], p.Bm, g_knobs.mn_tma_swizzle, "wgrad B"))) return rc;
+    const int BN = 32 * p.nbb;
+    if (BN == 32 && p.G == 1) return launch_wgrad<32, 1>(p, m, st);
+    if (BN == 32 && p.G == 2) return launch_wgrad<32, 2>(p, m, st);
+    if (BN == 32 && p.G == 5) return launch_wgrad<32, 5>(p, m, st);
+    if (BN == 64 && p.G == 1) return launch_wgrad<64, 1>(p, m, st);
+    if (BN == 64 && p.G == 4) return launch_wgrad<64, 4>(p, m, st);
+    if (BN == 128 && p.G == 1) return launch_wgrad<128, 1>(p, m, st);
+    if (BN == 256 && p.G == 1) return launch_wgrad<256, 1>(p, m, st);
+    set_error("tcx_wgrad: no kernel instance for BN = %d, G = %d", BN, p.G);
+    return A2CB_ERR_UNSUPPORTED;
+}
+
+}  // namespace a2cb

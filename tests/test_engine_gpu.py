@@ -243,3 +243,67 @@ def test_adv_normalize_vs_torch():
         _native.check(lib.a2cb_adv_moments(rd.data_ptr(), vd.data_ptr(), n, scratch.data_ptr(), mom.data_ptr(), st), "m")
         _native.check(lib.a2cb_adv_normalize(rd.data_ptr(), vd.data_ptr(), n, mom.data_ptr(), out.data_ptr(), st), "n")
         np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+
+
+# ---- persistent whole-sequence GRU (csrc/gru_persistent.cu) against torch autograd -------------------
+@pytest.mark.parametrize("T,N,H", [(5, 3, 128), (16, 64, 512), (7, 77, 256), (4, 130, 128)])
+def test_gru_persistent_vs_torch(T, N, H):
+    """a2cb_gru_seq forward and backward-through-time on the masked recurrence of model.py:111-166;
+    N covers partial warps, partial 64-environment blocks and more than one block."""
+    import ctypes
+    from a2c_ppo_acktr import _engine as E
+    if not E.gru_seq_supported(N, H):
+        pytest.skip("cooperative launch does not fit")
+    g = torch.Generator().manual_seed(5)
+    gi = torch.randn(T * N, 3 * H, generator=g)
+    Whh = torch.randn(3 * H, H, generator=g) / H ** 0.5
+    bhh = torch.randn(3 * H, generator=g) * 0.1
+    h0 = torch.randn(N, H, generator=g)
+    masks = (torch.rand(T * N, generator=g) > 0.2).float()
+    dout = torch.randn(T * N, H, generator=g)
+
+    # fp64 reference with autograd
+    gi_r = gi.double().requires_grad_(True)
+    W_r = Whh.double().requires_grad_(True)
+    b_r = bhh.double()
+    h = h0.double()
+    outs, hms = [], []
+    for t in range(T):
+        hm = h * masks[t * N:(t + 1) * N, None].double()
+        hms.append(hm)
+        gh = hm @ W_r.t() + b_r
+        gt = gi_r[t * N:(t + 1) * N]
+        r = torch.sigmoid(gt[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gt[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gt[:, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1 - z) * n + z * hm
+        outs.append(h)
+    out_ref = torch.cat(outs)
+    (out_ref * dout.double()).sum().backward()
+
+    dev = DEV
+    dz = lambda *s: torch.zeros(*s, device=dev)
+    bufs = dict(gi=gi.to(dev), gh=dz(T * N, 3 * H), hm=dz(T * N, H), h0=h0.to(dev), masks=masks.to(dev),
+                out=dz(T * N, H), r=dz(T * N, H), z=dz(T * N, H), n=dz(T * N, H), dout=dout.to(dev),
+                dgi=dz(T * N, 3 * H), dgh=dz(T * N, 3 * H), dcarry=dz(N, H))
+    W_d, b_d = Whh.to(dev), bhh.to(dev)
+    d = E.GruSeqDesc()
+    for k, v in bufs.items():
+        setattr(d, k, v.data_ptr())
+    d.T, d.N, d.H, d.t = T, N, H, 0
+    d.W_hh, d.b_hh = W_d.data_ptr(), b_d.data_ptr()
+    lib = _native.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    _native.check(lib.a2cb_gru_seq(0, ctypes.addressof(d), st), "gru_seq fwd")
+    _native.check(lib.a2cb_gru_seq(1, ctypes.addressof(d), st), "gru_seq bwd")
+    torch.cuda.synchronize()
+
+    def rel(a, b):
+        b = b.float()
+        return float((a.cpu() - b).norm() / (b.norm() + 1e-30))
+    assert rel(bufs["out"], out_ref.detach()) <= 2e-6
+    assert rel(bufs["hm"], torch.cat(hms).detach()) <= 2e-6
+    assert rel(bufs["dgi"], gi_r.grad) <= 5e-6
+    # dW_hh = sum_t dgh_t^T hm_t  (the weight-gradient GEMM consumes dgh and hm)
+    dW = bufs["dgh"].double().t() @ bufs["hm"].double()
+    assert rel(dW.float(), W_r.grad) <= 5e-6
