@@ -241,6 +241,12 @@ int a2cb_tcx_s2d(float* out, float* out_lo, const void* frames, int32_t src_is_u
  * partials, folded by a2cb_reduce_splits: bias gradients */
 int a2cb_tcx_colsum(float* part, const float* x, int64_t rows, int32_t C, int64_t pitch, a2cb_stream_t stream);
 int a2cb_tcx_colsum_blocks(int64_t rows);
+/* Weight + bias gradient of a narrow Linear layer (policy / value heads, distributions.py:69-72, model.py:185;
+ * N <= 8 outputs): part[blk][n K + k] = sum_rows gy[row gy_stride + n] x[row K + k], part[blk][N K + n] = sum_rows gy;
+ * a2cb_tcx_narrow_wgrad_blocks(rows) partial slabs of N K + N floats, folded by a2cb_reduce_splits. */
+int a2cb_tcx_narrow_wgrad(float* part, const float* x, const float* gy, int64_t rows, int32_t K, int32_t N,
+                          int32_t gy_stride, a2cb_stream_t stream);
+int a2cb_tcx_narrow_wgrad_blocks(int64_t rows);
 /* sizeof of a2cb_tcx_fwd_t (0), a2cb_tcx_wgrad_t (1), a2cb_tcx_view_t (2) as compiled: lets a binding check its mirror */
 int a2cb_tcx_sizeof(int32_t which);
 /* hardware-semantics knobs of the MN-major (weight-gradient) path, for probing: UMMA layout type, stride
@@ -345,6 +351,7 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_TCX_PREP 17
 #define A2CB_OP_TCX_S2D 18
 #define A2CB_OP_TCX_COLSUM 19
+#define A2CB_OP_TCX_NARROW_WGRAD 20
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -363,6 +370,7 @@ typedef struct { float* lo; const float* x; int64_t n; } a2cb_tcx_lo_t;
 typedef struct { float* img; float* img_lo; const float* src; int64_t N, K; const int32_t* ntab; const int32_t* ktab; } a2cb_tcx_prep_t;
 typedef struct { float* out; float* out_lo; const void* frames; const int64_t* idx; int32_t src_is_u8, B, C, H, W, S; } a2cb_tcx_s2d_t;
 typedef struct { float* part; const float* x; int64_t rows; int64_t pitch; int32_t C; int32_t pad_; } a2cb_tcx_colsum_t;
+typedef struct { float* part; const float* x; const float* gy; int64_t rows; int32_t K, N, gy_stride, pad_; } a2cb_tcx_narrow_wgrad_t;
 typedef struct { int32_t kind; int32_t flags; const void* desc; } a2cb_op_t;
 
 int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream);

@@ -637,7 +637,12 @@ class NetBuilder(object):
         dz = self.buf("dz", B * self.zs)
         gh = self.buf("gh", B * H)
         gw, gb = self.gwb("heads")
-        return [P.linear_wgrad(self.heads, B, h, dz, gw, gb),
+        if self.tcx is not None and self.zs <= 8:
+            # [1 + A, H] weight gradient + bias gradient (contiguous in the flat layout): one streaming pass
+            wg = _tcx.narrow_wgrad_ops(self, "heads", h, dz, B, H, self.zs, self.zs, gw)
+        else:
+            wg = [P.linear_wgrad(self.heads, B, h, dz, gw, gb)]
+        return wg + [
                 P.linear_dgrad(self.heads, B, dz, ("P", self.L.layers["heads"][0]), gh,
                                mask=h if relu_mask else None, mask_mode=1 if relu_mask else 0)], gh
 

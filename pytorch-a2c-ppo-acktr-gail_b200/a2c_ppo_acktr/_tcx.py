@@ -52,7 +52,14 @@ class ColsumDesc(ctypes.Structure):
     _fields_ = [("part", c_vp), ("x", c_vp), ("rows", c_i64), ("pitch", c_i64), ("C", c_i32), ("pad_", c_i32)]
 
 
+class NarrowWgradDesc(ctypes.Structure):
+    _fields_ = [("part", c_vp), ("x", c_vp), ("gy", c_vp), ("rows", c_i64), ("K", c_i32), ("N", c_i32),
+                ("gy_stride", c_i32), ("pad_", c_i32)]
+
+
 _native.register({
+    "a2cb_tcx_narrow_wgrad": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
+    "a2cb_tcx_narrow_wgrad_blocks": (c_i32, [c_i64]),
     "a2cb_tcx_fwd": (c_i32, [ctypes.POINTER(FwdDesc), c_vp]),
     "a2cb_tcx_wgrad": (c_i32, [ctypes.POINTER(WgradDesc), c_vp]),
     "a2cb_tcx_lo_plane": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
@@ -92,6 +99,7 @@ def tiling(n_tiles, tr_dim, tr_step, t_div=None, tq_dim=4, tq_step=0):
 # build time, exactly like the GEMM plans of _plans.py)
 # ---------------------------------------------------------------------------------------------------
 OP_TCX_FWD, OP_TCX_WGRAD, OP_TCX_LO, OP_TCX_PREP, OP_TCX_S2D, OP_TCX_COLSUM = 14, 15, 16, 17, 18, 19
+OP_TCX_NARROW_WGRAD = 20
 
 
 class TcxOp(object):
@@ -184,7 +192,27 @@ def colsum_op(name, part, x, rows, C, pitch):
 
 def colsum_blocks(rows):
     # mirrors tcx_colsum_blocks (csrc/tcx_aux.cu)
-    return int(min((rows + 255) // 256, 148 * 2))
+    return int(min((rows + 127) // 128, 148 * 8))
+
+
+def narrow_wgrad_blocks(rows):
+    # mirrors tcx_narrow_wgrad_blocks (csrc/tcx_aux.cu)
+    return int(min((rows + 63) // 64, 148 * 4))
+
+
+def narrow_wgrad_ops(nb, name, x, gy, rows, K, N, gy_stride, dst):
+    """dW [N, K] and db [N] (contiguous at dst) of a narrow Linear layer: one streaming pass + one fold."""
+    from ._engine import RawOp, ReduceDesc, OP_REDUCE
+    blocks = narrow_wgrad_blocks(rows)
+    span = N * K + N
+    part = nb.buf("npart_" + name, blocks * span)
+
+    def make(arena):
+        return NarrowWgradDesc(arena.ptr(part), arena.ptr(x), arena.ptr(gy), rows, K, N, gy_stride, 0)
+    return [TcxOp(OP_TCX_NARROW_WGRAD, make, name + ".wgrad"),
+            RawOp(OP_REDUCE, {"dst": dst, "src": part},
+                  dict(count=span, stride=span, splits=blocks, accumulate=0, ncols=0, act=0, beta=1.0), False,
+                  name + ".fold", ReduceDesc)]
 
 
 def split_rows(n_rt, want_ctas):

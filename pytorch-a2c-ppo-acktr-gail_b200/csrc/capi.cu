@@ -174,6 +174,11 @@ int a2cb_tcx_s2d(float* out, float* out_lo, const void* frames, int32_t src_is_u
 int a2cb_tcx_colsum(float* part, const float* x, int64_t rows, int32_t C, int64_t pitch, a2cb_stream_t stream) {
     return tcx_colsum(part, x, (long)rows, C, (long)pitch, (cudaStream_t)stream);
 }
+int a2cb_tcx_narrow_wgrad(float* part, const float* x, const float* gy, int64_t rows, int32_t K, int32_t N,
+                          int32_t gy_stride, a2cb_stream_t stream) {
+    return tcx_narrow_wgrad(part, x, gy, (long)rows, K, N, gy_stride, (cudaStream_t)stream);
+}
+int a2cb_tcx_narrow_wgrad_blocks(int64_t rows) { return tcx_narrow_wgrad_blocks((long)rows); }
 int a2cb_tcx_sizeof(int32_t which) {
     return which == 0 ? (int)sizeof(TcxFwd) : which == 1 ? (int)sizeof(TcxWgrad) : (int)sizeof(TcxView);
 }
@@ -272,6 +277,11 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             case A2CB_OP_TCX_COLSUM: {
                 const a2cb_tcx_colsum_t& q = *reinterpret_cast<const a2cb_tcx_colsum_t*>(op.desc);
                 rc = tcx_colsum(q.part, q.x, (long)q.rows, q.C, (long)q.pitch, st);
+                break;
+            }
+            case A2CB_OP_TCX_NARROW_WGRAD: {
+                const a2cb_tcx_narrow_wgrad_t& q = *reinterpret_cast<const a2cb_tcx_narrow_wgrad_t*>(op.desc);
+                rc = tcx_narrow_wgrad(q.part, q.x, q.gy, (long)q.rows, q.K, q.N, q.gy_stride, st);
                 break;
             }
             case A2CB_OP_GRU_INIT:

@@ -73,5 +73,7 @@ int tcx_s2d(float* out, float* out_lo, const void* frames, int src_is_u8, const 
             int S, cudaStream_t st);
 int tcx_colsum(float* part, const float* x, long rows, int C, long pitch, cudaStream_t st);
 int tcx_colsum_blocks(long rows);
+int tcx_narrow_wgrad(float* part, const float* x, const float* gy, long rows, int K, int N, int gy_stride, cudaStream_t st);
+int tcx_narrow_wgrad_blocks(long rows);
 
 }  // namespace a2cb

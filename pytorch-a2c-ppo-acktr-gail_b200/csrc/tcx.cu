@@ -132,9 +132,11 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
     const int chain = p.chain > 0 ? p.chain : p.n_kb;
     const int n_chains = (p.n_kb + chain - 1) / chain;
-    int base[5];
-    tx_tile_base(p.tiles, blockIdx.x, base);
-    const int n0 = blockIdx.y * BN;
+    // persistent: work item w = tile_m * n_n + tile_n, strided over the grid.  The three roles walk the same
+    // sequence with running k-block / chain counters, so the epilogue of one tile overlaps the loads and MMAs
+    // of the next (the two TMEM accumulators double as the hand-over buffers).
+    const int n_n = (p.N + BN - 1) / BN;
+    const int n_work = p.tiles.n_tiles * n_n;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { tx_mbar_init(&bars.full[s], 1); tx_mbar_init(&bars.empty[s], 1); }
@@ -154,108 +156,124 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)(R * TX_ROWB * (has_lo ? 2 : 1) + 2 * B_BYTES);
-            for (int kb = 0; kb < p.n_kb; ++kb) {
-                const int s = kb % stages;
-                if (kb >= stages) tx_mbar_wait(&bars.empty[s], (uint32_t)(((kb / stages) - 1) & 1));
-                const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
-                const uint32_t sb = sa + (uint32_t)(A_BYTES * (has_lo ? 2 : 1));
-                tx_expect(&bars.full[s], bytes);
-                const int c0 = p.kb_a[kb][0], c1 = p.kb_a[kb][1] + base[1], c2 = p.kb_a[kb][2] + base[2],
-                          c3 = p.kb_a[kb][3] + base[3], c4 = base[4];
-                tx_tma5(sa, &tmA, &bars.full[s], c0, c1, c2, c3, c4);
-                if (has_lo) tx_tma5(sa + A_BYTES, &tmAlo, &bars.full[s], c0, c1, c2, c3, c4);
-                tx_tma5(sb, &tmB, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
-                tx_tma5(sb + B_BYTES, &tmBlo, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
+            int it = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                int base[5];
+                tx_tile_base(p.tiles, w / n_n, base);
+                const int n0 = (w % n_n) * BN;
+                for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
+                    const int s = it % stages;
+                    if (it >= stages) tx_mbar_wait(&bars.empty[s], (uint32_t)(((it / stages) - 1) & 1));
+                    const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
+                    const uint32_t sb = sa + (uint32_t)(A_BYTES * (has_lo ? 2 : 1));
+                    tx_expect(&bars.full[s], bytes);
+                    const int c0 = p.kb_a[kb][0], c1 = p.kb_a[kb][1] + base[1], c2 = p.kb_a[kb][2] + base[2],
+                              c3 = p.kb_a[kb][3] + base[3], c4 = base[4];
+                    tx_tma5(sa, &tmA, &bars.full[s], c0, c1, c2, c3, c4);
+                    if (has_lo) tx_tma5(sa + A_BYTES, &tmAlo, &bars.full[s], c0, c1, c2, c3, c4);
+                    tx_tma5(sb, &tmB, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
+                    tx_tma5(sb + B_BYTES, &tmBlo, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // D fp32, A/B tf32, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int kb = 0; kb < p.n_kb; ++kb) {
-                const int s = kb % stages;
-                const int c = kb / chain, buf = c & 1;
-                const bool first = (kb - c * chain) == 0;
-                if (first && c >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)(((c >> 1) - 1) & 1));
-                tx_mbar_wait(&bars.full[s], (uint32_t)((kb / stages) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
-                const uint32_t sb = sa + (uint32_t)(A_BYTES * (has_lo ? 2 : 1));
+            int it = 0, cc = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
+                    const int s = it % stages;
+                    const int c = kb / chain, buf = (cc + c) & 1;
+                    const bool first = (kb - c * chain) == 0;
+                    if (first && cc + c >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)((((cc + c) >> 1) - 1) & 1));
+                    tx_mbar_wait(&bars.full[s], (uint32_t)((it / stages) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
+                    const uint32_t sb = sa + (uint32_t)(A_BYTES * (has_lo ? 2 : 1));
 #pragma unroll
-                for (int mb = 0; mb < MB; ++mb) {
-                    const uint32_t d = tmem + (uint32_t)(buf * MB * BN + mb * BN);
-                    const uint32_t ah = sa + (uint32_t)(mb * 128 * TX_ROWB);
+                    for (int mb = 0; mb < MB; ++mb) {
+                        const uint32_t d = tmem + (uint32_t)(buf * MB * BN + mb * BN);
+                        const uint32_t ah = sa + (uint32_t)(mb * 128 * TX_ROWB);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t o = ks * 32;
-                        const uint64_t dah = tx_desc(ah + o, 16, 1024, 2), dbh = tx_desc(sb + o, 16, 1024, 2);
-                        const uint64_t dbl = tx_desc(sb + B_BYTES + o, 16, 1024, 2);
-                        const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
-                        if (has_lo) tx_mma(d, tx_desc(ah + A_BYTES + o, 16, 1024, 2), dbh, idesc, acc0);
-                        tx_mma(d, dah, dbl, idesc, has_lo ? 1u : acc0);
-                        tx_mma(d, dah, dbh, idesc, 1u);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t o = ks * 32;
+                            const uint64_t dah = tx_desc(ah + o, 16, 1024, 2), dbh = tx_desc(sb + o, 16, 1024, 2);
+                            const uint64_t dbl = tx_desc(sb + B_BYTES + o, 16, 1024, 2);
+                            const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
+                            if (has_lo) tx_mma(d, tx_desc(ah + A_BYTES + o, 16, 1024, 2), dbh, idesc, acc0);
+                            tx_mma(d, dah, dbl, idesc, has_lo ? 1u : acc0);
+                            tx_mma(d, dah, dbh, idesc, 1u);
+                        }
                     }
+                    tx_commit(&bars.empty[s]);
+                    if (kb == p.n_kb - 1 || (kb + 1) % chain == 0) tx_commit(&bars.acc_full[buf]);
                 }
-                tx_commit(&bars.empty[s]);
-                if (kb == p.n_kb - 1 || (kb + 1) % chain == 0) tx_commit(&bars.acc_full[buf]);
+                cc += n_chains;
             }
         }
     } else {
         // ---- drain chains into registers, then the epilogue ----
         const int q = warp & 3, hf = (warp - TX_EPI0) >> 2;          // TMEM lane quadrant, column half
-        float acc[MB][HALF];
-#pragma unroll
-        for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-            for (int n = 0; n < HALF; ++n) acc[mb][n] = 0.f;
-        for (int c = 0; c < n_chains; ++c) {
-            const int buf = c & 1;
-            tx_mbar_wait(&bars.acc_full[buf], (uint32_t)((c >> 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int b1 = p.A.box[1], b2 = p.A.box[2], b3 = p.A.box[3];
+        int cc = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            int base[5];
+            tx_tile_base(p.tiles, w / n_n, base);
+            const int n0 = (w % n_n) * BN;
+            float acc[MB][HALF];
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-                for (int c0 = 0; c0 < HALF; c0 += 16) {
-                    uint32_t v[16];
-                    tx_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * MB * BN + mb * BN + hf * HALF + c0), v);
+                for (int n = 0; n < HALF; ++n) acc[mb][n] = 0.f;
+            for (int c = 0; c < n_chains; ++c, ++cc) {
+                const int buf = cc & 1;
+                tx_mbar_wait(&bars.acc_full[buf], (uint32_t)((cc >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                    for (int n = 0; n < 16; ++n) acc[mb][c0 + n] += __uint_as_float(v[n]);
-                }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            tx_mbar_arrive(&bars.acc_empty[buf]);
-        }
-        const int b1 = p.A.box[1], b2 = p.A.box[2], b3 = p.A.box[3];
+                for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-            const int r = mb * 128 + 32 * q + lane;
-            if (r >= R) continue;
-            int t = r;
-            const int i1 = t % b1; t /= b1;
-            const int i2 = t % b2; t /= b2;
-            const int i3 = t % b3; t /= b3;
-            const int i4 = t;
-            const int g1 = base[1] + i1, g2 = base[2] + i2, g3 = base[3] + i3, g4 = base[4] + i4;
-            if (g1 >= p.o_ext[1] || g2 >= p.o_ext[2] || g3 >= p.o_ext[3] || g4 >= p.o_ext[4]) continue;
-            const long off = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
+                    for (int c0 = 0; c0 < HALF; c0 += 16) {
+                        uint32_t v[16];
+                        tx_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * MB * BN + mb * BN + hf * HALF + c0), v);
 #pragma unroll
-            for (int n = 0; n < HALF; n += 4) {
-                const int ch = n0 + hf * HALF + n;
-                if (ch >= p.N) continue;
-                float4 v = make_float4(acc[mb][n] * p.alpha, acc[mb][n + 1] * p.alpha, acc[mb][n + 2] * p.alpha,
-                                       acc[mb][n + 3] * p.alpha);
-                if (p.bias) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-                    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        for (int n = 0; n < 16; ++n) acc[mb][c0 + n] += __uint_as_float(v[n]);
+                    }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                tx_mbar_arrive(&bars.acc_empty[buf]);
+            }
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const int r = mb * 128 + 32 * q + lane;
+                if (r >= R) continue;
+                int t = r;
+                const int i1 = t % b1; t /= b1;
+                const int i2 = t % b2; t /= b2;
+                const int i3 = t % b3; t /= b3;
+                const int i4 = t;
+                const int g1 = base[1] + i1, g2 = base[2] + i2, g3 = base[3] + i3, g4 = base[4] + i4;
+                if (g1 >= p.o_ext[1] || g2 >= p.o_ext[2] || g3 >= p.o_ext[3] || g4 >= p.o_ext[4]) continue;
+                const long off = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
+#pragma unroll
+                for (int n = 0; n < HALF; n += 4) {
+                    const int ch = n0 + hf * HALF + n;
+                    if (ch >= p.N) continue;
+                    float4 v = make_float4(acc[mb][n] * p.alpha, acc[mb][n + 1] * p.alpha, acc[mb][n + 2] * p.alpha,
+                                           acc[mb][n + 3] * p.alpha);
+                    if (p.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                    }
+                    if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (p.mask) {
+                        const float4 m = __ldg(reinterpret_cast<const float4*>(p.mask + off + ch));
+                        v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+                        v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(p.out + off + ch) = v;
+                    if (p.out_lo)
+                        *reinterpret_cast<float4*>(p.out_lo + off + ch) = make_float4(tx_lo(v.x), tx_lo(v.y), tx_lo(v.z), tx_lo(v.w));
                 }
-                if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                if (p.mask) {
-                    const float4 m = __ldg(reinterpret_cast<const float4*>(p.mask + off + ch));
-                    v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
-                    v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
-                }
-                *reinterpret_cast<float4*>(p.out + off + ch) = v;
-                if (p.out_lo)
-                    *reinterpret_cast<float4*>(p.out_lo + off + ch) = make_float4(tx_lo(v.x), tx_lo(v.y), tx_lo(v.z), tx_lo(v.w));
             }
         }
     }
@@ -493,7 +511,8 @@ int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
         if (e != cudaSuccess) { set_error("tcx_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return A2CB_ERR_CUDA; }
         attr = true;
     }
-    dim3 grid((unsigned)p.tiles.n_tiles, (unsigned)((p.N + BN - 1) / BN));
+    const long n_work = (long)p.tiles.n_tiles * ((p.N + BN - 1) / BN);
+    dim3 grid((unsigned)(n_work < kNumSM ? n_work : kNumSM));
     tcx_fwd_kernel<BN, MB><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], p, stages);
     return check_launch("tcx_fwd");
 }

@@ -55,27 +55,118 @@ tcx_s2d_kernel(float* __restrict__ out, float* __restrict__ out_lo, const T* __r
     }
 }
 
-// part[blk][c] = sum over this block's rows of x[row * pitch + c]   (C <= 2048 channels, row-contiguous)
+// Atari geometry (C = 4, 84 x 84, S = 4): one block per (image, block row).  The 16 source rows (c, dy) of
+// 84 pixels are read as coalesced 4-byte / 16-byte words into shared memory and written back as 21 x 64
+// contiguous floats -- both sides of the transposition are fully coalesced.
+template <typename T>
+__global__ void __launch_bounds__(352)
+tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, const T* __restrict__ frames,
+                     const int64_t* __restrict__ idx) {
+    __shared__ float4 tile[16][21];
+    const int b = blockIdx.x / 21, by = blockIdx.x % 21;
+    const long row = idx ? (long)idx[b] : b;
+    const int i = threadIdx.x;
+    if (i < 336) {
+        const int r = i / 21, bx = i % 21;                       // r = c * 4 + dy
+        const long src = ((row * 4 + (r >> 2)) * 84 + (by * 4 + (r & 3))) * 84 + bx * 4;
+        float4 v;
+        if (sizeof(T) == 1) {
+            const uchar4 u = *reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(frames) + src);
+            v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+        } else {
+            v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(frames) + src);
+        }
+        tile[r][bx] = v;
+    }
+    __syncthreads();
+    if (i < 336) {
+        const int bx = i >> 4, r = i & 15;
+        const float4 v = tile[r][bx];
+        const long o = ((long)(b * 21 + by) * 21 + bx) * 16 + r;
+        out[o] = v;
+        if (out_lo) out_lo[o] = make_float4(ax_lo(v.x), ax_lo(v.y), ax_lo(v.z), ax_lo(v.w));
+    }
+}
+
+// part[blk][c] = sum over this block's rows of x[row * pitch + c]   (C a multiple of 4, row-contiguous).
+// Thread = (channel quad, row lane); float4 loads, four independent accumulator sets, shared-memory fold
+// across the row lanes in a fixed order (deterministic).
 __global__ void __launch_bounds__(256)
 tcx_colsum_kernel(float* __restrict__ part, const float* __restrict__ x, long rows, int C, long pitch, long rows_per_blk) {
-    __shared__ float red[256];
+    __shared__ float4 red[256];
     const long r0 = (long)blockIdx.x * rows_per_blk, r1 = min(rows, r0 + rows_per_blk);
-    // thread -> (channel lane cl, row lane rl): consecutive threads read consecutive channels of a row
-    const int cw = C < 256 ? C : 256;              // channels covered per pass
-    const int rl_n = 256 / cw;                     // rows in flight
-    const int cl = threadIdx.x % cw, rl = threadIdx.x / cw;
-    for (int c0 = 0; c0 < C; c0 += cw) {
-        float s = 0.f;
-        if (rl < rl_n && c0 + cl < C)
-            for (long r = r0 + rl; r < r1; r += rl_n) s += x[r * pitch + c0 + cl];
-        red[threadIdx.x] = s;
+    const int nq = C / 4;
+    const int qw = nq < 256 ? nq : 256;            // channel quads covered per pass
+    const int rl_n = 256 / qw;                     // row lanes
+    const int ql = threadIdx.x % qw, rl = threadIdx.x / qw;
+    for (int q0 = 0; q0 < nq; q0 += qw) {
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+        if (rl < rl_n && q0 + ql < nq) {
+            const float* base = x + (long)(q0 + ql) * 4;
+            long r = r0 + rl;
+            for (; r + 3L * rl_n < r1; r += 4L * rl_n) {
+                const float4 a = *reinterpret_cast<const float4*>(base + r * pitch);
+                const float4 b = *reinterpret_cast<const float4*>(base + (r + rl_n) * pitch);
+                const float4 c = *reinterpret_cast<const float4*>(base + (r + 2L * rl_n) * pitch);
+                const float4 d = *reinterpret_cast<const float4*>(base + (r + 3L * rl_n) * pitch);
+                s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+                s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+                s2.x += c.x; s2.y += c.y; s2.z += c.z; s2.w += c.w;
+                s3.x += d.x; s3.y += d.y; s3.z += d.z; s3.w += d.w;
+            }
+            for (; r < r1; r += rl_n) {
+                const float4 a = *reinterpret_cast<const float4*>(base + r * pitch);
+                s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+            }
+        }
+        red[threadIdx.x] = make_float4((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y),
+                                       (s0.z + s1.z) + (s2.z + s3.z), (s0.w + s1.w) + (s2.w + s3.w));
         __syncthreads();
-        if (rl == 0 && c0 + cl < C) {
-            float tsum = 0.f;
-            for (int j = 0; j < rl_n; ++j) tsum += red[j * cw + cl];
-            part[(long)blockIdx.x * C + c0 + cl] = tsum;
+        if (rl == 0 && q0 + ql < nq) {
+            float4 t = red[ql];
+            for (int j = 1; j < rl_n; ++j) {
+                const float4 u = red[j * qw + ql];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            *reinterpret_cast<float4*>(part + (long)blockIdx.x * C + (long)(q0 + ql) * 4) = t;
         }
         __syncthreads();
+    }
+}
+
+// Weight + bias gradient of a narrow Linear layer (the policy / value heads, N <= 8 outputs):
+//   part[blk][n * K + k] = sum over the block's rows of gy[row * gy_stride + n] * x[row * K + k]
+//   part[blk][N * K + n] = sum of gy[row * gy_stride + n]
+// x is streamed once with coalesced loads (HBM-bound); the N gradients of a row are warp-uniform broadcasts.
+template <int N>
+__global__ void __launch_bounds__(256)
+tcx_narrow_wgrad_kernel(float* __restrict__ part, const float* __restrict__ x, const float* __restrict__ gy, long rows,
+                        int K, int gy_stride, long rows_per_blk) {
+    const long r0 = (long)blockIdx.x * rows_per_blk, r1 = min(rows, r0 + rows_per_blk);
+    float* dst = part + (long)blockIdx.x * (N * K + N);
+    for (int k = threadIdx.x; k < K; k += 256) {
+        float acc[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) acc[n] = 0.f;
+        float bsum[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) bsum[n] = 0.f;
+#pragma unroll 4
+        for (long r = r0; r < r1; ++r) {
+            const float xv = x[r * K + k];
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                const float g = __ldg(gy + r * gy_stride + n);
+                acc[n] = fmaf(g, xv, acc[n]);
+                bsum[n] += g;
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < N; ++n) dst[n * K + k] = acc[n];
+        if (k < 1) {
+#pragma unroll
+            for (int n = 0; n < N; ++n) dst[N * K + n] = bsum[n];
+        }
     }
 }
 
@@ -101,6 +192,15 @@ int tcx_prep_weights(float* img, float* img_lo, const float* src, long N, long K
 int tcx_s2d(float* out, float* out_lo, const void* frames, int src_is_u8, const int64_t* idx, int B, int C, int H, int W,
             int S, cudaStream_t st) {
     A2CB_REQUIRE(out && frames && B > 0 && S > 0 && H % S == 0 && W % S == 0, "tcx_s2d: bad arguments");
+    if (C == 4 && H == 84 && W == 84 && S == 4) {
+        if (src_is_u8)
+            tcx_s2d_atari_kernel<uint8_t><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
+                                                                               reinterpret_cast<const uint8_t*>(frames), idx);
+        else
+            tcx_s2d_atari_kernel<float><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
+                                                                             reinterpret_cast<const float*>(frames), idx);
+        return check_launch("tcx_s2d");
+    }
     const long total = (long)B * C * H * W;
     const unsigned grid = (unsigned)min((total + 255) / 256, (long)kNumSM * 32);
     if (src_is_u8)
@@ -110,14 +210,28 @@ int tcx_s2d(float* out, float* out_lo, const void* frames, int src_is_u8, const 
     return check_launch("tcx_s2d");
 }
 
-int tcx_colsum_blocks(long rows) { return (int)min((rows + 255) / 256, (long)kNumSM * 2); }
+int tcx_colsum_blocks(long rows) { return (int)min((rows + 127) / 128, (long)kNumSM * 8); }
 
 int tcx_colsum(float* part, const float* x, long rows, int C, long pitch, cudaStream_t st) {
-    A2CB_REQUIRE(part && x && rows > 0 && C > 0, "tcx_colsum: bad arguments");
+    A2CB_REQUIRE(part && x && rows > 0 && C > 0 && C % 4 == 0 && pitch % 4 == 0, "tcx_colsum: bad arguments");
     const int blocks = tcx_colsum_blocks(rows);
     const long per = (rows + blocks - 1) / blocks;
     tcx_colsum_kernel<<<blocks, 256, 0, st>>>(part, x, rows, C, pitch, per);
     return check_launch("tcx_colsum");
+}
+
+int tcx_narrow_wgrad_blocks(long rows) { return (int)min((rows + 63) / 64, (long)kNumSM * 4); }
+
+int tcx_narrow_wgrad(float* part, const float* x, const float* gy, long rows, int K, int N, int gy_stride, cudaStream_t st) {
+    A2CB_REQUIRE(part && x && gy && rows > 0 && K > 0 && N >= 1 && N <= 8, "tcx_narrow_wgrad: bad arguments (N = %d)", N);
+    const int blocks = tcx_narrow_wgrad_blocks(rows);
+    const long per = (rows + blocks - 1) / blocks;
+    switch (N) {
+#define A2CB_NW(n) case n: tcx_narrow_wgrad_kernel<n><<<blocks, 256, 0, st>>>(part, x, gy, rows, K, gy_stride, per); break;
+        A2CB_NW(1) A2CB_NW(2) A2CB_NW(3) A2CB_NW(4) A2CB_NW(5) A2CB_NW(6) A2CB_NW(7) A2CB_NW(8)
+#undef A2CB_NW
+    }
+    return check_launch("tcx_narrow_wgrad");
 }
 
 }  // namespace a2cb
