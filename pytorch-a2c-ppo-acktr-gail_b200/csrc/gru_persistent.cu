@@ -2,14 +2,14 @@
 //
 // The per-step formulation (gru.cu + one tiny GEMM per step) is launch- and latency-bound: at the
 // C5 minibatch shape (T = 128, N = 64 environments, H = 512) the 2 x 128 sequential GEMMs of
-// 0.1 GFLOP each cost ~18 us apiece although they are ~1.5 us of fp32 math.  Here CTA b owns 4 hidden
-// units for ALL environments and keeps its slice of W_hh (12 gate rows forward, 4 columns backward,
-// 24 KiB) resident in shared memory for all T steps; H / 4 = 128 CTAs, one per SM.  Per step a warp
-// takes 8 environments, its lanes split the reduction dimension, operands stream from L2 with
-// coalesced ld.global.cg float4 (no shared-memory staging, no bank conflicts), partial sums are
-// transpose-reduced with shuffles so that lane 4 r + j finishes (environment r, unit j), and the
-// CTAs meet at ONE grid barrier per step.  Episode boundaries are the mask multiply, exactly as in
-// gru.cu (reference model.py:111-166).
+// 0.1 GFLOP each cost ~18 us apiece although they are ~1.5 us of fp32 math.  Here CTA (bx, by) owns 32
+// hidden units and 8 environments: its slice of W_hh (96 gate rows forward, 32 columns backward, 192 KiB)
+// stays resident in shared memory for all T steps, and per step it streams only ITS 8 rows of the previous
+// state / gate gradients from L2 (16 / 48 KiB; a first version in which every CTA read all 64 rows was L2-
+// bandwidth-bound at 17 / 50 MB per step).  16 x 8 = 128 CTAs, one per SM.  A warp takes 4 units, its lanes
+// split the reduction dimension, partial sums are transpose-reduced with shuffles so that lane 4 r + j
+// finishes (environment r, unit j), and the CTAs meet at ONE grid barrier per step.  Episode boundaries
+// are the mask multiply, exactly as in gru.cu (reference model.py:111-166).
 //
 // Same buffers and the same saved quantities as the per-step path, so either path can feed the
 // weight-gradient GEMMs and the tests compare both against the reference goldens.
@@ -23,10 +23,10 @@ namespace cg = cooperative_groups;
 
 namespace a2cb {
 
-constexpr int PG_KB = 4;        // hidden units per CTA  (H / 4 CTAs: 128 for the 512-unit GRU)
-constexpr int PG_RW = 8;        // environments per warp
-constexpr int PG_NW = 8;        // warps per CTA -> 64 environments per pass
-constexpr int PG_RB = PG_RW * PG_NW;
+constexpr int PG_UW = 4;         // hidden units per warp (12 gate rows)
+constexpr int PG_NW = 8;         // warps per CTA
+constexpr int PG_UB = PG_UW * PG_NW;   // hidden units per CTA (32): H / 32 unit groups
+constexpr int PG_RW = 8;         // environments per CTA and pass (all warps share them through L1)
 constexpr int PG_NT = 32 * PG_NW;
 
 __device__ __forceinline__ float pg_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
@@ -41,6 +41,24 @@ __device__ __forceinline__ float pg_dot4(const float4 a, const float4 b, float a
     acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
     acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
     return acc;
+}
+
+// Barrier among the CTAs that share an environment group (same blockIdx.y): only those exchange data --
+// environments are independent -- so 16 CTAs meet instead of the whole grid, on their own monotonically
+// increasing counter.  release / acquire at gpu scope order the state writes of every CTA before the reads
+// of the others (the CTA-wide bar.sync on both sides extends that to all of its threads).
+__device__ unsigned pg_counters[2][256];
+
+__device__ __forceinline__ void pg_group_sync(unsigned* ctr, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
 }
 
 // Butterfly "transpose-reduce": every lane enters with NV partial sums v[0..NV) (NV = 32 * PER) of the
@@ -64,44 +82,47 @@ __device__ __forceinline__ void pg_reduce(float* v, int lane) {
 }
 
 // ---------------------------------------------------------------------------
-// forward: CTA b owns hidden units kb = 4 b .. 4 b + 3 (12 gate rows of W_hh resident in shared memory).
-// Per step and per block of 64 environments: warp w takes 8 environments, its lanes split the reduction
-// (lane l: k = 4 l .. 4 l + 3 of every 128), hm_t comes straight from L2 (ld.global.cg, coalesced float4,
-// 8 independent loads in flight per lane), the 96 partial sums are transpose-reduced so that lane
-// l = 4 r + j ends up with the three gate pre-activations of (environment r, unit j) and applies the gate
-// math.  One grid barrier per step.
+// forward: CTA (bx, by) owns hidden units 32 bx .. 32 bx + 31 (their 96 gate rows of W_hh, 192 KiB, stay in
+// shared memory for all T steps) and the environment groups by, by + gridDim.y, ... of 8 environments.
+// Warp w takes units 4 w .. 4 w + 3; its lanes split the reduction (lane l: k = 4 l .. 4 l + 3 of every
+// 128).  All 8 warps read the same 8 rows of hm_t, so the CTA pulls 16 KiB per step from L2 and the other
+// 7 reads hit L1 (every address is read only after its one write of this launch and was never cached
+// before, so the non-coherent L1 cannot serve stale data).  The 96 partial sums of a warp are
+// transpose-reduced so that lane 4 r + j ends up with the three gate pre-activations of (environment r,
+// unit j) and applies the gate math.  One grid barrier per step.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(PG_NT)
 gru_persistent_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh) {
     extern __shared__ __align__(16) float pg_smem[];
     const int H = d.H;
-    float* Ws = pg_smem;                                            // [j * 3 + g][H]
-    cg::grid_group grid = cg::this_grid();
+    unsigned* ctr = &pg_counters[0][blockIdx.y];
+    unsigned epoch = 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kb = blockIdx.x * PG_KB;
-    for (int e = tid; e < 3 * PG_KB * H; e += PG_NT) {
+    const int ub = blockIdx.x * PG_UB;                              // first unit of this CTA
+    // Ws[(w * 4 + j) * 3 + g][H] = W_hh[g * H + ub + 4 w + j][:]
+    for (int e = tid; e < 3 * PG_UB * H; e += PG_NT) {
         const int c = e / H, k = e - c * H;
-        const int j = c / 3, g = c - j * 3;
-        Ws[e] = Whh[(long)(g * H + kb + j) * H + k];
+        const int u = c / 3, g = c - u * 3;
+        pg_smem[e] = Whh[(long)(g * H + ub + u) * H + k];
     }
+    const float* Ws = pg_smem + (long)warp * 12 * H;
     const int rl = lane >> 2, jl = lane & 3;                        // this lane's (environment, unit) after the reduce
-    const int ku = kb + jl;
+    const int ku = ub + PG_UW * warp + jl;
     const float b_r = bhh[ku], b_z = bhh[H + ku], b_n = bhh[2 * H + ku];
-    const int nblk = (d.N + PG_RB - 1) / PG_RB;
+    const int ngrp = (d.N + PG_RW - 1) / PG_RW;
 
-    // hm_0 = h0 * mask_0 for this CTA's units
-    for (int e = tid; e < d.N * PG_KB; e += PG_NT) {
-        const int n = e / PG_KB, k = kb + (e - n * PG_KB);
-        d.hm[(long)n * H + k] = d.h0[(long)n * H + k] * pg_mask(d, 0, n);
+    // hm_0 = h0 * mask_0 for this CTA's units and environments
+    for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+        const int my = grp * PG_RW + rl;
+        if (my < d.N) d.hm[(long)my * H + ku] = d.h0[(long)my * H + ku] * pg_mask(d, 0, my);
     }
-    __syncthreads();
-    grid.sync();
+    pg_group_sync(ctr, ++epoch * gridDim.x);
 
     for (int t = 0; t < d.T; ++t) {
-        const float* hm_t = d.hm + (long)t * d.N * H;
-        for (int blk = 0; blk < nblk; ++blk) {
-            const int r0 = blk * PG_RB + warp * PG_RW;
+        float* hm_t = d.hm + (long)t * d.N * H;
+        for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+            const int r0 = grp * PG_RW;
             const int my = r0 + rl;                                 // the environment this lane finishes
             const bool live = my < d.N;
             const long row = (long)t * d.N + my;
@@ -109,7 +130,7 @@ gru_persistent_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const 
             if (live) {                                             // issued early, consumed after the matmul
                 const float* gi = d.gi + row * 3 * H;
                 gi_r = __ldg(gi + ku); gi_z = __ldg(gi + H + ku); gi_n = __ldg(gi + 2 * H + ku);
-                hprev = __ldcg(hm_t + (long)my * H + ku);
+                hprev = hm_t[(long)my * H + ku];
                 mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, my) : 0.f;
             }
             float acc[PG_RW * 12];
@@ -121,7 +142,7 @@ gru_persistent_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const 
 #pragma unroll
                 for (int r = 0; r < PG_RW; ++r) {
                     const int n = min(r0 + r, d.N - 1);
-                    h[r] = __ldcg(reinterpret_cast<const float4*>(hm_t + (long)n * H + k0 + 4 * lane));
+                    h[r] = *reinterpret_cast<const float4*>(hm_t + (long)n * H + k0 + 4 * lane);
                 }
             };
             auto mul_h = [&](const float4* h, int k0) {
@@ -151,39 +172,43 @@ gru_persistent_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const 
                     d.r[row * H + ku] = rr; d.z[row * H + ku] = zz; d.n[row * H + ku] = nn;
                     d.gh[row * 3 * H + 2 * H + ku] = ghn;            // the only part of gh the backward pass reads
                 }
-                if (t + 1 < d.T) __stcg(d.hm + (row + d.N) * H + ku, h * mnext);
+                if (t + 1 < d.T) d.hm[(row + d.N) * H + ku] = h * mnext;
             }
         }
-        if (t + 1 < d.T) grid.sync();
+        if (t + 1 < d.T) pg_group_sync(ctr, ++epoch * gridDim.x);
     }
 }
 
 // ---------------------------------------------------------------------------
-// backward through time: CTA b owns the same 4 units; its columns of W_hh (all 3H gate rows) stay in
-// shared memory.  Phase A (element-wise gate gradients of its units, needs the carry it computed itself),
-// grid barrier, phase B (carry = dh z + dgh_t W_hh restricted to its units, lanes split the 3H-long
-// reduction, 32 partial sums transpose-reduced to one per lane).
+// backward through time: same ownership; the 32 columns of W_hh (all 3H gate rows, 192 KiB) of the CTA's
+// units stay in shared memory.  Phase A (element-wise gate gradients of its units and environments, needs
+// the carry it computed itself), grid barrier, phase B (carry = dh z + dgh_t W_hh restricted to its units,
+// lanes split the 3H-long reduction, 32 partial sums transpose-reduced to one per lane).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(PG_NT)
 gru_persistent_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws) {
     extern __shared__ __align__(16) float pg_smem[];
     const int H = d.H, H3 = 3 * d.H;
-    float* Wc = pg_smem;     // [(c / 128) * 4 + c % 4][lane = (c % 128) / 4][4 units]: conflict-free float4 per lane
-    cg::grid_group grid = cg::this_grid();
+    unsigned* ctr = &pg_counters[1][blockIdx.y];
+    unsigned epoch = 0;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kb = blockIdx.x * PG_KB;
-    for (int e = tid; e < H3 * PG_KB; e += PG_NT) {
-        const int c = e / PG_KB, j = e - c * PG_KB;
+    const int ub = blockIdx.x * PG_UB;
+    const int nit = H3 / 128;
+    // Wc[w][(c / 128) * 4 + c % 4][lane = (c % 128) / 4][j] = W_hh[c][ub + 4 w + j]: one conflict-free float4 per lane
+    for (int e = tid; e < H3 * PG_UB; e += PG_NT) {
+        const int c = e / PG_UB, u = e - c * PG_UB;
+        const int w = u >> 2, j = u & 3;
         const int it = c >> 7, l = (c & 127) >> 2, q = c & 3;
-        Wc[(((it * 4 + q) * 32) + l) * 4 + j] = Whh[(long)c * H + kb + j];
+        pg_smem[((((long)w * nit + it) * 4 + q) * 32 + l) * 4 + j] = Whh[(long)c * H + ub + u];
     }
     __syncthreads();
+    const float4* Wc = reinterpret_cast<const float4*>(pg_smem) + (long)warp * nit * 4 * 32;
     const int rl = lane >> 2, jl = lane & 3;
-    const int ku = kb + jl;
-    const int nblk = (d.N + PG_RB - 1) / PG_RB;
-    // carry of (environment, unit): one per lane per environment block; blocks beyond the first spill to a
-    // small global workspace slice private to this CTA
+    const int ku = ub + PG_UW * warp + jl;
+    const int ngrp = (d.N + PG_RW - 1) / PG_RW;
+    // carry of (environment, unit): a register for the CTA's first environment group, the [N, H] workspace
+    // for further groups
     float carry0 = 0.f;
 
     struct PhaseA { float dout, r, z, n, hm, ghn, mnext; };
@@ -197,20 +222,21 @@ gru_persistent_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float*
         a.mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, my) : 0.f;
         return a;
     };
-    const int my0 = warp * PG_RW + rl;                       // this lane's environment in block 0
+    const int my0 = blockIdx.y * PG_RW + rl;                 // this lane's environment in the first group
     PhaseA pre = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (my0 < d.N) pre = load_a(d.T - 1, my0);
 
     for (int t = d.T - 1; t >= 0; --t) {
         // ---- phase A ----
-        for (int blk = 0; blk < nblk; ++blk) {
-            const int my = blk * PG_RB + warp * PG_RW + rl;
+        for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+            const int my = grp * PG_RW + rl;
             if (my >= d.N) continue;
+            const bool first = grp == (int)blockIdx.y;
             const long row = (long)t * d.N + my;
-            const PhaseA a = blk == 0 ? pre : load_a(t, my);   // block 0 was prefetched before the last barrier
+            const PhaseA a = first ? pre : load_a(t, my);      // the first group was prefetched before the last barrier
             float dh = a.dout;
             if (t + 1 < d.T) {
-                const float c = blk == 0 ? carry0 : carry_ws[((long)blockIdx.x * d.N + my) * PG_KB + jl];
+                const float c = first ? carry0 : carry_ws[(long)my * H + ku];
                 dh += c * a.mnext;
             }
             const float dn_pre = dh * (1.f - a.z) * (1.f - a.n * a.n);
@@ -219,35 +245,35 @@ gru_persistent_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float*
             float* dgi = d.dgi + row * 3 * H;
             float* dgh = d.dgh + row * 3 * H;
             dgi[ku] = dr_pre; dgi[H + ku] = dz_pre; dgi[2 * H + ku] = dn_pre;
-            __stcg(dgh + ku, dr_pre); __stcg(dgh + H + ku, dz_pre); __stcg(dgh + 2 * H + ku, dn_pre * a.r);
+            dgh[ku] = dr_pre; dgh[H + ku] = dz_pre; dgh[2 * H + ku] = dn_pre * a.r;
             const float dhz = dh * a.z;
-            if (blk == 0) carry0 = dhz;
-            else carry_ws[((long)blockIdx.x * d.N + my) * PG_KB + jl] = dhz;
+            if (first) carry0 = dhz;
+            else carry_ws[(long)my * H + ku] = dhz;
         }
         if (t == 0) break;                 // the gradient w.r.t. the initial state is not needed
-        if (my0 < d.N) pre = load_a(t - 1, my0);               // in flight across the barrier and phase B
-        grid.sync();
+        pg_group_sync(ctr, ++epoch * gridDim.x);
+        if (my0 < d.N) pre = load_a(t - 1, my0);               // in flight during phase B
         // ---- phase B ----
         const float* dgh_t = d.dgh + (long)t * d.N * H3;
-        for (int blk = 0; blk < nblk; ++blk) {
-            const int r0 = blk * PG_RB + warp * PG_RW;
-            float acc[PG_RW * PG_KB];
+        for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+            const int r0 = grp * PG_RW;
+            float acc[PG_RW * PG_UW];
 #pragma unroll
-            for (int i = 0; i < PG_RW * PG_KB; ++i) acc[i] = 0.f;
+            for (int i = 0; i < PG_RW * PG_UW; ++i) acc[i] = 0.f;
             float4 ga[PG_RW], gb[PG_RW];
             auto load_g = [&](float4* g, int it) {
 #pragma unroll
                 for (int r = 0; r < PG_RW; ++r) {
                     const int n = min(r0 + r, d.N - 1);
-                    g[r] = __ldcg(reinterpret_cast<const float4*>(dgh_t + (long)n * H3 + it * 128 + 4 * lane));
+                    g[r] = *reinterpret_cast<const float4*>(dgh_t + (long)n * H3 + it * 128 + 4 * lane);
                 }
             };
             auto mul_g = [&](const float4* g, int it) {
-                const float4* wp = reinterpret_cast<const float4*>(Wc) + (it * 4) * 32 + lane;
+                const float4* wp = Wc + (it * 4) * 32 + lane;
                 const float4 w0 = wp[0], w1 = wp[32], w2 = wp[64], w3 = wp[96];
 #pragma unroll
                 for (int r = 0; r < PG_RW; ++r) {
-                    float* a = acc + r * PG_KB;
+                    float* a = acc + r * PG_UW;
                     a[0] = fmaf(g[r].x, w0.x, a[0]); a[1] = fmaf(g[r].x, w0.y, a[1]);
                     a[2] = fmaf(g[r].x, w0.z, a[2]); a[3] = fmaf(g[r].x, w0.w, a[3]);
                     a[0] = fmaf(g[r].y, w1.x, a[0]); a[1] = fmaf(g[r].y, w1.y, a[1]);
@@ -258,7 +284,6 @@ gru_persistent_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float*
                     a[2] = fmaf(g[r].w, w3.z, a[2]); a[3] = fmaf(g[r].w, w3.w, a[3]);
                 }
             };
-            const int nit = H3 / 128;
             load_g(ga, 0);
             for (int it = 0; it < nit; it += 2) {
                 if (it + 1 < nit) load_g(gb, it + 1);
@@ -266,36 +291,42 @@ gru_persistent_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float*
                 if (it + 2 < nit) load_g(ga, it + 2);
                 if (it + 1 < nit) mul_g(gb, it + 1);
             }
-            pg_reduce<PG_RW * PG_KB>(acc, lane);                   // acc[0] = sum of (rl, jl)
+            pg_reduce<PG_RW * PG_UW>(acc, lane);                   // acc[0] = sum of (rl, jl)
             const int my = r0 + rl;
             if (my < d.N) {
-                if (blk == 0) carry0 += acc[0];
-                else carry_ws[((long)blockIdx.x * d.N + my) * PG_KB + jl] += acc[0];
+                if (grp == (int)blockIdx.y) carry0 += acc[0];
+                else carry_ws[(long)my * H + ku] += acc[0];
             }
         }
     }
 }
 
-static size_t pg_smem_bytes(int H) { return (size_t)(3 * PG_KB * H) * sizeof(float); }
+static size_t pg_smem_bytes(int H) { return (size_t)(3 * PG_UB * H) * sizeof(float); }
 
-// Cooperative launch: every CTA must be co-resident.  Asks the runtime how many fit.
-bool gru_persistent_supported(int N, int H) {
-    if (N <= 0 || H % 128 != 0) return false;
-    const size_t smem = pg_smem_bytes(H);
-    if (smem > 200 * 1024) return false;
+static int pg_sms() {
     static int sms = 0;
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    cudaFuncSetAttribute(gru_persistent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(gru_persistent_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return sms;
+}
+
+// Cooperative launch: every CTA must be co-resident (one per SM at this shared-memory footprint).
+bool gru_persistent_supported(int N, int H) {
+    if (N <= 0 || H % 128 != 0 || H % PG_UB != 0) return false;
+    const size_t smem = pg_smem_bytes(H);
+    if (smem > 220 * 1024) return false;
+    if (cudaFuncSetAttribute(gru_persistent_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(gru_persistent_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
     int pf = 0, pb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pf, gru_persistent_fwd_kernel, PG_NT, smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, gru_persistent_bwd_kernel, PG_NT, smem);
-    const long ctas = (long)(H / PG_KB);
-    return ctas <= (long)sms * (pf < pb ? pf : pb);
+    return (long)(H / PG_UB) <= (long)pg_sms() * (pf < pb ? pf : pb);
 }
 
 int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st) {
@@ -303,9 +334,21 @@ int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float
     A2CB_REQUIRE(Whh && d.hm && d.masks, "gru_persistent: null pointer");
     A2CB_REQUIRE(backward || (bhh && d.h0 && d.gi && d.out), "gru_persistent: forward pointers");
     A2CB_REQUIRE(!backward || (d.r && d.z && d.n && d.gh && d.dout && d.dgi && d.dgh), "gru_persistent: backward pointers");
-    A2CB_REQUIRE(!backward || d.N <= PG_RB || d.dcarry, "gru_persistent: dcarry workspace [N, H] needed for N > %d", PG_RB);
+    const int ug = d.H / PG_UB;                                    // unit groups
+    const int ngrp = (d.N + PG_RW - 1) / PG_RW;                    // environment groups
+    int gy = pg_sms() / ug;
+    gy = gy < 1 ? 1 : (gy > ngrp ? ngrp : gy);
+    A2CB_REQUIRE(!backward || ngrp <= gy || d.dcarry, "gru_persistent: dcarry workspace [N, H] needed for N > %d", gy * PG_RW);
+    A2CB_REQUIRE(gy <= 256, "gru_persistent: too many environment groups");
     const size_t smem = pg_smem_bytes(d.H);
-    dim3 grid((unsigned)(d.H / PG_KB));
+    dim3 grid((unsigned)ug, (unsigned)gy);
+    {
+        void* cptr = nullptr;
+        cudaError_t e0 = cudaGetSymbolAddress(&cptr, pg_counters);
+        if (e0 == cudaSuccess)
+            e0 = cudaMemsetAsync(reinterpret_cast<unsigned*>(cptr) + (backward ? 256 : 0), 0, 256 * sizeof(unsigned), st);
+        if (e0 != cudaSuccess) { set_error("gru_persistent: counter reset: %s", cudaGetErrorString(e0)); return A2CB_ERR_CUDA; }
+    }
     GruDesc dd = d;
     float* ws = d.dcarry;
     void* args_f[] = {(void*)&dd, (void*)&Whh, (void*)&bhh};
