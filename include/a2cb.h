@@ -206,6 +206,9 @@ typedef struct {
     int32_t N;
     float alpha;
     int32_t act;
+    int32_t o_cb;         /* column blocks: column n -> channel n % o_cb of an output shifted by o_cb_off[n / o_cb]; 0 = off */
+    int32_t pad_;
+    int64_t o_cb_off[4];
 } a2cb_tcx_fwd_t;
 typedef struct {
     a2cb_tcx_view_t A;

@@ -25,7 +25,8 @@ class FwdDesc(ctypes.Structure):
     _fields_ = [("A", View), ("B", c_vp), ("B_lo", c_vp), ("b_rows", c_i64), ("b_cols", c_i64), ("n_kb", c_i32),
                 ("chain", c_i32), ("kb_a", (c_i16 * 4) * MAX_KB), ("kb_b", c_i32 * MAX_KB), ("tiles", Tiling),
                 ("out", c_vp), ("out_lo", c_vp), ("mask", c_vp), ("bias", c_vp), ("o_stride", c_i64 * 5),
-                ("o_base", c_i64), ("o_ext", c_i32 * 5), ("N", c_i32), ("alpha", c_f32), ("act", c_i32)]
+                ("o_base", c_i64), ("o_ext", c_i32 * 5), ("N", c_i32), ("alpha", c_f32), ("act", c_i32),
+                ("o_cb", c_i32), ("pad_", c_i32), ("o_cb_off", c_i64 * 4)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -118,7 +119,8 @@ def _itab(arena, name, values):
 
 
 def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tiles, out, out_lo, o_stride, o_ext, N,
-           alpha=1.0, bias=None, act=0, mask=None, chain=4, o_base=0, flops=0.0):
+           alpha=1.0, bias=None, act=0, mask=None, chain=4, o_base=0, flops=0.0, col_blocks=None):
+    """col_blocks: (block width, [offset per block]) -- see a2cb_tcx_fwd_t.o_cb."""
     assert len(kbs) <= MAX_KB, (name, len(kbs))
 
     def make(arena):
@@ -138,6 +140,10 @@ def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tile
         for i in range(5):
             d.o_stride[i], d.o_ext[i] = os_[i], oe[i]
         d.o_base, d.N, d.alpha, d.act = o_base, N, alpha, act
+        if col_blocks is not None:
+            d.o_cb = col_blocks[0]
+            for i, o in enumerate(col_blocks[1]):
+                d.o_cb_off[i] = o
         return d
     return TcxOp(OP_TCX_FWD, make, name, flops=flops)
 
@@ -358,15 +364,15 @@ class CnnNet(object):
         (g3, g3_lo), (g2, g2_lo), (g1, g1_lo) = self.buf2("g3", B * 49 * 32), self.buf2("g2", B * 81 * 64), \
             self.buf2("g1", B * 400 * 32)
         # ---- data-gradient weight images ----
-        wfd, w3d, w2d = self.image("img_fc_d", 1568, H), self.image("img_c3_d", 64, 288), self.image("img_c2_d", 32, 1024)
+        wfd, w3d, w2d = self.image("img_fc_d", 1568, H), self.image("img_c3_d", 64, 288), self.image("img_c2_d", 128, 256)
         ops += [prep_op("weight_image", wfd, self.P("base.main.7.weight"), 1568, H, self.fc_perm, [k * 1568 for k in range(H)]),
                 # [ci][(ky, kx | co)] = W3[co, ci, ky, kx]
                 prep_op("weight_image", w3d, self.P("base.main.4.weight"), 64, 288, [ci * 9 for ci in range(64)],
                         [co * 576 + ky * 3 + kx for ky in range(3) for kx in range(3) for co in range(32)]),
-                # [ci][(py, px | b, a | co)] = W2[co, ci, py + 2 b, px + 2 a]
-                prep_op("weight_image", w2d, self.P("base.main.2.weight"), 32, 1024, [ci * 16 for ci in range(32)],
-                        [co * 512 + (py + 2 * b) * 4 + (px + 2 * a) for py in range(2) for px in range(2)
-                         for b in range(2) for a in range(2) for co in range(64)])]
+                # [(py, px | ci)][(b, a | co)] = W2[co, ci, py + 2 b, px + 2 a]
+                prep_op("weight_image", w2d, self.P("base.main.2.weight"), 128, 256,
+                        [ci * 16 + py * 4 + px for py in range(2) for px in range(2) for ci in range(32)],
+                        [co * 512 + (2 * b) * 4 + 2 * a for b in range(2) for a in range(2) for co in range(64)])]
         # ---- fc ----
         ops += self.linear_wgrad("fc.wgrad", r["a3"], r["a3_lo"], 1568, gh, gh_lo, H, self.G("base.main.7.weight"),
                                  perm=self.fc_perm)
@@ -383,15 +389,14 @@ class CnnNet(object):
         # ---- conv2 ----
         ops += self.conv2_wgrad(g2, g2_lo)
         ops += self.bias_grad("conv2", g2, B * 81, 64, self.G("base.main.2.bias"))
+        # the four stride-parity classes (py, px) of the transposed convolution read the SAME boxes of g2 (tap (b, a)
+        # -> rows (u - b, v - a)); only the weights differ, so they are 4 x 32 columns of one product
         k = 2
-        for py in range(2):
-            for px in range(2):
-                cls = py * 2 + px
-                kbs = [((c0, -a, -b, 0), cls * 256 + (b * 2 + a) * 64 + c0) for b in range(2) for a in range(2)
-                       for c0 in (0, 32)]
-                ops.append(fwd_op("conv2.dgrad", g2, g2_lo, (64, 9, 9, B), (1, 64, 576, 5184), (32, 10, 10, k), w2d, 32, 1024,
-                                  kbs, tiling(-(-B // k), 3, k), g1, g1_lo, (0, 64, 1280, 12800), (0, 10, 10, B), 32,
-                                  mask=r["a1"], o_base=(py * 20 + px) * 32, flops=2.0 * B * 81 * 64 * 512 / 4))
+        kbs = [((c0, -a, -b, 0), (b * 2 + a) * 64 + c0) for b in range(2) for a in range(2) for c0 in (0, 32)]
+        ops.append(fwd_op("conv2.dgrad", g2, g2_lo, (64, 9, 9, B), (1, 64, 576, 5184), (32, 10, 10, k), w2d, 128, 256,
+                          kbs, tiling(-(-B // k), 3, k), g1, g1_lo, (0, 64, 1280, 12800), (0, 10, 10, B), 128,
+                          mask=r["a1"], flops=2.0 * B * 81 * 64 * 512,
+                          col_blocks=(32, [(py * 20 + px) * 32 for py in range(2) for px in range(2)])))
         # ---- conv1 ----
         ops += self.conv1_wgrad(g1, g1_lo)
         ops += self.bias_grad("conv1", g1, B * 400, 32, self.G("base.main.0.bias"))

@@ -253,11 +253,17 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int i4 = t;
                 const int g1 = base[1] + i1, g2 = base[2] + i2, g3 = base[3] + i3, g4 = base[4] + i4;
                 if (g1 >= p.o_ext[1] || g2 >= p.o_ext[2] || g3 >= p.o_ext[3] || g4 >= p.o_ext[4]) continue;
-                const long off = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
+                const long off0 = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
 #pragma unroll
                 for (int n = 0; n < HALF; n += 4) {
-                    const int ch = n0 + hf * HALF + n;
+                    int ch = n0 + hf * HALF + n;
                     if (ch >= p.N) continue;
+                    long off = off0;
+                    if (p.o_cb > 0) {
+                        const int cb = ch / p.o_cb;
+                        off += p.o_cb_off[cb];
+                        ch -= cb * p.o_cb;
+                    }
                     float4 v = make_float4(acc[mb][n] * p.alpha, acc[mb][n + 1] * p.alpha, acc[mb][n + 2] * p.alpha,
                                            acc[mb][n + 3] * p.alpha);
                     if (p.bias) {
@@ -546,6 +552,7 @@ int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
     A2CB_REQUIRE(p.A.x && p.B && p.B_lo && p.out, "tcx_fwd: null pointer");
     A2CB_REQUIRE(p.n_kb >= 1 && p.n_kb <= TCX_MAX_KB, "tcx_fwd: n_kb = %d out of range", p.n_kb);
     A2CB_REQUIRE(p.N > 0 && p.N % 4 == 0, "tcx_fwd: N = %d must be a positive multiple of 4", p.N);
+    A2CB_REQUIRE(p.o_cb == 0 || (p.o_cb % 4 == 0 && !p.bias && (p.N + p.o_cb - 1) / p.o_cb <= 4), "tcx_fwd: bad column blocks");
     A2CB_REQUIRE(p.tiles.n_tiles > 0 && p.tiles.t_div > 0 && p.tiles.tr_dim >= 1 && p.tiles.tr_dim <= 4 &&
                  p.tiles.tq_dim >= 1 && p.tiles.tq_dim <= 4, "tcx_fwd: bad tiling");
     const long R = (long)p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];

@@ -45,6 +45,12 @@ struct TcxFwd {
     int32_t N;                      // output channels (multiple of 4)
     float alpha;
     int32_t act;                    // 0 none, 1 relu
+    // optional column blocks: output column n belongs to block n / o_cb and is stored at channel n % o_cb of an
+    // output shifted by o_cb_off[block] (the four stride-parity classes of a transposed stride-2 convolution
+    // share their input boxes, so they run as ONE product with 4 x C_in columns).  o_cb = 0: off.
+    int32_t o_cb;
+    int32_t pad_;
+    int64_t o_cb_off[4];
 };
 
 // partial[split][row_off[m] + n * col_stride] = alpha * sum_rows A[row, m] * Bm[row, n]
