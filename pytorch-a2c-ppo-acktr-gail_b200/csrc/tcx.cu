@@ -35,6 +35,7 @@ constexpr int TX_NT = 320;                    // warp 0 TMA, warp 1 MMA, warps 2
 constexpr int TX_EPI0 = 2;                    // first epilogue warp
 constexpr int TX_ROWB = 128;                  // bytes per operand row (32 floats, one swizzle span)
 constexpr int TX_MAX_STAGES = 6;
+constexpr int TX_EPI_STAGING = 8 * 2048 + 2048;   // forward kernel: epilogue transposition slabs + row offsets (1 KiB multiple)
 
 TcxKnobs g_knobs = {1 /* SWIZZLE_128B_BASE32B */, 512, 1024, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
@@ -125,7 +126,9 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int HALF = BN / 2;
     extern __shared__ uint8_t tx_dyn[];
     __shared__ TxBars bars;
-    const uint32_t dyn = (tx_smem(tx_dyn) + 1023u) & ~1023u;
+    const uint32_t dyn0 = (tx_smem(tx_dyn) + 1023u) & ~1023u;
+    uint8_t* stage_base = tx_dyn + (dyn0 - tx_smem(tx_dyn));      // epilogue staging: 8 x 4 KiB slabs + row offsets
+    const uint32_t dyn = dyn0 + TX_EPI_STAGING;                   // operand pipeline stages
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool has_lo = p.A.lo != nullptr;
     const int stage_bytes = A_BYTES * (has_lo ? 2 : 1) + 2 * B_BYTES;
@@ -242,43 +245,89 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 tx_mbar_arrive(&bars.acc_empty[buf]);
             }
+            // Stores: a thread owns a ROW of the accumulator, so writing straight from registers would touch 32
+            // different 128-byte lines per instruction.  Each warp instead transposes 16 rows x CW columns at a time
+            // through its private 2 KiB staging slab (16-byte chunks xor-swizzled by row: conflict-free both ways) and
+            // then writes / reads global memory with LPR lanes per row: whole 128-byte (CW = 32) or 64-byte segments.
+            constexpr int CW = HALF < 32 ? HALF : 32;                 // columns per pass
+            constexpr int LPR = CW / 4;                                // lanes per row in the coalesced phase
+            constexpr int RPI = 32 / LPR;                              // rows per instruction
+            float4* slab = reinterpret_cast<float4*>(stage_base + (warp - TX_EPI0) * 2048);
+            long* rowoff = reinterpret_cast<long*>(stage_base + 8 * 2048) + (warp - TX_EPI0) * 32;
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
-                const int r = mb * 128 + 32 * q + lane;
-                if (r >= R) continue;
-                int t = r;
-                const int i1 = t % b1; t /= b1;
-                const int i2 = t % b2; t /= b2;
-                const int i3 = t % b3; t /= b3;
-                const int i4 = t;
-                const int g1 = base[1] + i1, g2 = base[2] + i2, g3 = base[3] + i3, g4 = base[4] + i4;
-                if (g1 >= p.o_ext[1] || g2 >= p.o_ext[2] || g3 >= p.o_ext[3] || g4 >= p.o_ext[4]) continue;
-                const long off0 = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
+                {
+                    const int r = mb * 128 + 32 * q + lane;
+                    long off0 = -1;
+                    if (r < R) {
+                        int t = r;
+                        const int i1 = t % b1; t /= b1;
+                        const int i2 = t % b2; t /= b2;
+                        const int i3 = t % b3; t /= b3;
+                        const int i4 = t;
+                        const int g1 = base[1] + i1, g2 = base[2] + i2, g3 = base[3] + i3, g4 = base[4] + i4;
+                        if (g1 < p.o_ext[1] && g2 < p.o_ext[2] && g3 < p.o_ext[3] && g4 < p.o_ext[4])
+                            off0 = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
+                    }
+                    __syncwarp();
+                    rowoff[lane] = off0;
+                }
 #pragma unroll
-                for (int n = 0; n < HALF; n += 4) {
-                    int ch = n0 + hf * HALF + n;
-                    if (ch >= p.N) continue;
-                    long off = off0;
-                    if (p.o_cb > 0) {
-                        const int cb = ch / p.o_cb;
-                        off += p.o_cb_off[cb];
-                        ch -= cb * p.o_cb;
+                for (int cc0 = 0; cc0 < HALF; cc0 += CW) {
+#pragma unroll
+                  for (int hr = 0; hr < 2; ++hr) {                       // rows 16 hr .. 16 hr + 15 of this warp's 32
+                    constexpr int NIT = 16 / RPI;
+                    // addresses and the relu' mask of this lane's NIT segments first: the loads are independent of the
+                    // accumulators, so their latency hides behind the slab round trip instead of serialising the stores
+                    long offs[NIT];
+                    int chs[NIT];
+                    float4 mk[NIT];
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) {
+                        const int lr = it * RPI + lane / LPR, c4 = lane % LPR;
+                        long off = rowoff[16 * hr + lr];
+                        int ch = n0 + hf * HALF + cc0 + c4 * 4;
+                        if (ch >= p.N) off = -1;
+                        if (off >= 0 && p.o_cb > 0) {
+                            const int cb = ch / p.o_cb;
+                            off += p.o_cb_off[cb];
+                            ch -= cb * p.o_cb;
+                        }
+                        offs[it] = off; chs[it] = ch;
+                        mk[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (p.mask && off >= 0) mk[it] = __ldg(reinterpret_cast<const float4*>(p.mask + off + ch));
                     }
-                    float4 v = make_float4(acc[mb][n] * p.alpha, acc[mb][n + 1] * p.alpha, acc[mb][n + 2] * p.alpha,
-                                           acc[mb][n + 3] * p.alpha);
-                    if (p.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                    __syncwarp();
+                    if ((lane >> 4) == hr) {
+                        const int lr = lane & 15;
+#pragma unroll
+                        for (int n = 0; n < CW; n += 4) {
+                            float4 v = make_float4(acc[mb][cc0 + n] * p.alpha, acc[mb][cc0 + n + 1] * p.alpha,
+                                                   acc[mb][cc0 + n + 2] * p.alpha, acc[mb][cc0 + n + 3] * p.alpha);
+                            slab[lr * LPR + ((n >> 2) ^ (lr & (LPR - 1)))] = v;
+                        }
                     }
-                    if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                    if (p.mask) {
-                        const float4 m = __ldg(reinterpret_cast<const float4*>(p.mask + off + ch));
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < NIT; ++it) {
+                        const int lr = it * RPI + lane / LPR, c4 = lane % LPR;
+                        const long off = offs[it];
+                        const int ch = chs[it];
+                        if (off < 0) continue;
+                        float4 v = slab[lr * LPR + (c4 ^ (lr & (LPR - 1)))];
+                        if (p.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        }
+                        if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        const float4 m = mk[it];
                         v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
                         v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                        *reinterpret_cast<float4*>(p.out + off + ch) = v;
+                        if (p.out_lo)
+                            *reinterpret_cast<float4*>(p.out_lo + off + ch) = make_float4(tx_lo(v.x), tx_lo(v.y), tx_lo(v.z), tx_lo(v.w));
                     }
-                    *reinterpret_cast<float4*>(p.out + off + ch) = v;
-                    if (p.out_lo)
-                        *reinterpret_cast<float4*>(p.out_lo + off + ch) = make_float4(tx_lo(v.x), tx_lo(v.y), tx_lo(v.z), tx_lo(v.w));
+                  }
                 }
             }
         }
@@ -502,18 +551,19 @@ int view_maps(CUtensorMap* hi, CUtensorMap* lo, const TcxView& v, int swizzle, c
 }
 
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemMax = 232448 - 1024;          // 227 KiB opt-in limit minus the kernels' static shared memory
 
 template <int BN, int MB>
 int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
     const int a_planes = p.A.lo ? 2 : 1;
     const int stage = MB * 128 * TX_ROWB * a_planes + 2 * BN * TX_ROWB;
-    int stages = kSmemBudget / stage;
+    int stages = (kSmemMax - 1024 - TX_EPI_STAGING) / stage;
     stages = stages > TX_MAX_STAGES ? TX_MAX_STAGES : stages;
     A2CB_REQUIRE(stages >= 2, "tcx_fwd: tile does not fit shared memory");
-    const int smem = stages * stage + 1024;
+    const int smem = stages * stage + 1024 + TX_EPI_STAGING;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tcx_fwd_kernel<BN, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+        cudaError_t e = cudaFuncSetAttribute(tcx_fwd_kernel<BN, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
         if (e != cudaSuccess) { set_error("tcx_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return A2CB_ERR_CUDA; }
         attr = true;
     }
