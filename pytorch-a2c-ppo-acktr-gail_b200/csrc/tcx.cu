@@ -90,6 +90,26 @@ __device__ __forceinline__ uint64_t tx_desc(uint32_t addr, uint32_t lbo_bytes, u
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
+// One leader lane of a fully converged warp.  The single-thread instructions (TMA, tcgen05.mma / commit) sit under
+// this predicate while the WHOLE warp runs the surrounding loop: with the loop itself inside `if (lane == 0)` the
+// compiler cannot prove a single active thread and wraps every UTCHMMA / UTMALDG in an elect-and-loop sequence
+// (~6 extra instructions and a branch per MMA -- the issuing thread, not the tensor pipe, became the bottleneck).
+__device__ __forceinline__ bool tx_elect() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// K-major SWIZZLE_128B descriptor with SBO = 1024 B: only the start address varies
+__device__ __forceinline__ uint64_t tx_desc_k(uint32_t addr) {
+    constexpr uint64_t kConst = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    return kConst | (uint64_t)((addr & 0x3FFFF) >> 4);
+}
 __device__ __forceinline__ void tx_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32"
@@ -157,16 +177,17 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem = bars.tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(R * TX_ROWB * (has_lo ? 2 : 1) + 2 * B_BYTES);
-            int it = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                int base[5];
-                tx_tile_base(p.tiles, w / n_n, base);
-                const int n0 = (w % n_n) * BN;
-                for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-                    const int s = it % stages;
-                    if (it >= stages) tx_mbar_wait(&bars.empty[s], (uint32_t)(((it / stages) - 1) & 1));
+        // ===== TMA producer: the whole warp walks the loop, one elected lane issues =====
+        const uint32_t bytes = (uint32_t)(R * TX_ROWB * (has_lo ? 2 : 1) + 2 * B_BYTES);
+        int it = 0, s = 0;
+        uint32_t ph = 0;                                   // parity of the NEXT completion of empty[s] to wait for
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            int base[5];
+            tx_tile_base(p.tiles, w / n_n, base);
+            const int n0 = (w % n_n) * BN;
+            for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
+                if (it >= stages) tx_mbar_wait(&bars.empty[s], ph ^ 1u);
+                if (tx_elect()) {
                     const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
                     const uint32_t sb = sa + (uint32_t)(A_BYTES * (has_lo ? 2 : 1));
                     tx_expect(&bars.full[s], bytes);
@@ -177,21 +198,26 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tx_tma5(sb, &tmB, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
                     tx_tma5(sb + B_BYTES, &tmBlo, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
                 }
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // D fp32, A/B tf32, both K-major, N = BN, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            int it = 0, cc = 0;
-            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const int c = kb / chain, buf = (cc + c) & 1;
-                    const bool first = (kb - c * chain) == 0;
-                    if (first && cc + c >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)((((cc + c) >> 1) - 1) & 1));
-                    tx_mbar_wait(&bars.full[s], (uint32_t)((it / stages) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ===== MMA issuer: the whole warp waits on the barriers, one elected lane issues the MMAs =====
+        // D fp32, A/B tf32, both K-major, N = BN, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        int s = 0, cc = 0;
+        uint32_t ph = 0;                                   // parity of full[s] to wait for
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+            int kc = 0, c = 0;                             // position inside the chain, chain index inside the tile
+            for (int kb = 0; kb < p.n_kb; ++kb) {
+                const int g = cc + c, buf = g & 1;
+                const bool first = kc == 0;
+                if (first && g >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)(((g >> 1) - 1) & 1));
+                tx_mbar_wait(&bars.full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool last = (kb == p.n_kb - 1) || (kc + 1 == chain);
+                if (tx_elect()) {
                     const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
                     const uint32_t sb = sa + (uint32_t)(A_BYTES * (has_lo ? 2 : 1));
 #pragma unroll
@@ -201,19 +227,26 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t o = ks * 32;
-                            const uint64_t dah = tx_desc(ah + o, 16, 1024, 2), dbh = tx_desc(sb + o, 16, 1024, 2);
-                            const uint64_t dbl = tx_desc(sb + B_BYTES + o, 16, 1024, 2);
-                            const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
-                            if (has_lo) tx_mma(d, tx_desc(ah + A_BYTES + o, 16, 1024, 2), dbh, idesc, acc0);
-                            tx_mma(d, dah, dbl, idesc, has_lo ? 1u : acc0);
+                            const uint64_t dah = tx_desc_k(ah + o), dbh = tx_desc_k(sb + o), dbl = tx_desc_k(sb + B_BYTES + o);
+                            if (ks == 0) {
+                                const uint32_t acc0 = first ? 0u : 1u;
+                                if (has_lo) { tx_mma(d, tx_desc_k(ah + A_BYTES + o), dbh, idesc, acc0); tx_mma(d, dah, dbl, idesc, 1u); }
+                                else tx_mma(d, dah, dbl, idesc, acc0);
+                            } else {
+                                if (has_lo) tx_mma(d, tx_desc_k(ah + A_BYTES + o), dbh, idesc, 1u);
+                                tx_mma(d, dah, dbl, idesc, 1u);
+                            }
                             tx_mma(d, dah, dbh, idesc, 1u);
                         }
                     }
                     tx_commit(&bars.empty[s]);
-                    if (kb == p.n_kb - 1 || (kb + 1) % chain == 0) tx_commit(&bars.acc_full[buf]);
+                    if (last) tx_commit(&bars.acc_full[buf]);
                 }
-                cc += n_chains;
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
+                if (last) { kc = 0; ++c; } else ++kc;
             }
+            cc += n_chains;
         }
     } else {
         // ---- drain chains into registers, then the epilogue ----
@@ -395,15 +428,16 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem = bars.tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(R * TX_ROWB * (4 * a_planes + 2 * NBB));
-            int qn = 0;
-            for (int rt = rt0; rt < rt1; ++rt) {
-                int base[5];
-                tx_tile_base(p.rows, rt, base);
-                for (int g = 0; g < G; ++g, ++qn) {
-                    const int s = qn % stages;
-                    if (qn >= stages) tx_mbar_wait(&bars.empty[s], (uint32_t)(((qn / stages) - 1) & 1));
+        // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
+        const uint32_t bytes = (uint32_t)(R * TX_ROWB * (4 * a_planes + 2 * NBB));
+        int qn = 0, s = 0;
+        uint32_t ph = 0;
+        for (int rt = rt0; rt < rt1; ++rt) {
+            int base[5];
+            tx_tile_base(p.rows, rt, base);
+            for (int g = 0; g < G; ++g, ++qn) {
+                if (qn >= stages) tx_mbar_wait(&bars.empty[s], ph ^ 1u);
+                if (tx_elect()) {
                     const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
                     const uint32_t sb = sa + (uint32_t)(4 * a_planes * box_bytes);
                     tx_expect(&bars.full[s], bytes);
@@ -422,43 +456,57 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tx_tma5(sb + (uint32_t)((NBB + j) * box_bytes), &tmBlo, &bars.full[s], c0, c1, c2, c3, c4);
                     }
                 }
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // D fp32, A/B tf32, both MN-major, N = BN, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t lt = (uint32_t)knobs.mn_layout_type, sbo = (uint32_t)knobs.mn_sbo_bytes;
-            const int ksteps = R8 / 8;
-            int qn = 0;
-            for (int i = 0; i < n_rt; ++i) {
-                const int c = i / chain, buf = c & 1;
-                const bool first = (i - c * chain) == 0;
-                if (first && c >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)(((c >> 1) - 1) & 1));
-                for (int g = 0; g < G; ++g, ++qn) {
-                    const int s = qn % stages;
-                    tx_mbar_wait(&bars.full[s], (uint32_t)((qn / stages) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ===== MMA issuer (whole warp waits, one elected lane issues) =====
+        // D fp32, A/B tf32, both MN-major, N = BN, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // MN-major descriptors differ only in the start address: LBO = distance between 32-channel boxes
+        const uint64_t dconst = tx_desc(0, (uint32_t)box_bytes, (uint32_t)knobs.mn_sbo_bytes, (uint32_t)knobs.mn_layout_type);
+        const uint32_t kstep16 = (uint32_t)knobs.mn_kstep_bytes >> 4;
+        const int ksteps = R8 / 8;
+        int s = 0, kc = 0, c = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < n_rt; ++i) {
+            const int buf = c & 1;
+            const bool first = kc == 0;
+            const bool last = (i == n_rt - 1) || (kc + 1 == chain);
+            if (first && c >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)(((c >> 1) - 1) & 1));
+            for (int g = 0; g < G; ++g) {
+                tx_mbar_wait(&bars.full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tx_elect()) {
                     const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
-                    const uint32_t sal = sa + (uint32_t)(4 * box_bytes);
+                    uint64_t dah = dconst | (uint64_t)((sa & 0x3FFFF) >> 4);
+                    uint64_t dal = dconst | (uint64_t)(((sa + (uint32_t)(4 * box_bytes)) & 0x3FFFF) >> 4);
                     const uint32_t sb = sa + (uint32_t)(4 * a_planes * box_bytes);
-                    const uint32_t sbl = sb + (uint32_t)(NBB * box_bytes);
+                    uint64_t dbh = dconst | (uint64_t)((sb & 0x3FFFF) >> 4);
+                    uint64_t dbl = dconst | (uint64_t)(((sb + (uint32_t)(NBB * box_bytes)) & 0x3FFFF) >> 4);
                     const uint32_t d = tmem + (uint32_t)(buf * G * BN + g * BN);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t o = (uint32_t)(ks * knobs.mn_kstep_bytes);
-                        const uint64_t dah = tx_desc(sa + o, (uint32_t)box_bytes, sbo, lt);
-                        const uint64_t dbh = tx_desc(sb + o, (uint32_t)box_bytes, sbo, lt);
-                        const uint64_t dbl = tx_desc(sbl + o, (uint32_t)box_bytes, sbo, lt);
-                        const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
-                        if (has_lo) tx_mma(d, tx_desc(sal + o, (uint32_t)box_bytes, sbo, lt), dbh, idesc, acc0);
-                        tx_mma(d, dah, dbl, idesc, has_lo ? 1u : acc0);
+                    if (has_lo) {
+                        tx_mma(d, dal, dbh, idesc, first ? 0u : 1u);
+                        tx_mma(d, dah, dbl, idesc, 1u);
+                    } else {
+                        tx_mma(d, dah, dbl, idesc, first ? 0u : 1u);
+                    }
+                    tx_mma(d, dah, dbh, idesc, 1u);
+                    for (int ks = 1; ks < ksteps; ++ks) {
+                        dah += kstep16; dal += kstep16; dbh += kstep16; dbl += kstep16;
+                        if (has_lo) tx_mma(d, dal, dbh, idesc, 1u);
+                        tx_mma(d, dah, dbl, idesc, 1u);
                         tx_mma(d, dah, dbh, idesc, 1u);
                     }
                     tx_commit(&bars.empty[s]);
+                    if (last && g == G - 1) tx_commit(&bars.acc_full[buf]);
                 }
-                if (i == n_rt - 1 || (i + 1) % chain == 0) tx_commit(&bars.acc_full[buf]);
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
+            if (last) { kc = 0; ++c; } else ++kc;
         }
     } else {
         const int q = warp & 3, hf = (warp - TX_EPI0) >> 2;
