@@ -391,7 +391,7 @@ class CnnNet(object):
         ops += self.bias_grad("conv2", g2, B * 81, 64, self.G("base.main.2.bias"))
         # the four stride-parity classes (py, px) of the transposed convolution read the SAME boxes of g2 (tap (b, a)
         # -> rows (u - b, v - a)); only the weights differ, so they are 4 x 32 columns of one product
-        k = 2
+        k = 1          # 100 rows / tile: one M block, 64 KiB stages -> a 3-deep pipeline (2 images would leave only 2 stages)
         kbs = [((c0, -a, -b, 0), (b * 2 + a) * 64 + c0) for b in range(2) for a in range(2) for c0 in (0, 32)]
         ops.append(fwd_op("conv2.dgrad", g2, g2_lo, (64, 9, 9, B), (1, 64, 576, 5184), (32, 10, 10, k), w2d, 128, 256,
                           kbs, tiling(-(-B // k), 3, k), g1, g1_lo, (0, 64, 1280, 12800), (0, 10, 10, B), 128,

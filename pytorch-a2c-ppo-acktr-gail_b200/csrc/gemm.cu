@@ -389,10 +389,46 @@ reduce_splits_kernel(float* __restrict__ dst, const float* __restrict__ src, lon
     dst[e] = accumulate ? beta * dst[e] + s : s;
 }
 
+// Same fold for MANY splits (weight-gradient slabs of 148 CTAs, bias column sums of ~1000 blocks): 32 consecutive
+// elements per block, 8 split lanes each summing every 8th slab (coalesced 128-byte rows, 8 x fewer dependent
+// loads per thread), then a fixed-order shared-memory fold -- still deterministic.
+__global__ void __launch_bounds__(256)
+reduce_splits_wide_kernel(float* __restrict__ dst, const float* __restrict__ src, long count, long stride,
+                          int splits, int accumulate, const float* __restrict__ bias, int ncols, int act, float beta) {
+    __shared__ float red[8][32];
+    const int el = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const long e = (long)blockIdx.x * 32 + el;
+    float s0 = 0.f, s1 = 0.f;
+    if (e < count) {
+        int k = sl;
+        for (; k + 8 < splits; k += 16) {
+            s0 += __ldg(src + (long)k * stride + e);
+            s1 += __ldg(src + (long)(k + 8) * stride + e);
+        }
+        if (k < splits) s0 += __ldg(src + (long)k * stride + e);
+    }
+    red[sl][el] = s0 + s1;
+    __syncthreads();
+    if (sl == 0 && e < count) {
+        float s = red[0][el];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) s += red[j][el];
+        if (bias) s += __ldg(bias + (e % ncols));
+        if (act == 1) s = fmaxf(s, 0.f);
+        else if (act == 2) s = tanhf(s);
+        dst[e] = accumulate ? beta * dst[e] + s : s;
+    }
+}
+
 int reduce_splits(float* dst, const float* src, long count, long stride, int splits, int accumulate,
                   const float* bias, int ncols, int act, float beta, cudaStream_t st) {
     if (count == 0) return A2CB_OK;
     A2CB_REQUIRE(!bias || ncols > 0, "reduce_splits: bias needs ncols");
+    if (splits >= 32) {
+        reduce_splits_wide_kernel<<<(unsigned)((count + 31) / 32), 256, 0, st>>>(dst, src, count, stride, splits, accumulate,
+                                                                                  bias, ncols, act, beta);
+        return check_launch("reduce_splits");
+    }
     reduce_splits_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(dst, src, count, stride, splits, accumulate,
                                                                           bias, ncols, act, beta);
     return check_launch("reduce_splits");

@@ -35,7 +35,7 @@ constexpr int TX_NT = 320;                    // warp 0 TMA, warp 1 MMA, warps 2
 constexpr int TX_EPI0 = 2;                    // first epilogue warp
 constexpr int TX_ROWB = 128;                  // bytes per operand row (32 floats, one swizzle span)
 constexpr int TX_MAX_STAGES = 6;
-constexpr int TX_EPI_STAGING = 8 * 2048 + 2048;   // forward kernel: epilogue transposition slabs + row offsets (1 KiB multiple)
+constexpr int TX_EPI_STAGING = 8 * 2048 + 4096;   // forward kernel: epilogue transposition slabs + row offsets (1 KiB multiple)
 
 TcxKnobs g_knobs = {1 /* SWIZZLE_128B_BASE32B */, 512, 1024, (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B};
 
@@ -262,6 +262,41 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
                 for (int n = 0; n < HALF; ++n) acc[mb][n] = 0.f;
+            // output offsets of this thread's rows (both M blocks), shared with the warp through shared memory; the
+            // relu' mask lines of the tile are pulled into L2 now, while the MMAs of the tile are still running
+            long* rowoff = reinterpret_cast<long*>(stage_base + 8 * 2048) + (warp - TX_EPI0) * 64;
+            __syncwarp();
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const int r = mb * 128 + 32 * q + lane;
+                long off0 = -1;
+                if (r < R) {
+                    int t = r;
+                    const int i1 = t % b1; t /= b1;
+                    const int i2 = t % b2; t /= b2;
+                    const int i3 = t % b3; t /= b3;
+                    const int i4 = t;
+                    const int g1 = base[1] + i1, g2 = base[2] + i2, g3 = base[3] + i3, g4 = base[4] + i4;
+                    if (g1 < p.o_ext[1] && g2 < p.o_ext[2] && g3 < p.o_ext[3] && g4 < p.o_ext[4])
+                        off0 = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
+                }
+                rowoff[mb * 32 + lane] = off0;
+                if (p.mask && off0 >= 0) {
+#pragma unroll
+                    for (int c0 = 0; c0 < HALF; c0 += 32) {
+                        int ch = n0 + hf * HALF + c0;
+                        if (ch >= p.N) continue;
+                        long off = off0;
+                        if (p.o_cb > 0) {
+                            const int cb = ch / p.o_cb;
+                            off += p.o_cb_off[cb];
+                            ch -= cb * p.o_cb;
+                        }
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask + off + ch));
+                    }
+                }
+            }
+            __syncwarp();
             for (int c = 0; c < n_chains; ++c, ++cc) {
                 const int buf = cc & 1;
                 tx_mbar_wait(&bars.acc_full[buf], (uint32_t)((cc >> 1) & 1));
@@ -286,25 +321,8 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr int LPR = CW / 4;                                // lanes per row in the coalesced phase
             constexpr int RPI = 32 / LPR;                              // rows per instruction
             float4* slab = reinterpret_cast<float4*>(stage_base + (warp - TX_EPI0) * 2048);
-            long* rowoff = reinterpret_cast<long*>(stage_base + 8 * 2048) + (warp - TX_EPI0) * 32;
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
-                {
-                    const int r = mb * 128 + 32 * q + lane;
-                    long off0 = -1;
-                    if (r < R) {
-                        int t = r;
-                        const int i1 = t % b1; t /= b1;
-                        const int i2 = t % b2; t /= b2;
-                        const int i3 = t % b3; t /= b3;
-                        const int i4 = t;
-                        const int g1 = base[1] + i1, g2 = base[2] + i2, g3 = base[3] + i3, g4 = base[4] + i4;
-                        if (g1 < p.o_ext[1] && g2 < p.o_ext[2] && g3 < p.o_ext[3] && g4 < p.o_ext[4])
-                            off0 = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
-                    }
-                    __syncwarp();
-                    rowoff[lane] = off0;
-                }
 #pragma unroll
                 for (int cc0 = 0; cc0 < HALF; cc0 += CW) {
 #pragma unroll
@@ -318,7 +336,7 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int it = 0; it < NIT; ++it) {
                         const int lr = it * RPI + lane / LPR, c4 = lane % LPR;
-                        long off = rowoff[16 * hr + lr];
+                        long off = rowoff[mb * 32 + 16 * hr + lr];
                         int ch = n0 + hf * HALF + cc0 + c4 * 4;
                         if (ch >= p.N) off = -1;
                         if (off >= 0 && p.o_cb > 0) {
