@@ -291,6 +291,8 @@ class CnnNet(object):
                           (0, 20, 20, B), 32, alpha=1.0 / 255.0, bias=self.P("base.main.0.bias"), act=1,
                           flops=2.0 * B * 400 * 32 * 256))
         # ---- conv2 (stride 2): parity view (px|c, X, py, Y, n) of a1, tile = 3 images ----
+        # (2 images / 3 stages measured slower: these layers are bound by bytes moved into shared memory, and smaller
+        # tiles re-load the weight tile more often)
         kbs = [(((kx % 2) * 32, kx // 2, ky % 2, ky // 2), (ky * 4 + kx) * 32) for ky in range(4) for kx in range(4)]
         k = 3
         ops.append(fwd_op("conv2.fwd", a1, a1_lo, (64, 10, 2, 10, B), (1, 64, 640, 1280, 12800), (32, 9, 1, 9, k), w2, 64, 512,

@@ -141,11 +141,14 @@ __global__ void __launch_bounds__(TX_NT, 1)
 tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ TcxFwd p, const int stages) {
-    constexpr int A_BYTES = MB * 128 * TX_ROWB;             // one plane of the A tile
     constexpr int B_BYTES = BN * TX_ROWB;
     constexpr int HALF = BN / 2;
     extern __shared__ uint8_t tx_dyn[];
     __shared__ TxBars bars;
+    // one plane of the A tile: the R rows TMA writes, rounded up to a swizzle atom (8 rows).  The last M block's MMAs
+    // read up to 128 * MB rows, i.e. run on into the following operand planes of the stage: finite garbage that only
+    // reaches accumulator rows >= R, which are never stored.
+    const int A_BYTES = ((p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4] + 7) & ~7) * TX_ROWB;
     const uint32_t dyn0 = (tx_smem(tx_dyn) + 1023u) & ~1023u;
     uint8_t* stage_base = tx_dyn + (dyn0 - tx_smem(tx_dyn));      // epilogue staging: 8 x 4 KiB slabs + row offsets
     const uint32_t dyn = dyn0 + TX_EPI_STAGING;                   // operand pipeline stages
@@ -622,11 +625,14 @@ constexpr int kSmemMax = 232448 - 1024;          // 227 KiB opt-in limit minus t
 template <int BN, int MB>
 int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
     const int a_planes = p.A.lo ? 2 : 1;
-    const int stage = MB * 128 * TX_ROWB * a_planes + 2 * BN * TX_ROWB;
-    int stages = (kSmemMax - 1024 - TX_EPI_STAGING) / stage;
+    const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
+    const int stage = ((R + 7) & ~7) * TX_ROWB * a_planes + 2 * BN * TX_ROWB;
+    // the last stage's M-block reads may run past its own end: keep that many rows of slack inside the allocation
+    const int slack = (MB * 128 - ((R + 7) & ~7)) * TX_ROWB;
+    int stages = (kSmemMax - 1024 - TX_EPI_STAGING - slack) / stage;
     stages = stages > TX_MAX_STAGES ? TX_MAX_STAGES : stages;
     A2CB_REQUIRE(stages >= 2, "tcx_fwd: tile does not fit shared memory");
-    const int smem = stages * stage + 1024 + TX_EPI_STAGING;
+    const int smem = stages * stage + 1024 + TX_EPI_STAGING + slack;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(tcx_fwd_kernel<BN, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
