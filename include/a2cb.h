@@ -207,8 +207,9 @@ typedef struct {
     float alpha;
     int32_t act;
     int32_t o_cb;         /* column blocks: column n -> channel n % o_cb of an output shifted by o_cb_off[n / o_cb]; 0 = off */
-    int32_t pad_;
+    int32_t gather_dim;   /* image gather: A coordinate of this dimension -> gather_idx[coordinate]; 0 = off */
     int64_t o_cb_off[4];
+    const int64_t* gather_idx; /* device list (minibatch rows inside a whole-rollout tensor, storage.py:127,181) */
 } a2cb_tcx_fwd_t;
 typedef struct {
     a2cb_tcx_view_t A;
@@ -225,6 +226,9 @@ typedef struct {
     int64_t col_stride;
     int32_t n_cols;
     float alpha;
+    const int64_t* gather_idx; /* image gather of the A boxes, see a2cb_tcx_fwd_t */
+    int32_t gather_dim;
+    int32_t pad_;
 } a2cb_tcx_wgrad_t;
 int a2cb_tcx_fwd(const a2cb_tcx_fwd_t* desc, a2cb_stream_t stream);
 int a2cb_tcx_wgrad(const a2cb_tcx_wgrad_t* desc, a2cb_stream_t stream);

@@ -362,12 +362,13 @@ class NetBuilder(object):
     """Builds forward / backward plan lists for one policy spec and one batch size."""
 
     def __init__(self, spec, layout, B, obs_buf, obs_code, gather, tag, seq=None, masks=("masks_in", 0),
-                 hxs=("hxs_in", 0), keep_gates=True, allow_tcx=True):
+                 hxs=("hxs_in", 0), keep_gates=True, allow_tcx=True, full_rows=0):
         self.spec, self.L, self.B = spec, layout, B
         # recurrent policies see the batch as a [T, N] sequence, rows time-major (model.py:119-126)
         self.seqT, self.seqN = seq if seq is not None else (1, B)
         assert self.seqT * self.seqN == B
         self.masks_ref, self.hxs_ref, self.keep_gates = masks, hxs, keep_gates
+        self.full_rows = full_rows  # rows of the observation source when it is a whole rollout read through a row list
         self.obs = obs_buf          # arena name of the observation source
         self.obs_code = obs_code    # a_dtype of the first layer: 0 raw fp32, 1 uint8/255, 2 fp32/255
         self.gather = gather
@@ -885,7 +886,7 @@ class PolicyRuntime(object):
             else:
                 self.arena.bind("hxs_mb", storage.recurrent_hidden_states[0].contiguous().view(-1))
             kw = dict(seq=seq, masks=("masks_st", 0), hxs=("hxs_mb", 0))
-        nb = NetBuilder(s, self.L, mbs, "obs_st", code, use_idx, tag, **kw)
+        nb = NetBuilder(s, self.L, mbs, "obs_st", code, use_idx, tag, full_rows=T * N if use_idx else 0, **kw)
         fwd = nb.forward_plans()
         bwd = nb.backward_plans() if with_backward else []
         if not with_backward:
@@ -922,6 +923,13 @@ class PolicyRuntime(object):
         prog.loss_desc = d
         prog.loss_out = lo
         prog.builder = nb
+        # once-per-update work (frame re-layout of the whole rollout): the caller runs it before the first minibatch
+        prog.prologue = None
+        if nb.tcx is not None and nb.tcx.prologue:
+            prog.prologue = Program(self.dev)
+            for p in nb.tcx.prologue:
+                prog.prologue.add_plan(p, self.arena)
+            prog.prologue.finalize()
         return prog
 
     def acktr_programs(self, storage, hyper, noise, inv_B=None):

@@ -26,14 +26,15 @@ class FwdDesc(ctypes.Structure):
                 ("chain", c_i32), ("kb_a", (c_i16 * 4) * MAX_KB), ("kb_b", c_i32 * MAX_KB), ("tiles", Tiling),
                 ("out", c_vp), ("out_lo", c_vp), ("mask", c_vp), ("bias", c_vp), ("o_stride", c_i64 * 5),
                 ("o_base", c_i64), ("o_ext", c_i32 * 5), ("N", c_i32), ("alpha", c_f32), ("act", c_i32),
-                ("o_cb", c_i32), ("pad_", c_i32), ("o_cb_off", c_i64 * 4)]
+                ("o_cb", c_i32), ("gather_dim", c_i32), ("o_cb_off", c_i64 * 4), ("gather_idx", c_vp)]
 
 
 class WgradDesc(ctypes.Structure):
     _fields_ = [("A", View), ("Bm", View), ("G", c_i32), ("nbb", c_i32), ("ga", ((c_i16 * 4) * 4) * MAX_G),
                 ("gb", (c_i16 * 4) * 8), ("rows", Tiling), ("splits", c_i32), ("chain", c_i32), ("ot_a", c_i32),
                 ("ot_b", c_i32), ("ot_a_step", c_i32), ("ot_b_step", c_i32), ("partial", c_vp), ("split_stride", c_i64),
-                ("row_off", c_vp), ("col_stride", c_i64), ("n_cols", c_i32), ("alpha", c_f32)]
+                ("row_off", c_vp), ("col_stride", c_i64), ("n_cols", c_i32), ("alpha", c_f32), ("gather_idx", c_vp),
+                ("gather_dim", c_i32), ("pad_", c_i32)]
 
 
 class LoDesc(ctypes.Structure):
@@ -119,7 +120,7 @@ def _itab(arena, name, values):
 
 
 def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tiles, out, out_lo, o_stride, o_ext, N,
-           alpha=1.0, bias=None, act=0, mask=None, chain=4, o_base=0, flops=0.0, col_blocks=None):
+           alpha=1.0, bias=None, act=0, mask=None, chain=4, o_base=0, flops=0.0, col_blocks=None, gather_dim=0):
     """col_blocks: (block width, [offset per block]) -- see a2cb_tcx_fwd_t.o_cb."""
     assert len(kbs) <= MAX_KB, (name, len(kbs))
 
@@ -144,13 +145,15 @@ def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tile
             d.o_cb = col_blocks[0]
             for i, o in enumerate(col_blocks[1]):
                 d.o_cb_off[i] = o
+        d.gather_dim = gather_dim
+        d.gather_idx = 1 if gather_dim else None          # placeholder: a2cb_run_ops substitutes the runtime row list
         return d
-    return TcxOp(OP_TCX_FWD, make, name, flops=flops)
+    return TcxOp(OP_TCX_FWD, make, name, flops=flops, runtime_idx=bool(gather_dim))
 
 
 def wgrad_op(name, A, A_lo, a_dims, a_strides, a_box, Bm, Bm_lo, b_dims, b_strides, b_box, groups, b_boxes, rows, splits,
              chain, ot_a, ot_b, ot_a_step, ot_b_step, partial, split_stride, row_off, col_stride, n_cols, alpha=1.0,
-             flops=0.0):
+             flops=0.0, gather_dim=0):
     """groups: per accumulator group, 4 coordinate-offset tuples (dims 0..3); b_boxes: per 32-channel box of Bm one
     tuple; row_off: list of ot_a * G * 128 element offsets (-1 = unused accumulator row)."""
     G = len(groups)
@@ -173,8 +176,10 @@ def wgrad_op(name, A, A_lo, a_dims, a_strides, a_box, Bm, Bm_lo, b_dims, b_strid
         d.partial, d.split_stride = arena.ptr(partial), split_stride
         d.row_off = _itab(arena, partial[0] + "_rowoff", row_off)
         d.col_stride, d.n_cols, d.alpha = col_stride, n_cols, alpha
+        d.gather_dim = gather_dim
+        d.gather_idx = 1 if gather_dim else None
         return d
-    return TcxOp(OP_TCX_WGRAD, make, name, flops=flops)
+    return TcxOp(OP_TCX_WGRAD, make, name, flops=flops, runtime_idx=bool(gather_dim))
 
 
 def lo_op(name, x, lo, n):
@@ -236,6 +241,11 @@ class CnnNet(object):
         self.nb = nb
         self.B, self.H = nb.B, nb.spec.hidden
         self.frames_lo = nb.obs_code != 1          # fp32 frames are not exact in TF32: they get a lo plane too
+        # Training programs read minibatch rows of the rollout buffer through a runtime row list.  The frames do
+        # not change during an update, so their space-to-depth re-layout is done ONCE per update for the whole
+        # rollout (`prologue`) and conv1 gathers its images from it through the row list (TMA coordinates).
+        self.full_rows = getattr(nb, "full_rows", 0) if nb.gather else 0
+        self.prologue = []
 
     # -- small helpers ------------------------------------------------------------------------------
     def buf2(self, name, numel):
@@ -257,8 +267,19 @@ class CnnNet(object):
     def forward(self):
         nb, B, H = self.nb, self.B, self.H
         ops = []
-        x0 = nb.buf("x0", B * 441 * 64)
-        x0_lo = nb.buf("x0_lo", B * 441 * 64) if self.frames_lo else None
+        if self.full_rows:
+            nb.sizes["x0_full"] = self.full_rows * 441 * 64
+            x0 = ("x0_full", 0)
+            x0_lo = None
+            if self.frames_lo:
+                nb.sizes["x0_full_lo"] = self.full_rows * 441 * 64
+                x0_lo = ("x0_full_lo", 0)
+        else:
+            x0 = nb.buf("x0", B * 441 * 64)
+            x0_lo = nb.buf("x0_lo", B * 441 * 64) if self.frames_lo else None
+        n_img = self.full_rows or B                  # images in the tensor conv1 reads
+        gd = 3 if self.full_rows else 0              # ... gathered through the row list along the image dimension
+        self.x0_imgs, self.x0_gather = n_img, gd
         (a1, a1_lo), (a2, a2_lo) = self.buf2("a1", B * 400 * 32), self.buf2("a2", B * 81 * 64)
         (a3, a3_lo), (h, h_lo) = self.buf2("a3", B * 49 * 32), self.buf2("h", B * H)
         self.refs = dict(x0=x0, x0_lo=x0_lo, a1=a1, a1_lo=a1_lo, a2=a2, a2_lo=a2_lo, a3=a3, a3_lo=a3_lo, h=h, h_lo=h_lo)
@@ -281,15 +302,18 @@ class CnnNet(object):
         frames, is_u8, gather = (nb.obs, 0), nb.obs_code == 1, nb.gather
 
         def make_s2d(arena):
-            return S2dDesc(arena.ptr(x0), arena.ptr(x0_lo), arena.ptr(frames), None, 1 if is_u8 else 0, B, 4, 84, 84, 4)
-        ops.append(TcxOp(OP_TCX_S2D, make_s2d, "frames_s2d", runtime_idx=gather))
+            return S2dDesc(arena.ptr(x0), arena.ptr(x0_lo), arena.ptr(frames), None, 1 if is_u8 else 0, n_img, 4, 84, 84, 4)
+        if self.full_rows:
+            self.prologue.append(TcxOp(OP_TCX_S2D, make_s2d, "frames_s2d"))
+        else:
+            ops.append(TcxOp(OP_TCX_S2D, make_s2d, "frames_s2d", runtime_idx=gather))
 
         # ---- conv1: 2 x 2 taps x 64 channels, tile = 12 output rows of one image ----
         kbs = [((c0, bx, by, 0), (by * 2 + bx) * 64 + c0) for by in range(2) for bx in range(2) for c0 in (0, 32)]
-        ops.append(fwd_op("conv1.fwd", x0, x0_lo, (64, 21, 21, B), (1, 64, 64 * 21, 64 * 441), (32, 20, 12, 1), w1, 32, 256,
+        ops.append(fwd_op("conv1.fwd", x0, x0_lo, (64, 21, 21, n_img), (1, 64, 64 * 21, 64 * 441), (32, 20, 12, 1), w1, 32, 256,
                           kbs, tiling(2 * B, 2, 12, t_div=2, tq_dim=3, tq_step=1), a1, a1_lo, (0, 32, 640, 12800),
                           (0, 20, 20, B), 32, alpha=1.0 / 255.0, bias=self.P("base.main.0.bias"), act=1,
-                          flops=2.0 * B * 400 * 32 * 256))
+                          flops=2.0 * B * 400 * 32 * 256, gather_dim=gd))
         # ---- conv2 (stride 2): parity view (px|c, X, py, Y, n) of a1, tile = 3 images ----
         # (2 images / 3 stages measured slower: these layers are bound by bytes moved into shared memory, and smaller
         # tiles re-load the weight tile more often)
@@ -456,10 +480,11 @@ class CnnNet(object):
         n_rt = (20 // yr) * B
         splits, per = split_rows(n_rt, 148)
         part = self.nb.buf("wpart_conv1", splits * 32 * 256)
-        op = wgrad_op("conv1.wgrad", r["x0"], r["x0_lo"], (64, 21, 21, B), (1, 64, 64 * 21, 64 * 441), (32, 20, yr, 1), g1, g1_lo,
-                      (32, 20, 20, B), (1, 32, 640, 12800), (32, 20, yr, 1), groups, [(0, 0, 0, 0)],
+        op = wgrad_op("conv1.wgrad", r["x0"], r["x0_lo"], (64, 21, 21, self.x0_imgs), (1, 64, 64 * 21, 64 * 441), (32, 20, yr, 1),
+                      g1, g1_lo, (32, 20, 20, B), (1, 32, 640, 12800), (32, 20, yr, 1), groups, [(0, 0, 0, 0)],
                       tiling(n_rt, 2, yr, t_div=20 // yr, tq_dim=3, tq_step=1), splits, 6 if yr == 4 else 12, 1, 1, 0, 0, part,
-                      32 * 256, row_off, 256, 32, alpha=1.0 / 255.0, flops=2.0 * B * 400 * 32 * 256)
+                      32 * 256, row_off, 256, 32, alpha=1.0 / 255.0, flops=2.0 * B * 400 * 32 * 256,
+                      gather_dim=self.x0_gather)
         return [op, self.fold("conv1.wgrad", part, self.G("base.main.0.weight"), 32 * 256, splits)]
 
     # -- GRU linear parts (the recurrence itself is csrc/gru_persistent.cu) ---------------------------

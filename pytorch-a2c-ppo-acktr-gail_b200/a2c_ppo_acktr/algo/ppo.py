@@ -104,11 +104,16 @@ class PPO():
             prog.finalize()
             opt.finalize()
             self._prog, self._opt_prog, self._prog_key = prog, opt, key
+        pro = getattr(self._prog, "prologue", None)
+        if pro is not None and getattr(self, "_prologue_serial", None) != getattr(self, "_update_serial", 0):
+            pro.run()                       # once per update: the rollout's frames do not change between minibatches
+            self._prologue_serial = getattr(self, "_update_serial", 0)
         return self._prog, self._opt_prog
 
     def update(self, rollouts):
         policy = self.actor_critic
         rt = policy.runtime()
+        self._update_serial = getattr(self, "_update_serial", 0) + 1
         T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         if policy.is_recurrent:
             if self.shard is not None:
@@ -238,6 +243,7 @@ class PPO():
         environment sets gives the same result; the partition is stratified by rank, not one global
         randperm.)  Yields the tensors to sum-all-reduce, like `sharded_steps`."""
         sh = self.shard
+        self._update_serial = getattr(self, "_update_serial", 0) + 1
         T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         assert n_loc == sh.n_local and n_loc >= self.num_mini_batch
         E = n_loc // self.num_mini_batch
@@ -278,6 +284,7 @@ class PPO():
         collective can be real NCCL (`_update_sharded`) or, in single-GPU tests, an emulation that
         steps several ranks in lock-step."""
         sh = self.shard
+        self._update_serial = getattr(self, "_update_serial", 0) + 1
         T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         assert n_loc == sh.n_local, "rollouts hold %d environments, the shard declares %d" % (n_loc, sh.n_local)
         batch_global = T * sh.n_total

@@ -253,12 +253,20 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
                 rc = gru_persistent(op.kind == A2CB_OP_GRU_SEQ_BWD, d, q.W_hh, q.b_hh, st);
                 break;
             }
-            case A2CB_OP_TCX_FWD:
-                rc = tcx_fwd(*reinterpret_cast<const TcxFwd*>(op.desc), st);
+            case A2CB_OP_TCX_FWD: {
+                if (!rt) { rc = tcx_fwd(*reinterpret_cast<const TcxFwd*>(op.desc), st); break; }
+                TcxFwd d = *reinterpret_cast<const TcxFwd*>(op.desc);
+                d.gather_idx = idx;
+                rc = tcx_fwd(d, st);
                 break;
-            case A2CB_OP_TCX_WGRAD:
-                rc = tcx_wgrad(*reinterpret_cast<const TcxWgrad*>(op.desc), st);
+            }
+            case A2CB_OP_TCX_WGRAD: {
+                if (!rt) { rc = tcx_wgrad(*reinterpret_cast<const TcxWgrad*>(op.desc), st); break; }
+                TcxWgrad d = *reinterpret_cast<const TcxWgrad*>(op.desc);
+                d.gather_idx = idx;
+                rc = tcx_wgrad(d, st);
                 break;
+            }
             case A2CB_OP_TCX_LO: {
                 const a2cb_tcx_lo_t& q = *reinterpret_cast<const a2cb_tcx_lo_t*>(op.desc);
                 rc = tcx_lo_plane(q.lo, q.x, (long)q.n, st);

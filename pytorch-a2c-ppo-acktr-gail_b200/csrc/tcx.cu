@@ -187,6 +187,7 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             int base[5];
             tx_tile_base(p.tiles, w / n_n, base);
+            if (p.gather_dim > 0) base[p.gather_dim] = (int)__ldg(p.gather_idx + base[p.gather_dim]);
             const int n0 = (w % n_n) * BN;
             for (int kb = 0; kb < p.n_kb; ++kb, ++it) {
                 if (it >= stages) tx_mbar_wait(&bars.empty[s], ph ^ 1u);
@@ -454,8 +455,11 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int qn = 0, s = 0;
         uint32_t ph = 0;
         for (int rt = rt0; rt < rt1; ++rt) {
-            int base[5];
+            int base[5], ba[5];
             tx_tile_base(p.rows, rt, base);
+#pragma unroll
+            for (int d = 0; d < 5; ++d) ba[d] = base[d];
+            if (p.gather_dim > 0) ba[p.gather_dim] = (int)__ldg(p.gather_idx + base[p.gather_dim]);
             for (int g = 0; g < G; ++g, ++qn) {
                 if (qn >= stages) tx_mbar_wait(&bars.empty[s], ph ^ 1u);
                 if (tx_elect()) {
@@ -464,8 +468,8 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tx_expect(&bars.full[s], bytes);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int c0 = p.ga[g][j][0] + ota * p.ot_a_step, c1 = p.ga[g][j][1] + base[1],
-                                  c2 = p.ga[g][j][2] + base[2], c3 = p.ga[g][j][3] + base[3], c4 = base[4];
+                        const int c0 = p.ga[g][j][0] + ota * p.ot_a_step, c1 = p.ga[g][j][1] + ba[1],
+                                  c2 = p.ga[g][j][2] + ba[2], c3 = p.ga[g][j][3] + ba[3], c4 = ba[4];
                         tx_tma5(sa + (uint32_t)(j * box_bytes), &tmA, &bars.full[s], c0, c1, c2, c3, c4);
                         if (has_lo) tx_tma5(sa + (uint32_t)((4 + j) * box_bytes), &tmAlo, &bars.full[s], c0, c1, c2, c3, c4);
                     }
@@ -674,6 +678,7 @@ int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
     A2CB_REQUIRE(p.A.x && p.B && p.B_lo && p.out, "tcx_fwd: null pointer");
     A2CB_REQUIRE(p.n_kb >= 1 && p.n_kb <= TCX_MAX_KB, "tcx_fwd: n_kb = %d out of range", p.n_kb);
     A2CB_REQUIRE(p.N > 0 && p.N % 4 == 0, "tcx_fwd: N = %d must be a positive multiple of 4", p.N);
+    A2CB_REQUIRE(p.gather_dim == 0 || (p.gather_dim >= 1 && p.gather_dim <= 4 && p.gather_idx), "tcx_fwd: bad gather");
     A2CB_REQUIRE(p.o_cb == 0 || (p.o_cb % 4 == 0 && !p.bias && (p.N + p.o_cb - 1) / p.o_cb <= 4), "tcx_fwd: bad column blocks");
     A2CB_REQUIRE(p.tiles.n_tiles > 0 && p.tiles.t_div > 0 && p.tiles.tr_dim >= 1 && p.tiles.tr_dim <= 4 &&
                  p.tiles.tq_dim >= 1 && p.tiles.tq_dim <= 4, "tcx_fwd: bad tiling");
@@ -703,6 +708,7 @@ int tcx_wgrad(const TcxWgrad& p, cudaStream_t st) {
     const long RA = (long)p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
     const long RB = (long)p.Bm.box[1] * p.Bm.box[2] * p.Bm.box[3] * p.Bm.box[4];
     A2CB_REQUIRE(RA == RB && RA >= 1, "tcx_wgrad: operand boxes enumerate %ld vs %ld rows", RA, RB);
+    A2CB_REQUIRE(p.gather_dim == 0 || (p.gather_dim >= 1 && p.gather_dim <= 4 && p.gather_idx), "tcx_wgrad: bad gather");
     CUtensorMap m[4];
     int rc = view_maps(&m[0], &m[1], p.A, g_knobs.mn_tma_swizzle, "wgrad A");
     if (rc) return rc;

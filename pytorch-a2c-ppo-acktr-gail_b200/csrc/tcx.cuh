@@ -49,8 +49,11 @@ struct TcxFwd {
     // output shifted by o_cb_off[block] (the four stride-parity classes of a transposed stride-2 convolution
     // share their input boxes, so they run as ONE product with 4 x C_in columns).  o_cb = 0: off.
     int32_t o_cb;
-    int32_t pad_;
+    // optional image gather: the A coordinate of dimension gather_dim becomes gather_idx[coordinate] (rows of a
+    // minibatch inside a tensor that holds the whole rollout); output coordinates are not affected.  0 = off.
+    int32_t gather_dim;
     int64_t o_cb_off[4];
+    const int64_t* gather_idx;
 };
 
 // partial[split][row_off[m] + n * col_stride] = alpha * sum_rows A[row, m] * Bm[row, n]
@@ -73,6 +76,9 @@ struct TcxWgrad {
     int64_t col_stride;
     int32_t n_cols;                 // valid B channels in total
     float alpha;
+    const int64_t* gather_idx;      // optional image gather of the A boxes (see TcxFwd), dimension gather_dim
+    int32_t gather_dim;
+    int32_t pad_;
 };
 
 // hardware-semantics knobs of the MN-major path (host-overridable for probing)
