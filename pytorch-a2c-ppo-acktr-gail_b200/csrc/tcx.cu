@@ -123,6 +123,7 @@ __device__ __forceinline__ float tx_lo(float v) { return v - __uint_as_float(__f
 
 struct TxBars {
     uint64_t full[TX_MAX_STAGES], empty[TX_MAX_STAGES], acc_full[2], acc_empty[2];
+    uint64_t fullB[2], emptyB[2];        // weight-gradient kernel: ring of the operand shared by all groups
     uint32_t tmem_base;
 };
 
@@ -415,7 +416,12 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int R8 = (R + 7) & ~7;
     const int box_bytes = R8 * TX_ROWB;
     const int a_planes = has_lo ? 2 : 1;
-    const int stage_bytes = box_bytes * (4 * a_planes + 2 * NBB);
+    // shared memory: [2 slots of the shared operand Bm: 2 NBB boxes each][`stages` stages of A: 4 a_planes boxes each].
+    // Bm (the output gradient) is the same for every accumulator group of a row tile, so it is loaded once per row
+    // tile into its own 2-deep ring instead of once per (row tile, group).
+    const int slotB_bytes = box_bytes * 2 * NBB;
+    const int stage_bytes = box_bytes * 4 * a_planes;
+    const uint32_t dynA = dyn + 2u * (uint32_t)slotB_bytes;
     const int per = (p.rows.n_tiles + p.splits - 1) / p.splits;
     const int rt0 = blockIdx.x * per;
     const int rt1 = min(p.rows.n_tiles, rt0 + per);
@@ -426,7 +432,10 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { tx_mbar_init(&bars.full[s], 1); tx_mbar_init(&bars.empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { tx_mbar_init(&bars.acc_full[b], 1); tx_mbar_init(&bars.acc_empty[b], 256); }
+        for (int b = 0; b < 2; ++b) {
+            tx_mbar_init(&bars.acc_full[b], 1); tx_mbar_init(&bars.acc_empty[b], 256);
+            tx_mbar_init(&bars.fullB[b], 1); tx_mbar_init(&bars.emptyB[b], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -436,7 +445,7 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     // rows R..R8-1 of every box are never written by TMA but take part in the K = 8 MMA steps: zero them once
     if (R8 > R) {
-        const int nbox = stages * (4 * a_planes + 2 * NBB);
+        const int nbox = 2 * 2 * NBB + stages * 4 * a_planes;
         const int per_box = (R8 - R) * (TX_ROWB / 4);
         for (int e = threadIdx.x; e < nbox * per_box; e += TX_NT) {
             const int b = e / per_box, w = e - b * per_box;
@@ -451,34 +460,40 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
-        const uint32_t bytes = (uint32_t)(R * TX_ROWB * (4 * a_planes + 2 * NBB));
+        const uint32_t bytesA = (uint32_t)(R * TX_ROWB * 4 * a_planes), bytesB = (uint32_t)(R * TX_ROWB * 2 * NBB);
         int qn = 0, s = 0;
         uint32_t ph = 0;
-        for (int rt = rt0; rt < rt1; ++rt) {
+        for (int i = 0; i < n_rt; ++i) {
             int base[5], ba[5];
-            tx_tile_base(p.rows, rt, base);
+            tx_tile_base(p.rows, rt0 + i, base);
 #pragma unroll
             for (int d = 0; d < 5; ++d) ba[d] = base[d];
             if (p.gather_dim > 0) ba[p.gather_dim] = (int)__ldg(p.gather_idx + base[p.gather_dim]);
+            const int sl = i & 1;
+            if (i >= 2) tx_mbar_wait(&bars.emptyB[sl], (uint32_t)(((i >> 1) - 1) & 1));
+            if (tx_elect()) {
+                const uint32_t sb = dyn + (uint32_t)(sl * slotB_bytes);
+                tx_expect(&bars.fullB[sl], bytesB);
+#pragma unroll
+                for (int j = 0; j < NBB; ++j) {
+                    const int c0 = p.gb[j][0] + otb * p.ot_b_step, c1 = p.gb[j][1] + base[1], c2 = p.gb[j][2] + base[2],
+                              c3 = p.gb[j][3] + base[3], c4 = base[4];
+                    tx_tma5(sb + (uint32_t)(j * box_bytes), &tmB, &bars.fullB[sl], c0, c1, c2, c3, c4);
+                    tx_tma5(sb + (uint32_t)((NBB + j) * box_bytes), &tmBlo, &bars.fullB[sl], c0, c1, c2, c3, c4);
+                }
+            }
+            __syncwarp();
             for (int g = 0; g < G; ++g, ++qn) {
                 if (qn >= stages) tx_mbar_wait(&bars.empty[s], ph ^ 1u);
                 if (tx_elect()) {
-                    const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
-                    const uint32_t sb = sa + (uint32_t)(4 * a_planes * box_bytes);
-                    tx_expect(&bars.full[s], bytes);
+                    const uint32_t sa = dynA + (uint32_t)(s * stage_bytes);
+                    tx_expect(&bars.full[s], bytesA);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int c0 = p.ga[g][j][0] + ota * p.ot_a_step, c1 = p.ga[g][j][1] + ba[1],
                                   c2 = p.ga[g][j][2] + ba[2], c3 = p.ga[g][j][3] + ba[3], c4 = ba[4];
                         tx_tma5(sa + (uint32_t)(j * box_bytes), &tmA, &bars.full[s], c0, c1, c2, c3, c4);
                         if (has_lo) tx_tma5(sa + (uint32_t)((4 + j) * box_bytes), &tmAlo, &bars.full[s], c0, c1, c2, c3, c4);
-                    }
-#pragma unroll
-                    for (int j = 0; j < NBB; ++j) {
-                        const int c0 = p.gb[j][0] + otb * p.ot_b_step, c1 = p.gb[j][1] + base[1], c2 = p.gb[j][2] + base[2],
-                                  c3 = p.gb[j][3] + base[3], c4 = base[4];
-                        tx_tma5(sb + (uint32_t)(j * box_bytes), &tmB, &bars.full[s], c0, c1, c2, c3, c4);
-                        tx_tma5(sb + (uint32_t)((NBB + j) * box_bytes), &tmBlo, &bars.full[s], c0, c1, c2, c3, c4);
                     }
                 }
                 __syncwarp();
@@ -497,18 +512,19 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int s = 0, kc = 0, c = 0;
         uint32_t ph = 0;
         for (int i = 0; i < n_rt; ++i) {
-            const int buf = c & 1;
+            const int buf = c & 1, sl = i & 1;
             const bool first = kc == 0;
             const bool last = (i == n_rt - 1) || (kc + 1 == chain);
             if (first && c >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)(((c >> 1) - 1) & 1));
+            tx_mbar_wait(&bars.fullB[sl], (uint32_t)((i >> 1) & 1));
             for (int g = 0; g < G; ++g) {
                 tx_mbar_wait(&bars.full[s], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tx_elect()) {
-                    const uint32_t sa = dyn + (uint32_t)(s * stage_bytes);
+                    const uint32_t sa = dynA + (uint32_t)(s * stage_bytes);
                     uint64_t dah = dconst | (uint64_t)((sa & 0x3FFFF) >> 4);
                     uint64_t dal = dconst | (uint64_t)(((sa + (uint32_t)(4 * box_bytes)) & 0x3FFFF) >> 4);
-                    const uint32_t sb = sa + (uint32_t)(4 * a_planes * box_bytes);
+                    const uint32_t sb = dyn + (uint32_t)(sl * slotB_bytes);
                     uint64_t dbh = dconst | (uint64_t)((sb & 0x3FFFF) >> 4);
                     uint64_t dbl = dconst | (uint64_t)(((sb + (uint32_t)(NBB * box_bytes)) & 0x3FFFF) >> 4);
                     const uint32_t d = tmem + (uint32_t)(buf * G * BN + g * BN);
@@ -526,7 +542,10 @@ tcx_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tx_mma(d, dah, dbh, idesc, 1u);
                     }
                     tx_commit(&bars.empty[s]);
-                    if (last && g == G - 1) tx_commit(&bars.acc_full[buf]);
+                    if (g == G - 1) {
+                        tx_commit(&bars.emptyB[sl]);
+                        if (last) tx_commit(&bars.acc_full[buf]);
+                    }
                 }
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1u; }
@@ -653,11 +672,12 @@ template <int BN, int G>
 int launch_wgrad(const TcxWgrad& p, const CUtensorMap* m, cudaStream_t st) {
     const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
     const int R8 = (R + 7) & ~7;
-    const int stage = R8 * TX_ROWB * (4 * (p.A.lo ? 2 : 1) + 2 * (BN / 32));
-    int stages = kSmemBudget / stage;
+    const int stage = R8 * TX_ROWB * 4 * (p.A.lo ? 2 : 1);          // A boxes of one (row tile, group)
+    const int slots = 2 * R8 * TX_ROWB * 2 * (BN / 32);              // two slots of the shared operand
+    int stages = (kSmemBudget - slots) / stage;
     stages = stages > TX_MAX_STAGES ? TX_MAX_STAGES : stages;
     A2CB_REQUIRE(stages >= 2, "tcx_wgrad: row tile of %d rows does not fit shared memory", R);
-    const int smem = stages * stage + 1024;
+    const int smem = stages * stage + slots + 1024;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(tcx_wgrad_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
