@@ -239,14 +239,19 @@ int a2cb_tcx_lo_plane(float* lo, const float* x, int64_t n, a2cb_stream_t stream
  * step).  ntab [N], ktab [K]: device int32 element offsets. */
 int a2cb_tcx_prep_weights(float* img, float* img_lo, const float* src, int64_t N, int64_t K, const int32_t* ntab,
                           const int32_t* ktab, a2cb_stream_t stream);
+/* Several weight images in one launch.  jobs: device array of a2cb_tcx_prep_job_t (first = index of the image's first
+ * element in the concatenated element range of all jobs, ascending), total = sum of N K. */
+typedef struct { float* img; float* img_lo; const float* src; const int32_t* ntab; const int32_t* ktab; int64_t N, K, first; } a2cb_tcx_prep_job_t;
+int a2cb_tcx_prep_multi(const a2cb_tcx_prep_job_t* jobs, int32_t n_jobs, int64_t total, a2cb_stream_t stream);
 /* frames [*, C, H, W] (uint8 or fp32; rows through idx, NULL = identity) -> fp32 space-to-depth
  * [B, H/S, W/S, C*S*S], channel (c, dy, dx): fuses the minibatch gather of storage.py:127 with the layout
  * change that turns the stride-S first convolution into a stride-1 one.  out_lo optional. */
 int a2cb_tcx_s2d(float* out, float* out_lo, const void* frames, int32_t src_is_u8, const int64_t* idx, int32_t B,
                  int32_t C, int32_t H, int32_t W, int32_t S, a2cb_stream_t stream);
 /* part[blk][c] = partial column sums of x[rows][C] (row pitch in elements); a2cb_tcx_colsum_blocks(rows)
- * partials, folded by a2cb_reduce_splits: bias gradients */
-int a2cb_tcx_colsum(float* part, const float* x, int64_t rows, int32_t C, int64_t pitch, a2cb_stream_t stream);
+ * partials, folded by a2cb_reduce_splits: bias gradients.  lo (optional): also writes the lo plane of x in the
+ * same pass (the GRU's gate gradients need both). */
+int a2cb_tcx_colsum(float* part, const float* x, float* lo, int64_t rows, int32_t C, int64_t pitch, a2cb_stream_t stream);
 int a2cb_tcx_colsum_blocks(int64_t rows);
 /* Weight + bias gradient of a narrow Linear layer (policy / value heads, distributions.py:69-72, model.py:185;
  * N <= 8 outputs): part[blk][n K + k] = sum_rows gy[row gy_stride + n] x[row K + k], part[blk][N K + n] = sum_rows gy;
@@ -359,6 +364,7 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_TCX_S2D 18
 #define A2CB_OP_TCX_COLSUM 19
 #define A2CB_OP_TCX_NARROW_WGRAD 20
+#define A2CB_OP_TCX_PREP_MULTI 21
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -376,8 +382,9 @@ typedef struct { float* out; const float* in; int64_t img_stride; int64_t pitch;
 typedef struct { float* lo; const float* x; int64_t n; } a2cb_tcx_lo_t;
 typedef struct { float* img; float* img_lo; const float* src; int64_t N, K; const int32_t* ntab; const int32_t* ktab; } a2cb_tcx_prep_t;
 typedef struct { float* out; float* out_lo; const void* frames; const int64_t* idx; int32_t src_is_u8, B, C, H, W, S; } a2cb_tcx_s2d_t;
-typedef struct { float* part; const float* x; int64_t rows; int64_t pitch; int32_t C; int32_t pad_; } a2cb_tcx_colsum_t;
+typedef struct { float* part; const float* x; int64_t rows; int64_t pitch; int32_t C; int32_t pad_; float* lo; } a2cb_tcx_colsum_t;
 typedef struct { float* part; const float* x; const float* gy; int64_t rows; int32_t K, N, gy_stride, pad_; } a2cb_tcx_narrow_wgrad_t;
+typedef struct { const a2cb_tcx_prep_job_t* jobs; int64_t total; int32_t n_jobs; int32_t pad_; } a2cb_tcx_prep_multi_t;
 typedef struct { int32_t kind; int32_t flags; const void* desc; } a2cb_op_t;
 
 int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream);

@@ -775,6 +775,8 @@ class PolicyRuntime(object):
             nb = NetBuilder(self.spec, self.L, B, "obs_in", code, False, "b%d_" % B, seq=seq,
                             keep_gates=keep_for_backward or not self.spec.recurrent)
             plans = nb.forward_plans()
+            if nb.tcx is not None:
+                plans, = _tcx.hoist_preps([plans], "b%d_f" % B)
             self._alloc(nb)
             prog = Program(self.dev)
             for p in plans:
@@ -848,6 +850,8 @@ class PolicyRuntime(object):
             nb = NetBuilder(self.spec, self.L, B, "obs_in", code, False, tag, seq=seq)
             nb.forward_plans()
             plans = nb.backward_plans()
+            if nb.tcx is not None:
+                plans, = _tcx.hoist_preps([plans], tag + "b")
             self._alloc(nb)
             prog = Program(self.dev)
             for p in plans:
@@ -889,6 +893,8 @@ class PolicyRuntime(object):
         nb = NetBuilder(s, self.L, mbs, "obs_st", code, use_idx, tag, full_rows=T * N if use_idx else 0, **kw)
         fwd = nb.forward_plans()
         bwd = nb.backward_plans() if with_backward else []
+        if nb.tcx is not None:
+            fwd, bwd = _tcx.hoist_preps([fwd, bwd], tag)      # all weight images: one launch at the top of the step
         if not with_backward:
             nb.buf("dz", mbs * self.zs)
         self._alloc(nb)

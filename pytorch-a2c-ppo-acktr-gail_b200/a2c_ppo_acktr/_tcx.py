@@ -51,7 +51,16 @@ class S2dDesc(ctypes.Structure):
 
 
 class ColsumDesc(ctypes.Structure):
-    _fields_ = [("part", c_vp), ("x", c_vp), ("rows", c_i64), ("pitch", c_i64), ("C", c_i32), ("pad_", c_i32)]
+    _fields_ = [("part", c_vp), ("x", c_vp), ("rows", c_i64), ("pitch", c_i64), ("C", c_i32), ("pad_", c_i32), ("lo", c_vp)]
+
+
+class PrepJob(ctypes.Structure):
+    _fields_ = [("img", c_vp), ("img_lo", c_vp), ("src", c_vp), ("ntab", c_vp), ("ktab", c_vp), ("N", c_i64), ("K", c_i64),
+                ("first", c_i64)]
+
+
+class PrepMultiDesc(ctypes.Structure):
+    _fields_ = [("jobs", c_vp), ("total", c_i64), ("n_jobs", c_i32), ("pad_", c_i32)]
 
 
 class NarrowWgradDesc(ctypes.Structure):
@@ -60,6 +69,7 @@ class NarrowWgradDesc(ctypes.Structure):
 
 
 _native.register({
+    "a2cb_tcx_prep_multi": (c_i32, [c_vp, c_i32, c_i64, c_vp]),
     "a2cb_tcx_narrow_wgrad": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
     "a2cb_tcx_narrow_wgrad_blocks": (c_i32, [c_i64]),
     "a2cb_tcx_fwd": (c_i32, [ctypes.POINTER(FwdDesc), c_vp]),
@@ -67,7 +77,7 @@ _native.register({
     "a2cb_tcx_lo_plane": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "a2cb_tcx_prep_weights": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "a2cb_tcx_s2d": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
-    "a2cb_tcx_colsum": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
+    "a2cb_tcx_colsum": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
     "a2cb_tcx_colsum_blocks": (c_i32, [c_i64]),
     "a2cb_tcx_sizeof": (c_i32, [c_i32]),
     "a2cb_tcx_set_knobs": (c_i32, [c_i32, c_i32, c_i32, c_i32]),
@@ -102,6 +112,7 @@ def tiling(n_tiles, tr_dim, tr_step, t_div=None, tq_dim=4, tq_step=0):
 # ---------------------------------------------------------------------------------------------------
 OP_TCX_FWD, OP_TCX_WGRAD, OP_TCX_LO, OP_TCX_PREP, OP_TCX_S2D, OP_TCX_COLSUM = 14, 15, 16, 17, 18, 19
 OP_TCX_NARROW_WGRAD = 20
+OP_TCX_PREP_MULTI = 21
 
 
 class TcxOp(object):
@@ -192,12 +203,59 @@ def prep_op(name, img, src, N, K, ntab, ktab):
     def make(arena):
         return PrepDesc(arena.ptr((img, 0)), arena.ptr((img + "_lo", 0)), arena.ptr(src), N, K,
                         _itab(arena, img + "_ntab", ntab), _itab(arena, img + "_ktab", ktab))
-    return TcxOp(OP_TCX_PREP, make, name)
+    op = TcxOp(OP_TCX_PREP, make, name)
+    op.prep = (img, src, N, K, ntab, ktab)
+    return op
 
 
-def colsum_op(name, part, x, rows, C, pitch):
+def hoist_preps(lists, tag):
+    """Weight images depend on the weights only: moves every weight-image op of the given plan lists to the front of
+    the first one and merges them into one launch.  Returns the new lists."""
+    is_prep = lambda o: isinstance(o, TcxOp) and o.kind == OP_TCX_PREP
+    preps = [o for l in lists for o in l if is_prep(o)]
+    rest = [[o for o in l if not is_prep(o)] for l in lists]
+    rest[0] = merge_preps(preps, tag) + rest[0]
+    return rest
+
+
+def merge_preps(ops, tag):
+    """Replaces runs of consecutive weight-image ops of a plan list by ONE launch each (a2cb_tcx_prep_multi)."""
+    import torch
+    out, run = [], []
+
+    def flush():
+        if len(run) <= 1:
+            out.extend(run)
+        else:
+            jobs_spec = [o.prep for o in run]
+            name = "%sprepjobs_%d" % (tag, len(out))
+
+            def make(arena, jobs_spec=jobs_spec, name=name):
+                arr = (PrepJob * len(jobs_spec))()
+                first = 0
+                for i, (img, src, N, K, ntab, ktab) in enumerate(jobs_spec):
+                    arr[i].img, arr[i].img_lo, arr[i].src = arena.ptr((img, 0)), arena.ptr((img + "_lo", 0)), arena.ptr(src)
+                    arr[i].ntab, arr[i].ktab = _itab(arena, img + "_ntab", ntab), _itab(arena, img + "_ktab", ktab)
+                    arr[i].N, arr[i].K, arr[i].first = N, K, first
+                    first += N * K
+                raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(arena.device)
+                arena.bind(name, raw)
+                return PrepMultiDesc(raw.data_ptr(), first, len(jobs_spec), 0)
+            out.append(TcxOp(OP_TCX_PREP_MULTI, make, "weight_image"))
+        del run[:]
+    for o in ops:
+        if isinstance(o, TcxOp) and o.kind == OP_TCX_PREP:
+            run.append(o)
+        else:
+            flush()
+            out.append(o)
+    flush()
+    return out
+
+
+def colsum_op(name, part, x, rows, C, pitch, lo=None):
     def make(arena):
-        return ColsumDesc(arena.ptr(part), arena.ptr(x), rows, pitch, C, 0)
+        return ColsumDesc(arena.ptr(part), arena.ptr(x), rows, pitch, C, 0, arena.ptr(lo))
     return TcxOp(OP_TCX_COLSUM, make, name)
 
 
@@ -349,12 +407,13 @@ class CnnNet(object):
                 self.linear_fwd("gru_ih.fwd", r["h"], r["h_lo"], H, wi, 3 * H, gi, None, bias=self.P("base.gru.bias_ih_l0"))]
 
     # -- backward -------------------------------------------------------------------------------------
-    def bias_grad(self, name, x, rows, C, dst):
+    def bias_grad(self, name, x, rows, C, dst, lo=None):
+        """Bias gradient = column sums of the output gradient (lo: also emit its lo plane in the same pass)."""
         nb = self.nb
         blocks = colsum_blocks(rows)
         part = nb.buf("bpart_" + name, blocks * C)
         from ._engine import RawOp, ReduceDesc, OP_REDUCE
-        return [colsum_op(name + ".bias_colsum", part, x, rows, C, C),
+        return [colsum_op(name + ".bias_colsum", part, x, rows, C, C, lo=lo),
                 RawOp(OP_REDUCE, {"dst": dst, "src": part},
                       dict(count=C, stride=C, splits=blocks, accumulate=0, ncols=0, act=0, beta=1.0), False,
                       name + ".bias_fold", ReduceDesc)]
@@ -493,12 +552,12 @@ class CnnNet(object):
         nb, B, H, r = self.nb, self.B, self.H, self.refs
         dgi_lo, dgh_lo, hm_lo = nb.buf("gru_dgi_lo", B * 3 * H), nb.buf("gru_dgh_lo", B * 3 * H), nb.buf("gru_hm_lo", B * H)
         wid = self.image("img_gih_d", H, 3 * H)
-        ops = [lo_op("lo_plane", dgi, dgi_lo, B * 3 * H), lo_op("lo_plane", dgh, dgh_lo, B * 3 * H),
-               lo_op("lo_plane", hm, hm_lo, B * H)]
+        # bias gradients (column sums) and the lo planes of the gate gradients come out of one pass over them
+        ops = [lo_op("lo_plane", hm, hm_lo, B * H)]
+        ops += self.bias_grad("gru_hh", dgh, B, 3 * H, self.G("base.gru.bias_hh_l0"), lo=dgh_lo)
+        ops += self.bias_grad("gru_ih", dgi, B, 3 * H, self.G("base.gru.bias_ih_l0"), lo=dgi_lo)
         ops += self.linear_wgrad("gru_hh.wgrad", hm, hm_lo, H, dgh, dgh_lo, 3 * H, self.G("base.gru.weight_hh_l0"))
-        ops += self.bias_grad("gru_hh", dgh, B, 3 * H, self.G("base.gru.bias_hh_l0"))
         ops += self.linear_wgrad("gru_ih.wgrad", r["h"], r["h_lo"], H, dgi, dgi_lo, 3 * H, self.G("base.gru.weight_ih_l0"))
-        ops += self.bias_grad("gru_ih", dgi, B, 3 * H, self.G("base.gru.bias_ih_l0"))
         ops.append(prep_op("weight_image", wid, self.P("base.gru.weight_ih_l0"), H, 3 * H, list(range(H)),
                            [k * H for k in range(3 * H)]))
         ops.append(self.linear_fwd("gru_ih.dgrad", dgi, dgi_lo, 3 * H, wid, H, gx, gx_lo, mask=r["h"]))

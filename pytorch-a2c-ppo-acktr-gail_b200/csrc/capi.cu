@@ -171,8 +171,11 @@ int a2cb_tcx_s2d(float* out, float* out_lo, const void* frames, int32_t src_is_u
                  int32_t C, int32_t H, int32_t W, int32_t S, a2cb_stream_t stream) {
     return tcx_s2d(out, out_lo, frames, src_is_u8, idx, B, C, H, W, S, (cudaStream_t)stream);
 }
-int a2cb_tcx_colsum(float* part, const float* x, int64_t rows, int32_t C, int64_t pitch, a2cb_stream_t stream) {
-    return tcx_colsum(part, x, (long)rows, C, (long)pitch, (cudaStream_t)stream);
+int a2cb_tcx_colsum(float* part, const float* x, float* lo, int64_t rows, int32_t C, int64_t pitch, a2cb_stream_t stream) {
+    return tcx_colsum(part, x, lo, (long)rows, C, (long)pitch, (cudaStream_t)stream);
+}
+int a2cb_tcx_prep_multi(const a2cb_tcx_prep_job_t* jobs, int32_t n_jobs, int64_t total, a2cb_stream_t stream) {
+    return tcx_prep_multi(jobs, n_jobs, (long)total, (cudaStream_t)stream);
 }
 int a2cb_tcx_narrow_wgrad(float* part, const float* x, const float* gy, int64_t rows, int32_t K, int32_t N,
                           int32_t gy_stride, a2cb_stream_t stream) {
@@ -284,7 +287,12 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             }
             case A2CB_OP_TCX_COLSUM: {
                 const a2cb_tcx_colsum_t& q = *reinterpret_cast<const a2cb_tcx_colsum_t*>(op.desc);
-                rc = tcx_colsum(q.part, q.x, (long)q.rows, q.C, (long)q.pitch, st);
+                rc = tcx_colsum(q.part, q.x, q.lo, (long)q.rows, q.C, (long)q.pitch, st);
+                break;
+            }
+            case A2CB_OP_TCX_PREP_MULTI: {
+                const a2cb_tcx_prep_multi_t& q = *reinterpret_cast<const a2cb_tcx_prep_multi_t*>(op.desc);
+                rc = tcx_prep_multi(q.jobs, q.n_jobs, (long)q.total, st);
                 break;
             }
             case A2CB_OP_TCX_NARROW_WGRAD: {

@@ -71,8 +71,9 @@ int tcx_prep_weights(float* img, float* img_lo, const float* src, long N, long K
                      const int32_t* ktab, cudaStream_t st);
 int tcx_s2d(float* out, float* out_lo, const void* frames, int src_is_u8, const int64_t* idx, int B, int C, int H, int W,
             int S, cudaStream_t st);
-int tcx_colsum(float* part, const float* x, long rows, int C, long pitch, cudaStream_t st);
+int tcx_colsum(float* part, const float* x, float* lo, long rows, int C, long pitch, cudaStream_t st);
 int tcx_colsum_blocks(long rows);
+int tcx_prep_multi(const void* jobs, int n_jobs, long total, cudaStream_t st);
 int tcx_narrow_wgrad(float* part, const float* x, const float* gy, long rows, int K, int N, int gy_stride, cudaStream_t st);
 int tcx_narrow_wgrad_blocks(long rows);
 

@@ -55,6 +55,25 @@ tcx_s2d_kernel(float* __restrict__ out, float* __restrict__ out_lo, const T* __r
     }
 }
 
+// Several weight images in one launch: jobs[j] describes one image, `first` = index of its first element in the
+// concatenated element range.
+struct PrepJob { float* img; float* img_lo; const float* src; const int32_t* ntab; const int32_t* ktab; long N, K, first; };
+
+__global__ void __launch_bounds__(256)
+tcx_prep_multi_kernel(const PrepJob* __restrict__ jobs, int n_jobs, long total) {
+    const long e0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e0 >= total) return;
+    int j = 0;
+    while (j + 1 < n_jobs && e0 >= jobs[j + 1].first) ++j;
+    const PrepJob q = jobs[j];
+    const long e = e0 - q.first;
+    const long n = e / q.K, k = e - n * q.K;
+    const int a = __ldg(q.ntab + n), b = __ldg(q.ktab + k);
+    const float v = (a >= 0 && b >= 0) ? __ldg(q.src + (long)a + b) : 0.f;
+    q.img[e] = v;
+    q.img_lo[e] = ax_lo(v);
+}
+
 // Atari geometry (C = 4, 84 x 84, S = 4): one block per (image, block row).  The 16 source rows (c, dy) of
 // 84 pixels are read as coalesced 4-byte / 16-byte words into shared memory and written back as 21 x 64
 // contiguous floats -- both sides of the transposition are fully coalesced.
@@ -91,8 +110,10 @@ tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, cons
 // part[blk][c] = sum over this block's rows of x[row * pitch + c]   (C a multiple of 4, row-contiguous).
 // Thread = (channel quad, row lane); float4 loads, four independent accumulator sets, shared-memory fold
 // across the row lanes in a fixed order (deterministic).
+template <bool LO>
 __global__ void __launch_bounds__(256)
-tcx_colsum_kernel(float* __restrict__ part, const float* __restrict__ x, long rows, int C, long pitch, long rows_per_blk) {
+tcx_colsum_kernel(float* __restrict__ part, const float* __restrict__ x, float* __restrict__ lo, long rows, int C, long pitch,
+                  long rows_per_blk) {
     __shared__ float4 red[256];
     const long r0 = (long)blockIdx.x * rows_per_blk, r1 = min(rows, r0 + rows_per_blk);
     const int nq = C / 4;
@@ -104,11 +125,16 @@ tcx_colsum_kernel(float* __restrict__ part, const float* __restrict__ x, long ro
         if (rl < rl_n && q0 + ql < nq) {
             const float* base = x + (long)(q0 + ql) * 4;
             long r = r0 + rl;
+            float* lob = LO ? lo + (long)(q0 + ql) * 4 : nullptr;
+            auto put_lo = [&](long rr, const float4 v) {
+                if (LO) *reinterpret_cast<float4*>(lob + rr * pitch) = make_float4(ax_lo(v.x), ax_lo(v.y), ax_lo(v.z), ax_lo(v.w));
+            };
             for (; r + 3L * rl_n < r1; r += 4L * rl_n) {
                 const float4 a = *reinterpret_cast<const float4*>(base + r * pitch);
                 const float4 b = *reinterpret_cast<const float4*>(base + (r + rl_n) * pitch);
                 const float4 c = *reinterpret_cast<const float4*>(base + (r + 2L * rl_n) * pitch);
                 const float4 d = *reinterpret_cast<const float4*>(base + (r + 3L * rl_n) * pitch);
+                put_lo(r, a); put_lo(r + rl_n, b); put_lo(r + 2L * rl_n, c); put_lo(r + 3L * rl_n, d);
                 s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
                 s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
                 s2.x += c.x; s2.y += c.y; s2.z += c.z; s2.w += c.w;
@@ -116,6 +142,7 @@ tcx_colsum_kernel(float* __restrict__ part, const float* __restrict__ x, long ro
             }
             for (; r < r1; r += rl_n) {
                 const float4 a = *reinterpret_cast<const float4*>(base + r * pitch);
+                put_lo(r, a);
                 s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
             }
         }
@@ -212,12 +239,19 @@ int tcx_s2d(float* out, float* out_lo, const void* frames, int src_is_u8, const 
 
 int tcx_colsum_blocks(long rows) { return (int)min((rows + 127) / 128, (long)kNumSM * 8); }
 
-int tcx_colsum(float* part, const float* x, long rows, int C, long pitch, cudaStream_t st) {
+int tcx_colsum(float* part, const float* x, float* lo, long rows, int C, long pitch, cudaStream_t st) {
     A2CB_REQUIRE(part && x && rows > 0 && C > 0 && C % 4 == 0 && pitch % 4 == 0, "tcx_colsum: bad arguments");
     const int blocks = tcx_colsum_blocks(rows);
     const long per = (rows + blocks - 1) / blocks;
-    tcx_colsum_kernel<<<blocks, 256, 0, st>>>(part, x, rows, C, pitch, per);
+    if (lo) tcx_colsum_kernel<true><<<blocks, 256, 0, st>>>(part, x, lo, rows, C, pitch, per);
+    else tcx_colsum_kernel<false><<<blocks, 256, 0, st>>>(part, x, nullptr, rows, C, pitch, per);
     return check_launch("tcx_colsum");
+}
+
+int tcx_prep_multi(const void* jobs, int n_jobs, long total, cudaStream_t st) {
+    A2CB_REQUIRE(jobs && n_jobs > 0 && total > 0, "tcx_prep_multi: bad arguments");
+    tcx_prep_multi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const PrepJob*>(jobs), n_jobs, total);
+    return check_launch("tcx_prep_multi");
 }
 
 int tcx_narrow_wgrad_blocks(long rows) { return (int)min((rows + 63) / 64, (long)kNumSM * 4); }

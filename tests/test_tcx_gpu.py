@@ -302,5 +302,7 @@ def test_s2d_and_colsum():
     x = torch.randn(1000, 96, generator=g).to(DEV)
     blocks = lib().a2cb_tcx_colsum_blocks(1000)
     part = torch.zeros(blocks, 96, device=DEV)
-    _native.check(lib().a2cb_tcx_colsum(part.data_ptr(), x.data_ptr(), 1000, 96, 96, st()), "colsum")
+    lo = torch.zeros_like(x)
+    _native.check(lib().a2cb_tcx_colsum(part.data_ptr(), x.data_ptr(), lo.data_ptr(), 1000, 96, 96, st()), "colsum")
     assert rel(part.sum(0), x.double().sum(0)) <= 1e-6
+    assert torch.equal(lo, lo_plane(x))
