@@ -261,7 +261,7 @@ def colsum_op(name, part, x, rows, C, pitch, lo=None):
 
 def colsum_blocks(rows):
     # mirrors tcx_colsum_blocks (csrc/tcx_aux.cu)
-    return int(min((rows + 127) // 128, 148 * 8))
+    return int(min((rows + 15) // 16, 148 * 8))
 
 
 def narrow_wgrad_blocks(rows):

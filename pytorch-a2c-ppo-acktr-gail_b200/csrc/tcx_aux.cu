@@ -237,7 +237,7 @@ int tcx_s2d(float* out, float* out_lo, const void* frames, int src_is_u8, const 
     return check_launch("tcx_s2d");
 }
 
-int tcx_colsum_blocks(long rows) { return (int)min((rows + 127) / 128, (long)kNumSM * 8); }
+int tcx_colsum_blocks(long rows) { return (int)min((rows + 15) / 16, (long)kNumSM * 8); }
 
 int tcx_colsum(float* part, const float* x, float* lo, long rows, int C, long pitch, cudaStream_t st) {
     A2CB_REQUIRE(part && x && rows > 0 && C > 0 && C % 4 == 0 && pitch % 4 == 0, "tcx_colsum: bad arguments");
