@@ -295,6 +295,12 @@ def run_ours(args):
         print(json.dumps(out))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the C5 shard
+# (profiles/r01c_tcx_gru_full_c5.txt); only meaningful for that workload
+NCU_DRAM_SOURCE = "profiles/r01c_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
+NCU_DRAM_BYTES = {}
+
+
 def describe(cfg):
     if cfg["algo"] == "ppo":
         return ("PPO %s, %d steps x %d procs per GPU, %d epochs x %d minibatches, clip %.2g%s"
@@ -329,6 +335,9 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
         elif kind in (14, 15):              # TMA-fed tensor-core engine: labelled by layer
             labels.append(lab)
             flops.append(fl)
+        elif kind in (12, 13):              # persistent GRU recurrence: T steps of [N, H] x [H, 3H] (fp32 SIMT pipe)
+            labels.append(kind_names[kind])
+            flops.append(2.0 * desc.T * desc.N * 3 * desc.H * desc.H)
         else:
             labels.append(kind_names.get(kind, lab or "op%d" % kind))
             flops.append(0.0)
@@ -370,8 +379,9 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
     rows = [{"op": lab, "launches": a[2], "ms": float(a[0]), "share": float(a[0] / total),
              "tflops": float(a[1] / a[0] / 1e9) if a[1] else None} for lab, a in agg.items()]
     rows.sort(key=lambda r: -r["ms"])
-    gemm_rows = [r for r in rows if r["tflops"] is not None]
+    gemm_rows = [r for r in rows if r["tflops"] is not None and not r["op"].startswith("gru.seq")]
     top = gemm_rows[0]
+    gru_rows = [r for r in rows if r["op"].startswith("gru.seq")]
     from a2c_ppo_acktr import _native as nat
     peak = pk["tensor_sustained"]
     tcx_ops = any(kind in (14, 15) for kind, _, _ in prog.entries)
@@ -383,6 +393,23 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
                            "TF32 peak (no TF32 figure is published for this pool) is attainable",
             "share_of_step": top["share"], "launch_ms": top["ms"] / top["launches"], "launches_per_step": top["launches"],
             "step_program_ms": float(total), "gemm_engine_mode": int(nat.lib().a2cb_get_gemm_mode())}
+    # what the fp32-parity arithmetic can reach on this tensor pipe: TF32 runs at half the bf16 rate and every product
+    # costs 3 MMAs (2 when one operand is exact in TF32: the uint8 frames of conv1)
+    mmas = 2 if top["op"].startswith("conv1") else 3
+    roof["peak_3xtf32"] = peak / 2.0 / mmas
+    roof["frac_3xtf32"] = top["tflops"] / roof["peak_3xtf32"]
+    is_c5 = bool(cfg.get("recurrent")) and cfg["T"] == 128 and cfg["N"] == 256
+    roof["traffic"] = NCU_DRAM_BYTES.get(top["op"]) if is_c5 else None
+    roof["traffic_source"] = NCU_DRAM_SOURCE if roof["traffic"] else None
+    if gru_rows:
+        # the recurrence is the largest single launch of the recurrent workload; it runs on the fp32 SIMT pipe
+        # (148 SMs x 128 lanes x 2 flop x sm clock) with one barrier per time step, not on the tensor pipe
+        g = max(gru_rows, key=lambda r: r["ms"])
+        fp32_peak = 148 * 128 * 2 * 1.965e-3
+        roof["recurrence"] = {"kernel": "a2cb::gru_persistent_%s_kernel" % ("bwd" if g["op"].endswith("bwd") else "fwd"),
+                              "bound": "fp32 pipe + per-step barrier", "achieved": g["tflops"], "peak": fp32_peak,
+                              "unit": "TFLOP/s", "frac": g["tflops"] / fp32_peak, "launch_ms": g["ms"],
+                              "share_of_step": g["share"]}
     return roof, rows[:24]
 
 

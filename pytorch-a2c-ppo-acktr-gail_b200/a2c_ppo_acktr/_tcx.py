@@ -159,7 +159,11 @@ def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tile
         d.gather_dim = gather_dim
         d.gather_idx = 1 if gather_dim else None          # placeholder: a2cb_run_ops substitutes the runtime row list
         return d
-    return TcxOp(OP_TCX_FWD, make, name, flops=flops, runtime_idx=bool(gather_dim))
+    op = TcxOp(OP_TCX_FWD, make, name, flops=flops, runtime_idx=bool(gather_dim))
+    op.spec = dict(A=A, dims=dims, strides=strides, box=box, img=img, img_rows=img_rows, img_cols=img_cols, kbs=kbs,
+                   tiles=tiles, out=out, o_stride=o_stride, o_ext=o_ext, N=N, alpha=alpha, bias=bias, act=act, mask=mask,
+                   o_base=o_base, col_blocks=col_blocks, gather_dim=gather_dim)
+    return op
 
 
 def wgrad_op(name, A, A_lo, a_dims, a_strides, a_box, Bm, Bm_lo, b_dims, b_strides, b_box, groups, b_boxes, rows, splits,
@@ -190,13 +194,20 @@ def wgrad_op(name, A, A_lo, a_dims, a_strides, a_box, Bm, Bm_lo, b_dims, b_strid
         d.gather_dim = gather_dim
         d.gather_idx = 1 if gather_dim else None
         return d
-    return TcxOp(OP_TCX_WGRAD, make, name, flops=flops, runtime_idx=bool(gather_dim))
+    op = TcxOp(OP_TCX_WGRAD, make, name, flops=flops, runtime_idx=bool(gather_dim))
+    op.spec = dict(A=A, a_dims=a_dims, a_strides=a_strides, a_box=a_box, Bm=Bm, b_dims=b_dims, b_strides=b_strides,
+                   b_box=b_box, groups=groups, b_boxes=b_boxes, rows=rows, splits=splits, ot_a=ot_a, ot_b=ot_b,
+                   ot_a_step=ot_a_step, ot_b_step=ot_b_step, partial=partial, split_stride=split_stride, row_off=row_off,
+                   col_stride=col_stride, n_cols=n_cols, alpha=alpha, gather_dim=gather_dim)
+    return op
 
 
 def lo_op(name, x, lo, n):
     def make(arena):
         return LoDesc(arena.ptr(lo), arena.ptr(x), n)
-    return TcxOp(OP_TCX_LO, make, name)
+    op = TcxOp(OP_TCX_LO, make, name)
+    op.spec = dict(x=x, lo=lo, n=n)
+    return op
 
 
 def prep_op(name, img, src, N, K, ntab, ktab):
@@ -256,7 +267,9 @@ def merge_preps(ops, tag):
 def colsum_op(name, part, x, rows, C, pitch, lo=None):
     def make(arena):
         return ColsumDesc(arena.ptr(part), arena.ptr(x), rows, pitch, C, 0, arena.ptr(lo))
-    return TcxOp(OP_TCX_COLSUM, make, name)
+    op = TcxOp(OP_TCX_COLSUM, make, name)
+    op.spec = dict(part=part, x=x, rows=rows, C=C, pitch=pitch, lo=lo, blocks=colsum_blocks(rows))
+    return op
 
 
 def colsum_blocks(rows):
@@ -278,7 +291,9 @@ def narrow_wgrad_ops(nb, name, x, gy, rows, K, N, gy_stride, dst):
 
     def make(arena):
         return NarrowWgradDesc(arena.ptr(part), arena.ptr(x), arena.ptr(gy), rows, K, N, gy_stride, 0)
-    return [TcxOp(OP_TCX_NARROW_WGRAD, make, name + ".wgrad"),
+    nw = TcxOp(OP_TCX_NARROW_WGRAD, make, name + ".wgrad")
+    nw.spec = dict(part=part, x=x, gy=gy, rows=rows, K=K, N=N, gy_stride=gy_stride, blocks=blocks)
+    return [nw,
             RawOp(OP_REDUCE, {"dst": dst, "src": part},
                   dict(count=span, stride=span, splits=blocks, accumulate=0, ncols=0, act=0, beta=1.0), False,
                   name + ".fold", ReduceDesc)]
@@ -361,10 +376,12 @@ class CnnNet(object):
 
         def make_s2d(arena):
             return S2dDesc(arena.ptr(x0), arena.ptr(x0_lo), arena.ptr(frames), None, 1 if is_u8 else 0, n_img, 4, 84, 84, 4)
+        s2d = TcxOp(OP_TCX_S2D, make_s2d, "frames_s2d", runtime_idx=gather and not self.full_rows)
+        s2d.spec = dict(out=x0, out_lo=x0_lo, frames=frames, n_img=n_img)
         if self.full_rows:
-            self.prologue.append(TcxOp(OP_TCX_S2D, make_s2d, "frames_s2d"))
+            self.prologue.append(s2d)
         else:
-            ops.append(TcxOp(OP_TCX_S2D, make_s2d, "frames_s2d", runtime_idx=gather))
+            ops.append(s2d)
 
         # ---- conv1: 2 x 2 taps x 64 channels, tile = 12 output rows of one image ----
         kbs = [((c0, bx, by, 0), (by * 2 + bx) * 64 + c0) for by in range(2) for bx in range(2) for c0 in (0, 32)]
@@ -562,3 +579,160 @@ class CnnNet(object):
                            [k * H for k in range(3 * H)]))
         ops.append(self.linear_fwd("gru_ih.dgrad", dgi, dgi_lo, 3 * H, wid, H, gx, gx_lo, mask=r["h"]))
         return ops
+
+
+# ---------------------------------------------------------------------------------------------------
+# numpy emulator of the ops above (CPU tests of the host-side geometry: boxes, tap tables, tilings, weight
+# images, row-offset tables).  Planes: the x plane is treated as the exact fp32 value, lo planes are ignored.
+# ---------------------------------------------------------------------------------------------------
+def _np_view(bufs, ref):
+    name, off = ref
+    return bufs[name][off:]
+
+
+def _tile_base(t, tile):
+    base = [0, 0, 0, 0, 0]
+    tq, tr = divmod(tile, t.t_div)
+    base[t.tr_dim] += tr * t.tr_step
+    base[t.tq_dim] += tq * t.tq_step
+    return base
+
+
+def _box_rows(box):
+    """Box-local indices (i1..i4) of every row, dimension 1 fastest."""
+    import numpy as np
+    r = np.arange(box[1] * box[2] * box[3] * box[4])
+    i1 = r % box[1]; r = r // box[1]
+    i2 = r % box[2]; r = r // box[2]
+    i3 = r % box[3]; i4 = r // box[3]
+    return i1, i2, i3, i4
+
+
+def _load_box(src, dims, strides, box, c, fill=0.0):
+    """[rows, 32] values of the box whose corner has coordinates c (5 ints); out-of-bounds elements are zero."""
+    import numpy as np
+    ii = _box_rows(box)
+    ok = np.ones(ii[0].shape, bool)
+    off = np.zeros(ii[0].shape, np.int64)
+    for d in range(1, 5):
+        g = c[d] + ii[d - 1]
+        ok &= (g >= 0) & (g < dims[d])
+        off += np.clip(g, 0, dims[d] - 1) * strides[d]
+    ch = c[0] + np.arange(32)
+    okc = (ch >= 0) & (ch < dims[0])
+    vals = src[off[:, None] + np.clip(ch, 0, dims[0] - 1)[None, :]].astype(np.float64)
+    return np.where(ok[:, None] & okc[None, :], vals, fill)
+
+
+def _pad5(dims, strides, box):
+    dims, strides, box = list(dims), list(strides), list(box)
+    while len(dims) < 5:
+        strides.append(strides[-1] * dims[-1]); dims.append(1); box.append(1)
+    return dims, strides, box
+
+
+def emulate(op, bufs, idx=None):
+    """Executes one plan-list entry on numpy buffers (dict name -> flat array).  idx: runtime row list."""
+    import numpy as np
+    from . import _engine
+    if isinstance(op, _engine.RawOp):
+        assert op.kind == _engine.OP_REDUCE, op.kind
+        dst, src = _np_view(bufs, op.fields["dst"]), _np_view(bufs, op.fields["src"])
+        cnt, stride, splits = op.ints["count"], op.ints["stride"], op.ints["splits"]
+        dst[:cnt] = sum(src[s * stride:s * stride + cnt].astype(np.float64) for s in range(splits)).astype(np.float32)
+        return
+    k, sp = op.kind, getattr(op, "spec", None)
+    if k == OP_TCX_PREP:
+        img, src, N, K, ntab, ktab = op.prep
+        nt, kt = np.asarray(ntab)[:, None], np.asarray(ktab)[None, :]
+        s = _np_view(bufs, src)
+        bufs[img][:N * K] = np.where((nt >= 0) & (kt >= 0), s[np.maximum(nt, 0) + np.maximum(kt, 0)], 0.0).ravel()
+    elif k == OP_TCX_S2D:
+        fr = _np_view(bufs, sp["frames"])
+        n = sp["n_img"]
+        rows = np.asarray(idx) if (op.runtime_idx and idx is not None) else np.arange(n)
+        f = fr.reshape(-1, 4, 21, 4, 21, 4)[rows].astype(np.float32)            # [b, c, by, dy, bx, dx]
+        _np_view(bufs, sp["out"])[:n * 28224] = f.transpose(0, 2, 4, 1, 3, 5).reshape(-1)
+    elif k == OP_TCX_LO:
+        pass
+    elif k == OP_TCX_COLSUM:
+        x = _np_view(bufs, sp["x"])
+        rows, C, pitch = sp["rows"], sp["C"], sp["pitch"]
+        m = np.lib.stride_tricks.as_strided(x, (rows, C), (pitch * x.itemsize, x.itemsize))
+        part = _np_view(bufs, sp["part"])
+        part[:sp["blocks"] * C] = 0
+        part[:C] = m.astype(np.float64).sum(0)
+    elif k == OP_TCX_NARROW_WGRAD:
+        x, gy = _np_view(bufs, sp["x"]), _np_view(bufs, sp["gy"])
+        rows, K, N, gs = sp["rows"], sp["K"], sp["N"], sp["gy_stride"]
+        X = x[:rows * K].reshape(rows, K).astype(np.float64)
+        G = np.lib.stride_tricks.as_strided(gy, (rows, N), (gs * gy.itemsize, gy.itemsize)).astype(np.float64)
+        part = _np_view(bufs, sp["part"])
+        part[:sp["blocks"] * (N * K + N)] = 0
+        part[:N * K] = (G.T @ X).ravel()
+        part[N * K:N * K + N] = G.sum(0)
+    elif k == OP_TCX_FWD:
+        dims, strides, box = _pad5(sp["dims"], sp["strides"], sp["box"])
+        A = _np_view(bufs, sp["A"])
+        img = bufs[sp["img"]][:sp["img_rows"] * sp["img_cols"]].reshape(sp["img_rows"], sp["img_cols"]).astype(np.float64)
+        out = _np_view(bufs, sp["out"])
+        mask = _np_view(bufs, sp["mask"]) if sp["mask"] is not None else None
+        bias = _np_view(bufs, sp["bias"])[:sp["N"]].astype(np.float64) if sp["bias"] is not None else 0.0
+        os_ = list(sp["o_stride"]) + [0] * (5 - len(sp["o_stride"]))
+        oe = list(sp["o_ext"]) + [1] * (5 - len(sp["o_ext"]))
+        ii = _box_rows(box)
+        N = sp["N"]
+        for tile in range(sp["tiles"].n_tiles):
+            base = _tile_base(sp["tiles"], tile)
+            ba = list(base)
+            if sp["gather_dim"]:
+                ba[sp["gather_dim"]] = int(idx[base[sp["gather_dim"]]])
+            acc = np.zeros((len(ii[0]), N))
+            for a, b in sp["kbs"]:
+                c = [a[0], a[1] + ba[1], a[2] + ba[2], a[3] + ba[3], ba[4]]
+                acc += _load_box(A, dims, strides, box, c) @ img[:N, b:b + 32].T
+            v = acc * sp["alpha"] + bias
+            if sp["act"] == 1:
+                v = np.maximum(v, 0.0)
+            g = [base[d + 1] + ii[d] for d in range(4)]
+            ok = np.ones(len(ii[0]), bool)
+            off = np.full(len(ii[0]), sp["o_base"], np.int64)
+            for d in range(4):
+                ok &= g[d] < oe[d + 1]
+                off += g[d] * os_[d + 1]
+            cb = sp["col_blocks"]
+            for n in range(N):
+                o = off + (cb[1][n // cb[0]] + n % cb[0] if cb else n)
+                col = v[:, n]
+                if mask is not None:
+                    col = np.where(mask[np.where(ok, o, 0)] > 0, col, 0.0)
+                out[o[ok]] = col[ok].astype(np.float32)
+    elif k == OP_TCX_WGRAD:
+        ad, as_, ab = _pad5(sp["a_dims"], sp["a_strides"], sp["a_box"])
+        bd, bs, bb = _pad5(sp["b_dims"], sp["b_strides"], sp["b_box"])
+        A, Bm = _np_view(bufs, sp["A"]), _np_view(bufs, sp["Bm"])
+        part = _np_view(bufs, sp["partial"])
+        part[:sp["splits"] * sp["split_stride"]] = 0
+        G, nbb = len(sp["groups"]), len(sp["b_boxes"])
+        row_off = np.asarray(sp["row_off"])
+        for ota in range(sp["ot_a"]):
+            for otb in range(sp["ot_b"]):
+                D = np.zeros((G * 128, 32 * nbb))
+                for rt in range(sp["rows"].n_tiles):
+                    base = _tile_base(sp["rows"], rt)
+                    ba = list(base)
+                    if sp["gather_dim"]:
+                        ba[sp["gather_dim"]] = int(idx[base[sp["gather_dim"]]])
+                    Bt = np.concatenate([_load_box(Bm, bd, bs, bb, [c[0] + otb * sp["ot_b_step"], c[1] + base[1], c[2] + base[2],
+                                                                      c[3] + base[3], base[4]]) for c in sp["b_boxes"]], 1)
+                    for g, boxes in enumerate(sp["groups"]):
+                        At = np.concatenate([_load_box(A, ad, as_, ab, [c[0] + ota * sp["ot_a_step"], c[1] + ba[1], c[2] + ba[2],
+                                                                         c[3] + ba[3], ba[4]]) for c in boxes], 1)
+                        D[g * 128:(g + 1) * 128] += At.T @ Bt
+                ro = row_off[ota * G * 128:(ota + 1) * G * 128]
+                for n in range(32 * nbb):
+                    col = otb * 32 * nbb + n
+                    if col < sp["n_cols"]:
+                        part[ro[ro >= 0] + col * sp["col_stride"]] = (D[ro >= 0, n] * sp["alpha"]).astype(np.float32)
+    else:
+        raise NotImplementedError(k)
