@@ -298,7 +298,12 @@ def run_ours(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the C5 shard
 # (profiles/r01c_tcx_gru_full_c5.txt); only meaningful for that workload
 NCU_DRAM_SOURCE = "profiles/r01c_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
-NCU_DRAM_BYTES = {}
+NCU_DRAM_BYTES = {
+    "conv1.fwd": 0.925621e9 + 798.895e6, "conv2.fwd": 0.840913e9 + 316.076e6, "conv3.fwd": 0.340068e9 + 83.165e6,
+    "conv2.dgrad": 0.759555e9 + 794.400e6, "conv3.dgrad": 0.272850e9 + 293.151e6,
+    "conv1.wgrad": 1.764648e9 + 4.253e6, "conv2.wgrad": 1.182853e9 + 7.797e6, "conv3.wgrad": 0.442568e9 + 3.896e6,
+    "gru.seq_fwd": 0.053858e9 + 45.924e6, "gru.seq_bwd": 0.104027e9 + 57.874e6,
+}
 
 
 def describe(cfg):
@@ -407,6 +412,7 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
         g = max(gru_rows, key=lambda r: r["ms"])
         fp32_peak = 148 * 128 * 2 * 1.965e-3
         roof["recurrence"] = {"kernel": "a2cb::gru_persistent_%s_kernel" % ("bwd" if g["op"].endswith("bwd") else "fwd"),
+                              "traffic": NCU_DRAM_BYTES.get(g["op"]) if is_c5 else None,
                               "bound": "fp32 pipe + per-step barrier", "achieved": g["tflops"], "peak": fp32_peak,
                               "unit": "TFLOP/s", "frac": g["tflops"] / fp32_peak, "launch_ms": g["ms"],
                               "share_of_step": g["share"]}
