@@ -14,6 +14,7 @@
 // Same buffers and the same saved quantities as the per-step path, so either path can feed the
 // weight-gradient GEMMs and the tests compare both against the reference goldens.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "decls.cuh"
@@ -180,6 +181,126 @@ gru_persistent_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const 
 }
 
 // ---------------------------------------------------------------------------
+// forward, cluster variant: the H / 32 CTAs of ONE environment group are a thread-block cluster.  The masked state
+// hm_t of the group's 8 environments (8 x H floats) lives in every CTA's shared memory, double-buffered; after the
+// gate math each CTA pushes its 8 x 32 slice of hm_{t+1} into all peers through distributed shared memory
+// (st.shared::cluster, 16-byte stores) and the cluster meets at the hardware cluster barrier.  No global-memory
+// round trip and no software barrier remain on the per-step critical path; clusters (environment groups) are
+// completely independent, so there is no co-residency requirement beyond the cluster itself.
+// Correct (same tests as the default kernel) but NOT the default: see gru_cluster_forward() for the measurement.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pg_st_cluster_v4(uint32_t local_addr, uint32_t peer, const float4 v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(peer));
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void pg_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(PG_NT)
+gru_cluster_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh) {
+    extern __shared__ __align__(16) float pg_smem[];
+    const int H = d.H;
+    float* hbuf = pg_smem + 3 * PG_UB * H;                          // [2][PG_RW][H] masked state of the group
+    float* tile = hbuf + 2 * PG_RW * H;                             // [PG_RW][PG_UB] this CTA's slice, staged for the push
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncta = gridDim.x;                                     // cluster size = unit groups
+    const int ub = blockIdx.x * PG_UB;
+    for (int e = tid; e < 3 * PG_UB * H; e += PG_NT) {
+        const int c = e / H, k = e - c * H;
+        const int u = c / 3, g = c - u * 3;
+        pg_smem[e] = Whh[(long)(g * H + ub + u) * H + k];
+    }
+    const float* Ws = pg_smem + (long)warp * 12 * H;
+    const int rl = lane >> 2, jl = lane & 3;
+    const int ku = ub + PG_UW * warp + jl;
+    const float b_r = bhh[ku], b_z = bhh[H + ku], b_n = bhh[2 * H + ku];
+    const int r0 = blockIdx.y * PG_RW;
+    const int my = r0 + rl;
+    const bool live = my < d.N;
+
+    // pushes tile[PG_RW][PG_UB] into hbuf[buf][:, ub .. ub + 31] of every CTA of the cluster (incl. this one)
+    auto push = [&](int buf) {
+        __syncthreads();                                            // tile complete
+        // 64 float4 per peer; warp w serves peers w, w + 8, ...: lanes 0..31 take two float4 each
+        for (int peer = warp; peer < ncta; peer += PG_NW) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int f4 = lane + 32 * q;                       // 0..63: row = f4 / 8, 4-unit chunk = f4 % 8
+                const int r = f4 >> 3, c4 = f4 & 7;
+                const float4 v = *reinterpret_cast<const float4*>(tile + r * PG_UB + c4 * 4);
+                pg_st_cluster_v4(pg_smem_u32(hbuf + ((long)buf * PG_RW + r) * H + ub + c4 * 4), (uint32_t)peer, v);
+            }
+        }
+    };
+
+    // hm_0 = h0 * mask_0
+    {
+        float v = 0.f;
+        if (live) {
+            v = d.h0[(long)my * H + ku] * pg_mask(d, 0, my);
+            d.hm[(long)my * H + ku] = v;
+        }
+        tile[rl * PG_UB + PG_UW * warp + jl] = v;
+        push(0);
+        pg_cluster_sync();
+    }
+
+    for (int t = 0; t < d.T; ++t) {
+        const float* hcur = hbuf + (long)(t & 1) * PG_RW * H;
+        const long row = (long)t * d.N + my;
+        float gi_r = 0.f, gi_z = 0.f, gi_n = 0.f, mnext = 0.f;
+        if (live) {
+            const float* gi = d.gi + row * 3 * H;
+            gi_r = __ldg(gi + ku); gi_z = __ldg(gi + H + ku); gi_n = __ldg(gi + 2 * H + ku);
+            mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, my) : 0.f;
+        }
+        const float hprev = hcur[rl * H + ku];
+        float acc[PG_RW * 12];
+#pragma unroll
+        for (int i = 0; i < PG_RW * 12; ++i) acc[i] = 0.f;
+#pragma unroll 1
+        for (int k0 = 0; k0 < H; k0 += 128) {
+            float4 h[PG_RW];
+#pragma unroll
+            for (int r = 0; r < PG_RW; ++r) h[r] = *reinterpret_cast<const float4*>(hcur + r * H + k0 + 4 * lane);
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                const float4 w = *reinterpret_cast<const float4*>(Ws + c * H + k0 + 4 * lane);
+#pragma unroll
+                for (int r = 0; r < PG_RW; ++r) acc[r * 12 + c] = pg_dot4(h[r], w, acc[r * 12 + c]);
+            }
+        }
+        pg_reduce<PG_RW * 12>(acc, lane);
+        float hm_next = 0.f;
+        if (live) {
+            const float ghr = acc[0] + b_r, ghz = acc[1] + b_z, ghn = acc[2] + b_n;
+            const float rr = pg_sigmoid(gi_r + ghr);
+            const float zz = pg_sigmoid(gi_z + ghz);
+            const float nn = tanhf(gi_n + rr * ghn);
+            const float hn = (1.f - zz) * nn + zz * hprev;
+            d.out[row * H + ku] = hn;
+            if (d.r) {
+                d.r[row * H + ku] = rr; d.z[row * H + ku] = zz; d.n[row * H + ku] = nn;
+                d.gh[row * 3 * H + 2 * H + ku] = ghn;
+            }
+            hm_next = hn * mnext;
+            if (t + 1 < d.T) d.hm[(row + d.N) * H + ku] = hm_next;      // kept for the backward pass
+        }
+        if (t + 1 < d.T) {
+            tile[rl * PG_UB + PG_UW * warp + jl] = hm_next;
+            push((t + 1) & 1);
+            pg_cluster_sync();
+        }
+    }
+    pg_cluster_sync();                                               // no CTA exits while peers may still push into it
+}
+
+// ---------------------------------------------------------------------------
 // backward through time: same ownership; the 32 columns of W_hh (all 3H gate rows, 192 KiB) of the CTA's
 // units stay in shared memory.  Phase A (element-wise gate gradients of its units and environments, needs
 // the carry it computed itself), grid barrier, phase B (carry = dh z + dgh_t W_hh restricted to its units,
@@ -329,11 +450,61 @@ bool gru_persistent_supported(int N, int H) {
     return (long)(H / PG_UB) <= (long)pg_sms() * (pf < pb ? pf : pb);
 }
 
+// Cluster launch of the forward kernel when the H / 32 unit groups fit one cluster (H = 512 -> 16 CTAs, the
+// non-portable maximum).  Returns 1 if launched, 0 if this shape / device cannot take it, < 0 on error.
+static int gru_cluster_forward(const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st) {
+    // Opt-in (A2CB_GRU_CLUSTER=1).  Measured on B200 at H = 512, 8 environment groups: 1.43 ms vs 0.82 ms for the
+    // L2 / counter-barrier kernel -- the 8 clusters of 16 CTAs do not all become co-resident (GPCs of 16-20 SMs, one
+    // die each), so the groups run in two waves; per wave the step time is 5.6 us, no better than the L2 exchange.
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("A2CB_GRU_CLUSTER"); mode = (e && e[0] == '1') ? 1 : 0; }
+    const int ug = d.H / PG_UB;
+    if (!mode || ug < 2 || ug > 16 || (ug & (ug - 1)) != 0) return 0;
+    const size_t smem = (size_t)(3 * PG_UB * d.H + 2 * PG_RW * d.H + PG_RW * PG_UB) * sizeof(float);
+    if (smem > 227 * 1024) return 0;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(gru_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(gru_cluster_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        attr = true;
+    }
+    const int ngrp = (d.N + PG_RW - 1) / PG_RW;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ug, (unsigned)ngrp);
+    cfg.blockDim = dim3(PG_NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ug; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, gru_cluster_fwd_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gru_cluster_fwd_kernel, d, Whh, bhh);
+    if (e != cudaSuccess) {
+        set_error("gru_persistent: cluster launch failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return A2CB_ERR_CUDA;
+    }
+    return check_launch("gru_cluster_fwd") == A2CB_OK ? 1 : A2CB_ERR_CUDA;
+}
+
 int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st) {
     A2CB_REQUIRE(gru_persistent_supported(d.N, d.H), "gru_persistent: unsupported shape (N=%d H=%d)", d.N, d.H);
     A2CB_REQUIRE(Whh && d.hm && d.masks, "gru_persistent: null pointer");
     A2CB_REQUIRE(backward || (bhh && d.h0 && d.gi && d.out), "gru_persistent: forward pointers");
     A2CB_REQUIRE(!backward || (d.r && d.z && d.n && d.gh && d.dout && d.dgi && d.dgh), "gru_persistent: backward pointers");
+    if (!backward) {
+        const int rc = gru_cluster_forward(d, Whh, bhh, st);
+        if (rc != 0) return rc > 0 ? A2CB_OK : rc;
+    }
     const int ug = d.H / PG_UB;                                    // unit groups
     const int ngrp = (d.N + PG_RW - 1) / PG_RW;                    // environment groups
     int gy = pg_sms() / ug;
