@@ -102,9 +102,11 @@ def test_gemm_split_k_and_reduce():
     assert np.all(got["G"][:5] == 3.0)
 
 
+@pytest.mark.parametrize("B", [5, 1, 37])
 @pytest.mark.parametrize("obs_dtype", [torch.uint8, torch.float32])
-def test_cnn_forward_backward_vs_torch(obs_dtype):
-    """Whole CNN trunk + heads through the engine (gathered rows, fused /255) vs torch autograd."""
+def test_cnn_forward_backward_vs_torch(obs_dtype, B):
+    """Whole CNN trunk + heads through the engine (gathered rows, fused /255) vs torch autograd; B covers a single
+    row, partial image tiles and more than one tile of every layer."""
     from a2c_ppo_acktr.model import Policy
 
     class Discrete(object):
@@ -119,9 +121,9 @@ def test_cnn_forward_backward_vs_torch(obs_dtype):
             sd[k] = torch.randn(sd[k].shape, generator=g) * 0.1
     pol.load_state_dict(sd)
     pol.to(DEV)
-    rows, B = 11, 5
+    rows = 11
     obs_u8 = torch.randint(0, 256, (rows, 4, 84, 84), generator=g, dtype=torch.uint8)
-    idx = torch.tensor([7, 0, 3, 10, 3])
+    idx = torch.tensor([7, 0, 3, 10, 3] * 8)[:B]
     action = torch.randint(0, 6, (B, 1), generator=g)
     # torch reference on CPU
     ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
