@@ -340,6 +340,10 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
         elif kind in (14, 15):              # TMA-fed tensor-core engine: labelled by layer
             labels.append(lab)
             flops.append(fl)
+        elif kind in (22, 23):              # fused MLPBase: 19.7 kFLOP / row forward, 36.6 backward (d_in = 11)
+            labels.append("mlp.fused_bwd" if kind == 23 else "mlp.fused_fwd")
+            per_row = 2.0 * (2 * (desc.d_in * 64 + 64 * 64) + 64 * desc.zs)
+            flops.append(desc.B * per_row * (2.0 if kind == 23 else 1.0))
         elif kind in (12, 13):              # persistent GRU recurrence: T steps of [N, H] x [H, 3H] (fp32 SIMT pipe)
             labels.append(kind_names[kind])
             flops.append(2.0 * desc.T * desc.N * 3 * desc.H * desc.H)
@@ -385,12 +389,16 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
              "tflops": float(a[1] / a[0] / 1e9) if a[1] else None} for lab, a in agg.items()]
     rows.sort(key=lambda r: -r["ms"])
     gemm_rows = [r for r in rows if r["tflops"] is not None and not r["op"].startswith("gru.seq")]
+    if not gemm_rows:
+        return None, rows[:24]
     top = gemm_rows[0]
     gru_rows = [r for r in rows if r["op"].startswith("gru.seq")]
     from a2c_ppo_acktr import _native as nat
     peak = pk["tensor_sustained"]
     tcx_ops = any(kind in (14, 15) for kind, _, _ in prog.entries)
-    roof = {"bound": "tensor", "kernel": ("a2cb::tcx_fwd_kernel / tcx_wgrad_kernel (%s)" if tcx_ops else
+    fused_mlp = top["op"].startswith("mlp.fused")
+    roof = {"bound": "tensor", "kernel": ("a2cb::mlp_%s_kernel (%%s; fp32 SIMT, latency-bound at 64 rows)" % top["op"][-3:] if fused_mlp
+                                          else "a2cb::tcx_fwd_kernel / tcx_wgrad_kernel (%s)" if tcx_ops else
                                           "a2cb::gemm_tc_kernel / gemm_kernel (%s)") % top["op"],
             "achieved": top["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": top["tflops"] / peak, "traffic": None,
             "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step); algorithmic fp32 "

@@ -266,6 +266,29 @@ int a2cb_tcx_sizeof(int32_t which);
 int a2cb_tcx_set_knobs(int32_t mn_layout_type, int32_t mn_sbo_bytes, int32_t mn_kstep_bytes, int32_t mn_tma_swizzle);
 
 /* ---------------------------------------------------------------------------
+ * (3c) fused MLPBase                                   a2c_ppo_acktr/model.py:198-229
+ * Both 2-layer tanh trunks (hidden width 64), critic_linear and the distribution head in one launch per direction;
+ * a CTA takes 64 rows through the whole network with all weights and activations in shared memory (exact fp32).
+ * forward: z[b] = (value, head outputs), saves the post-tanh activations; backward: dz -> every weight / bias
+ * gradient of the trunks and heads (per-CTA slabs folded by a2cb_reduce_splits when B > 64).
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    const float* P;
+    float* G;
+    const float* obs;
+    const int64_t* idx;
+    float* acts;          /* [4][B][64]: actor l1, actor l2, critic l1, critic l2 */
+    float* z;             /* [B][zs] */
+    const float* dz;      /* [B][zs] */
+    float* partial;       /* [ceil(B / 64)][span] */
+    int64_t off_a0w, off_a0b, off_a2w, off_a2b, off_c0w, off_c0b, off_c2w, off_c2b, off_hw, off_hb;
+    int64_t span;
+    int32_t B, d_in, H, zs;
+} a2cb_mlp_t;
+int a2cb_mlp_fused(int32_t backward, const a2cb_mlp_t* desc, a2cb_stream_t stream);
+int a2cb_mlp_fused_supported(int32_t d_in, int32_t H, int32_t zs);
+
+/* ---------------------------------------------------------------------------
  * (4) fused loss epilogue                a2c_ppo_acktr/algo/ppo.py:35-37,61-77,86-88
  *                                         algo/a2c_acktr.py:48-51,55-64
  *                                         distributions.py:18-44, model.py:76-77
@@ -365,6 +388,8 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_TCX_COLSUM 19
 #define A2CB_OP_TCX_NARROW_WGRAD 20
 #define A2CB_OP_TCX_PREP_MULTI 21
+#define A2CB_OP_MLP_FWD 22
+#define A2CB_OP_MLP_BWD 23
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;

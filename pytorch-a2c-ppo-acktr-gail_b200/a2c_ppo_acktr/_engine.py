@@ -73,6 +73,17 @@ class SpatialSumDesc(ctypes.Structure):
                 ("C", c_i32), ("ow", c_i32)]
 
 
+class MlpDesc(ctypes.Structure):
+    """Mirror of a2cb_mlp_t."""
+    _fields_ = [("P", c_vp), ("G", c_vp), ("obs", c_vp), ("idx", c_vp), ("acts", c_vp), ("z", c_vp), ("dz", c_vp),
+                ("partial", c_vp)] + [(k, c_i64) for k in ("off_a0w", "off_a0b", "off_a2w", "off_a2b", "off_c0w", "off_c0b",
+                                                            "off_c2w", "off_c2b", "off_hw", "off_hb", "span")] + \
+               [("B", c_i32), ("d_in", c_i32), ("H", c_i32), ("zs", c_i32)]
+
+
+OP_MLP_FWD, OP_MLP_BWD = 22, 23
+
+
 class GruSeqDesc(ctypes.Structure):
     """Mirror of a2cb_gru_seq_t: the per-step descriptor + the recurrent weights."""
     _fields_ = GruDesc._fields_ + [("W_hh", c_vp), ("b_hh", c_vp)]
@@ -116,6 +127,8 @@ _native.register({
     "a2cb_run_ops": (c_i32, [ctypes.POINTER(Op), c_i32, c_vp, c_vp]),
     "a2cb_gru_op": (c_i32, [c_i32, ctypes.POINTER(GruDesc), c_vp]),
     "a2cb_gru_seq": (c_i32, [c_i32, c_vp, c_vp]),
+    "a2cb_mlp_fused": (c_i32, [c_i32, ctypes.POINTER(MlpDesc), c_vp]),
+    "a2cb_mlp_fused_supported": (c_i32, [c_i32, c_i32, c_i32]),
     "a2cb_gru_seq_supported": (c_i32, [c_i32, c_i32]),
 })
 
@@ -386,6 +399,9 @@ class NetBuilder(object):
         self.heads = P.Linear("heads", H, 1 + A)
         # CNN trunk (+ the GRU's input product) on the TMA-fed tensor-core engine (csrc/tcx.cu) unless the exact
         # fp32 SIMT engine was requested; other geometries stay on the affine-indexed engine
+        # MLPBase without GRU: both trunks + heads fused into one launch per direction (csrc/mlp_fused.cu)
+        self.mlp_fused = (not spec.cnn and not spec.recurrent and os.environ.get("A2CB_MLP_FUSED", "1") != "0"
+                          and bool(_native.lib().a2cb_mlp_fused_supported(int(spec.obs_shape[0]), int(H), 1 + A)))
         self.tcx = None
         if (allow_tcx and spec.cnn and spec.obs_shape[0] == 4 and H % 256 == 0 and obs_code in (1, 2)
                 and _native.lib().a2cb_get_gemm_mode() != 0 and os.environ.get("A2CB_TCX", "1") != "0"):
@@ -496,6 +512,38 @@ class NetBuilder(object):
         plans = [p0c, P.linear_forward(l2c, B, hc1, *self.wb("critic2"), hc2, act=P.ACT_TANH),
                  p0a, P.linear_forward(l2a, B, ha1, *self.wb("actor2"), ha2, act=P.ACT_TANH)]
         return plans, (hc2, ha2)
+
+    def mlp_fused_fields(self):
+        B, H = self.B, self.spec.hidden
+        lay, L = self.L.layers, self.L
+        hw, hb = lay["heads"]
+        span = hb + self.zs
+        ints = dict(off_a0w=lay["actor0"][0], off_a0b=lay["actor0"][1], off_a2w=lay["actor2"][0], off_a2b=lay["actor2"][1],
+                    off_c0w=lay["critic0"][0], off_c0b=lay["critic0"][1], off_c2w=lay["critic2"][0], off_c2b=lay["critic2"][1],
+                    off_hw=hw, off_hb=hb, span=span, B=B, d_in=self.spec.obs_shape[0], H=H, zs=self.zs)
+        fields = dict(P=("P", 0), G=("G", 0), obs=(self.obs, 0), acts=self.buf("mlp_acts", 4 * B * H),
+                      z=self.buf("z", B * self.zs))
+        return fields, ints, span
+
+    def mlp_fused_op(self, backward):
+        fields, ints, span = self.mlp_fused_fields()
+        if backward:
+            fields["dz"] = self.buf("dz", self.B * self.zs)
+            ncta = (self.B + 63) // 64
+            if ncta > 1:
+                fields["partial"] = self.buf("mlp_gpart", ncta * span)
+        return RawOp(OP_MLP_BWD if backward else OP_MLP_FWD, fields, ints, self.gather,
+                     "mlp.fused_bwd" if backward else "mlp.fused_fwd", MlpDesc)
+
+    def mlp_fused_backward(self):
+        op = self.mlp_fused_op(True)
+        ncta = (self.B + 63) // 64
+        if ncta == 1:
+            return [op]
+        span = op.ints["span"]
+        return [op, RawOp(OP_REDUCE, {"dst": ("G", 0), "src": op.fields["partial"]},
+                          dict(count=span, stride=span, splits=ncta, accumulate=0, ncols=0, act=0, beta=1.0), False,
+                          "mlp.fold", ReduceDesc)]
 
     def mlp_heads_forward(self, hc2, ha2):
         B, H, A = self.B, self.spec.hidden, self.spec.num_actions
@@ -662,6 +710,8 @@ class NetBuilder(object):
             gops[0].vecA = 1 if s.obs_shape[0] % 4 == 0 else 0
             plans, (hc2, ha2) = self.mlp_forward(x=feat, d_in=s.hidden)
             return gops + plans + self.mlp_heads_forward(hc2, ha2)
+        if self.mlp_fused:
+            return [self.mlp_fused_op(False)]
         plans, (hc2, ha2) = self.mlp_forward()
         return plans + self.mlp_heads_forward(hc2, ha2)
 
@@ -687,6 +737,8 @@ class NetBuilder(object):
             w.gather_red = self.gather
             w.vecA = 0 if self.gather else w.vecA
             return plans + gb
+        if self.mlp_fused:
+            return self.mlp_fused_backward()
         return self.mlp_backward()
 
 

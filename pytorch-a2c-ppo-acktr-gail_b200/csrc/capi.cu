@@ -6,6 +6,7 @@
 #include "loss.cuh"
 #include "gru.cuh"
 #include "tcx.cuh"
+#include "mlp_fused.cuh"
 
 #include <atomic>
 #include <stdarg.h>
@@ -150,6 +151,13 @@ int a2cb_gru_seq(int32_t backward, const a2cb_gru_seq_t* desc, a2cb_stream_t str
 }
 int a2cb_gru_seq_supported(int32_t N, int32_t H) { return gru_persistent_supported(N, H) ? 1 : 0; }
 
+int a2cb_mlp_fused(int32_t backward, const a2cb_mlp_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc, "mlp_fused: null descriptor");
+    static_assert(sizeof(a2cb_mlp_t) == sizeof(MlpDesc), "a2cb_mlp_t out of sync with MlpDesc");
+    return mlp_fused(backward != 0, *reinterpret_cast<const MlpDesc*>(desc), (cudaStream_t)stream);
+}
+int a2cb_mlp_fused_supported(int32_t d_in, int32_t H, int32_t zs) { return mlp_fused_supported(d_in, H, zs) ? 1 : 0; }
+
 int a2cb_tcx_fwd(const a2cb_tcx_fwd_t* desc, a2cb_stream_t stream) {
     A2CB_REQUIRE(desc, "tcx_fwd: null descriptor");
     static_assert(sizeof(a2cb_tcx_fwd_t) == sizeof(TcxFwd), "a2cb_tcx_fwd_t out of sync with TcxFwd");
@@ -288,6 +296,13 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             case A2CB_OP_TCX_COLSUM: {
                 const a2cb_tcx_colsum_t& q = *reinterpret_cast<const a2cb_tcx_colsum_t*>(op.desc);
                 rc = tcx_colsum(q.part, q.x, q.lo, (long)q.rows, q.C, (long)q.pitch, st);
+                break;
+            }
+            case A2CB_OP_MLP_FWD:
+            case A2CB_OP_MLP_BWD: {
+                MlpDesc q = *reinterpret_cast<const MlpDesc*>(op.desc);
+                if (rt) q.idx = idx;
+                rc = mlp_fused(op.kind == A2CB_OP_MLP_BWD, q, st);
                 break;
             }
             case A2CB_OP_TCX_PREP_MULTI: {

@@ -77,4 +77,9 @@ int tcx_prep_multi(const void* jobs, int n_jobs, long total, cudaStream_t st);
 int tcx_narrow_wgrad(float* part, const float* x, const float* gy, long rows, int K, int N, int gy_stride, cudaStream_t st);
 int tcx_narrow_wgrad_blocks(long rows);
 
+// mlp_fused.cu
+struct MlpDesc;
+bool mlp_fused_supported(int d_in, int H, int zs);
+int mlp_fused(int backward, const MlpDesc& d, cudaStream_t st);
+
 }  // namespace a2cb
