@@ -328,7 +328,7 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
     mbs = prog.builder.B if hasattr(prog, "builder") else T * N
     kind_names = {2: "reduce_splits", 3: "loss_epilogue", 4: "grad_norm", 5: "optim_step", 7: "gru_init",
                   8: "gru_gates", 9: "gru_gates_bwd", 10: "bias_pixel_sum", 11: "weight_prep", 12: "gru.seq_fwd",
-                  13: "gru.seq_bwd", 16: "lo_plane", 17: "weight_image", 18: "frames_s2d", 19: "bias_colsum", 20: "heads.wgrad", 21: "weight_image"}
+                  13: "gru.seq_bwd", 16: "lo_plane", 17: "weight_image", 18: "frames_s2d", 19: "bias_colsum", 20: "heads.wgrad", 21: "weight_image", 24: "heads.fwd", 25: "heads.dgrad"}
     labels, flops = [], []
     plan_names = [p for p in getattr(prog, "plan_names", [])]
     gi = 0

@@ -259,6 +259,12 @@ int a2cb_tcx_colsum_blocks(int64_t rows);
 int a2cb_tcx_narrow_wgrad(float* part, const float* x, const float* gy, int64_t rows, int32_t K, int32_t N,
                           int32_t gy_stride, a2cb_stream_t stream);
 int a2cb_tcx_narrow_wgrad_blocks(int64_t rows);
+/* The same narrow layer forward, z[row z_stride + o] = bias[o] + sum_k x[row K + k] W[o K + k], and its data gradient
+ * gx[row K + k] = sum_o dz[row dz_stride + o] W[o K + k] (optionally masked by relu'(mask) and with its lo plane). */
+int a2cb_tcx_narrow_fwd(float* z, const float* x, const float* W, const float* bias, int64_t rows, int32_t K, int32_t N,
+                        int32_t z_stride, a2cb_stream_t stream);
+int a2cb_tcx_narrow_dgrad(float* gx, float* gx_lo, const float* dz, const float* W, const float* mask, int64_t rows,
+                          int32_t K, int32_t N, int32_t dz_stride, a2cb_stream_t stream);
 /* sizeof of a2cb_tcx_fwd_t (0), a2cb_tcx_wgrad_t (1), a2cb_tcx_view_t (2) as compiled: lets a binding check its mirror */
 int a2cb_tcx_sizeof(int32_t which);
 /* hardware-semantics knobs of the MN-major (weight-gradient) path, for probing: UMMA layout type, stride
@@ -390,6 +396,8 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_TCX_PREP_MULTI 21
 #define A2CB_OP_MLP_FWD 22
 #define A2CB_OP_MLP_BWD 23
+#define A2CB_OP_TCX_NARROW_FWD 24
+#define A2CB_OP_TCX_NARROW_DGRAD 25
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -410,6 +418,8 @@ typedef struct { float* out; float* out_lo; const void* frames; const int64_t* i
 typedef struct { float* part; const float* x; int64_t rows; int64_t pitch; int32_t C; int32_t pad_; float* lo; } a2cb_tcx_colsum_t;
 typedef struct { float* part; const float* x; const float* gy; int64_t rows; int32_t K, N, gy_stride, pad_; } a2cb_tcx_narrow_wgrad_t;
 typedef struct { const a2cb_tcx_prep_job_t* jobs; int64_t total; int32_t n_jobs; int32_t pad_; } a2cb_tcx_prep_multi_t;
+typedef struct { float* z; const float* x; const float* W; const float* bias; int64_t rows; int32_t K, N, z_stride, pad_; } a2cb_tcx_narrow_fwd_t;
+typedef struct { float* gx; float* gx_lo; const float* dz; const float* W; const float* mask; int64_t rows; int32_t K, N, dz_stride, pad_; } a2cb_tcx_narrow_dgrad_t;
 typedef struct { int32_t kind; int32_t flags; const void* desc; } a2cb_op_t;
 
 int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_stream_t stream);

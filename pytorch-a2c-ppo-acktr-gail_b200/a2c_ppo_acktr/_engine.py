@@ -677,6 +677,9 @@ class NetBuilder(object):
     # ---- heads (CNN: one [1+A, H] matrix on the shared feature) ----
     def cnn_heads_forward(self, h):
         w, b = self.wb("heads")
+        if self.tcx is not None and self.zs <= 8:
+            # [1 + A, H] heads: one streaming pass over the features (a warp per row)
+            return [_tcx.narrow_fwd_op("heads.fwd", (self.n("z"), 0), h, w, b, self.B, self.spec.hidden, self.zs, self.zs)]
         sp = forward_splits(self.B, self.zs, self.spec.hidden)
         part = self.buf("part_heads_fwd", sp * self.B * self.zs) if sp > 1 else None
         return [P.linear_forward(self.heads, self.B, h, w, b, (self.n("z"), 0), splits=sp, partial=part)]
@@ -691,6 +694,11 @@ class NetBuilder(object):
             wg = _tcx.narrow_wgrad_ops(self, "heads", h, dz, B, H, self.zs, self.zs, gw)
         else:
             wg = [P.linear_wgrad(self.heads, B, h, dz, gw, gb)]
+        if self.tcx is not None and self.zs <= 8:
+            # gradient w.r.t. the features, relu' mask and lo plane in the same pass
+            self.gh_lo = self.buf("gh_lo", B * H) if relu_mask else None      # the GRU consumes the plain plane only
+            return wg + [_tcx.narrow_dgrad_op("heads.dgrad", gh, self.gh_lo, dz, ("P", self.L.layers["heads"][0]),
+                                              h if relu_mask else None, B, H, self.zs, self.zs)], gh
         return wg + [
                 P.linear_dgrad(self.heads, B, dz, ("P", self.L.layers["heads"][0]), gh,
                                mask=h if relu_mask else None, mask_mode=1 if relu_mask else 0)], gh
@@ -726,7 +734,7 @@ class NetBuilder(object):
                 gx_lo = self.buf("gru_dx_lo", self.B * s.hidden) if self.tcx is not None else None
                 return hp + self.gru_backward(h, s.hidden, gfeat, dx=gx, dx_mask=h) + self.cnn_backward(gx, gx_lo)
             hp, gh = self.cnn_heads_backward(h)
-            return hp + self.cnn_backward(gh)
+            return hp + self.cnn_backward(gh, getattr(self, "gh_lo", None))
         self.buf("dz", self.B * self.zs)
         if s.recurrent:
             feat = (self.n("gru_out"), 0)

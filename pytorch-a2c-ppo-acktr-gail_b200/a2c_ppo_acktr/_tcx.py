@@ -54,6 +54,16 @@ class ColsumDesc(ctypes.Structure):
     _fields_ = [("part", c_vp), ("x", c_vp), ("rows", c_i64), ("pitch", c_i64), ("C", c_i32), ("pad_", c_i32), ("lo", c_vp)]
 
 
+class NarrowFwdDesc(ctypes.Structure):
+    _fields_ = [("z", c_vp), ("x", c_vp), ("W", c_vp), ("bias", c_vp), ("rows", c_i64), ("K", c_i32), ("N", c_i32),
+                ("z_stride", c_i32), ("pad_", c_i32)]
+
+
+class NarrowDgradDesc(ctypes.Structure):
+    _fields_ = [("gx", c_vp), ("gx_lo", c_vp), ("dz", c_vp), ("W", c_vp), ("mask", c_vp), ("rows", c_i64), ("K", c_i32),
+                ("N", c_i32), ("dz_stride", c_i32), ("pad_", c_i32)]
+
+
 class PrepJob(ctypes.Structure):
     _fields_ = [("img", c_vp), ("img_lo", c_vp), ("src", c_vp), ("ntab", c_vp), ("ktab", c_vp), ("N", c_i64), ("K", c_i64),
                 ("first", c_i64)]
@@ -69,6 +79,8 @@ class NarrowWgradDesc(ctypes.Structure):
 
 
 _native.register({
+    "a2cb_tcx_narrow_fwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
+    "a2cb_tcx_narrow_dgrad": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
     "a2cb_tcx_prep_multi": (c_i32, [c_vp, c_i32, c_i64, c_vp]),
     "a2cb_tcx_narrow_wgrad": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
     "a2cb_tcx_narrow_wgrad_blocks": (c_i32, [c_i64]),
@@ -113,6 +125,7 @@ def tiling(n_tiles, tr_dim, tr_step, t_div=None, tq_dim=4, tq_step=0):
 OP_TCX_FWD, OP_TCX_WGRAD, OP_TCX_LO, OP_TCX_PREP, OP_TCX_S2D, OP_TCX_COLSUM = 14, 15, 16, 17, 18, 19
 OP_TCX_NARROW_WGRAD = 20
 OP_TCX_PREP_MULTI = 21
+OP_TCX_NARROW_FWD, OP_TCX_NARROW_DGRAD = 24, 25
 
 
 class TcxOp(object):
@@ -280,6 +293,23 @@ def colsum_blocks(rows):
 def narrow_wgrad_blocks(rows):
     # mirrors tcx_narrow_wgrad_blocks (csrc/tcx_aux.cu)
     return int(min((rows + 63) // 64, 148 * 4))
+
+
+def narrow_fwd_op(name, z, x, W, bias, rows, K, N, z_stride):
+    def make(arena):
+        return NarrowFwdDesc(arena.ptr(z), arena.ptr(x), arena.ptr(W), arena.ptr(bias), rows, K, N, z_stride, 0)
+    op = TcxOp(OP_TCX_NARROW_FWD, make, name)
+    op.spec = dict(z=z, x=x, W=W, bias=bias, rows=rows, K=K, N=N, z_stride=z_stride)
+    return op
+
+
+def narrow_dgrad_op(name, gx, gx_lo, dz, W, mask, rows, K, N, dz_stride):
+    def make(arena):
+        return NarrowDgradDesc(arena.ptr(gx), arena.ptr(gx_lo), arena.ptr(dz), arena.ptr(W), arena.ptr(mask), rows, K, N,
+                               dz_stride, 0)
+    op = TcxOp(OP_TCX_NARROW_DGRAD, make, name)
+    op.spec = dict(gx=gx, gx_lo=gx_lo, dz=dz, W=W, mask=mask, rows=rows, K=K, N=N, dz_stride=dz_stride)
+    return op
 
 
 def narrow_wgrad_ops(nb, name, x, gy, rows, K, N, gy_stride, dst):

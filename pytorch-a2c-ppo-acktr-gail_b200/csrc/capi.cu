@@ -189,6 +189,14 @@ int a2cb_tcx_narrow_wgrad(float* part, const float* x, const float* gy, int64_t 
                           int32_t gy_stride, a2cb_stream_t stream) {
     return tcx_narrow_wgrad(part, x, gy, (long)rows, K, N, gy_stride, (cudaStream_t)stream);
 }
+int a2cb_tcx_narrow_fwd(float* z, const float* x, const float* W, const float* bias, int64_t rows, int32_t K, int32_t N,
+                        int32_t z_stride, a2cb_stream_t stream) {
+    return tcx_narrow_fwd(z, x, W, bias, (long)rows, K, N, z_stride, (cudaStream_t)stream);
+}
+int a2cb_tcx_narrow_dgrad(float* gx, float* gx_lo, const float* dz, const float* W, const float* mask, int64_t rows,
+                          int32_t K, int32_t N, int32_t dz_stride, a2cb_stream_t stream) {
+    return tcx_narrow_dgrad(gx, gx_lo, dz, W, mask, (long)rows, K, N, dz_stride, (cudaStream_t)stream);
+}
 int a2cb_tcx_narrow_wgrad_blocks(int64_t rows) { return tcx_narrow_wgrad_blocks((long)rows); }
 int a2cb_tcx_sizeof(int32_t which) {
     return which == 0 ? (int)sizeof(TcxFwd) : which == 1 ? (int)sizeof(TcxWgrad) : (int)sizeof(TcxView);
@@ -303,6 +311,16 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
                 MlpDesc q = *reinterpret_cast<const MlpDesc*>(op.desc);
                 if (rt) q.idx = idx;
                 rc = mlp_fused(op.kind == A2CB_OP_MLP_BWD, q, st);
+                break;
+            }
+            case A2CB_OP_TCX_NARROW_FWD: {
+                const a2cb_tcx_narrow_fwd_t& q = *reinterpret_cast<const a2cb_tcx_narrow_fwd_t*>(op.desc);
+                rc = tcx_narrow_fwd(q.z, q.x, q.W, q.bias, (long)q.rows, q.K, q.N, q.z_stride, st);
+                break;
+            }
+            case A2CB_OP_TCX_NARROW_DGRAD: {
+                const a2cb_tcx_narrow_dgrad_t& q = *reinterpret_cast<const a2cb_tcx_narrow_dgrad_t*>(op.desc);
+                rc = tcx_narrow_dgrad(q.gx, q.gx_lo, q.dz, q.W, q.mask, (long)q.rows, q.K, q.N, q.dz_stride, st);
                 break;
             }
             case A2CB_OP_TCX_PREP_MULTI: {

@@ -76,6 +76,10 @@ int tcx_colsum_blocks(long rows);
 int tcx_prep_multi(const void* jobs, int n_jobs, long total, cudaStream_t st);
 int tcx_narrow_wgrad(float* part, const float* x, const float* gy, long rows, int K, int N, int gy_stride, cudaStream_t st);
 int tcx_narrow_wgrad_blocks(long rows);
+int tcx_narrow_fwd(float* z, const float* x, const float* W, const float* bias, long rows, int K, int N, int z_stride,
+                   cudaStream_t st);
+int tcx_narrow_dgrad(float* gx, float* gx_lo, const float* dz, const float* W, const float* mask, long rows, int K, int N,
+                     int dz_stride, cudaStream_t st);
 
 // mlp_fused.cu
 struct MlpDesc;

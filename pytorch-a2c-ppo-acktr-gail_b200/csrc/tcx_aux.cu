@@ -197,6 +197,62 @@ tcx_narrow_wgrad_kernel(float* __restrict__ part, const float* __restrict__ x, c
     }
 }
 
+// Narrow Linear layer forward (heads): z[row][o] = bias[o] + sum_k x[row][k] W[o][k], o < N <= 8.  One warp per row,
+// lanes split k with 16-byte loads (x is streamed once: HBM-bound), N warp reductions.
+template <int N>
+__global__ void __launch_bounds__(256)
+tcx_narrow_fwd_kernel(float* __restrict__ z, const float* __restrict__ x, const float* __restrict__ W,
+                      const float* __restrict__ bias, long rows, int K, int z_stride) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float acc[N];
+#pragma unroll
+    for (int o = 0; o < N; ++o) acc[o] = 0.f;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * K);
+    for (int k4 = lane; k4 < K / 4; k4 += 32) {
+        const float4 xv = xr[k4];
+#pragma unroll
+        for (int o = 0; o < N; ++o) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (long)o * K) + k4);
+            acc[o] = fmaf(xv.x, wv.x, acc[o]); acc[o] = fmaf(xv.y, wv.y, acc[o]);
+            acc[o] = fmaf(xv.z, wv.z, acc[o]); acc[o] = fmaf(xv.w, wv.w, acc[o]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < N; ++o) acc[o] = warp_sum(acc[o]);
+    if (lane == 0) {
+#pragma unroll
+        for (int o = 0; o < N; ++o) z[row * z_stride + o] = acc[o] + __ldg(bias + o);
+    }
+}
+
+// Narrow Linear layer data gradient: gx[row][k] = sum_o dz[row][o] W[o][k], optionally masked by relu'(mask) and
+// with the lo plane of the result.  Thread = (row, 4 consecutive k); W (N x K) is read through L1.
+template <int N>
+__global__ void __launch_bounds__(256)
+tcx_narrow_dgrad_kernel(float4* __restrict__ gx, float4* __restrict__ gx_lo, const float* __restrict__ dz,
+                        const float* __restrict__ W, const float4* __restrict__ mask, long rows, int K, int dz_stride) {
+    const int k4n = K / 4;
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * k4n) return;
+    const long row = e / k4n;
+    const int k4 = (int)(e - row * k4n);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int o = 0; o < N; ++o) {
+        const float g = __ldg(dz + row * dz_stride + o);
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (long)o * K) + k4);
+        s.x = fmaf(g, wv.x, s.x); s.y = fmaf(g, wv.y, s.y); s.z = fmaf(g, wv.z, s.z); s.w = fmaf(g, wv.w, s.w);
+    }
+    if (mask) {
+        const float4 m = mask[e];
+        s.x = m.x > 0.f ? s.x : 0.f; s.y = m.y > 0.f ? s.y : 0.f; s.z = m.z > 0.f ? s.z : 0.f; s.w = m.w > 0.f ? s.w : 0.f;
+    }
+    gx[e] = s;
+    if (gx_lo) gx_lo[e] = make_float4(ax_lo(s.x), ax_lo(s.y), ax_lo(s.z), ax_lo(s.w));
+}
+
 }  // namespace
 
 int tcx_lo_plane(float* lo, const float* x, long n, cudaStream_t st) {
@@ -246,6 +302,30 @@ int tcx_colsum(float* part, const float* x, float* lo, long rows, int C, long pi
     if (lo) tcx_colsum_kernel<true><<<blocks, 256, 0, st>>>(part, x, lo, rows, C, pitch, per);
     else tcx_colsum_kernel<false><<<blocks, 256, 0, st>>>(part, x, nullptr, rows, C, pitch, per);
     return check_launch("tcx_colsum");
+}
+
+int tcx_narrow_fwd(float* z, const float* x, const float* W, const float* bias, long rows, int K, int N, int z_stride,
+                   cudaStream_t st) {
+    A2CB_REQUIRE(z && x && W && bias && rows > 0 && K > 0 && K % 4 == 0 && N >= 1 && N <= 8, "tcx_narrow_fwd: bad arguments");
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    switch (N) {
+#define A2CB_NF(n) case n: tcx_narrow_fwd_kernel<n><<<grid, 256, 0, st>>>(z, x, W, bias, rows, K, z_stride); break;
+        A2CB_NF(1) A2CB_NF(2) A2CB_NF(3) A2CB_NF(4) A2CB_NF(5) A2CB_NF(6) A2CB_NF(7) A2CB_NF(8)
+#undef A2CB_NF
+    }
+    return check_launch("tcx_narrow_fwd");
+}
+
+int tcx_narrow_dgrad(float* gx, float* gx_lo, const float* dz, const float* W, const float* mask, long rows, int K, int N,
+                     int dz_stride, cudaStream_t st) {
+    A2CB_REQUIRE(gx && dz && W && rows > 0 && K > 0 && K % 4 == 0 && N >= 1 && N <= 8, "tcx_narrow_dgrad: bad arguments");
+    const unsigned grid = (unsigned)((rows * (K / 4) + 255) / 256);
+    switch (N) {
+#define A2CB_ND(n) case n: tcx_narrow_dgrad_kernel<n><<<grid, 256, 0, st>>>(reinterpret_cast<float4*>(gx), reinterpret_cast<float4*>(gx_lo), dz, W, reinterpret_cast<const float4*>(mask), rows, K, dz_stride); break;
+        A2CB_ND(1) A2CB_ND(2) A2CB_ND(3) A2CB_ND(4) A2CB_ND(5) A2CB_ND(6) A2CB_ND(7) A2CB_ND(8)
+#undef A2CB_ND
+    }
+    return check_launch("tcx_narrow_dgrad");
 }
 
 int tcx_prep_multi(const void* jobs, int n_jobs, long total, cudaStream_t st) {
