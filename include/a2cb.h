@@ -210,6 +210,7 @@ typedef struct {
     int32_t gather_dim;   /* image gather: A coordinate of this dimension -> gather_idx[coordinate]; 0 = off */
     int64_t o_cb_off[4];
     const int64_t* gather_idx; /* device list (minibatch rows inside a whole-rollout tensor, storage.py:127,181) */
+    float* colsum_part;   /* optional [CTAs][N] partial column sums of the stored values (bias gradients); N <= 128 */
 } a2cb_tcx_fwd_t;
 typedef struct {
     a2cb_tcx_view_t A;

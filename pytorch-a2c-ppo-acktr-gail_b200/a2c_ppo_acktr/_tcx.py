@@ -26,7 +26,7 @@ class FwdDesc(ctypes.Structure):
                 ("chain", c_i32), ("kb_a", (c_i16 * 4) * MAX_KB), ("kb_b", c_i32 * MAX_KB), ("tiles", Tiling),
                 ("out", c_vp), ("out_lo", c_vp), ("mask", c_vp), ("bias", c_vp), ("o_stride", c_i64 * 5),
                 ("o_base", c_i64), ("o_ext", c_i32 * 5), ("N", c_i32), ("alpha", c_f32), ("act", c_i32),
-                ("o_cb", c_i32), ("gather_dim", c_i32), ("o_cb_off", c_i64 * 4), ("gather_idx", c_vp)]
+                ("o_cb", c_i32), ("gather_dim", c_i32), ("o_cb_off", c_i64 * 4), ("gather_idx", c_vp), ("colsum_part", c_vp)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -144,7 +144,8 @@ def _itab(arena, name, values):
 
 
 def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tiles, out, out_lo, o_stride, o_ext, N,
-           alpha=1.0, bias=None, act=0, mask=None, chain=4, o_base=0, flops=0.0, col_blocks=None, gather_dim=0):
+           alpha=1.0, bias=None, act=0, mask=None, chain=4, o_base=0, flops=0.0, col_blocks=None, gather_dim=0,
+           colsum_part=None):
     """col_blocks: (block width, [offset per block]) -- see a2cb_tcx_fwd_t.o_cb."""
     assert len(kbs) <= MAX_KB, (name, len(kbs))
 
@@ -171,11 +172,12 @@ def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tile
                 d.o_cb_off[i] = o
         d.gather_dim = gather_dim
         d.gather_idx = 1 if gather_dim else None          # placeholder: a2cb_run_ops substitutes the runtime row list
+        d.colsum_part = arena.ptr(colsum_part)
         return d
     op = TcxOp(OP_TCX_FWD, make, name, flops=flops, runtime_idx=bool(gather_dim))
     op.spec = dict(A=A, dims=dims, strides=strides, box=box, img=img, img_rows=img_rows, img_cols=img_cols, kbs=kbs,
                    tiles=tiles, out=out, o_stride=o_stride, o_ext=o_ext, N=N, alpha=alpha, bias=bias, act=act, mask=mask,
-                   o_base=o_base, col_blocks=col_blocks, gather_dim=gather_dim)
+                   o_base=o_base, col_blocks=col_blocks, gather_dim=gather_dim, colsum_part=colsum_part)
     return op
 
 
@@ -283,6 +285,12 @@ def colsum_op(name, part, x, rows, C, pitch, lo=None):
     op = TcxOp(OP_TCX_COLSUM, make, name)
     op.spec = dict(part=part, x=x, rows=rows, C=C, pitch=pitch, lo=lo, blocks=colsum_blocks(rows))
     return op
+
+
+def fwd_grid(n_tiles, N):
+    """CTAs of a forward-like launch (persistent kernel: min(work items, SMs)); mirrors launch_fwd in csrc/tcx.cu."""
+    bn = 32 if N <= 32 else (64 if N <= 64 else 128)
+    return int(min(n_tiles * (-(-N // bn)), 148))
 
 
 def colsum_blocks(rows):
@@ -515,23 +523,29 @@ class CnnNet(object):
         ops += self.bias_grad("conv3", g3, B * 49, 32, self.G("base.main.4.bias"))
         kbs = [((0, -kx, -ky, 0), (ky * 3 + kx) * 32) for ky in range(3) for kx in range(3)]
         k = 3
+        # conv2's bias gradient = column sums of g2: accumulated by the epilogue that writes g2 (one partial row per CTA)
+        n_t = -(-B // k)
+        bp2 = nb.buf("bpart_conv2", fwd_grid(n_t, 64) * 64)
         ops.append(fwd_op("conv3.dgrad", g3, g3_lo, (32, 7, 7, B), (1, 32, 224, 1568), (32, 9, 9, k), w3d, 64, 288, kbs,
-                          tiling(-(-B // k), 3, k), g2, g2_lo, (0, 64, 576, 5184), (0, 9, 9, B), 64, mask=r["a2"], chain=5,
-                          flops=2.0 * B * 49 * 32 * 576))
+                          tiling(n_t, 3, k), g2, g2_lo, (0, 64, 576, 5184), (0, 9, 9, B), 64, mask=r["a2"], chain=5,
+                          flops=2.0 * B * 49 * 32 * 576, colsum_part=bp2))
+        ops.append(self.fold("conv2.bias", bp2, self.G("base.main.2.bias"), 64, fwd_grid(n_t, 64)))
         # ---- conv2 ----
         ops += self.conv2_wgrad(g2, g2_lo)
-        ops += self.bias_grad("conv2", g2, B * 81, 64, self.G("base.main.2.bias"))
         # the four stride-parity classes (py, px) of the transposed convolution read the SAME boxes of g2 (tap (b, a)
         # -> rows (u - b, v - a)); only the weights differ, so they are 4 x 32 columns of one product
         k = 1          # 100 rows / tile: one M block, 64 KiB stages -> a 3-deep pipeline (2 images would leave only 2 stages)
         kbs = [((c0, -a, -b, 0), (b * 2 + a) * 64 + c0) for b in range(2) for a in range(2) for c0 in (0, 32)]
+        n_t = -(-B // k)
+        bp1 = nb.buf("bpart_conv1", fwd_grid(n_t, 128) * 128)
         ops.append(fwd_op("conv2.dgrad", g2, g2_lo, (64, 9, 9, B), (1, 64, 576, 5184), (32, 10, 10, k), w2d, 128, 256,
-                          kbs, tiling(-(-B // k), 3, k), g1, g1_lo, (0, 64, 1280, 12800), (0, 10, 10, B), 128,
+                          kbs, tiling(n_t, 3, k), g1, g1_lo, (0, 64, 1280, 12800), (0, 10, 10, B), 128,
                           mask=r["a1"], flops=2.0 * B * 81 * 64 * 512,
-                          col_blocks=(32, [(py * 20 + px) * 32 for py in range(2) for px in range(2)])))
+                          col_blocks=(32, [(py * 20 + px) * 32 for py in range(2) for px in range(2)]), colsum_part=bp1))
+        # conv1's bias gradient: the partial rows hold 4 parity classes x 32 channels -> fold over CTAs and classes
+        ops.append(self.fold("conv1.bias", bp1, self.G("base.main.0.bias"), 32, 4 * fwd_grid(n_t, 128)))
         # ---- conv1 ----
         ops += self.conv1_wgrad(g1, g1_lo)
-        ops += self.bias_grad("conv1", g1, B * 400, 32, self.G("base.main.0.bias"))
         return ops
 
     def conv3_wgrad(self, g3, g3_lo):
@@ -712,6 +726,7 @@ def emulate(op, bufs, idx=None):
         oe = list(sp["o_ext"]) + [1] * (5 - len(sp["o_ext"]))
         ii = _box_rows(box)
         N = sp["N"]
+        csum = np.zeros(N)
         for tile in range(sp["tiles"].n_tiles):
             base = _tile_base(sp["tiles"], tile)
             ba = list(base)
@@ -737,6 +752,12 @@ def emulate(op, bufs, idx=None):
                 if mask is not None:
                     col = np.where(mask[np.where(ok, o, 0)] > 0, col, 0.0)
                 out[o[ok]] = col[ok].astype(np.float32)
+                if sp.get("colsum_part") is not None:
+                    csum[n] += col[ok].sum()
+        if sp.get("colsum_part") is not None:
+            part = _np_view(bufs, sp["colsum_part"])
+            part[:fwd_grid(sp["tiles"].n_tiles, N) * N] = 0
+            part[:N] = csum
     elif k == OP_TCX_WGRAD:
         ad, as_, ab = _pad5(sp["a_dims"], sp["a_strides"], sp["a_box"])
         bd, bs, bb = _pad5(sp["b_dims"], sp["b_strides"], sp["b_box"])

@@ -258,6 +258,10 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3, hf = (warp - TX_EPI0) >> 2;          // TMEM lane quadrant, column half
         const int b1 = p.A.box[1], b2 = p.A.box[2], b3 = p.A.box[3];
         int cc = 0;
+        constexpr int NCH = (HALF + 31) / 32;                        // 32-column passes of the store phase
+        float4 bsum[NCH];                                            // column sums of what this lane stores (bias gradient)
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) bsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             int base[5];
             tx_tile_base(p.tiles, w / n_n, base);
@@ -382,9 +386,28 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         *reinterpret_cast<float4*>(p.out + off + ch) = v;
                         if (p.out_lo)
                             *reinterpret_cast<float4*>(p.out_lo + off + ch) = make_float4(tx_lo(v.x), tx_lo(v.y), tx_lo(v.z), tx_lo(v.w));
+                        bsum[cc0 / 32].x += v.x; bsum[cc0 / 32].y += v.y; bsum[cc0 / 32].z += v.z; bsum[cc0 / 32].w += v.w;
                     }
                   }
                 }
+            }
+        }
+        if (p.colsum_part) {
+            // lanes with the same lane % LPR hold sums of the same 4 columns: fold them, then park the warp's HALF sums in
+            // its own staging slab for the cross-warp fold after the final barrier
+            constexpr int CWc = HALF < 32 ? HALF : 32;
+            constexpr int LPRc = CWc / 4;
+            float* wsum = reinterpret_cast<float*>(stage_base + (warp - TX_EPI0) * 2048);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                float4 t = bsum[i];
+#pragma unroll
+                for (int o = LPRc; o < 32; o <<= 1) {
+                    t.x += __shfl_xor_sync(0xffffffffu, t.x, o); t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+                    t.z += __shfl_xor_sync(0xffffffffu, t.z, o); t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
+                }
+                if (lane < LPRc) *reinterpret_cast<float4*>(wsum + i * 32 + lane * 4) = t;
             }
         }
     }
@@ -392,6 +415,14 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * MB * BN)));
+    }
+    if (p.colsum_part && threadIdx.x < BN && (int)threadIdx.x < p.N) {
+        // column n lives in column half n / HALF: sum its four quadrant warps (fixed order) -> one partial row per CTA
+        const int n = threadIdx.x, h = n / HALF, c = n - h * HALF;
+        float s = 0.f;
+#pragma unroll
+        for (int qi = 0; qi < 4; ++qi) s += reinterpret_cast<const float*>(stage_base + (h * 4 + qi) * 2048)[c];
+        p.colsum_part[(long)blockIdx.x * p.N + n] = s;
     }
 }
 
@@ -699,6 +730,7 @@ int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
     A2CB_REQUIRE(p.n_kb >= 1 && p.n_kb <= TCX_MAX_KB, "tcx_fwd: n_kb = %d out of range", p.n_kb);
     A2CB_REQUIRE(p.N > 0 && p.N % 4 == 0, "tcx_fwd: N = %d must be a positive multiple of 4", p.N);
     A2CB_REQUIRE(p.gather_dim == 0 || (p.gather_dim >= 1 && p.gather_dim <= 4 && p.gather_idx), "tcx_fwd: bad gather");
+    A2CB_REQUIRE(!p.colsum_part || p.N <= 128, "tcx_fwd: column sums need a single column tile (N <= 128)");
     A2CB_REQUIRE(p.o_cb == 0 || (p.o_cb % 4 == 0 && !p.bias && (p.N + p.o_cb - 1) / p.o_cb <= 4), "tcx_fwd: bad column blocks");
     A2CB_REQUIRE(p.tiles.n_tiles > 0 && p.tiles.t_div > 0 && p.tiles.tr_dim >= 1 && p.tiles.tr_dim <= 4 &&
                  p.tiles.tq_dim >= 1 && p.tiles.tq_dim <= 4, "tcx_fwd: bad tiling");

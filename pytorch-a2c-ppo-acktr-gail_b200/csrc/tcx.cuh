@@ -54,6 +54,9 @@ struct TcxFwd {
     int32_t gather_dim;
     int64_t o_cb_off[4];
     const int64_t* gather_idx;
+    // optional: column sums of the stored values (= bias gradient of the layer that produced this gradient), one
+    // partial row [N] per CTA at colsum_part[blockIdx.x * N + n]; single column tile only (N <= BN)
+    float* colsum_part;
 };
 
 // partial[split][row_off[m] + n * col_stride] = alpha * sum_rows A[row, m] * Bm[row, n]
