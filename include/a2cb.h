@@ -211,6 +211,9 @@ typedef struct {
     int64_t o_cb_off[4];
     const int64_t* gather_idx; /* device list (minibatch rows inside a whole-rollout tensor, storage.py:127,181) */
     float* colsum_part;   /* optional [CTAs][N] partial column sums of the stored values (bias gradients); N <= 128 */
+    const float* B3;      /* bf16 mode: third plane of the weight image */
+    int32_t bf16;         /* 1: A.x and B / B_lo / B3 hold bf16 (exact operands, e.g. uint8 frames); 64-channel k-blocks */
+    int32_t pad2_;
 } a2cb_tcx_fwd_t;
 typedef struct {
     a2cb_tcx_view_t A;
@@ -242,13 +245,18 @@ int a2cb_tcx_prep_weights(float* img, float* img_lo, const float* src, int64_t N
                           const int32_t* ktab, a2cb_stream_t stream);
 /* Several weight images in one launch.  jobs: device array of a2cb_tcx_prep_job_t (first = index of the image's first
  * element in the concatenated element range of all jobs, ascending), total = sum of N K. */
-typedef struct { float* img; float* img_lo; const float* src; const int32_t* ntab; const int32_t* ktab; int64_t N, K, first; } a2cb_tcx_prep_job_t;
+typedef struct { float* img; float* img_lo; const float* src; const int32_t* ntab; const int32_t* ktab; int64_t N, K, first;
+                 float* img3; int64_t bf16; /* bf16 = 1: img, img_lo, img3 are bf16 planes b1, b2, b3 with w = b1 + b2 + b3 */
+} a2cb_tcx_prep_job_t;
 int a2cb_tcx_prep_multi(const a2cb_tcx_prep_job_t* jobs, int32_t n_jobs, int64_t total, a2cb_stream_t stream);
 /* frames [*, C, H, W] (uint8 or fp32; rows through idx, NULL = identity) -> fp32 space-to-depth
  * [B, H/S, W/S, C*S*S], channel (c, dy, dx): fuses the minibatch gather of storage.py:127 with the layout
  * change that turns the stride-S first convolution into a stride-1 one.  out_lo optional. */
 int a2cb_tcx_s2d(float* out, float* out_lo, const void* frames, int32_t src_is_u8, const int64_t* idx, int32_t B,
                  int32_t C, int32_t H, int32_t W, int32_t S, a2cb_stream_t stream);
+/* same with an additional bf16 copy of the output (Atari geometry only) */
+int a2cb_tcx_s2d_b16(float* out, float* out_lo, void* out_b16, const void* frames, int32_t src_is_u8, const int64_t* idx,
+                     int32_t B, int32_t C, int32_t H, int32_t W, int32_t S, a2cb_stream_t stream);
 /* part[blk][c] = partial column sums of x[rows][C] (row pitch in elements); a2cb_tcx_colsum_blocks(rows)
  * partials, folded by a2cb_reduce_splits: bias gradients.  lo (optional): also writes the lo plane of x in the
  * same pass (the GRU's gate gradients need both). */
@@ -415,7 +423,8 @@ typedef struct { void* dst; int64_t bytes; int32_t value; int32_t pad_; } a2cb_f
 typedef struct { float* out; const float* in; int64_t img_stride; int64_t pitch; int32_t B, P, C, ow; } a2cb_spatial_sum_t;
 typedef struct { float* lo; const float* x; int64_t n; } a2cb_tcx_lo_t;
 typedef struct { float* img; float* img_lo; const float* src; int64_t N, K; const int32_t* ntab; const int32_t* ktab; } a2cb_tcx_prep_t;
-typedef struct { float* out; float* out_lo; const void* frames; const int64_t* idx; int32_t src_is_u8, B, C, H, W, S; } a2cb_tcx_s2d_t;
+typedef struct { float* out; float* out_lo; const void* frames; const int64_t* idx; int32_t src_is_u8, B, C, H, W, S;
+                 void* out_b16; /* optional bf16 copy of out (uint8 frames are exact in bf16) */ } a2cb_tcx_s2d_t;
 typedef struct { float* part; const float* x; int64_t rows; int64_t pitch; int32_t C; int32_t pad_; float* lo; } a2cb_tcx_colsum_t;
 typedef struct { float* part; const float* x; const float* gy; int64_t rows; int32_t K, N, gy_stride, pad_; } a2cb_tcx_narrow_wgrad_t;
 typedef struct { const a2cb_tcx_prep_job_t* jobs; int64_t total; int32_t n_jobs; int32_t pad_; } a2cb_tcx_prep_multi_t;

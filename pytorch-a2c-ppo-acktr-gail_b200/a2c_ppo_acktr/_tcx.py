@@ -26,7 +26,8 @@ class FwdDesc(ctypes.Structure):
                 ("chain", c_i32), ("kb_a", (c_i16 * 4) * MAX_KB), ("kb_b", c_i32 * MAX_KB), ("tiles", Tiling),
                 ("out", c_vp), ("out_lo", c_vp), ("mask", c_vp), ("bias", c_vp), ("o_stride", c_i64 * 5),
                 ("o_base", c_i64), ("o_ext", c_i32 * 5), ("N", c_i32), ("alpha", c_f32), ("act", c_i32),
-                ("o_cb", c_i32), ("gather_dim", c_i32), ("o_cb_off", c_i64 * 4), ("gather_idx", c_vp), ("colsum_part", c_vp)]
+                ("o_cb", c_i32), ("gather_dim", c_i32), ("o_cb_off", c_i64 * 4), ("gather_idx", c_vp), ("colsum_part", c_vp),
+                ("B3", c_vp), ("bf16", c_i32), ("pad2_", c_i32)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -47,7 +48,7 @@ class PrepDesc(ctypes.Structure):
 
 class S2dDesc(ctypes.Structure):
     _fields_ = [("out", c_vp), ("out_lo", c_vp), ("frames", c_vp), ("idx", c_vp), ("src_is_u8", c_i32), ("B", c_i32),
-                ("C", c_i32), ("H", c_i32), ("W", c_i32), ("S", c_i32)]
+                ("C", c_i32), ("H", c_i32), ("W", c_i32), ("S", c_i32), ("out_b16", c_vp)]
 
 
 class ColsumDesc(ctypes.Structure):
@@ -66,7 +67,7 @@ class NarrowDgradDesc(ctypes.Structure):
 
 class PrepJob(ctypes.Structure):
     _fields_ = [("img", c_vp), ("img_lo", c_vp), ("src", c_vp), ("ntab", c_vp), ("ktab", c_vp), ("N", c_i64), ("K", c_i64),
-                ("first", c_i64)]
+                ("first", c_i64), ("img3", c_vp), ("bf16", c_i64)]
 
 
 class PrepMultiDesc(ctypes.Structure):
@@ -89,6 +90,7 @@ _native.register({
     "a2cb_tcx_lo_plane": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "a2cb_tcx_prep_weights": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "a2cb_tcx_s2d": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "a2cb_tcx_s2d_b16": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "a2cb_tcx_colsum": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i64, c_vp]),
     "a2cb_tcx_colsum_blocks": (c_i32, [c_i64]),
     "a2cb_tcx_sizeof": (c_i32, [c_i32]),
@@ -96,7 +98,7 @@ _native.register({
 })
 
 
-def view(x_ptr, lo_ptr, dims, strides, box):
+def view(x_ptr, lo_ptr, dims, strides, box, bf16=False):
     """5-D view, innermost first; shorter tuples are padded with unit dimensions."""
     v = View()
     v.x, v.lo = x_ptr, lo_ptr
@@ -105,7 +107,7 @@ def view(x_ptr, lo_ptr, dims, strides, box):
         strides.append(strides[-1] * dims[-1])
         dims.append(1)
         box.append(1)
-    assert strides[0] == 1 and box[0] == 32
+    assert strides[0] == 1 and box[0] == (64 if bf16 else 32)
     for d in range(5):
         v.dim[d], v.stride[d], v.box[d] = dims[d], strides[d], box[d]
     return v
@@ -145,14 +147,17 @@ def _itab(arena, name, values):
 
 def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tiles, out, out_lo, o_stride, o_ext, N,
            alpha=1.0, bias=None, act=0, mask=None, chain=4, o_base=0, flops=0.0, col_blocks=None, gather_dim=0,
-           colsum_part=None):
-    """col_blocks: (block width, [offset per block]) -- see a2cb_tcx_fwd_t.o_cb."""
-    assert len(kbs) <= MAX_KB, (name, len(kbs))
+           colsum_part=None, bf16=False, emu_A=None):
+    """bf16: A and the three-plane weight image (img, img_lo, img_3) are bf16, k-blocks are 64 channels wide
+    (emu_A: fp32 tensor with the same values, read by the numpy emulator instead)."""
+    assert len(kbs) <= MAX_KB, (name, len(kbs))      # col_blocks: (block width, [offset per block]) -- a2cb_tcx_fwd_t.o_cb
 
     def make(arena):
         d = FwdDesc()
-        d.A = view(arena.ptr(A), arena.ptr(A_lo), dims, strides, box)
+        d.A = view(arena.ptr(A), arena.ptr(A_lo), dims, strides, box, bf16)
         d.B, d.B_lo = arena.ptr((img, 0)), arena.ptr((img + "_lo", 0))
+        if bf16:
+            d.B3, d.bf16 = arena.ptr((img + "_3", 0)), 1
         d.b_rows, d.b_cols = img_rows, img_cols
         d.n_kb, d.chain = len(kbs), chain
         for i, (a, b) in enumerate(kbs):
@@ -175,7 +180,8 @@ def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tile
         d.colsum_part = arena.ptr(colsum_part)
         return d
     op = TcxOp(OP_TCX_FWD, make, name, flops=flops, runtime_idx=bool(gather_dim))
-    op.spec = dict(A=A, dims=dims, strides=strides, box=box, img=img, img_rows=img_rows, img_cols=img_cols, kbs=kbs,
+    op.spec = dict(A=emu_A if emu_A is not None else A, cw=64 if bf16 else 32,
+                   dims=dims, strides=strides, box=box, img=img, img_rows=img_rows, img_cols=img_cols, kbs=kbs,
                    tiles=tiles, out=out, o_stride=o_stride, o_ext=o_ext, N=N, alpha=alpha, bias=bias, act=act, mask=mask,
                    o_base=o_base, col_blocks=col_blocks, gather_dim=gather_dim, colsum_part=colsum_part)
     return op
@@ -225,12 +231,15 @@ def lo_op(name, x, lo, n):
     return op
 
 
-def prep_op(name, img, src, N, K, ntab, ktab):
+def prep_op(name, img, src, N, K, ntab, ktab, bf16=False):
+    """bf16: three bf16 planes (img, img_lo, img_3) with w = b1 + b2 + b3; only through the merged launch."""
     def make(arena):
+        assert not bf16
         return PrepDesc(arena.ptr((img, 0)), arena.ptr((img + "_lo", 0)), arena.ptr(src), N, K,
                         _itab(arena, img + "_ntab", ntab), _itab(arena, img + "_ktab", ktab))
     op = TcxOp(OP_TCX_PREP, make, name)
     op.prep = (img, src, N, K, ntab, ktab)
+    op.bf16 = bf16
     return op
 
 
@@ -250,17 +259,21 @@ def merge_preps(ops, tag):
     out, run = [], []
 
     def flush():
-        if len(run) <= 1:
+        if not run:
+            return
+        if len(run) == 1 and not run[0].bf16:
             out.extend(run)
         else:
-            jobs_spec = [o.prep for o in run]
+            jobs_spec = [o.prep + (o.bf16,) for o in run]
             name = "%sprepjobs_%d" % (tag, len(out))
 
             def make(arena, jobs_spec=jobs_spec, name=name):
                 arr = (PrepJob * len(jobs_spec))()
                 first = 0
-                for i, (img, src, N, K, ntab, ktab) in enumerate(jobs_spec):
+                for i, (img, src, N, K, ntab, ktab, b16) in enumerate(jobs_spec):
                     arr[i].img, arr[i].img_lo, arr[i].src = arena.ptr((img, 0)), arena.ptr((img + "_lo", 0)), arena.ptr(src)
+                    if b16:
+                        arr[i].img3, arr[i].bf16 = arena.ptr((img + "_3", 0)), 1
                     arr[i].ntab, arr[i].ktab = _itab(arena, img + "_ntab", ntab), _itab(arena, img + "_ktab", ktab)
                     arr[i].N, arr[i].K, arr[i].first = N, K, first
                     first += N * K
@@ -388,6 +401,16 @@ class CnnNet(object):
         else:
             x0 = nb.buf("x0", B * 441 * 64)
             x0_lo = nb.buf("x0_lo", B * 441 * 64) if self.frames_lo else None
+        # uint8 frames are exact in bf16: conv1's forward reads a bf16 copy of x0 (half the bytes, 64 channels per
+        # 128-byte row) against a three-plane bf16 weight image; its weight gradient keeps the fp32 tensor
+        self.c1_bf16 = not self.frames_lo
+        x0b = None
+        if self.c1_bf16:
+            if self.full_rows:
+                nb.sizes["x0b_full"] = self.full_rows * 441 * 32
+                x0b = ("x0b_full", 0)
+            else:
+                x0b = nb.buf("x0b", B * 441 * 32)
         n_img = self.full_rows or B                  # images in the tensor conv1 reads
         gd = 3 if self.full_rows else 0              # ... gathered through the row list along the image dimension
         self.x0_imgs, self.x0_gather = n_img, gd
@@ -404,6 +427,11 @@ class CnnNet(object):
         k2 = [c * 16 + ky * 4 + kx for ky in range(4) for kx in range(4) for c in range(32)]
         k3 = [c * 9 + ky * 3 + kx for ky in range(3) for kx in range(3) for c in range(64)]
         self.fc_perm = [c * 49 + y * 7 + x for y in range(7) for x in range(7) for c in range(32)]   # NHWC -> NCHW flatten
+        if self.c1_bf16:
+            w1b = self.image("img_c1b", 32, 256)
+            nb.buf("img_c1b_3", 32 * 256)
+            ops.append(prep_op("weight_image", w1b, self.P("base.main.0.weight"), 32, 256, [n * 256 for n in range(32)], k1,
+                               bf16=True))
         ops += [prep_op("weight_image", w1, self.P("base.main.0.weight"), 32, 256, [n * 256 for n in range(32)], k1),
                 prep_op("weight_image", w2, self.P("base.main.2.weight"), 64, 512, [n * 512 for n in range(64)], k2),
                 prep_op("weight_image", w3, self.P("base.main.4.weight"), 32, 576, [n * 576 for n in range(32)], k3),
@@ -413,7 +441,8 @@ class CnnNet(object):
         frames, is_u8, gather = (nb.obs, 0), nb.obs_code == 1, nb.gather
 
         def make_s2d(arena):
-            return S2dDesc(arena.ptr(x0), arena.ptr(x0_lo), arena.ptr(frames), None, 1 if is_u8 else 0, n_img, 4, 84, 84, 4)
+            return S2dDesc(arena.ptr(x0), arena.ptr(x0_lo), arena.ptr(frames), None, 1 if is_u8 else 0, n_img, 4, 84, 84, 4,
+                           arena.ptr(x0b))
         s2d = TcxOp(OP_TCX_S2D, make_s2d, "frames_s2d", runtime_idx=gather and not self.full_rows)
         s2d.spec = dict(out=x0, out_lo=x0_lo, frames=frames, n_img=n_img)
         if self.full_rows:
@@ -422,11 +451,18 @@ class CnnNet(object):
             ops.append(s2d)
 
         # ---- conv1: 2 x 2 taps x 64 channels, tile = 12 output rows of one image ----
-        kbs = [((c0, bx, by, 0), (by * 2 + bx) * 64 + c0) for by in range(2) for bx in range(2) for c0 in (0, 32)]
-        ops.append(fwd_op("conv1.fwd", x0, x0_lo, (64, 21, 21, n_img), (1, 64, 64 * 21, 64 * 441), (32, 20, 12, 1), w1, 32, 256,
-                          kbs, tiling(2 * B, 2, 12, t_div=2, tq_dim=3, tq_step=1), a1, a1_lo, (0, 32, 640, 12800),
-                          (0, 20, 20, B), 32, alpha=1.0 / 255.0, bias=self.P("base.main.0.bias"), act=1,
-                          flops=2.0 * B * 400 * 32 * 256, gather_dim=gd))
+        if self.c1_bf16:
+            kbs = [((0, bx, by, 0), (by * 2 + bx) * 64) for by in range(2) for bx in range(2)]
+            ops.append(fwd_op("conv1.fwd", x0b, None, (64, 21, 21, n_img), (1, 64, 64 * 21, 64 * 441), (64, 20, 12, 1), w1b, 32, 256,
+                              kbs, tiling(2 * B, 2, 12, t_div=2, tq_dim=3, tq_step=1), a1, a1_lo, (0, 32, 640, 12800),
+                              (0, 20, 20, B), 32, alpha=1.0 / 255.0, bias=self.P("base.main.0.bias"), act=1, chain=2,
+                              flops=2.0 * B * 400 * 32 * 256, gather_dim=gd, bf16=True, emu_A=x0))
+        else:
+            kbs = [((c0, bx, by, 0), (by * 2 + bx) * 64 + c0) for by in range(2) for bx in range(2) for c0 in (0, 32)]
+            ops.append(fwd_op("conv1.fwd", x0, x0_lo, (64, 21, 21, n_img), (1, 64, 64 * 21, 64 * 441), (32, 20, 12, 1), w1, 32, 256,
+                              kbs, tiling(2 * B, 2, 12, t_div=2, tq_dim=3, tq_step=1), a1, a1_lo, (0, 32, 640, 12800),
+                              (0, 20, 20, B), 32, alpha=1.0 / 255.0, bias=self.P("base.main.0.bias"), act=1,
+                              flops=2.0 * B * 400 * 32 * 256, gather_dim=gd))
         # ---- conv2 (stride 2): parity view (px|c, X, py, Y, n) of a1, tile = 3 images ----
         # (2 images / 3 stages measured slower: these layers are bound by bytes moved into shared memory, and smaller
         # tiles re-load the weight tile more often)
@@ -652,8 +688,8 @@ def _box_rows(box):
     return i1, i2, i3, i4
 
 
-def _load_box(src, dims, strides, box, c, fill=0.0):
-    """[rows, 32] values of the box whose corner has coordinates c (5 ints); out-of-bounds elements are zero."""
+def _load_box(src, dims, strides, box, c, fill=0.0, cw=32):
+    """[rows, cw] values of the box whose corner has coordinates c (5 ints); out-of-bounds elements are zero."""
     import numpy as np
     ii = _box_rows(box)
     ok = np.ones(ii[0].shape, bool)
@@ -662,7 +698,7 @@ def _load_box(src, dims, strides, box, c, fill=0.0):
         g = c[d] + ii[d - 1]
         ok &= (g >= 0) & (g < dims[d])
         off += np.clip(g, 0, dims[d] - 1) * strides[d]
-    ch = c[0] + np.arange(32)
+    ch = c[0] + np.arange(cw)
     okc = (ch >= 0) & (ch < dims[0])
     vals = src[off[:, None] + np.clip(ch, 0, dims[0] - 1)[None, :]].astype(np.float64)
     return np.where(ok[:, None] & okc[None, :], vals, fill)
@@ -735,7 +771,7 @@ def emulate(op, bufs, idx=None):
             acc = np.zeros((len(ii[0]), N))
             for a, b in sp["kbs"]:
                 c = [a[0], a[1] + ba[1], a[2] + ba[2], a[3] + ba[3], ba[4]]
-                acc += _load_box(A, dims, strides, box, c) @ img[:N, b:b + 32].T
+                acc += _load_box(A, dims, strides, box, c, cw=sp.get("cw", 32)) @ img[:N, b:b + sp.get("cw", 32)].T
             v = acc * sp["alpha"] + bias
             if sp["act"] == 1:
                 v = np.maximum(v, 0.0)

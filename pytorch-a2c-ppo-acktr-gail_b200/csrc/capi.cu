@@ -177,7 +177,11 @@ int a2cb_tcx_prep_weights(float* img, float* img_lo, const float* src, int64_t N
 }
 int a2cb_tcx_s2d(float* out, float* out_lo, const void* frames, int32_t src_is_u8, const int64_t* idx, int32_t B,
                  int32_t C, int32_t H, int32_t W, int32_t S, a2cb_stream_t stream) {
-    return tcx_s2d(out, out_lo, frames, src_is_u8, idx, B, C, H, W, S, (cudaStream_t)stream);
+    return tcx_s2d(out, out_lo, nullptr, frames, src_is_u8, idx, B, C, H, W, S, (cudaStream_t)stream);
+}
+int a2cb_tcx_s2d_b16(float* out, float* out_lo, void* out_b16, const void* frames, int32_t src_is_u8, const int64_t* idx,
+                     int32_t B, int32_t C, int32_t H, int32_t W, int32_t S, a2cb_stream_t stream) {
+    return tcx_s2d(out, out_lo, out_b16, frames, src_is_u8, idx, B, C, H, W, S, (cudaStream_t)stream);
 }
 int a2cb_tcx_colsum(float* part, const float* x, float* lo, int64_t rows, int32_t C, int64_t pitch, a2cb_stream_t stream) {
     return tcx_colsum(part, x, lo, (long)rows, C, (long)pitch, (cudaStream_t)stream);
@@ -298,7 +302,7 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             }
             case A2CB_OP_TCX_S2D: {
                 const a2cb_tcx_s2d_t& q = *reinterpret_cast<const a2cb_tcx_s2d_t*>(op.desc);
-                rc = tcx_s2d(q.out, q.out_lo, q.frames, q.src_is_u8, rt ? idx : q.idx, q.B, q.C, q.H, q.W, q.S, st);
+                rc = tcx_s2d(q.out, q.out_lo, q.out_b16, q.frames, q.src_is_u8, rt ? idx : q.idx, q.B, q.C, q.H, q.W, q.S, st);
                 break;
             }
             case A2CB_OP_TCX_COLSUM: {

@@ -84,6 +84,15 @@ __device__ __forceinline__ void tx_mma(uint32_t d_tmem, uint64_t a, uint64_t b, 
         "}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc)
         : "memory");
 }
+__device__ __forceinline__ void tx_mma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
 // version 1 << 46 | layout type << 61
 __device__ __forceinline__ uint64_t tx_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -137,11 +146,11 @@ __device__ __forceinline__ void tx_tile_base(const TcxTiling& t, int tile, int* 
 // ---------------------------------------------------------------------------------------------------
 // forward-like: out tile [R <= 128 * MB pixels] x [BN channels], reduction over n_kb k-blocks of 32
 // ---------------------------------------------------------------------------------------------------
-template <int BN, int MB>
+template <int BN, int MB, bool BF16>
 __global__ void __launch_bounds__(TX_NT, 1)
 tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-               const __grid_constant__ TcxFwd p, const int stages) {
+               const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ TcxFwd p, const int stages) {
     constexpr int B_BYTES = BN * TX_ROWB;
     constexpr int HALF = BN / 2;
     extern __shared__ uint8_t tx_dyn[];
@@ -154,8 +163,9 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* stage_base = tx_dyn + (dyn0 - tx_smem(tx_dyn));      // epilogue staging: 8 x 4 KiB slabs + row offsets
     const uint32_t dyn = dyn0 + TX_EPI_STAGING;                   // operand pipeline stages
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool has_lo = p.A.lo != nullptr;
-    const int stage_bytes = A_BYTES * (has_lo ? 2 : 1) + 2 * B_BYTES;
+    const bool has_lo = !BF16 && p.A.lo != nullptr;
+    constexpr int NB = BF16 ? 3 : 2;                              // planes of the weight tile
+    const int stage_bytes = A_BYTES * (has_lo ? 2 : 1) + NB * B_BYTES;
     const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
     const int chain = p.chain > 0 ? p.chain : p.n_kb;
     const int n_chains = (p.n_kb + chain - 1) / chain;
@@ -182,7 +192,7 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ===== TMA producer: the whole warp walks the loop, one elected lane issues =====
-        const uint32_t bytes = (uint32_t)(R * TX_ROWB * (has_lo ? 2 : 1) + 2 * B_BYTES);
+        const uint32_t bytes = (uint32_t)(R * TX_ROWB * (has_lo ? 2 : 1) + NB * B_BYTES);
         int it = 0, s = 0;
         uint32_t ph = 0;                                   // parity of the NEXT completion of empty[s] to wait for
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -202,6 +212,7 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (has_lo) tx_tma5(sa + A_BYTES, &tmAlo, &bars.full[s], c0, c1, c2, c3, c4);
                     tx_tma5(sb, &tmB, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
                     tx_tma5(sb + B_BYTES, &tmBlo, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
+                    if (BF16) tx_tma5(sb + 2 * B_BYTES, &tmB3, &bars.full[s], p.kb_b[kb], n0, 0, 0, 0);
                 }
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1u; }
@@ -209,8 +220,9 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===== MMA issuer: the whole warp waits on the barriers, one elected lane issues the MMAs =====
-        // D fp32, A/B tf32, both K-major, N = BN, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // D fp32, A/B tf32 (format 2) or bf16 (format 1), both K-major, N = BN, M = 128
+        constexpr uint32_t fmt = BF16 ? 1u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         int s = 0, cc = 0;
         uint32_t ph = 0;                                   // parity of full[s] to wait for
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
@@ -231,8 +243,15 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t ah = sa + (uint32_t)(mb * 128 * TX_ROWB);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint32_t o = ks * 32;
+                            const uint32_t o = ks * 32;                  // 8 tf32 or 16 bf16 reduction elements = 32 bytes
                             const uint64_t dah = tx_desc_k(ah + o), dbh = tx_desc_k(sb + o), dbl = tx_desc_k(sb + B_BYTES + o);
+                            if (BF16) {
+                                // exact bf16 operand x (b1 + b2 + b3): smallest term first
+                                tx_mma_f16(d, dah, tx_desc_k(sb + 2 * B_BYTES + o), idesc, (first && ks == 0) ? 0u : 1u);
+                                tx_mma_f16(d, dah, dbl, idesc, 1u);
+                                tx_mma_f16(d, dah, dbh, idesc, 1u);
+                                continue;
+                            }
                             if (ks == 0) {
                                 const uint32_t acc0 = first ? 0u : 1u;
                                 if (has_lo) { tx_mma(d, tx_desc_k(ah + A_BYTES + o), dbh, idesc, acc0); tx_mma(d, dah, dbl, idesc, 1u); }
@@ -647,18 +666,18 @@ EncodeTiledFn encode_fn() {
 }
 
 int make_map(CUtensorMap* out, const float* base, const int64_t* dim, const int64_t* stride, const int32_t* box, int swizzle,
-             const char* what) {
+             const char* what, int esize = 4) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("tcx: cuTensorMapEncodeTiled is not available"); return A2CB_ERR_CUDA; }
     cuuint64_t gd[5], gs[4];
     cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
     for (int d = 0; d < 5; ++d) { gd[d] = (cuuint64_t)dim[d]; bx[d] = (cuuint32_t)box[d]; }
-    for (int d = 1; d < 5; ++d) gs[d - 1] = (cuuint64_t)stride[d] * 4;
-    A2CB_REQUIRE(stride[0] == 1 && box[0] == 32, "tcx(%s): innermost dimension must be contiguous with a 32-float box", what);
+    for (int d = 1; d < 5; ++d) gs[d - 1] = (cuuint64_t)stride[d] * esize;
+    A2CB_REQUIRE(stride[0] == 1 && box[0] * esize == 128, "tcx(%s): innermost dimension must be contiguous with a 128-byte box", what);
     A2CB_REQUIRE(((uintptr_t)base & 15) == 0, "tcx(%s): base pointer must be 16-byte aligned", what);
     for (int d = 1; d < 5; ++d)
-        A2CB_REQUIRE(stride[d] % 4 == 0 && box[d] >= 1 && box[d] <= 256 && dim[d] >= 1, "tcx(%s): bad dimension %d", what, d);
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gd, gs, bx, es,
+        A2CB_REQUIRE((stride[d] * esize) % 16 == 0 && box[d] >= 1 && box[d] <= 256 && dim[d] >= 1, "tcx(%s): bad dimension %d", what, d);
+    CUresult r = fn(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gd, gs, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tcx(%s): cuTensorMapEncodeTiled failed (%d)", what, (int)r); return A2CB_ERR_CUDA; }
@@ -676,11 +695,11 @@ int view_maps(CUtensorMap* hi, CUtensorMap* lo, const TcxView& v, int swizzle, c
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kSmemMax = 232448 - 1024;          // 227 KiB opt-in limit minus the kernels' static shared memory
 
-template <int BN, int MB>
+template <int BN, int MB, bool BF16 = false>
 int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
-    const int a_planes = p.A.lo ? 2 : 1;
+    const int a_planes = (!BF16 && p.A.lo) ? 2 : 1;
     const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
-    const int stage = ((R + 7) & ~7) * TX_ROWB * a_planes + 2 * BN * TX_ROWB;
+    const int stage = ((R + 7) & ~7) * TX_ROWB * a_planes + (BF16 ? 3 : 2) * BN * TX_ROWB;
     // the last stage's M-block reads may run past its own end: keep that many rows of slack inside the allocation
     const int slack = (MB * 128 - ((R + 7) & ~7)) * TX_ROWB;
     int stages = (kSmemMax - 1024 - TX_EPI_STAGING - slack) / stage;
@@ -689,13 +708,13 @@ int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
     const int smem = stages * stage + 1024 + TX_EPI_STAGING + slack;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tcx_fwd_kernel<BN, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+        cudaError_t e = cudaFuncSetAttribute(tcx_fwd_kernel<BN, MB, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
         if (e != cudaSuccess) { set_error("tcx_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return A2CB_ERR_CUDA; }
         attr = true;
     }
     const long n_work = (long)p.tiles.n_tiles * ((p.N + BN - 1) / BN);
     dim3 grid((unsigned)(n_work < kNumSM ? n_work : kNumSM));
-    tcx_fwd_kernel<BN, MB><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], p, stages);
+    tcx_fwd_kernel<BN, MB, BF16><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], p, stages);
     return check_launch("tcx_fwd");
 }
 
@@ -738,7 +757,22 @@ int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
     A2CB_REQUIRE(R >= 1 && R <= 256, "tcx_fwd: %ld rows per tile (max 256)", R);
     const int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
     const int MB = R <= 128 ? 1 : 2;
-    CUtensorMap m[4];
+    CUtensorMap m[5];
+    if (p.bf16) {
+        // exact bf16 operand, three-plane bf16 weight image, 64-channel k-blocks
+        A2CB_REQUIRE(p.B3 && !p.A.lo && BN == 32 && MB == 2, "tcx_fwd: bf16 mode is built for 32 output channels and 129..256 rows per tile");
+        int rc = make_map(&m[0], p.A.x, p.A.dim, p.A.stride, p.A.box, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd A (bf16)", 2);
+        if (rc) return rc;
+        m[1] = m[0];
+        const int64_t bd[5] = {p.b_cols, p.b_rows, 1, 1, 1};
+        const int64_t bs[5] = {1, p.b_cols, p.b_cols * p.b_rows, p.b_cols * p.b_rows, p.b_cols * p.b_rows};
+        const int32_t bb[5] = {64, BN, 1, 1, 1};
+        A2CB_REQUIRE(p.b_cols % 8 == 0, "tcx_fwd: weight image pitch must be a multiple of 8 (bf16)");
+        if ((rc = make_map(&m[2], p.B, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B1", 2))) return rc;
+        if ((rc = make_map(&m[3], p.B_lo, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B2", 2))) return rc;
+        if ((rc = make_map(&m[4], p.B3, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B3", 2))) return rc;
+        return launch_fwd<32, 2, true>(p, m, st);
+    }
     int rc = view_maps(&m[0], &m[1], p.A, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd A");
     if (rc) return rc;
     const int64_t bd[5] = {p.b_cols, p.b_rows, 1, 1, 1};
@@ -747,6 +781,7 @@ int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
     A2CB_REQUIRE(p.b_cols % 4 == 0, "tcx_fwd: weight image pitch must be a multiple of 4");
     if ((rc = make_map(&m[2], p.B, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B"))) return rc;
     if ((rc = make_map(&m[3], p.B_lo, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B_lo"))) return rc;
+    m[4] = m[3];
     if (BN == 32) return MB == 1 ? launch_fwd<32, 1>(p, m, st) : launch_fwd<32, 2>(p, m, st);
     if (BN == 64) return MB == 1 ? launch_fwd<64, 1>(p, m, st) : launch_fwd<64, 2>(p, m, st);
     return MB == 1 ? launch_fwd<128, 1>(p, m, st) : launch_fwd<128, 2>(p, m, st);

@@ -57,6 +57,12 @@ struct TcxFwd {
     // optional: column sums of the stored values (= bias gradient of the layer that produced this gradient), one
     // partial row [N] per CTA at colsum_part[blockIdx.x * N + n]; single column tile only (N <= BN)
     float* colsum_part;
+    // bf16 mode (operands exactly representable in bf16, e.g. uint8 frames): A.x and the weight image are bf16; the
+    // image has THREE planes B, B_lo, B3 (w = b1 + b2 + b3 to 24 bits), k-blocks are 64 channels (128-byte rows) and
+    // every product costs three kind::f16 MMAs at twice the TF32 rate with half the operand bytes.
+    const float* B3;
+    int32_t bf16;
+    int32_t pad2_;
 };
 
 // partial[split][row_off[m] + n * col_stride] = alpha * sum_rows A[row, m] * Bm[row, n]

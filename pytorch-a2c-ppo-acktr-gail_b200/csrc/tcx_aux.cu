@@ -1,5 +1,7 @@
 // Element-wise helpers around the TMA-fed tensor-core engine (tcx.cu): operand planes, weight images,
 // the frame layout the first convolution reads, and bias gradients.  All HBM-bound.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "decls.cuh"
 #include "gemm.cuh"
@@ -57,7 +59,8 @@ tcx_s2d_kernel(float* __restrict__ out, float* __restrict__ out_lo, const T* __r
 
 // Several weight images in one launch: jobs[j] describes one image, `first` = index of its first element in the
 // concatenated element range.
-struct PrepJob { float* img; float* img_lo; const float* src; const int32_t* ntab; const int32_t* ktab; long N, K, first; };
+struct PrepJob { float* img; float* img_lo; const float* src; const int32_t* ntab; const int32_t* ktab; long N, K, first;
+                 float* img3; long bf16; };
 
 __global__ void __launch_bounds__(256)
 tcx_prep_multi_kernel(const PrepJob* __restrict__ jobs, int n_jobs, long total) {
@@ -70,6 +73,17 @@ tcx_prep_multi_kernel(const PrepJob* __restrict__ jobs, int n_jobs, long total) 
     const long n = e / q.K, k = e - n * q.K;
     const int a = __ldg(q.ntab + n), b = __ldg(q.ktab + k);
     const float v = (a >= 0 && b >= 0) ? __ldg(q.src + (long)a + b) : 0.f;
+    if (q.bf16) {
+        // w = b1 + b2 + b3 with three bf16 terms (8 + 8 + 8 significant bits)
+        const __nv_bfloat16 b1 = __float2bfloat16_rn(v);
+        const float r1 = v - __bfloat162float(b1);
+        const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+        reinterpret_cast<__nv_bfloat16*>(q.img)[e] = b1;
+        reinterpret_cast<__nv_bfloat16*>(q.img_lo)[e] = b2;
+        reinterpret_cast<__nv_bfloat16*>(q.img3)[e] = b3;
+        return;
+    }
     q.img[e] = v;
     q.img_lo[e] = ax_lo(v);
 }
@@ -79,8 +93,8 @@ tcx_prep_multi_kernel(const PrepJob* __restrict__ jobs, int n_jobs, long total) 
 // contiguous floats -- both sides of the transposition are fully coalesced.
 template <typename T>
 __global__ void __launch_bounds__(352)
-tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, const T* __restrict__ frames,
-                     const int64_t* __restrict__ idx) {
+tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, uint2* __restrict__ out_b16,
+                     const T* __restrict__ frames, const int64_t* __restrict__ idx) {
     __shared__ float4 tile[16][21];
     const int b = blockIdx.x / 21, by = blockIdx.x % 21;
     const long row = idx ? (long)idx[b] : b;
@@ -104,6 +118,13 @@ tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, cons
         const long o = ((long)(b * 21 + by) * 21 + bx) * 16 + r;
         out[o] = v;
         if (out_lo) out_lo[o] = make_float4(ax_lo(v.x), ax_lo(v.y), ax_lo(v.z), ax_lo(v.w));
+        if (out_b16) {
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&p0);
+            u.y = *reinterpret_cast<const uint32_t*>(&p1);
+            out_b16[o] = u;
+        }
     }
 }
 
@@ -272,18 +293,21 @@ int tcx_prep_weights(float* img, float* img_lo, const float* src, long N, long K
     return check_launch("tcx_prep_weights");
 }
 
-int tcx_s2d(float* out, float* out_lo, const void* frames, int src_is_u8, const int64_t* idx, int B, int C, int H, int W,
-            int S, cudaStream_t st) {
+int tcx_s2d(float* out, float* out_lo, void* out_b16, const void* frames, int src_is_u8, const int64_t* idx, int B, int C,
+            int H, int W, int S, cudaStream_t st) {
     A2CB_REQUIRE(out && frames && B > 0 && S > 0 && H % S == 0 && W % S == 0, "tcx_s2d: bad arguments");
     if (C == 4 && H == 84 && W == 84 && S == 4) {
         if (src_is_u8)
             tcx_s2d_atari_kernel<uint8_t><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
+                                                                               reinterpret_cast<uint2*>(out_b16),
                                                                                reinterpret_cast<const uint8_t*>(frames), idx);
         else
             tcx_s2d_atari_kernel<float><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
+                                                                             reinterpret_cast<uint2*>(out_b16),
                                                                              reinterpret_cast<const float*>(frames), idx);
         return check_launch("tcx_s2d");
     }
+    A2CB_REQUIRE(!out_b16, "tcx_s2d: the bf16 copy is only produced for the Atari geometry");
     const long total = (long)B * C * H * W;
     const unsigned grid = (unsigned)min((total + 255) / 256, (long)kNumSM * 32);
     if (src_is_u8)

@@ -103,7 +103,7 @@ def test_hoist_preps_merges_weight_images():
     bwd = net.backward(nb.buf("gh", 1024), nb.buf("gh_lo", 1024))
     n_prep = sum(1 for o in fwd + bwd if isinstance(o, _tcx.TcxOp) and o.kind == _tcx.OP_TCX_PREP)
     f2, b2 = _tcx.hoist_preps([fwd, bwd], "t_")
-    assert n_prep == 7
+    assert n_prep == 8          # 4 forward (+ the bf16 image of conv1 for uint8 frames) + 3 data-gradient images
     assert f2[0].kind == _tcx.OP_TCX_PREP_MULTI
     assert not any(isinstance(o, _tcx.TcxOp) and o.kind == _tcx.OP_TCX_PREP for o in f2 + b2)
     assert len(f2) + len(b2) == len(fwd) + len(bwd) - n_prep + 1
