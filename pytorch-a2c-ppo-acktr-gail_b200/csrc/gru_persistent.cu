@@ -422,6 +422,241 @@ gru_persistent_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float*
     }
 }
 
+// ---------------------------------------------------------------------------
+// Tensor-core variant of both recurrence kernels.  The per-step product is tiny ([8 environments] x [96 gate rows]
+// x [H] per CTA) and its operands must stay where they are (W slice in shared memory, state in L2 / L1), so the
+// tcgen05 path (M >= 64 rows per CTA, both operands through shared-memory descriptors) does not apply; warp-level
+// mma.sync.m16n8k8 TF32 does: M = gate rows (forward) / hidden units (backward), N = the 8 environments, K split
+// over the 8 warps, 3xTF32 (hi / lo split by truncation, in registers) for fp32-level accuracy, partial tiles
+// folded through shared memory.  It replaces 1536 FFMA + a 96-value shuffle transpose per warp and step by 144 MMAs.
+// Ownership, buffers, barriers and the gate math are those of the SIMT kernels above; the element-wise owner of
+// (environment r, unit u) is thread 32 r + u, so every global access is a coalesced 128-byte row segment.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pm_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void pm_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// one K = 8 step of MT m-tiles: A = W rows [mt * 16 + g (+ 8)][k0 + t (+ 4)] (pitch P), B = x[g][k0 + t (+ 4)]
+template <int MT>
+__device__ __forceinline__ void pm_kstep(float (*acc)[4], const float* __restrict__ Wsm, int P, int k0, float x0, float x1,
+                                         int g, int t) {
+    uint32_t bh0, bl0, bh1, bl1;
+    pm_split(x0, bh0, bl0);
+    pm_split(x1, bh1, bl1);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        const float* w = Wsm + (long)(mt * 16 + g) * P + k0 + t;
+        uint32_t ah[4], al[4];
+        pm_split(w[0], ah[0], al[0]);
+        pm_split(w[8 * P], ah[1], al[1]);
+        pm_split(w[4], ah[2], al[2]);
+        pm_split(w[8 * P + 4], ah[3], al[3]);
+        pm_mma(acc[mt], al, bh0, bh1);
+        pm_mma(acc[mt], ah, bl0, bl1);
+        pm_mma(acc[mt], ah, bh0, bh1);
+    }
+}
+
+__global__ void __launch_bounds__(PG_NT)
+gru_mma_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh) {
+    extern __shared__ __align__(16) float pg_smem[];
+    const int H = d.H, P = H + 4;
+    float* Ws = pg_smem;                                            // [96 gate rows: (u, g) -> u * 3 + g][P]
+    float4* red = reinterpret_cast<float4*>(pg_smem + 3 * PG_UB * P);   // [8 warps][6 tiles][32 lanes]
+    unsigned* ctr = &pg_counters[0][blockIdx.y];
+    unsigned epoch = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int ub = blockIdx.x * PG_UB;
+    for (int e = tid; e < 3 * PG_UB * H; e += PG_NT) {
+        const int c = e / H, k = e - c * H;
+        const int u = c / 3, gg = c - u * 3;
+        Ws[(long)c * P + k] = Whh[(long)(gg * H + ub + u) * H + k];
+    }
+    const int ro = warp, uo = lane;                                 // element-wise owner: (environment ro, unit uo)
+    const int ku = ub + uo;
+    const float b_r = bhh[ku], b_z = bhh[H + ku], b_n = bhh[2 * H + ku];
+    const int ngrp = (d.N + PG_RW - 1) / PG_RW;
+    const int ksteps = H / 8 / PG_NW;                               // K = 8 steps per warp
+
+    for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+        const int my = grp * PG_RW + ro;
+        if (my < d.N) d.hm[(long)my * H + ku] = d.h0[(long)my * H + ku] * pg_mask(d, 0, my);
+    }
+    pg_group_sync(ctr, ++epoch * gridDim.x);
+
+    for (int t = 0; t < d.T; ++t) {
+        const float* hm_t = d.hm + (long)t * d.N * H;
+        for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+            const int r0 = grp * PG_RW;
+            const int my = r0 + ro;
+            const bool live = my < d.N;
+            const long row = (long)t * d.N + my;
+            float gi_r = 0.f, gi_z = 0.f, gi_n = 0.f, hprev = 0.f, mnext = 0.f;
+            if (live) {
+                const float* gi = d.gi + row * 3 * H;
+                gi_r = __ldg(gi + ku); gi_z = __ldg(gi + H + ku); gi_n = __ldg(gi + 2 * H + ku);
+                hprev = hm_t[(long)my * H + ku];
+                mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, my) : 0.f;
+            }
+            float acc[6][4];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+            const float* hrow = hm_t + (long)min(r0 + g, d.N - 1) * H + warp * ksteps * 8 + tq;
+            // operands of all this warp's k-steps first (independent loads), then the MMAs
+            float x0[8], x1[8];
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+                if (ks < ksteps) { x0[ks] = hrow[ks * 8]; x1[ks] = hrow[ks * 8 + 4]; }
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+                if (ks < ksteps) pm_kstep<6>(acc, Ws, P, (warp * ksteps + ks) * 8, x0[ks], x1[ks], g, tq);
+            __syncthreads();                                         // previous readers of `red` are done
+#pragma unroll
+            for (int mt = 0; mt < 6; ++mt)
+                red[(warp * 6 + mt) * 32 + lane] = make_float4(acc[mt][0], acc[mt][1], acc[mt][2], acc[mt][3]);
+            __syncthreads();
+            float gsum[3];
+#pragma unroll
+            for (int gg = 0; gg < 3; ++gg) {
+                const int col = uo * 3 + gg, mt = col >> 4, i = col & 15;
+                const int ln = (i & 7) * 4 + (ro >> 1), rg = (i >> 3) * 2 + (ro & 1);
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < PG_NW; ++w) s += reinterpret_cast<const float*>(red + (w * 6 + mt) * 32 + ln)[rg];
+                gsum[gg] = s;
+            }
+            if (live) {
+                const float ghr = gsum[0] + b_r, ghz = gsum[1] + b_z, ghn = gsum[2] + b_n;
+                const float rr = pg_sigmoid(gi_r + ghr);
+                const float zz = pg_sigmoid(gi_z + ghz);
+                const float nn = tanhf(gi_n + rr * ghn);
+                const float h = (1.f - zz) * nn + zz * hprev;
+                d.out[row * H + ku] = h;
+                if (d.r) {
+                    d.r[row * H + ku] = rr; d.z[row * H + ku] = zz; d.n[row * H + ku] = nn;
+                    d.gh[row * 3 * H + 2 * H + ku] = ghn;
+                }
+                if (t + 1 < d.T) d.hm[(row + d.N) * H + ku] = h * mnext;
+            }
+        }
+        if (t + 1 < d.T) pg_group_sync(ctr, ++epoch * gridDim.x);
+    }
+}
+
+__global__ void __launch_bounds__(PG_NT)
+gru_mma_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws) {
+    extern __shared__ __align__(16) float pg_smem[];
+    const int H = d.H, H3 = 3 * d.H, P = H3 + 4;
+    float* Wt = pg_smem;                                            // [32 units][P]: Wt[u][c] = W_hh[c][ub + u]
+    float4* red = reinterpret_cast<float4*>(pg_smem + PG_UB * P);   // [8 warps][2 tiles][32 lanes]
+    unsigned* ctr = &pg_counters[1][blockIdx.y];
+    unsigned epoch = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int ub = blockIdx.x * PG_UB;
+    for (int e = tid; e < H3 * PG_UB; e += PG_NT) {
+        const int c = e / PG_UB, u = e - c * PG_UB;
+        Wt[(long)u * P + c] = Whh[(long)c * H + ub + u];
+    }
+    __syncthreads();
+    const int ro = warp, uo = lane;
+    const int ku = ub + uo;
+    const int ngrp = (d.N + PG_RW - 1) / PG_RW;
+    const int ksteps = H3 / 8 / PG_NW;                              // 24 for H = 512
+    float carry0 = 0.f;
+
+    struct PhaseA { float dout, r, z, n, hm, ghn, mnext; };
+    auto load_a = [&](int t, int my) {
+        PhaseA a;
+        const long row = (long)t * d.N + my;
+        a.dout = d.dout[row * H + ku];
+        a.r = d.r[row * H + ku]; a.z = d.z[row * H + ku]; a.n = d.n[row * H + ku];
+        a.hm = d.hm[row * H + ku];
+        a.ghn = d.gh[row * 3 * H + 2 * H + ku];
+        a.mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, my) : 0.f;
+        return a;
+    };
+    const int my0 = blockIdx.y * PG_RW + ro;
+    PhaseA pre = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (my0 < d.N) pre = load_a(d.T - 1, my0);
+
+    for (int t = d.T - 1; t >= 0; --t) {
+        // ---- phase A ----
+        for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+            const int my = grp * PG_RW + ro;
+            if (my >= d.N) continue;
+            const bool first = grp == (int)blockIdx.y;
+            const long row = (long)t * d.N + my;
+            const PhaseA a = first ? pre : load_a(t, my);
+            float dh = a.dout;
+            if (t + 1 < d.T) {
+                const float c = first ? carry0 : carry_ws[(long)my * H + ku];
+                dh += c * a.mnext;
+            }
+            const float dn_pre = dh * (1.f - a.z) * (1.f - a.n * a.n);
+            const float dz_pre = dh * (a.hm - a.n) * a.z * (1.f - a.z);
+            const float dr_pre = dn_pre * a.ghn * a.r * (1.f - a.r);
+            float* dgi = d.dgi + row * 3 * H;
+            float* dgh = d.dgh + row * 3 * H;
+            dgi[ku] = dr_pre; dgi[H + ku] = dz_pre; dgi[2 * H + ku] = dn_pre;
+            dgh[ku] = dr_pre; dgh[H + ku] = dz_pre; dgh[2 * H + ku] = dn_pre * a.r;
+            const float dhz = dh * a.z;
+            if (first) carry0 = dhz;
+            else carry_ws[(long)my * H + ku] = dhz;
+        }
+        if (t == 0) break;
+        pg_group_sync(ctr, ++epoch * gridDim.x);
+        if (my0 < d.N) pre = load_a(t - 1, my0);
+        // ---- phase B: carry[r][u] += sum_c dgh_t[r][c] W_hh[c][u] ----
+        const float* dgh_t = d.dgh + (long)t * d.N * H3;
+        for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+            const int r0 = grp * PG_RW;
+            float acc[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+            const float* grow = dgh_t + (long)min(r0 + g, d.N - 1) * H3 + warp * ksteps * 8 + tq;
+            for (int ks0 = 0; ks0 < ksteps; ks0 += 8) {
+                float x0[8], x1[8];
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    if (ks0 + ks < ksteps) { x0[ks] = grow[(ks0 + ks) * 8]; x1[ks] = grow[(ks0 + ks) * 8 + 4]; }
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    if (ks0 + ks < ksteps) pm_kstep<2>(acc, Wt, P, (warp * ksteps + ks0 + ks) * 8, x0[ks], x1[ks], g, tq);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                red[(warp * 2 + mt) * 32 + lane] = make_float4(acc[mt][0], acc[mt][1], acc[mt][2], acc[mt][3]);
+            __syncthreads();
+            const int mt = uo >> 4, i = uo & 15;
+            const int ln = (i & 7) * 4 + (ro >> 1), rg = (i >> 3) * 2 + (ro & 1);
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < PG_NW; ++w) sum += reinterpret_cast<const float*>(red + (w * 2 + mt) * 32 + ln)[rg];
+            const int my = r0 + ro;
+            if (my < d.N) {
+                if (grp == (int)blockIdx.y) carry0 += sum;
+                else carry_ws[(long)my * H + ku] += sum;
+            }
+        }
+    }
+}
+
+static size_t pm_smem_fwd(int H) { return (size_t)(3 * PG_UB * (H + 4)) * sizeof(float) + (size_t)PG_NW * 6 * 32 * sizeof(float4); }
+static size_t pm_smem_bwd(int H) { return (size_t)(PG_UB * (3 * H + 4)) * sizeof(float) + (size_t)PG_NW * 2 * 32 * sizeof(float4); }
+static bool pm_enabled(int H) {
+    static int mode = -1;                                           // A2CB_GRU_MMA=0 selects the SIMT kernels
+    if (mode < 0) { const char* e = getenv("A2CB_GRU_MMA"); mode = (e && e[0] == '0') ? 0 : 1; }
+    return mode == 1 && H % 64 == 0 && H / 8 / PG_NW <= 8 && pm_smem_fwd(H) <= 227 * 1024 && pm_smem_bwd(H) <= 227 * 1024;
+}
+
 static size_t pg_smem_bytes(int H) { return (size_t)(3 * PG_UB * H) * sizeof(float); }
 
 static int pg_sms() {
@@ -511,7 +746,20 @@ int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float
     gy = gy < 1 ? 1 : (gy > ngrp ? ngrp : gy);
     A2CB_REQUIRE(!backward || ngrp <= gy || d.dcarry, "gru_persistent: dcarry workspace [N, H] needed for N > %d", gy * PG_RW);
     A2CB_REQUIRE(gy <= 256, "gru_persistent: too many environment groups");
-    const size_t smem = pg_smem_bytes(d.H);
+    const bool mma = pm_enabled(d.H);
+    const size_t smem = mma ? (backward ? pm_smem_bwd(d.H) : pm_smem_fwd(d.H)) : pg_smem_bytes(d.H);
+    if (mma) {
+        static bool attr = false;
+        if (!attr) {
+            if (cudaFuncSetAttribute(gru_mma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+                cudaFuncSetAttribute(gru_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+                set_error("gru_persistent: shared memory attribute");
+                cudaGetLastError();
+                return A2CB_ERR_CUDA;
+            }
+            attr = true;
+        }
+    }
     dim3 grid((unsigned)ug, (unsigned)gy);
     {
         void* cptr = nullptr;
@@ -524,9 +772,10 @@ int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float
     float* ws = d.dcarry;
     void* args_f[] = {(void*)&dd, (void*)&Whh, (void*)&bhh};
     void* args_b[] = {(void*)&dd, (void*)&Whh, (void*)&ws};
-    cudaError_t e = backward
-        ? cudaLaunchCooperativeKernel((const void*)gru_persistent_bwd_kernel, grid, dim3(PG_NT), args_b, smem, st)
-        : cudaLaunchCooperativeKernel((const void*)gru_persistent_fwd_kernel, grid, dim3(PG_NT), args_f, smem, st);
+    const void* kf = mma ? (const void*)gru_mma_fwd_kernel : (const void*)gru_persistent_fwd_kernel;
+    const void* kb = mma ? (const void*)gru_mma_bwd_kernel : (const void*)gru_persistent_bwd_kernel;
+    cudaError_t e = backward ? cudaLaunchCooperativeKernel(kb, grid, dim3(PG_NT), args_b, smem, st)
+                             : cudaLaunchCooperativeKernel(kf, grid, dim3(PG_NT), args_f, smem, st);
     if (e != cudaSuccess) {
         set_error("gru_persistent: cooperative launch failed: %s", cudaGetErrorString(e));
         cudaGetLastError();
