@@ -62,6 +62,22 @@ __device__ __forceinline__ void pg_group_sync(unsigned* ctr, unsigned target) {
     __syncthreads();
 }
 
+// The same barrier in two halves: arrive right after the stores the other CTAs wait for, then do work that nobody
+// waits for (non-critical stores, prefetches of the next step's operands), then wait.
+__device__ __forceinline__ void pg_group_arrive(unsigned* ctr) {
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+__device__ __forceinline__ void pg_group_wait(unsigned* ctr, unsigned target) {
+    if (threadIdx.x == 0) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
 // Butterfly "transpose-reduce": every lane enters with NV partial sums v[0..NV) (NV = 32 * PER) of the
 // same NV outputs and leaves with the complete sums of outputs lane * PER + i in v[i], i < PER.  Each of
 // the five halving rounds exchanges the half a lane does not keep with its xor-partner.
@@ -490,20 +506,31 @@ gru_mma_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* 
     }
     pg_group_sync(ctr, ++epoch * gridDim.x);
 
+    // single environment group per CTA (the common case): the next step's gate inputs are prefetched while the CTA
+    // waits at the barrier, and only the state store precedes the barrier arrival
+    const bool single = ngrp <= (int)gridDim.y;
+    struct GateIn { float r, z, n, mnext; };
+    auto load_gi = [&](int t, int my) {
+        GateIn q = {0.f, 0.f, 0.f, 0.f};
+        if (my < d.N) {
+            const float* gi = d.gi + ((long)t * d.N + my) * 3 * H;
+            q.r = __ldg(gi + ku); q.z = __ldg(gi + H + ku); q.n = __ldg(gi + 2 * H + ku);
+            q.mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, my) : 0.f;
+        }
+        return q;
+    };
+    GateIn pre = load_gi(0, blockIdx.y * PG_RW + ro);
+
     for (int t = 0; t < d.T; ++t) {
         const float* hm_t = d.hm + (long)t * d.N * H;
+        bool arrived = false;
         for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
             const int r0 = grp * PG_RW;
             const int my = r0 + ro;
             const bool live = my < d.N;
             const long row = (long)t * d.N + my;
-            float gi_r = 0.f, gi_z = 0.f, gi_n = 0.f, hprev = 0.f, mnext = 0.f;
-            if (live) {
-                const float* gi = d.gi + row * 3 * H;
-                gi_r = __ldg(gi + ku); gi_z = __ldg(gi + H + ku); gi_n = __ldg(gi + 2 * H + ku);
-                hprev = hm_t[(long)my * H + ku];
-                mnext = (t + 1 < d.T) ? pg_mask(d, t + 1, my) : 0.f;
-            }
+            const GateIn q = single ? pre : load_gi(t, my);
+            const float hprev = live ? hm_t[(long)my * H + ku] : 0.f;
             float acc[6][4];
 #pragma unroll
             for (int i = 0; i < 6; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
@@ -531,21 +558,29 @@ gru_mma_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* 
                 for (int w = 0; w < PG_NW; ++w) s += reinterpret_cast<const float*>(red + (w * 6 + mt) * 32 + ln)[rg];
                 gsum[gg] = s;
             }
+            const float ghr = gsum[0] + b_r, ghz = gsum[1] + b_z, ghn = gsum[2] + b_n;
+            const float rr = pg_sigmoid(q.r + ghr);
+            const float zz = pg_sigmoid(q.z + ghz);
+            const float nn = tanhf(q.n + rr * ghn);
+            const float h = (1.f - zz) * nn + zz * hprev;
+            if (live && t + 1 < d.T) d.hm[(row + d.N) * H + ku] = h * q.mnext;      // what the other CTAs wait for
+            if (single && t + 1 < d.T) {
+                pg_group_arrive(ctr);
+                arrived = true;
+                pre = load_gi(t + 1, my);                                           // in flight during the barrier wait
+            }
             if (live) {
-                const float ghr = gsum[0] + b_r, ghz = gsum[1] + b_z, ghn = gsum[2] + b_n;
-                const float rr = pg_sigmoid(gi_r + ghr);
-                const float zz = pg_sigmoid(gi_z + ghz);
-                const float nn = tanhf(gi_n + rr * ghn);
-                const float h = (1.f - zz) * nn + zz * hprev;
                 d.out[row * H + ku] = h;
                 if (d.r) {
                     d.r[row * H + ku] = rr; d.z[row * H + ku] = zz; d.n[row * H + ku] = nn;
                     d.gh[row * 3 * H + 2 * H + ku] = ghn;
                 }
-                if (t + 1 < d.T) d.hm[(row + d.N) * H + ku] = h * mnext;
             }
         }
-        if (t + 1 < d.T) pg_group_sync(ctr, ++epoch * gridDim.x);
+        if (t + 1 < d.T) {
+            if (!arrived) pg_group_arrive(ctr);
+            pg_group_wait(ctr, ++epoch * gridDim.x);
+        }
     }
 }
 
@@ -585,6 +620,8 @@ gru_mma_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __rest
     const int my0 = blockIdx.y * PG_RW + ro;
     PhaseA pre = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (my0 < d.N) pre = load_a(d.T - 1, my0);
+    float dgi_keep[3] = {0.f, 0.f, 0.f};
+    long keep_row = -1;
 
     for (int t = d.T - 1; t >= 0; --t) {
         // ---- phase A ----
@@ -604,15 +641,22 @@ gru_mma_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __rest
             const float dr_pre = dn_pre * a.ghn * a.r * (1.f - a.r);
             float* dgi = d.dgi + row * 3 * H;
             float* dgh = d.dgh + row * 3 * H;
-            dgi[ku] = dr_pre; dgi[H + ku] = dz_pre; dgi[2 * H + ku] = dn_pre;
-            dgh[ku] = dr_pre; dgh[H + ku] = dz_pre; dgh[2 * H + ku] = dn_pre * a.r;
+            dgh[ku] = dr_pre; dgh[H + ku] = dz_pre; dgh[2 * H + ku] = dn_pre * a.r;     // what the other CTAs wait for
+            if (first) { dgi_keep[0] = dr_pre; dgi_keep[1] = dz_pre; dgi_keep[2] = dn_pre; keep_row = row; }
+            else { dgi[ku] = dr_pre; dgi[H + ku] = dz_pre; dgi[2 * H + ku] = dn_pre; }
             const float dhz = dh * a.z;
             if (first) carry0 = dhz;
             else carry_ws[(long)my * H + ku] = dhz;
         }
+        if (t > 0) pg_group_arrive(ctr);
+        if (keep_row >= 0) {                                       // not needed by anyone inside this kernel
+            float* dgi = d.dgi + keep_row * 3 * H;
+            dgi[ku] = dgi_keep[0]; dgi[H + ku] = dgi_keep[1]; dgi[2 * H + ku] = dgi_keep[2];
+            keep_row = -1;
+        }
         if (t == 0) break;
-        pg_group_sync(ctr, ++epoch * gridDim.x);
-        if (my0 < d.N) pre = load_a(t - 1, my0);
+        if (my0 < d.N) pre = load_a(t - 1, my0);                    // in flight during the barrier wait and phase B
+        pg_group_wait(ctr, ++epoch * gridDim.x);
         // ---- phase B: carry[r][u] += sum_c dgh_t[r][c] W_hh[c][u] ----
         const float* dgh_t = d.dgh + (long)t * d.N * H3;
         for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
