@@ -296,13 +296,13 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the C5 shard
-# (profiles/r01c_tcx_gru_full_c5.txt); only meaningful for that workload
-NCU_DRAM_SOURCE = "profiles/r01c_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
+# (profiles/r01d_tcx_gru_full_c5.txt); only meaningful for that workload
+NCU_DRAM_SOURCE = "profiles/r01d_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
 NCU_DRAM_BYTES = {
-    "conv1.fwd": 0.925621e9 + 798.895e6, "conv2.fwd": 0.840913e9 + 316.076e6, "conv3.fwd": 0.340068e9 + 83.165e6,
-    "conv2.dgrad": 0.759555e9 + 794.400e6, "conv3.dgrad": 0.272850e9 + 293.151e6,
-    "conv1.wgrad": 1.764648e9 + 4.253e6, "conv2.wgrad": 1.182853e9 + 7.797e6, "conv3.wgrad": 0.442568e9 + 3.896e6,
-    "gru.seq_fwd": 0.053858e9 + 45.924e6, "gru.seq_bwd": 0.104027e9 + 57.874e6,
+    "conv1.fwd": 0.463439e9 + 786.812e6, "conv2.fwd": 0.840850e9 + 314.908e6, "conv3.fwd": 0.340078e9 + 82.521e6,
+    "conv2.dgrad": 0.759568e9 + 793.399e6, "conv3.dgrad": 0.272844e9 + 292.938e6,
+    "conv1.wgrad": 1.764639e9 + 4.516e6, "conv2.wgrad": 1.182880e9 + 7.834e6, "conv3.wgrad": 0.442569e9 + 5.279e6,
+    "gru.seq_fwd": 0.053849e9 + 46.974e6, "gru.seq_bwd": 0.104056e9 + 60.236e6,
 }
 
 
@@ -407,9 +407,8 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
             "share_of_step": top["share"], "launch_ms": top["ms"] / top["launches"], "launches_per_step": top["launches"],
             "step_program_ms": float(total), "gemm_engine_mode": int(nat.lib().a2cb_get_gemm_mode())}
     # what the fp32-parity arithmetic can reach on this tensor pipe: TF32 runs at half the bf16 rate and every product
-    # costs 3 MMAs (2 when one operand is exact in TF32: the uint8 frames of conv1)
-    mmas = 2 if top["op"].startswith("conv1") else 3
-    roof["peak_3xtf32"] = peak / 2.0 / mmas
+    # costs 3 MMAs; conv1.fwd (uint8 frames, exact in bf16) runs 3 bf16 MMAs at the full rate, conv1.wgrad 2 TF32 MMAs
+    roof["peak_3xtf32"] = peak / 3.0 if top["op"] == "conv1.fwd" else peak / 2.0 / (2 if top["op"] == "conv1.wgrad" else 3)
     roof["frac_3xtf32"] = top["tflops"] / roof["peak_3xtf32"]
     is_c5 = bool(cfg.get("recurrent")) and cfg["T"] == 128 and cfg["N"] == 256
     roof["traffic"] = NCU_DRAM_BYTES.get(top["op"]) if is_c5 else None
@@ -419,9 +418,10 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
         # (148 SMs x 128 lanes x 2 flop x sm clock) with one barrier per time step, not on the tensor pipe
         g = max(gru_rows, key=lambda r: r["ms"])
         fp32_peak = 148 * 128 * 2 * 1.965e-3
-        roof["recurrence"] = {"kernel": "a2cb::gru_persistent_%s_kernel" % ("bwd" if g["op"].endswith("bwd") else "fwd"),
+        roof["recurrence"] = {"kernel": "a2cb::gru_mma_%s_kernel" % ("bwd" if g["op"].endswith("bwd") else "fwd"),
                               "traffic": NCU_DRAM_BYTES.get(g["op"]) if is_c5 else None,
-                              "bound": "fp32 pipe + per-step barrier", "achieved": g["tflops"], "peak": fp32_peak,
+                              "bound": "per-step barrier + L2 latency (mma.sync 3xTF32; peak shown = fp32 SIMT pipe)",
+                              "achieved": g["tflops"], "peak": fp32_peak,
                               "unit": "TFLOP/s", "frac": g["tflops"] / fp32_peak, "launch_ms": g["ms"],
                               "share_of_step": g["share"]}
     return roof, rows[:24]
