@@ -203,6 +203,13 @@ def run_ours(args):
             getattr(st, k).copy_(host[k], non_blocking=True)
         return host["next_value"].to(dev, non_blocking=True)
 
+    def upload_e2e():
+        """The public ingest call: narrow tensors now, frames pulled by update() on a side stream (recurrent PPO:
+        per minibatch environment set, so that the upload overlaps the compute of earlier minibatches)."""
+        st.stage_host({k: host[k] for k in ("obs", "rewards", "masks", "bad_masks", "actions", "action_log_probs",
+                                            "value_preds", "recurrent_hidden_states")})
+        return host["next_value"].to(dev, non_blocking=True)
+
     def hot_path(nv):
         st.compute_returns(nv, cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"], cfg["use_proper_time_limits"])
         out = agent.update(st)
@@ -230,7 +237,7 @@ def run_ours(args):
                 torch.cuda.profiler.start()                    # ncu --profile-from-start off: one timed step
             e0.record()
             if e2e:
-                nv = upload()
+                nv = upload_e2e()
             losses = hot_path(nv)                              # update() ends with the D2H of the losses
             e1.record()
             if prof:

@@ -424,7 +424,9 @@ typedef struct { float* out; const float* in; int64_t img_stride; int64_t pitch;
 typedef struct { float* lo; const float* x; int64_t n; } a2cb_tcx_lo_t;
 typedef struct { float* img; float* img_lo; const float* src; int64_t N, K; const int32_t* ntab; const int32_t* ktab; } a2cb_tcx_prep_t;
 typedef struct { float* out; float* out_lo; const void* frames; const int64_t* idx; int32_t src_is_u8, B, C, H, W, S;
-                 void* out_b16; /* optional bf16 copy of out (uint8 frames are exact in bf16) */ } a2cb_tcx_s2d_t;
+                 void* out_b16; /* optional bf16 copy of out (uint8 frames are exact in bf16) */
+                 int32_t scatter; /* 1: image b is written to slot idx[b] of out (in-place re-layout of a row subset) */
+                 int32_t pad_; } a2cb_tcx_s2d_t;
 typedef struct { float* part; const float* x; int64_t rows; int64_t pitch; int32_t C; int32_t pad_; float* lo; } a2cb_tcx_colsum_t;
 typedef struct { float* part; const float* x; const float* gy; int64_t rows; int32_t K, N, gy_stride, pad_; } a2cb_tcx_narrow_wgrad_t;
 typedef struct { const a2cb_tcx_prep_job_t* jobs; int64_t total; int32_t n_jobs; int32_t pad_; } a2cb_tcx_prep_multi_t;
@@ -492,6 +494,16 @@ int a2cb_kfac_scale(float* v, const float* dg, const float* da, int32_t rows, in
 int a2cb_kfac_nu(const float* v, const float* grads, int64_t n, double* scratch, float* out, float lr, float kl_clip,
                  a2cb_stream_t stream);
 int a2cb_frames_to_f32(float* dst, const void* src, int64_t n, int32_t src_is_u8, float div, a2cb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Rollout ingest (the host -> device half of RolloutStorage, reference storage.py:35-58 / envs.py:167-190).
+ * Uploads the columns of the listed environments of a time-major [rows, N, col_bytes] tensor from (pinned) host
+ * memory into the device tensor of the same layout: one strided DMA copy per run of adjacent environments,
+ * asynchronous on `stream`.  envs is a HOST list (it is consumed before the call returns).  The recurrent PPO
+ * update pulls the frames of each minibatch's environments this way while earlier minibatches compute.
+ * ------------------------------------------------------------------------- */
+int a2cb_upload_env_columns(void* dst, const void* src_host, int64_t col_bytes, int64_t rows, int64_t pitch_bytes,
+                            const int64_t* envs, int32_t n_envs, a2cb_stream_t stream);
 
 #ifdef __cplusplus
 }

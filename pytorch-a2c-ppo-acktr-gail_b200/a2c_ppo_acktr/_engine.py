@@ -996,6 +996,12 @@ class PolicyRuntime(object):
             for p in nb.tcx.prologue:
                 prog.prologue.add_plan(p, self.arena)
             prog.prologue.finalize()
+        prog.prologue_chunk = None
+        if nb.tcx is not None and nb.tcx.prologue_chunk:
+            prog.prologue_chunk = Program(self.dev)
+            for p in nb.tcx.prologue_chunk:
+                prog.prologue_chunk.add_plan(p, self.arena)
+            prog.prologue_chunk.finalize()
         return prog
 
     def acktr_programs(self, storage, hyper, noise, inv_B=None):

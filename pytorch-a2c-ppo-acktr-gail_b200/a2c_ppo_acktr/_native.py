@@ -36,6 +36,7 @@ _SIGNATURES = {
     "a2cb_get_gemm_mode": (c_int, []),
     "a2cb_returns_scan": (c_int, [c_void_p] * 6 + [c_int, c_i64, c_f64, c_f64, c_int, c_int, c_int, c_void_p]),
     "a2cb_gather_rows": (c_int, [ctypes.POINTER(GatherField), c_int, c_void_p, c_i64, c_int, c_i64, c_i64, c_void_p]),
+    "a2cb_upload_env_columns": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_int, c_void_p]),
 }
 
 _lib = None
@@ -140,3 +141,19 @@ def gather_rows(pairs, idx, n_out_rows, mode=0, E=0, N=0):
         rc = lib().a2cb_gather_rows(arr, len(pairs), idx_p, int(n_out_rows),
                                     int(mode), int(E), int(N), stream_ptr(dev))
     check(rc, "a2cb_gather_rows")
+
+
+def upload_env_columns(dst, src_host, envs, stream):
+    """Columns `envs` (host int64 list) of the time-major [rows, N, ...] pinned host tensor -> the device tensor of
+    the same shape, asynchronously on `stream` (one strided DMA copy per run of adjacent environments)."""
+    if src_host.is_cuda or not src_host.is_pinned():
+        raise NativeError("upload_env_columns: the source must be a pinned host tensor")
+    if tuple(src_host.shape) != tuple(dst.shape) or src_host.dtype != dst.dtype or not src_host.is_contiguous():
+        raise NativeError("upload_env_columns: source and destination must share shape, dtype and layout")
+    rows, N = dst.shape[0], dst.shape[1]
+    col_bytes = dst[0, 0].numel() * dst.element_size()
+    e = torch.as_tensor(envs, dtype=torch.int64).contiguous()
+    with torch.cuda.device(dst.device):
+        rc = lib().a2cb_upload_env_columns(dptr(dst, name="upload dst"), c_void_p(src_host.data_ptr()), col_bytes, rows,
+                                           N * col_bytes, c_void_p(e.data_ptr()), e.numel(), c_void_p(stream.cuda_stream))
+    check(rc, "a2cb_upload_env_columns")

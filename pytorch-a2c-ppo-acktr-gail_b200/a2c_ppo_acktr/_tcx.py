@@ -48,7 +48,7 @@ class PrepDesc(ctypes.Structure):
 
 class S2dDesc(ctypes.Structure):
     _fields_ = [("out", c_vp), ("out_lo", c_vp), ("frames", c_vp), ("idx", c_vp), ("src_is_u8", c_i32), ("B", c_i32),
-                ("C", c_i32), ("H", c_i32), ("W", c_i32), ("S", c_i32), ("out_b16", c_vp)]
+                ("C", c_i32), ("H", c_i32), ("W", c_i32), ("S", c_i32), ("out_b16", c_vp), ("scatter", c_i32), ("pad_", c_i32)]
 
 
 class ColsumDesc(ctypes.Structure):
@@ -370,6 +370,10 @@ class CnnNet(object):
         # rollout (`prologue`) and conv1 gathers its images from it through the row list (TMA coordinates).
         self.full_rows = getattr(nb, "full_rows", 0) if nb.gather else 0
         self.prologue = []
+        # the same re-layout restricted to the rows of ONE minibatch (row list, scattered to the rows' own slots):
+        # recurrent updates run it before each minibatch of the first epoch, so that the frames of a minibatch's
+        # environments can still be in flight from the host while earlier minibatches compute
+        self.prologue_chunk = []
 
     # -- small helpers ------------------------------------------------------------------------------
     def buf2(self, name, numel):
@@ -447,6 +451,13 @@ class CnnNet(object):
         s2d.spec = dict(out=x0, out_lo=x0_lo, frames=frames, n_img=n_img)
         if self.full_rows:
             self.prologue.append(s2d)
+
+            def make_s2d_chunk(arena):
+                return S2dDesc(arena.ptr(x0), arena.ptr(x0_lo), arena.ptr(frames), None, 1 if is_u8 else 0, B, 4, 84, 84, 4,
+                               arena.ptr(x0b), 1, 0)
+            chunk = TcxOp(OP_TCX_S2D, make_s2d_chunk, "frames_s2d_chunk", runtime_idx=True)
+            chunk.spec = dict(out=x0, out_lo=x0_lo, frames=frames, n_img=B, scatter=True)
+            self.prologue_chunk.append(chunk)
         else:
             ops.append(s2d)
 
@@ -732,7 +743,11 @@ def emulate(op, bufs, idx=None):
         n = sp["n_img"]
         rows = np.asarray(idx) if (op.runtime_idx and idx is not None) else np.arange(n)
         f = fr.reshape(-1, 4, 21, 4, 21, 4)[rows].astype(np.float32)            # [b, c, by, dy, bx, dx]
-        _np_view(bufs, sp["out"])[:n * 28224] = f.transpose(0, 2, 4, 1, 3, 5).reshape(-1)
+        f = f.transpose(0, 2, 4, 1, 3, 5).reshape(len(rows), 28224)
+        if sp.get("scatter"):
+            _np_view(bufs, sp["out"]).reshape(-1, 28224)[rows] = f              # image b -> slot rows[b]
+        else:
+            _np_view(bufs, sp["out"])[:n * 28224] = f.reshape(-1)
     elif k == OP_TCX_LO:
         pass
     elif k == OP_TCX_COLSUM:

@@ -50,6 +50,8 @@ class A2C_ACKTR():
         rt = policy.runtime()
         T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         B = T * N
+        if getattr(rollouts, "wait_staged", None) is not None:
+            rollouts.wait_staged()          # frames registered with stage_host(): upload them before the pass
         if self.acktr:
             return self._update_acktr(rt, rollouts)
         key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(), B,

@@ -42,6 +42,12 @@ def _adv_apply(rt, rollouts, moments):
     return adv
 
 
+def _wait_staged(rollouts):
+    f = getattr(rollouts, "wait_staged", None)
+    if f is not None:
+        f()
+
+
 def _adv_normalize(rt, rollouts):
     return _adv_apply(rt, rollouts, _adv_moments(rt, rollouts))
 
@@ -83,9 +89,10 @@ class PPO():
         self.shard = _dist.ShardInfo(world, rank, env_range[0], env_range[1], n_total) if world > 1 else None
         self._prog_key = None
 
-    def _program(self, rt, rollouts, mbs, adv, accum, inv_B=None, seq=None):
+    def _program(self, rt, rollouts, mbs, adv, accum, inv_B=None, seq=None, chunked=False):
         """(forward + loss + backward) program and the (clip + Adam) program.  Unsharded they are one
-        op list; sharded they are separated by the gradient all-reduce."""
+        op list; sharded they are separated by the gradient all-reduce.  `chunked`: the caller re-lays the
+        frames out per minibatch during the first epoch (`_first_epoch_chunk`) when the program offers it."""
         key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(),
                rollouts.value_preds.data_ptr(), rollouts.action_log_probs.data_ptr(), adv.data_ptr(),
                accum.data_ptr(), mbs, inv_B, seq, rollouts.masks.data_ptr(), self.clip_param, self.value_loss_coef, self.entropy_coef,
@@ -105,10 +112,38 @@ class PPO():
             opt.finalize()
             self._prog, self._opt_prog, self._prog_key = prog, opt, key
         pro = getattr(self._prog, "prologue", None)
+        if chunked and getattr(self._prog, "prologue_chunk", None) is not None:
+            return self._prog, self._opt_prog
+        _wait_staged(rollouts)
         if pro is not None and getattr(self, "_prologue_serial", None) != getattr(self, "_update_serial", 0):
             pro.run()                       # once per update: the rollout's frames do not change between minibatches
             self._prologue_serial = getattr(self, "_update_serial", 0)
         return self._prog, self._opt_prog
+
+    @staticmethod
+    def _first_epoch_chunks(prog, rollouts, perm, E, n_chunks):
+        """First epoch of a recurrent update.  The frames of minibatch k's environments are re-laid out right before
+        that minibatch (same bytes as one pass over the whole rollout); if the rollout was staged on the host
+        (`RolloutStorage.stage_host`) their upload is started here, in minibatch order on the copy stream, and
+        minibatch k only waits for ITS environments -- the rest of the upload overlaps the compute.
+        Returns prepare(k, rows) to call before minibatch k, and finish() after the epoch."""
+        chunked = getattr(prog, "prologue_chunk", None) is not None
+        events = None
+        if chunked and getattr(rollouts, "_staged_obs", None) is not None:
+            events = rollouts._upload_staged([perm[k * E:(k + 1) * E] for k in range(n_chunks)])
+        cur = torch.cuda.current_stream(rollouts.rewards.device)
+
+        def prepare(k, rows):
+            if chunked:
+                if events is not None:
+                    cur.wait_event(events[k])
+                prog.prologue_chunk.run(rows)
+
+        def finish():
+            if events is not None:
+                for ev in events[n_chunks:]:
+                    cur.wait_event(ev)
+        return prepare, finish
 
     def update(self, rollouts):
         policy = self.actor_critic
@@ -202,23 +237,29 @@ class PPO():
         adv = _adv_normalize(rt, rollouts)
         accum = rt.arena.ensure("loss_accum", 4)
         accum.zero_()
-        prog, _ = self._program(rt, rollouts, T * E, adv, accum, seq=(T, E))
+        prog, _ = self._program(rt, rollouts, T * E, adv, accum, seq=(T, E), chunked=True)
         hxs_mb = rt.arena.bufs["hxs_mb"][:E * rt.spec.hidden].view(E, rt.spec.hidden)
         h0 = rollouts.recurrent_hidden_states[0]
         t_off = (torch.arange(T, device=rt.dev, dtype=torch.int64) * N).view(T, 1)
         launches0 = _native.launch_count()
-        for _ in range(self.ppo_epoch):
+        for epoch in range(self.ppo_epoch):
             perm = torch.randperm(N)
-            for start in range(0, N, E):
+            if epoch == 0:
+                prepare, finish = self._first_epoch_chunks(prog, rollouts, perm, E, N // E)
+            for k, start in enumerate(range(0, N, E)):
                 if start + E > N:
                     raise IndexError("index {} is out of bounds for dimension 0 with size {}".format(N, N))
                 env = perm[start:start + E].to(rt.dev)
                 rows = (t_off + env.view(1, E)).reshape(-1).contiguous()
+                if epoch == 0:
+                    prepare(k, rows)
                 _native.gather_rows([(h0, hxs_mb)], env, E)
                 self.optimizer.configure(prog.optim_desc)
                 prog.run(rows)
                 if self.step_hook is not None:
                     self.step_hook(self.optimizer.step_count)
+            if epoch == 0:
+                finish()
         self.last_launches = _native.launch_count() - launches0
         num_updates = self.ppo_epoch * self.num_mini_batch
         sums = accum[:3].cpu()
@@ -253,17 +294,21 @@ class PPO():
         adv = _adv_apply(rt, rollouts, moments)
         accum = rt.arena.ensure("loss_accum", 4)
         accum.zero_()
-        prog, opt = self._program(rt, rollouts, T * E, adv, accum, inv_B=1.0 / (T * E_global), seq=(T, E))
+        prog, opt = self._program(rt, rollouts, T * E, adv, accum, inv_B=1.0 / (T * E_global), seq=(T, E), chunked=True)
         hxs_mb = rt.arena.bufs["hxs_mb"][:E * rt.spec.hidden].view(E, rt.spec.hidden)
         h0 = rollouts.recurrent_hidden_states[0]
         t_off = (torch.arange(T, device=rt.dev, dtype=torch.int64) * n_loc).view(T, 1)
         grads = rt.arena.bufs["G"]
         launches0 = _native.launch_count()
-        for _ in range(self.ppo_epoch):
+        for epoch in range(self.ppo_epoch):
             perm = torch.randperm(n_loc)                      # same seed on every rank -> same local order
-            for start in range(0, E * self.num_mini_batch, E):
+            if epoch == 0:
+                prepare, finish = self._first_epoch_chunks(prog, rollouts, perm, E, self.num_mini_batch)
+            for k, start in enumerate(range(0, E * self.num_mini_batch, E)):
                 env = perm[start:start + E].to(rt.dev)
                 rows = (t_off + env.view(1, E)).reshape(-1).contiguous()
+                if epoch == 0:
+                    prepare(k, rows)
                 _native.gather_rows([(h0, hxs_mb)], env, E)
                 prog.run(rows)
                 yield grads
@@ -271,6 +316,8 @@ class PPO():
                 opt.run()
                 if self.step_hook is not None:
                     self.step_hook(self.optimizer.step_count)
+            if epoch == 0:
+                finish()
         self.last_launches = _native.launch_count() - launches0
         yield accum
         num_updates = self.ppo_epoch * self.num_mini_batch

@@ -9,9 +9,13 @@ advanced).  `compute_returns` is one reverse-scan kernel instead of a Python loo
 over time; the generators are one fused gather launch per minibatch instead of
 eight `aten::index` calls.
 
-One opt-in extension: `obs_dtype=torch.uint8` stores Atari frames as bytes (a
+Two opt-in extensions: `obs_dtype=torch.uint8` stores Atari frames as bytes (a
 quarter of the HBM footprint and gather traffic); the policy kernels normalise
 bytes to fp32/255 while loading.  The default (fp32) keeps the reference contract.
+`stage_host(...)` ingests a whole rollout collected on the host (pinned memory): the
+narrow tensors are copied at once, the frames are pulled on a side stream --
+per minibatch environment set by the recurrent PPO update, so that the upload of
+later minibatches overlaps the compute of earlier ones.
 """
 import torch
 
@@ -47,11 +51,73 @@ class RolloutStorage(object):
         self.num_steps = T
         self.step = 0
         self._idx_cache = None
+        self._staged_obs = None          # pinned host frames whose upload has not been started yet
+        self._copy_stream = None
 
     # -- placement ---------------------------------------------------------
     def to(self, device):
         for name in self._MOVABLE:
             setattr(self, name, getattr(self, name).to(device))
+
+    # -- host ingest (extension; the device-side half of envs.py:167-190 `VecPyTorch`) ------------
+    def stage_host(self, host):
+        """`host`: dict attribute name -> PINNED host tensor of the attribute's shape and dtype (any subset of the
+        buffer's tensors).  Everything except `obs` is copied now, asynchronously on the current stream.  The frames
+        are only registered: the next `update()` (or `wait_staged()`, which every other reader of `obs` in this
+        package calls) uploads them on a side stream.  The host tensors must stay untouched until then."""
+        dev = self.rewards.device
+        if dev.type != "cuda":
+            raise _native.NativeError("stage_host: the rollout buffer must live on a CUDA device")
+        for name, src in host.items():
+            if name not in self._MOVABLE:
+                raise KeyError("stage_host: unknown rollout tensor %r" % name)
+            dst = getattr(self, name)
+            if tuple(src.shape) != tuple(dst.shape) or src.dtype != dst.dtype:
+                raise ValueError("stage_host: %s must be %s %s" % (name, tuple(dst.shape), dst.dtype))
+            if name == "obs":
+                if not src.is_pinned() or not src.is_contiguous():
+                    raise _native.NativeError("stage_host: obs must be a contiguous pinned host tensor")
+                self._staged_obs = src
+            else:
+                dst.copy_(src, non_blocking=True)
+
+    def _upload_staged(self, env_chunks=None):
+        """Starts the upload of the registered frames on the copy stream, one strided copy set per chunk of
+        environments (default: everything at once).  Returns one event per chunk, or None if nothing is staged."""
+        host, self._staged_obs = self._staged_obs, None
+        if host is None:
+            return None
+        dev = self.obs.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream(dev))      # earlier readers / writers of obs are done
+        N = self.obs.shape[1]
+        if env_chunks is None:
+            env_chunks = [torch.arange(N)]
+        else:
+            seen = torch.zeros(N, dtype=torch.bool)
+            for c in env_chunks:
+                seen[c] = True
+            rest = (~seen).nonzero().view(-1)
+            if rest.numel():
+                env_chunks = list(env_chunks) + [rest]
+        events = []
+        for envs in env_chunks:
+            _native.upload_env_columns(self.obs, host, envs, cs)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            events.append(ev)
+        self._staged_keepalive = host                       # until the next stage / upload replaces it
+        return events
+
+    def wait_staged(self):
+        """Makes the current stream wait for the staged frames (no-op when nothing is staged)."""
+        events = self._upload_staged()
+        if events:
+            cur = torch.cuda.current_stream(self.obs.device)
+            for ev in events:
+                cur.wait_event(ev)
 
     # -- actor-side writes (reference storage.py:46-64) --------------------------
     def insert(self, obs, recurrent_hidden_states, actions, action_log_probs,
@@ -68,6 +134,7 @@ class RolloutStorage(object):
         self.step = (t + 1) % self.num_steps
 
     def after_update(self):
+        self.wait_staged()
         for buf in (self.obs, self.recurrent_hidden_states, self.masks, self.bad_masks):
             buf[0].copy_(buf[-1])
 
@@ -119,6 +186,7 @@ class RolloutStorage(object):
         # consecutive chunks (reference storage.py:122-125).
         perm = torch.randperm(batch_size)
         dev = self.rewards.device
+        self.wait_staged()
         perm_dev = perm.to(dev, non_blocking=False)
         srcs = self._flat_sources(advantages)
         for k in range(batch_size // mini_batch_size):
@@ -140,6 +208,7 @@ class RolloutStorage(object):
         T, N = self.num_steps, num_processes
         perm = torch.randperm(num_processes)
         dev = self.rewards.device
+        self.wait_staged()
         perm_dev = perm.to(dev)
         srcs = self._flat_sources(advantages)
         hidden_src = self.recurrent_hidden_states[0]            # [N, H]: state at t = 0 only

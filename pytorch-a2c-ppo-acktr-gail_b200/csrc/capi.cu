@@ -8,7 +8,9 @@
 #include "tcx.cuh"
 #include "mlp_fused.cuh"
 
+#include <algorithm>
 #include <atomic>
+#include <vector>
 #include <stdarg.h>
 
 namespace a2cb {
@@ -136,6 +138,28 @@ int a2cb_kfac_nu(const float* v, const float* grads, int64_t n, double* scratch,
 }
 int a2cb_frames_to_f32(float* dst, const void* src, int64_t n, int32_t src_is_u8, float div, a2cb_stream_t stream) {
     return frames_to_f32(dst, src, (long)n, src_is_u8, div, (cudaStream_t)stream);
+}
+
+int a2cb_upload_env_columns(void* dst, const void* src_host, int64_t col_bytes, int64_t rows, int64_t pitch_bytes,
+                            const int64_t* envs, int32_t n_envs, a2cb_stream_t stream) {
+    A2CB_REQUIRE(dst && src_host && envs && col_bytes > 0 && rows > 0 && n_envs > 0 && pitch_bytes >= col_bytes &&
+                 pitch_bytes % col_bytes == 0, "upload_env_columns: bad arguments");
+    const int64_t N = pitch_bytes / col_bytes;
+    std::vector<int64_t> e(envs, envs + n_envs);
+    std::sort(e.begin(), e.end());
+    for (size_t i = 0; i < e.size();) {
+        A2CB_REQUIRE(e[i] >= 0 && e[i] < N, "upload_env_columns: environment %lld out of range", (long long)e[i]);
+        size_t j = i + 1;
+        while (j < e.size() && e[j] == e[j - 1] + 1) ++j;               // run of adjacent environments: one copy
+        const int64_t off = e[i] * col_bytes;
+        const cudaError_t err = cudaMemcpy2DAsync(static_cast<char*>(dst) + off, (size_t)pitch_bytes,
+                                                  static_cast<const char*>(src_host) + off, (size_t)pitch_bytes,
+                                                  (size_t)((int64_t)(j - i) * col_bytes), (size_t)rows,
+                                                  cudaMemcpyHostToDevice, (cudaStream_t)stream);
+        if (err != cudaSuccess) { set_error("upload_env_columns: %s", cudaGetErrorString(err)); return A2CB_ERR_CUDA; }
+        i = j;
+    }
+    return 0;
 }
 
 int a2cb_gru_op(int32_t which, const a2cb_gru_t* desc, a2cb_stream_t stream) {
@@ -302,7 +326,7 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             }
             case A2CB_OP_TCX_S2D: {
                 const a2cb_tcx_s2d_t& q = *reinterpret_cast<const a2cb_tcx_s2d_t*>(op.desc);
-                rc = tcx_s2d(q.out, q.out_lo, q.out_b16, q.frames, q.src_is_u8, rt ? idx : q.idx, q.B, q.C, q.H, q.W, q.S, st);
+                rc = tcx_s2d(q.out, q.out_lo, q.out_b16, q.frames, q.src_is_u8, rt ? idx : q.idx, q.B, q.C, q.H, q.W, q.S, st, q.scatter);
                 break;
             }
             case A2CB_OP_TCX_COLSUM: {

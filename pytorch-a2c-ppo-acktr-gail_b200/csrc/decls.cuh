@@ -70,7 +70,7 @@ int tcx_lo_plane(float* lo, const float* x, long n, cudaStream_t st);
 int tcx_prep_weights(float* img, float* img_lo, const float* src, long N, long K, const int32_t* ntab,
                      const int32_t* ktab, cudaStream_t st);
 int tcx_s2d(float* out, float* out_lo, void* out_b16, const void* frames, int src_is_u8, const int64_t* idx, int B, int C,
-            int H, int W, int S, cudaStream_t st);
+            int H, int W, int S, cudaStream_t st, int scatter = 0);
 int tcx_colsum(float* part, const float* x, float* lo, long rows, int C, long pitch, cudaStream_t st);
 int tcx_colsum_blocks(long rows);
 int tcx_prep_multi(const void* jobs, int n_jobs, long total, cudaStream_t st);

@@ -40,7 +40,7 @@ tcx_prep_kernel(float* __restrict__ img, float* __restrict__ img_lo, const float
 template <typename T>
 __global__ void __launch_bounds__(256)
 tcx_s2d_kernel(float* __restrict__ out, float* __restrict__ out_lo, const T* __restrict__ frames,
-               const int64_t* __restrict__ idx, int B, int C, int H, int W, int S) {
+               const int64_t* __restrict__ idx, int B, int C, int H, int W, int S, int scatter) {
     const int Hb = H / S, Wb = W / S, CC = C * S * S;
     const long total = (long)B * Hb * Wb * CC;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -52,8 +52,9 @@ tcx_s2d_kernel(float* __restrict__ out, float* __restrict__ out_lo, const T* __r
         const int dx = ch % S, dy = (ch / S) % S, c = ch / (S * S);
         const long row = idx ? (long)idx[b] : b;
         const float v = (float)frames[((row * C + c) * H + (by * S + dy)) * W + bx * S + dx];
-        out[e] = v;
-        if (out_lo) out_lo[e] = ax_lo(v);
+        const long o = scatter ? e + (row - b) * ((long)Hb * Wb * CC) : e;     // scatter: image slot = source row
+        out[o] = v;
+        if (out_lo) out_lo[o] = ax_lo(v);
     }
 }
 
@@ -94,10 +95,11 @@ tcx_prep_multi_kernel(const PrepJob* __restrict__ jobs, int n_jobs, long total) 
 template <typename T>
 __global__ void __launch_bounds__(352)
 tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, uint2* __restrict__ out_b16,
-                     const T* __restrict__ frames, const int64_t* __restrict__ idx) {
+                     const T* __restrict__ frames, const int64_t* __restrict__ idx, int scatter) {
     __shared__ float4 tile[16][21];
     const int b = blockIdx.x / 21, by = blockIdx.x % 21;
     const long row = idx ? (long)idx[b] : b;
+    const long slot = scatter ? row : b;                                 // scatter: image slot = source row
     const int i = threadIdx.x;
     if (i < 336) {
         const int r = i / 21, bx = i % 21;                       // r = c * 4 + dy
@@ -115,7 +117,7 @@ tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, uint
     if (i < 336) {
         const int bx = i >> 4, r = i & 15;
         const float4 v = tile[r][bx];
-        const long o = ((long)(b * 21 + by) * 21 + bx) * 16 + r;
+        const long o = ((slot * 21 + by) * 21 + bx) * 16 + r;
         out[o] = v;
         if (out_lo) out_lo[o] = make_float4(ax_lo(v.x), ax_lo(v.y), ax_lo(v.z), ax_lo(v.w));
         if (out_b16) {
@@ -294,26 +296,27 @@ int tcx_prep_weights(float* img, float* img_lo, const float* src, long N, long K
 }
 
 int tcx_s2d(float* out, float* out_lo, void* out_b16, const void* frames, int src_is_u8, const int64_t* idx, int B, int C,
-            int H, int W, int S, cudaStream_t st) {
+            int H, int W, int S, cudaStream_t st, int scatter) {
     A2CB_REQUIRE(out && frames && B > 0 && S > 0 && H % S == 0 && W % S == 0, "tcx_s2d: bad arguments");
+    A2CB_REQUIRE(!scatter || idx, "tcx_s2d: scatter mode needs a row list");
     if (C == 4 && H == 84 && W == 84 && S == 4) {
         if (src_is_u8)
             tcx_s2d_atari_kernel<uint8_t><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
                                                                                reinterpret_cast<uint2*>(out_b16),
-                                                                               reinterpret_cast<const uint8_t*>(frames), idx);
+                                                                               reinterpret_cast<const uint8_t*>(frames), idx, scatter);
         else
             tcx_s2d_atari_kernel<float><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
                                                                              reinterpret_cast<uint2*>(out_b16),
-                                                                             reinterpret_cast<const float*>(frames), idx);
+                                                                             reinterpret_cast<const float*>(frames), idx, scatter);
         return check_launch("tcx_s2d");
     }
     A2CB_REQUIRE(!out_b16, "tcx_s2d: the bf16 copy is only produced for the Atari geometry");
     const long total = (long)B * C * H * W;
     const unsigned grid = (unsigned)min((total + 255) / 256, (long)kNumSM * 32);
     if (src_is_u8)
-        tcx_s2d_kernel<uint8_t><<<grid, 256, 0, st>>>(out, out_lo, reinterpret_cast<const uint8_t*>(frames), idx, B, C, H, W, S);
+        tcx_s2d_kernel<uint8_t><<<grid, 256, 0, st>>>(out, out_lo, reinterpret_cast<const uint8_t*>(frames), idx, B, C, H, W, S, scatter);
     else
-        tcx_s2d_kernel<float><<<grid, 256, 0, st>>>(out, out_lo, reinterpret_cast<const float*>(frames), idx, B, C, H, W, S);
+        tcx_s2d_kernel<float><<<grid, 256, 0, st>>>(out, out_lo, reinterpret_cast<const float*>(frames), idx, B, C, H, W, S, scatter);
     return check_launch("tcx_s2d");
 }
 

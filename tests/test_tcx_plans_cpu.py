@@ -34,7 +34,7 @@ class _FakeBuilder(object):
         return (self.n(name), 0)
 
 
-@pytest.mark.parametrize("gather_full", [False, True])
+@pytest.mark.parametrize("gather_full", [False, True, "chunk"])
 @pytest.mark.parametrize("u8", [True, False])
 def test_cnn_trunk_ops_match_torch(u8, gather_full):
     torch.manual_seed(0)
@@ -71,9 +71,16 @@ def test_cnn_trunk_ops_match_torch(u8, gather_full):
     bufs = {"obs": (obs_u8.numpy().ravel() if u8 else obs_u8.float().numpy().ravel()), "P": Pbuf, "G": np.zeros_like(Pbuf)}
     for name, numel in nb.sizes.items():
         bufs[name] = np.zeros(numel, np.float32)
-    assert bool(net.prologue) == gather_full
-    for op in net.prologue:
-        _tcx.emulate(op, bufs)
+    assert bool(net.prologue) == bool(gather_full) and bool(net.prologue_chunk) == bool(gather_full)
+    if gather_full == "chunk":
+        # per-minibatch re-layout: only the minibatch's rows are converted, each into its own slot of the full tensor
+        for op in net.prologue_chunk:
+            _tcx.emulate(op, bufs, idx)
+        x0 = bufs["x0_full"].reshape(rows, -1)
+        assert all((np.abs(x0[r]).sum() > 0) == (r in idx) for r in range(rows))
+    else:
+        for op in net.prologue:
+            _tcx.emulate(op, bufs)
     for op in fwd:
         _tcx.emulate(op, bufs, idx)
     nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().detach().numpy()

@@ -411,3 +411,55 @@ def test_sharded_recurrent_ppo_equals_single_device(gemm_engine, monkeypatch):
         d = (p - p1[k]).double().norm() / p1[k].double().norm().clamp_min(1e-30)
         assert d <= 2e-4, (k, d.item())
         assert torch.equal(p, dict(ranks[1]["pol"].named_parameters())[k])
+
+
+@pytest.mark.parametrize("name", ["C5s", "C3u", "C2"])
+def test_staged_host_ingest_equals_resident_rollout(name, gemm_engine):
+    """`RolloutStorage.stage_host` (narrow tensors copied at once, frames pulled on a side stream -- per minibatch
+    environment set by the recurrent PPO update) must give bit-identical results to a rollout that was resident
+    before the update: same kernels, same order, only the arrival time of the frames differs."""
+    results = []
+    for staged in (False, True):
+        case, cfg, pol, st, agent = build(name, True)
+        if staged:
+            host = {k: getattr(st, k).cpu().pin_memory() for k in
+                    ("obs", "rewards", "masks", "bad_masks", "actions", "action_log_probs", "value_preds",
+                     "recurrent_hidden_states")}
+            st.obs.fill_(7)                                   # whatever was resident is stale
+            st.rewards.zero_()
+            st.stage_host(host)
+            ro = helpers.rollout_from_case(case, cfg, obs_uint8=True)
+            st.compute_returns(ro["next_value"].to(DEV), cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"],
+                               cfg["use_proper_time_limits"], schedule=1)
+        torch.manual_seed(7)
+        losses = agent.update(st)
+        st.after_update()
+        if staged:
+            assert torch.equal(st.obs.cpu(), torch.cat([host["obs"][-1:], host["obs"][1:]]))
+        results.append((losses, {k: p.detach().clone() for k, p in pol.named_parameters()}))
+    assert results[0][0] == results[1][0]
+    for k, p in results[0][1].items():
+        assert torch.equal(p, results[1][1][k]), k
+
+
+def test_upload_env_columns_and_wait_staged():
+    """The strided column upload (runs of adjacent environments merged) and the plain wait_staged() path."""
+    from a2c_ppo_acktr import _native
+    T, N = 5, 12
+    st = RolloutStorage(T, N, (4, 84, 84), Discrete(6), 1, obs_dtype=torch.uint8)
+    st.to(DEV)
+    host = torch.randint(0, 256, (T + 1, N, 4, 84, 84), dtype=torch.uint8).pin_memory()
+    s = torch.cuda.Stream(DEV)
+    envs = torch.tensor([7, 3, 4, 11, 0, 5])
+    _native.upload_env_columns(st.obs, host, envs, s)
+    s.synchronize()
+    got = st.obs.cpu()
+    for n in range(N):
+        want = host[:, n] if n in envs.tolist() else torch.zeros_like(host[:, n])
+        assert torch.equal(got[:, n], want), n
+    st.stage_host({"obs": host})
+    st.wait_staged()
+    torch.cuda.synchronize()
+    assert torch.equal(st.obs.cpu(), host)
+    with pytest.raises(_native.NativeError):
+        st.stage_host({"obs": host.clone()})                # not pinned
