@@ -38,10 +38,10 @@ class A2C_ACKTR():
         self.shard = None
 
     def set_distributed(self, world, rank, env_range, n_total):
-        """Environment-sharded ACKTR: per-update factor increments and the gradient are all-reduced
-        (SURVEY.md section 8e); every rank then performs the identical KFAC step."""
-        if not self.acktr and world > 1:
-            raise _native.NativeError("sharded A2C is not built; use PPO or ACKTR")
+        """Environment-sharded update.  ACKTR: per-update factor increments and the
+        gradient are all-reduced, every rank then performs the identical KFAC step.  A2C: loss terms are local
+        sums over the GLOBAL batch size, the flat gradient is all-reduced before the (redundant, identical)
+        clip + RMSprop step."""
         self.shard = _dist.ShardInfo(world, rank, env_range[0], env_range[1], n_total) if world > 1 else None
         self._prog_key = None
 
@@ -54,21 +54,46 @@ class A2C_ACKTR():
             rollouts.wait_staged()          # frames registered with stage_host(): upload them before the pass
         if self.acktr:
             return self._update_acktr(rt, rollouts)
+        gen = self.a2c_steps(rt, rollouts)
+        try:
+            while True:
+                _dist.all_reduce_sum(next(gen))
+        except StopIteration as done:
+            return done.value
+
+    def a2c_steps(self, rt, rollouts):
+        """reference a2c_acktr.py:38-80 with acktr=False.  Generator: yields every tensor that must be
+        sum-all-reduced when the rollout is sharded (nothing is yielded on a single device)."""
+        from .. import _engine
+        policy = self.actor_critic
+        sh = self.shard
+        world = sh.world if sh is not None else 1
+        T, N = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+        B = T * N
+        assert sh is None or N == sh.n_local, "rollouts hold %d environments, the shard declares %d" % (N, sh.n_local)
         key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(), B,
                rollouts.masks.data_ptr(), rollouts.recurrent_hidden_states.data_ptr(),
-               self.value_loss_coef, self.entropy_coef, self.max_grad_norm)
+               self.value_loss_coef, self.entropy_coef, self.max_grad_norm, world)
         if key != self._prog_key:
             hyper = dict(value_loss_coef=self.value_loss_coef, entropy_coef=self.entropy_coef)
+            if sh is not None:
+                hyper["inv_B"] = 1.0 / (B * world)
             prog = rt.train_program(rollouts, B, 1, hyper, use_idx=False,
                                     seq=(T, N) if policy.is_recurrent else None)
             self.optimizer._ensure_state()
-            rt.add_optimizer_ops(prog, 1, self.optimizer.state1, None, self.max_grad_norm)
+            opt = prog if sh is None else _engine.Program(rt.dev)     # sharded: the all-reduce sits in between
+            opt.optim_desc = rt.add_optimizer_ops(opt, 1, self.optimizer.state1, None, self.max_grad_norm)
             prog.finalize()
-            self._prog, self._prog_key = prog, key
-        prog = self._prog
+            opt.finalize()
+            self._prog, self._opt_prog, self._prog_key = prog, opt, key
+        prog, opt = self._prog, self._opt_prog
         launches0 = _native.launch_count()
-        self.optimizer.configure(prog.optim_desc)
+        self.optimizer.configure(opt.optim_desc)
         prog.run()
+        if sh is not None:
+            yield rt.arena.bufs["G"]
+            opt.run()
+            yield prog.loss_out
         self.last_launches = _native.launch_count() - launches0
         out = prog.loss_out[:3].cpu()
         return out[0].item(), out[1].item(), out[2].item()

@@ -464,18 +464,23 @@ __device__ __forceinline__ void pm_kstep(float (*acc)[4], const float* __restric
     uint32_t bh0, bl0, bh1, bl1;
     pm_split(x0, bh0, bl0);
     pm_split(x1, bh1, bl1);
+    // all A fragments of the k-step first, then the MMAs product-major: consecutive MMAs hit DIFFERENT accumulators,
+    // so the three products of one tile do not wait for each other's latency
+    uint32_t ah[MT][4], al[MT][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         const float* w = Wsm + (long)(mt * 16 + g) * P + k0 + t;
-        uint32_t ah[4], al[4];
-        pm_split(w[0], ah[0], al[0]);
-        pm_split(w[8 * P], ah[1], al[1]);
-        pm_split(w[4], ah[2], al[2]);
-        pm_split(w[8 * P + 4], ah[3], al[3]);
-        pm_mma(acc[mt], al, bh0, bh1);
-        pm_mma(acc[mt], ah, bl0, bl1);
-        pm_mma(acc[mt], ah, bh0, bh1);
+        pm_split(w[0], ah[mt][0], al[mt][0]);
+        pm_split(w[8 * P], ah[mt][1], al[mt][1]);
+        pm_split(w[4], ah[mt][2], al[mt][2]);
+        pm_split(w[8 * P + 4], ah[mt][3], al[mt][3]);
     }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) pm_mma(acc[mt], al[mt], bh0, bh1);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) pm_mma(acc[mt], ah[mt], bl0, bl1);
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) pm_mma(acc[mt], ah[mt], bh0, bh1);
 }
 
 __global__ void __launch_bounds__(PG_NT)
@@ -553,10 +558,10 @@ gru_mma_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* 
             for (int gg = 0; gg < 3; ++gg) {
                 const int col = uo * 3 + gg, mt = col >> 4, i = col & 15;
                 const int ln = (i & 7) * 4 + (ro >> 1), rg = (i >> 3) * 2 + (ro & 1);
-                float s = 0.f;
+                float v[PG_NW];
 #pragma unroll
-                for (int w = 0; w < PG_NW; ++w) s += reinterpret_cast<const float*>(red + (w * 6 + mt) * 32 + ln)[rg];
-                gsum[gg] = s;
+                for (int w = 0; w < PG_NW; ++w) v[w] = reinterpret_cast<const float*>(red + (w * 6 + mt) * 32 + ln)[rg];
+                gsum[gg] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
             }
             const float ghr = gsum[0] + b_r, ghz = gsum[1] + b_z, ghn = gsum[2] + b_n;
             const float rr = pg_sigmoid(q.r + ghr);
@@ -681,9 +686,10 @@ gru_mma_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __rest
             __syncthreads();
             const int mt = uo >> 4, i = uo & 15;
             const int ln = (i & 7) * 4 + (ro >> 1), rg = (i >> 3) * 2 + (ro & 1);
-            float sum = 0.f;
+            float v[PG_NW];
 #pragma unroll
-            for (int w = 0; w < PG_NW; ++w) sum += reinterpret_cast<const float*>(red + (w * 2 + mt) * 32 + ln)[rg];
+            for (int w = 0; w < PG_NW; ++w) v[w] = reinterpret_cast<const float*>(red + (w * 2 + mt) * 32 + ln)[rg];
+            const float sum = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
             const int my = r0 + ro;
             if (my < d.N) {
                 if (grp == (int)blockIdx.y) carry0 += sum;

@@ -51,6 +51,9 @@ def main():
                        cfg["use_proper_time_limits"], schedule=1)
     if cfg["algo"] == "acktr":
         agent = algo.A2C_ACKTR(pol, cfg["value_loss_coef"], cfg["entropy_coef"], acktr=True)
+    elif cfg["algo"] == "a2c":
+        agent = algo.A2C_ACKTR(pol, cfg["value_loss_coef"], cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"],
+                               alpha=cfg["alpha"], max_grad_norm=cfg["max_grad_norm"])
     else:
         agent = algo.PPO(pol, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
                          cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"], max_grad_norm=cfg["max_grad_norm"])

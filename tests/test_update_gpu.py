@@ -463,3 +463,39 @@ def test_upload_env_columns_and_wait_staged():
     assert torch.equal(st.obs.cpu(), host)
     with pytest.raises(_native.NativeError):
         st.stage_host({"obs": host.clone()})                # not pinned
+
+
+@pytest.mark.parametrize("name,world", [("C2", 2), ("C2", 4), ("C2g", 2)])
+def test_sharded_a2c_equals_single_device(name, world, gemm_engine):
+    """A2C on `world` emulated ranks (environment shards, gradient + loss sums exchanged) vs the reference golden
+    of the single-device update; C2g is the recurrent variant (whole environments per rank)."""
+    case = helpers.load("update_" + name)
+    cfg = helpers.case_config(case)
+    ro = helpers.rollout_from_case(case, cfg, obs_uint8=True)
+    per = cfg["N"] // world
+    ranks = []
+    for r in range(world):
+        lo, hi = r * per, (r + 1) * per
+        torch.manual_seed(1)
+        pol = Policy(cfg["obs_shape"], space(cfg["action"]), base_kwargs={"recurrent": cfg["recurrent"]}).to(DEV)
+        st = RolloutStorage(cfg["T"], per, cfg["obs_shape"], space(cfg["action"]), helpers.hidden_size_of(cfg),
+                            obs_dtype=torch.uint8)
+        for nme in ("obs", "recurrent_hidden_states", "rewards", "value_preds", "action_log_probs", "actions",
+                    "masks", "bad_masks"):
+            getattr(st, nme).copy_(ro[nme][:, lo:hi])
+        st.to(DEV)
+        st.compute_returns(ro["next_value"][lo:hi].to(DEV), cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"],
+                           cfg["use_proper_time_limits"], schedule=1)
+        agent = algo.A2C_ACKTR(pol, cfg["value_loss_coef"], cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"],
+                               alpha=cfg["alpha"], max_grad_norm=cfg["max_grad_norm"])
+        agent.set_distributed(world, r, (lo, hi), cfg["N"])
+        ranks.append(dict(pol=pol, st=st, agent=agent, rng=torch.get_rng_state(),
+                          gen=agent.a2c_steps(pol.runtime(), st)))
+    results = _lockstep(ranks)
+    for res in results:
+        np.testing.assert_allclose(np.array(res), case["losses"], rtol=1e-4, atol=2e-6)
+    p0 = dict(ranks[0]["pol"].named_parameters())
+    for r in ranks[1:]:
+        for k, p in r["pol"].named_parameters():
+            assert torch.equal(p, p0[k]), k
+    assert helpers.rel_l2(case, "finaldense_", p0) <= 1e-4
