@@ -407,6 +407,7 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_MLP_BWD 23
 #define A2CB_OP_TCX_NARROW_FWD 24
 #define A2CB_OP_TCX_NARROW_DGRAD 25
+#define A2CB_OP_SAMPLE 26
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -494,6 +495,20 @@ int a2cb_kfac_scale(float* v, const float* dg, const float* da, int32_t rows, in
 int a2cb_kfac_nu(const float* v, const float* grads, int64_t n, double* scratch, float* out, float lr, float kl_clip,
                  a2cb_stream_t stream);
 int a2cb_frames_to_f32(float* dst, const void* src, int64_t n, int32_t src_is_u8, float div, a2cb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Actor-side head of Policy.act          a2c_ppo_acktr/model.py:54-66, distributions.py:18-44,59-95
+ * From the head outputs z[b] = (value, logits[A] | mean[A]): draws the action (Categorical: inverse CDF of the
+ * softmax; DiagGaussian: mean + exp(logstd) * N(0,1)) or takes the mode (deterministic: argmax | mean), and writes
+ * value, action and log-prob to their destinations (e.g. the [step] slots of the rollout buffer, storage.py:46-58).
+ * rng = DEVICE {seed, offset, ticket} (3 x uint64, ticket zeroed once): Philox4x32-10 keyed by seed, counter
+ * (row, draw, offset); every sampling launch advances offset by one on the device.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    const float* z; const float* logstd; float* value_out; void* action_out; float* logp_out; uint64_t* rng;
+    int32_t B, A, z_stride, dist, deterministic, pad_;
+} a2cb_sample_t;
+int a2cb_sample_actions(const a2cb_sample_t* desc, a2cb_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Rollout ingest (the host -> device half of RolloutStorage, reference storage.py:35-58 / envs.py:167-190).

@@ -82,6 +82,56 @@ class MlpDesc(ctypes.Structure):
 
 
 OP_MLP_FWD, OP_MLP_BWD = 22, 23
+OP_SAMPLE = 26
+
+
+class SampleDesc(ctypes.Structure):
+    """Mirror of a2cb_sample_t."""
+    _fields_ = [("z", c_vp), ("logstd", c_vp), ("value_out", c_vp), ("action_out", c_vp), ("logp_out", c_vp),
+                ("rng", c_vp), ("B", c_i32), ("A", c_i32), ("z_stride", c_i32), ("dist", c_i32),
+                ("deterministic", c_i32), ("pad_", c_i32)]
+
+
+def _pointer_sites(obj, lo, hi, out):
+    """Every c_void_p field of a descriptor (nested structures and arrays of structures included) whose value
+    lies in [lo, hi): appended to `out` as (owner, field name, offset from lo)."""
+    for name, typ in obj._fields_:
+        if typ is c_vp:
+            v = getattr(obj, name)
+            if v is not None and lo <= v < hi:
+                out.append((obj, name, v - lo))
+        elif isinstance(typ, type) and issubclass(typ, ctypes.Structure):
+            _pointer_sites(getattr(obj, name), lo, hi, out)
+        elif isinstance(typ, type) and issubclass(typ, ctypes.Array) and issubclass(typ._type_, ctypes.Structure):
+            for el in getattr(obj, name):
+                _pointer_sites(el, lo, hi, out)
+
+
+class ActPlan(object):
+    """No-grad forward + sampling head of one actor step for a fixed batch size (Policy.act / Policy.act_into).
+    The program is built once against arena-owned placeholder tensors; `sites[role]` lists every descriptor field
+    that points into a placeholder, so a call can re-point inputs and outputs (e.g. at the [step] slots of the
+    rollout buffer) by patching a handful of pointers -- no staging copies, no per-step program."""
+
+    ROLES_IN = ("obs", "hxs", "masks")
+    ROLES_OUT = ("value", "action", "logp", "hout")
+
+    def __init__(self, prog, sample, tensors, sites):
+        self.prog, self.sample, self.tensors, self.sites = prog, sample, tensors, sites
+        self.home = {r: t.data_ptr() for r, t in tensors.items()}
+        self.current = dict(self.home)
+
+    def point(self, role, address):
+        if self.current[role] != address:
+            for owner, field, off in self.sites[role]:
+                setattr(owner, field, address + off)
+            self.current[role] = address
+
+    def run(self, deterministic, pointers=None):
+        for role, base in self.home.items():
+            self.point(role, base if pointers is None else pointers.get(role, base))
+        self.sample.deterministic = int(bool(deterministic))
+        self.prog.run()
 
 
 class GruSeqDesc(ctypes.Structure):
@@ -119,6 +169,7 @@ _native.register({
     "a2cb_kfac_nu": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_f32, c_f32, c_vp]),
     "a2cb_frames_to_f32": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f32, c_vp]),
     "a2cb_loss_epilogue": (c_i32, [ctypes.POINTER(LossDesc), c_vp]),
+    "a2cb_sample_actions": (c_i32, [ctypes.POINTER(SampleDesc), c_vp]),
     "a2cb_loss_scratch_floats": (c_i64, [c_i32]),
     "a2cb_adv_moments": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "a2cb_adv_normalize": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -146,6 +197,28 @@ class Arena(object):
 
     def bind(self, name, tensor):
         self.bufs[name] = tensor
+
+    def const(self, host_array):
+        """Device copy of a small read-only host table (numpy array), shared by content: programs keep raw device
+        pointers to these tables, so a table must stay alive -- and unmoved -- for as long as ANY program built
+        from it does; rebuilding a program therefore never replaces a table."""
+        consts = self.__dict__.setdefault("_consts", {})
+        key = (host_array.dtype.str, host_array.tobytes())
+        t = consts.get(key)
+        if t is None:
+            t = torch.from_numpy(host_array.copy()).to(self.device)
+            consts[key] = t
+        return t
+
+    def stage(self, name, src):
+        """Copies `src` into an arena-owned buffer of the same size and dtype (one per name) and returns it: the
+        programs that read it are then independent of where the caller's tensor lives."""
+        t = self.bufs.get(name)
+        if t is None or t.numel() != src.numel() or t.dtype != src.dtype:
+            t = torch.empty(src.numel(), dtype=src.dtype, device=self.device)
+            self.bufs[name] = t
+        t.copy_(src.reshape(-1))
+        return t
 
     def ensure(self, name, numel, dtype=torch.float32):
         t = self.bufs.get(name)
@@ -755,6 +828,7 @@ class NetBuilder(object):
 # ---------------------------------------------------------------------------
 class PolicyRuntime(object):
     MAX_CACHE = 96
+    STAGE_BYTES = 64 << 20
 
     def __init__(self, spec, layout, flat, flat_grad):
         self.spec, self.L = spec, layout
@@ -800,6 +874,77 @@ class PolicyRuntime(object):
             return None
         return ("P", self.L.entries["dist.logstd._bias"][0])
 
+    # -- actor step ---------------------------------------------------------
+    def rng_state(self):
+        """Device {seed, offset, ticket} of the sampling stream (a2cb_sample_t.rng).  Seeded from torch's CPU seed
+        WITHOUT consuming the generator (the minibatch permutations of update() must stay the reference's)."""
+        st = getattr(self, "_rng_state", None)
+        if st is None:
+            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & 0x7FFFFFFFFFFFFFFF
+            st = self._rng_state = torch.tensor([seed, 0, 0], dtype=torch.int64, device=self.dev)
+        return st
+
+    def sample(self, z, action, value, logp, deterministic):
+        """Sampling head alone on head outputs z [B, 1 + A] (contiguous)."""
+        d = SampleDesc()
+        d.z, d.logstd = z.data_ptr(), self.arena.ptr(self.logstd_ref())
+        d.value_out, d.action_out, d.logp_out = value.data_ptr(), action.data_ptr(), logp.data_ptr()
+        d.rng = self.rng_state().data_ptr()
+        d.B, d.A, d.z_stride, d.dist = z.shape[0], self.spec.num_actions, z.stride(0), 0 if self.spec.action_kind == "discrete" else 1
+        d.deterministic = int(bool(deterministic))
+        with torch.cuda.device(self.dev):
+            rc = _native.lib().a2cb_sample_actions(ctypes.byref(d), _native.stream_ptr(self.dev))
+        _native.check(rc, "a2cb_sample_actions")
+
+    def act_plan(self, B, obs_dtype):
+        key = ("act", B, obs_dtype)
+        plan = self.cache.get(key)
+        if plan is not None:
+            return plan
+        s, A = self.spec, self.spec.num_actions
+        tag = "a%d_" % B
+        n_obs = B * int(math.prod(s.obs_shape))
+        t = {"obs": torch.zeros(n_obs, dtype=obs_dtype, device=self.dev),
+             "value": torch.zeros(B, device=self.dev), "logp": torch.zeros(B, device=self.dev),
+             "action": (torch.zeros(B, dtype=torch.int64, device=self.dev) if s.action_kind == "discrete"
+                        else torch.zeros(B * A, device=self.dev))}
+        code = self.obs_code(t["obs"])
+        self.arena.bind("obs_in", t["obs"])
+        seq = None
+        if s.recurrent:
+            t["hxs"] = torch.zeros(B * s.hidden, device=self.dev)
+            t["masks"] = torch.ones(B, device=self.dev)
+            self.arena.bind("hxs_in", t["hxs"])
+            self.arena.bind("masks_in", t["masks"])
+            seq = (1, B)
+        nb = NetBuilder(s, self.L, B, "obs_in", code, False, tag, seq=seq, keep_gates=not s.recurrent)
+        plans = nb.forward_plans()
+        if nb.tcx is not None:
+            plans, = _tcx.hoist_preps([plans], tag + "f")
+        self._alloc(nb)
+        if s.recurrent:
+            t["hout"] = self.arena.bufs[tag + "gru_out"]
+            assert t["hout"].numel() == B * s.hidden
+        prog = Program(self.dev)
+        for p in plans:
+            prog.add_plan(p, self.arena)
+        d = SampleDesc()
+        d.z, d.logstd = self.arena.ptr((tag + "z", 0)), self.arena.ptr(self.logstd_ref())
+        d.value_out, d.action_out, d.logp_out = t["value"].data_ptr(), t["action"].data_ptr(), t["logp"].data_ptr()
+        d.rng = self.rng_state().data_ptr()
+        d.B, d.A, d.z_stride, d.dist = B, A, self.zs, 0 if s.action_kind == "discrete" else 1
+        prog.add(OP_SAMPLE, d)
+        prog.finalize()
+        sites = {}
+        for role, ten in t.items():
+            lo = ten.data_ptr()
+            found = []
+            for _, _, desc in prog.entries:
+                _pointer_sites(desc, lo, lo + ten.numel() * ten.element_size(), found)
+            assert found, "actor program: nothing reads / writes the %s placeholder" % role
+            sites[role] = found
+        return self._remember(key, ActPlan(prog, d, t, sites))
+
     # -- forward only -------------------------------------------------------
     def _bind_inputs(self, obs, hxs, masks):
         """Binds the caller's tensors into the arena; returns (B, seq, key part)."""
@@ -809,6 +954,11 @@ class PolicyRuntime(object):
         B = obs.shape[0]
         if tuple(obs.shape[1:]) != self.spec.obs_shape:
             raise ValueError("expected observations of shape [B, %s], got %s" % (self.spec.obs_shape, tuple(obs.shape)))
+        # Actor-side calls pass a different slice of the rollout buffer every step (`rollouts.obs[step]`,
+        # reference main.py:117): inputs up to STAGE_BYTES are copied into arena-owned buffers so that ONE cached
+        # program per batch size serves every step; larger batches are read in place (program keyed by address).
+        if obs.numel() * obs.element_size() <= self.STAGE_BYTES:
+            obs = self.arena.stage("obs_in_%d_%s" % (B, obs.dtype), obs).view(obs.shape)
         self.arena.bind("obs_in", obs.view(-1))
         self.keep["obs"] = obs
         seq, extra = None, ()
@@ -820,6 +970,9 @@ class PolicyRuntime(object):
             mk = masks.detach().to(torch.float32).contiguous().view(-1)
             if not (hx.is_cuda and mk.is_cuda):
                 raise _native.NativeError("recurrent state and masks must be CUDA tensors")
+            if hx.numel() * 4 <= self.STAGE_BYTES:
+                hx = self.arena.stage("hxs_in_%d" % hx.numel(), hx).view(hx.shape)
+                mk = self.arena.stage("masks_in_%d" % mk.numel(), mk)
             self.arena.bind("hxs_in", hx.view(-1))
             self.arena.bind("masks_in", mk)
             self.keep["hxs"], self.keep["masks"] = hx, mk

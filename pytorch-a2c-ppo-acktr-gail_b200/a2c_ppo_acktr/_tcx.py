@@ -139,10 +139,7 @@ class TcxOp(object):
 
 def _itab(arena, name, values):
     import numpy as np
-    import torch
-    t = torch.from_numpy(np.ascontiguousarray(np.asarray(values, dtype=np.int32))).to(arena.device)
-    arena.bind(name, t)
-    return t.data_ptr()
+    return arena.const(np.ascontiguousarray(np.asarray(values, dtype=np.int32))).data_ptr()
 
 
 def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tiles, out, out_lo, o_stride, o_ext, N,
@@ -255,7 +252,7 @@ def hoist_preps(lists, tag):
 
 def merge_preps(ops, tag):
     """Replaces runs of consecutive weight-image ops of a plan list by ONE launch each (a2cb_tcx_prep_multi)."""
-    import torch
+    import numpy as np
     out, run = [], []
 
     def flush():
@@ -277,8 +274,7 @@ def merge_preps(ops, tag):
                     arr[i].ntab, arr[i].ktab = _itab(arena, img + "_ntab", ntab), _itab(arena, img + "_ktab", ktab)
                     arr[i].N, arr[i].K, arr[i].first = N, K, first
                     first += N * K
-                raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(arena.device)
-                arena.bind(name, raw)
+                raw = arena.const(np.frombuffer(bytes(arr), dtype=np.uint8))
                 return PrepMultiDesc(raw.data_ptr(), first, len(jobs_spec), 0)
             out.append(TcxOp(OP_TCX_PREP_MULTI, make, "weight_image"))
         del run[:]

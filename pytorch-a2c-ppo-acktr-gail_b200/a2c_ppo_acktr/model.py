@@ -207,26 +207,109 @@ class Policy(nn.Module):
         raise NotImplementedError
 
     def act(self, inputs, rnn_hxs, masks, deterministic=False):
-        """-> (value [N,1], action [N,1] int64 | [N,A] fp32, action_log_probs [N,1], rnn_hxs)."""
+        """-> (value [N,1], action [N,1] int64 | [N,A] fp32, action_log_probs [N,1], rnn_hxs).
+        One native program: no-grad forward + the sampling head (csrc/actor.cu).  Inputs are copied into the
+        program's own buffers, so one cached program per batch size serves every step of a rollout."""
+        rt = self.runtime()
+        if not inputs.is_cuda:
+            raise _native.NativeError("observations must be CUDA tensors; there is no CPU fallback")
+        B, s = inputs.shape[0], self._spec
+        if tuple(inputs.shape[1:]) != s.obs_shape:
+            raise ValueError("expected observations of shape [B, %s], got %s" % (s.obs_shape, tuple(inputs.shape)))
+        rt.obs_code(inputs)                                   # dtype check
+        if s.recurrent and rnn_hxs.shape[0] != B:
+            return self._act_sequence(inputs, rnn_hxs, masks, deterministic)
+        with torch.no_grad():
+            plan = rt.act_plan(B, inputs.dtype)
+            t = plan.tensors
+            t["obs"].copy_(inputs.reshape(-1))
+            if s.recurrent:
+                t["hxs"].copy_(rnn_hxs.reshape(-1))
+                t["masks"].copy_(masks.reshape(-1))
+            plan.run(deterministic)
+            rt.forward_token += 1
+            hxs = t["hout"].view(B, s.hidden).clone() if s.recurrent else rnn_hxs
+            action = t["action"].view(B, -1).clone()
+            return t["value"].view(B, 1).clone(), action, t["logp"].view(B, 1).clone(), hxs
+
+    def _act_sequence(self, inputs, rnn_hxs, masks, deterministic):
+        """act() on a [T*N] batch of a recurrent policy (not used by the reference's actor loop): generic forward,
+        then the sampling head on its outputs."""
         rt = self.runtime()
         with torch.no_grad():
             out = rt.forward(inputs, rnn_hxs, masks)
             z = out["z"]
-            if self._spec.action_kind == "discrete":
-                logits = z[:, 1:]
-                if deterministic:
-                    action = logits.argmax(dim=-1, keepdim=True)
-                else:
-                    action = torch.multinomial(torch.softmax(logits, dim=-1), 1, True)
-            else:
-                mean = z[:, 1:]
-                if deterministic:
-                    action = mean.clone()
-                else:
-                    std = self.dist.logstd._bias.detach().t().exp().expand_as(mean)
-                    action = torch.normal(mean, std)
-            stats = rt.head_stats(z.shape[0], action)
-        return z[:, 0:1].clone(), action, stats["logp"].view(-1, 1).clone(), out["hxs"]
+            B = z.shape[0]
+            action = torch.zeros(B, 1, dtype=torch.int64, device=z.device) if self._spec.action_kind == "discrete" \
+                else torch.zeros(B, self._spec.num_actions, device=z.device)
+            value, logp = torch.zeros(B, 1, device=z.device), torch.zeros(B, 1, device=z.device)
+            rt.sample(z, action, value, logp, deterministic)
+        return value, action, logp, out["hxs"]
+
+    def act_into(self, rollouts, step=None, deterministic=False):
+        """Fused actor step (extension; reference main.py:115-134 = act + the policy half of insert): reads
+        `rollouts.obs[step]`, `.recurrent_hidden_states[step]`, `.masks[step]` IN PLACE and writes
+        `.value_preds[step]`, `.actions[step]`, `.action_log_probs[step]` and `.recurrent_hidden_states[step + 1]`
+        directly -- one native program, no staging copies, no temporaries.  Returns views of those slots in the
+        order of act(); passing them on to `rollouts.insert(...)` is harmless (copies onto themselves)."""
+        rt = self.runtime()
+        s = self._spec
+        step = rollouts.step if step is None else step
+        wait = getattr(rollouts, "wait_staged", None)
+        if wait is not None:
+            wait()
+        obs, hxs, masks = rollouts.obs[step], rollouts.recurrent_hidden_states[step], rollouts.masks[step]
+        value, action = rollouts.value_preds[step], rollouts.actions[step]
+        logp, hout = rollouts.action_log_probs[step], rollouts.recurrent_hidden_states[step + 1]
+        B = obs.shape[0]
+        want_act = torch.int64 if s.action_kind == "discrete" else torch.float32
+        ok = (obs.is_cuda and tuple(obs.shape[1:]) == s.obs_shape and action.dtype == want_act
+              and all(x.is_contiguous() for x in (obs, hxs, masks, value, action, logp, hout))
+              and obs.data_ptr() % 16 == 0 and (not s.recurrent or (hxs.data_ptr() % 16 == 0 and hout.data_ptr() % 16 == 0))
+              and obs.numel() * obs.element_size() <= rt.STAGE_BYTES)
+        if not ok:                                            # odd layouts: the copying path
+            v, a, lp, h = self.act(obs, hxs, masks, deterministic)
+            value.copy_(v); action.copy_(a); logp.copy_(lp); hout.copy_(h)
+            return value, action, logp, hout
+        rt.obs_code(obs)
+        with torch.no_grad():
+            plan = rt.act_plan(B, obs.dtype)
+            ptrs = {"obs": obs.data_ptr(), "value": value.data_ptr(), "action": action.data_ptr(), "logp": logp.data_ptr()}
+            if s.recurrent:
+                ptrs.update(hxs=hxs.data_ptr(), masks=masks.data_ptr(), hout=hout.data_ptr())
+            def launch():
+                plan.run(deterministic, ptrs)
+                if not s.recurrent:
+                    hout.copy_(hxs)
+            self._act_graphed(plan, (bool(deterministic),) + tuple(sorted(ptrs.items())), launch)
+            rt.forward_token += 1
+        return value, action, logp, hout
+
+    use_cuda_graph = True      # act_into: one CUDA graph per (rollout slot, mode), captured on its second use
+
+    def _act_graphed(self, plan, key, launch):
+        """A slot's actor step is the same launch sequence with the same pointers every iteration (the sampling
+        stream advances on the device), so from its second use on it is replayed as a CUDA graph: the host cost
+        of a step drops from ~10 launches + their TMA descriptor encodes to one replay."""
+        graphs = plan.__dict__.setdefault("graphs", {})
+        g = graphs.get(key)
+        if not self.use_cuda_graph or (g is None and len(graphs) >= 4096):
+            return launch()
+        if g is None:
+            graphs[key] = "seen"
+            return launch()
+        if g == "seen":
+            dev = self._flat.device
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(dev)
+            n0 = _native.launch_count()
+            with torch.cuda.graph(graph):
+                launch()
+            n = _native.launch_count() - n0
+            _native.lib().a2cb_add_launches(-n)               # capture recorded, did not run, them
+            g = graphs[key] = (graph, n)
+        g[0].replay()
+        _native.lib().a2cb_add_launches(g[1])
 
     def get_value(self, inputs, rnn_hxs, masks):
         with torch.no_grad():

@@ -140,6 +140,11 @@ int a2cb_frames_to_f32(float* dst, const void* src, int64_t n, int32_t src_is_u8
     return frames_to_f32(dst, src, (long)n, src_is_u8, div, (cudaStream_t)stream);
 }
 
+int a2cb_sample_actions(const a2cb_sample_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc, "sample_actions: null descriptor");
+    return sample_actions(desc, (cudaStream_t)stream);
+}
+
 int a2cb_upload_env_columns(void* dst, const void* src_host, int64_t col_bytes, int64_t rows, int64_t pitch_bytes,
                             const int64_t* envs, int32_t n_envs, a2cb_stream_t stream) {
     A2CB_REQUIRE(dst && src_host && envs && col_bytes > 0 && rows > 0 && n_envs > 0 && pitch_bytes >= col_bytes &&
@@ -334,6 +339,9 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
                 rc = tcx_colsum(q.part, q.x, q.lo, (long)q.rows, q.C, (long)q.pitch, st);
                 break;
             }
+            case A2CB_OP_SAMPLE:
+                rc = sample_actions(op.desc, st);
+                break;
             case A2CB_OP_MLP_FWD:
             case A2CB_OP_MLP_BWD: {
                 MlpDesc q = *reinterpret_cast<const MlpDesc*>(op.desc);

@@ -81,6 +81,9 @@ int tcx_narrow_fwd(float* z, const float* x, const float* W, const float* bias, 
 int tcx_narrow_dgrad(float* gx, float* gx_lo, const float* dz, const float* W, const float* mask, long rows, int K, int N,
                      int dz_stride, cudaStream_t st);
 
+// actor.cu
+int sample_actions(const void* desc, cudaStream_t st);   // desc: a2cb_sample_t
+
 // mlp_fused.cu
 struct MlpDesc;
 bool mlp_fused_supported(int d_in, int H, int zs);

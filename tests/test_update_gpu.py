@@ -465,7 +465,7 @@ def test_upload_env_columns_and_wait_staged():
         st.stage_host({"obs": host.clone()})                # not pinned
 
 
-@pytest.mark.parametrize("name,world", [("C2", 2), ("C2", 4), ("C2g", 2)])
+@pytest.mark.parametrize("name,world", [("C2", 2), ("C2", 4), ("C2g", 3)])
 def test_sharded_a2c_equals_single_device(name, world, gemm_engine):
     """A2C on `world` emulated ranks (environment shards, gradient + loss sums exchanged) vs the reference golden
     of the single-device update; C2g is the recurrent variant (whole environments per rank)."""
@@ -499,3 +499,41 @@ def test_sharded_a2c_equals_single_device(name, world, gemm_engine):
         for k, p in r["pol"].named_parameters():
             assert torch.equal(p, p0[k]), k
     assert helpers.rel_l2(case, "finaldense_", p0) <= 1e-4
+
+
+@pytest.mark.parametrize("recurrent", [False, True])
+def test_act_over_rollout_slices_reuses_one_program(recurrent, gemm_engine):
+    """The actor loop passes a different slice of the rollout buffer every step (reference main.py:115-134).  Every
+    step must be served by the same cached program (inputs are staged), and calling the loop again must give the
+    same result (regression: rebuilt programs used to free the device tables older programs still pointed at)."""
+    torch.manual_seed(1)
+    pol = Policy((4, 84, 84), Discrete(6), base_kwargs={"recurrent": recurrent}).to(DEV)
+    T, N, H = 6, 8, pol.recurrent_hidden_state_size
+    st = RolloutStorage(T, N, (4, 84, 84), Discrete(6), H, obs_dtype=torch.uint8)
+    st.to(DEV)
+    st.obs.random_(0, 256)
+    st.masks[2, 3] = 0.0
+    rt = pol.runtime()
+
+    def loop():
+        out = []
+        hx = st.recurrent_hidden_states[0].clone()
+        for t in range(T):
+            v, a, lp, hx = pol.act(st.obs[t], hx, st.masks[t], deterministic=True)
+            out.append((v.clone(), a.clone(), lp.clone(), hx.clone()))
+        return out
+    first = loop()
+    n_prog = len(rt.cache)
+    second = loop()
+    assert len(rt.cache) == n_prog == 1
+    for a, b in zip(first, second):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    # in-place reference: the same rows evaluated as one batch through evaluate_actions (no staging for the values)
+    if not recurrent:
+        with torch.no_grad():
+            v_all, lp_all, _, _ = pol.evaluate_actions(st.obs[:T].reshape(T * N, 4, 84, 84),
+                                                       st.recurrent_hidden_states[:T].reshape(T * N, 1),
+                                                       st.masks[:T].reshape(T * N, 1), torch.cat([o[1] for o in first]))
+        np.testing.assert_allclose(v_all.cpu().numpy(), torch.cat([o[0] for o in first]).cpu().numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(lp_all.cpu().numpy(), torch.cat([o[2] for o in first]).cpu().numpy(), rtol=1e-4, atol=1e-6)
