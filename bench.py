@@ -145,6 +145,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = workload_config(args.workload)
