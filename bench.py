@@ -304,13 +304,13 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the C5 shard
-# (profiles/r01d_tcx_gru_full_c5.txt); only meaningful for that workload
-NCU_DRAM_SOURCE = "profiles/r01d_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
+# (profiles/r01e_tcx_gru_full_c5.txt); only meaningful for that workload
+NCU_DRAM_SOURCE = "profiles/r01e_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
 NCU_DRAM_BYTES = {
-    "conv1.fwd": 0.463439e9 + 786.812e6, "conv2.fwd": 0.840850e9 + 314.908e6, "conv3.fwd": 0.340078e9 + 82.521e6,
-    "conv2.dgrad": 0.759568e9 + 793.399e6, "conv3.dgrad": 0.272844e9 + 292.938e6,
-    "conv1.wgrad": 1.764639e9 + 4.516e6, "conv2.wgrad": 1.182880e9 + 7.834e6, "conv3.wgrad": 0.442569e9 + 5.279e6,
-    "gru.seq_fwd": 0.053849e9 + 46.974e6, "gru.seq_bwd": 0.104056e9 + 60.236e6,
+    "conv1.fwd": 0.463094e9 + 786.847e6, "conv2.fwd": 0.841122e9 + 318.661e6, "conv3.fwd": 0.340054e9 + 84.430e6,
+    "conv2.dgrad": 0.759601e9 + 794.670e6, "conv3.dgrad": 0.272846e9 + 291.947e6,
+    "conv1.wgrad": 1.764720e9 + 3.852e6, "conv2.wgrad": 1.183497e9 + 8.131e6, "conv3.wgrad": 0.442570e9 + 3.583e6,
+    "gru.seq_fwd": 0.053890e9 + 48.604e6, "gru.seq_bwd": 0.104025e9 + 60.963e6,
 }
 
 
