@@ -345,6 +345,8 @@ typedef struct {
     int32_t n_valid;          /* rows [n_valid, B) are padding of a sharded minibatch; < 0: all valid */
     int32_t valid_mod;        /* > 0: row b is valid iff (b % valid_mod) < n_valid (recurrent, padded per env) */
     int32_t pad2_;
+    float* dlogstd_rows;      /* optional [B, A]: per-row gradient w.r.t. the broadcast log-std (DiagGaussian) --
+                                 the output gradient of the reference's logstd AddBias module, for its KFAC g-factor */
 } a2cb_loss_t;
 
 int a2cb_loss_epilogue(const a2cb_loss_t* desc, a2cb_stream_t stream);

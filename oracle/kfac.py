@@ -42,6 +42,32 @@ def cnn_forward_capture(p, obs):
     return value, logits, ins, outs
 
 
+def mlp_forward_capture(p, obs):
+    """MLPBase (model.py:198-229) + DiagGaussian head (distributions.py:76-95) with every layer input and every
+    bias-free layer output kept.  -> (value, mean, logstd [B, A], inputs dict, outputs dict).  The logstd AddBias
+    module (distributions.py:89-94) sees a zeros input and its own output's gradient: aa = [[1]], gg = B s^T s."""
+    ins, outs = OrderedDict(), OrderedDict()
+    x = obs.to(torch.float32)
+
+    def lin(name, key, inp, act):
+        ins[name] = inp
+        y = F.linear(inp, p[key + ".weight"])
+        outs[name] = y
+        y = y + p[key + ".bias"]
+        return torch.tanh(y) if act else y
+    hc = lin("critic2", "base.critic.2", lin("critic0", "base.critic.0", x, True), True)
+    ha = lin("actor2", "base.actor.2", lin("actor0", "base.actor.0", x, True), True)
+    value = lin("critic", "base.critic_linear", hc, False)
+    mean = lin("dist", "dist.fc_mean", ha, False)
+    zeros = torch.zeros_like(mean)
+    outs["logstd"] = zeros                                   # input of the AddBias module; its output gets the hook
+    logstd = zeros + p["dist.logstd._bias"].t().view(1, -1)
+    return value, mean, logstd, ins, outs
+
+
+MLP_LAYERS = (("actor0", "base.actor.0"), ("actor2", "base.actor.2"), ("critic0", "base.critic.0"),
+              ("critic2", "base.critic.2"), ("critic", "base.critic_linear"), ("dist", "dist.fc_mean"))
+
 LAYERS = (("conv1", "base.main.0", (8, 4)), ("conv2", "base.main.2", (4, 2)), ("conv3", "base.main.4", (3, 1)),
           ("fc", "base.main.7", None), ("critic", "base.critic_linear", None), ("dist", "dist.linear", None))
 
@@ -86,6 +112,8 @@ def running(m, key, new, decay, first):
 
 def acktr_update(p, ro, hp, st):
     """p: dict of leaf tensors (requires_grad), updated in place.  st: KFACState."""
+    if "dist.logstd._bias" in p:
+        return acktr_update_mlp(p, ro, hp, st)
     T, N = ro["rewards"].shape[:2]
     B = T * N
     obs = ro["obs"][:-1].reshape(B, *ro["obs"].shape[2:])
@@ -110,6 +138,50 @@ def acktr_update(p, ro, hp, st):
     total = vl * hp["value_loss_coef"] + al - ent * hp["entropy_coef"]
     keys = list(p.keys())
     grads = dict(zip(keys, torch.autograd.grad(total, [p[k] for k in keys])))
+    return _kfac_step(p, grads, st, (vl, al, ent))
+
+
+def acktr_update_mlp(p, ro, hp, st):
+    """The same update for MLPBase + DiagGaussian (13 KFAC modules: 6 Linear weights, 6 biases, the logstd AddBias)."""
+    from . import policy as o_pol
+    T, N = ro["rewards"].shape[:2]
+    B = T * N
+    obs = ro["obs"][:-1].reshape(B, -1)
+    value, mean, logstd, ins, outs = mlp_forward_capture(p, obs)
+    actions = ro["actions"].reshape(B, -1)
+    logp, ent = o_pol.gaussian_stats(mean, p["dist.logstd._bias"], actions)
+    ent = ent.mean()
+    values = value.view(T, N, 1)
+    vl, al = losses.a2c_losses(values, logp.view(T, N, 1), ro["returns"][:-1])
+    first = st.steps == 0
+    if st.steps % st.Ts == 0:
+        for name, key in MLP_LAYERS:
+            running(st.m_aa, key + ".weight", cov_a(ins[name].detach(), None), st.stat_decay, first)
+            running(st.m_aa, key + ".bias", torch.ones(1, 1), st.stat_decay, first)
+        running(st.m_aa, "dist.logstd._bias", torch.ones(1, 1), st.stat_decay, first)
+        noise = torch.randn(values.size())
+        fisher = losses.fisher_sample_loss(values, logp.view(T, N, 1), noise)
+        # the AddBias output is (zeros + bias): a per-row gradient w.r.t. the broadcast log-std, taken through a
+        # per-row copy of the bias
+        ls_rows = p["dist.logstd._bias"].t().view(1, -1).expand(B, -1).clone().requires_grad_(True)
+        std = ls_rows.exp()
+        lp_rows = (-((actions - mean) ** 2) / (2 * std * std) - ls_rows - math.log(math.sqrt(2 * math.pi))).sum(-1, keepdim=True)
+        fisher_rows = losses.fisher_sample_loss(values, lp_rows.view(T, N, 1), noise)
+        gouts = torch.autograd.grad(fisher, [outs[n] for n, _ in MLP_LAYERS], retain_graph=True)
+        g_ls, = torch.autograd.grad(fisher_rows, [ls_rows], retain_graph=True)
+        for (name, key), g in zip(MLP_LAYERS, gouts):
+            running(st.m_gg, key + ".weight", cov_g(g, None, False), st.stat_decay, first)
+            running(st.m_gg, key + ".bias", cov_g(g, None, False), st.stat_decay, first)
+        running(st.m_gg, "dist.logstd._bias", cov_g(g_ls, None, False), st.stat_decay, first)
+    total = vl * hp["value_loss_coef"] + al - ent * hp["entropy_coef"]
+    keys = list(p.keys())
+    grads = dict(zip(keys, torch.autograd.grad(total, [p[k] for k in keys])))
+    return _kfac_step(p, grads, st, (vl, al, ent))
+
+
+def _kfac_step(p, grads, st, loss_terms):
+    vl, al, ent = loss_terms
+    keys = list(p.keys())
     # ---- KFACOptimizer.step (kfac.py:190-242) ----
     updates = {}
     for k in keys:

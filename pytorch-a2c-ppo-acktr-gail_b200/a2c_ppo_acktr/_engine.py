@@ -36,6 +36,7 @@ class LossDesc(ctypes.Structure):
         ("B", c_i32), ("A", c_i32), ("z_stride", c_i32), ("dz_stride", c_i32), ("act_stride", c_i32),
         ("dlogstd_stride", c_i32), ("dist", c_i32), ("mode", c_i32), ("use_clipped_value_loss", c_i32),
         ("clip", c_f32), ("c_v", c_f32), ("c_e", c_f32), ("inv_B", c_f32), ("n_valid", c_i32), ("valid_mod", c_i32), ("pad2_", c_i32),
+        ("dlogstd_rows", c_vp),
     ]
 
 
@@ -448,7 +449,7 @@ class NetBuilder(object):
     """Builds forward / backward plan lists for one policy spec and one batch size."""
 
     def __init__(self, spec, layout, B, obs_buf, obs_code, gather, tag, seq=None, masks=("masks_in", 0),
-                 hxs=("hxs_in", 0), keep_gates=True, allow_tcx=True, full_rows=0):
+                 hxs=("hxs_in", 0), keep_gates=True, allow_tcx=True, full_rows=0, allow_mlp_fused=True):
         self.spec, self.L, self.B = spec, layout, B
         # recurrent policies see the batch as a [T, N] sequence, rows time-major (model.py:119-126)
         self.seqT, self.seqN = seq if seq is not None else (1, B)
@@ -473,7 +474,8 @@ class NetBuilder(object):
         # CNN trunk (+ the GRU's input product) on the TMA-fed tensor-core engine (csrc/tcx.cu) unless the exact
         # fp32 SIMT engine was requested; other geometries stay on the affine-indexed engine
         # MLPBase without GRU: both trunks + heads fused into one launch per direction (csrc/mlp_fused.cu)
-        self.mlp_fused = (not spec.cnn and not spec.recurrent and os.environ.get("A2CB_MLP_FUSED", "1") != "0"
+        # (KFAC needs every layer's input and output gradient in memory: it asks for the layer-by-layer plans)
+        self.mlp_fused = (allow_mlp_fused and not spec.cnn and not spec.recurrent and os.environ.get("A2CB_MLP_FUSED", "1") != "0"
                           and bool(_native.lib().a2cb_mlp_fused_supported(int(spec.obs_shape[0]), int(H), 1 + A)))
         self.tcx = None
         if (allow_tcx and spec.cnn and spec.obs_shape[0] == 4 and H % 256 == 0 and obs_code in (1, 2)
@@ -1165,13 +1167,14 @@ class PolicyRuntime(object):
         T, N = storage.rewards.shape[0], storage.rewards.shape[1]
         B = T * N
         tag = "t%d_" % B
-        nb = NetBuilder(s, self.L, B, "obs_f32", 0, False, tag)
+        nb = NetBuilder(s, self.L, B, "obs_f32", 0, False, tag, allow_mlp_fused=False)
         fwd = nb.forward_plans()
         bwd = nb.backward_plans()
         self._alloc(nb)
         acts = storage.actions.view(B, -1)
         lo = self.arena.ensure(tag + "loss_out", 4)
         lo_f = self.arena.ensure(tag + "loss_out_fisher", 4)
+        ls_rows = self.arena.ensure("kfac_dlogstd_rows", B * s.num_actions) if s.action_kind == "box" else None
 
         def loss(mode, out):
             d = self._loss_desc(B, tag, mode, acts, returns=storage.returns.data_ptr(),
@@ -1180,6 +1183,11 @@ class PolicyRuntime(object):
                                 noise=noise.data_ptr())
             if inv_B is not None:
                 d.inv_B = float(inv_B)          # sharded: loss terms are local sums over the GLOBAL batch size
+            if s.action_kind == "box":
+                d.dlogstd = self.arena.ptr(("G", self.L.entries["dist.logstd._bias"][0]))
+                if mode == 2:                   # Fisher pass: per-row gradient of the logstd AddBias (its g-factor)
+                    d.dlogstd_rows = ls_rows.data_ptr()
+                    d.dlogstd = None
             return d
         progs = {}
         progs["fwd"] = Program(self.dev)

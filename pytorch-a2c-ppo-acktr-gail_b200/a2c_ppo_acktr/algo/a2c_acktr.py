@@ -120,7 +120,8 @@ class A2C_ACKTR():
         obs_flat = rollouts.obs[:-1].view(B, -1)
         obs_f32 = rt.arena.ensure("obs_f32", obs_flat.numel())
         _native.check(lib.a2cb_frames_to_f32(obs_f32.data_ptr(), _native.dptr(obs_flat, name="obs"), obs_flat.numel(),
-                                             int(obs_flat.dtype == torch.uint8), 255.0, st), "a2cb_frames_to_f32")
+                                             int(obs_flat.dtype == torch.uint8), 255.0 if rt.spec.cnn else 1.0, st),
+                      "a2cb_frames_to_f32")
         # value noise of the Fisher sample: drawn on the CPU from the global generator, as the
         # reference does (a2c_acktr.py:58-60), then uploaded
         noise = rt.arena.ensure("kfac_noise", B)

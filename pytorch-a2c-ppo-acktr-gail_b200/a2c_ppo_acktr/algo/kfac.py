@@ -1,8 +1,8 @@
 """KFAC optimiser of ACKTR on the sm_100a engine.
 
 Native counterpart of `a2c_ppo_acktr.algo.kfac.KFACOptimizer` (reference algo/kfac.py:87-242) for
-the CNN policy (the reference's ACKTR recipe, README "ACKTR"; recurrent policies are excluded by the
-reference itself, arguments.py:156-159).  Same hyper-parameters and the same arithmetic:
+the CNN policy (the reference's ACKTR recipe, README "ACKTR") and the MLP / DiagGaussian policy
+(recurrent policies are excluded by the reference itself, arguments.py:156-159).  Same hyper-parameters and the same arithmetic:
 
   * a-factors  aa = cov(inputs)   (compute_cov_a, kfac.py:29-46): for a conv layer the patch
     covariance  sum_rows p p^T / (B (oh ow)^2), for a Linear layer x^T x / B, for a bias [[1]];
@@ -39,8 +39,6 @@ class KFACOptimizer(object):
                  weight_decay=0, fast_cnn=False, Ts=1, Tf=10):
         if model.is_recurrent:
             raise _native.NativeError("ACKTR does not support recurrent policies (reference arguments.py:156-159)")
-        if not model._spec.cnn:
-            raise _native.NativeError("native KFAC currently covers the CNN policy (the reference's ACKTR recipe)")
         if fast_cnn or weight_decay:
             raise _native.NativeError("fast_cnn / weight_decay are not supported (reference defaults are off)")
         self.model = model
@@ -79,10 +77,9 @@ class KFACOptimizer(object):
             return
         A, H = spec.num_actions, spec.hidden
         tag = "t%d_" % B
-        nb = _engine.NetBuilder(spec, L, B, "obs_f32", 0, False, tag)
+        nb = _engine.NetBuilder(spec, L, B, "obs_f32", 0, False, tag, allow_mlp_fused=False)
         nb.forward_plans()
         nb.backward_plans()
-        c1, c2, c3 = nb.c1, nb.c2, nb.c3
         arena = rt.arena
         zs = 1 + A
 
@@ -107,7 +104,11 @@ class KFACOptimizer(object):
             p.base_scale = scale
             return p
 
-        layers = [("conv1", c1, ("obs_f32", 0), ("base.main.0.weight", "base.main.0.bias")),
+        if not spec.cnn:
+            self._mlp_modules(spec, tag, B, Bg, factor_plan, a_plans, g_plans)
+        c1, c2, c3 = (nb.c1, nb.c2, nb.c3) if spec.cnn else (None, None, None)
+        layers = [] if not spec.cnn else [
+                  ("conv1", c1, ("obs_f32", 0), ("base.main.0.weight", "base.main.0.bias")),
                   ("conv2", c2, (tag + "a1", 0), ("base.main.2.weight", "base.main.2.bias")),
                   ("conv3", c3, (tag + "a2", 0), ("base.main.4.weight", "base.main.4.bias"))]
         gbufs = {"conv1": (tag + "g1", 0), "conv2": (tag + "g2", 0), "conv3": (tag + "g3", 0)}
@@ -131,6 +132,46 @@ class KFACOptimizer(object):
                                        float(Bg), 2, 1))
             self.modules.append(_Module(wk, cv.cout, cv.K, "aa_" + name, "gg_" + name))
             self.modules.append(_Module(bk, cv.cout, 1, "one", "ggb_" + name))
+        if spec.cnn:
+            self._cnn_dense_modules(spec, tag, B, Bg, factor_plan, a_plans, g_plans)
+
+        self._a_plans, self._g_plans = a_plans, g_plans
+        self._finish_build(rt, key, a_plans, g_plans, buf)
+
+    def _mlp_modules(self, spec, tag, B, Bg, factor_plan, a_plans, g_plans):
+        """MLPBase + DiagGaussian (reference model.py:198-229, distributions.py:76-95): six Linear layers, their
+        biases, and the logstd AddBias -- 13 modules.  Inputs and output gradients are the
+        layer-by-layer engine's buffers; the two first layers share their input statistics."""
+        A, H, d = spec.num_actions, spec.hidden, spec.obs_shape[0]
+        zs = 1 + A
+        pl = P.plain
+
+        def aa(name, src, n):
+            v = (2, 1) if n % 4 == 0 else (0, 0)
+            a_plans.append(factor_plan(name, n, src, src, pl(1), pl(n), pl(n), pl(1), pl(n), pl(1), B, 1.0 / Bg, *v))
+
+        def gg(name, src, n, stride):
+            v = (2, 1) if (n % 4 == 0 and stride == n) else (0, 0)
+            g_plans.append(factor_plan(name, n, src, src, pl(1), pl(stride), pl(stride), pl(1), pl(n), pl(1), B, float(Bg), *v))
+        aa("aa_x", ("obs_f32", 0), d)
+        for nm in ("ha1", "hc1", "ha2", "hc2"):
+            aa("aa_" + nm, (tag + nm, 0), H)
+        for nm in ("ga1", "ga2", "gc1", "gc2"):
+            gg("gg_" + nm, (tag + nm, 0), H, H)
+        gg("gg_critic", (tag + "dz", 0), 1, zs)
+        gg("gg_dist", (tag + "dz", 1), A, zs)
+        gg("gg_logstd", ("kfac_dlogstd_rows", 0), A, A)
+        for key, r, c, fa, fg in (("base.actor.0", H, d, "aa_x", "gg_ga1"), ("base.actor.2", H, H, "aa_ha1", "gg_ga2"),
+                                  ("base.critic.0", H, d, "aa_x", "gg_gc1"), ("base.critic.2", H, H, "aa_hc1", "gg_gc2"),
+                                  ("base.critic_linear", 1, H, "aa_hc2", "gg_critic"),
+                                  ("dist.fc_mean", A, H, "aa_ha2", "gg_dist")):
+            self.modules.append(_Module(key + ".weight", r, c, fa, fg))
+            self.modules.append(_Module(key + ".bias", r, 1, "one", fg))
+        self.modules.append(_Module("dist.logstd._bias", A, 1, "one", "gg_logstd"))
+
+    def _cnn_dense_modules(self, spec, tag, B, Bg, factor_plan, a_plans, g_plans):
+        A, H = spec.num_actions, spec.hidden
+        zs = 1 + A
         # fc: input a3 (NCHW-flatten order == the reference's), output gradient gh
         a_plans.append(factor_plan("aa_fc", 1568, (tag + "a3", 0), (tag + "a3", 0), P.plain(1), P.plain(1568),
                                    P.plain(1568), P.plain(1), P.plain(1568), P.plain(1), B, 1.0 / Bg, 2, 1))
@@ -151,7 +192,8 @@ class KFACOptimizer(object):
         self.modules.append(_Module(hw + ".weight", A, H, "aa_heads", "gg_dist"))
         self.modules.append(_Module(hw + ".bias", A, 1, "one", "gg_dist"))
 
-        self._a_plans, self._g_plans = a_plans, g_plans
+    def _finish_build(self, rt, key, a_plans, g_plans, buf):
+        L, dev, arena = rt.L, rt.dev, rt.arena
         self._a_prog, self._g_prog = _engine.Program(dev), _engine.Program(dev)
         for p in a_plans:
             self._a_prog.add_plan(p, arena)

@@ -42,6 +42,8 @@ loss_kernel(const LossDesc d) {
         // padding row of a sharded minibatch: contributes nothing
         float* dz = d.dz + (long)b * d.dz_stride;
         for (int j = 0; j <= A; ++j) dz[j] = 0.f;
+        if (d.dlogstd_rows)
+            for (int a = 0; a < A; ++a) d.dlogstd_rows[(long)b * A + a] = 0.f;
     }
     if (b < d.B && row_valid) {
         const long src = d.idx ? (long)d.idx[b] : (long)b;
@@ -151,6 +153,7 @@ loss_kernel(const LossDesc d) {
                     const float diff = x[a] - z[1 + a];
                     dz[1 + a] = g_logp * diff / var;
                     dls[a] = g_logp * (diff * diff / var - 1.f) - ce;   // entropy: -c_e per action dim per row mean
+                    if (d.dlogstd_rows) d.dlogstd_rows[(long)b * A + a] = dls[a];
                 }
             }
         }

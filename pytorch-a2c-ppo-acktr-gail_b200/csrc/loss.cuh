@@ -34,6 +34,7 @@ struct LossDesc {
     int32_t n_valid;           // rows [n_valid, B) are padding (dz = 0, no loss); < 0: all B rows valid
     int32_t valid_mod;         // > 0: row b is valid iff (b % valid_mod) < n_valid (time-major recurrent batches)
     int32_t pad2_;
+    float* dlogstd_rows;       // optional [B, A] per-row gradient w.r.t. the broadcast log-std (KFAC g-factor of the AddBias)
 };
 
 }  // namespace a2cb

@@ -215,6 +215,8 @@ UPDATE_CASES = {
     "C3": ("C3", dict()),
     "C4s": ("C4", dict(T=4, N=4)),
     "C4": ("C4", dict()),
+    # ACKTR on the MLP policy (MLPBase + DiagGaussian; 13 KFAC modules incl. the logstd AddBias)
+    "C4m": ("C1", dict(algo="acktr", T=32, N=4, entropy_coef=0.01, use_gae=False, use_proper_time_limits=False)),
 }
 
 

@@ -173,7 +173,7 @@ def test_update_matches_reference(name):
                                      atol=1e-6, what="param " + k, elem_frac=0.1 if full else 0.0)
 
 
-@pytest.mark.parametrize("name", ["C4s", "C4"])
+@pytest.mark.parametrize("name", ["C4s", "C4", "C4m"])
 def test_acktr_oracle_matches_reference(name):
     """oracle/kfac.py (functional KFAC) against the reference's hook-based KFACOptimizer."""
     from oracle import kfac
