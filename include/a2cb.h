@@ -213,7 +213,8 @@ typedef struct {
     float* colsum_part;   /* optional [CTAs][N] partial column sums of the stored values (bias gradients); N <= 128 */
     const float* B3;      /* bf16 mode: third plane of the weight image */
     int32_t bf16;         /* 1: A.x and B / B_lo / B3 hold bf16 (exact operands, e.g. uint8 frames); 64-channel k-blocks */
-    int32_t pad2_;
+    int32_t patch;        /* bf16 mode, stride-1 taps: > 0 = A.box is the tile's input PATCH (pixels + tap halo), loaded once
+                             per tile; kb_a[kb][1..2] = tap shift inside it; value = accumulator rows to store */
 } a2cb_tcx_fwd_t;
 typedef struct {
     a2cb_tcx_view_t A;

@@ -2,6 +2,7 @@
 `a2cb_tcx_*_t` (include/a2cb.h) and small builders for the views / tilings the CNN layers use.
 Pure integer bookkeeping -- no tensor math happens here."""
 import ctypes
+import os
 
 from . import _native
 from . import _plans as P
@@ -27,7 +28,7 @@ class FwdDesc(ctypes.Structure):
                 ("out", c_vp), ("out_lo", c_vp), ("mask", c_vp), ("bias", c_vp), ("o_stride", c_i64 * 5),
                 ("o_base", c_i64), ("o_ext", c_i32 * 5), ("N", c_i32), ("alpha", c_f32), ("act", c_i32),
                 ("o_cb", c_i32), ("gather_dim", c_i32), ("o_cb_off", c_i64 * 4), ("gather_idx", c_vp), ("colsum_part", c_vp),
-                ("B3", c_vp), ("bf16", c_i32), ("pad2_", c_i32)]
+                ("B3", c_vp), ("bf16", c_i32), ("patch", c_i32)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -144,9 +145,12 @@ def _itab(arena, name, values):
 
 def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tiles, out, out_lo, o_stride, o_ext, N,
            alpha=1.0, bias=None, act=0, mask=None, chain=4, o_base=0, flops=0.0, col_blocks=None, gather_dim=0,
-           colsum_part=None, bf16=False, emu_A=None):
+           colsum_part=None, bf16=False, emu_A=None, patch=None):
     """bf16: A and the three-plane weight image (img, img_lo, img_3) are bf16, k-blocks are 64 channels wide
-    (emu_A: fp32 tensor with the same values, read by the numpy emulator instead)."""
+    (emu_A: fp32 tensor with the same values, read by the numpy emulator instead).
+    patch = (rows, tile box): `box` is the input patch of a tile (tile pixels + tap halo) that is loaded once; the
+    k-block offsets are tap shifts inside it; `rows` accumulator rows (patch pixels) are stored, `tile box` is the
+    tile's own pixel box over the same row pitch (what the emulator enumerates)."""
     assert len(kbs) <= MAX_KB, (name, len(kbs))      # col_blocks: (block width, [offset per block]) -- a2cb_tcx_fwd_t.o_cb
 
     def make(arena):
@@ -175,10 +179,13 @@ def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tile
         d.gather_dim = gather_dim
         d.gather_idx = 1 if gather_dim else None          # placeholder: a2cb_run_ops substitutes the runtime row list
         d.colsum_part = arena.ptr(colsum_part)
+        if patch is not None:
+            assert bf16 and patch[1][1] == box[1] and patch[0] == patch[1][1] * patch[1][2] * patch[1][3]
+            d.patch = patch[0]
         return d
     op = TcxOp(OP_TCX_FWD, make, name, flops=flops, runtime_idx=bool(gather_dim))
     op.spec = dict(A=emu_A if emu_A is not None else A, cw=64 if bf16 else 32,
-                   dims=dims, strides=strides, box=box, img=img, img_rows=img_rows, img_cols=img_cols, kbs=kbs,
+                   dims=dims, strides=strides, box=patch[1] if patch is not None else box, img=img, img_rows=img_rows, img_cols=img_cols, kbs=kbs,
                    tiles=tiles, out=out, o_stride=o_stride, o_ext=o_ext, N=N, alpha=alpha, bias=bias, act=act, mask=mask,
                    o_base=o_base, col_blocks=col_blocks, gather_dim=gather_dim, colsum_part=colsum_part)
     return op
@@ -460,10 +467,15 @@ class CnnNet(object):
         # ---- conv1: 2 x 2 taps x 64 channels, tile = 12 output rows of one image ----
         if self.c1_bf16:
             kbs = [((0, bx, by, 0), (by * 2 + bx) * 64) for by in range(2) for bx in range(2)]
-            ops.append(fwd_op("conv1.fwd", x0b, None, (64, 21, 21, n_img), (1, 64, 64 * 21, 64 * 441), (64, 20, 12, 1), w1b, 32, 256,
+            # patch mode: the 2 x 2 taps of a tile are windows of ONE 21 x 13 pixel patch (12 output rows + 1 halo row,
+            # the full 21-pixel row pitch); accumulator row = patch pixel, the 21st column is junk (x >= o_ext)
+            pm = os.environ.get("A2CB_TCX_PATCH", "1") != "0"
+            ops.append(fwd_op("conv1.fwd", x0b, None, (64, 21, 21, n_img), (1, 64, 64 * 21, 64 * 441),
+                              (64, 21, 13, 1) if pm else (64, 20, 12, 1), w1b, 32, 256,
                               kbs, tiling(2 * B, 2, 12, t_div=2, tq_dim=3, tq_step=1), a1, a1_lo, (0, 32, 640, 12800),
                               (0, 20, 20, B), 32, alpha=1.0 / 255.0, bias=self.P("base.main.0.bias"), act=1, chain=2,
-                              flops=2.0 * B * 400 * 32 * 256, gather_dim=gd, bf16=True, emu_A=x0))
+                              flops=2.0 * B * 400 * 32 * 256, gather_dim=gd, bf16=True, emu_A=x0,
+                              patch=(252, (64, 21, 12, 1)) if pm else None))
         else:
             kbs = [((c0, bx, by, 0), (by * 2 + bx) * 64 + c0) for by in range(2) for bx in range(2) for c0 in (0, 32)]
             ops.append(fwd_op("conv1.fwd", x0, x0_lo, (64, 21, 21, n_img), (1, 64, 64 * 21, 64 * 441), (32, 20, 12, 1), w1, 32, 256,

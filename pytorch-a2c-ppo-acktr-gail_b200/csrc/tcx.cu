@@ -22,6 +22,7 @@
 //     two TMEM accumulators; the epilogue warps add finished chains into fp32 registers while the next
 //     chain runs.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "decls.cuh"
@@ -146,11 +147,19 @@ __device__ __forceinline__ void tx_tile_base(const TcxTiling& t, int tile, int* 
 // ---------------------------------------------------------------------------------------------------
 // forward-like: out tile [R <= 128 * MB pixels] x [BN channels], reduction over n_kb k-blocks of 32
 // ---------------------------------------------------------------------------------------------------
-template <int BN, int MB, bool BF16>
+// PATCH (bf16 mode, stride-1 taps): the taps of a tile are row-shifted windows of ONE input patch (box = the tile's
+// pixels plus the tap halo, one image row = box[1] pixels), so the patch is loaded ONCE per tile and every tap's A
+// operand is a UMMA descriptor whose start address is advanced by (dy * box[1] + dx) 128-byte rows inside it (the
+// swizzle is a function of the absolute shared-memory address, for TMA's writes and the tensor core's reads alike).  Accumulator row m
+// is patch pixel m: the columns / rows past the tile's valid extent are junk and never stored.  The weight image
+// (all k-blocks, three planes) is loaded once per CTA and stays resident.  Bytes staged per tile: one patch instead
+// of n_kb boxes + n_kb weight tiles.
+template <int BN, int MB, bool BF16, bool PATCH = false>
 __global__ void __launch_bounds__(TX_NT, 1)
 tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-               const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ TcxFwd p, const int stages) {
+               const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ TcxFwd p, const int stages,
+               const int patch_base_offset) {
     constexpr int B_BYTES = BN * TX_ROWB;
     constexpr int HALF = BN / 2;
     extern __shared__ uint8_t tx_dyn[];
@@ -165,8 +174,11 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool has_lo = !BF16 && p.A.lo != nullptr;
     constexpr int NB = BF16 ? 3 : 2;                              // planes of the weight tile
-    const int stage_bytes = A_BYTES * (has_lo ? 2 : 1) + NB * B_BYTES;
-    const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
+    const int stage_bytes = PATCH ? A_BYTES : A_BYTES * (has_lo ? 2 : 1) + NB * B_BYTES;
+    const int RBOX = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];      // rows TMA writes
+    const int R = PATCH ? p.patch : RBOX;                                      // accumulator rows the epilogue stores
+    const uint32_t dynB = dyn;                                                 // PATCH: resident weight image ...
+    const uint32_t dynA = dyn + (PATCH ? (uint32_t)(p.n_kb * NB * B_BYTES) : 0u);   // ... then the patch ring
     const int chain = p.chain > 0 ? p.chain : p.n_kb;
     const int n_chains = (p.n_kb + chain - 1) / chain;
     // persistent: work item w = tile_m * n_n + tile_n, strided over the grid.  The three roles walk the same
@@ -178,6 +190,7 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { tx_mbar_init(&bars.full[s], 1); tx_mbar_init(&bars.empty[s], 1); }
         for (int b = 0; b < 2; ++b) { tx_mbar_init(&bars.acc_full[b], 1); tx_mbar_init(&bars.acc_empty[b], 256); }
+        tx_mbar_init(&bars.fullB[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -192,9 +205,33 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ===== TMA producer: the whole warp walks the loop, one elected lane issues =====
-        const uint32_t bytes = (uint32_t)(R * TX_ROWB * (has_lo ? 2 : 1) + NB * B_BYTES);
+        const uint32_t bytes = (uint32_t)(RBOX * TX_ROWB * (has_lo ? 2 : 1) + NB * B_BYTES);
         int it = 0, s = 0;
         uint32_t ph = 0;                                   // parity of the NEXT completion of empty[s] to wait for
+        if constexpr (PATCH) {
+            if (tx_elect()) {
+                tx_expect(&bars.fullB[0], (uint32_t)(p.n_kb * NB * B_BYTES));
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                    const uint32_t sb = dynB + (uint32_t)(kb * NB * B_BYTES);
+                    tx_tma5(sb, &tmB, &bars.fullB[0], p.kb_b[kb], 0, 0, 0, 0);
+                    tx_tma5(sb + B_BYTES, &tmBlo, &bars.fullB[0], p.kb_b[kb], 0, 0, 0, 0);
+                    tx_tma5(sb + 2 * B_BYTES, &tmB3, &bars.fullB[0], p.kb_b[kb], 0, 0, 0, 0);
+                }
+            }
+            __syncwarp();
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+                int base[5];
+                tx_tile_base(p.tiles, w, base);
+                if (p.gather_dim > 0) base[p.gather_dim] = (int)__ldg(p.gather_idx + base[p.gather_dim]);
+                if (it >= stages) tx_mbar_wait(&bars.empty[s], ph ^ 1u);
+                if (tx_elect()) {
+                    tx_expect(&bars.full[s], (uint32_t)(RBOX * TX_ROWB));
+                    tx_tma5(dynA + (uint32_t)(s * stage_bytes), &tmA, &bars.full[s], 0, base[1], base[2], base[3], base[4]);
+                }
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+        } else
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             int base[5];
             tx_tile_base(p.tiles, w / n_n, base);
@@ -225,6 +262,49 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         int s = 0, cc = 0;
         uint32_t ph = 0;                                   // parity of full[s] to wait for
+        if constexpr (PATCH) {
+            tx_mbar_wait(&bars.fullB[0], 0u);
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                tx_mbar_wait(&bars.full[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                int kc = 0, c = 0;
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                    const int g = cc + c, buf = g & 1;
+                    const bool first = kc == 0;
+                    if (first && g >= 2) {
+                        tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)(((g >> 1) - 1) & 1));
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    const bool last = (kb == p.n_kb - 1) || (kc + 1 == chain);
+                    if (tx_elect()) {
+                        // tap (dx, dy) of this k-block: rows shifted by dy * (pixels per patch row) + dx
+                        const uint32_t sa = dynA + (uint32_t)(s * stage_bytes) +
+                                            (uint32_t)((p.kb_a[kb][1] + p.kb_a[kb][2] * p.A.box[1]) * TX_ROWB);
+                        const uint32_t sb = dynB + (uint32_t)(kb * NB * B_BYTES);
+#pragma unroll
+                        for (int mb = 0; mb < MB; ++mb) {
+                            const uint32_t d = tmem + (uint32_t)(buf * MB * BN + mb * BN);
+                            const uint32_t ah = sa + (uint32_t)(mb * 128 * TX_ROWB);
+                            const uint64_t bo = patch_base_offset ? ((uint64_t)((ah >> 7) & 7u) << 49) : 0ull;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint32_t o = ks * 32;
+                                const uint64_t dah = tx_desc_k(ah + o) | bo;
+                                tx_mma_f16(d, dah, tx_desc_k(sb + 2 * B_BYTES + o), idesc, (first && ks == 0) ? 0u : 1u);
+                                tx_mma_f16(d, dah, tx_desc_k(sb + B_BYTES + o), idesc, 1u);
+                                tx_mma_f16(d, dah, tx_desc_k(sb + o), idesc, 1u);
+                            }
+                        }
+                        if (kb == p.n_kb - 1) tx_commit(&bars.empty[s]);
+                        if (last) tx_commit(&bars.acc_full[buf]);
+                    }
+                    __syncwarp();
+                    if (last) { kc = 0; ++c; } else ++kc;
+                }
+                if (++s == stages) { s = 0; ph ^= 1u; }
+                cc += n_chains;
+            }
+        } else
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             int kc = 0, c = 0;                             // position inside the chain, chain index inside the tile
             for (int kb = 0; kb < p.n_kb; ++kb) {
@@ -281,6 +361,28 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float4 bsum[NCH];                                            // column sums of what this lane stores (bias gradient)
 #pragma unroll
         for (int i = 0; i < NCH; ++i) bsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // Everything that does not depend on the tile is computed ONCE: the box coordinates of this thread's
+        // accumulator rows (three runtime divisions each) and the uniform feature flags.  The epilogue is the
+        // critical path of the small-N layers (~1400 instructions per warp and 256 x 32 tile before this, ncu source
+        // view), so the per-tile and per-segment bookkeeping is kept to additions.
+        int ri[MB][4];
+        bool rin[MB];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+            int t = mb * 128 + 32 * q + lane;
+            rin[mb] = t < R;
+            ri[mb][0] = t % b1; t /= b1;
+            ri[mb][1] = t % b2; t /= b2;
+            ri[mb][2] = t % b3; t /= b3;
+            ri[mb][3] = t;
+        }
+        const bool has_mask = p.mask != nullptr, has_bias = p.bias != nullptr, has_cs = p.colsum_part != nullptr;
+        const bool has_cb = p.o_cb > 0, has_lo_out = p.out_lo != nullptr;
+        constexpr int CW = HALF < 32 ? HALF : 32;                    // columns per store pass
+        constexpr int LPR = CW / 4;                                  // lanes per row in the coalesced phase
+        constexpr int RPI = 32 / LPR;                                // rows per instruction
+        constexpr int NPASS = HALF / CW;
+        const int c4 = lane % LPR, lrow = lane / LPR;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
             int base[5];
             tx_tile_base(p.tiles, w / n_n, base);
@@ -290,32 +392,44 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
                 for (int n = 0; n < HALF; ++n) acc[mb][n] = 0.f;
+            // this lane's four channels of every store pass: channel, column-block shift, bias
+            int chs[NPASS];
+            long cbo[NPASS];
+            float4 bia[NPASS];
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ++ps) {
+                int ch = n0 + hf * HALF + ps * CW + c4 * 4;
+                long co = 0;
+                const bool ok = ch < p.N;
+                if (ok && has_cb) {
+                    const int cb = ch / p.o_cb;
+                    co = p.o_cb_off[cb];
+                    ch -= cb * p.o_cb;
+                }
+                chs[ps] = ok ? ch : -1;
+                cbo[ps] = co;
+                bia[ps] = (ok && has_bias) ? __ldg(reinterpret_cast<const float4*>(p.bias + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             // output offsets of this thread's rows (both M blocks), shared with the warp through shared memory; the
             // relu' mask lines of the tile are pulled into L2 now, while the MMAs of the tile are still running
             long* rowoff = reinterpret_cast<long*>(stage_base + 8 * 2048) + (warp - TX_EPI0) * 64;
             __syncwarp();
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
-                const int r = mb * 128 + 32 * q + lane;
                 long off0 = -1;
-                if (r < R) {
-                    int t = r;
-                    const int i1 = t % b1; t /= b1;
-                    const int i2 = t % b2; t /= b2;
-                    const int i3 = t % b3; t /= b3;
-                    const int i4 = t;
-                    const int g1 = base[1] + i1, g2 = base[2] + i2, g3 = base[3] + i3, g4 = base[4] + i4;
+                if (rin[mb]) {
+                    const int g1 = base[1] + ri[mb][0], g2 = base[2] + ri[mb][1], g3 = base[3] + ri[mb][2], g4 = base[4] + ri[mb][3];
                     if (g1 < p.o_ext[1] && g2 < p.o_ext[2] && g3 < p.o_ext[3] && g4 < p.o_ext[4])
                         off0 = p.o_base + g1 * p.o_stride[1] + g2 * p.o_stride[2] + g3 * p.o_stride[3] + g4 * p.o_stride[4];
                 }
                 rowoff[mb * 32 + lane] = off0;
-                if (p.mask && off0 >= 0) {
+                if (has_mask && off0 >= 0) {
 #pragma unroll
                     for (int c0 = 0; c0 < HALF; c0 += 32) {
                         int ch = n0 + hf * HALF + c0;
                         if (ch >= p.N) continue;
                         long off = off0;
-                        if (p.o_cb > 0) {
+                        if (has_cb) {
                             const int cb = ch / p.o_cb;
                             off += p.o_cb_off[cb];
                             ch -= cb * p.o_cb;
@@ -345,36 +459,25 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // different 128-byte lines per instruction.  Each warp instead transposes 16 rows x CW columns at a time
             // through its private 2 KiB staging slab (16-byte chunks xor-swizzled by row: conflict-free both ways) and
             // then writes / reads global memory with LPR lanes per row: whole 128-byte (CW = 32) or 64-byte segments.
-            constexpr int CW = HALF < 32 ? HALF : 32;                 // columns per pass
-            constexpr int LPR = CW / 4;                                // lanes per row in the coalesced phase
-            constexpr int RPI = 32 / LPR;                              // rows per instruction
             float4* slab = reinterpret_cast<float4*>(stage_base + (warp - TX_EPI0) * 2048);
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
-                for (int cc0 = 0; cc0 < HALF; cc0 += CW) {
+                for (int ps = 0; ps < NPASS; ++ps) {
+                  const int cc0 = ps * CW;
 #pragma unroll
                   for (int hr = 0; hr < 2; ++hr) {                       // rows 16 hr .. 16 hr + 15 of this warp's 32
                     constexpr int NIT = 16 / RPI;
                     // addresses and the relu' mask of this lane's NIT segments first: the loads are independent of the
                     // accumulators, so their latency hides behind the slab round trip instead of serialising the stores
                     long offs[NIT];
-                    int chs[NIT];
                     float4 mk[NIT];
 #pragma unroll
                     for (int it = 0; it < NIT; ++it) {
-                        const int lr = it * RPI + lane / LPR, c4 = lane % LPR;
-                        long off = rowoff[mb * 32 + 16 * hr + lr];
-                        int ch = n0 + hf * HALF + cc0 + c4 * 4;
-                        if (ch >= p.N) off = -1;
-                        if (off >= 0 && p.o_cb > 0) {
-                            const int cb = ch / p.o_cb;
-                            off += p.o_cb_off[cb];
-                            ch -= cb * p.o_cb;
-                        }
-                        offs[it] = off; chs[it] = ch;
-                        mk[it] = make_float4(1.f, 1.f, 1.f, 1.f);
-                        if (p.mask && off >= 0) mk[it] = __ldg(reinterpret_cast<const float4*>(p.mask + off + ch));
+                        long off = rowoff[mb * 32 + 16 * hr + it * RPI + lrow];
+                        off = (chs[ps] >= 0 && off >= 0) ? off + cbo[ps] + chs[ps] : -1;
+                        offs[it] = off;
+                        if (has_mask && off >= 0) mk[it] = __ldg(reinterpret_cast<const float4*>(p.mask + off));
                     }
                     __syncwarp();
                     if ((lane >> 4) == hr) {
@@ -389,23 +492,22 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
 #pragma unroll
                     for (int it = 0; it < NIT; ++it) {
-                        const int lr = it * RPI + lane / LPR, c4 = lane % LPR;
+                        const int lr = it * RPI + lrow;
                         const long off = offs[it];
-                        const int ch = chs[it];
                         if (off < 0) continue;
                         float4 v = slab[lr * LPR + (c4 ^ (lr & (LPR - 1)))];
-                        if (p.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                        }
+                        const float4 b = bia[ps];
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
                         if (p.act == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        const float4 m = mk[it];
-                        v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
-                        v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
-                        *reinterpret_cast<float4*>(p.out + off + ch) = v;
-                        if (p.out_lo)
-                            *reinterpret_cast<float4*>(p.out_lo + off + ch) = make_float4(tx_lo(v.x), tx_lo(v.y), tx_lo(v.z), tx_lo(v.w));
-                        bsum[cc0 / 32].x += v.x; bsum[cc0 / 32].y += v.y; bsum[cc0 / 32].z += v.z; bsum[cc0 / 32].w += v.w;
+                        if (has_mask) {
+                            const float4 m = mk[it];
+                            v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+                            v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                        }
+                        *reinterpret_cast<float4*>(p.out + off) = v;
+                        if (has_lo_out)
+                            *reinterpret_cast<float4*>(p.out_lo + off) = make_float4(tx_lo(v.x), tx_lo(v.y), tx_lo(v.z), tx_lo(v.w));
+                        if (has_cs) { bsum[cc0 / 32].x += v.x; bsum[cc0 / 32].y += v.y; bsum[cc0 / 32].z += v.z; bsum[cc0 / 32].w += v.w; }
                     }
                   }
                 }
@@ -695,26 +797,42 @@ int view_maps(CUtensorMap* hi, CUtensorMap* lo, const TcxView& v, int swizzle, c
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kSmemMax = 232448 - 1024;          // 227 KiB opt-in limit minus the kernels' static shared memory
 
-template <int BN, int MB, bool BF16 = false>
+template <int BN, int MB, bool BF16 = false, bool PATCH = false>
 int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
     const int a_planes = (!BF16 && p.A.lo) ? 2 : 1;
     const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
-    const int stage = ((R + 7) & ~7) * TX_ROWB * a_planes + (BF16 ? 3 : 2) * BN * TX_ROWB;
+    const int R8 = (R + 7) & ~7;
+    // patch mode: a stage is one patch; the weight image (all k-blocks, three planes) is resident next to the ring
+    const int resident = PATCH ? p.n_kb * 3 * BN * TX_ROWB : 0;
+    const int stage = PATCH ? R8 * TX_ROWB : R8 * TX_ROWB * a_planes + (BF16 ? 3 : 2) * BN * TX_ROWB;
     // the last stage's M-block reads may run past its own end: keep that many rows of slack inside the allocation
-    const int slack = (MB * 128 - ((R + 7) & ~7)) * TX_ROWB;
-    int stages = (kSmemMax - 1024 - TX_EPI_STAGING - slack) / stage;
+    int max_shift = 0;
+    if (PATCH)
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+            const int sh = p.kb_a[kb][1] + p.kb_a[kb][2] * p.A.box[1];
+            max_shift = sh > max_shift ? sh : max_shift;
+        }
+    int slack = (MB * 128 + max_shift - R8) * TX_ROWB;
+    slack = slack > 0 ? slack : 0;
+    int stages = (kSmemMax - 1024 - TX_EPI_STAGING - slack - resident) / stage;
     stages = stages > TX_MAX_STAGES ? TX_MAX_STAGES : stages;
     A2CB_REQUIRE(stages >= 2, "tcx_fwd: tile does not fit shared memory");
-    const int smem = stages * stage + 1024 + TX_EPI_STAGING + slack;
+    const int smem = stages * stage + 1024 + TX_EPI_STAGING + slack + resident;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tcx_fwd_kernel<BN, MB, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+        cudaError_t e = cudaFuncSetAttribute(tcx_fwd_kernel<BN, MB, BF16, PATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
         if (e != cudaSuccess) { set_error("tcx_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return A2CB_ERR_CUDA; }
         attr = true;
     }
+    // Measured on B200: the 128-byte swizzle of a UMMA operand is a function of the ABSOLUTE shared-memory address
+    // (bits 7..9 xor-ed into bits 4..6), exactly like TMA's, so a descriptor whose start is advanced by whole rows reads
+    // a row-shifted window of the patch as is; filling the descriptor's base-offset field with the start's row phase
+    // (A2CB_TCX_PATCH_BO=1) applies the phase twice and gives wrong products.
+    static int base_offset = -1;
+    if (base_offset < 0) { const char* e = getenv("A2CB_TCX_PATCH_BO"); base_offset = (e && e[0] == '1') ? 1 : 0; }
     const long n_work = (long)p.tiles.n_tiles * ((p.N + BN - 1) / BN);
     dim3 grid((unsigned)(n_work < kNumSM ? n_work : kNumSM));
-    tcx_fwd_kernel<BN, MB, BF16><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], p, stages);
+    tcx_fwd_kernel<BN, MB, BF16, PATCH><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], p, stages, base_offset);
     return check_launch("tcx_fwd");
 }
 
@@ -754,13 +872,15 @@ int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
     A2CB_REQUIRE(p.tiles.n_tiles > 0 && p.tiles.t_div > 0 && p.tiles.tr_dim >= 1 && p.tiles.tr_dim <= 4 &&
                  p.tiles.tq_dim >= 1 && p.tiles.tq_dim <= 4, "tcx_fwd: bad tiling");
     const long R = (long)p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
-    A2CB_REQUIRE(R >= 1 && R <= 256, "tcx_fwd: %ld rows per tile (max 256)", R);
+    A2CB_REQUIRE(R >= 1 && (R <= 256 || (p.bf16 && p.patch > 0 && R <= 512)), "tcx_fwd: %ld rows per tile (max 256)", R);
     const int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
     const int MB = R <= 128 ? 1 : 2;
     CUtensorMap m[5];
     if (p.bf16) {
         // exact bf16 operand, three-plane bf16 weight image, 64-channel k-blocks
-        A2CB_REQUIRE(p.B3 && !p.A.lo && BN == 32 && MB == 2, "tcx_fwd: bf16 mode is built for 32 output channels and 129..256 rows per tile");
+        const bool patch = p.patch > 0;
+        A2CB_REQUIRE(p.B3 && !p.A.lo && BN == 32 && (patch || MB == 2), "tcx_fwd: bf16 mode is built for 32 output channels and 129..256 rows per tile");
+        A2CB_REQUIRE(!patch || (p.patch > 128 && p.patch <= 256 && p.N <= 32 && p.n_kb <= 8), "tcx_fwd: patch mode takes 129..256 accumulator rows, one column tile, <= 8 taps");
         int rc = make_map(&m[0], p.A.x, p.A.dim, p.A.stride, p.A.box, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd A (bf16)", 2);
         if (rc) return rc;
         m[1] = m[0];
@@ -771,7 +891,7 @@ int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
         if ((rc = make_map(&m[2], p.B, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B1", 2))) return rc;
         if ((rc = make_map(&m[3], p.B_lo, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B2", 2))) return rc;
         if ((rc = make_map(&m[4], p.B3, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B3", 2))) return rc;
-        return launch_fwd<32, 2, true>(p, m, st);
+        return patch ? launch_fwd<32, 2, true, true>(p, m, st) : launch_fwd<32, 2, true>(p, m, st);
     }
     int rc = view_maps(&m[0], &m[1], p.A, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd A");
     if (rc) return rc;

@@ -62,7 +62,10 @@ struct TcxFwd {
     // every product costs three kind::f16 MMAs at twice the TF32 rate with half the operand bytes.
     const float* B3;
     int32_t bf16;
-    int32_t pad2_;
+    // patch mode (bf16 mode only; 0 = off): A.box is the input PATCH of a tile (tile pixels + tap halo), kb_a[kb][1..2]
+    // are the tap shifts (dx, dy) inside it, and `patch` = accumulator rows to store (patch pixels enumerated box[1] per
+    // row; pixels past o_ext are junk).  One TMA box per tile instead of one per tap.
+    int32_t patch;
 };
 
 // partial[split][row_off[m] + n * col_stride] = alpha * sum_rows A[row, m] * Bm[row, n]
