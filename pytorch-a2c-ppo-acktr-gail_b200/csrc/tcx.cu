@@ -129,6 +129,23 @@ __device__ __forceinline__ void tx_ld16(uint32_t taddr, uint32_t* v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same load without the wait, and a wait that "touches" the destination registers so that the compiler cannot
+// move their uses above it: several loads in flight per wait
+__device__ __forceinline__ void tx_ld16_issue(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tx_ld_wait16(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ float tx_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 struct TxBars {
@@ -138,10 +155,12 @@ struct TxBars {
 };
 
 __device__ __forceinline__ void tx_tile_base(const TcxTiling& t, int tile, int* base) {
-    base[0] = base[1] = base[2] = base[3] = base[4] = 0;
+    // selects instead of base[t.tr_dim] += ...: a dynamically indexed array lives in local memory
     const int tq = tile / t.t_div, tr = tile - tq * t.t_div;
-    base[t.tr_dim] += tr * t.tr_step;
-    base[t.tq_dim] += tq * t.tq_step;
+    const int vr = tr * t.tr_step, vq = tq * t.tq_step;
+    base[0] = 0;
+#pragma unroll
+    for (int d = 1; d < 5; ++d) base[d] = (t.tr_dim == d ? vr : 0) + (t.tq_dim == d ? vq : 0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -443,15 +462,32 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int buf = cc & 1;
                 tx_mbar_wait(&bars.acc_full[buf], (uint32_t)((cc >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // two 16-column loads in flight per wait (the pair is the two M blocks when a thread owns 16 columns)
+                constexpr int NLD = MB * (HALF / 16);
+                static_assert(NLD % 2 == 0 || NLD == 1, "tcx_fwd: loads are drained in pairs");
 #pragma unroll
-                for (int mb = 0; mb < MB; ++mb)
+                for (int l0 = 0; l0 < NLD; l0 += 2) {
+                    uint32_t v[2][16];
 #pragma unroll
-                    for (int c0 = 0; c0 < HALF; c0 += 16) {
-                        uint32_t v[16];
-                        tx_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * MB * BN + mb * BN + hf * HALF + c0), v);
-#pragma unroll
-                        for (int n = 0; n < 16; ++n) acc[mb][c0 + n] += __uint_as_float(v[n]);
+                    for (int j = 0; j < 2; ++j) {
+                        const int l = l0 + j;
+                        if (l < NLD) {
+                            const int mb = l / (HALF / 16), c0 = (l % (HALF / 16)) * 16;
+                            tx_ld16_issue(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * MB * BN + mb * BN + hf * HALF + c0), v[j]);
+                        }
                     }
+                    tx_ld_wait16(v[0]);
+                    if (l0 + 1 < NLD) tx_ld_wait16(v[1]);              // already complete: only pins the registers
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int l = l0 + j;
+                        if (l < NLD) {
+                            const int mb = l / (HALF / 16), c0 = (l % (HALF / 16)) * 16;
+#pragma unroll
+                            for (int n = 0; n < 16; ++n) acc[mb][c0 + n] += __uint_as_float(v[j][n]);
+                        }
+                    }
+                }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 tx_mbar_arrive(&bars.acc_empty[buf]);
             }
