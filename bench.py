@@ -304,13 +304,13 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the C5 shard
-# (profiles/r01e_tcx_gru_full_c5.txt); only meaningful for that workload
-NCU_DRAM_SOURCE = "profiles/r01e_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
+# (profiles/r01f_tcx_gru_full_c5.txt); only meaningful for that workload
+NCU_DRAM_SOURCE = "profiles/r01f_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
 NCU_DRAM_BYTES = {
-    "conv1.fwd": 0.463094e9 + 786.847e6, "conv2.fwd": 0.841122e9 + 318.661e6, "conv3.fwd": 0.340054e9 + 84.430e6,
-    "conv2.dgrad": 0.759601e9 + 794.670e6, "conv3.dgrad": 0.272846e9 + 291.947e6,
-    "conv1.wgrad": 1.764720e9 + 3.852e6, "conv2.wgrad": 1.183497e9 + 8.131e6, "conv3.wgrad": 0.442570e9 + 3.583e6,
-    "gru.seq_fwd": 0.053890e9 + 48.604e6, "gru.seq_bwd": 0.104025e9 + 60.963e6,
+    "conv1.fwd": 0.464279e9 + 783.700e6, "conv2.fwd": 0.840722e9 + 310.317e6, "conv3.fwd": 0.340063e9 + 82.415e6,
+    "conv2.dgrad": 0.759710e9 + 793.716e6, "conv3.dgrad": 0.272854e9 + 291.207e6,
+    "conv1.wgrad": 1.764638e9 + 3.536e6, "conv2.wgrad": 1.184132e9 + 8.677e6, "conv3.wgrad": 0.442583e9 + 4.129e6,
+    "gru.seq_fwd": 0.053970e9 + 47.836e6, "gru.seq_bwd": 0.104082e9 + 59.566e6,
 }
 
 
