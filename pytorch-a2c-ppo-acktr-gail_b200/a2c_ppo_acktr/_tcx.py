@@ -180,7 +180,7 @@ def fwd_op(name, A, A_lo, dims, strides, box, img, img_rows, img_cols, kbs, tile
         d.gather_idx = 1 if gather_dim else None          # placeholder: a2cb_run_ops substitutes the runtime row list
         d.colsum_part = arena.ptr(colsum_part)
         if patch is not None:
-            assert bf16 and patch[1][1] == box[1] and patch[0] == patch[1][1] * patch[1][2] * patch[1][3]
+            assert patch[1][1] == box[1] and patch[0] == patch[1][1] * patch[1][2] * patch[1][3]
             d.patch = patch[0]
         return d
     op = TcxOp(OP_TCX_FWD, make, name, flops=flops, runtime_idx=bool(gather_dim))
@@ -491,11 +491,21 @@ class CnnNet(object):
                           kbs, tiling(-(-B // k), 4, k), a2, a2_lo, (0, 64, 0, 576, 5184), (0, 9, 1, 9, B), 64,
                           bias=self.P("base.main.2.bias"), act=1, flops=2.0 * B * 81 * 64 * 512))
         # ---- conv3: tile = 5 images ----
-        kbs = [((c0, kx, ky, 0), (ky * 3 + kx) * 64 + c0) for ky in range(3) for kx in range(3) for c0 in (0, 32)]
-        k = 5
-        ops.append(fwd_op("conv3.fwd", a2, a2_lo, (64, 9, 9, B), (1, 64, 576, 5184), (32, 7, 7, k), w3, 32, 576, kbs,
-                          tiling(-(-B // k), 3, k), a3, a3_lo, (0, 32, 224, 1568), (0, 7, 7, B), 32,
-                          bias=self.P("base.main.4.bias"), act=1, chain=6, flops=2.0 * B * 49 * 32 * 576))
+        if os.environ.get("A2CB_TCX_PATCH3", "0") == "1":
+            # patch mode (TF32, streamed weights): per tile and channel half ONE 9 x 9 x 3-image patch (x and lo planes);
+            # the nine taps are row-shifted windows of it, accumulator row = patch pixel (x, y >= 7 are junk)
+            kbs = [((c0, kx, ky, 0), (ky * 3 + kx) * 64 + c0) for c0 in (0, 32) for ky in range(3) for kx in range(3)]
+            k = 3
+            ops.append(fwd_op("conv3.fwd", a2, a2_lo, (64, 9, 9, B), (1, 64, 576, 5184), (32, 9, 9, k), w3, 32, 576, kbs,
+                              tiling(-(-B // k), 3, k), a3, a3_lo, (0, 32, 224, 1568), (0, 7, 7, B), 32,
+                              bias=self.P("base.main.4.bias"), act=1, chain=6, flops=2.0 * B * 49 * 32 * 576,
+                              patch=(81 * k, (32, 9, 9, k))))
+        else:
+            kbs = [((c0, kx, ky, 0), (ky * 3 + kx) * 64 + c0) for ky in range(3) for kx in range(3) for c0 in (0, 32)]
+            k = 5
+            ops.append(fwd_op("conv3.fwd", a2, a2_lo, (64, 9, 9, B), (1, 64, 576, 5184), (32, 7, 7, k), w3, 32, 576, kbs,
+                              tiling(-(-B // k), 3, k), a3, a3_lo, (0, 32, 224, 1568), (0, 7, 7, B), 32,
+                              bias=self.P("base.main.4.bias"), act=1, chain=6, flops=2.0 * B * 49 * 32 * 576))
         # ---- fc ----
         ops.append(self.linear_fwd("fc.fwd", a3, a3_lo, 1568, wf, H, h, h_lo, bias=self.P("base.main.7.bias"), act=1))
         return ops, h

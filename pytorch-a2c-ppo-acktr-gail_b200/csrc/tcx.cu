@@ -150,7 +150,8 @@ __device__ __forceinline__ float tx_lo(float v) { return v - __uint_as_float(__f
 
 struct TxBars {
     uint64_t full[TX_MAX_STAGES], empty[TX_MAX_STAGES], acc_full[2], acc_empty[2];
-    uint64_t fullB[2], emptyB[2];        // weight-gradient kernel: ring of the operand shared by all groups
+    uint64_t fullB[TX_MAX_STAGES], emptyB[TX_MAX_STAGES];   // weight-gradient kernel: ring of the operand shared by all
+                                                            // groups; TF32 patch mode: ring of the weight k-blocks
     uint32_t tmem_base;
 };
 
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(TX_NT, 1)
 tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ TcxFwd p, const int stages,
-               const int patch_base_offset) {
+               const int patch_base_offset, const int stagesB) {
     constexpr int B_BYTES = BN * TX_ROWB;
     constexpr int HALF = BN / 2;
     extern __shared__ uint8_t tx_dyn[];
@@ -193,11 +194,13 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool has_lo = !BF16 && p.A.lo != nullptr;
     constexpr int NB = BF16 ? 3 : 2;                              // planes of the weight tile
-    const int stage_bytes = PATCH ? A_BYTES : A_BYTES * (has_lo ? 2 : 1) + NB * B_BYTES;
+    // PATCH: a stage is one patch (all planes).  bf16: the weight image is resident ahead of the patch ring;
+    // TF32: the weight k-blocks stream through their own ring behind it.
+    const int stage_bytes = PATCH ? A_BYTES * (has_lo ? 2 : 1) : A_BYTES * (has_lo ? 2 : 1) + NB * B_BYTES;
     const int RBOX = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];      // rows TMA writes
     const int R = PATCH ? p.patch : RBOX;                                      // accumulator rows the epilogue stores
-    const uint32_t dynB = dyn;                                                 // PATCH: resident weight image ...
-    const uint32_t dynA = dyn + (PATCH ? (uint32_t)(p.n_kb * NB * B_BYTES) : 0u);   // ... then the patch ring
+    const uint32_t dynB = (PATCH && !BF16) ? dyn + (uint32_t)(stages * stage_bytes) : dyn;
+    const uint32_t dynA = dyn + ((PATCH && BF16) ? (uint32_t)(p.n_kb * NB * B_BYTES) : 0u);
     const int chain = p.chain > 0 ? p.chain : p.n_kb;
     const int n_chains = (p.n_kb + chain - 1) / chain;
     // persistent: work item w = tile_m * n_n + tile_n, strided over the grid.  The three roles walk the same
@@ -209,7 +212,7 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { tx_mbar_init(&bars.full[s], 1); tx_mbar_init(&bars.empty[s], 1); }
         for (int b = 0; b < 2; ++b) { tx_mbar_init(&bars.acc_full[b], 1); tx_mbar_init(&bars.acc_empty[b], 256); }
-        tx_mbar_init(&bars.fullB[0], 1);
+        for (int s = 0; s < TX_MAX_STAGES; ++s) { tx_mbar_init(&bars.fullB[s], 1); tx_mbar_init(&bars.emptyB[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -227,7 +230,40 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t bytes = (uint32_t)(RBOX * TX_ROWB * (has_lo ? 2 : 1) + NB * B_BYTES);
         int it = 0, s = 0;
         uint32_t ph = 0;                                   // parity of the NEXT completion of empty[s] to wait for
-        if constexpr (PATCH) {
+        if constexpr (PATCH && !BF16) {
+            // patches (one per run of k-blocks with the same channel offset) and weight k-blocks, issued in the
+            // order the MMA warp consumes them -- two rings, one program order, so neither can starve the other
+            int itB = 0, sB = 0;
+            uint32_t phB = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                int base[5];
+                tx_tile_base(p.tiles, w, base);
+                if (p.gather_dim > 0) base[p.gather_dim] = (int)__ldg(p.gather_idx + base[p.gather_dim]);
+                for (int kb = 0; kb < p.n_kb; ++kb, ++itB) {
+                    if (kb == 0 || p.kb_a[kb][0] != p.kb_a[kb - 1][0]) {
+                        if (it >= stages) tx_mbar_wait(&bars.empty[s], ph ^ 1u);
+                        if (tx_elect()) {
+                            const uint32_t sa = dynA + (uint32_t)(s * stage_bytes);
+                            tx_expect(&bars.full[s], (uint32_t)(RBOX * TX_ROWB * (has_lo ? 2 : 1)));
+                            tx_tma5(sa, &tmA, &bars.full[s], p.kb_a[kb][0], base[1], base[2], base[3], base[4]);
+                            if (has_lo) tx_tma5(sa + A_BYTES, &tmAlo, &bars.full[s], p.kb_a[kb][0], base[1], base[2], base[3], base[4]);
+                        }
+                        __syncwarp();
+                        ++it;
+                        if (++s == stages) { s = 0; ph ^= 1u; }
+                    }
+                    if (itB >= stagesB) tx_mbar_wait(&bars.emptyB[sB], phB ^ 1u);
+                    if (tx_elect()) {
+                        const uint32_t sb = dynB + (uint32_t)(sB * NB * B_BYTES);
+                        tx_expect(&bars.fullB[sB], (uint32_t)(NB * B_BYTES));
+                        tx_tma5(sb, &tmB, &bars.fullB[sB], p.kb_b[kb], 0, 0, 0, 0);
+                        tx_tma5(sb + B_BYTES, &tmBlo, &bars.fullB[sB], p.kb_b[kb], 0, 0, 0, 0);
+                    }
+                    __syncwarp();
+                    if (++sB == stagesB) { sB = 0; phB ^= 1u; }
+                }
+            }
+        } else if constexpr (PATCH) {
             if (tx_elect()) {
                 tx_expect(&bars.fullB[0], (uint32_t)(p.n_kb * NB * B_BYTES));
                 for (int kb = 0; kb < p.n_kb; ++kb) {
@@ -281,7 +317,58 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         int s = 0, cc = 0;
         uint32_t ph = 0;                                   // parity of full[s] to wait for
-        if constexpr (PATCH) {
+        if constexpr (PATCH && !BF16) {
+            int sB = 0;
+            uint32_t phB = 0;
+            const int pitch1 = p.A.box[1], pitch2 = p.A.box[1] * p.A.box[2];
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                int kc = 0, c = 0;
+                for (int kb = 0; kb < p.n_kb; ++kb) {
+                    const bool grp_first = kb == 0 || p.kb_a[kb][0] != p.kb_a[kb - 1][0];
+                    const bool grp_last = kb == p.n_kb - 1 || p.kb_a[kb + 1][0] != p.kb_a[kb][0];
+                    const int g = cc + c, buf = g & 1;
+                    const bool first = kc == 0;
+                    if (first && g >= 2) tx_mbar_wait(&bars.acc_empty[buf], (uint32_t)(((g >> 1) - 1) & 1));
+                    if (grp_first) tx_mbar_wait(&bars.full[s], ph);
+                    tx_mbar_wait(&bars.fullB[sB], phB);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const bool last = (kb == p.n_kb - 1) || (kc + 1 == chain);
+                    if (tx_elect()) {
+                        // tap shift of this k-block inside the patch, in whole 128-byte rows
+                        const int shift = p.kb_a[kb][1] + p.kb_a[kb][2] * pitch1 + p.kb_a[kb][3] * pitch2;
+                        const uint32_t sa = dynA + (uint32_t)(s * stage_bytes) + (uint32_t)(shift * TX_ROWB);
+                        const uint32_t sb = dynB + (uint32_t)(sB * NB * B_BYTES);
+#pragma unroll
+                        for (int mb = 0; mb < MB; ++mb) {
+                            const uint32_t d = tmem + (uint32_t)(buf * MB * BN + mb * BN);
+                            const uint32_t ah = sa + (uint32_t)(mb * 128 * TX_ROWB);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint32_t o = ks * 32;
+                                const uint64_t dah = tx_desc_k(ah + o), dbh = tx_desc_k(sb + o), dbl = tx_desc_k(sb + B_BYTES + o);
+                                if (ks == 0) {
+                                    const uint32_t acc0 = first ? 0u : 1u;
+                                    if (has_lo) { tx_mma(d, tx_desc_k(ah + A_BYTES + o), dbh, idesc, acc0); tx_mma(d, dah, dbl, idesc, 1u); }
+                                    else tx_mma(d, dah, dbl, idesc, acc0);
+                                } else {
+                                    if (has_lo) tx_mma(d, tx_desc_k(ah + A_BYTES + o), dbh, idesc, 1u);
+                                    tx_mma(d, dah, dbl, idesc, 1u);
+                                }
+                                tx_mma(d, dah, dbh, idesc, 1u);
+                            }
+                        }
+                        tx_commit(&bars.emptyB[sB]);
+                        if (grp_last) tx_commit(&bars.empty[s]);
+                        if (last) tx_commit(&bars.acc_full[buf]);
+                    }
+                    __syncwarp();
+                    if (++sB == stagesB) { sB = 0; phB ^= 1u; }
+                    if (grp_last) { if (++s == stages) { s = 0; ph ^= 1u; } }
+                    if (last) { kc = 0; ++c; } else ++kc;
+                }
+                cc += n_chains;
+            }
+        } else if constexpr (PATCH) {
             tx_mbar_wait(&bars.fullB[0], 0u);
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
                 tx_mbar_wait(&bars.full[s], ph);
@@ -838,18 +925,23 @@ int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
     const int a_planes = (!BF16 && p.A.lo) ? 2 : 1;
     const int R = p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
     const int R8 = (R + 7) & ~7;
-    // patch mode: a stage is one patch; the weight image (all k-blocks, three planes) is resident next to the ring
-    const int resident = PATCH ? p.n_kb * 3 * BN * TX_ROWB : 0;
-    const int stage = PATCH ? R8 * TX_ROWB : R8 * TX_ROWB * a_planes + (BF16 ? 3 : 2) * BN * TX_ROWB;
+    // patch mode: a stage is one patch (all planes).  bf16: the weight image (all k-blocks, three planes) is resident
+    // next to the ring; TF32: the weight k-blocks stream through a ring of their own behind the patch ring.
+    const int slotB = (BF16 ? 3 : 2) * BN * TX_ROWB;
+    const int stagesB = (PATCH && !BF16) ? 4 : 0;
+    const int resident = PATCH ? (BF16 ? p.n_kb * slotB : stagesB * slotB) : 0;
+    const int stage = PATCH ? R8 * TX_ROWB * a_planes : R8 * TX_ROWB * a_planes + slotB;
     // the last stage's M-block reads may run past its own end: keep that many rows of slack inside the allocation
     int max_shift = 0;
     if (PATCH)
         for (int kb = 0; kb < p.n_kb; ++kb) {
-            const int sh = p.kb_a[kb][1] + p.kb_a[kb][2] * p.A.box[1];
+            const int sh = p.kb_a[kb][1] + p.kb_a[kb][2] * p.A.box[1] + p.kb_a[kb][3] * p.A.box[1] * p.A.box[2];
+            A2CB_REQUIRE(sh >= 0, "tcx_fwd: patch mode takes non-negative tap shifts");
             max_shift = sh > max_shift ? sh : max_shift;
         }
     int slack = (MB * 128 + max_shift - R8) * TX_ROWB;
     slack = slack > 0 ? slack : 0;
+    if (PATCH && !BF16) slack = slack > stagesB * slotB ? slack - stagesB * slotB : 0;   // the weight ring follows the patches
     int stages = (kSmemMax - 1024 - TX_EPI_STAGING - slack - resident) / stage;
     stages = stages > TX_MAX_STAGES ? TX_MAX_STAGES : stages;
     A2CB_REQUIRE(stages >= 2, "tcx_fwd: tile does not fit shared memory");
@@ -868,7 +960,7 @@ int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
     if (base_offset < 0) { const char* e = getenv("A2CB_TCX_PATCH_BO"); base_offset = (e && e[0] == '1') ? 1 : 0; }
     const long n_work = (long)p.tiles.n_tiles * ((p.N + BN - 1) / BN);
     dim3 grid((unsigned)(n_work < kNumSM ? n_work : kNumSM));
-    tcx_fwd_kernel<BN, MB, BF16, PATCH><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], p, stages, base_offset);
+    tcx_fwd_kernel<BN, MB, BF16, PATCH><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], p, stages, base_offset, stagesB);
     return check_launch("tcx_fwd");
 }
 
@@ -908,7 +1000,7 @@ int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
     A2CB_REQUIRE(p.tiles.n_tiles > 0 && p.tiles.t_div > 0 && p.tiles.tr_dim >= 1 && p.tiles.tr_dim <= 4 &&
                  p.tiles.tq_dim >= 1 && p.tiles.tq_dim <= 4, "tcx_fwd: bad tiling");
     const long R = (long)p.A.box[1] * p.A.box[2] * p.A.box[3] * p.A.box[4];
-    A2CB_REQUIRE(R >= 1 && (R <= 256 || (p.bf16 && p.patch > 0 && R <= 512)), "tcx_fwd: %ld rows per tile (max 256)", R);
+    A2CB_REQUIRE(R >= 1 && (R <= 256 || (p.patch > 0 && R <= 512)), "tcx_fwd: %ld rows per tile (max 256)", R);
     const int BN = p.N <= 32 ? 32 : (p.N <= 64 ? 64 : 128);
     const int MB = R <= 128 ? 1 : 2;
     CUtensorMap m[5];
@@ -938,6 +1030,11 @@ int tcx_fwd(const TcxFwd& p, cudaStream_t st) {
     if ((rc = make_map(&m[2], p.B, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B"))) return rc;
     if ((rc = make_map(&m[3], p.B_lo, bd, bs, bb, (int)CU_TENSOR_MAP_SWIZZLE_128B, "fwd B_lo"))) return rc;
     m[4] = m[3];
+    if (p.patch > 0) {
+        A2CB_REQUIRE(MB == 2 && p.patch > 128 && p.patch <= 256 && p.N <= BN && BN <= 64,
+                     "tcx_fwd: patch mode takes 129..256 accumulator rows and one column tile of <= 64 channels");
+        return BN == 32 ? launch_fwd<32, 2, false, true>(p, m, st) : launch_fwd<64, 2, false, true>(p, m, st);
+    }
     if (BN == 32) return MB == 1 ? launch_fwd<32, 1>(p, m, st) : launch_fwd<32, 2>(p, m, st);
     if (BN == 64) return MB == 1 ? launch_fwd<64, 1>(p, m, st) : launch_fwd<64, 2>(p, m, st);
     return MB == 1 ? launch_fwd<128, 1>(p, m, st) : launch_fwd<128, 2>(p, m, st);

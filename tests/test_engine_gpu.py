@@ -102,6 +102,16 @@ def test_gemm_split_k_and_reduce():
     assert np.all(got["G"][:5] == 3.0)
 
 
+@pytest.mark.parametrize("B", [4, 37])
+def test_cnn_forward_backward_conv3_patch_mode(B, monkeypatch):
+    """The opt-in TF32 patch mode of conv3's forward (A2CB_TCX_PATCH3=1: one 9 x 9 patch per tile and channel half,
+    the nine taps as row-shifted UMMA windows, weight k-blocks through their own ring) against the same reference.
+    Correct, but measured slower than the per-tap boxes (0.285 vs 0.204 ms: 40 % of a patch's accumulator rows are
+    junk and the small-N layers are epilogue-bound), hence off by default."""
+    monkeypatch.setenv("A2CB_TCX_PATCH3", "1")
+    test_cnn_forward_backward_vs_torch(torch.uint8, B)
+
+
 @pytest.mark.parametrize("B", [5, 1, 37])
 @pytest.mark.parametrize("obs_dtype", [torch.uint8, torch.float32])
 def test_cnn_forward_backward_vs_torch(obs_dtype, B):
