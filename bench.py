@@ -576,12 +576,23 @@ def main():
     args = ap.parse_args()
     global ENVS_OVERRIDE
     ENVS_OVERRIDE = args.envs
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        if args.warmup < 3:
-            args.warmup = 3
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: everything else any library writes to file descriptor 1 during the run (NCCL
+    # prints its version banner there) is sent to stderr; the JSON line goes to the saved descriptor at the end.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = sys.stdout
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            if args.warmup < 3:
+                args.warmup = 3
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        sys.stdout = real_stdout
 
 
 if __name__ == "__main__":
