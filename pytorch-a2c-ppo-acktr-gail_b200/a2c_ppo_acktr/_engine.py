@@ -121,6 +121,7 @@ class ActPlan(object):
         self.prog, self.sample, self.tensors, self.sites = prog, sample, tensors, sites
         self.home = {r: t.data_ptr() for r, t in tensors.items()}
         self.current = dict(self.home)
+        self.graphs = {}            # (mode, pointers) -> "seen" | (CUDA graph, launches): Policy._act_graphed
 
     def point(self, role, address):
         if self.current[role] != address:
@@ -195,6 +196,7 @@ class Arena(object):
     def __init__(self, device):
         self.device = device
         self.bufs = {}
+        self._consts = {}           # (dtype, bytes) -> device tensor, see const()
 
     def bind(self, name, tensor):
         self.bufs[name] = tensor
@@ -203,12 +205,11 @@ class Arena(object):
         """Device copy of a small read-only host table (numpy array), shared by content: programs keep raw device
         pointers to these tables, so a table must stay alive -- and unmoved -- for as long as ANY program built
         from it does; rebuilding a program therefore never replaces a table."""
-        consts = self.__dict__.setdefault("_consts", {})
         key = (host_array.dtype.str, host_array.tobytes())
-        t = consts.get(key)
+        t = self._consts.get(key)
         if t is None:
             t = torch.from_numpy(host_array.copy()).to(self.device)
-            consts[key] = t
+            self._consts[key] = t
         return t
 
     def stage(self, name, src):

@@ -269,7 +269,8 @@ class Policy(nn.Module):
               and obs.numel() * obs.element_size() <= rt.STAGE_BYTES)
         if not ok:                                            # odd layouts: the copying path
             v, a, lp, h = self.act(obs, hxs, masks, deterministic)
-            value.copy_(v); action.copy_(a); logp.copy_(lp); hout.copy_(h)
+            for dst, src in ((value, v), (action, a), (logp, lp), (hout, h)):
+                dst.copy_(src)
             return value, action, logp, hout
         rt.obs_code(obs)
         with torch.no_grad():
@@ -291,7 +292,7 @@ class Policy(nn.Module):
         """A slot's actor step is the same launch sequence with the same pointers every iteration (the sampling
         stream advances on the device), so from its second use on it is replayed as a CUDA graph: the host cost
         of a step drops from ~10 launches + their TMA descriptor encodes to one replay."""
-        graphs = plan.__dict__.setdefault("graphs", {})
+        graphs = plan.graphs
         g = graphs.get(key)
         if not self.use_cuda_graph or (g is None and len(graphs) >= 4096):
             return launch()

@@ -31,7 +31,7 @@ def test_pointer_sites_finds_nested_fields_and_patching_moves_them():
     got = sorted((f, off) for _, f, off in sites)
     assert got == [("p", 0), ("x", 16), ("x", 4095)]
     plan = _engine.ActPlan.__new__(_engine.ActPlan)
-    plan.sites, plan.home, plan.current = {"obs": sites}, {"obs": base}, {"obs": base}
+    plan.sites, plan.home, plan.current, plan.graphs = {"obs": sites}, {"obs": base}, {"obs": base}, {}
     plan.point("obs", 0x9000_0000)
     assert (d.p, d.a.x, d.arr[0].x) == (0x9000_0000, 0x9000_0010, 0x9000_0FFF)
     assert d.a.lo == 0x1234 and d.arr[1].lo == base + size and d.vals[0] == base + 8
