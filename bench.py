@@ -54,6 +54,41 @@ def peaks():
     return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def measure_tf32_peak(dev, seconds=1.5):
+    """Dense TF32 peak of THIS box, measured the way MEASURED_PEAKS.json measures bf16: cuBLAS fp32 matmul with TF32
+    tensor cores on 8192^3 (2 N^3 flops), best of 10 (burst) and back to back for `seconds` (sustained)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(10, int(seconds * 1e3 / best))
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        flops = 2.0 * n ** 3
+        return {"tf32_tflops": flops / best / 1e9, "tf32_tflops_sustained": flops * reps / e0.elapsed_time(e1) / 1e9,
+                "how": "torch.matmul fp32 with allow_tf32 (cuBLAS TF32 tensor cores), 8192^3, best of 10 / %d back to back" % reps}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 # ---------------------------------------------------------------------------
 # clocks sampler (nvidia-smi during the timed region)
 # ---------------------------------------------------------------------------
@@ -195,6 +230,8 @@ def run_ours(args):
                                alpha=cfg["alpha"], max_grad_norm=cfg["max_grad_norm"])
     if world > 1:
         agent.set_distributed(world, rank, env_range, N_total)
+    if hasattr(agent, "recurrent_sharding") and args.recurrent_sharding:
+        agent.recurrent_sharding = args.recurrent_sharding
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
@@ -273,6 +310,8 @@ def run_ours(args):
     out = None
     if rank == 0:
         pk = peaks()
+        if world == 1:
+            pk.update(measure_tf32_peak(dev))
         roof, kernels = kernel_roofline(agent, st, cfg, dev, pk) if world == 1 else (None, None)
         scan = scan_roofline(dev, pk) if world == 1 else None
         out = {
@@ -281,6 +320,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: %s" % (cfg["name"], describe(cfg)), "envs_per_gpu": Nloc, "num_steps": T,
+                       "recurrent_sharding": (getattr(agent, "recurrent_sharding", None) if (world > 1 and cfg.get("recurrent")) else None),
                        "obs": "uint8 4x84x84" if obs_dtype == torch.uint8 else "fp32", "l2": "flushed between steps (256 MiB write)",
                        "step": "compute_returns + update + after_update"},
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d_bytes,
@@ -294,13 +334,57 @@ def run_ours(args):
             out["kernels"] = kernels
         if scan:
             out["scan"] = scan
+        if world == 1 and cfg["name"] == "C5" and Nloc == 256:
+            out["parity"] = golden_parity_check(cfg, obs_np, dev)
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(cfg, steps=3)
+            out["cpu_baseline"] = cpu_baseline(cfg, (obs_np, rew_np, mask_np, bad_np))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out))
+
+
+def golden_parity_check(cfg, obs_np, dev):
+    """First update of the benchmarked shape against the REFERENCE's losses: tests/golden/update_C5m.npz holds the
+    policy outputs and losses the unmodified reference produced on this very rollout (same counter-based frames,
+    128 x 256, one epoch of four 64-environment minibatches).  A fixture, not the oracle: nothing under oracle/ runs
+    here.  Raises if the losses differ by more than the north-star 1e-4."""
+    from a2c_ppo_acktr import algo
+    from a2c_ppo_acktr.model import Policy
+    from a2c_ppo_acktr.storage import RolloutStorage
+    path = os.path.join(ROOT, "tests", "golden", "update_C5m.npz")
+    if not os.path.exists(path):
+        return {"checked": False, "why": "tests/golden/update_C5m.npz missing"}
+    with np.load(path, allow_pickle=False) as z:
+        case = {k: z[k] for k in z.files}
+    g = json.loads(str(case["config"]))
+    T, N = g["T"], g["N"]
+    assert (T, N) == (cfg["T"], cfg["N"]) and abs(float(obs_np.astype(np.float64).sum()) - float(case["obs_sum"])) < 1e-3
+    torch.manual_seed(1)
+    pol = Policy(tuple(g["obs_shape"]), Discrete(6), base_kwargs={"recurrent": True}).to(dev)
+    st = RolloutStorage(T, N, tuple(g["obs_shape"]), Discrete(6), 512, obs_dtype=torch.uint8)
+    st.to(dev)
+    rew, msk, bad = synthetic.atari_signals(T, N, 0)                      # frames: obs_np, the bench's own rollout
+    st.obs.copy_(torch.from_numpy(obs_np))
+    for k, a in (("rewards", rew), ("masks", msk), ("bad_masks", bad), ("actions", case["ro_actions"]),
+                 ("action_log_probs", case["ro_action_log_probs"]), ("value_preds", case["ro_value_preds"])):
+        getattr(st, k).copy_(torch.from_numpy(a))
+    st.recurrent_hidden_states[0].copy_(torch.from_numpy(case["ro_h0"]))
+    st.compute_returns(torch.from_numpy(case["ro_next_value"]).to(dev), g["use_gae"], g["gamma"], g["gae_lambda"],
+                       g["use_proper_time_limits"])
+    assert np.array_equal(st.returns.cpu().numpy()[:T], case["returns"][:T]), "returns differ from the reference"
+    agent = algo.PPO(pol, g["clip_param"], g["ppo_epoch"], g["num_mini_batch"], g["value_loss_coef"], g["entropy_coef"],
+                     lr=g["lr"], eps=g["eps"], max_grad_norm=g["max_grad_norm"])
+    torch.manual_seed(7)
+    got = np.array(agent.update(st))
+    want = case["losses"]
+    err = float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 2e-2)))
+    res = {"checked": True, "case": "update_C5m (reference-generated golden, T=128, N=256, 4 x 8192-row recurrent minibatches)",
+           "losses": got.tolist(), "reference_losses": want.tolist(), "max_rel_err": err, "tolerance": 1e-4}
+    if not np.allclose(got, want, rtol=1e-4, atol=2e-6):
+        raise SystemExit("bench.py: first-update losses differ from the reference golden: %s" % json.dumps(res))
+    return res
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the C5 shard
@@ -396,42 +480,50 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
     rows = [{"op": lab, "launches": a[2], "ms": float(a[0]), "share": float(a[0] / total),
              "tflops": float(a[1] / a[0] / 1e9) if a[1] else None} for lab, a in agg.items()]
     rows.sort(key=lambda r: -r["ms"])
-    gemm_rows = [r for r in rows if r["tflops"] is not None and not r["op"].startswith("gru.seq")]
-    if not gemm_rows:
+    flop_rows = [r for r in rows if r["tflops"] is not None]
+    if not flop_rows:
         return None, rows[:24]
-    top = gemm_rows[0]
-    gru_rows = [r for r in rows if r["op"].startswith("gru.seq")]
     from a2c_ppo_acktr import _native as nat
-    peak = pk["tensor_sustained"]
     tcx_ops = any(kind in (14, 15) for kind, _, _ in prog.entries)
-    fused_mlp = top["op"].startswith("mlp.fused")
-    roof = {"bound": "tensor", "kernel": ("a2cb::mlp_%s_kernel (%%s; fp32 SIMT, latency-bound at 64 rows)" % top["op"][-3:] if fused_mlp
-                                          else "a2cb::tcx_fwd_kernel / tcx_wgrad_kernel (%s)" if tcx_ops else
-                                          "a2cb::gemm_tc_kernel / gemm_kernel (%s)") % top["op"],
-            "achieved": top["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": top["tflops"] / peak, "traffic": None,
-            "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step); algorithmic fp32 "
-                           "flops: the tensor-core engine spends 3 TF32 MMAs per product (3xTF32), so <= 1/3 of a "
-                           "TF32 peak (no TF32 figure is published for this pool) is attainable",
-            "share_of_step": top["share"], "launch_ms": top["ms"] / top["launches"], "launches_per_step": top["launches"],
-            "step_program_ms": float(total), "gemm_engine_mode": int(nat.lib().a2cb_get_gemm_mode())}
-    # what the fp32-parity arithmetic can reach on this tensor pipe: TF32 runs at half the bf16 rate and every product
-    # costs 3 MMAs; conv1.fwd (uint8 frames, exact in bf16) runs 3 bf16 MMAs at the full rate, conv1.wgrad 2 TF32 MMAs
-    roof["peak_3xtf32"] = peak / 3.0 if top["op"] == "conv1.fwd" else peak / 2.0 / (2 if top["op"] == "conv1.wgrad" else 3)
-    roof["frac_3xtf32"] = top["tflops"] / roof["peak_3xtf32"]
     is_c5 = bool(cfg.get("recurrent")) and cfg["T"] == 128 and cfg["N"] == 256
-    roof["traffic"] = NCU_DRAM_BYTES.get(top["op"]) if is_c5 else None
-    roof["traffic_source"] = NCU_DRAM_SOURCE if roof["traffic"] else None
-    if gru_rows:
-        # the recurrence is the largest single launch of the recurrent workload; it runs on the fp32 SIMT pipe
-        # (148 SMs x 128 lanes x 2 flop x sm clock) with one barrier per time step, not on the tensor pipe
-        g = max(gru_rows, key=lambda r: r["ms"])
-        fp32_peak = 148 * 128 * 2 * 1.965e-3
-        roof["recurrence"] = {"kernel": "a2cb::gru_mma_%s_kernel" % ("bwd" if g["op"].endswith("bwd") else "fwd"),
-                              "traffic": NCU_DRAM_BYTES.get(g["op"]) if is_c5 else None,
-                              "bound": "per-step barrier + L2 latency (mma.sync 3xTF32; peak shown = fp32 SIMT pipe)",
-                              "achieved": g["tflops"], "peak": fp32_peak,
-                              "unit": "TFLOP/s", "frac": g["tflops"] / fp32_peak, "launch_ms": g["ms"],
-                              "share_of_step": g["share"]}
+    bf16_peak = pk["tensor_sustained"]
+    tf32_peak = pk.get("tf32_tflops_sustained") or bf16_peak / 2.0
+    tf32_src = ("measured in this run: " + pk["how"]) if pk.get("tf32_tflops_sustained") else "bf16 sustained / 2 (stand-in)"
+
+    def describe_row(r):
+        """Roofline entry of one op row: kernel name, the tensor-pipe peak of the arithmetic it issues, and what its
+        fp32-parity scheme can reach of it (every fp32 product costs 3 MMAs; conv1.wgrad 2: uint8 frames are exact)."""
+        op = r["op"]
+        if op.startswith("gru.seq"):
+            kern = "a2cb::gru_%s_%s_kernel" % (nat.gru_seq_variant(), "bwd" if op.endswith("bwd") else "fwd")
+            f16 = nat.gru_seq_variant() == "tc"
+            peak, mmas, what = (bf16_peak, 3, "kind::f16, fp16 hi/lo operand pairs") if f16 else (tf32_peak, 3, "mma.sync 3xTF32")
+            bound = "sequential: T dependent steps, one cross-CTA exchange per step (latency), " + what
+        elif op.startswith("mlp.fused"):
+            kern, peak, mmas, bound = "a2cb::mlp_%s_kernel" % op[-3:], 148 * 128 * 2 * 1.965e-3, 1, "fp32 SIMT, latency-bound at 64 rows"
+        elif tcx_ops and op == "conv1.fwd":
+            kern, peak, mmas, bound = "a2cb::tcx_fwd_kernel (conv1.fwd, bf16 mode)", bf16_peak, 3, "tensor (3 x kind::f16 on exact bf16 frames)"
+        elif tcx_ops:
+            kern = "a2cb::tcx_%s_kernel (%s)" % ("wgrad" if op.endswith("wgrad") else "fwd", op)
+            peak, mmas, bound = tf32_peak, (2 if op == "conv1.wgrad" else 3), "tensor (3xTF32 on tcgen05)"
+        else:
+            kern, peak, mmas, bound = "a2cb::gemm_tc_kernel / gemm_kernel (%s)" % op, tf32_peak, 3, "tensor (3xTF32) / fp32 SIMT"
+        return {"kernel": kern, "op": op, "bound": "tensor", "bound_detail": bound, "achieved": r["tflops"], "peak": peak,
+                "unit": "TFLOP/s", "frac": r["tflops"] / peak, "mmas_per_product": mmas,
+                "frac_of_attainable": r["tflops"] / (peak / mmas), "share_of_step": r["share"],
+                "launch_ms": r["ms"] / r["launches"], "launches_per_step": r["launches"],
+                "traffic": NCU_DRAM_BYTES.get(op) if is_c5 else None}
+
+    top = flop_rows[0]                                  # the largest-share launch of the minibatch program
+    roof = describe_row(top)
+    roof.update({
+        "peak_source": "%s bf16_tflops_sustained = %.1f; TF32 dense peak %.1f TFLOP/s (%s).  `achieved` counts ALGORITHMIC fp32 "
+                       "flops; `frac_of_attainable` divides by peak / mmas_per_product" % (pk["source"], bf16_peak, tf32_peak, tf32_src),
+        "step_program_ms": float(total), "gemm_engine_mode": int(nat.lib().a2cb_get_gemm_mode()),
+        "traffic_source": NCU_DRAM_SOURCE if (is_c5 and NCU_DRAM_BYTES.get(top["op"])) else None})
+    conv = [r for r in flop_rows if not r["op"].startswith("gru.seq") and r is not top]
+    if conv:
+        roof["next_kernel"] = describe_row(conv[0])      # the largest dense-layer launch besides the dominant one
     return roof, rows[:24]
 
 
@@ -489,75 +581,95 @@ def cpu_update_once(cfg, state):
     return time.perf_counter() - t0, out[:3]
 
 
-def cpu_sample_config(cfg):
-    """Bounded CPU sample: workloads with more than 4096 transitions per update are timed on a reduced
-    number of environments (the per-transition cost of the reference path does not depend on it)."""
+def cpu_sample_config(cfg, envs):
+    """The same workload on `envs` environments (the per-transition cost of the reference path does not depend on it)."""
     c = dict(cfg)
-    if c["T"] * c["N"] > 4096 and c["N"] > 1:
-        c["N"] = max(c.get("num_mini_batch", 1) * 4, 2048 // c["T"])
+    c["N"] = max(int(envs), c.get("num_mini_batch", 1))
     return c
 
 
-def cpu_state(cfg):
+def cpu_state(cfg, inputs=None):
     from oracle import policy as o_pol
     from oracle import update as o_upd
     spec = o_pol.Spec(cfg["obs_shape"], cfg["action"], cfg["recurrent"])
     p0 = o_pol.init_params(spec, seed=1)
     torch.manual_seed(2)
+    if inputs is not None:
+        obs, rew, msk, bad = inputs
+        inputs = (obs.astype(np.float32) if obs.dtype != np.float32 else obs, rew, msk, bad)
     with torch.no_grad():
         ro = synthetic.make_rollout(cfg, lambda o, h, m: o_pol.act(p0, spec, o, h, m),
-                                    lambda o, h, m: o_pol.get_value(p0, spec, o, h, m), spec.hidden_state_size, seed=0)
+                                    lambda o, h, m: o_pol.get_value(p0, spec, o, h, m), spec.hidden_state_size, seed=0,
+                                    inputs=inputs)
     return {"ro": ro, "p": o_upd.make_leaf_params(p0), "spec": spec}
 
 
-def cpu_baseline(cfg, steps=3, warmup=1):
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    full = cfg
-    cfg = cpu_sample_config(cfg)
-    if cfg["T"] * cfg["N"] > 2048:
-        steps = 2
-    state = cpu_state(cfg)
-    ts = []
+def cpu_time_updates(cfg, threads, steps, warmup, inputs=None, budget_s=None):
+    """Times `steps` updates (after `warmup`) of the oracle port on `threads` host threads; stops early when the
+    timed updates have used `budget_s` seconds.  -> (seconds per update, updates timed, last losses)."""
+    torch.set_num_threads(threads)
+    state = cpu_state(cfg, inputs)
+    ts, losses, used = [], None, 0.0
     for i in range(warmup + steps):
         torch.manual_seed(7 + i)
-        dt, _ = cpu_update_once(cfg, state)
+        dt, losses = cpu_update_once(cfg, state)
         if i >= warmup:
             ts.append(dt)
+            used += dt
+            if budget_s is not None and used >= budget_s:
+                break
+    return float(np.mean(ts)), len(ts), losses
+
+
+def cpu_baseline(cfg, inputs=None):
+    """Reported baseline (not a target): the oracle port of the reference on this box's host cores, on a bounded
+    sample of the SAME workload -- ONE full-size update with all cores (no warm-up: a C5 update is ~20 s), plus the
+    reference's own training setting `torch.set_num_threads(1)` (reference main.py:38) on a reduced number of
+    environments."""
+    cores = os.cpu_count() or 1
+    big = cfg["T"] * cfg["N"] > 8192
+    sec, n, _ = cpu_time_updates(cfg, cores, 1 if big else 3, 0 if big else 1, inputs)
     tr = cfg["T"] * cfg["N"]
-    what = "full" if cfg["N"] == full["N"] else "reduced (%d of %d environments)" % (cfg["N"], full["N"])
-    return {"value": tr / float(np.mean(ts)), "unit": "transitions/s", "cores": cores, "kind": "port",
-            "sample": "%d %s %s updates (%d transitions each) of the oracle port (torch %s CPU, %d threads), "
-                      "mean %.3f s/update" % (steps, what, cfg["name"], tr, torch.__version__, cores, float(np.mean(ts)))}
+    out = {"value": tr / sec, "unit": "transitions/s", "cores": cores, "kind": "port",
+           "sample": "%d full-size %s update%s (%d transitions each, %s) of the oracle port (torch %s CPU, %d threads), "
+                     "%.3f s/update" % (n, cfg["name"], "s" if n > 1 else "", tr,
+                                        "no warm-up" if big else "1 warm-up", torch.__version__, cores, sec)}
+    c1 = cpu_sample_config(cfg, max(cfg.get("num_mini_batch", 1) * 4, 2048 // cfg["T"])) if big else cfg
+    sec1, n1, _ = cpu_time_updates(c1, 1, 1, 0 if big else 1)
+    tr1 = c1["T"] * c1["N"]
+    out["threads_1"] = {"value": tr1 / sec1, "unit": "transitions/s", "cores": 1,
+                        "sample": "%d update of %d transitions (%d of %d environments) with torch.set_num_threads(1), the "
+                                  "reference's own training setting (main.py:38), %.3f s/update" % (n1, tr1, c1["N"], cfg["N"], sec1)}
+    torch.set_num_threads(cores)
+    return out
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (its oracle port: the pure-Python reference cannot
+    travel to the GPU box) on ALL host cores, on the ours-arm's config at FULL size (every environment of one GPU's
+    shard).  One warm-up update; the timed updates stop after A2CB_REF_BUDGET_S seconds (default 360) so that the run
+    ends within minutes whatever --steps says -- the sample string says how many were timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    full = workload_config(args.workload)
-    cfg = cpu_sample_config(full)
+    cfg = workload_config(args.workload)
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    state = cpu_state(cfg)
-    ts, losses = [], None
-    for i in range(args.warmup + args.steps):
-        torch.manual_seed(7 + i)
-        dt, losses = cpu_update_once(cfg, state)
-        if i >= args.warmup:
-            ts.append(dt)
+    budget = float(os.environ.get("A2CB_REF_BUDGET_S", "360"))
+    big = cfg["T"] * cfg["N"] > 8192
+    warm = min(args.warmup, 1) if big else args.warmup
+    sec, n, losses = cpu_time_updates(cfg, cores, args.steps, warm, None, budget)
     tr = cfg["T"] * cfg["N"]
-    val = tr / float(np.mean(ts))
-    what = "full" if cfg["N"] == full["N"] else "reduced (%d of %d environments per GPU)" % (cfg["N"], full["N"])
-    sample = "%d %s %s updates (%d transitions each) of the oracle port of the reference (torch %s CPU, %d threads)" % (
-        args.steps, what, cfg["name"], tr, torch.__version__, cores)
+    val = tr / sec
+    sample = ("%d of the %d requested full-size %s updates (%d transitions each, %d warm-up; time budget %.0f s) of the "
+              "oracle port of the reference (torch %s CPU, %d threads), %.3f s/update"
+              % (n, args.steps, cfg["name"], tr, warm, budget, torch.__version__, cores, sec))
     print(json.dumps({
         "impl": "reference", "metric": "%s update transitions/sec" % cfg["algo"].upper(),
         "value": val, "unit": "transitions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * float(np.mean(ts)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "steps_timed": n, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %s" % (full["name"], describe(full)), "envs_per_gpu": full["N"], "num_steps": full["T"],
-                   "step": "compute_returns + update + after_update", "cpu_sample_envs": cfg["N"]},
+        "config": {"workload": "%s: %s" % (cfg["name"], describe(cfg)), "envs_per_gpu": cfg["N"], "num_steps": cfg["T"],
+                   "obs": "fp32 (reference storage)", "step": "compute_returns + update + after_update"},
         "cpu_baseline": {"value": val, "unit": "transitions/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "losses": [float(x) for x in losses],
@@ -573,6 +685,9 @@ def main():
     ap.add_argument("--workload", default="C5", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--envs", type=int, default=0, help="override the number of environments per GPU")
+    ap.add_argument("--recurrent-sharding", default="", choices=["", "global", "stratified"],
+                    help="N > 1, recurrent PPO: 'global' (default) = the reference's one randperm(N_total); "
+                         "'stratified' = balanced per-rank permutations (not the reference's minibatch composition)")
     args = ap.parse_args()
     global ENVS_OVERRIDE
     ENVS_OVERRIDE = args.envs

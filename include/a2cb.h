@@ -478,6 +478,9 @@ int a2cb_gru_op(int32_t which, const a2cb_gru_t* desc, a2cb_stream_t stream);
 typedef struct { a2cb_gru_t d; const float* W_hh; const float* b_hh; } a2cb_gru_seq_t;
 int a2cb_gru_seq(int32_t backward, const a2cb_gru_seq_t* desc, a2cb_stream_t stream);
 int a2cb_gru_seq_supported(int32_t N, int32_t H);
+/* which kernel pair a2cb_gru_seq runs for this shape: 0 fp32 SIMT, 1 mma.sync 3xTF32, 2 tcgen05 (fp16 hi/lo operand
+ * pairs, state exchanged as shared-memory images), -1 unsupported */
+int a2cb_gru_seq_variant(int32_t N, int32_t H);
 
 /* ---------------------------------------------------------------------------
  * (5) ACKTR / KFAC helpers                              a2c_ppo_acktr/algo/kfac.py
@@ -504,7 +507,7 @@ int a2cb_frames_to_f32(float* dst, const void* src, int64_t n, int32_t src_is_u8
  * From the head outputs z[b] = (value, logits[A] | mean[A]): draws the action (Categorical: inverse CDF of the
  * softmax; DiagGaussian: mean + exp(logstd) * N(0,1)) or takes the mode (deterministic: argmax | mean), and writes
  * value, action and log-prob to their destinations (e.g. the [step] slots of the rollout buffer, storage.py:46-58).
- * rng = DEVICE {seed, offset, ticket} (3 x uint64, ticket zeroed once): Philox4x32-10 keyed by seed, counter
+ * rng = DEVICE {seed, offset, ticket, row_base} (4 x uint64, ticket zeroed once; row_base = global index of row 0): Philox4x32-10 keyed by seed, counter
  * (row, draw, offset); every sampling launch advances offset by one on the device.
  * ------------------------------------------------------------------------- */
 typedef struct {

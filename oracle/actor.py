@@ -34,15 +34,15 @@ def u01(x):
     return ((x >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
 
 
-def _counters(B, draw, offset):
+def _counters(B, draw, offset, row_base=0):
     c = np.zeros((B, 4), np.uint32)
-    c[:, 0] = np.arange(B, dtype=np.uint32)
+    c[:, 0] = (np.arange(B, dtype=np.uint64) + np.uint64(row_base)).astype(np.uint32)
     c[:, 1] = draw
     c[:, 2], c[:, 3] = offset & MASK, (offset >> 32) & MASK
     return c
 
 
-def categorical(z, seed, offset, deterministic=False):
+def categorical(z, seed, offset, deterministic=False, row_base=0):
     """z: [B, 1 + A] fp32 head outputs.  -> (value [B], action [B] int64, logp [B], u [B], cdf [B, A])."""
     z = np.asarray(z, np.float32)
     B, A = z.shape[0], z.shape[1] - 1
@@ -51,7 +51,7 @@ def categorical(z, seed, offset, deterministic=False):
     lse = mx[:, 0] + np.log(np.exp(logits - mx).sum(1, dtype=np.float32))
     p = np.exp(logits - lse[:, None]).astype(np.float32)
     cdf = np.cumsum(p, 1, dtype=np.float32)
-    u = u01(philox4x32_10(_counters(B, 0, offset), (seed & MASK, (seed >> 32) & MASK))[:, 0])
+    u = u01(philox4x32_10(_counters(B, 0, offset, row_base), (seed & MASK, (seed >> 32) & MASK))[:, 0])
     if deterministic:
         act = logits.argmax(1)
     else:
@@ -60,7 +60,7 @@ def categorical(z, seed, offset, deterministic=False):
     return z[:, 0], act.astype(np.int64), logp, u, cdf
 
 
-def gaussian(z, logstd, seed, offset, deterministic=False):
+def gaussian(z, logstd, seed, offset, deterministic=False, row_base=0):
     """z: [B, 1 + A] (value, mean), logstd [A].  -> (value, action [B, A], logp [B])."""
     z, logstd = np.asarray(z, np.float32), np.asarray(logstd, np.float32)
     B, A = z.shape[0], z.shape[1] - 1
@@ -68,7 +68,7 @@ def gaussian(z, logstd, seed, offset, deterministic=False):
     n = np.zeros((B, (A + 3) // 4 * 4), np.float32)
     if not deterministic:
         for blk in range((A + 3) // 4):
-            r = philox4x32_10(_counters(B, blk, offset), (seed & MASK, (seed >> 32) & MASK))
+            r = philox4x32_10(_counters(B, blk, offset, row_base), (seed & MASK, (seed >> 32) & MASK))
             u = u01(r)
             r0, r1 = np.sqrt(-2.0 * np.log(u[:, 0])), np.sqrt(-2.0 * np.log(u[:, 2]))
             a0, a1 = 2.0 * np.pi * u[:, 1].astype(np.float64), 2.0 * np.pi * u[:, 3].astype(np.float64)

@@ -54,6 +54,34 @@ def default_capacity(mbs_global, shard):
     return min(mbs_global, (cap + 3) // 4 * 4)
 
 
+def shard_env_chunks(perm, E_global, n_mb, shard):
+    """Recurrent minibatches of ONE global environment permutation (reference storage.py:152-156: chunk k =
+    perm[k E : (k + 1) E]): the environments of each chunk that this shard owns, renumbered to the local buffer,
+    in the order of the permutation.  -> list of n_mb int64 arrays (possibly empty)."""
+    g = np.asarray(perm, dtype=np.int64)
+    out = []
+    for k in range(n_mb):
+        c = g[k * E_global:(k + 1) * E_global]
+        out.append(c[(c >= shard.lo) & (c < shard.hi)] - shard.lo)
+    return out
+
+
+def env_capacity(E_global, shard, gran):
+    """Environments per recurrent minibatch a shard must be able to hold: the hypergeometric expectation plus a
+    6-sigma margin, rounded up to the program granularity and capped by what the shard owns."""
+    frac = shard.n_local / float(shard.n_total)
+    mean = E_global * frac
+    fpc = (shard.n_total - E_global) / max(shard.n_total - 1.0, 1.0)
+    sigma = (E_global * frac * (1 - frac) * fpc) ** 0.5
+    cap = int(mean + 6 * sigma + 1)
+    cap = (cap + gran - 1) // gran * gran
+    return max(gran, min(cap, (shard.n_local + gran - 1) // gran * gran))
+
+
+def round_up_envs(count, gran):
+    return max(gran, (int(count) + gran - 1) // gran * gran)
+
+
 def all_reduce_sum(t):
     import torch.distributed as dist
     dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -829,6 +829,12 @@ class NetBuilder(object):
 # ---------------------------------------------------------------------------
 # runtime: caches programs per batch shape and runs them
 # ---------------------------------------------------------------------------
+def derive_sampling_seed(cpu_seed):
+    """Philox key of the sampling stream from torch's CPU seed, WITHOUT consuming the generator (the minibatch
+    permutations of update() must stay the reference's)."""
+    return (int(cpu_seed) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & 0x7FFFFFFFFFFFFFFF
+
+
 class PolicyRuntime(object):
     MAX_CACHE = 96
     STAGE_BYTES = 64 << 20
@@ -847,6 +853,7 @@ class PolicyRuntime(object):
         self.forward_token = 0
         self.keep = {}
         self.zs = 1 + spec.num_actions
+        self.rng_provider = None     # callable -> device int64[4] {seed, offset, ticket, row_base}
 
     # -- helpers ------------------------------------------------------------
     def obs_code(self, obs):
@@ -879,12 +886,15 @@ class PolicyRuntime(object):
 
     # -- actor step ---------------------------------------------------------
     def rng_state(self):
-        """Device {seed, offset, ticket} of the sampling stream (a2cb_sample_t.rng).  Seeded from torch's CPU seed
-        WITHOUT consuming the generator (the minibatch permutations of update() must stay the reference's)."""
+        """Device {seed, offset, ticket, row_base} of the sampling stream (a2cb_sample_t.rng).  Owned by the Policy
+        (`Policy.sampling_state`), so that it survives re-flattening, device moves and pickling; a runtime built
+        without a policy (tests) keeps its own."""
+        if self.rng_provider is not None:
+            return self.rng_provider()
         st = getattr(self, "_rng_state", None)
         if st is None:
-            seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & 0x7FFFFFFFFFFFFFFF
-            st = self._rng_state = torch.tensor([seed, 0, 0], dtype=torch.int64, device=self.dev)
+            st = self._rng_state = torch.tensor([derive_sampling_seed(torch.initial_seed()), 0, 0, 0],
+                                                dtype=torch.int64, device=self.dev)
         return st
 
     def sample(self, z, action, value, logp, deterministic):
@@ -1086,15 +1096,18 @@ class PolicyRuntime(object):
 
     # -- fused training step --------------------------------------------------
     def train_program(self, storage, mbs, mode, hyper, adv=None, noise=None, loss_accum=None, use_idx=True,
-                      with_backward=True, seq=None):
+                      with_backward=True, seq=None, tag=None):
         """Op list of one minibatch step reading rows of `storage` through the runtime index list:
-        forward -> loss epilogue (mode) -> backward.  Optimiser ops are appended by the caller."""
+        forward -> loss epilogue (mode) -> backward.  Optimiser ops are appended by the caller.
+        `tag`: arena name prefix of the program's buffers (default: one set per minibatch size).  Programs of
+        different sizes that never run concurrently may share a tag -- build the LARGEST first, since growing a
+        buffer re-allocates it under the programs that already point at it."""
         s = self.spec
         T, N = storage.rewards.shape[0], storage.rewards.shape[1]
         obs_flat = storage.obs[:-1].view(T * N, *storage.obs.shape[2:])
         code = self.obs_code(obs_flat)
         self.arena.bind("obs_st", obs_flat.view(-1))
-        tag = "t%d_" % mbs
+        tag = tag or "t%d_" % mbs
         kw = {}
         if s.recurrent:
             # rows of the minibatch are time-major (t * E + e); masks come from the rollout buffer through

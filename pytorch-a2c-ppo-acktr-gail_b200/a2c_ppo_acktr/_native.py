@@ -37,6 +37,7 @@ _SIGNATURES = {
     "a2cb_returns_scan": (c_int, [c_void_p] * 6 + [c_int, c_i64, c_f64, c_f64, c_int, c_int, c_int, c_void_p]),
     "a2cb_gather_rows": (c_int, [ctypes.POINTER(GatherField), c_int, c_void_p, c_i64, c_int, c_i64, c_i64, c_void_p]),
     "a2cb_upload_env_columns": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_int, c_void_p]),
+    "a2cb_gru_seq_variant": (c_int, [c_int, c_int]),
 }
 
 _lib = None
@@ -82,6 +83,11 @@ def check(rc, what):
 def set_gemm_mode(mode):
     """0: exact-fp32 SIMT engine; 1: tcgen05 3xTF32 engine everywhere; 2: automatic choice (default)."""
     check(lib().a2cb_set_gemm_mode(int(mode)), "a2cb_set_gemm_mode")
+
+
+def gru_seq_variant(N=64, H=512):
+    """Kernel pair behind a2cb_gru_seq for this shape: "simt" | "mma" | "tc" (None: unsupported)."""
+    return {0: "simt", 1: "mma", 2: "tc"}.get(int(lib().a2cb_gru_seq_variant(int(N), int(H))))
 
 
 def launch_count():

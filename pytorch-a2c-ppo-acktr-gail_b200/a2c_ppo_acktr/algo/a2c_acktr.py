@@ -44,6 +44,8 @@ class A2C_ACKTR():
         clip + RMSprop step."""
         self.shard = _dist.ShardInfo(world, rank, env_range[0], env_range[1], n_total) if world > 1 else None
         self._prog_key = None
+        if world > 1 and hasattr(self.actor_critic, "set_sampling_shard"):
+            self.actor_critic.set_sampling_shard(env_range[0])      # exploration noise differs between ranks
 
     def update(self, rollouts):
         policy = self.actor_critic
@@ -148,8 +150,11 @@ class A2C_ACKTR():
             progs["fisher"].run()
             opt.accumulate_g(rt)
             opt.acc_stats = False
-        if sh is not None:
-            for fname, f in opt.factors.items():      # ~15.6 MB of factor statistics per update (CNN)
+        if sh is not None and use_fisher:
+            # ~15.6 MB of factor statistics per update (CNN).  Only on steps that folded new statistics: each rank
+            # then holds decay / world * m + (1 - decay) * its increment, so the SUM over ranks is the new average;
+            # on any other step (Ts > 1) nothing was rescaled and a sum would multiply every factor by `world`.
+            for fname, f in opt.factors.items():
                 if fname != "one":
                     yield f["m"]
         progs["main"].run()

@@ -53,6 +53,10 @@ def _adv_normalize(rt, rollouts):
 
 
 class PPO():
+    GRAPH_SLOTS = 4            # epochs whose index / scalar uploads may be in flight at once (_epoch_graph)
+    ENV_GRANULARITY = 4        # sharded recurrent minibatches: local environment count rounded up to this many slots
+    recurrent_sharding = "global"      # "global": the reference's one randperm(N_total); "stratified": balanced opt-in
+
     def __init__(self,
                  actor_critic,
                  clip_param,
@@ -88,6 +92,8 @@ class PPO():
         rollout of n_total environments, one shard per rank of the default process group."""
         self.shard = _dist.ShardInfo(world, rank, env_range[0], env_range[1], n_total) if world > 1 else None
         self._prog_key = None
+        if world > 1 and hasattr(self.actor_critic, "set_sampling_shard"):
+            self.actor_critic.set_sampling_shard(env_range[0])      # exploration noise differs between ranks
 
     def _program(self, rt, rollouts, mbs, adv, accum, inv_B=None, seq=None, chunked=False):
         """(forward + loss + backward) program and the (clip + Adam) program.  Unsharded they are one
@@ -127,17 +133,26 @@ class PPO():
         (`RolloutStorage.stage_host`) their upload is started here, in minibatch order on the copy stream, and
         minibatch k only waits for ITS environments -- the rest of the upload overlaps the compute.
         Returns prepare(k, rows) to call before minibatch k, and finish() after the epoch."""
-        chunked = getattr(prog, "prologue_chunk", None) is not None
+        progs = prog if isinstance(prog, (list, tuple)) else [prog] * n_chunks      # one program per chunk, or one for all
+        chunks = perm if isinstance(perm, (list, tuple)) else [perm[k * E:(k + 1) * E] for k in range(n_chunks)]
+        chunked = all(getattr(p, "prologue_chunk", None) is not None for p in progs)
         events = None
         if chunked and getattr(rollouts, "_staged_obs", None) is not None:
-            events = rollouts._upload_staged([perm[k * E:(k + 1) * E] for k in range(n_chunks)])
+            events = rollouts._upload_staged(chunks)
+        elif not chunked and isinstance(prog, (list, tuple)):
+            # sized programs without a per-chunk re-layout: the whole rollout once (PPO._program does this for the
+            # single-program paths)
+            _wait_staged(rollouts)
+            pro = getattr(progs[0], "prologue", None)
+            if pro is not None:
+                pro.run()
         cur = torch.cuda.current_stream(rollouts.rewards.device)
 
         def prepare(k, rows):
             if chunked:
                 if events is not None:
                     cur.wait_event(events[k])
-                prog.prologue_chunk.run(rows)
+                progs[k].prologue_chunk.run(rows)
 
         def finish():
             if events is not None:
@@ -204,23 +219,35 @@ class PPO():
                         prog.optim_desc.dyn = dyn_buf.data_ptr() + 16 * k
                         prog.run(idx_buf[k * mbs:(k + 1) * mbs])
                 prog.optim_desc.dyn = None
+                # The uploads below are asynchronous and queue up behind the previous epoch's replay (milliseconds),
+                # while the host only needs a randperm to reach the next epoch: every epoch in flight therefore needs
+                # its OWN pinned staging slot.  A ring of slots, each guarded by an event recorded after its two
+                # uploads; a slot is rewritten only after that event has completed.
+                slots = [dict(dyn=torch.zeros(n_mb, 4).pin_memory(),
+                              idx=torch.zeros(n_mb * mbs, dtype=torch.int64).pin_memory(), event=None)
+                         for _ in range(self.GRAPH_SLOTS)]
                 self._graph = g = dict(key=key, graph=graph, idx=idx_buf, dyn=dyn_buf,
-                                       launches=_native.launch_count() - n0,
-                                       host_dyn=torch.zeros(n_mb, 4).pin_memory(),
-                                       host_idx=torch.zeros(n_mb * mbs, dtype=torch.int64).pin_memory())
+                                       launches=_native.launch_count() - n0, slots=slots, next_slot=0)
                 _native.lib().a2cb_add_launches(-g["launches"])          # capture recorded, did not run, them
             else:
                 self._graph = dict(key=None, pending=key)
                 return False
         opt = self.optimizer
-        hd = g["host_dyn"]
+        slot = g["slots"][g["next_slot"]]
+        g["next_slot"] = (g["next_slot"] + 1) % len(g["slots"])
+        if slot["event"] is not None:
+            slot["event"].synchronize()          # the uploads that last read this slot have completed
+        hd = slot["dyn"]
         for k in range(n_mb):
             opt.step_count += 1
             sc = opt.scalars()
             hd[k, 0], hd[k, 1], hd[k, 2] = sc["lr_eff"], sc["bc2_sqrt"], float(sc["first_step"])
-        g["host_idx"].copy_(perm[:n_mb * mbs])
-        g["idx"].copy_(g["host_idx"], non_blocking=True)
+        slot["idx"].copy_(perm[:n_mb * mbs])
+        g["idx"].copy_(slot["idx"], non_blocking=True)
         g["dyn"].copy_(hd, non_blocking=True)
+        if slot["event"] is None:
+            slot["event"] = torch.cuda.Event()
+        slot["event"].record(torch.cuda.current_stream(rt.dev))
         g["graph"].replay()
         _native.lib().a2cb_add_launches(g["launches"])
         return True
@@ -277,12 +304,111 @@ class PPO():
             return done.value
 
     def sharded_recurrent_steps(self, rt, rollouts):
-        """Recurrent PPO on an environment shard.  Whole environments are the unit of a recurrent
-        minibatch and every rank owns the same number of them, so the global minibatch k is the union
-        over ranks of the k-th chunk of each rank's LOCAL environment permutation: perfectly balanced,
-        nothing padded, no frame or hidden state ever leaves its GPU.  (A single-device run fed the same
-        environment sets gives the same result; the partition is stratified by rank, not one global
-        randperm.)  Yields the tensors to sum-all-reduce, like `sharded_steps`."""
+        """Recurrent PPO on an environment shard; yields the tensors to sum-all-reduce, like `sharded_steps`.
+        `recurrent_sharding` selects how the global minibatches are formed (see the two methods)."""
+        if self.recurrent_sharding == "stratified":
+            return self._sharded_recurrent_stratified(rt, rollouts)
+        return self._sharded_recurrent_global(rt, rollouts)
+
+    def _sized_recurrent_program(self, rt, rollouts, E_p, adv, accum, inv_B):
+        """Forward + loss + backward program for E_p environment slots (rows time-major, slot e valid iff
+        e < n_valid), and the shared clip + Adam program.  All sizes share one set of activation buffers (tag "tR_"):
+        the largest size is built first and the cache is dropped if a larger one is ever needed."""
+        from .. import _engine
+        T = rollouts.rewards.shape[0]
+        key = (id(rt), rollouts.obs.data_ptr(), rollouts.actions.data_ptr(), rollouts.returns.data_ptr(),
+               rollouts.value_preds.data_ptr(), rollouts.action_log_probs.data_ptr(), adv.data_ptr(), accum.data_ptr(),
+               inv_B, rollouts.masks.data_ptr(), self.clip_param, self.value_loss_coef, self.entropy_coef,
+               self.use_clipped_value_loss, self.max_grad_norm)
+        if key != getattr(self, "_rec_key", None):
+            self._rec_key, self._rec_progs, self._rec_opt = key, {}, None
+        prog = self._rec_progs.get(E_p)
+        if prog is None:
+            if self._rec_progs and E_p > max(self._rec_progs):
+                self._rec_progs = {}
+            hyper = dict(clip_param=self.clip_param, value_loss_coef=self.value_loss_coef, entropy_coef=self.entropy_coef,
+                         use_clipped_value_loss=self.use_clipped_value_loss, inv_B=inv_B)
+            prog = rt.train_program(rollouts, T * E_p, 0, hyper, adv=adv, loss_accum=accum, seq=(T, E_p), tag="tR_")
+            prog.loss_desc.valid_mod = E_p
+            prog.finalize()
+            self._rec_progs[E_p] = prog
+        if self._rec_opt is None:
+            self.optimizer._ensure_state()
+            opt = _engine.Program(rt.dev)
+            opt.optim_desc = rt.add_optimizer_ops(opt, 0, self.optimizer.state1, self.optimizer.state2, self.max_grad_norm)
+            self._rec_opt = opt.finalize()
+        return prog, self._rec_opt
+
+    def _sharded_recurrent_global(self, rt, rollouts):
+        """Reference-identical minibatches (the default): every rank draws the ONE `randperm(N_total)` of reference
+        storage.py:152 (same CPU seed), global minibatch k is perm[k E : (k + 1) E], and each rank processes the
+        environments of that chunk it owns -- no frame or hidden state ever leaves its GPU.  The local count is
+        hypergeometric, so the program runs on the count rounded up to `ENV_GRANULARITY` environment slots; padding
+        slots repeat a real environment and contribute neither loss nor gradient (a2cb_loss_t.n_valid / valid_mod);
+        loss terms are local sums over the GLOBAL minibatch size."""
+        sh = self.shard
+        self._update_serial = getattr(self, "_update_serial", 0) + 1
+        T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+        assert n_loc == sh.n_local, "rollouts hold %d environments, the shard declares %d" % (n_loc, sh.n_local)
+        nmb = self.num_mini_batch
+        assert sh.n_total >= nmb and sh.n_total % nmb == 0, (
+            "sharded recurrent PPO needs a number of processes ({}) divisible by the number of PPO mini batches ({})"
+            .format(sh.n_total, nmb))
+        E_g = sh.n_total // nmb
+        gran = self.ENV_GRANULARITY if n_loc >= 2 * self.ENV_GRANULARITY else 1
+        cap = _dist.env_capacity(E_g, sh, gran)
+        moments = _adv_moments(rt, rollouts)
+        yield moments
+        adv = _adv_apply(rt, rollouts, moments)
+        accum = rt.arena.ensure("loss_accum", 4)
+        accum.zero_()
+        inv_B = 1.0 / (T * E_g)
+        self._sized_recurrent_program(rt, rollouts, cap, adv, accum, inv_B)        # largest first: owns the buffers
+        H = rt.spec.hidden
+        h0 = rollouts.recurrent_hidden_states[0]
+        t_off = (torch.arange(T, device=rt.dev, dtype=torch.int64) * n_loc).view(T, 1)
+        grads = rt.arena.bufs["G"]
+        launches0 = _native.launch_count()
+        for epoch in range(self.ppo_epoch):
+            perm = torch.randperm(sh.n_total).numpy()         # identical on every rank (same CPU seed)
+            chunks = _dist.shard_env_chunks(perm, E_g, nmb, sh)
+            plan = []
+            for mine in chunks:
+                E_p = _dist.round_up_envs(len(mine), gran)
+                prog, opt = self._sized_recurrent_program(rt, rollouts, E_p, adv, accum, inv_B)
+                env = torch.full((E_p,), int(mine[0]) if len(mine) else 0, dtype=torch.int64)
+                env[:len(mine)] = torch.from_numpy(mine)
+                plan.append((prog, env, len(mine), E_p))
+            if epoch == 0:
+                prepare, finish = self._first_epoch_chunks([p[0] for p in plan], rollouts,
+                                                           [torch.from_numpy(c) for c in chunks], None, nmb)
+            for k, (prog, env, count, E_p) in enumerate(plan):
+                env = env.to(rt.dev)
+                rows = (t_off + env.view(1, E_p)).reshape(-1).contiguous()
+                if epoch == 0:
+                    prepare(k, rows)
+                hxs_mb = rt.arena.bufs["hxs_mb"][:E_p * H].view(E_p, H)
+                _native.gather_rows([(h0, hxs_mb)], env, E_p)
+                prog.loss_desc.n_valid = count
+                prog.run(rows)
+                yield grads
+                self.optimizer.configure(opt.optim_desc)
+                opt.run()
+                if self.step_hook is not None:
+                    self.step_hook(self.optimizer.step_count)
+            if epoch == 0:
+                finish()
+        self.last_launches = _native.launch_count() - launches0
+        yield accum
+        num_updates = self.ppo_epoch * self.num_mini_batch
+        sums = accum[:3].cpu()
+        return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
+
+    def _sharded_recurrent_stratified(self, rt, rollouts):
+        """Opt-in (`recurrent_sharding = "stratified"`): global minibatch k is the union over ranks of the k-th chunk
+        of each rank's LOCAL environment permutation -- perfectly balanced, nothing padded, but NOT the reference's
+        minibatch composition (the partition is stratified by rank instead of one global randperm).  A single-device
+        run fed the same environment sets gives the same result."""
         sh = self.shard
         self._update_serial = getattr(self, "_update_serial", 0) + 1
         T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]

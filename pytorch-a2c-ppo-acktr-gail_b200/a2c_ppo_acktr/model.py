@@ -8,8 +8,9 @@ construction order, orthogonal init with the same gains, zero biases).
 
 All parameters are views into ONE flat fp32 buffer (and their .grad into one flat gradient
 buffer) so that the fused update needs a single norm / optimiser launch and, when sharded,
-a single NCCL all-reduce.  The dense math runs on the affine-indexed GEMM engine
-(csrc/gemm.cu); log-prob / entropy / losses on the fused epilogue (csrc/loss.cu).
+a single NCCL all-reduce.  The CNN trunk and the GRU input product run on the TMA-fed tcgen05 engine
+(csrc/tcx.cu), the GRU recurrence on csrc/gru_*.cu, MLP policies on csrc/mlp_fused.cu, everything else on
+the affine-indexed GEMM engine (csrc/gemm*.cu); log-prob / entropy / losses on the fused epilogue (csrc/loss.cu).
 There is no CPU path: calling the policy with CPU tensors raises.
 """
 import math
@@ -135,6 +136,7 @@ class Policy(nn.Module):
         self._flat = None
         self._flat_grad = None
         self._runtime = None
+        self._rng = None             # sampling stream of act(): see sampling_state()
         self._flatten()
 
     # -- flat parameter buffer ------------------------------------------------
@@ -181,10 +183,14 @@ class Policy(nn.Module):
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_flat"] = st["_flat_grad"] = st["_runtime"] = None
+        rng = st.get("_rng")
+        if rng is not None:          # a checkpoint resumes the sampling stream where it stopped
+            st["_rng"] = dict(rng, state=rng["state"].cpu())
         return st
 
     def __setstate__(self, st):
         self.__dict__.update(st)
+        self.__dict__.setdefault("_rng", None)
         self._flatten()
 
     def runtime(self):
@@ -192,7 +198,35 @@ class Policy(nn.Module):
             self._flatten()
         if self._runtime is None:
             self._runtime = _engine.PolicyRuntime(self._spec, self._layout, self._flat, self._flat_grad)
+            self._runtime.rng_provider = self.sampling_state
         return self._runtime
+
+    # -- sampling stream of act() (csrc/actor.cu) -------------------------------
+    def sampling_state(self):
+        """Device int64 {seed, offset, ticket, row_base}: Philox key, launches drawn so far, the kernel's ticket
+        counter and the GLOBAL index of this policy's first environment (`set_sampling_shard`).  The state belongs to
+        the policy, not to its runtime: it survives `_flatten()`, `.to(device)` and pickling (`torch.save` of the
+        policy, reference main.py:173-176).  The key is derived from `torch.initial_seed()`; a later
+        `torch.manual_seed` is noticed here and restarts the stream with the new key."""
+        dev = self._flat.device
+        cpu_seed = torch.initial_seed()
+        rng = self._rng
+        if rng is None:
+            rng = self._rng = dict(cpu_seed=cpu_seed, state=torch.tensor(
+                [_engine.derive_sampling_seed(cpu_seed), 0, 0, 0], dtype=torch.int64, device=dev))
+        if rng["state"].device != dev:
+            rng["state"] = rng["state"].to(dev)
+            self._runtime = None     # cached actor programs hold the old device address
+        if rng["cpu_seed"] != cpu_seed:
+            base = int(rng["state"][3].item())
+            rng["state"].copy_(torch.tensor([_engine.derive_sampling_seed(cpu_seed), 0, 0, base], dtype=torch.int64))
+            rng["cpu_seed"] = cpu_seed
+        return rng["state"]
+
+    def set_sampling_shard(self, first_env):
+        """Environment-sharded actors: rank r passes the global index of its first environment, so that identically
+        seeded ranks draw DIFFERENT exploration noise for different environments (counter = first_env + local row)."""
+        self.sampling_state()[3] = int(first_env)
 
     # -- reference surface -----------------------------------------------------
     @property
@@ -217,6 +251,8 @@ class Policy(nn.Module):
         if tuple(inputs.shape[1:]) != s.obs_shape:
             raise ValueError("expected observations of shape [B, %s], got %s" % (s.obs_shape, tuple(inputs.shape)))
         rt.obs_code(inputs)                                   # dtype check
+        if not deterministic:
+            self.sampling_state()                             # notices a re-seeded CPU generator
         if s.recurrent and rnn_hxs.shape[0] != B:
             return self._act_sequence(inputs, rnn_hxs, masks, deterministic)
         with torch.no_grad():
@@ -273,6 +309,8 @@ class Policy(nn.Module):
                 dst.copy_(src)
             return value, action, logp, hout
         rt.obs_code(obs)
+        if not deterministic:
+            self.sampling_state()
         with torch.no_grad():
             plan = rt.act_plan(B, obs.dtype)
             ptrs = {"obs": obs.data_ptr(), "value": value.data_ptr(), "action": action.data_ptr(), "logp": logp.data_ptr()}

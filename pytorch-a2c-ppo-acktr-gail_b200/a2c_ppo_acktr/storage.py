@@ -104,7 +104,8 @@ class RolloutStorage(object):
                 env_chunks = list(env_chunks) + [rest]
         events = []
         for envs in env_chunks:
-            _native.upload_env_columns(self.obs, host, envs, cs)
+            if len(envs):
+                _native.upload_env_columns(self.obs, host, envs, cs)
             ev = torch.cuda.Event()
             ev.record(cs)
             events.append(ev)
@@ -140,7 +141,11 @@ class RolloutStorage(object):
 
     # -- (1) returns / GAE: one reverse-scan kernel (reference storage.py:66-105) --
     def compute_returns(self, next_value, use_gae, gamma, gae_lambda,
-                        use_proper_time_limits=True, schedule=0):
+                        use_proper_time_limits=True, schedule=1):
+        """`schedule` (extension): 1 = env-parallel scan, every fp32 operation in the reference's order -- BIT-IDENTICAL
+        to the reference loop (the default: the drop-in contract); 2 = time-parallel warp scan, re-associated carry,
+        <= 1e-5 relative (faster when N is too small to fill the machine); 0 = pick by shape (2 when N < 16384 and
+        T >= 16)."""
         nv = next_value.detach().to(dtype=torch.float32).reshape(-1).contiguous()
         if nv.numel() != self.rewards.size(1):
             raise ValueError("next_value must hold one value per process")

@@ -4,8 +4,9 @@
 // log-prob to their destinations -- which may be the [step] slots of the rollout buffer (storage.py:46-58), so the
 // per-step softmax / multinomial / gather / copy launches of the reference disappear.
 //
-// Randomness: Philox4x32-10, key = seed, counter = (row, draw, offset_lo, offset_hi).  The stream state
-// {seed, offset, ticket} lives in device memory; the last block of a launch advances offset by one, so replaying the
+// Randomness: Philox4x32-10, key = seed, counter = (row_base + row, draw, offset_lo, offset_hi).  The stream state
+// {seed, offset, ticket, row_base} lives in device memory (row_base = first GLOBAL environment of this rank's shard, so
+// that ranks seeded identically still draw different numbers for different environments); the last block of a launch advances offset by one, so replaying the
 // same op list (or a CUDA graph holding it) keeps drawing fresh numbers without any host involvement.
 // The reference samples with torch.multinomial / torch.normal on the device generator; the draws are a different
 // stream of the SAME distribution (tests: exact against oracle/actor.py on the Philox stream, chi-square against the
@@ -22,7 +23,7 @@ struct SampleDesc {
     float* value_out;          // [B]
     void* action_out;          // int64 [B] (Categorical) | float [B, A] (DiagGaussian)
     float* logp_out;           // [B]
-    unsigned long long* rng;   // device {seed, offset, ticket}
+    unsigned long long* rng;   // device {seed, offset, ticket, row_base}
     int32_t B, A, z_stride, dist, deterministic, pad_;
 };
 
@@ -45,10 +46,11 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 
 __global__ void __launch_bounds__(128)
 sample_actions_kernel(const SampleDesc d) {
-    __shared__ unsigned long long s_seed, s_off;
+    __shared__ unsigned long long s_seed, s_off, s_base;
     if (threadIdx.x == 0) {
         s_seed = d.rng ? d.rng[0] : 0ull;
         s_off = d.rng ? d.rng[1] : 0ull;
+        s_base = d.rng ? d.rng[3] : 0ull;
     }
     __syncthreads();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +69,7 @@ sample_actions_kernel(const SampleDesc d) {
             const float lse = mx + logf(se);
             int act = amax;
             if (!d.deterministic) {
-                uint32_t c[4] = {(uint32_t)b, 0u, (uint32_t)s_off, (uint32_t)(s_off >> 32)};
+                uint32_t c[4] = {(uint32_t)s_base + (uint32_t)b, 0u, (uint32_t)s_off, (uint32_t)(s_off >> 32)};
                 philox4x32_10(c, k0, k1);
                 const float u = u01(c[0]);
                 // inverse CDF over p_j = exp(z_j - lse); the last category absorbs the rounding of the sum
@@ -86,7 +88,7 @@ sample_actions_kernel(const SampleDesc d) {
             for (int a0 = 0; a0 < A; a0 += 4) {
                 float n[4] = {0.f, 0.f, 0.f, 0.f};
                 if (!d.deterministic) {
-                    uint32_t c[4] = {(uint32_t)b, (uint32_t)(a0 >> 2), (uint32_t)s_off, (uint32_t)(s_off >> 32)};
+                    uint32_t c[4] = {(uint32_t)s_base + (uint32_t)b, (uint32_t)(a0 >> 2), (uint32_t)s_off, (uint32_t)(s_off >> 32)};
                     philox4x32_10(c, k0, k1);
                     // Box-Muller on two pairs of uniforms
                     const float r0 = sqrtf(-2.f * logf(u01(c[0]))), r1 = sqrtf(-2.f * logf(u01(c[2])));

@@ -179,6 +179,7 @@ int a2cb_gru_seq(int32_t backward, const a2cb_gru_seq_t* desc, a2cb_stream_t str
                           (cudaStream_t)stream);
 }
 int a2cb_gru_seq_supported(int32_t N, int32_t H) { return gru_persistent_supported(N, H) ? 1 : 0; }
+int a2cb_gru_seq_variant(int32_t N, int32_t H) { return gru_persistent_variant(N, H); }
 
 int a2cb_mlp_fused(int32_t backward, const a2cb_mlp_t* desc, a2cb_stream_t stream) {
     A2CB_REQUIRE(desc, "mlp_fused: null descriptor");

@@ -57,6 +57,7 @@ int gru_op(int which, const GruDesc& d, cudaStream_t st);   // which: 0 init, 1 
 
 // gru_persistent.cu
 bool gru_persistent_supported(int N, int H);
+int gru_persistent_variant(int N, int H);     // 0 SIMT, 1 mma.sync 3xTF32, 2 tcgen05 (gru_tc.cu), -1 unsupported
 int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st);
 
 // tcx.cu / tcx_aux.cu

@@ -735,6 +735,11 @@ bool gru_persistent_supported(int N, int H) {
     return (long)(H / PG_UB) <= (long)pg_sms() * (pf < pb ? pf : pb);
 }
 
+int gru_persistent_variant(int N, int H) {
+    if (!gru_persistent_supported(N, H)) return -1;
+    return pm_enabled(H) ? 1 : 0;
+}
+
 // Cluster launch of the forward kernel when the H / 32 unit groups fit one cluster (H = 512 -> 16 CTAs, the
 // non-portable maximum).  Returns 1 if launched, 0 if this shape / device cannot take it, < 0 on error.
 static int gru_cluster_forward(const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st) {

@@ -130,14 +130,15 @@ def rollout_inputs(cfg, seed=0, env_range=None, N_total=None, obs_uint8=False):
 
 
 def make_rollout(cfg, act_fn, value_fn, hidden_state_size, seed=0, env_range=None, N_total=None,
-                 obs_uint8=False, device="cpu"):
+                 obs_uint8=False, device="cpu", inputs=None):
     """Policy-consistent rollout as a dict named like the RolloutStorage attributes.
 
     act_fn(obs, hxs, masks) -> (value, action, log_prob, hxs); value_fn(obs, hxs, masks) -> value.
     Mirrors the actor loop of reference main.py:113-139 on synthetic observations.
     """
     import torch
-    obs, rewards, masks, bad = rollout_inputs(cfg, seed, env_range, N_total, obs_uint8)
+    # `inputs`: (obs, rewards, masks, bad_masks) already generated by the caller (same generator, same arguments)
+    obs, rewards, masks, bad = inputs if inputs is not None else rollout_inputs(cfg, seed, env_range, N_total, obs_uint8)
     T, n = cfg["T"], obs.shape[1]
     ro = {
         "obs": torch.from_numpy(obs).to(device),

@@ -41,8 +41,8 @@ def main():
     per = cfg["N"] // world
     lo, hi = rank * per, (rank + 1) * per
     torch.manual_seed(1)
-    pol = Policy(cfg["obs_shape"], Discrete(6)).to(dev)
-    st = RolloutStorage(cfg["T"], per, cfg["obs_shape"], Discrete(6), 1, obs_dtype=torch.uint8)
+    pol = Policy(cfg["obs_shape"], Discrete(6), base_kwargs={"recurrent": cfg["recurrent"]}).to(dev)
+    st = RolloutStorage(cfg["T"], per, cfg["obs_shape"], Discrete(6), helpers.hidden_size_of(cfg), obs_dtype=torch.uint8)
     for nme in ("obs", "recurrent_hidden_states", "rewards", "value_preds", "action_log_probs", "actions", "masks",
                 "bad_masks"):
         getattr(st, nme).copy_(ro[nme][:, lo:hi])
@@ -60,6 +60,8 @@ def main():
     agent.set_distributed(world, rank, (lo, hi), cfg["N"])
     torch.manual_seed(7)
     losses = agent.update(st)
+    # recurrent cases (C5s / C5m): the default sharding draws the reference's global randperm(N), so the result is
+    # the reference golden's, minibatch for minibatch
     np.testing.assert_allclose(np.array(losses), case["losses"], rtol=2e-4, atol=2e-6)
     flat = pol._flat.clone()
     ref = flat.clone()
@@ -67,7 +69,7 @@ def main():
     assert torch.equal(flat, ref), "parameters diverged across ranks"
     for k, p in pol.named_parameters():
         helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2, atol=1e-6, what=k, elem_frac=0.1)
-    assert helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters())) <= 2e-3
+    assert helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters())) <= (1e-4 if cfg["recurrent"] else 2e-3)
     dist.barrier()
     if rank == 0:
         print("dist_check ok: case=%s world=%d losses=%s" % (name, world, losses))

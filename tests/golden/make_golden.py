@@ -209,6 +209,10 @@ UPDATE_CASES = {
     "C3u": ("C3", dict(T=8, N=4, ppo_epoch=1, num_mini_batch=2, use_clipped_value_loss=False,
                        use_proper_time_limits=True)),
     "C5s": ("C5", dict(T=8, N=4, ppo_epoch=2, num_mini_batch=2)),
+    # the benchmarked shape: one GPU's C5 shard, T = 128, 256 environments, recurrent minibatches of 64 environments
+    # (8,192 rows); one epoch keeps the reference run short.  Only slot 0 of the hidden states is stored (the update
+    # reads nothing else, reference storage.py:160-161).
+    "C5m": ("C5", dict(T=128, N=256, ppo_epoch=1, num_mini_batch=4)),
     "C2": ("C2", dict()),
     "C2g": ("C2", dict(T=6, N=3, use_gae=True, use_proper_time_limits=True)),
     "C1": ("C1", dict()),
@@ -262,7 +266,10 @@ def case_update(name):
     for k in ("actions", "action_log_probs", "value_preds", "next_value"):
         out["ro_" + k] = ro[k].numpy()
     if cfg["recurrent"]:
-        out["ro_recurrent_hidden_states"] = ro["recurrent_hidden_states"].numpy()
+        if cfg["T"] * cfg["N"] > 4096:
+            out["ro_h0"] = ro["recurrent_hidden_states"][0].numpy()
+        else:
+            out["ro_recurrent_hidden_states"] = ro["recurrent_hidden_states"].numpy()
     out["returns"] = st.returns.numpy().copy()
     out["obs_sum"] = np.array(ro["obs"].double().sum().item())
     for k, v in pol.state_dict().items():

@@ -58,10 +58,18 @@ def hidden_size_of(cfg):
     return 512 if len(cfg["obs_shape"]) == 3 else 64
 
 
+_INPUT_CACHE = {}        # the counter-based generator costs ~1 min for a C5-sized rollout: reuse across parametrisations
+
+
 def rollout_from_case(case, cfg, obs_uint8=False, device="cpu"):
     """Rebuilds the rollout the golden file was produced from: frames/signals from the
     counter-based generator, policy outputs (actions, log-probs, values) from the file."""
-    obs, rewards, masks, bad = synthetic.rollout_inputs(cfg, seed=0, obs_uint8=obs_uint8)
+    key = (cfg["kind"], cfg["T"], cfg["N"], tuple(cfg["obs_shape"]), bool(obs_uint8))
+    if key not in _INPUT_CACHE:
+        if len(_INPUT_CACHE) >= 2:
+            _INPUT_CACHE.clear()
+        _INPUT_CACHE[key] = synthetic.rollout_inputs(cfg, seed=0, obs_uint8=obs_uint8)
+    obs, rewards, masks, bad = (a.copy() if a.nbytes < (64 << 20) else a for a in _INPUT_CACHE[key])
     T, N = cfg["T"], cfg["N"]
     H = hidden_size_of(cfg)
     ro = {
@@ -75,7 +83,11 @@ def rollout_from_case(case, cfg, obs_uint8=False, device="cpu"):
         "next_value": torch.from_numpy(case["ro_next_value"]),
         "returns": torch.zeros(T + 1, N, 1),
     }
-    if cfg["recurrent"]:
+    if cfg["recurrent"] and "ro_h0" in case:
+        # large recurrent cases store slot 0 only: the update reads nothing else (reference storage.py:160-161)
+        ro["recurrent_hidden_states"] = torch.zeros(T + 1, N, H)
+        ro["recurrent_hidden_states"][0].copy_(torch.from_numpy(case["ro_h0"]))
+    elif cfg["recurrent"]:
         ro["recurrent_hidden_states"] = torch.from_numpy(case["ro_recurrent_hidden_states"])
     else:
         ro["recurrent_hidden_states"] = torch.zeros(T + 1, N, H)

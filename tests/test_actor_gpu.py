@@ -26,7 +26,7 @@ class Box(object):
 
 
 def _set_rng(rt, seed, offset):
-    rt.rng_state().copy_(torch.tensor([seed, offset, 0], dtype=torch.int64))
+    rt.rng_state().copy_(torch.tensor([seed, offset, 0, 0], dtype=torch.int64))
 
 
 @pytest.mark.parametrize("B", [1, 77, 4096])
@@ -49,10 +49,10 @@ def test_categorical_head_vs_oracle(B):
         assert torch.equal(val.view(-1).cpu(), torch.from_numpy(v))
         same = got == a
         np.testing.assert_allclose(lp.view(-1).cpu().numpy()[same], logp[same], rtol=1e-5, atol=1e-6)
-    assert rt.rng_state().cpu().tolist() == [seed, 2, 0]
+    assert rt.rng_state().cpu().tolist() == [seed, 2, 0, 0]
     rt.sample(z, act, val, lp, True)
     assert torch.equal(act.view(-1), z[:, 1:].argmax(1))
-    assert rt.rng_state().cpu().tolist() == [seed, 2, 0]     # the mode draws nothing
+    assert rt.rng_state().cpu().tolist() == [seed, 2, 0, 0]     # the mode draws nothing
 
 
 def test_categorical_head_frequencies():
@@ -156,3 +156,42 @@ def test_act_into_graph_replay_matches_eager_and_keeps_sampling():
         draws.append(pol.act_into(st, 0)[1].clone())
     assert rt.rng_state().cpu().tolist()[1] == 7
     assert any(not torch.equal(draws[0], d) for d in draws[1:])
+
+
+def test_sampling_stream_is_sharded_persistent_and_reseedable(tmp_path):
+    """identically seeded ranks must not draw identical noise for their local environment i (the Philox
+    counter carries the GLOBAL environment index), the stream must survive pickling / device moves / re-flattening,
+    and a later torch.manual_seed must take effect."""
+    torch.manual_seed(5)
+    pol = Policy((11,), Discrete(6)).to(DEV)
+    rt = pol.runtime()
+    B = 64
+    z = (torch.randn(B, 7) * 2.0).to(DEV)
+    act = torch.zeros(B, 1, dtype=torch.int64, device=DEV)
+    val, lp = torch.zeros(B, 1, device=DEV), torch.zeros(B, 1, device=DEV)
+    seed = int(pol.sampling_state()[0].item())
+    from a2c_ppo_acktr import _engine
+    assert seed == _engine.derive_sampling_seed(5)
+    rt.sample(z, act, val, lp, False)
+    a_rank0 = act.clone()
+    # "rank 1": same seed, same offset, environments 64..127
+    pol.sampling_state()[1] = 0
+    pol.set_sampling_shard(64)
+    rt.sample(z, act, val, lp, False)
+    v, a, logp, u, cdf = actor.categorical(z.cpu().numpy(), seed, 0, row_base=64)
+    near = (np.abs(u[:, None] - cdf).min(1) < 1e-5)
+    assert np.array_equal(act.view(-1).cpu().numpy()[~near], a[~near])
+    assert not torch.equal(act, a_rank0)
+    assert pol.sampling_state().cpu().tolist() == [seed, 1, 0, 64]
+    # survives re-flattening (a new runtime) and pickling
+    pol._flatten()
+    assert pol.runtime() is not rt and pol.runtime().rng_state().cpu().tolist() == [seed, 1, 0, 64]
+    path = tmp_path / "p.pt"
+    torch.save([pol, None], path)
+    pol2, _ = torch.load(path, weights_only=False)
+    assert pol2.runtime().rng_state().cpu().tolist() == [seed, 1, 0, 64]
+    # re-seeding restarts the stream under the new key, keeping the shard offset
+    torch.manual_seed(6)
+    obs = torch.randn(4, 11, device=DEV)
+    pol.act(obs, torch.zeros(4, 1, device=DEV), torch.ones(4, 1, device=DEV))
+    assert pol.sampling_state().cpu().tolist() == [_engine.derive_sampling_seed(6), 1, 0, 64]

@@ -38,6 +38,29 @@ def test_shard_epoch_padding_and_capacity():
         assert not idx[k, counts[k]:].any()
 
 
+def test_shard_env_chunks_partition_property():
+    """Recurrent minibatches of the ONE global randperm(N) (reference storage.py:152): the shards' pieces of every
+    chunk are disjoint, cover it, and keep the permutation's order."""
+    N, nmb = 64, 4
+    perm = torch.randperm(N).numpy()
+    shards = [_dist.ShardInfo(4, r, 16 * r, 16 * (r + 1), N) for r in range(4)]
+    pieces = [_dist.shard_env_chunks(perm, N // nmb, nmb, sh) for sh in shards]
+    for k in range(nmb):
+        chunk = perm[k * 16:(k + 1) * 16].tolist()
+        merged = [int(e) + sh.lo for sh, pc in zip(shards, pieces) for e in pc[k]]
+        assert sorted(merged) == sorted(chunk)
+        for sh, pc in zip(shards, pieces):
+            assert [int(e) + sh.lo for e in pc[k]] == [e for e in chunk if sh.lo <= e < sh.hi]
+    sh = _dist.ShardInfo(8, 3, 768, 1024, 2048)
+    cap = _dist.env_capacity(512, sh, 4)
+    assert 64 < cap <= 112 and cap % 4 == 0
+    counts = [len(c) for _ in range(200) for c in _dist.shard_env_chunks(torch.randperm(2048).numpy(), 512, 4, sh)]
+    assert max(counts) <= cap and abs(np.mean(counts) - 64) < 2
+    assert _dist.round_up_envs(0, 4) == 4 and _dist.round_up_envs(65, 4) == 68 and _dist.round_up_envs(3, 1) == 3
+    small = _dist.ShardInfo(2, 0, 0, 2, 4)
+    assert _dist.env_capacity(2, small, 1) == 2
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -258,10 +258,13 @@ def test_adv_normalize_vs_torch():
 
 
 # ---- persistent whole-sequence GRU (csrc/gru_persistent.cu) against torch autograd -------------------
-@pytest.mark.parametrize("T,N,H", [(5, 3, 128), (16, 64, 512), (7, 77, 256), (4, 130, 128)])
-def test_gru_persistent_vs_torch(T, N, H):
+@pytest.mark.parametrize("T,N,H,p_done", [(5, 3, 128, 0.2), (16, 64, 512, 0.2), (7, 77, 256, 0.2), (4, 130, 128, 0.2),
+                                          (128, 64, 512, 0.01), (128, 8, 512, 0.0), (128, 150, 512, 0.01)])
+def test_gru_persistent_vs_torch(T, N, H, p_done):
     """a2cb_gru_seq forward and backward-through-time on the masked recurrence of model.py:111-166;
-    N covers partial warps, partial 64-environment blocks and more than one block."""
+    N covers partial warps, partial 64-environment blocks and more than one block.  The T = 128 cases are the
+    benchmarked C5 minibatch shape (64 environments, H = 512, episodes ~100 steps long: a 128-step BPTT chain), a
+    single environment group without any episode boundary, and more groups than resident CTA groups."""
     import ctypes
     from a2c_ppo_acktr import _engine as E
     if not E.gru_seq_supported(N, H):
@@ -271,7 +274,7 @@ def test_gru_persistent_vs_torch(T, N, H):
     Whh = torch.randn(3 * H, H, generator=g) / H ** 0.5
     bhh = torch.randn(3 * H, generator=g) * 0.1
     h0 = torch.randn(N, H, generator=g)
-    masks = (torch.rand(T * N, generator=g) > 0.2).float()
+    masks = (torch.rand(T * N, generator=g) >= p_done).float()
     dout = torch.randn(T * N, H, generator=g)
 
     # fp64 reference with autograd

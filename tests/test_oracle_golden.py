@@ -123,7 +123,7 @@ def test_policy_matches_reference(tag):
     np.testing.assert_allclose(lp2.numpy(), g[tag + "_sample_logp"], **tol)
 
 
-UPDATE_SMALL = ["C1s", "C3s", "C3u", "C5s", "C2", "C2g"]
+UPDATE_SMALL = ["C1s", "C3s", "C3u", "C5s", "C2", "C2g", "C5m"]      # C5m: the benchmarked shape (128 x 256, 4 steps)
 UPDATE_FULL = ["C1", "C3"]
 
 
