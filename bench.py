@@ -195,17 +195,34 @@ def run_ours(args):
     obs_dtype = torch.uint8 if cfg["kind"] == "atari" else torch.float32
 
     # ---- synthetic rollout: frames on the host, policy outputs from Policy.act on the device ----
+    # Atari-shaped workloads use the frame-ring format by default (--stacked-frames: the round-1 layout): every 84 x 84
+    # frame is generated and stored ONCE, observation t is the rolling stack of frames t .. t + 3 with the stack cleared
+    # where an episode ended (reference envs.py:218-259) -- a quarter of the bytes on the host link and in HBM.
     torch.manual_seed(2 + rank)
-    obs_np, rew_np, mask_np, bad_np = synthetic.rollout_inputs(cfg, 0, env_range, N_total, obs_uint8=(obs_dtype == torch.uint8))
-    host = {
-        "obs": torch.from_numpy(obs_np).pin_memory(),
+    ring = cfg["kind"] == "atari" and not args.stacked_frames
+    if ring:
+        C = cfg["obs_shape"][0]
+        fr_np = synthetic.atari_frames(T + C, N_total, 0, env_range, (1,) + tuple(cfg["obs_shape"][1:]))
+        fr_np = fr_np.reshape((T + C, Nloc) + tuple(cfg["obs_shape"][1:]))
+        rew_np, mask_np, bad_np = synthetic.atari_signals(T, N_total, 0, env_range)
+        valid_np = np.ones((T + 1, Nloc), np.uint8)
+        valid_np[0] = C
+        for t in range(T):
+            valid_np[t + 1] = np.where(mask_np[t + 1, :, 0] == 0, 1, np.minimum(valid_np[t].astype(np.int64) + 1, C))
+        host = {"frames": torch.from_numpy(fr_np).pin_memory(), "stack_valid": torch.from_numpy(valid_np).pin_memory()}
+        obs_key = ("frames", "stack_valid")
+    else:
+        obs_np, rew_np, mask_np, bad_np = synthetic.rollout_inputs(cfg, 0, env_range, N_total, obs_uint8=(obs_dtype == torch.uint8))
+        host = {"obs": torch.from_numpy(obs_np).pin_memory()}
+        obs_key = ("obs",)
+    host.update({
         "rewards": torch.from_numpy(rew_np).pin_memory(),
         "masks": torch.from_numpy(mask_np).pin_memory(),
         "bad_masks": torch.from_numpy(bad_np).pin_memory(),
-    }
-    st = RolloutStorage(T, Nloc, cfg["obs_shape"], space(cfg["action"]), H, obs_dtype=obs_dtype)
+    })
+    st = RolloutStorage(T, Nloc, cfg["obs_shape"], space(cfg["action"]), H, obs_dtype=obs_dtype, frame_ring=ring)
     st.to(dev)
-    for k in ("obs", "rewards", "masks", "bad_masks"):
+    for k in obs_key + ("rewards", "masks", "bad_masks"):
         getattr(st, k).copy_(host[k])
     with torch.no_grad():
         for t in range(T):
@@ -219,6 +236,8 @@ def run_ours(args):
         host[k] = getattr(st, k).cpu().pin_memory()
     host["next_value"] = next_value.cpu().pin_memory()
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    rollout_keys = obs_key + ("rewards", "masks", "bad_masks", "actions", "action_log_probs", "value_preds",
+                              "recurrent_hidden_states")
 
     if cfg["algo"] == "ppo":
         agent = algo.PPO(policy, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
@@ -236,16 +255,14 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def upload():
-        for k in ("obs", "rewards", "masks", "bad_masks", "actions", "action_log_probs", "value_preds",
-                  "recurrent_hidden_states"):
+        for k in rollout_keys:
             getattr(st, k).copy_(host[k], non_blocking=True)
         return host["next_value"].to(dev, non_blocking=True)
 
     def upload_e2e():
         """The public ingest call: narrow tensors now, frames pulled by update() on a side stream (recurrent PPO:
         per minibatch environment set, so that the upload overlaps the compute of earlier minibatches)."""
-        st.stage_host({k: host[k] for k in ("obs", "rewards", "masks", "bad_masks", "actions", "action_log_probs",
-                                            "value_preds", "recurrent_hidden_states")})
+        st.stage_host({k: host[k] for k in rollout_keys})
         return host["next_value"].to(dev, non_blocking=True)
 
     def hot_path(nv):
@@ -321,7 +338,8 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: %s" % (cfg["name"], describe(cfg)), "envs_per_gpu": Nloc, "num_steps": T,
                        "recurrent_sharding": (getattr(agent, "recurrent_sharding", None) if (world > 1 and cfg.get("recurrent")) else None),
-                       "obs": "uint8 4x84x84" if obs_dtype == torch.uint8 else "fp32", "l2": "flushed between steps (256 MiB write)",
+                       "obs": ("uint8 frame ring (each 84x84 frame stored once, 4-stacks assembled on the device)" if ring
+                               else "uint8 4x84x84 stacks" if obs_dtype == torch.uint8 else "fp32"), "l2": "flushed between steps (256 MiB write)",
                        "step": "compute_returns + update + after_update"},
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 12},
@@ -334,10 +352,11 @@ def run_ours(args):
             out["kernels"] = kernels
         if scan:
             out["scan"] = scan
-        if world == 1 and cfg["name"] == "C5" and Nloc == 256:
-            out["parity"] = golden_parity_check(cfg, obs_np, dev)
+        if world == 1 and cfg["name"] == "C5" and Nloc == 256 and not args.no_parity:
+            out["parity"] = golden_parity_check(cfg, None if ring else obs_np, dev)
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(cfg, (obs_np, rew_np, mask_np, bad_np))
+            stacks_np = st.obs[:].cpu().numpy() if ring else obs_np       # the oracle port reads stacked fp32 observations
+            out["cpu_baseline"] = cpu_baseline(cfg, (stacks_np, rew_np, mask_np, bad_np))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -360,6 +379,8 @@ def golden_parity_check(cfg, obs_np, dev):
         case = {k: z[k] for k in z.files}
     g = json.loads(str(case["config"]))
     T, N = g["T"], g["N"]
+    if obs_np is None:             # the bench itself runs on ring frames: regenerate the golden's independent stacks
+        obs_np = synthetic.atari_frames(T + 1, N, 0, None, tuple(g["obs_shape"]))
     assert (T, N) == (cfg["T"], cfg["N"]) and abs(float(obs_np.astype(np.float64).sum()) - float(case["obs_sum"])) < 1e-3
     torch.manual_seed(1)
     pol = Policy(tuple(g["obs_shape"]), Discrete(6), base_kwargs={"recurrent": True}).to(dev)
@@ -684,6 +705,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C5", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the first-update check against the reference golden (C5)")
+    ap.add_argument("--stacked-frames", action="store_true",
+                    help="Atari workloads: store / upload full 4-frame stacks (reference layout) instead of the frame ring")
     ap.add_argument("--envs", type=int, default=0, help="override the number of environments per GPU")
     ap.add_argument("--recurrent-sharding", default="", choices=["", "global", "stratified"],
                     help="N > 1, recurrent PPO: 'global' (default) = the reference's one randperm(N_total); "

@@ -430,7 +430,11 @@ typedef struct { float* img; float* img_lo; const float* src; int64_t N, K; cons
 typedef struct { float* out; float* out_lo; const void* frames; const int64_t* idx; int32_t src_is_u8, B, C, H, W, S;
                  void* out_b16; /* optional bf16 copy of out (uint8 frames are exact in bf16) */
                  int32_t scatter; /* 1: image b is written to slot idx[b] of out (in-place re-layout of a row subset) */
-                 int32_t pad_; } a2cb_tcx_s2d_t;
+                 int32_t ring_n;  /* frame ring (valid != NULL): environments per ring slot */
+                 const uint8_t* valid; /* frame ring: frames = uint8 [slots, ring_n, 84, 84], each frame stored ONCE; the stack
+                                          of row (t, n) is slots t .. t + 3, of which the newest valid[row] (1..4) are real and
+                                          the older ones read as zero (a2c_ppo_acktr/envs.py:218-259 VecPyTorchFrameStack) */
+               } a2cb_tcx_s2d_t;
 typedef struct { float* part; const float* x; int64_t rows; int64_t pitch; int32_t C; int32_t pad_; float* lo; } a2cb_tcx_colsum_t;
 typedef struct { float* part; const float* x; const float* gy; int64_t rows; int32_t K, N, gy_stride, pad_; } a2cb_tcx_narrow_wgrad_t;
 typedef struct { const a2cb_tcx_prep_job_t* jobs; int64_t total; int32_t n_jobs; int32_t pad_; } a2cb_tcx_prep_multi_t;
@@ -481,6 +485,9 @@ int a2cb_gru_seq_supported(int32_t N, int32_t H);
 /* which kernel pair a2cb_gru_seq runs for this shape: 0 fp32 SIMT, 1 mma.sync 3xTF32, 2 tcgen05 (fp16 hi/lo operand
  * pairs, state exchanged as shared-memory images), -1 unsupported */
 int a2cb_gru_seq_variant(int32_t N, int32_t H);
+/* selects the kernel family of a2cb_gru_seq: 2 (default) tcgen05 where the shape allows, 1 mma.sync, 0 fp32 SIMT,
+ * < 0 back to the default / environment (A2CB_GRU_MODE) */
+int a2cb_set_gru_mode(int32_t mode);
 
 /* ---------------------------------------------------------------------------
  * (5) ACKTR / KFAC helpers                              a2c_ppo_acktr/algo/kfac.py

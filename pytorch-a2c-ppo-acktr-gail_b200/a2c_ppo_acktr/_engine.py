@@ -450,8 +450,11 @@ class NetBuilder(object):
     """Builds forward / backward plan lists for one policy spec and one batch size."""
 
     def __init__(self, spec, layout, B, obs_buf, obs_code, gather, tag, seq=None, masks=("masks_in", 0),
-                 hxs=("hxs_in", 0), keep_gates=True, allow_tcx=True, full_rows=0, allow_mlp_fused=True):
+                 hxs=("hxs_in", 0), keep_gates=True, allow_tcx=True, full_rows=0, allow_mlp_fused=True, ring=None):
         self.spec, self.L, self.B = spec, layout, B
+        # frame ring (RolloutStorage(frame_ring=True)): obs_buf holds uint8 [slots, ring_n, 84, 84] frames stored once,
+        # ring = ((arena name, offset) of the per-row valid counts, ring_n)
+        self.ring = ring
         # recurrent policies see the batch as a [T, N] sequence, rows time-major (model.py:119-126)
         self.seqT, self.seqN = seq if seq is not None else (1, B)
         assert self.seqT * self.seqN == B
@@ -483,6 +486,9 @@ class NetBuilder(object):
                 and _native.lib().a2cb_get_gemm_mode() != 0 and os.environ.get("A2CB_TCX", "1") != "0"):
             from . import _tcx
             self.tcx = _tcx.CnnNet(self)
+        if ring is not None and self.tcx is None:
+            raise _native.NativeError("a frame-ring rollout is read by the TMA-fed engine only (4 x 84 x 84 uint8 stacks, "
+                                      "hidden size a multiple of 256, gemm mode != 0)")
 
     def n(self, name):
         return self.t + name
@@ -1104,9 +1110,24 @@ class PolicyRuntime(object):
         buffer re-allocates it under the programs that already point at it."""
         s = self.spec
         T, N = storage.rewards.shape[0], storage.rewards.shape[1]
-        obs_flat = storage.obs[:-1].view(T * N, *storage.obs.shape[2:])
-        code = self.obs_code(obs_flat)
-        self.arena.bind("obs_st", obs_flat.view(-1))
+        ring = None
+        if getattr(storage, "frame_ring", False) and not use_idx:
+            # full-batch programs (A2C): the stacks are materialised into an arena buffer by the caller before every
+            # run (`stage_ring_batch`); the batches of these algorithms are a few hundred rows
+            code = 1
+            self.stage_ring_batch(storage)
+        elif getattr(storage, "frame_ring", False):
+            # every frame stored once: the frame re-layout kernel assembles the 4-stacks from the ring
+            if tuple(storage.obs.shape[2:]) != s.obs_shape:
+                raise _native.NativeError("frame ring: observation shape not supported")
+            code = 1
+            self.arena.bind("obs_st", storage.frames.view(-1))
+            self.arena.bind("obs_valid", storage.stack_valid.view(-1))
+            ring = (("obs_valid", 0), N)
+        else:
+            obs_flat = storage.obs[:-1].view(T * N, *storage.obs.shape[2:])
+            code = self.obs_code(obs_flat)
+            self.arena.bind("obs_st", obs_flat.view(-1))
         tag = tag or "t%d_" % mbs
         kw = {}
         if s.recurrent:
@@ -1119,7 +1140,7 @@ class PolicyRuntime(object):
             else:
                 self.arena.bind("hxs_mb", storage.recurrent_hidden_states[0].contiguous().view(-1))
             kw = dict(seq=seq, masks=("masks_st", 0), hxs=("hxs_mb", 0))
-        nb = NetBuilder(s, self.L, mbs, "obs_st", code, use_idx, tag, full_rows=T * N if use_idx else 0, **kw)
+        nb = NetBuilder(s, self.L, mbs, "obs_st", code, use_idx, tag, full_rows=T * N if use_idx else 0, ring=ring, **kw)
         fwd = nb.forward_plans()
         bwd = nb.backward_plans() if with_backward else []
         if nb.tcx is not None:
@@ -1172,6 +1193,13 @@ class PolicyRuntime(object):
                 prog.prologue_chunk.add_plan(p, self.arena)
             prog.prologue_chunk.finalize()
         return prog
+
+    def stage_ring_batch(self, storage):
+        """Frame-ring rollout read by a full-batch program: materialises observation slots [0, T) as stacked uint8 rows
+        in the arena buffer the program was built against (same address every update)."""
+        flat = self.arena.stage("obs_ring_flat", storage.obs[:-1])
+        self.arena.bind("obs_st", flat)
+        return flat
 
     def acktr_programs(self, storage, hyper, noise, inv_B=None):
         """ACKTR's three passes over the FULL batch (reference a2c_acktr.py:38-72) as separate programs:

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "a2cb_gather_rows": (c_int, [ctypes.POINTER(GatherField), c_int, c_void_p, c_i64, c_int, c_i64, c_i64, c_void_p]),
     "a2cb_upload_env_columns": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_int, c_void_p]),
     "a2cb_gru_seq_variant": (c_int, [c_int, c_int]),
+    "a2cb_set_gru_mode": (c_int, [c_int]),
 }
 
 _lib = None
@@ -83,6 +84,11 @@ def check(rc, what):
 def set_gemm_mode(mode):
     """0: exact-fp32 SIMT engine; 1: tcgen05 3xTF32 engine everywhere; 2: automatic choice (default)."""
     check(lib().a2cb_set_gemm_mode(int(mode)), "a2cb_set_gemm_mode")
+
+
+def set_gru_mode(mode):
+    """Kernel family of the persistent GRU recurrence: 2 tcgen05 (default), 1 mma.sync 3xTF32, 0 fp32 SIMT, -1 default."""
+    check(lib().a2cb_set_gru_mode(int(mode)), "a2cb_set_gru_mode")
 
 
 def gru_seq_variant(N=64, H=512):

@@ -49,7 +49,8 @@ class PrepDesc(ctypes.Structure):
 
 class S2dDesc(ctypes.Structure):
     _fields_ = [("out", c_vp), ("out_lo", c_vp), ("frames", c_vp), ("idx", c_vp), ("src_is_u8", c_i32), ("B", c_i32),
-                ("C", c_i32), ("H", c_i32), ("W", c_i32), ("S", c_i32), ("out_b16", c_vp), ("scatter", c_i32), ("pad_", c_i32)]
+                ("C", c_i32), ("H", c_i32), ("W", c_i32), ("S", c_i32), ("out_b16", c_vp), ("scatter", c_i32), ("ring_n", c_i32),
+                ("valid", c_vp)]
 
 
 class ColsumDesc(ctypes.Structure):
@@ -447,9 +448,13 @@ class CnnNet(object):
         # ---- frames -> space-to-depth ----
         frames, is_u8, gather = (nb.obs, 0), nb.obs_code == 1, nb.gather
 
+        ring = getattr(nb, "ring", None)
+        ring_valid, ring_n = ring if ring is not None else (None, 0)
+        assert ring is None or (self.full_rows and is_u8), "the frame ring feeds whole-rollout training programs"
+
         def make_s2d(arena):
             return S2dDesc(arena.ptr(x0), arena.ptr(x0_lo), arena.ptr(frames), None, 1 if is_u8 else 0, n_img, 4, 84, 84, 4,
-                           arena.ptr(x0b))
+                           arena.ptr(x0b), 0, ring_n, arena.ptr(ring_valid))
         s2d = TcxOp(OP_TCX_S2D, make_s2d, "frames_s2d", runtime_idx=gather and not self.full_rows)
         s2d.spec = dict(out=x0, out_lo=x0_lo, frames=frames, n_img=n_img)
         if self.full_rows:
@@ -457,7 +462,7 @@ class CnnNet(object):
 
             def make_s2d_chunk(arena):
                 return S2dDesc(arena.ptr(x0), arena.ptr(x0_lo), arena.ptr(frames), None, 1 if is_u8 else 0, B, 4, 84, 84, 4,
-                               arena.ptr(x0b), 1, 0)
+                               arena.ptr(x0b), 1, ring_n, arena.ptr(ring_valid))
             chunk = TcxOp(OP_TCX_S2D, make_s2d_chunk, "frames_s2d_chunk", runtime_idx=True)
             chunk.spec = dict(out=x0, out_lo=x0_lo, frames=frames, n_img=B, scatter=True)
             self.prologue_chunk.append(chunk)

@@ -90,6 +90,8 @@ class A2C_ACKTR():
             self._prog, self._opt_prog, self._prog_key = prog, opt, key
         prog, opt = self._prog, self._opt_prog
         launches0 = _native.launch_count()
+        if getattr(rollouts, "frame_ring", False):
+            rt.stage_ring_batch(rollouts)            # the program reads materialised stacks at a fixed address
         self.optimizer.configure(opt.optim_desc)
         prog.run()
         if sh is not None:

@@ -294,7 +294,9 @@ class Policy(nn.Module):
         wait = getattr(rollouts, "wait_staged", None)
         if wait is not None:
             wait()
-        obs, hxs, masks = rollouts.obs[step], rollouts.recurrent_hidden_states[step], rollouts.masks[step]
+        # frame ring: the slot's stack is assembled in a persistent staging tensor (stable address for the graph)
+        obs = rollouts.ring_stack(step) if getattr(rollouts, "frame_ring", False) else rollouts.obs[step]
+        hxs, masks = rollouts.recurrent_hidden_states[step], rollouts.masks[step]
         value, action = rollouts.value_preds[step], rollouts.actions[step]
         logp, hout = rollouts.action_log_probs[step], rollouts.recurrent_hidden_states[step + 1]
         B = obs.shape[0]

@@ -16,6 +16,13 @@ bytes to fp32/255 while loading.  The default (fp32) keeps the reference contrac
 narrow tensors are copied at once, the frames are pulled on a side stream --
 per minibatch environment set by the recurrent PPO update, so that the upload of
 later minibatches overlaps the compute of earlier ones.
+`frame_ring=True` (uint8 Atari stacks only) stores every 84 x 84 frame ONCE: the reference's
+`VecPyTorchFrameStack` (envs.py:218-259) rolls a 4-frame stack, so consecutive observations
+share three of their four frames.  `frames[t + c]` is channel c of observation slot t and
+`stack_valid[t]` (1..4) says how many of the newest frames of slot t are real (the stack is
+cleared when an episode ends) -- a quarter of the HBM footprint and of the host upload; the
+update's frame re-layout kernel reads the ring directly (csrc/tcx_aux.cu).  `obs` stays
+readable / assignable per slot for the reference's call sites.
 """
 import torch
 
@@ -27,14 +34,90 @@ def _space_is_discrete(action_space):
     return action_space.__class__.__name__ == 'Discrete'
 
 
+class _RingSlot(torch.Tensor):
+    """Materialised stack of ONE observation slot of a frame-ring rollout: a plain tensor for every reader, whose
+    in-place `copy_` writes through to the ring (`rollouts.obs[0].copy_(obs)`, reference main.py:97)."""
+
+    @staticmethod
+    def make(data, storage, slot):
+        t = torch.Tensor._make_subclass(_RingSlot, data)
+        t._ring, t._slot = storage, slot
+        return t
+
+    def copy_(self, src, non_blocking=False):
+        self._ring._write_stack(self._slot, src)
+        return super(_RingSlot, self).copy_(src, non_blocking)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        with torch._C.DisableTorchFunctionSubclass():
+            out = func(*args, **(kwargs or {}))
+        return out
+
+
+class _RingObs(object):
+    """`rollouts.obs` of a frame-ring rollout: indexable like the [T + 1, N, C, H, W] tensor it stands for."""
+
+    def __init__(self, storage):
+        self._s = storage
+
+    def __getitem__(self, key):
+        s = self._s
+        n_slots = s.stack_valid.shape[0]
+        if isinstance(key, int):
+            t = key + n_slots if key < 0 else key
+            return _RingSlot.make(s._stacks(t, t + 1)[0], s, t)
+        if isinstance(key, slice):
+            lo, hi, step = key.indices(n_slots)
+            assert step == 1, "frame ring: only contiguous slot ranges"
+            return s._stacks(lo, hi)
+        raise TypeError("frame ring: index observation slots with an int or a slice")
+
+    def __len__(self):
+        return self._s.stack_valid.shape[0]
+
+    def size(self, *a):
+        return self.shape if not a else self.shape[a[0]]
+
+    @property
+    def shape(self):
+        s = self._s
+        return torch.Size((s.stack_valid.shape[0], s.frames.shape[1], s._ring_c) + tuple(s.frames.shape[2:]))
+
+    @property
+    def dtype(self):
+        return torch.uint8
+
+    @property
+    def device(self):
+        return self._s.frames.device
+
+    def data_ptr(self):
+        return self._s.frames.data_ptr()
+
+    def fill_(self, v):
+        self._s.frames.fill_(v)
+        self._s.stack_valid.fill_(self._s._ring_c)
+        return self
+
+
 class RolloutStorage(object):
     _MOVABLE = ('obs', 'recurrent_hidden_states', 'rewards', 'value_preds', 'returns',
                 'action_log_probs', 'actions', 'masks', 'bad_masks')
 
     def __init__(self, num_steps, num_processes, obs_shape, action_space,
-                 recurrent_hidden_state_size, obs_dtype=torch.float32):
+                 recurrent_hidden_state_size, obs_dtype=torch.float32, frame_ring=False):
         T, N = num_steps, num_processes
-        self.obs = torch.zeros(T + 1, N, *obs_shape, dtype=obs_dtype)
+        self.frame_ring = bool(frame_ring)
+        if self.frame_ring:
+            if len(obs_shape) != 3 or obs_dtype != torch.uint8:
+                raise ValueError("frame_ring stores uint8 image stacks [C, H, W]")
+            self._ring_c = int(obs_shape[0])
+            self.frames = torch.zeros(T + self._ring_c, N, *obs_shape[1:], dtype=torch.uint8)
+            self.stack_valid = torch.ones(T + 1, N, dtype=torch.uint8)
+            self._MOVABLE = ('frames', 'stack_valid') + tuple(k for k in RolloutStorage._MOVABLE if k != 'obs')
+        else:
+            self.obs = torch.zeros(T + 1, N, *obs_shape, dtype=obs_dtype)
         self.recurrent_hidden_states = torch.zeros(T + 1, N, recurrent_hidden_state_size)
         self.rewards = torch.zeros(T, N, 1)
         self.value_preds = torch.zeros(T + 1, N, 1)
@@ -53,6 +136,37 @@ class RolloutStorage(object):
         self._idx_cache = None
         self._staged_obs = None          # pinned host frames whose upload has not been started yet
         self._copy_stream = None
+
+    # -- frame ring --------------------------------------------------------
+    def __getattr__(self, name):
+        # `obs` of a frame-ring rollout is a view object (the attribute only exists in stacked mode)
+        if name == "obs" and self.__dict__.get("frame_ring"):
+            return _RingObs(self)
+        raise AttributeError(name)
+
+    def _stacks(self, lo, hi):
+        """Materialised observation stacks of slots [lo, hi): uint8 [hi - lo, N, C, H, W] (a copy)."""
+        C = self._ring_c
+        out = torch.stack([self.frames[lo + c:hi + c] for c in range(C)], dim=2)
+        keep = torch.arange(C, device=out.device).view(1, 1, C) >= (C - self.stack_valid[lo:hi].long().unsqueeze(-1))
+        return out * keep.view(hi - lo, -1, C, 1, 1).to(out.dtype)
+
+    def _write_stack(self, slot, src):
+        """Stores a full stack [N, C, H, W] at `slot` (all C frames as given: valid = C)."""
+        C = self._ring_c
+        src = src.to(self.frames.device)
+        for c in range(C):
+            self.frames[slot + c].copy_(src[:, c])
+        self.stack_valid[slot].fill_(C)
+
+    def ring_stack(self, slot):
+        """Stack of `slot` in a persistent staging tensor (stable address: Policy.act_into replays CUDA graphs)."""
+        st = self.__dict__.get("_ring_stage")
+        if st is None or st.device != self.frames.device:
+            st = self._ring_stage = torch.zeros((self.frames.shape[1], self._ring_c) + tuple(self.frames.shape[2:]),
+                                                dtype=torch.uint8, device=self.frames.device)
+        st.copy_(self._stacks(slot, slot + 1)[0])
+        return st
 
     # -- placement ---------------------------------------------------------
     def to(self, device):
@@ -74,9 +188,9 @@ class RolloutStorage(object):
             dst = getattr(self, name)
             if tuple(src.shape) != tuple(dst.shape) or src.dtype != dst.dtype:
                 raise ValueError("stage_host: %s must be %s %s" % (name, tuple(dst.shape), dst.dtype))
-            if name == "obs":
+            if name == ("frames" if self.frame_ring else "obs"):
                 if not src.is_pinned() or not src.is_contiguous():
-                    raise _native.NativeError("stage_host: obs must be a contiguous pinned host tensor")
+                    raise _native.NativeError("stage_host: %s must be a contiguous pinned host tensor" % name)
                 self._staged_obs = src
             else:
                 dst.copy_(src, non_blocking=True)
@@ -87,12 +201,13 @@ class RolloutStorage(object):
         host, self._staged_obs = self._staged_obs, None
         if host is None:
             return None
-        dev = self.obs.device
+        frames = self.frames if self.frame_ring else self.obs
+        dev = frames.device
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         cs = self._copy_stream
         cs.wait_stream(torch.cuda.current_stream(dev))      # earlier readers / writers of obs are done
-        N = self.obs.shape[1]
+        N = frames.shape[1]
         if env_chunks is None:
             env_chunks = [torch.arange(N)]
         else:
@@ -105,7 +220,7 @@ class RolloutStorage(object):
         events = []
         for envs in env_chunks:
             if len(envs):
-                _native.upload_env_columns(self.obs, host, envs, cs)
+                _native.upload_env_columns(frames, host, envs, cs)
             ev = torch.cuda.Event()
             ev.record(cs)
             events.append(ev)
@@ -116,7 +231,7 @@ class RolloutStorage(object):
         """Makes the current stream wait for the staged frames (no-op when nothing is staged)."""
         events = self._upload_staged()
         if events:
-            cur = torch.cuda.current_stream(self.obs.device)
+            cur = torch.cuda.current_stream(self.rewards.device)
             for ev in events:
                 cur.wait_event(ev)
 
@@ -124,7 +239,16 @@ class RolloutStorage(object):
     def insert(self, obs, recurrent_hidden_states, actions, action_log_probs,
                value_preds, rewards, masks, bad_masks):
         t = self.step
-        self.obs[t + 1].copy_(obs)
+        if self.frame_ring:
+            # the newest frame of the rolling stack; the stack restarts where the episode ended (masks == 0: the
+            # wrapper cleared it before writing this frame, reference envs.py:246-249, main.py:129-134)
+            C = self._ring_c
+            self.frames[t + C].copy_(obs[:, -1])
+            grown = torch.clamp(self.stack_valid[t].to(torch.int64) + 1, max=C)
+            fresh = masks.to(self.stack_valid.device).view(-1) == 0
+            self.stack_valid[t + 1].copy_(torch.where(fresh, torch.ones_like(grown), grown).to(torch.uint8))
+        else:
+            self.obs[t + 1].copy_(obs)
         self.recurrent_hidden_states[t + 1].copy_(recurrent_hidden_states)
         self.masks[t + 1].copy_(masks)
         self.bad_masks[t + 1].copy_(bad_masks)
@@ -136,7 +260,11 @@ class RolloutStorage(object):
 
     def after_update(self):
         self.wait_staged()
-        for buf in (self.obs, self.recurrent_hidden_states, self.masks, self.bad_masks):
+        if self.frame_ring:
+            C = self._ring_c
+            self.frames[:C].copy_(self.frames[-C:].clone())
+            self.stack_valid[0].copy_(self.stack_valid[-1])
+        for buf in (() if self.frame_ring else (self.obs,)) + (self.recurrent_hidden_states, self.masks, self.bad_masks):
             buf[0].copy_(buf[-1])
 
     # -- (1) returns / GAE: one reverse-scan kernel (reference storage.py:66-105) --

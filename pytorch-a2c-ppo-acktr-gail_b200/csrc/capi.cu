@@ -180,6 +180,7 @@ int a2cb_gru_seq(int32_t backward, const a2cb_gru_seq_t* desc, a2cb_stream_t str
 }
 int a2cb_gru_seq_supported(int32_t N, int32_t H) { return gru_persistent_supported(N, H) ? 1 : 0; }
 int a2cb_gru_seq_variant(int32_t N, int32_t H) { return gru_persistent_variant(N, H); }
+int a2cb_set_gru_mode(int32_t mode) { set_gru_mode(mode); return A2CB_OK; }
 
 int a2cb_mlp_fused(int32_t backward, const a2cb_mlp_t* desc, a2cb_stream_t stream) {
     A2CB_REQUIRE(desc, "mlp_fused: null descriptor");
@@ -332,7 +333,8 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
             }
             case A2CB_OP_TCX_S2D: {
                 const a2cb_tcx_s2d_t& q = *reinterpret_cast<const a2cb_tcx_s2d_t*>(op.desc);
-                rc = tcx_s2d(q.out, q.out_lo, q.out_b16, q.frames, q.src_is_u8, rt ? idx : q.idx, q.B, q.C, q.H, q.W, q.S, st, q.scatter);
+                rc = tcx_s2d(q.out, q.out_lo, q.out_b16, q.frames, q.src_is_u8, rt ? idx : q.idx, q.B, q.C, q.H, q.W, q.S, st, q.scatter,
+                             q.valid, q.ring_n);
                 break;
             }
             case A2CB_OP_TCX_COLSUM: {

@@ -58,6 +58,11 @@ int gru_op(int which, const GruDesc& d, cudaStream_t st);   // which: 0 init, 1 
 // gru_persistent.cu
 bool gru_persistent_supported(int N, int H);
 int gru_persistent_variant(int N, int H);     // 0 SIMT, 1 mma.sync 3xTF32, 2 tcgen05 (gru_tc.cu), -1 unsupported
+// gru_tc.cu
+bool gru_tc_supported(int N, int H);
+int gru_mode();
+void set_gru_mode(int mode);
+int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st);
 int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st);
 
 // tcx.cu / tcx_aux.cu
@@ -71,7 +76,7 @@ int tcx_lo_plane(float* lo, const float* x, long n, cudaStream_t st);
 int tcx_prep_weights(float* img, float* img_lo, const float* src, long N, long K, const int32_t* ntab,
                      const int32_t* ktab, cudaStream_t st);
 int tcx_s2d(float* out, float* out_lo, void* out_b16, const void* frames, int src_is_u8, const int64_t* idx, int B, int C,
-            int H, int W, int S, cudaStream_t st, int scatter = 0);
+            int H, int W, int S, cudaStream_t st, int scatter = 0, const uint8_t* valid = nullptr, int ring_n = 0);
 int tcx_colsum(float* part, const float* x, float* lo, long rows, int C, long pitch, cudaStream_t st);
 int tcx_colsum_blocks(long rows);
 int tcx_prep_multi(const void* jobs, int n_jobs, long total, cudaStream_t st);

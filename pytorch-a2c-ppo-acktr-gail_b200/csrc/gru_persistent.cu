@@ -702,8 +702,7 @@ gru_mma_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __rest
 static size_t pm_smem_fwd(int H) { return (size_t)(3 * PG_UB * (H + 4)) * sizeof(float) + (size_t)PG_NW * 6 * 32 * sizeof(float4); }
 static size_t pm_smem_bwd(int H) { return (size_t)(PG_UB * (3 * H + 4)) * sizeof(float) + (size_t)PG_NW * 2 * 32 * sizeof(float4); }
 static bool pm_enabled(int H) {
-    static int mode = -1;                                           // A2CB_GRU_MMA=0 selects the SIMT kernels
-    if (mode < 0) { const char* e = getenv("A2CB_GRU_MMA"); mode = (e && e[0] == '0') ? 0 : 1; }
+    const int mode = gru_mode() >= 1 ? 1 : 0;                       // a2cb_set_gru_mode(0) selects the SIMT kernels
     return mode == 1 && H % 64 == 0 && H / 8 / PG_NW <= 8 && pm_smem_fwd(H) <= 227 * 1024 && pm_smem_bwd(H) <= 227 * 1024;
 }
 
@@ -721,6 +720,7 @@ static int pg_sms() {
 
 // Cooperative launch: every CTA must be co-resident (one per SM at this shared-memory footprint).
 bool gru_persistent_supported(int N, int H) {
+    if (gru_tc_supported(N, H)) return true;
     if (N <= 0 || H % 128 != 0 || H % PG_UB != 0) return false;
     const size_t smem = pg_smem_bytes(H);
     if (smem > 220 * 1024) return false;
@@ -736,6 +736,7 @@ bool gru_persistent_supported(int N, int H) {
 }
 
 int gru_persistent_variant(int N, int H) {
+    if (gru_tc_supported(N, H)) return 2;
     if (!gru_persistent_supported(N, H)) return -1;
     return pm_enabled(H) ? 1 : 0;
 }
@@ -787,6 +788,7 @@ static int gru_cluster_forward(const GruDesc& d, const float* Whh, const float* 
 }
 
 int gru_persistent(int backward, const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st) {
+    if (gru_tc_supported(d.N, d.H)) return gru_tc(backward, d, Whh, bhh, st);      // tcgen05 kernels (gru_tc.cu)
     A2CB_REQUIRE(gru_persistent_supported(d.N, d.H), "gru_persistent: unsupported shape (N=%d H=%d)", d.N, d.H);
     A2CB_REQUIRE(Whh && d.hm && d.masks, "gru_persistent: null pointer");
     A2CB_REQUIRE(backward || (bhh && d.h0 && d.gi && d.out), "gru_persistent: forward pointers");

@@ -92,10 +92,16 @@ tcx_prep_multi_kernel(const PrepJob* __restrict__ jobs, int n_jobs, long total) 
 // Atari geometry (C = 4, 84 x 84, S = 4): one block per (image, block row).  The 16 source rows (c, dy) of
 // 84 pixels are read as coalesced 4-byte / 16-byte words into shared memory and written back as 21 x 64
 // contiguous floats -- both sides of the transposition are fully coalesced.
+//
+// Frame ring (valid != nullptr; uint8 only): `frames` is [slots, ring_n, 84, 84] with every 84 x 84 frame stored ONCE;
+// the 4-stack of rollout row (t, n) = row / ring_n, row % ring_n is frames of slots t .. t + 3 (channel c <-> slot
+// t + c, newest last), of which only the newest valid[row] are real: the older ones are zero, exactly as
+// VecPyTorchFrameStack clears the stack when an episode ends (reference envs.py:243-250).
 template <typename T>
 __global__ void __launch_bounds__(352)
 tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, uint2* __restrict__ out_b16,
-                     const T* __restrict__ frames, const int64_t* __restrict__ idx, int scatter) {
+                     const T* __restrict__ frames, const int64_t* __restrict__ idx, int scatter,
+                     const uint8_t* __restrict__ valid, int ring_n) {
     __shared__ float4 tile[16][21];
     const int b = blockIdx.x / 21, by = blockIdx.x % 21;
     const long row = idx ? (long)idx[b] : b;
@@ -103,9 +109,16 @@ tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, uint
     const int i = threadIdx.x;
     if (i < 336) {
         const int r = i / 21, bx = i % 21;                       // r = c * 4 + dy
-        const long src = ((row * 4 + (r >> 2)) * 84 + (by * 4 + (r & 3))) * 84 + bx * 4;
+        long src = ((row * 4 + (r >> 2)) * 84 + (by * 4 + (r & 3))) * 84 + bx * 4;
         float4 v;
-        if (sizeof(T) == 1) {
+        if (sizeof(T) == 1 && valid != nullptr) {
+            const int c = r >> 2;
+            const long t = row / ring_n, n = row - t * ring_n;
+            src = (((t + c) * ring_n + n) * 84 + (by * 4 + (r & 3))) * 84 + bx * 4;
+            uchar4 u = make_uchar4(0, 0, 0, 0);
+            if (c >= 4 - (int)valid[row]) u = *reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(frames) + src);
+            v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+        } else if (sizeof(T) == 1) {
             const uchar4 u = *reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(frames) + src);
             v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
         } else {
@@ -296,18 +309,22 @@ int tcx_prep_weights(float* img, float* img_lo, const float* src, long N, long K
 }
 
 int tcx_s2d(float* out, float* out_lo, void* out_b16, const void* frames, int src_is_u8, const int64_t* idx, int B, int C,
-            int H, int W, int S, cudaStream_t st, int scatter) {
+            int H, int W, int S, cudaStream_t st, int scatter, const uint8_t* valid, int ring_n) {
     A2CB_REQUIRE(out && frames && B > 0 && S > 0 && H % S == 0 && W % S == 0, "tcx_s2d: bad arguments");
     A2CB_REQUIRE(!scatter || idx, "tcx_s2d: scatter mode needs a row list");
+    A2CB_REQUIRE(!valid || (src_is_u8 && C == 4 && H == 84 && W == 84 && S == 4 && ring_n > 0),
+                 "tcx_s2d: the frame ring holds uint8 84 x 84 frames stacked 4 deep");
     if (C == 4 && H == 84 && W == 84 && S == 4) {
         if (src_is_u8)
             tcx_s2d_atari_kernel<uint8_t><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
                                                                                reinterpret_cast<uint2*>(out_b16),
-                                                                               reinterpret_cast<const uint8_t*>(frames), idx, scatter);
+                                                                               reinterpret_cast<const uint8_t*>(frames), idx, scatter,
+                                                                               valid, ring_n);
         else
             tcx_s2d_atari_kernel<float><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
                                                                              reinterpret_cast<uint2*>(out_b16),
-                                                                             reinterpret_cast<const float*>(frames), idx, scatter);
+                                                                             reinterpret_cast<const float*>(frames), idx, scatter,
+                                                                             nullptr, 0);
         return check_launch("tcx_s2d");
     }
     A2CB_REQUIRE(!out_b16, "tcx_s2d: the bf16 copy is only produced for the Atari geometry");

@@ -260,15 +260,28 @@ def test_adv_normalize_vs_torch():
 # ---- persistent whole-sequence GRU (csrc/gru_persistent.cu) against torch autograd -------------------
 @pytest.mark.parametrize("T,N,H,p_done", [(5, 3, 128, 0.2), (16, 64, 512, 0.2), (7, 77, 256, 0.2), (4, 130, 128, 0.2),
                                           (128, 64, 512, 0.01), (128, 8, 512, 0.0), (128, 150, 512, 0.01)])
-def test_gru_persistent_vs_torch(T, N, H, p_done):
+@pytest.mark.parametrize("mode", ["tc", "mma", "simt"])
+def test_gru_persistent_vs_torch(T, N, H, p_done, mode):
     """a2cb_gru_seq forward and backward-through-time on the masked recurrence of model.py:111-166;
     N covers partial warps, partial 64-environment blocks and more than one block.  The T = 128 cases are the
     benchmarked C5 minibatch shape (64 environments, H = 512, episodes ~100 steps long: a 128-step BPTT chain), a
     single environment group without any episode boundary, and more groups than resident CTA groups."""
     import ctypes
     from a2c_ppo_acktr import _engine as E
-    if not E.gru_seq_supported(N, H):
-        pytest.skip("cooperative launch does not fit")
+    _native.set_gru_mode({"tc": 2, "mma": 1, "simt": 0}[mode])
+    try:
+        if not E.gru_seq_supported(N, H):
+            pytest.skip("cooperative launch does not fit")
+        if _native.gru_seq_variant(N, H) != mode:
+            pytest.skip("this shape runs the %s kernels" % _native.gru_seq_variant(N, H))
+        _run_gru_case(T, N, H, p_done)
+    finally:
+        _native.set_gru_mode(-1)
+
+
+def _run_gru_case(T, N, H, p_done):
+    import ctypes
+    from a2c_ppo_acktr import _engine as E
     g = torch.Generator().manual_seed(5)
     gi = torch.randn(T * N, 3 * H, generator=g)
     Whh = torch.randn(3 * H, H, generator=g) / H ** 0.5

@@ -568,6 +568,63 @@ def test_staged_host_ingest_equals_resident_rollout(name, gemm_engine):
         assert torch.equal(p, results[1][1][k]), k
 
 
+@pytest.mark.parametrize("recurrent,staged", [(False, False), (True, False), (True, True)])
+def test_frame_ring_update_equals_stacked_update(recurrent, staged, gemm_engine):
+    """RolloutStorage(frame_ring=True): every 84 x 84 frame stored once (a quarter of the bytes in HBM and on the
+    host link), the 4-stacks assembled by the frame re-layout kernel.  On a rolling-stack rollout (episode ends clear
+    the stack, reference envs.py:218-259) the update must be BIT-identical to the same update on stacked storage."""
+    if gemm_engine != "tcgen05":
+        pytest.skip("the frame ring is read by the TMA-fed engine")
+    T, N, C = 8, 6, 4
+    g = torch.Generator().manual_seed(11)
+    frames = torch.randint(0, 256, (T + C, N, 84, 84), generator=g, dtype=torch.uint8)
+    masks = (torch.rand(T + 1, N, 1, generator=g) > 0.2).float()
+    valid = torch.zeros(T + 1, N, dtype=torch.uint8)
+    valid[0] = torch.randint(1, C + 1, (N,), generator=g).to(torch.uint8)
+    for t in range(T):
+        valid[t + 1] = torch.where(masks[t + 1, :, 0] == 0, torch.ones(N, dtype=torch.int64),
+                                   torch.clamp(valid[t].long() + 1, max=C)).to(torch.uint8)
+    narrow = dict(rewards=torch.randn(T, N, 1, generator=g), value_preds=torch.randn(T + 1, N, 1, generator=g),
+                  action_log_probs=-torch.rand(T, N, 1, generator=g) - 1.0,
+                  actions=torch.randint(0, 6, (T, N, 1), generator=g), masks=masks, bad_masks=torch.ones(T + 1, N, 1),
+                  recurrent_hidden_states=torch.randn(T + 1, N, 512 if recurrent else 1, generator=g) * 0.1)
+    nv = torch.randn(N, 1, generator=g)
+    tmp = RolloutStorage(T, N, (C, 84, 84), Discrete(6), 1, obs_dtype=torch.uint8, frame_ring=True)
+    tmp.frames.copy_(frames)
+    tmp.stack_valid.copy_(valid)
+    stacks = tmp.obs[:]                                          # the stacked observations the ring stands for
+    results = []
+    for ring in (False, True):
+        torch.manual_seed(1)
+        pol = Policy((C, 84, 84), Discrete(6), base_kwargs={"recurrent": recurrent}).to(DEV)
+        st = RolloutStorage(T, N, (C, 84, 84), Discrete(6), 512 if recurrent else 1, obs_dtype=torch.uint8, frame_ring=ring)
+        for k, v in narrow.items():
+            getattr(st, k).copy_(v)
+        if ring:
+            st.frames.copy_(frames)
+            st.stack_valid.copy_(valid)
+            assert torch.equal(st.obs[:], stacks)
+        else:
+            st.obs.copy_(stacks)
+        st.to(DEV)
+        if ring and staged:
+            host = {"frames": frames.clone().pin_memory(), "stack_valid": valid.clone().pin_memory()}
+            st.frames.fill_(3)
+            st.stage_host(host)
+        st.compute_returns(nv.to(DEV), True, 0.99, 0.95, False)
+        agent = algo.PPO(pol, 0.1, 2, 2, 0.5, 0.01, lr=2.5e-4, eps=1e-5, max_grad_norm=0.5)
+        torch.manual_seed(7)
+        losses = agent.update(st)
+        st.after_update()
+        torch.manual_seed(8)
+        losses2 = agent.update(st)
+        results.append((losses, losses2, {k: p.detach().clone() for k, p in pol.named_parameters()}, st.obs[0].clone()))
+    assert results[0][0] == results[1][0] and results[0][1] == results[1][1]
+    for k, p in results[0][2].items():
+        assert torch.equal(p, results[1][2][k]), k
+    assert torch.equal(results[0][3].cpu(), results[1][3].cpu())
+
+
 def test_upload_env_columns_and_wait_staged():
     """The strided column upload (runs of adjacent environments merged) and the plain wait_staged() path."""
     from a2c_ppo_acktr import _native
