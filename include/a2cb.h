@@ -510,6 +510,31 @@ int a2cb_kfac_nu(const float* v, const float* grads, int64_t n, double* scratch,
 int a2cb_frames_to_f32(float* dst, const void* src, int64_t n, int32_t src_is_u8, float div, a2cb_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * GAIL discriminator                      a2c_ppo_acktr/algo/gail.py:11-110, main.py:141-155
+ * trunk = Linear(D, H) - Tanh - Linear(H, H) - Tanh - Linear(H, 1), D = Ds + Da <= 128, H <= 128, flat parameters
+ * [W1 (H x D) | b1 | W2 (H x H) | b2 | w3 (H) | b3] (the reference's state_dict order, row-major).
+ *  a2cb_gail_disc(0, ..): ONE minibatch step of Discriminator.update (gail.py:57-96): policy rows gathered from the
+ *    rollout buffer through idx, expert rows, mixup rows (gail.py:31-55 compute_grad_pen, alpha given by the caller);
+ *    BCE-with-logits(expert, 1) + BCE-with-logits(policy, 0) + lambda mean((||dD/dmixup||_2 - 1)^2) and ALL parameter
+ *    gradients incl. the double-backward terms; writes a2cb_gail_ctas(B) slabs of a2cb_gail_slab_floats(D, H) floats
+ *    (gradients in parameter order, then {BCE loss, penalty}) to be summed (a2cb_reduce_splits).
+ *  a2cb_gail_disc(1, ..): raw rewards log s - log(1 - s), s = sigmoid(D(state, action)), of B rows (gail.py:98-103).
+ *  a2cb_gail_normalize: the sequential rest of predict_reward for T steps of N environments in one launch:
+ *    returns = returns * masks * gamma + r (returns_init: 0 until `returns` exists), RunningMeanStd merge of the batch
+ *    moments of `returns` into rms = double {mean, var, count}, out = r / sqrt(var + 1e-8)  (gail.py:104-110).
+ * ------------------------------------------------------------------------- */
+typedef struct {
+    const float* P; float* slabs; const float* pol_state; const float* pol_action; const int64_t* idx;
+    const float* exp_state; const float* exp_action; const float* alpha; float* raw_out;
+    int32_t B, Ds, Da, H; float lambda; int32_t pad_;
+} a2cb_gail_t;
+int a2cb_gail_disc(int32_t reward, const a2cb_gail_t* desc, a2cb_stream_t stream);
+int a2cb_gail_slab_floats(int32_t D, int32_t H);
+int a2cb_gail_ctas(int32_t B);
+int a2cb_gail_normalize(float* out, const float* raw, const float* masks, int32_t T, int32_t N, float gamma, float* returns,
+                        int32_t* returns_init, double* rms, int32_t update_rms, a2cb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Actor-side head of Policy.act          a2c_ppo_acktr/model.py:54-66, distributions.py:18-44,59-95
  * From the head outputs z[b] = (value, logits[A] | mean[A]): draws the action (Categorical: inverse CDF of the
  * softmax; DiagGaussian: mean + exp(logstd) * N(0,1)) or takes the mode (deterministic: argmax | mean), and writes

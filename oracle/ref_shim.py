@@ -26,6 +26,31 @@ class _Dummy(object):
         pass
 
 
+class RunningMeanStd(object):
+    """Functional stand-in for stable_baselines3.common.running_mean_std.RunningMeanStd (an ABSENT third-party
+    dependency of reference algo/gail.py:9,30,109; the reference pins no version, requirements.txt:1-5).  Restates the
+    published algorithm of that class (sb3 1.x / 2.x, unchanged since OpenAI baselines): parallel-variance merge of
+    batch moments (Chan et al.), all float64, count starts at epsilon = 1e-4, mean 0, var 1."""
+
+    def __init__(self, epsilon=1e-4, shape=()):
+        import numpy as np
+        self.mean = np.zeros(shape, np.float64)
+        self.var = np.ones(shape, np.float64)
+        self.count = epsilon
+
+    def update(self, arr):
+        import numpy as np
+        self.update_from_moments(np.mean(arr, axis=0), np.var(arr, axis=0), arr.shape[0])
+
+    def update_from_moments(self, batch_mean, batch_var, batch_count):
+        import numpy as np
+        delta = batch_mean - self.mean
+        tot = self.count + batch_count
+        new_mean = self.mean + delta * batch_count / tot
+        m2 = self.var * self.count + batch_var * batch_count + np.square(delta) * self.count * batch_count / tot
+        self.mean, self.var, self.count = new_mean, m2 / tot, tot
+
+
 def _stub(name, attrs=()):
     m = sys.modules.get(name)
     if m is None:
@@ -57,7 +82,7 @@ def install():
     _stub("stable_baselines3.common.monitor", ["Monitor"])
     _stub("stable_baselines3.common.vec_env", ["DummyVecEnv", "SubprocVecEnv", "VecEnvWrapper"])
     _stub("stable_baselines3.common.vec_env.vec_normalize", ["VecNormalize"])
-    _stub("stable_baselines3.common.running_mean_std", ["RunningMeanStd"])
+    _stub("stable_baselines3.common.running_mean_std").RunningMeanStd = RunningMeanStd
     _stub("h5py")
 
     if not hasattr(torch, "symeig") or getattr(torch.symeig, "_a2cb_shim", False) is False:
@@ -77,7 +102,8 @@ def install():
         sys.path.insert(0, REFERENCE_DIR)
     import importlib
     mods = {}
-    for name in ("storage", "model", "distributions", "utils", "algo", "algo.ppo", "algo.a2c_acktr", "algo.kfac"):
+    for name in ("storage", "model", "distributions", "utils", "algo", "algo.ppo", "algo.a2c_acktr", "algo.kfac",
+                 "algo.gail"):
         mods[name] = importlib.import_module("a2c_ppo_acktr." + name)
     return mods
 

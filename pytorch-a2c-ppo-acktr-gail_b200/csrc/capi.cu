@@ -182,6 +182,17 @@ int a2cb_gru_seq_supported(int32_t N, int32_t H) { return gru_persistent_support
 int a2cb_gru_seq_variant(int32_t N, int32_t H) { return gru_persistent_variant(N, H); }
 int a2cb_set_gru_mode(int32_t mode) { set_gru_mode(mode); return A2CB_OK; }
 
+int a2cb_gail_disc(int32_t reward, const a2cb_gail_t* desc, a2cb_stream_t stream) {
+    A2CB_REQUIRE(desc, "gail_disc: null descriptor");
+    return gail_disc(reward, desc, (cudaStream_t)stream);
+}
+int a2cb_gail_slab_floats(int32_t D, int32_t H) { return gail_slab_floats(D, H); }
+int a2cb_gail_ctas(int32_t B) { return gail_ctas(B); }
+int a2cb_gail_normalize(float* out, const float* raw, const float* masks, int32_t T, int32_t N, float gamma, float* returns,
+                        int32_t* returns_init, double* rms, int32_t update_rms, a2cb_stream_t stream) {
+    return gail_normalize(out, raw, masks, T, N, gamma, returns, returns_init, rms, update_rms, (cudaStream_t)stream);
+}
+
 int a2cb_mlp_fused(int32_t backward, const a2cb_mlp_t* desc, a2cb_stream_t stream) {
     A2CB_REQUIRE(desc, "mlp_fused: null descriptor");
     static_assert(sizeof(a2cb_mlp_t) == sizeof(MlpDesc), "a2cb_mlp_t out of sync with MlpDesc");

@@ -58,6 +58,12 @@ int gru_op(int which, const GruDesc& d, cudaStream_t st);   // which: 0 init, 1 
 // gru_persistent.cu
 bool gru_persistent_supported(int N, int H);
 int gru_persistent_variant(int N, int H);     // 0 SIMT, 1 mma.sync 3xTF32, 2 tcgen05 (gru_tc.cu), -1 unsupported
+// gail.cu
+int gail_slab_floats(int D, int H);
+int gail_ctas(int B);
+int gail_disc(int reward, const void* desc, cudaStream_t st);
+int gail_normalize(float* out, const float* raw, const float* masks, int T, int N, float gamma, float* returns,
+                   int* returns_init, double* rms, int update_rms, cudaStream_t st);
 // gru_tc.cu
 bool gru_tc_supported(int N, int H);
 int gru_mode();

@@ -332,8 +332,56 @@ def case_update(name):
     save("update_" + name, **out)
 
 
+def gail_inputs(seed=21, T=32, N=4, obs_dim=11, act_dim=3, n_expert=80):
+    """Seeded inputs of the GAIL case (shared with tests/test_gail_*.py through the fixture itself)."""
+    g = torch.Generator().manual_seed(seed)
+    return dict(obs=torch.randn(T + 1, N, obs_dim, generator=g), actions=torch.randn(T, N, act_dim, generator=g),
+                masks=(torch.rand(T + 1, N, 1, generator=g) > 0.1).float(),
+                expert_states=torch.randn(n_expert, obs_dim, generator=g) * 2.0 + 0.3,
+                expert_actions=torch.randn(n_expert, act_dim, generator=g))
+
+
+def gail_obsfilt(x, update=False):
+    """Stand-in for VecNormalize._obfilt (reference envs.py:199-208 with frozen statistics): numpy in, numpy out."""
+    return np.clip((x - 0.3) / np.sqrt(4.0 + 1e-8), -10.0, 10.0)
+
+
+def case_gail():
+    """reference algo/gail.py: two Discriminator.update calls, then the per-step predict_reward loop of main.py:152-155."""
+    gail = REF["algo.gail"]
+    inp = gail_inputs()
+    T, N = inp["actions"].shape[:2]
+    obs_dim, act_dim = inp["obs"].shape[-1], inp["actions"].shape[-1]
+    torch.manual_seed(1)
+    disc = gail.Discriminator(obs_dim + act_dim, 100, torch.device("cpu"))
+    out = {"in_" + k: v.numpy() for k, v in inp.items()}
+    for k, v in disc.state_dict().items():
+        out["init_" + k] = v.numpy().copy()
+    st = REF["storage"].RolloutStorage(T, N, (obs_dim,), Box(act_dim), 1)
+    st.obs.copy_(inp["obs"])
+    st.actions.copy_(inp["actions"])
+    st.masks.copy_(inp["masks"])
+    ds = torch.utils.data.TensorDataset(inp["expert_states"], inp["expert_actions"])
+    loader = torch.utils.data.DataLoader(ds, batch_size=16, shuffle=True, drop_last=True)
+    torch.manual_seed(7)
+    losses = [disc.update(loader, st, gail_obsfilt) for _ in range(2)]
+    out["losses"] = np.array(losses, np.float64)
+    for k, v in disc.state_dict().items():
+        out["final_" + k] = v.numpy().copy()
+    rewards = torch.zeros(T, N, 1)
+    for step in range(T):
+        rewards[step] = disc.predict_reward(st.obs[step], st.actions[step], 0.99, st.masks[step])
+    out["rewards"] = rewards.numpy()
+    out["rms"] = np.array([float(np.asarray(disc.ret_rms.mean).reshape(-1)[0]), float(np.asarray(disc.ret_rms.var).reshape(-1)[0]),
+                           float(disc.ret_rms.count)], np.float64)
+    out["returns_state"] = disc.returns.numpy().copy()
+    # a second rollout's worth with update_rms=False (evaluation path)
+    out["rewards_frozen"] = disc.predict_reward(st.obs[0], st.actions[0], 0.99, st.masks[0], update_rms=False).numpy()
+    save("gail", **out)
+
+
 if __name__ == "__main__":
-    want = sys.argv[1:] or ["returns", "generators", "policy"] + ["update:" + k for k in UPDATE_CASES]
+    want = sys.argv[1:] or ["returns", "generators", "policy", "gail"] + ["update:" + k for k in UPDATE_CASES]
     for w in want:
         if w == "returns":
             case_returns()
@@ -341,6 +389,8 @@ if __name__ == "__main__":
             case_generators()
         elif w == "policy":
             case_policy()
+        elif w == "gail":
+            case_gail()
         elif w.startswith("update:"):
             case_update(w.split(":", 1)[1])
         else:
