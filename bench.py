@@ -327,9 +327,9 @@ def run_ours(args):
     out = None
     if rank == 0:
         pk = peaks()
-        if world == 1:
-            pk.update(measure_tf32_peak(dev))
-        roof, kernels = kernel_roofline(agent, st, cfg, dev, pk) if world == 1 else (None, None)
+        # the TF32 peak is measured AFTER the per-kernel timings: seconds of dense GEMMs at the power cap pull the SM clock
+        # down for a while, which would inflate every kernel time taken right after them
+        roof, kernels = kernel_roofline(agent, st, cfg, dev, pk, lambda: measure_tf32_peak(dev)) if world == 1 else (None, None)
         scan = scan_roofline(dev, pk) if world == 1 else None
         out = {
             "metric": "%s update transitions/sec" % cfg["algo"].upper(),
@@ -430,7 +430,7 @@ def describe(cfg):
 # ---------------------------------------------------------------------------
 # per-kernel timing (CUDA events around every op of one minibatch program)
 # ---------------------------------------------------------------------------
-def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
+def kernel_roofline(agent, st, cfg, dev, pk, measure_peak=None, reps=8):
     from a2c_ppo_acktr import _engine
     prog = getattr(agent, "_prog", None)
     if isinstance(prog, dict):           # ACKTR keeps three programs; profile the main fwd/bwd pass
@@ -504,6 +504,8 @@ def kernel_roofline(agent, st, cfg, dev, pk, reps=8):
     flop_rows = [r for r in rows if r["tflops"] is not None]
     if not flop_rows:
         return None, rows[:24]
+    if measure_peak is not None:
+        pk.update(measure_peak())
     from a2c_ppo_acktr import _native as nat
     tcx_ops = any(kind in (14, 15) for kind, _, _ in prog.entries)
     is_c5 = bool(cfg.get("recurrent")) and cfg["T"] == 128 and cfg["N"] == 256

@@ -411,6 +411,8 @@ int a2cb_optim_step(int32_t kind, float* params, float* grads, float* state1, fl
 #define A2CB_OP_TCX_NARROW_FWD 24
 #define A2CB_OP_TCX_NARROW_DGRAD 25
 #define A2CB_OP_SAMPLE 26
+#define A2CB_OP_COMM_FORK 27   /* a2cb_comm_op_t: all-reduce buf[0..count) on the side stream, ordered after the ops so far */
+#define A2CB_OP_COMM_JOIN 28   /* a2cb_comm_op_t: the launching stream waits for every all-reduce forked since the last join */
 #define A2CB_OP_RUNTIME_IDX 1
 
 typedef struct { float* dst; const float* src; int64_t count; int64_t stride; int32_t splits; int32_t accumulate;
@@ -508,6 +510,29 @@ int a2cb_kfac_scale(float* v, const float* dg, const float* da, int32_t rows, in
 int a2cb_kfac_nu(const float* v, const float* grads, int64_t n, double* scratch, float* out, float lr, float kl_clip,
                  a2cb_stream_t stream);
 int a2cb_frames_to_f32(float* dst, const void* src, int64_t n, int32_t src_is_u8, float div, a2cb_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * NCCL gradient exchange of the environment-sharded update          SURVEY.md section 8e (no reference counterpart:
+ * the reference is single-device; correctness = the single-device result up to the summation order of the all-reduce)
+ * All entry points take an ALREADY INITIALISED communicator (ncclComm_t as void*); a2cb_nccl_unique_id /
+ * a2cb_nccl_comm_init_rank wrap ncclGetUniqueId / ncclCommInitRank for callers that have none (the 128-byte id is
+ * produced on rank 0 and distributed by the host side).  libnccl.so.2 is resolved with dlopen at first use
+ * (a2cb_nccl_load(path) pins a specific copy).  a2cb_comm_ctx_* own a side stream and events: inside an op list
+ * A2CB_OP_COMM_FORK hands a finished gradient segment to ncclAllReduce(sum, fp32, in place) on the side stream while
+ * the remaining weight-gradient kernels run, A2CB_OP_COMM_JOIN orders the optimiser ops after all of them.
+ * ------------------------------------------------------------------------- */
+typedef void* a2cb_nccl_comm_t;
+typedef void* a2cb_comm_ctx_t;
+typedef struct { a2cb_comm_ctx_t ctx; float* buf; int64_t count; } a2cb_comm_op_t;
+int a2cb_nccl_load(const char* path);
+int a2cb_nccl_unique_id(void* out128);
+int a2cb_nccl_comm_init_rank(a2cb_nccl_comm_t* comm, int32_t world, int32_t rank, const void* id128);
+int a2cb_nccl_comm_destroy(a2cb_nccl_comm_t comm);
+int a2cb_nccl_allreduce_sum_f32(a2cb_nccl_comm_t comm, float* buf, int64_t count, a2cb_stream_t stream);
+int a2cb_comm_ctx_create(a2cb_comm_ctx_t* ctx, a2cb_nccl_comm_t comm);
+int a2cb_comm_ctx_destroy(a2cb_comm_ctx_t ctx);
+int a2cb_comm_fork_allreduce(a2cb_comm_ctx_t ctx, float* buf, int64_t count, a2cb_stream_t stream);
+int a2cb_comm_join(a2cb_comm_ctx_t ctx, a2cb_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * GAIL discriminator                      a2c_ppo_acktr/algo/gail.py:11-110, main.py:141-155

@@ -10,8 +10,34 @@ before the clip + optimiser step, which every rank then performs identically.
 
 This module is host logic only (pure index bookkeeping + the torch.distributed plumbing).
 """
+import ctypes
+
 import numpy as np
 import torch
+
+from . import _native
+
+c_i32, c_i64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+
+OP_COMM_FORK, OP_COMM_JOIN = 27, 28
+
+
+class CommOpDesc(ctypes.Structure):
+    """Mirror of a2cb_comm_op_t."""
+    _fields_ = [("ctx", c_vp), ("buf", c_vp), ("count", c_i64)]
+
+
+_native.register({
+    "a2cb_nccl_load": (c_i32, [ctypes.c_char_p]),
+    "a2cb_nccl_unique_id": (c_i32, [c_vp]),
+    "a2cb_nccl_comm_init_rank": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_vp]),
+    "a2cb_nccl_comm_destroy": (c_i32, [c_vp]),
+    "a2cb_nccl_allreduce_sum_f32": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    "a2cb_comm_ctx_create": (c_i32, [ctypes.POINTER(c_vp), c_vp]),
+    "a2cb_comm_ctx_destroy": (c_i32, [c_vp]),
+    "a2cb_comm_fork_allreduce": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    "a2cb_comm_join": (c_i32, [c_vp, c_vp]),
+})
 
 
 class ShardInfo(object):
@@ -80,6 +106,105 @@ def env_capacity(E_global, shard, gran):
 
 def round_up_envs(count, gran):
     return max(gran, (int(count) + gran - 1) // gran * gran)
+
+
+class NativeComm(object):
+    """An NCCL communicator owned by liba2cb (a2cb_nccl_* / a2cb_comm_* in include/a2cb.h) next to the default
+    torch.distributed group: the 128-byte unique id is made on rank 0 and broadcast through the existing group, every
+    rank then calls ncclCommInitRank.  `ctx` adds the side stream + events with which an op list overlaps the
+    all-reduce of finished gradient segments with the remaining weight-gradient kernels (OP_COMM_FORK / OP_COMM_JOIN)."""
+
+    def __init__(self, device):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise _native.NativeError("NativeComm needs an initialised torch.distributed process group for the rendezvous")
+        lib = _native.lib()
+        self.device = torch.device(device)
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        try:                                          # the NCCL copy torch itself runs on
+            import nvidia.nccl as n
+            import os
+            base = os.path.dirname(n.__file__) if getattr(n, "__file__", None) else list(n.__path__)[0]
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                lib.a2cb_nccl_load(path.encode())
+        except Exception:
+            pass
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            _native.check(lib.a2cb_nccl_unique_id(c_vp(uid.data_ptr())), "a2cb_nccl_unique_id")
+        uid_dev = uid.to(self.device)
+        dist.broadcast(uid_dev, 0)
+        uid = uid_dev.cpu()
+        comm = c_vp()
+        with torch.cuda.device(self.device):
+            _native.check(lib.a2cb_nccl_comm_init_rank(ctypes.byref(comm), self.world, self.rank, c_vp(uid.data_ptr())),
+                          "a2cb_nccl_comm_init_rank")
+            ctx = c_vp()
+            _native.check(lib.a2cb_comm_ctx_create(ctypes.byref(ctx), comm), "a2cb_comm_ctx_create")
+        self.comm, self.ctx = comm, ctx
+
+    def all_reduce_sum(self, t):
+        """In-place fp32 sum on the current stream."""
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().a2cb_nccl_allreduce_sum_f32(self.comm, t.data_ptr(), t.numel(),
+                                                                    _native.stream_ptr(self.device)), "a2cb_nccl_allreduce_sum_f32")
+        return t
+
+    def fork_op(self, tensor, lo, hi):
+        """Descriptor of an OP_COMM_FORK on tensor[lo:hi] (fp32, flat)."""
+        d = CommOpDesc()
+        d.ctx, d.buf, d.count = self.ctx, tensor.data_ptr() + 4 * lo, hi - lo
+        return d
+
+    def join_op(self):
+        d = CommOpDesc()
+        d.ctx = self.ctx
+        return d
+
+    def close(self):
+        lib = _native.lib()
+        if getattr(self, "ctx", None):
+            lib.a2cb_comm_ctx_destroy(self.ctx)
+            self.ctx = None
+        if getattr(self, "comm", None):
+            lib.a2cb_nccl_comm_destroy(self.comm)
+            self.comm = None
+
+
+def native_comm(device):
+    """NativeComm on `device` if the default process group runs NCCL on CUDA, else None (the gloo CPU tests and the
+    single-GPU lock-step emulation keep exchanging through their own all-reduce of the yielded tensors)."""
+    import torch.distributed as dist
+    try:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl" \
+                and torch.device(device).type == "cuda":
+            return NativeComm(device)
+    except Exception as e:                            # pragma: no cover - depends on the box
+        import warnings
+        warnings.warn("native NCCL communicator unavailable (%s): gradients are exchanged through torch.distributed" % e)
+    return None
+
+
+def gradient_buckets(layout):
+    """[(lo, hi, label of the first backward op that must NOT precede the fork)] of the flat gradient buffer, in the
+    order the backward pass finishes them: [GRU + heads (+ logstd)] once the GRU weight gradients are folded (before
+    `gru_ih.dgrad`), [fc] once its weight / bias gradients are folded (before `fc.dgrad`), the convolutions at the end."""
+    L = layout.layers
+    total = layout.total
+    if "fc" not in L:
+        return [(0, total, None)]
+    fc_lo = L["fc"][0]
+    tail_lo = L["gru"][0] if "gru" in L else L["heads"][0]
+    out = []
+    if "gru" in L:
+        out.append((tail_lo, total, "gru_ih.dgrad"))
+        out.append((fc_lo, tail_lo, "fc.dgrad"))
+    else:
+        out.append((fc_lo, total, "fc.dgrad"))
+    out.append((0, fc_lo, None))
+    return out
 
 
 def all_reduce_sum(t):

@@ -348,6 +348,19 @@ class Program(object):
                            plan.accumulate, arena.ptr(plan.split_bias), plan.N, plan.split_act, plan.split_beta, 0)
             self.add(OP_REDUCE, r)
 
+    def insert(self, index, kind, desc, flags=0, label=None):
+        self.entries.insert(index, (kind, flags, desc))
+        self.labels.insert(index, (label, 0.0))
+        self._arr = None
+        return desc
+
+    def index_of(self, label):
+        """Index of the first entry carrying `label` (None if absent)."""
+        for i, (lab, _) in enumerate(self.labels):
+            if lab == label:
+                return i
+        return None
+
     def extend(self, other):
         self.entries.extend(other.entries)
         self.labels.extend(other.labels)

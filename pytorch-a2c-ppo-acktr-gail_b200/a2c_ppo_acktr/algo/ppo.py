@@ -55,6 +55,7 @@ def _adv_normalize(rt, rollouts):
 class PPO():
     GRAPH_SLOTS = 4            # epochs whose index / scalar uploads may be in flight at once (_epoch_graph)
     ENV_GRANULARITY = 4        # sharded recurrent minibatches: local environment count rounded up to this many slots
+    native_exchange = True     # sharded: exchange gradients inside the op list through liba2cb's NCCL communicator
     recurrent_sharding = "global"      # "global": the reference's one randperm(N_total); "stratified": balanced opt-in
 
     def __init__(self,
@@ -92,8 +93,39 @@ class PPO():
         rollout of n_total environments, one shard per rank of the default process group."""
         self.shard = _dist.ShardInfo(world, rank, env_range[0], env_range[1], n_total) if world > 1 else None
         self._prog_key = None
+        self._rec_key = None
+        self._comm, self._comm_tried = None, False
         if world > 1 and hasattr(self.actor_critic, "set_sampling_shard"):
             self.actor_critic.set_sampling_shard(env_range[0])      # exploration noise differs between ranks
+
+    def _native_comm(self, rt):
+        """liba2cb's own NCCL communicator (created on first use when the default process group runs NCCL): with it the
+        gradient exchange is part of the op list -- finished segments are all-reduced on a side stream while the remaining
+        weight-gradient kernels run (`_fuse_exchange`).  None: the sharded generators yield the gradient buffer and the
+        caller all-reduces it between two op lists (torch.distributed, the lock-step tests, gloo)."""
+        if self.shard is None or not self.native_exchange:
+            return None
+        if not getattr(self, "_comm_tried", False):
+            self._comm_tried = True
+            self._comm = _dist.native_comm(rt.dev)
+        return getattr(self, "_comm", None)
+
+    def _fuse_exchange(self, rt, prog, comm):
+        """Turns a (forward + loss + backward) program into the whole sharded step: OP_COMM_FORK all-reduces of the
+        gradient segments as the backward pass finishes them (GRU + heads, fc, convolutions: `_dist.gradient_buckets`),
+        OP_COMM_JOIN, then grad-norm clip + Adam."""
+        from .. import _engine
+        G = rt.arena.bufs["G"]
+        for lo, hi, before in _dist.gradient_buckets(rt.L):
+            at = prog.index_of(before) if before is not None else None
+            if at is None:
+                at = len(prog.entries)
+            prog.insert(at, _dist.OP_COMM_FORK, comm.fork_op(G, lo, hi), label="comm.fork")
+        prog.add(_dist.OP_COMM_JOIN, comm.join_op(), label="comm.join")
+        self.optimizer._ensure_state()
+        prog.optim_desc = rt.add_optimizer_ops(prog, 0, self.optimizer.state1, self.optimizer.state2, self.max_grad_norm)
+        prog.fused_exchange = True
+        return prog.finalize()
 
     def _program(self, rt, rollouts, mbs, adv, accum, inv_B=None, seq=None, chunked=False):
         """(forward + loss + backward) program and the (clip + Adam) program.  Unsharded they are one
@@ -111,11 +143,15 @@ class PPO():
                 hyper["inv_B"] = inv_B
             prog = rt.train_program(rollouts, mbs, 0, hyper, adv=adv, loss_accum=accum, seq=seq)
             self.optimizer._ensure_state()
-            opt = prog if self.shard is None else _engine.Program(rt.dev)
-            opt.optim_desc = rt.add_optimizer_ops(opt, 0, self.optimizer.state1, self.optimizer.state2,
-                                                  self.max_grad_norm)
-            prog.finalize()
-            opt.finalize()
+            comm = self._native_comm(rt)
+            if comm is not None:
+                opt = self._fuse_exchange(rt, prog, comm)          # one op list: exchange overlapped with the backward tail
+            else:
+                opt = prog if self.shard is None else _engine.Program(rt.dev)
+                opt.optim_desc = rt.add_optimizer_ops(opt, 0, self.optimizer.state1, self.optimizer.state2,
+                                                      self.max_grad_norm)
+                prog.finalize()
+                opt.finalize()
             self._prog, self._opt_prog, self._prog_key = prog, opt, key
         pro = getattr(self._prog, "prologue", None)
         if chunked and getattr(self._prog, "prologue_chunk", None) is not None:
@@ -330,8 +366,14 @@ class PPO():
                          use_clipped_value_loss=self.use_clipped_value_loss, inv_B=inv_B)
             prog = rt.train_program(rollouts, T * E_p, 0, hyper, adv=adv, loss_accum=accum, seq=(T, E_p), tag="tR_")
             prog.loss_desc.valid_mod = E_p
-            prog.finalize()
+            comm = self._native_comm(rt)
+            if comm is not None:
+                self._fuse_exchange(rt, prog, comm)
+            else:
+                prog.finalize()
             self._rec_progs[E_p] = prog
+        if getattr(prog, "fused_exchange", False):
+            return prog, prog
         if self._rec_opt is None:
             self.optimizer._ensure_state()
             opt = _engine.Program(rt.dev)
@@ -390,10 +432,14 @@ class PPO():
                 hxs_mb = rt.arena.bufs["hxs_mb"][:E_p * H].view(E_p, H)
                 _native.gather_rows([(h0, hxs_mb)], env, E_p)
                 prog.loss_desc.n_valid = count
-                prog.run(rows)
-                yield grads
-                self.optimizer.configure(opt.optim_desc)
-                opt.run()
+                if getattr(prog, "fused_exchange", False):
+                    self.optimizer.configure(prog.optim_desc)
+                    prog.run(rows)                                  # exchange + clip + Adam are part of the op list
+                else:
+                    prog.run(rows)
+                    yield grads
+                    self.optimizer.configure(opt.optim_desc)
+                    opt.run()
                 if self.step_hook is not None:
                     self.step_hook(self.optimizer.step_count)
             if epoch == 0:
@@ -436,10 +482,14 @@ class PPO():
                 if epoch == 0:
                     prepare(k, rows)
                 _native.gather_rows([(h0, hxs_mb)], env, E)
-                prog.run(rows)
-                yield grads
-                self.optimizer.configure(opt.optim_desc)
-                opt.run()
+                if getattr(prog, "fused_exchange", False):
+                    self.optimizer.configure(prog.optim_desc)
+                    prog.run(rows)                                  # exchange + clip + Adam are part of the op list
+                else:
+                    prog.run(rows)
+                    yield grads
+                    self.optimizer.configure(opt.optim_desc)
+                    opt.run()
                 if self.step_hook is not None:
                     self.step_hook(self.optimizer.step_count)
             if epoch == 0:
@@ -484,10 +534,14 @@ class PPO():
             idx = torch.from_numpy(idx_np).to(rt.dev)
             for k in range(n_mb):
                 prog.loss_desc.n_valid = int(counts[k])
-                prog.run(idx[k])
-                yield grads
-                self.optimizer.configure(opt.optim_desc)
-                opt.run()
+                if getattr(prog, "fused_exchange", False):
+                    self.optimizer.configure(prog.optim_desc)
+                    prog.run(idx[k])
+                else:
+                    prog.run(idx[k])
+                    yield grads
+                    self.optimizer.configure(opt.optim_desc)
+                    opt.run()
                 if self.step_hook is not None:
                     self.step_hook(self.optimizer.step_count)
         self.last_launches = _native.launch_count() - launches0

@@ -70,10 +70,8 @@ def build(force=False, verbose=False):
                 if out and (verbose or "warning" in out.lower() or "spill" in out.lower()):
                     print(out)
     if jobs or force or not os.path.exists(LIB):
-        link = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
-        if libdir:
-            # NCCL is dlopen'ed lazily by nccl_glue.cu; no link-time dependency.
-            pass
+        # NCCL is resolved with dlopen at first use (csrc/nccl_glue.cu): no link-time dependency
+        link = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         r = subprocess.run(link, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -182,6 +182,22 @@ int a2cb_gru_seq_supported(int32_t N, int32_t H) { return gru_persistent_support
 int a2cb_gru_seq_variant(int32_t N, int32_t H) { return gru_persistent_variant(N, H); }
 int a2cb_set_gru_mode(int32_t mode) { set_gru_mode(mode); return A2CB_OK; }
 
+int a2cb_nccl_load(const char* path) { return nccl_load_library(path); }
+int a2cb_nccl_unique_id(void* out128) { return nccl_unique_id(out128); }
+int a2cb_nccl_comm_init_rank(a2cb_nccl_comm_t* comm, int32_t world, int32_t rank, const void* id128) {
+    return nccl_comm_init_rank(comm, world, rank, id128);
+}
+int a2cb_nccl_comm_destroy(a2cb_nccl_comm_t comm) { return nccl_comm_destroy(comm); }
+int a2cb_nccl_allreduce_sum_f32(a2cb_nccl_comm_t comm, float* buf, int64_t count, a2cb_stream_t stream) {
+    return nccl_allreduce_sum_f32(comm, buf, (long)count, (cudaStream_t)stream);
+}
+int a2cb_comm_ctx_create(a2cb_comm_ctx_t* ctx, a2cb_nccl_comm_t comm) { return comm_ctx_create(ctx, comm); }
+int a2cb_comm_ctx_destroy(a2cb_comm_ctx_t ctx) { return comm_ctx_destroy(ctx); }
+int a2cb_comm_fork_allreduce(a2cb_comm_ctx_t ctx, float* buf, int64_t count, a2cb_stream_t stream) {
+    return comm_fork_allreduce(ctx, buf, (long)count, (cudaStream_t)stream);
+}
+int a2cb_comm_join(a2cb_comm_ctx_t ctx, a2cb_stream_t stream) { return comm_join(ctx, (cudaStream_t)stream); }
+
 int a2cb_gail_disc(int32_t reward, const a2cb_gail_t* desc, a2cb_stream_t stream) {
     A2CB_REQUIRE(desc, "gail_disc: null descriptor");
     return gail_disc(reward, desc, (cudaStream_t)stream);
@@ -293,6 +309,16 @@ int a2cb_run_ops(const a2cb_op_t* ops, int32_t n_ops, const int64_t* idx, a2cb_s
                 const a2cb_optim_t& o = *reinterpret_cast<const a2cb_optim_t*>(op.desc);
                 rc = optim_step(o.kind, o.params, o.grads, o.state1, o.state2, (long)o.n, o.norm, o.lr_eff, o.eps,
                                 o.b1, o.b2, o.omb1, o.omb2, o.bc2_sqrt, o.max_norm, o.first_step, o.dyn, st);
+                break;
+            }
+            case A2CB_OP_COMM_FORK: {
+                const a2cb_comm_op_t& q = *reinterpret_cast<const a2cb_comm_op_t*>(op.desc);
+                rc = comm_fork_allreduce(q.ctx, q.buf, (long)q.count, st);
+                break;
+            }
+            case A2CB_OP_COMM_JOIN: {
+                const a2cb_comm_op_t& q = *reinterpret_cast<const a2cb_comm_op_t*>(op.desc);
+                rc = comm_join(q.ctx, st);
                 break;
             }
             case A2CB_OP_FILL: {

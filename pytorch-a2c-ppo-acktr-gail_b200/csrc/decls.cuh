@@ -58,6 +58,16 @@ int gru_op(int which, const GruDesc& d, cudaStream_t st);   // which: 0 init, 1 
 // gru_persistent.cu
 bool gru_persistent_supported(int N, int H);
 int gru_persistent_variant(int N, int H);     // 0 SIMT, 1 mma.sync 3xTF32, 2 tcgen05 (gru_tc.cu), -1 unsupported
+// nccl_glue.cu
+int nccl_load_library(const char* path);
+int nccl_unique_id(void* out128);
+int nccl_comm_init_rank(void** comm, int world, int rank, const void* id128);
+int nccl_comm_destroy(void* comm);
+int nccl_allreduce_sum_f32(void* comm, float* buf, long count, cudaStream_t st);
+int comm_ctx_create(void** ctx, void* comm);
+int comm_ctx_destroy(void* ctx);
+int comm_fork_allreduce(void* ctx, float* buf, long count, cudaStream_t st);
+int comm_join(void* ctx, cudaStream_t st);
 // gail.cu
 int gail_slab_floats(int D, int H);
 int gail_ctas(int B);

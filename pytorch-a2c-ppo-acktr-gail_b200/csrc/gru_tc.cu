@@ -560,7 +560,7 @@ void set_gru_mode(int mode) { g_gru_mode = mode < 0 ? -1 : (mode > 2 ? 2 : mode)
 bool gru_tc_supported(int N, int H) {
     if (gru_mode() != 2 || N <= 0 || H % 128 != 0 || H > GT_MAX_H) return false;
     if ((N + GT_RW - 1) / GT_RW > GT_MAX_GROUPS) return false;
-    if (gt_smem_fwd(H) > 227 * 1024 || gt_smem_bwd(H) > 227 * 1024) return false;
+    if (gt_smem_fwd(H) > 226 * 1024 || gt_smem_bwd(H) > 226 * 1024) return false;
     return H / GT_UB <= gt_sms();
 }
 
@@ -569,15 +569,19 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
     A2CB_REQUIRE(Whh && d.hm && d.masks, "gru_tc: null pointer");
     A2CB_REQUIRE(backward || (bhh && d.h0 && d.gi && d.out), "gru_tc: forward pointers");
     A2CB_REQUIRE(!backward || (d.r && d.z && d.n && d.gh && d.dout && d.dgi && d.dgh), "gru_tc: backward pointers");
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(gru_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(gru_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
-            set_error("gru_tc: shared memory attribute");
+    // dynamic shared memory: exactly what this H needs (the device limit of 227 KiB includes the kernels' few static bytes)
+    static int attr_h[2] = {0, 0};
+    if (attr_h[backward ? 1 : 0] < d.H) {
+        const cudaError_t ea = backward
+            ? cudaFuncSetAttribute(gru_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_bwd(d.H))
+            : cudaFuncSetAttribute(gru_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_fwd(d.H));
+        if (ea != cudaSuccess) {
+            set_error("gru_tc: shared memory attribute (%zu bytes): %s", backward ? gt_smem_bwd(d.H) : gt_smem_fwd(d.H),
+                      cudaGetErrorString(ea));
             cudaGetLastError();
             return A2CB_ERR_CUDA;
         }
-        attr = true;
+        attr_h[backward ? 1 : 0] = d.H;
     }
     static int swap = -1;                                                  // probe knob: exchange LBO / SBO of the MN-major operand
     if (swap < 0) { const char* e = getenv("A2CB_GRU_TC_SWAP"); swap = (e && e[0] == '1') ? 1 : 0; }

@@ -33,7 +33,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_python_binding_covers_header():
-    from a2c_ppo_acktr import _engine, _native  # noqa: F401  (_engine registers the descriptor entry points)
+    from a2c_ppo_acktr import _dist, _engine, _native  # noqa: F401  (_engine / _dist register the descriptor entry points)
+    from a2c_ppo_acktr.algo import gail  # noqa: F401
     missing = [s for s in declared_symbols() if s not in _native._SIGNATURES]
     assert not missing, "ctypes signatures missing for %s" % missing
     _native.lib()
