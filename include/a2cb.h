@@ -490,6 +490,11 @@ int a2cb_gru_seq_variant(int32_t N, int32_t H);
 /* selects the kernel family of a2cb_gru_seq: 2 (default) tcgen05 where the shape allows, 1 mma.sync, 0 fp32 SIMT,
  * < 0 back to the default / environment (A2CB_GRU_MODE) */
 int a2cb_set_gru_mode(int32_t mode);
+/* diagnostics: clock64 stamps [2 directions][16 steps][16 phases] of CTA (0, 0) of the last launches run with
+ * A2CB_GRU_TC_DEBUG=1; number of thread-block clusters of `cluster_size` CTAs with `smem_bytes` of dynamic shared
+ * memory each that can be co-resident on this device (cudaOccupancyMaxActiveClusters) */
+int a2cb_gru_tc_debug_stamps(int64_t* out);
+int a2cb_gru_cluster_probe(int32_t cluster_size, int32_t smem_bytes);
 
 /* ---------------------------------------------------------------------------
  * (5) ACKTR / KFAC helpers                              a2c_ppo_acktr/algo/kfac.py

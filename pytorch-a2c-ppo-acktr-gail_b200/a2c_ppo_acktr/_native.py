@@ -39,6 +39,8 @@ _SIGNATURES = {
     "a2cb_upload_env_columns": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p, c_int, c_void_p]),
     "a2cb_gru_seq_variant": (c_int, [c_int, c_int]),
     "a2cb_set_gru_mode": (c_int, [c_int]),
+    "a2cb_gru_tc_debug_stamps": (c_int, [c_void_p]),
+    "a2cb_gru_cluster_probe": (c_int, [c_int, c_int]),
 }
 
 _lib = None

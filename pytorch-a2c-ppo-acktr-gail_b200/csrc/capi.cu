@@ -181,6 +181,8 @@ int a2cb_gru_seq(int32_t backward, const a2cb_gru_seq_t* desc, a2cb_stream_t str
 int a2cb_gru_seq_supported(int32_t N, int32_t H) { return gru_persistent_supported(N, H) ? 1 : 0; }
 int a2cb_gru_seq_variant(int32_t N, int32_t H) { return gru_persistent_variant(N, H); }
 int a2cb_set_gru_mode(int32_t mode) { set_gru_mode(mode); return A2CB_OK; }
+int a2cb_gru_tc_debug_stamps(int64_t* out) { return gru_tc_debug_stamps(reinterpret_cast<long long*>(out)); }
+int a2cb_gru_cluster_probe(int32_t cluster_size, int32_t smem_bytes) { return gru_cluster_probe(cluster_size, smem_bytes); }
 
 int a2cb_nccl_load(const char* path) { return nccl_load_library(path); }
 int a2cb_nccl_unique_id(void* out128) { return nccl_unique_id(out128); }

@@ -76,6 +76,8 @@ int gail_normalize(float* out, const float* raw, const float* masks, int T, int 
                    int* returns_init, double* rms, int update_rms, cudaStream_t st);
 // gru_tc.cu
 bool gru_tc_supported(int N, int H);
+int gru_tc_debug_stamps(long long* out);
+int gru_cluster_probe(int cluster_size, int smem_bytes);
 int gru_mode();
 void set_gru_mode(int mode);
 int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, cudaStream_t st);

@@ -735,6 +735,28 @@ bool gru_persistent_supported(int N, int H) {
     return (long)(H / PG_UB) <= (long)pg_sms() * (pf < pb ? pf : pb);
 }
 
+// cudaOccupancyMaxActiveClusters for the cluster forward kernel's footprint (1 CTA / SM): how many clusters of
+// `cluster_size` CTAs the device can hold at once
+int gru_cluster_probe(int cluster_size, int smem_bytes) {
+    if (cudaFuncSetAttribute(gru_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(gru_cluster_fwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cluster_size, 64);
+    cfg.blockDim = dim3(PG_NT);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gru_cluster_fwd_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return -2; }
+    return n;
+}
+
 int gru_persistent_variant(int N, int H) {
     if (gru_tc_supported(N, H)) return 2;
     if (!gru_persistent_supported(N, H)) return -1;

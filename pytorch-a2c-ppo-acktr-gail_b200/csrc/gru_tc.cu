@@ -46,6 +46,8 @@ constexpr int GT_CTRL = 4;                    // control warp: polls, issues the
 constexpr float GT_SX = 16.f;                 // power-of-two scale of the forward state planes
 
 __device__ unsigned gt_flags[2][GT_MAX_GROUPS];
+__device__ long long gt_dbg[2][16][16];            // A2CB_GRU_TC_DEBUG=1: clock64 stamps of CTA (0, 0), steps 16..31, per phase
+#define GT_STAMP(dir, t, i) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && (t) >= 16 && (t) < 32) gt_dbg[dir][(t) - 16][i] = clock64(); } while (0)
 __device__ uint4 gt_img[(size_t)GT_MAX_GROUPS * 2 * GT_IMG_BYTES / 16];
 __device__ float gt_part[(size_t)GT_MAX_GROUPS * 2 * GT_PART_FLOATS];
 
@@ -182,7 +184,7 @@ __device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, i
 // the environment groups by, by + gridDim.y, ...  Shared memory: [state image][weight image][tail].
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GT_NT, 1)
-gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh) {
+gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh, const int dbg) {
     extern __shared__ uint8_t gt_dyn[];
     __shared__ uint64_t bar_state, bar_acc;
     __shared__ uint32_t tmem_slot;
@@ -277,8 +279,10 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
             if (warp == GT_CTRL) {
                 // ===== control warp: wait for the group's state of step t, fetch it, issue the step's MMAs =====
                 if (lane == 0) {
+                    GT_STAMP(0, t, 0);
                     const unsigned target = (unsigned)ug * (unsigned)(t + 1);
                     while (gt_ld_acquire(&gt_flags[0][grp]) < target) {}
+                    GT_STAMP(0, t, 1);
                 }
                 __syncwarp();
                 if (gt_elect()) {
@@ -288,6 +292,7 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                 }
                 __syncwarp();
                 gt_mbar_wait(&bar_state, it & 1u);
+                if (lane == 0) GT_STAMP(0, t, 2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (gt_elect()) {
                     for (int s = 0; s < k16; ++s) {
@@ -306,9 +311,11 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                     gt_commit(&bar_acc);
                 }
                 __syncwarp();
+                if (lane == 0) GT_STAMP(0, t, 3);
             } else if (warp < 3) {
                 // ===== drain: gate `warp`, row = lane: 4 accumulators x 8 environments =====
                 gt_mbar_wait(&bar_acc, it & 1u);
+                if (tid == 0) GT_STAMP(0, t, 4);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -321,8 +328,10 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
 #pragma unroll
                 for (int e = 0; e < 8; ++e) xchg[(warp * 8 + e) * 32 + lane] = s8[e] * inv_scale + bias;
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (tid == 0) GT_STAMP(0, t, 5);
             }
             __syncthreads();                                               // gate pre-activations of W_hh hm_t + b_hh are in xchg
+            if (tid == 0) GT_STAMP(0, t, 6);
             const float ghr = xchg[(0 * 8 + warp) * 32 + lane], ghz = xchg[(1 * 8 + warp) * 32 + lane],
                         ghn = xchg[(2 * 8 + warp) * 32 + lane];
             const float rr = gt_sigmoid(q.r + ghr);
@@ -332,8 +341,11 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
             const float hm_next = live ? h * q.mnext : 0.f;
             if (t + 1 < d.T) put_state(image_of(grp, (t + 1) & 1), hm_next);    // what the other CTAs wait for
             hm_cur = hm_next;
+            if (tid == 0) GT_STAMP(0, t, 7);
             __syncthreads();
+            if (tid == 0) GT_STAMP(0, t, 8);
             if (tid == 0 && t + 1 < d.T) gt_release_add(&gt_flags[0][grp]);
+            if (tid == 0) GT_STAMP(0, t, 9);
             // everything below is consumed by later kernels only
             if (single && t + 1 < d.T) pre = load_gi(t + 1, my);
             if (live) {
@@ -359,7 +371,8 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
 // Shared memory: [weight image][tail][gate-gradient operand: 2 planes x 2 blocks x 16 rows x 128 B].
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GT_NT, 1)
-gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws, const int swap_strides) {
+gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws, const int swap_strides,
+                  const int dbg) {
     extern __shared__ uint8_t gt_dyn[];
     __shared__ uint64_t bar_acc;
     __shared__ uint32_t tmem_slot;
@@ -425,8 +438,10 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
             float dh = a.dout;
             if (t + 1 < d.T) {
                 if (tid == 0) {
+                    GT_STAMP(1, t, 0);
                     const unsigned target = (unsigned)ug * (unsigned)(d.T - 1 - t);
                     while (gt_ld_acquire(&gt_flags[1][grp]) < target) {}
+                    GT_STAMP(1, t, 1);
                 }
                 __syncthreads();
                 const float* p = part_of(grp, (t + 1) & 1) + (((size_t)blockIdx.x * ug) * GT_RW + warp) * GT_UB + lane;
@@ -438,6 +453,7 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                 }
                 const float c = (first ? carry0 : (live ? carry_ws[(long)my * H + ku] : 0.f)) + sum;
                 dh += c * a.mnext;
+                if (tid == 0) GT_STAMP(1, t, 2);
             }
             // ---- phase A ----
             const float dn_pre = dh * (1.f - a.z) * (1.f - a.n * a.n);
@@ -467,7 +483,9 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (tid == 0) GT_STAMP(1, t, 3);
                 __syncthreads();
+                if (tid == 0) GT_STAMP(1, t, 4);
                 if (warp == GT_CTRL) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (gt_elect()) {
@@ -490,6 +508,7 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                 } else if (warp < 4) {
                     // ---- drain: row = unit mb * 128 + 32 warp + lane -> the partial carries of unit group 4 mb + warp ----
                     gt_mbar_wait(&bar_acc, it & 1u);
+                    if (tid == 0) GT_STAMP(1, t, 5);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const float unscale = 1.f / (sw * sg);
                     float* pbase = part_of(grp, t & 1);
@@ -501,10 +520,13 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                         for (int e = 0; e < 8; ++e) __stcg(p + e * GT_UB, v[e] * unscale);
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (tid == 0) GT_STAMP(1, t, 6);
                 }
                 ++it;
                 __syncthreads();
+                if (tid == 0) GT_STAMP(1, t, 7);
                 if (tid == 0) gt_release_add(&gt_flags[1][grp]);
+                if (tid == 0) GT_STAMP(1, t, 8);
             }
             // ---- consumed by the weight-gradient products after this kernel ----
             if (live) {
@@ -557,6 +579,11 @@ int gru_mode() {
 }
 void set_gru_mode(int mode) { g_gru_mode = mode < 0 ? -1 : (mode > 2 ? 2 : mode); }
 
+// copies the clock64 stamps of the last debug launches (2 directions x 16 steps x 16 phases) to the host
+int gru_tc_debug_stamps(long long* out) {
+    return cudaMemcpyFromSymbol(out, gt_dbg, sizeof(long long) * 2 * 16 * 16) == cudaSuccess ? A2CB_OK : A2CB_ERR_CUDA;
+}
+
 bool gru_tc_supported(int N, int H) {
     if (gru_mode() != 2 || N <= 0 || H % 128 != 0 || H > GT_MAX_H) return false;
     if ((N + GT_RW - 1) / GT_RW > GT_MAX_GROUPS) return false;
@@ -598,11 +625,13 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
                                  GT_MAX_GROUPS * sizeof(unsigned), st);
         if (e0 != cudaSuccess) { set_error("gru_tc: flag reset: %s", cudaGetErrorString(e0)); return A2CB_ERR_CUDA; }
     }
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("A2CB_GRU_TC_DEBUG"); dbg = (e && e[0] == '1') ? 1 : 0; }
     GruDesc dd = d;
     float* ws = d.dcarry;
     int sw = swap;
-    void* args_f[] = {(void*)&dd, (void*)&Whh, (void*)&bhh};
-    void* args_b[] = {(void*)&dd, (void*)&Whh, (void*)&ws, (void*)&sw};
+    void* args_f[] = {(void*)&dd, (void*)&Whh, (void*)&bhh, (void*)&dbg};
+    void* args_b[] = {(void*)&dd, (void*)&Whh, (void*)&ws, (void*)&sw, (void*)&dbg};
     dim3 grid((unsigned)ug, (unsigned)gy);
     cudaError_t e = backward
         ? cudaLaunchCooperativeKernel((const void*)gru_tc_bwd_kernel, grid, dim3(GT_NT), args_b, gt_smem_bwd(d.H), st)

@@ -210,8 +210,8 @@ UPDATE_CASES = {
                        use_proper_time_limits=True)),
     "C5s": ("C5", dict(T=8, N=4, ppo_epoch=2, num_mini_batch=2)),
     # the benchmarked shape: one GPU's C5 shard, T = 128, 256 environments, recurrent minibatches of 64 environments
-    # (8,192 rows); one epoch keeps the reference run short.  Only slot 0 of the hidden states is stored (the update
-    # reads nothing else, reference storage.py:160-161).
+    # (8,192 rows); one epoch keeps the reference run short.  Only slots 0 and T of the hidden states are stored (the
+    # update reads slot 0 only, reference storage.py:160-161; after_update() copies slot T into it).
     "C5m": ("C5", dict(T=128, N=256, ppo_epoch=1, num_mini_batch=4)),
     "C2": ("C2", dict()),
     "C2g": ("C2", dict(T=6, N=3, use_gae=True, use_proper_time_limits=True)),
@@ -268,6 +268,7 @@ def case_update(name):
     if cfg["recurrent"]:
         if cfg["T"] * cfg["N"] > 4096:
             out["ro_h0"] = ro["recurrent_hidden_states"][0].numpy()
+            out["ro_hT"] = ro["recurrent_hidden_states"][-1].numpy()      # after_update() carries it into slot 0
         else:
             out["ro_recurrent_hidden_states"] = ro["recurrent_hidden_states"].numpy()
     out["returns"] = st.returns.numpy().copy()

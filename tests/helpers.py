@@ -87,6 +87,8 @@ def rollout_from_case(case, cfg, obs_uint8=False, device="cpu"):
         # large recurrent cases store slot 0 only: the update reads nothing else (reference storage.py:160-161)
         ro["recurrent_hidden_states"] = torch.zeros(T + 1, N, H)
         ro["recurrent_hidden_states"][0].copy_(torch.from_numpy(case["ro_h0"]))
+        if "ro_hT" in case:
+            ro["recurrent_hidden_states"][-1].copy_(torch.from_numpy(case["ro_hT"]))
     elif cfg["recurrent"]:
         ro["recurrent_hidden_states"] = torch.from_numpy(case["ro_recurrent_hidden_states"])
     else:

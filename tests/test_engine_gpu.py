@@ -335,3 +335,49 @@ def _run_gru_case(T, N, H, p_done):
     # dW_hh = sum_t dgh_t^T hm_t  (the weight-gradient GEMM consumes dgh and hm)
     dW = bufs["dgh"].double().t() @ bufs["hm"].double()
     assert rel(dW.float(), W_r.grad) <= 5e-6
+
+
+def test_backward_products_with_the_engines_own_relu_masks_match_fp64():
+    """Pins the argument behind the gradient allowance of the tensor-core engine (tests/test_update_gpu.py): its forward
+    pre-activations differ from an exact-fp32 forward by ~2e-6 relative, which can flip the relu' bit of the few
+    activations that close to zero; everything ELSE in the backward pass -- the 3xTF32 data / weight gradient products
+    and their split folds -- must agree with an fp64 reference to 1e-5 once both use the SAME masks.  The fp64 reference
+    below takes its relu masks from the engine's own activations (a > 0) instead of its own pre-activations."""
+    from a2c_ppo_acktr.model import Policy
+
+    class Discrete(object):
+        n = 6
+    _native.set_gemm_mode(2)
+    torch.manual_seed(1)
+    pol = Policy((4, 84, 84), Discrete()).to(DEV)
+    B = 256                                                    # a C3 minibatch
+    g = torch.Generator().manual_seed(3)
+    obs_u8 = torch.randint(0, 256, (B, 4, 84, 84), generator=g, dtype=torch.uint8)
+    action = torch.randint(0, 6, (B, 1), generator=g)
+    cv, cl, ce = torch.randn(B, 1, generator=g) / B, torch.randn(B, 1, generator=g) / B, 0.01
+    v2, lp2, ent2, _ = pol.evaluate_actions(obs_u8.to(DEV), torch.zeros(B, 1, device=DEV), torch.ones(B, 1, device=DEV),
+                                            action.to(DEV))
+    rt = pol.runtime()
+    assert ("b%d_a1" % B) in rt.arena.bufs, "this test reads the TMA-fed engine's NHWC activations"
+    def mask(name, shape):                                     # NHWC x plane -> NCHW {0, 1} fp64
+        a = rt.arena.bufs["b%d_%s" % (B, name)][:B * shape[0] * shape[1] * shape[2]].view(B, *shape)
+        return (a > 0).permute(0, 3, 1, 2).double().cpu()
+    m1, m2, m3 = mask("a1", (20, 20, 32)), mask("a2", (9, 9, 64)), mask("a3", (7, 7, 32))
+    mh = (rt.arena.bufs["b%d_h" % B][:B * 512].view(B, 512) > 0).double().cpu()
+    for p in pol.parameters():
+        p.grad.zero_()
+    ((v2 * cv.to(DEV)).sum() + (lp2 * cl.to(DEV)).sum() + ce * ent2).backward()
+    ref = {k: v.detach().cpu().double().requires_grad_(True) for k, v in pol.state_dict().items()}
+    x = obs_u8.double() / 255.0
+    a = F.conv2d(x, ref["base.main.0.weight"], ref["base.main.0.bias"], stride=4) * m1
+    a = F.conv2d(a, ref["base.main.2.weight"], ref["base.main.2.bias"], stride=2) * m2
+    a = F.conv2d(a, ref["base.main.4.weight"], ref["base.main.4.bias"], stride=1) * m3
+    h = F.linear(a.reshape(B, -1), ref["base.main.7.weight"], ref["base.main.7.bias"]) * mh
+    value = F.linear(h, ref["base.critic_linear.weight"], ref["base.critic_linear.bias"])
+    dist = torch.distributions.Categorical(logits=F.linear(h, ref["dist.linear.weight"], ref["dist.linear.bias"]))
+    logp = dist.log_prob(action.squeeze(-1)).unsqueeze(-1)
+    ((value * cv.double()).sum() + (logp * cl.double()).sum() + ce * dist.entropy().mean()).backward()
+    for k, p in pol.named_parameters():
+        want = ref[k].grad
+        err = float((p.grad.cpu().double() - want).norm() / want.norm().clamp_min(1e-30))
+        assert err <= 1e-5, (k, err)

@@ -69,6 +69,20 @@ def main():
                 rec["rel_" + k] = float((outs[k] - ref[k]).double().norm() / ref[k].double().norm().clamp_min(1e-30))
         print(json.dumps(rec), flush=True)
     _native.set_gru_mode(-1)
+    if os.environ.get("A2CB_GRU_TC_DEBUG") == "1":
+        import numpy as np
+        buf = np.zeros((2, 16, 16), np.int64)
+        _native.check(lib.a2cb_gru_tc_debug_stamps(ctypes.c_void_p(buf.ctypes.data)), "stamps")
+        for direction, name, n in ((0, "fwd", 10), (1, "bwd", 9)):
+            st = buf[direction, :, :n].astype(np.float64)
+            prev_end = np.roll(st[:, n - 1], 1 if direction == 0 else -1)
+            d = np.diff(st, axis=1)
+            ok = slice(2, 14)
+            print(json.dumps({"stamps": name, "phase_cycles_median": np.median(d[ok], axis=0).round(0).tolist(),
+                              "step_cycles_median": float(np.median(np.abs(np.diff(st[:, 0]))[ok]))}))
+    for cs in (16, 8, 4, 2):
+        print(json.dumps({"cluster_size": cs, "max_active_clusters_217KB": int(lib.a2cb_gru_cluster_probe(cs, 217 * 1024)),
+                          "max_active_clusters_100KB": int(lib.a2cb_gru_cluster_probe(cs, 100 * 1024))}))
 
 
 if __name__ == "__main__":
