@@ -199,7 +199,9 @@ def run_ours(args):
     # frame is generated and stored ONCE, observation t is the rolling stack of frames t .. t + 3 with the stack cleared
     # where an episode ended (reference envs.py:218-259) -- a quarter of the bytes on the host link and in HBM.
     torch.manual_seed(2 + rank)
-    ring = cfg["kind"] == "atari" and not args.stacked_frames
+    # (PPO workloads: the update reads the ring in place.  A2C / ACKTR run ONE full-batch pass per update on a few hundred
+    # rows and would have to materialise the stacks first, so they keep the stacked layout.)
+    ring = cfg["kind"] == "atari" and cfg["algo"] == "ppo" and not args.stacked_frames
     if ring:
         C = cfg["obs_shape"][0]
         fr_np = synthetic.atari_frames(T + C, N_total, 0, env_range, (1,) + tuple(cfg["obs_shape"][1:]))

@@ -96,6 +96,21 @@ __device__ __forceinline__ void gt_mma(uint32_t d_tmem, uint64_t a, uint64_t b, 
         "}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc)
         : "memory");
 }
+// A operand from tensor memory (lane = row, one 32-bit column = two consecutive fp16 reduction elements), B from shared memory
+__device__ __forceinline__ void gt_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void gt_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 // shared-memory matrix descriptor: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46 | SWIZZLE_128B << 61
 __device__ __forceinline__ uint64_t gt_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
@@ -150,7 +165,8 @@ __device__ __forceinline__ float gt_pow2_scale(float amax, int e) {
 
 // Converts the CTA's weight slice (rows g * H + ub + u, g < 3, u < 32, all H columns) into the two fp16 planes of the
 // UMMA image at `img` (plane stride = (H / 64) * GT_WBLK); returns the scale (w * scale = hi + lo).
-__device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, int H, int ub, float* red) {
+// `planes`: 3 = both planes (plane 1 behind plane 0), 2 = the lo plane only (at img), 0 = none (scale only).
+__device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, int H, int ub, float* red, int planes = 3) {
     const int tid = threadIdx.x;
     float amax = 0.f;
     for (int e = tid; e < GT_ROWS * H; e += GT_NT) {
@@ -166,13 +182,18 @@ __device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, i
     for (int w = 1; w < GT_NT / 32; ++w) amax = fmaxf(amax, red[w]);
     const float sw = gt_pow2_scale(amax, 13);             // |w| * sw < 2^14: w_lo is a normal fp16 down to |w| sw 2^-11 >= 2^-14
     const uint32_t plane = (uint32_t)(H / 64) * GT_WBLK;
-    for (int e = tid; e < GT_ROWS * H; e += GT_NT) {
-        const int row = e / H, k = e - row * H;
-        const uint32_t p = gt_split(Whh[(long)((row >> 5) * H + ub + (row & 31)) * H + k] * sw);
-        const uint32_t off = gt_swz(row, k, GT_WBLK);
-        *reinterpret_cast<unsigned short*>(img + off) = (unsigned short)(p & 0xffffu);
-        *reinterpret_cast<unsigned short*>(img + plane + off) = (unsigned short)(p >> 16);
-    }
+    if (planes)
+        for (int e = tid; e < GT_ROWS * H; e += GT_NT) {
+            const int row = e / H, k = e - row * H;
+            const uint32_t p = gt_split(Whh[(long)((row >> 5) * H + ub + (row & 31)) * H + k] * sw);
+            const uint32_t off = gt_swz(row, k, GT_WBLK);
+            if (planes == 3) {
+                *reinterpret_cast<unsigned short*>(img + off) = (unsigned short)(p & 0xffffu);
+                *reinterpret_cast<unsigned short*>(img + plane + off) = (unsigned short)(p >> 16);
+            } else {
+                *reinterpret_cast<unsigned short*>(img + off) = (unsigned short)(p >> 16);
+            }
+        }
     __syncthreads();
     return sw;
 }
@@ -183,10 +204,15 @@ __device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, i
 // forward.  grid (H / 32 unit groups, resident environment groups); CTA (bx, by) owns units 32 bx .. 32 bx + 31 and
 // the environment groups by, by + gridDim.y, ...  Shared memory: [state image][weight image][tail].
 // ---------------------------------------------------------------------------------------------------------------
+// TA: the hi plane of the weight slice lives in TENSOR MEMORY (128 lanes x H / 2 columns behind the accumulators) and is
+// the A operand of two of the three products of every reduction step; only the lo plane stays in shared memory.  With
+// both planes in shared memory every MMA streams 4 KiB of A through the shared-memory port (~59 cycles per instruction
+// measured, 5,700 of the 10,200 cycles of a step).
+template <bool TA>
 __global__ void __launch_bounds__(GT_NT, 1)
 gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh, const int dbg) {
     extern __shared__ uint8_t gt_dyn[];
-    __shared__ uint64_t bar_state, bar_acc;
+    __shared__ uint64_t bar_state[4], bar_acc;
     __shared__ uint32_t tmem_slot;
     __shared__ float red[GT_NT / 32];
     const int H = d.H, nkb = H >> 6, ug = H >> 5;
@@ -195,29 +221,60 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
     const uint32_t st_bytes = 2u * nkb * 1024u;           // state image: [2 planes][nkb][8 rows x 128 B]
     const uint32_t w_plane = (uint32_t)nkb * GT_WBLK;
     const uint32_t s_state = base, s_w = base + st_bytes;
-    float* xchg = reinterpret_cast<float*>(sm + st_bytes + 2 * w_plane);      // [3 gates][8 environments][32 units]
+    constexpr int NPL = TA ? 1 : 2;                                        // weight planes in shared memory
+    constexpr uint32_t TCOLS = TA ? 512u : 64u;                            // tensor memory: 64 accumulator columns (+ H / 2)
+    float* xchg = reinterpret_cast<float*>(sm + st_bytes + NPL * w_plane);    // [3 gates][8 environments][32 units]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ub = blockIdx.x * GT_UB, ku = ub + lane;
     const int ngrp = (d.N + GT_RW - 1) / GT_RW;
     const bool single = ngrp <= (int)gridDim.y;
 
-    const float sw = gt_build_weights(sm + st_bytes, Whh, H, ub, red);
-    const float inv_scale = 1.f / (sw * GT_SX);
     if (tid == 0) {
-        gt_mbar_init(&bar_state, 1);
+        for (int c = 0; c < 4; ++c) gt_mbar_init(&bar_state[c], 1);
         gt_mbar_init(&bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == GT_CTRL) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem(&tmem_slot)), "r"(64u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem(&tmem_slot)), "r"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    const float sw = gt_build_weights(sm + st_bytes, Whh, H, ub, red, TA ? 2 : 3);
+    const float inv_scale = 1.f / (sw * GT_SX);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // weight image: generic stores -> tensor-core reads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
+    if (TA) {
+        // hi plane -> tensor memory: thread (warp w < 4, lane) owns row 32 w + lane (rows >= 96: zero); column
+        // 64 + c holds reduction elements 2 c, 2 c + 1 of that row
+        if (warp < 4) {
+            const int row = 32 * warp + lane;
+            const float* wr = Whh + (long)((row >> 5) * H + ub + (row & 31)) * H;       // rows >= 96 never dereferenced
+            for (int c0 = 0; c0 < H / 2; c0 += 8) {
+                uint32_t r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t lo16 = 0u, hi16 = 0u;
+                    if (row < GT_ROWS) {
+                        lo16 = gt_split(wr[2 * (c0 + j)] * sw) & 0xffffu;
+                        hi16 = gt_split(wr[2 * (c0 + j) + 1] * sw) & 0xffffu;
+                    }
+                    r[j] = lo16 | (hi16 << 16);
+                }
+                gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + 64u + (uint32_t)c0, r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     const float bias = warp < 3 ? bhh[warp * H + ku] : 0.f;               // drain warp g adds b_hh of gate g
+    // the state of a step arrives in NCH chunks of k-blocks (one mbarrier each): the MMAs of accumulator c only wait
+    // for chunk c, so most of the fetch hides behind the MMAs of the earlier chunks
+    const int NCH = (nkb % 4 == 0) ? 4 : 1;
+    const uint32_t ch_bytes = (uint32_t)(nkb / NCH) * 1024u;               // per plane and chunk
 
     // instruction descriptor: D fp32, A / B fp16, both K-major, N = 16, M = 128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -286,31 +343,46 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                 }
                 __syncwarp();
                 if (gt_elect()) {
-                    asm volatile("fence.proxy.async;" ::: "memory");     // other CTAs' generic stores -> this bulk copy
-                    gt_expect(&bar_state, st_bytes);
-                    gt_bulk_g2s(s_state, image_of(grp, t & 1), st_bytes, &bar_state);
-                }
-                __syncwarp();
-                gt_mbar_wait(&bar_state, it & 1u);
-                if (lane == 0) GT_STAMP(0, t, 2);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (gt_elect()) {
-                    for (int s = 0; s < k16; ++s) {
-                        const uint32_t o = (uint32_t)(s >> 2) * GT_WBLK + (uint32_t)(s & 3) * 32u;
-                        const uint32_t ob = (uint32_t)(s >> 2) * 1024u + (uint32_t)(s & 3) * 32u;
-                        const uint64_t ah = gt_desc(s_w + o, 16, 1024), al = gt_desc(s_w + w_plane + o, 16, 1024);
-                        // B: 16 "environment" rows = the group's 8 (first atom) + 8 junk rows: the second atom is made
-                        // to alias the start of the weight image (finite values) through SBO = size of the state image
-                        const uint64_t bh = gt_desc(s_state + ob, 16, st_bytes), bl = gt_desc(s_state + nkb * 1024u + ob, 16, st_bytes);
-                        const uint32_t dcol = tmem + (uint32_t)(s / per_acc) * 16u;
-                        const uint32_t first = (s % per_acc) == 0 ? 0u : 1u;
-                        gt_mma(dcol, al, bh, idesc, first);
-                        gt_mma(dcol, ah, bl, idesc, 1u);
-                        gt_mma(dcol, ah, bh, idesc, 1u);
+                    asm volatile("fence.proxy.async;" ::: "memory");     // other CTAs' generic stores -> these bulk copies
+                    const uint8_t* src = image_of(grp, t & 1);
+                    for (int c = 0; c < NCH; ++c) {
+                        gt_expect(&bar_state[c], 2 * ch_bytes);
+                        gt_bulk_g2s(s_state + c * ch_bytes, src + c * ch_bytes, ch_bytes, &bar_state[c]);
+                        gt_bulk_g2s(s_state + nkb * 1024u + c * ch_bytes, src + nkb * 1024u + c * ch_bytes, ch_bytes, &bar_state[c]);
                     }
-                    gt_commit(&bar_acc);
                 }
                 __syncwarp();
+                for (int c = 0; c < NCH; ++c) {
+                    gt_mbar_wait(&bar_state[c], it & 1u);
+                    if (lane == 0 && c == 0) GT_STAMP(0, t, 2);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (gt_elect()) {
+                        const int s0 = c * (k16 / NCH), s1 = s0 + k16 / NCH;
+                        for (int s = s0; s < s1; ++s) {
+                            const uint32_t o = (uint32_t)(s >> 2) * GT_WBLK + (uint32_t)(s & 3) * 32u;
+                            const uint32_t ob = (uint32_t)(s >> 2) * 1024u + (uint32_t)(s & 3) * 32u;
+                            // B: 16 "environment" rows = the group's 8 (first atom) + 8 junk rows: the second atom is made
+                            // to alias the start of the weight image (finite values) through SBO = size of the state image
+                            const uint64_t bh = gt_desc(s_state + ob, 16, st_bytes), bl = gt_desc(s_state + nkb * 1024u + ob, 16, st_bytes);
+                            const uint32_t dcol = tmem + (uint32_t)(s / per_acc) * 16u;
+                            const uint32_t first = (s % per_acc) == 0 ? 0u : 1u;
+                            if (TA) {
+                                const uint64_t al = gt_desc(s_w + o, 16, 1024);
+                                const uint32_t ah = tmem + 64u + 8u * (uint32_t)s;
+                                gt_mma(dcol, al, bh, idesc, first);
+                                gt_mma_ts(dcol, ah, bl, idesc, 1u);
+                                gt_mma_ts(dcol, ah, bh, idesc, 1u);
+                            } else {
+                                const uint64_t ah = gt_desc(s_w + o, 16, 1024), al = gt_desc(s_w + w_plane + o, 16, 1024);
+                                gt_mma(dcol, al, bh, idesc, first);
+                                gt_mma(dcol, ah, bl, idesc, 1u);
+                                gt_mma(dcol, ah, bh, idesc, 1u);
+                            }
+                        }
+                        if (c == NCH - 1) gt_commit(&bar_acc);
+                    }
+                    __syncwarp();
+                }
                 if (lane == 0) GT_STAMP(0, t, 3);
             } else if (warp < 3) {
                 // ===== drain: gate `warp`, row = lane: 4 accumulators x 8 environments =====
@@ -361,7 +433,7 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == GT_CTRL)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -370,6 +442,10 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
 // gate-gradient rows x its weight slice -> partial carries of ALL units (M = units, K = 96), written to the owners.
 // Shared memory: [weight image][tail][gate-gradient operand: 2 planes x 2 blocks x 16 rows x 128 B].
 // ---------------------------------------------------------------------------------------------------------------
+// TA: both planes of the TRANSPOSED weight slice (M = units, K = the CTA's 96 gate rows) live in tensor memory: per
+// 128-unit block and plane 48 columns (column c = gate rows 2 c, 2 c + 1), 384 columns behind the 64 accumulator columns
+// for H = 512 -- no weight image in shared memory at all, every MMA reads only the 512-byte gate-gradient operand from it.
+template <bool TA>
 __global__ void __launch_bounds__(GT_NT, 1)
 gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws, const int swap_strides,
                   const int dbg) {
@@ -381,30 +457,60 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
     const uint32_t base = (gt_smem(gt_dyn) + 1023u) & ~1023u;
     uint8_t* sm = gt_dyn + (base - gt_smem(gt_dyn));
     const uint32_t w_plane = (uint32_t)nkb * GT_WBLK;
-    const uint32_t s_w = base, s_g = base + 2 * w_plane + 4096u;          // gate-gradient operand behind the 4 KiB tail
-    uint8_t* gop = sm + 2 * w_plane + 4096u;
+    const uint32_t g_off = TA ? 0u : 2 * w_plane + 4096u;                  // gate-gradient operand (behind the image + 4 KiB tail)
+    const uint32_t s_w = base, s_g = base + g_off;
+    uint8_t* gop = sm + g_off;
     constexpr uint32_t G_PLANE = 2 * 2048;                                 // [2 blocks of 64 rows-of-K][16 rows x 128 B]
+    constexpr uint32_t TCOLS = TA ? 512u : 64u;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ub = blockIdx.x * GT_UB, ku = ub + lane;
     const int ngrp = (d.N + GT_RW - 1) / GT_RW;
 
-    const float sw = gt_build_weights(sm, Whh, H, ub, red);
-    for (int i = tid; i < (int)(2 * G_PLANE / 16); i += GT_NT) reinterpret_cast<uint4*>(gop)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
         gt_mbar_init(&bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == GT_CTRL) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem(&tmem_slot)), "r"(64u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem(&tmem_slot)), "r"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    const float sw = gt_build_weights(sm, Whh, H, ub, red, TA ? 0 : 3);
+    for (int i = tid; i < (int)(2 * G_PLANE / 16); i += GT_NT) reinterpret_cast<uint4*>(gop)[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    // D fp32, A fp16 MN-major (units contiguous), B fp16 K-major, N = 16, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (TA) {
+        // thread (warp w < 4, lane) owns unit 128 mb + 32 w + lane of every block mb; gate row j <-> weight row
+        // (j / 32) H + ub + j % 32: for a fixed j the lanes read consecutive columns (coalesced)
+        if (warp < 4) {
+            for (int mb = 0; mb < n_mb; ++mb) {
+                const int u = mb * 128 + 32 * warp + lane;
+                for (int j0 = 0; j0 < GT_ROWS; j0 += 16) {
+                    uint32_t rh[8], rl[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int ja = j0 + 2 * q, jb = ja + 1;
+                        const uint32_t pa = gt_split(Whh[(long)((ja >> 5) * H + ub + (ja & 31)) * H + u] * sw);
+                        const uint32_t pb = gt_split(Whh[(long)((jb >> 5) * H + ub + (jb & 31)) * H + u] * sw);
+                        rh[q] = (pa & 0xffffu) | (pb << 16);
+                        rl[q] = (pa >> 16) | (pb & 0xffff0000u);
+                    }
+                    const uint32_t col = 64u + (uint32_t)(mb * 2) * 48u + (uint32_t)(j0 / 2);
+                    gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + col, rh);
+                    gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + col + 48u, rl);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // D fp32, B fp16 K-major, N = 16, M = 128; A fp16: K-major from tensor memory (TA) | MN-major (units contiguous) from
+    // the shared-memory image
+    const uint32_t idesc = (1u << 4) | (TA ? 0u : (1u << 15)) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // MN-major SWIZZLE_128B: 64 units (128 B) x 8 gate rows per atom; LBO = next 64 units, SBO = next 8 gate rows
     const uint32_t a_lbo = swap_strides ? 1024u : (uint32_t)GT_WBLK, a_sbo = swap_strides ? (uint32_t)GT_WBLK : 1024u;
 
@@ -493,13 +599,20 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                             const uint32_t dcol = tmem + (uint32_t)mb * 16u;
 #pragma unroll
                             for (int j = 0; j < GT_ROWS / 16; ++j) {
-                                const uint32_t oa = (uint32_t)(2 * mb) * GT_WBLK + (uint32_t)j * 2048u;
                                 const uint32_t ob = (uint32_t)(j >> 2) * 2048u + (uint32_t)(j & 3) * 32u;
-                                const uint64_t ah = gt_desc(s_w + oa, a_lbo, a_sbo), al = gt_desc(s_w + w_plane + oa, a_lbo, a_sbo);
                                 const uint64_t bh = gt_desc(s_g + ob, 16, 1024), bl = gt_desc(s_g + G_PLANE + ob, 16, 1024);
-                                gt_mma(dcol, al, bh, idesc, j == 0 ? 0u : 1u);
-                                gt_mma(dcol, ah, bl, idesc, 1u);
-                                gt_mma(dcol, ah, bh, idesc, 1u);
+                                if (TA) {
+                                    const uint32_t ah = tmem + 64u + (uint32_t)(mb * 2) * 48u + 8u * (uint32_t)j, al = ah + 48u;
+                                    gt_mma_ts(dcol, al, bh, idesc, j == 0 ? 0u : 1u);
+                                    gt_mma_ts(dcol, ah, bl, idesc, 1u);
+                                    gt_mma_ts(dcol, ah, bh, idesc, 1u);
+                                } else {
+                                    const uint32_t oa = (uint32_t)(2 * mb) * GT_WBLK + (uint32_t)j * 2048u;
+                                    const uint64_t ah = gt_desc(s_w + oa, a_lbo, a_sbo), al = gt_desc(s_w + w_plane + oa, a_lbo, a_sbo);
+                                    gt_mma(dcol, al, bh, idesc, j == 0 ? 0u : 1u);
+                                    gt_mma(dcol, ah, bl, idesc, 1u);
+                                    gt_mma(dcol, ah, bh, idesc, 1u);
+                                }
                             }
                         }
                         gt_commit(&bar_acc);
@@ -541,14 +654,22 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == GT_CTRL)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static size_t gt_smem_fwd(int H) { return (size_t)2 * (H / 64) * 1024 + (size_t)2 * (H / 64) * GT_WBLK + 4096 + 1024; }
-static size_t gt_smem_bwd(int H) { return (size_t)2 * (H / 64) * GT_WBLK + 4096 + 8192 + 1024; }
+// weights resident in tensor memory (default) or in shared memory only (A2CB_GRU_TC_TMEM=0)
+static bool gt_tmem_weights() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("A2CB_GRU_TC_TMEM"); mode = (e && e[0] == '0') ? 0 : 1; }
+    return mode == 1;
+}
+static size_t gt_smem_fwd(int H) {
+    return (size_t)2 * (H / 64) * 1024 + (size_t)(gt_tmem_weights() ? 1 : 2) * (H / 64) * GT_WBLK + 4096 + 1024;
+}
+static size_t gt_smem_bwd(int H) { return (gt_tmem_weights() ? 0 : (size_t)2 * (H / 64) * GT_WBLK + 4096) + 8192 + 1024; }
 
 static int gt_sms() {
     static int sms = 0;
@@ -599,9 +720,11 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
     // dynamic shared memory: exactly what this H needs (the device limit of 227 KiB includes the kernels' few static bytes)
     static int attr_h[2] = {0, 0};
     if (attr_h[backward ? 1 : 0] < d.H) {
-        const cudaError_t ea = backward
-            ? cudaFuncSetAttribute(gru_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_bwd(d.H))
-            : cudaFuncSetAttribute(gru_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_fwd(d.H));
+        const bool ta = gt_tmem_weights();
+        const void* kfn = backward ? (ta ? (const void*)gru_tc_bwd_kernel<true> : (const void*)gru_tc_bwd_kernel<false>)
+                                   : (ta ? (const void*)gru_tc_fwd_kernel<true> : (const void*)gru_tc_fwd_kernel<false>);
+        const cudaError_t ea = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)(backward ? gt_smem_bwd(d.H) : gt_smem_fwd(d.H)));
         if (ea != cudaSuccess) {
             set_error("gru_tc: shared memory attribute (%zu bytes): %s", backward ? gt_smem_bwd(d.H) : gt_smem_fwd(d.H),
                       cudaGetErrorString(ea));
@@ -633,9 +756,11 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
     void* args_f[] = {(void*)&dd, (void*)&Whh, (void*)&bhh, (void*)&dbg};
     void* args_b[] = {(void*)&dd, (void*)&Whh, (void*)&ws, (void*)&sw, (void*)&dbg};
     dim3 grid((unsigned)ug, (unsigned)gy);
-    cudaError_t e = backward
-        ? cudaLaunchCooperativeKernel((const void*)gru_tc_bwd_kernel, grid, dim3(GT_NT), args_b, gt_smem_bwd(d.H), st)
-        : cudaLaunchCooperativeKernel((const void*)gru_tc_fwd_kernel, grid, dim3(GT_NT), args_f, gt_smem_fwd(d.H), st);
+    const bool ta = gt_tmem_weights();
+    const void* kf = ta ? (const void*)gru_tc_fwd_kernel<true> : (const void*)gru_tc_fwd_kernel<false>;
+    const void* kb = ta ? (const void*)gru_tc_bwd_kernel<true> : (const void*)gru_tc_bwd_kernel<false>;
+    cudaError_t e = backward ? cudaLaunchCooperativeKernel(kb, grid, dim3(GT_NT), args_b, gt_smem_bwd(d.H), st)
+                             : cudaLaunchCooperativeKernel(kf, grid, dim3(GT_NT), args_f, gt_smem_fwd(d.H), st);
     if (e != cudaSuccess) {
         set_error("gru_tc: cooperative launch failed: %s", cudaGetErrorString(e));
         cudaGetLastError();
