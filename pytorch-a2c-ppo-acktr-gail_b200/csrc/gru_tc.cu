@@ -6,20 +6,24 @@
 // exchanged state, a shared-memory fold of eight partial tiles.  Here
 //   * the CTA's slice of W_hh (the 96 gate rows of its 32 hidden units) is converted ONCE, at kernel start, into two
 //     fp16 planes w = (w_hi + w_lo) / s_W (scaled by a power of two so that w_lo stays a normal fp16: 22 significant
-//     bits, the same 4 bytes per element as fp32) laid out as the canonical 128-byte-swizzled UMMA operand.  The SAME
-//     image serves both directions: K-major A operand [gate rows x units] forward, MN-major A operand
-//     [units x gate rows] backward (the 8-row x 128-byte swizzle atom is identical for both views);
+//     bits, the same 4 bytes per element as fp32).  Forward: the hi plane lives in TENSOR MEMORY (A operand of a
+//     tcgen05.mma with the operand in TMEM: 21 cycles per M = 128, N = 16, K = 16 instruction, tools/mma_probe.cu), the lo
+//     plane in shared memory as the canonical 128-byte-swizzled K-major UMMA operand (46 cycles per instruction: the
+//     4 KiB A read, whatever N is).  Backward: both planes of the TRANSPOSED slice live in tensor memory;
 //   * the exchanged operand of a step (forward: the masked state of the group's 8 environments; backward: the CTA's own
-//     gate gradients) is written by its producers as fp16 hi / lo planes ALREADY in that shared-memory image layout, so a
-//     consumer CTA fetches the whole state of a step with ONE bulk copy (cp.async.bulk global -> shared, completion on
-//     an mbarrier) and one elected thread issues the 96 (forward) / 72 (backward) tcgen05.mma.kind::f16 of the step:
-//     x w = x_hi w_hi + x_lo w_hi + x_hi w_lo with fp32 accumulation in TMEM, split over four accumulators so that the
-//     tensor core's truncating accumulation sees chains of at most 24 instructions;
-//   * forward: all-gather of the state through L2 (each CTA contributes 32 units, reads 512); backward: every CTA
-//     multiplies ITS gate gradients (K = 96) by its weight slice for ALL units and the 16 partial products are summed
-//     by their owners (reduce-scatter through L2, fixed order: deterministic) -- no gate gradient ever needs to be
-//     gathered before the product;
-//   * one release / acquire counter per environment group and step, as before; environments are independent.
+//     gate gradients) is split into fp16 hi / lo and laid out as ONE 16-row B operand: rows 0..7 the hi parts of the 8
+//     environments, rows 8..15 their lo parts.  One instruction W_p x [x_hi | x_lo] therefore yields both products of a
+//     weight plane p, and a reduction step costs TWO instructions (W_hi, W_lo) instead of three; the epilogue adds
+//     accumulator columns e and e + 8: (W_hi + W_lo)(x_hi + x_lo), fp32 accumulation in TMEM, split over up to four
+//     accumulators so that the tensor core's truncating accumulation sees chains of at most 24 instructions;
+//   * forward: all-gather of the state through L2: producers write fp16 planes ALREADY in the shared-memory image layout,
+//     a consumer CTA fetches the state of a step with bulk copies (cp.async.bulk global -> shared, one mbarrier per
+//     chunk of k-blocks, so that the instructions of chunk c overlap the arrival of chunk c + 1).  A ninth warp does
+//     nothing but poll, fetch and issue; the eight gate warps never wait for it except through the accumulator barrier;
+//   * backward: every CTA multiplies ITS gate gradients (K = 96) by its weight slice for ALL units and the 16 partial
+//     products are summed by their owners (reduce-scatter through L2, fixed order: deterministic) -- no gate gradient
+//     ever needs to be gathered before the product;
+//   * one release / acquire counter per environment group and step; environments are independent.
 // Ownership, saved quantities, buffers and the gate arithmetic are those of gru_persistent.cu, so either path feeds
 // the same weight-gradient products and the same tests.
 #include <cuda_fp16.h>
@@ -33,7 +37,8 @@ namespace a2cb {
 
 namespace {
 
-constexpr int GT_NT = 256;                    // 8 warps: thread (warp e, lane u) owns (environment e, unit u)
+constexpr int GT_GW = 8;                      // gate warps: thread (warp e, lane u) owns (environment e, unit u)
+constexpr int GT_NT = 32 * (GT_GW + 1);       // + the control warp
 constexpr int GT_RW = 8;                      // environments per group
 constexpr int GT_UB = 32;                     // hidden units per CTA
 constexpr int GT_ROWS = 3 * GT_UB;            // gate rows per CTA: row g * 32 + u
@@ -42,7 +47,8 @@ constexpr int GT_MAX_H = 512;
 constexpr int GT_MAX_GROUPS = 64;             // environment groups per launch (N <= 512)
 constexpr int GT_IMG_BYTES = 2 * (GT_MAX_H / 64) * 1024;              // state image of one group and step (both planes)
 constexpr int GT_PART_FLOATS = (GT_MAX_H / 32) * (GT_MAX_H / 32) * GT_RW * GT_UB;   // partial carries of one group and step
-constexpr int GT_CTRL = 4;                    // control warp: polls, issues the bulk copy and the MMAs
+constexpr int GT_CTRL = GT_GW;                // control warp: polls, issues the bulk copies and the MMAs
+constexpr uint32_t GT_ACC_COLS = 64;          // tensor-memory columns of the accumulators (4 x 16)
 constexpr float GT_SX = 16.f;                 // power-of-two scale of the forward state planes
 
 __device__ unsigned gt_flags[2][GT_MAX_GROUPS];
@@ -136,6 +142,23 @@ __device__ __forceinline__ void gt_ld8(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 16 accumulator columns of this thread's row; the wait "touches" the registers so that their uses stay behind it
+__device__ __forceinline__ void gt_ld16_issue(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void gt_ld_wait16(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void gt_gate_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * GT_GW) : "memory"); }
 __device__ __forceinline__ unsigned gt_ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -200,31 +223,39 @@ __device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, i
 
 }  // namespace
 
+// tensor-memory columns to allocate: a power of two >= 32
+__host__ __device__ constexpr uint32_t gt_tmem_cols(uint32_t need) {
+    return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // forward.  grid (H / 32 unit groups, resident environment groups); CTA (bx, by) owns units 32 bx .. 32 bx + 31 and
-// the environment groups by, by + gridDim.y, ...  Shared memory: [state image][weight image][tail].
+// the environment groups by, by + gridDim.y, ...  Shared memory: [state image: hi plane, lo plane][lo weight plane][tail].
+// Tensor memory: [accumulators: 64 columns][hi weight plane: 128 lanes (96 used) x H / 2 columns].
+// NKB = H / 64 k-blocks (template: every descriptor offset of the issue loop is a compile-time constant).
 // ---------------------------------------------------------------------------------------------------------------
-// TA: the hi plane of the weight slice lives in TENSOR MEMORY (128 lanes x H / 2 columns behind the accumulators) and is
-// the A operand of two of the three products of every reduction step; only the lo plane stays in shared memory.  With
-// both planes in shared memory every MMA streams 4 KiB of A through the shared-memory port (~59 cycles per instruction
-// measured, 5,700 of the 10,200 cycles of a step).
-template <bool TA>
+template <int NKB>
 __global__ void __launch_bounds__(GT_NT, 1)
 gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh, const int dbg) {
+    constexpr int H = NKB * 64, UG = H / 32;
+    constexpr int NCH = (NKB % 4 == 0) ? 4 : 2;                             // chunks of the state fetch = accumulators
+    constexpr int SPC = NKB * 4 / NCH;                                      // 16-element reduction steps per chunk
+    constexpr uint32_t ST_PLANE = (uint32_t)NKB * 1024u;                    // one plane of the state image: [NKB][8 rows x 128 B]
+    constexpr uint32_t ST_BYTES = 2u * ST_PLANE;
+    constexpr uint32_t W_PLANE = (uint32_t)NKB * GT_WBLK;
+    constexpr uint32_t CH_BYTES = (uint32_t)(NKB / NCH) * 1024u;            // per plane and chunk
+    constexpr uint32_t TCOLS = gt_tmem_cols(GT_ACC_COLS + H / 2);
+    static_assert(NCH * 16 <= (int)GT_ACC_COLS && 2 * SPC <= 24, "gru_tc_fwd: accumulator chains");
     extern __shared__ uint8_t gt_dyn[];
     __shared__ uint64_t bar_state[4], bar_acc;
     __shared__ uint32_t tmem_slot;
     __shared__ float red[GT_NT / 32];
-    const int H = d.H, nkb = H >> 6, ug = H >> 5;
     const uint32_t base = (gt_smem(gt_dyn) + 1023u) & ~1023u;
     uint8_t* sm = gt_dyn + (base - gt_smem(gt_dyn));
-    const uint32_t st_bytes = 2u * nkb * 1024u;           // state image: [2 planes][nkb][8 rows x 128 B]
-    const uint32_t w_plane = (uint32_t)nkb * GT_WBLK;
-    const uint32_t s_state = base, s_w = base + st_bytes;
-    constexpr int NPL = TA ? 1 : 2;                                        // weight planes in shared memory
-    constexpr uint32_t TCOLS = TA ? 512u : 64u;                            // tensor memory: 64 accumulator columns (+ H / 2)
-    float* xchg = reinterpret_cast<float*>(sm + st_bytes + NPL * w_plane);    // [3 gates][8 environments][32 units]
+    const uint32_t s_state = base, s_w = base + ST_BYTES;
+    float* xchg = reinterpret_cast<float*>(sm + ST_BYTES + W_PLANE);        // [3 gates][8 environments][32 units]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool gate = warp < GT_GW;
     const int ub = blockIdx.x * GT_UB, ku = ub + lane;
     const int ngrp = (d.N + GT_RW - 1) / GT_RW;
     const bool single = ngrp <= (int)gridDim.y;
@@ -238,47 +269,36 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem(&tmem_slot)), "r"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    const float sw = gt_build_weights(sm + st_bytes, Whh, H, ub, red, TA ? 2 : 3);
+    const float sw = gt_build_weights(sm + ST_BYTES, Whh, H, ub, red, 2);  // lo plane -> shared memory
     const float inv_scale = 1.f / (sw * GT_SX);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // weight image: generic stores -> tensor-core reads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    if (TA) {
-        // hi plane -> tensor memory: thread (warp w < 4, lane) owns row 32 w + lane (rows >= 96: zero); column
-        // 64 + c holds reduction elements 2 c, 2 c + 1 of that row
-        if (warp < 4) {
-            const int row = 32 * warp + lane;
-            const float* wr = Whh + (long)((row >> 5) * H + ub + (row & 31)) * H;       // rows >= 96 never dereferenced
-            for (int c0 = 0; c0 < H / 2; c0 += 8) {
-                uint32_t r[8];
+    // hi plane -> tensor memory: thread (warp w < 4, lane) owns row 32 w + lane (rows >= 96: zero); column
+    // GT_ACC_COLS + c holds reduction elements 2 c, 2 c + 1 of that row
+    if (warp < 4) {
+        const int row = 32 * warp + lane;
+        const float* wr = Whh + (long)((row >> 5) * H + ub + (row & 31)) * H;       // rows >= 96 never dereferenced
+        for (int c0 = 0; c0 < H / 2; c0 += 8) {
+            uint32_t r[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint32_t lo16 = 0u, hi16 = 0u;
-                    if (row < GT_ROWS) {
-                        lo16 = gt_split(wr[2 * (c0 + j)] * sw) & 0xffffu;
-                        hi16 = gt_split(wr[2 * (c0 + j) + 1] * sw) & 0xffffu;
-                    }
-                    r[j] = lo16 | (hi16 << 16);
+            for (int j = 0; j < 8; ++j) {
+                uint32_t lo16 = 0u, hi16 = 0u;
+                if (row < GT_ROWS) {
+                    lo16 = gt_split(wr[2 * (c0 + j)] * sw) & 0xffffu;
+                    hi16 = gt_split(wr[2 * (c0 + j) + 1] * sw) & 0xffffu;
                 }
-                gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + 64u + (uint32_t)c0, r);
+                r[j] = lo16 | (hi16 << 16);
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + GT_ACC_COLS + (uint32_t)c0, r);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    const float bias = warp < 3 ? bhh[warp * H + ku] : 0.f;               // drain warp g adds b_hh of gate g
-    // the state of a step arrives in NCH chunks of k-blocks (one mbarrier each): the MMAs of accumulator c only wait
-    // for chunk c, so most of the fetch hides behind the MMAs of the earlier chunks
-    const int NCH = (nkb % 4 == 0) ? 4 : 1;
-    const uint32_t ch_bytes = (uint32_t)(nkb / NCH) * 1024u;               // per plane and chunk
-
-    // instruction descriptor: D fp32, A / B fp16, both K-major, N = 16, M = 128
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int k16 = H >> 4, per_acc = k16 >> 2;                            // 16-element reduction steps, steps per accumulator
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // writes this thread's masked state v of (environment `warp`, unit `lane`) into the group's image `img`
     auto put_state = [&](uint8_t* img, float v) {
@@ -290,7 +310,7 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                        w3 = __shfl_down_sync(0xffffffffu, w0, 6);
         if ((lane & 7) < 2) {                                             // lane 8 j: hi chunk of units 8 j .. 8 j + 7; 8 j + 1: lo chunk
             const int k = ub + (lane & ~7);
-            const uint32_t off = (uint32_t)(lane & 1) * (uint32_t)nkb * 1024u + gt_swz(warp, k, 1024);
+            const uint32_t off = (uint32_t)(lane & 1) * ST_PLANE + gt_swz(warp, k, 1024);
             *reinterpret_cast<uint4*>(img + off) = make_uint4(w0, w1, w2, w3);
         }
     };
@@ -302,42 +322,34 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
     float hm_cur = 0.f;                                                    // this thread's hm_t (single pass: kept in a register)
     for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
         const int my = grp * GT_RW + warp;
-        float v = 0.f;
-        if (my < d.N) {
-            v = d.h0[(long)my * H + ku] * gt_mask(d, 0, my);
-            d.hm[(long)my * H + ku] = v;
+        if (gate) {
+            float v = 0.f;
+            if (my < d.N) {
+                v = d.h0[(long)my * H + ku] * gt_mask(d, 0, my);
+                d.hm[(long)my * H + ku] = v;
+            }
+            put_state(image_of(grp, 0), v);
+            hm_cur = v;
         }
-        put_state(image_of(grp, 0), v);
-        hm_cur = v;
         __syncthreads();
         if (tid == 0) gt_release_add(&gt_flags[0][grp]);
     }
 
-    struct GateIn { float r, z, n, mnext; };
-    auto load_gi = [&](int t, int my) {
-        GateIn q = {0.f, 0.f, 0.f, 0.f};
-        if (my < d.N) {
-            const float* gi = d.gi + ((long)t * d.N + my) * 3 * H;
-            q.r = __ldg(gi + ku); q.z = __ldg(gi + H + ku); q.n = __ldg(gi + 2 * H + ku);
-            q.mnext = (t + 1 < d.T) ? gt_mask(d, t + 1, my) : 0.f;
-        }
-        return q;
-    };
-    GateIn pre = load_gi(0, blockIdx.y * GT_RW + warp);
-    uint32_t it = 0;                                                       // (step, pass) counter: barrier parities
-
-    for (int t = 0; t < d.T; ++t) {
-        for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y, ++it) {
-            const int my = grp * GT_RW + warp;
-            const bool live = my < d.N;
-            const long row = (long)t * d.N + my;
-            const GateIn q = single ? pre : load_gi(t, my);
-            const float hprev = single ? hm_cur : (live ? d.hm[row * H + ku] : 0.f);
-            if (warp == GT_CTRL) {
-                // ===== control warp: wait for the group's state of step t, fetch it, issue the step's MMAs =====
+    if (warp == GT_CTRL) {
+        // ===== control warp: per (step, group) wait for the group's state, fetch it, issue the step's instructions.
+        // It never meets the gate warps at a CTA barrier: the accumulators and the state image of step t + 1 cannot be
+        // touched before this CTA's own gate warps have released step t + 1, which they do after draining step t. =====
+        // instruction descriptor: D fp32, A / B fp16, both K-major, N = 16, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // B: 16 rows = the 8 environments' hi parts (first 8-row atom) and their lo parts (second atom, one plane further)
+        const uint64_t b0 = gt_desc(s_state, 16, ST_PLANE);
+        const uint64_t a0 = gt_desc(s_w, 16, 1024);                        // lo weight plane: 96 (128) rows, K-major
+        uint32_t it = 0;                                                   // (step, pass) counter: barrier parities
+        for (int t = 0; t < d.T; ++t) {
+            for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y, ++it) {
                 if (lane == 0) {
                     GT_STAMP(0, t, 0);
-                    const unsigned target = (unsigned)ug * (unsigned)(t + 1);
+                    const unsigned target = (unsigned)UG * (unsigned)(t + 1);
                     while (gt_ld_acquire(&gt_flags[0][grp]) < target) {}
                     GT_STAMP(0, t, 1);
                 }
@@ -345,88 +357,105 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                 if (gt_elect()) {
                     asm volatile("fence.proxy.async;" ::: "memory");     // other CTAs' generic stores -> these bulk copies
                     const uint8_t* src = image_of(grp, t & 1);
+#pragma unroll
                     for (int c = 0; c < NCH; ++c) {
-                        gt_expect(&bar_state[c], 2 * ch_bytes);
-                        gt_bulk_g2s(s_state + c * ch_bytes, src + c * ch_bytes, ch_bytes, &bar_state[c]);
-                        gt_bulk_g2s(s_state + nkb * 1024u + c * ch_bytes, src + nkb * 1024u + c * ch_bytes, ch_bytes, &bar_state[c]);
+                        gt_expect(&bar_state[c], 2 * CH_BYTES);
+                        gt_bulk_g2s(s_state + c * CH_BYTES, src + c * CH_BYTES, CH_BYTES, &bar_state[c]);
+                        gt_bulk_g2s(s_state + ST_PLANE + c * CH_BYTES, src + ST_PLANE + c * CH_BYTES, CH_BYTES, &bar_state[c]);
                     }
                 }
                 __syncwarp();
+#pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     gt_mbar_wait(&bar_state[c], it & 1u);
-                    if (lane == 0 && c == 0) GT_STAMP(0, t, 2);
+                    if (lane == 0) { if (c == 0) GT_STAMP(0, t, 2); else GT_STAMP(0, t, 10 + c); }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (gt_elect()) {
-                        const int s0 = c * (k16 / NCH), s1 = s0 + k16 / NCH;
-                        for (int s = s0; s < s1; ++s) {
+                        const uint32_t dcol = tmem + (uint32_t)c * 16u;
+#pragma unroll
+                        for (int j = 0; j < SPC; ++j) {
+                            const int s = c * SPC + j;                                     // compile-time after unrolling
                             const uint32_t o = (uint32_t)(s >> 2) * GT_WBLK + (uint32_t)(s & 3) * 32u;
                             const uint32_t ob = (uint32_t)(s >> 2) * 1024u + (uint32_t)(s & 3) * 32u;
-                            // B: 16 "environment" rows = the group's 8 (first atom) + 8 junk rows: the second atom is made
-                            // to alias the start of the weight image (finite values) through SBO = size of the state image
-                            const uint64_t bh = gt_desc(s_state + ob, 16, st_bytes), bl = gt_desc(s_state + nkb * 1024u + ob, 16, st_bytes);
-                            const uint32_t dcol = tmem + (uint32_t)(s / per_acc) * 16u;
-                            const uint32_t first = (s % per_acc) == 0 ? 0u : 1u;
-                            if (TA) {
-                                const uint64_t al = gt_desc(s_w + o, 16, 1024);
-                                const uint32_t ah = tmem + 64u + 8u * (uint32_t)s;
-                                gt_mma(dcol, al, bh, idesc, first);
-                                gt_mma_ts(dcol, ah, bl, idesc, 1u);
-                                gt_mma_ts(dcol, ah, bh, idesc, 1u);
-                            } else {
-                                const uint64_t ah = gt_desc(s_w + o, 16, 1024), al = gt_desc(s_w + w_plane + o, 16, 1024);
-                                gt_mma(dcol, al, bh, idesc, first);
-                                gt_mma(dcol, ah, bl, idesc, 1u);
-                                gt_mma(dcol, ah, bh, idesc, 1u);
-                            }
+                            const uint64_t b = b0 + (uint64_t)(ob >> 4);
+                            gt_mma(dcol, a0 + (uint64_t)(o >> 4), b, idesc, j == 0 ? 0u : 1u);   // W_lo [x_hi | x_lo]
+                            gt_mma_ts(dcol, tmem + GT_ACC_COLS + 8u * (uint32_t)s, b, idesc, 1u); // W_hi [x_hi | x_lo]
                         }
                         if (c == NCH - 1) gt_commit(&bar_acc);
                     }
                     __syncwarp();
+                    if (lane == 0 && c == 0) GT_STAMP(0, t, 10);
                 }
                 if (lane == 0) GT_STAMP(0, t, 3);
-            } else if (warp < 3) {
-                // ===== drain: gate `warp`, row = lane: 4 accumulators x 8 environments =====
-                gt_mbar_wait(&bar_acc, it & 1u);
-                if (tid == 0) GT_STAMP(0, t, 4);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    float v[8];
-                    gt_ld8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)a * 16u, v);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) s8[e] += v[e];
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) xchg[(warp * 8 + e) * 32 + lane] = s8[e] * inv_scale + bias;
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                if (tid == 0) GT_STAMP(0, t, 5);
             }
-            __syncthreads();                                               // gate pre-activations of W_hh hm_t + b_hh are in xchg
-            if (tid == 0) GT_STAMP(0, t, 6);
-            const float ghr = xchg[(0 * 8 + warp) * 32 + lane], ghz = xchg[(1 * 8 + warp) * 32 + lane],
-                        ghn = xchg[(2 * 8 + warp) * 32 + lane];
-            const float rr = gt_sigmoid(q.r + ghr);
-            const float zz = gt_sigmoid(q.z + ghz);
-            const float nn = tanhf(q.n + rr * ghn);
-            const float h = (1.f - zz) * nn + zz * hprev;
-            const float hm_next = live ? h * q.mnext : 0.f;
-            if (t + 1 < d.T) put_state(image_of(grp, (t + 1) & 1), hm_next);    // what the other CTAs wait for
-            hm_cur = hm_next;
-            if (tid == 0) GT_STAMP(0, t, 7);
-            __syncthreads();
-            if (tid == 0) GT_STAMP(0, t, 8);
-            if (tid == 0 && t + 1 < d.T) gt_release_add(&gt_flags[0][grp]);
-            if (tid == 0) GT_STAMP(0, t, 9);
-            // everything below is consumed by later kernels only
-            if (single && t + 1 < d.T) pre = load_gi(t + 1, my);
-            if (live) {
-                d.out[row * H + ku] = h;
-                if (d.r) {
-                    d.r[row * H + ku] = rr; d.z[row * H + ku] = zz; d.n[row * H + ku] = nn;
-                    d.gh[row * 3 * H + 2 * H + ku] = ghn;                  // the only part of gh the backward pass reads
+        }
+    } else {
+        const float bias = warp < 3 ? bhh[warp * H + ku] : 0.f;           // drain warp g adds b_hh of gate g
+        struct GateIn { float r, z, n, mnext; };
+        auto load_gi = [&](int t, int my) {
+            GateIn q = {0.f, 0.f, 0.f, 0.f};
+            if (my < d.N) {
+                const float* gi = d.gi + ((long)t * d.N + my) * 3 * H;
+                q.r = __ldg(gi + ku); q.z = __ldg(gi + H + ku); q.n = __ldg(gi + 2 * H + ku);
+                q.mnext = (t + 1 < d.T) ? gt_mask(d, t + 1, my) : 0.f;
+            }
+            return q;
+        };
+        GateIn pre = load_gi(0, blockIdx.y * GT_RW + warp);
+        uint32_t it = 0;
+        for (int t = 0; t < d.T; ++t) {
+            for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y, ++it) {
+                const int my = grp * GT_RW + warp;
+                const bool live = my < d.N;
+                const long row = (long)t * d.N + my;
+                const GateIn q = single ? pre : load_gi(t, my);
+                const float hprev = single ? hm_cur : (live ? d.hm[row * H + ku] : 0.f);
+                if (warp < 3) {
+                    // ===== drain: gate `warp`, row = lane: NCH accumulators x (8 environments hi | 8 lo) =====
+                    gt_mbar_wait(&bar_acc, it & 1u);
+                    if (tid == 0) GT_STAMP(0, t, 4);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t v[NCH][16];
+#pragma unroll
+                    for (int a = 0; a < NCH; ++a) gt_ld16_issue(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)a * 16u, v[a]);
+#pragma unroll
+                    for (int a = 0; a < NCH; ++a) gt_ld_wait16(v[a]);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        float s8 = 0.f;
+#pragma unroll
+                        for (int a = 0; a < NCH; ++a) s8 += __uint_as_float(v[a][e]) + __uint_as_float(v[a][e + 8]);
+                        xchg[(warp * 8 + e) * 32 + lane] = s8 * inv_scale + bias;
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (tid == 0) GT_STAMP(0, t, 5);
                 }
-                if (t + 1 < d.T) d.hm[(row + d.N) * H + ku] = hm_next;
+                gt_gate_barrier();                                         // gate pre-activations of W_hh hm_t + b_hh are in xchg
+                if (tid == 0) GT_STAMP(0, t, 6);
+                const float ghr = xchg[(0 * 8 + warp) * 32 + lane], ghz = xchg[(1 * 8 + warp) * 32 + lane],
+                            ghn = xchg[(2 * 8 + warp) * 32 + lane];
+                const float rr = gt_sigmoid(q.r + ghr);
+                const float zz = gt_sigmoid(q.z + ghz);
+                const float nn = tanhf(q.n + rr * ghn);
+                const float h = (1.f - zz) * nn + zz * hprev;
+                const float hm_next = live ? h * q.mnext : 0.f;
+                if (t + 1 < d.T) put_state(image_of(grp, (t + 1) & 1), hm_next);    // what the other CTAs wait for
+                hm_cur = hm_next;
+                if (tid == 0) GT_STAMP(0, t, 7);
+                gt_gate_barrier();
+                if (tid == 0) GT_STAMP(0, t, 8);
+                if (tid == 0 && t + 1 < d.T) gt_release_add(&gt_flags[0][grp]);
+                if (tid == 0) GT_STAMP(0, t, 9);
+                // everything below is consumed by later kernels only
+                if (single && t + 1 < d.T) pre = load_gi(t + 1, my);
+                if (live) {
+                    d.out[row * H + ku] = h;
+                    if (d.r) {
+                        d.r[row * H + ku] = rr; d.z[row * H + ku] = zz; d.n[row * H + ku] = nn;
+                        d.gh[row * 3 * H + 2 * H + ku] = ghn;              // the only part of gh the backward pass reads
+                    }
+                    if (t + 1 < d.T) d.hm[(row + d.N) * H + ku] = hm_next;
+                }
             }
         }
     }
@@ -440,29 +469,25 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
 // backward through time.  Same grid and ownership.  Per step: (A) element-wise gate gradients of the CTA's units
 // (needs the carry = dh z + the 16 partial products of the previous step that belong to its units), (B) the CTA's 96
 // gate-gradient rows x its weight slice -> partial carries of ALL units (M = units, K = 96), written to the owners.
-// Shared memory: [weight image][tail][gate-gradient operand: 2 planes x 2 blocks x 16 rows x 128 B].
+// Both planes of the TRANSPOSED weight slice live in tensor memory: per 128-unit block and plane 48 columns (column c =
+// gate rows 2 c, 2 c + 1) behind the 64 accumulator columns -- no weight image in shared memory at all; every
+// instruction reads only the 512-byte gate-gradient operand [8 environments hi | 8 lo] x 16 gate rows from it.
 // ---------------------------------------------------------------------------------------------------------------
-// TA: both planes of the TRANSPOSED weight slice (M = units, K = the CTA's 96 gate rows) live in tensor memory: per
-// 128-unit block and plane 48 columns (column c = gate rows 2 c, 2 c + 1), 384 columns behind the 64 accumulator columns
-// for H = 512 -- no weight image in shared memory at all, every MMA reads only the 512-byte gate-gradient operand from it.
-template <bool TA>
+template <int NKB>
 __global__ void __launch_bounds__(GT_NT, 1)
-gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws, const int swap_strides,
-                  const int dbg) {
+gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws, const int dbg) {
+    constexpr int H = NKB * 64, UG = H / 32, NMB = H / 128;
+    constexpr uint32_t TCOLS = gt_tmem_cols(GT_ACC_COLS + (uint32_t)NMB * 96u);
+    constexpr uint32_t G_BYTES = 2 * 2048;                                 // [2 blocks of 64 gate rows][16 rows x 128 B]
     extern __shared__ uint8_t gt_dyn[];
     __shared__ uint64_t bar_acc;
     __shared__ uint32_t tmem_slot;
     __shared__ float red[GT_NT / 32];
-    const int H = d.H, nkb = H >> 6, ug = H >> 5, n_mb = H >> 7;
     const uint32_t base = (gt_smem(gt_dyn) + 1023u) & ~1023u;
-    uint8_t* sm = gt_dyn + (base - gt_smem(gt_dyn));
-    const uint32_t w_plane = (uint32_t)nkb * GT_WBLK;
-    const uint32_t g_off = TA ? 0u : 2 * w_plane + 4096u;                  // gate-gradient operand (behind the image + 4 KiB tail)
-    const uint32_t s_w = base, s_g = base + g_off;
-    uint8_t* gop = sm + g_off;
-    constexpr uint32_t G_PLANE = 2 * 2048;                                 // [2 blocks of 64 rows-of-K][16 rows x 128 B]
-    constexpr uint32_t TCOLS = TA ? 512u : 64u;
+    uint8_t* gop = gt_dyn + (base - gt_smem(gt_dyn));
+    const uint32_t s_g = base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool gate = warp < GT_GW;
     const int ub = blockIdx.x * GT_UB, ku = ub + lane;
     const int ngrp = (d.N + GT_RW - 1) / GT_RW;
 
@@ -474,50 +499,46 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem(&tmem_slot)), "r"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    const float sw = gt_build_weights(sm, Whh, H, ub, red, TA ? 0 : 3);
-    for (int i = tid; i < (int)(2 * G_PLANE / 16); i += GT_NT) reinterpret_cast<uint4*>(gop)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const float sw = gt_build_weights(gop, Whh, H, ub, red, 0);           // scale only
+    for (int i = tid; i < (int)(G_BYTES / 16); i += GT_NT) reinterpret_cast<uint4*>(gop)[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    if (TA) {
-        // thread (warp w < 4, lane) owns unit 128 mb + 32 w + lane of every block mb; gate row j <-> weight row
-        // (j / 32) H + ub + j % 32: for a fixed j the lanes read consecutive columns (coalesced)
-        if (warp < 4) {
-            for (int mb = 0; mb < n_mb; ++mb) {
-                const int u = mb * 128 + 32 * warp + lane;
-                for (int j0 = 0; j0 < GT_ROWS; j0 += 16) {
-                    uint32_t rh[8], rl[8];
+    // thread (warp w < 4, lane) owns unit 128 mb + 32 w + lane of every block mb; gate row j <-> weight row
+    // (j / 32) H + ub + j % 32: for a fixed j the lanes read consecutive columns (coalesced)
+    if (warp < 4) {
+        for (int mb = 0; mb < NMB; ++mb) {
+            const int u = mb * 128 + 32 * warp + lane;
+            for (int j0 = 0; j0 < GT_ROWS; j0 += 16) {
+                uint32_t rh[8], rl[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int ja = j0 + 2 * q, jb = ja + 1;
-                        const uint32_t pa = gt_split(Whh[(long)((ja >> 5) * H + ub + (ja & 31)) * H + u] * sw);
-                        const uint32_t pb = gt_split(Whh[(long)((jb >> 5) * H + ub + (jb & 31)) * H + u] * sw);
-                        rh[q] = (pa & 0xffffu) | (pb << 16);
-                        rl[q] = (pa >> 16) | (pb & 0xffff0000u);
-                    }
-                    const uint32_t col = 64u + (uint32_t)(mb * 2) * 48u + (uint32_t)(j0 / 2);
-                    gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + col, rh);
-                    gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + col + 48u, rl);
+                for (int q = 0; q < 8; ++q) {
+                    const int ja = j0 + 2 * q, jb = ja + 1;
+                    const uint32_t pa = gt_split(Whh[(long)((ja >> 5) * H + ub + (ja & 31)) * H + u] * sw);
+                    const uint32_t pb = gt_split(Whh[(long)((jb >> 5) * H + ub + (jb & 31)) * H + u] * sw);
+                    rh[q] = (pa & 0xffffu) | (pb << 16);
+                    rl[q] = (pa >> 16) | (pb & 0xffff0000u);
                 }
+                const uint32_t col = GT_ACC_COLS + (uint32_t)mb * 96u + (uint32_t)(j0 / 2);
+                gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + col, rh);
+                gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + col + 48u, rl);
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
-    // D fp32, B fp16 K-major, N = 16, M = 128; A fp16: K-major from tensor memory (TA) | MN-major (units contiguous) from
-    // the shared-memory image
-    const uint32_t idesc = (1u << 4) | (TA ? 0u : (1u << 15)) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    // MN-major SWIZZLE_128B: 64 units (128 B) x 8 gate rows per atom; LBO = next 64 units, SBO = next 8 gate rows
-    const uint32_t a_lbo = swap_strides ? 1024u : (uint32_t)GT_WBLK, a_sbo = swap_strides ? (uint32_t)GT_WBLK : 1024u;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // D fp32, A fp16 K-major from tensor memory, B fp16 K-major, N = 16, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t b0 = gt_desc(s_g, 16, 1024);                            // rows 8..15 (the lo parts): the next 8-row atom
 
     struct PhaseA { float dout, r, z, n, hm, ghn, mnext; };
     auto load_a = [&](int t, int my) {
         PhaseA a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (my < d.N) {
+        if (gate && my < d.N) {
             const long row = (long)t * d.N + my;
             a.dout = d.dout[row * H + ku];
             a.r = d.r[row * H + ku]; a.z = d.z[row * H + ku]; a.n = d.n[row * H + ku];
@@ -536,7 +557,7 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
     for (int t = d.T - 1; t >= 0; --t) {
         for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
             const int my = grp * GT_RW + warp;
-            const bool live = my < d.N;
+            const bool live = gate && my < d.N;
             const bool first = grp == (int)blockIdx.y;
             const long row = (long)t * d.N + my;
             const PhaseA a = first ? pre : load_a(t, my);
@@ -545,20 +566,23 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
             if (t + 1 < d.T) {
                 if (tid == 0) {
                     GT_STAMP(1, t, 0);
-                    const unsigned target = (unsigned)ug * (unsigned)(d.T - 1 - t);
+                    const unsigned target = (unsigned)UG * (unsigned)(d.T - 1 - t);
                     while (gt_ld_acquire(&gt_flags[1][grp]) < target) {}
                     GT_STAMP(1, t, 1);
                 }
                 __syncthreads();
-                const float* p = part_of(grp, (t + 1) & 1) + (((size_t)blockIdx.x * ug) * GT_RW + warp) * GT_UB + lane;
-                float sum = 0.f;
-                for (int src = 0; src < ug; src += 4) {
-                    const float v0 = __ldcg(p + (size_t)(src + 0) * GT_RW * GT_UB), v1 = __ldcg(p + (size_t)(src + 1) * GT_RW * GT_UB),
-                                v2 = __ldcg(p + (size_t)(src + 2) * GT_RW * GT_UB), v3 = __ldcg(p + (size_t)(src + 3) * GT_RW * GT_UB);
-                    sum += (v0 + v1) + (v2 + v3);
+                if (gate) {
+                    const float* p = part_of(grp, (t + 1) & 1) + (((size_t)blockIdx.x * UG) * GT_RW + warp) * GT_UB + lane;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int src = 0; src < UG; src += 4) {
+                        const float v0 = __ldcg(p + (size_t)(src + 0) * GT_RW * GT_UB), v1 = __ldcg(p + (size_t)(src + 1) * GT_RW * GT_UB),
+                                    v2 = __ldcg(p + (size_t)(src + 2) * GT_RW * GT_UB), v3 = __ldcg(p + (size_t)(src + 3) * GT_RW * GT_UB);
+                        sum += (v0 + v1) + (v2 + v3);
+                    }
+                    const float c = (first ? carry0 : (live ? carry_ws[(long)my * H + ku] : 0.f)) + sum;
+                    dh += c * a.mnext;
                 }
-                const float c = (first ? carry0 : (live ? carry_ws[(long)my * H + ku] : 0.f)) + sum;
-                dh += c * a.mnext;
                 if (tid == 0) GT_STAMP(1, t, 2);
             }
             // ---- phase A ----
@@ -570,22 +594,23 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
             if (first) carry0 = dhz;
             else if (live) carry_ws[(long)my * H + ku] = dhz;
             if (t > 0) {
-                // ---- operand of the step: the CTA's gate gradients [8 environments x 96] as fp16 hi / lo, scaled by a
-                //      power of two chosen from this step's largest magnitude ----
+                // ---- operand of the step: the CTA's gate gradients [8 environments x 96] as fp16 hi (rows 0..7) / lo
+                //      (rows 8..15), scaled by a power of two chosen from this step's largest magnitude ----
                 float m = warp_max(fmaxf(fabsf(g0), fmaxf(fabsf(g1), fabsf(g2))));
                 if (lane == 0) red[warp] = m;
                 __syncthreads();
                 m = red[0];
 #pragma unroll
-                for (int w = 1; w < GT_NT / 32; ++w) m = fmaxf(m, red[w]);
+                for (int w = 1; w < GT_GW; ++w) m = fmaxf(m, red[w]);
                 const float sg = gt_pow2_scale(m, 12);
-                const float gv[3] = {g0, g1, g2};
+                if (gate) {
+                    const float gv[3] = {g0, g1, g2};
 #pragma unroll
-                for (int g = 0; g < 3; ++g) {
-                    const uint32_t p = gt_split(gv[g] * sg);
-                    const uint32_t off = gt_swz(warp, g * 32 + lane, 2048);
-                    *reinterpret_cast<unsigned short*>(gop + off) = (unsigned short)(p & 0xffffu);
-                    *reinterpret_cast<unsigned short*>(gop + G_PLANE + off) = (unsigned short)(p >> 16);
+                    for (int g = 0; g < 3; ++g) {
+                        const uint32_t p = gt_split(gv[g] * sg);
+                        *reinterpret_cast<unsigned short*>(gop + gt_swz(warp, g * 32 + lane, 2048)) = (unsigned short)(p & 0xffffu);
+                        *reinterpret_cast<unsigned short*>(gop + gt_swz(warp + 8, g * 32 + lane, 2048)) = (unsigned short)(p >> 16);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -595,24 +620,15 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                 if (warp == GT_CTRL) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (gt_elect()) {
-                        for (int mb = 0; mb < n_mb; ++mb) {
+#pragma unroll
+                        for (int mb = 0; mb < NMB; ++mb) {
                             const uint32_t dcol = tmem + (uint32_t)mb * 16u;
 #pragma unroll
                             for (int j = 0; j < GT_ROWS / 16; ++j) {
-                                const uint32_t ob = (uint32_t)(j >> 2) * 2048u + (uint32_t)(j & 3) * 32u;
-                                const uint64_t bh = gt_desc(s_g + ob, 16, 1024), bl = gt_desc(s_g + G_PLANE + ob, 16, 1024);
-                                if (TA) {
-                                    const uint32_t ah = tmem + 64u + (uint32_t)(mb * 2) * 48u + 8u * (uint32_t)j, al = ah + 48u;
-                                    gt_mma_ts(dcol, al, bh, idesc, j == 0 ? 0u : 1u);
-                                    gt_mma_ts(dcol, ah, bl, idesc, 1u);
-                                    gt_mma_ts(dcol, ah, bh, idesc, 1u);
-                                } else {
-                                    const uint32_t oa = (uint32_t)(2 * mb) * GT_WBLK + (uint32_t)j * 2048u;
-                                    const uint64_t ah = gt_desc(s_w + oa, a_lbo, a_sbo), al = gt_desc(s_w + w_plane + oa, a_lbo, a_sbo);
-                                    gt_mma(dcol, al, bh, idesc, j == 0 ? 0u : 1u);
-                                    gt_mma(dcol, ah, bl, idesc, 1u);
-                                    gt_mma(dcol, ah, bh, idesc, 1u);
-                                }
+                                const uint64_t b = b0 + (uint64_t)(((uint32_t)(j >> 2) * 2048u + (uint32_t)(j & 3) * 32u) >> 4);
+                                const uint32_t ah = tmem + GT_ACC_COLS + (uint32_t)mb * 96u + 8u * (uint32_t)j, al = ah + 48u;
+                                gt_mma_ts(dcol, al, b, idesc, j == 0 ? 0u : 1u);            // W_lo^T [g_hi | g_lo]
+                                gt_mma_ts(dcol, ah, b, idesc, 1u);                          // W_hi^T [g_hi | g_lo]
                             }
                         }
                         gt_commit(&bar_acc);
@@ -625,12 +641,17 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const float unscale = 1.f / (sw * sg);
                     float* pbase = part_of(grp, t & 1);
-                    for (int mb = 0; mb < n_mb; ++mb) {
-                        float v[8];
-                        gt_ld8(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)mb * 16u, v);
-                        float* p = pbase + ((size_t)((4 * mb + warp) * ug + blockIdx.x) * GT_RW) * GT_UB + lane;
+                    uint32_t v[NMB][16];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) __stcg(p + e * GT_UB, v[e] * unscale);
+                    for (int mb = 0; mb < NMB; ++mb) gt_ld16_issue(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)mb * 16u, v[mb]);
+#pragma unroll
+                    for (int mb = 0; mb < NMB; ++mb) gt_ld_wait16(v[mb]);
+#pragma unroll
+                    for (int mb = 0; mb < NMB; ++mb) {
+                        float* p = pbase + ((size_t)((4 * mb + warp) * UG + blockIdx.x) * GT_RW) * GT_UB + lane;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            __stcg(p + e * GT_UB, (__uint_as_float(v[mb][e]) + __uint_as_float(v[mb][e + 8])) * unscale);
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (tid == 0) GT_STAMP(1, t, 6);
@@ -660,16 +681,23 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-// weights resident in tensor memory (default) or in shared memory only (A2CB_GRU_TC_TMEM=0)
-static bool gt_tmem_weights() {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("A2CB_GRU_TC_TMEM"); mode = (e && e[0] == '0') ? 0 : 1; }
-    return mode == 1;
+static size_t gt_smem_fwd(int H) { return (size_t)2 * (H / 64) * 1024 + (size_t)(H / 64) * GT_WBLK + 4096 + 1024; }
+// the backward kernel needs 5 KiB; it asks for more than half an SM's shared memory so that two CTAs (512 tensor-memory
+// columns each) can never be placed on one SM
+static size_t gt_smem_bwd(int) { return 120 * 1024; }
+
+template <int NKB>
+static const void* gt_kernel(bool backward) {
+    return backward ? (const void*)gru_tc_bwd_kernel<NKB> : (const void*)gru_tc_fwd_kernel<NKB>;
 }
-static size_t gt_smem_fwd(int H) {
-    return (size_t)2 * (H / 64) * 1024 + (size_t)(gt_tmem_weights() ? 1 : 2) * (H / 64) * GT_WBLK + 4096 + 1024;
+static const void* gt_kernel_for(int H, bool backward) {
+    switch (H / 64) {
+        case 2: return gt_kernel<2>(backward);
+        case 4: return gt_kernel<4>(backward);
+        case 6: return gt_kernel<6>(backward);
+        default: return gt_kernel<8>(backward);
+    }
 }
-static size_t gt_smem_bwd(int H) { return (gt_tmem_weights() ? 0 : (size_t)2 * (H / 64) * GT_WBLK + 4096) + 8192 + 1024; }
 
 static int gt_sms() {
     static int sms = 0;
@@ -718,12 +746,9 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
     A2CB_REQUIRE(backward || (bhh && d.h0 && d.gi && d.out), "gru_tc: forward pointers");
     A2CB_REQUIRE(!backward || (d.r && d.z && d.n && d.gh && d.dout && d.dgi && d.dgh), "gru_tc: backward pointers");
     // dynamic shared memory: exactly what this H needs (the device limit of 227 KiB includes the kernels' few static bytes)
-    static int attr_h[2] = {0, 0};
-    if (attr_h[backward ? 1 : 0] < d.H) {
-        const bool ta = gt_tmem_weights();
-        const void* kfn = backward ? (ta ? (const void*)gru_tc_bwd_kernel<true> : (const void*)gru_tc_bwd_kernel<false>)
-                                   : (ta ? (const void*)gru_tc_fwd_kernel<true> : (const void*)gru_tc_fwd_kernel<false>);
-        const cudaError_t ea = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static bool attr_done[2][GT_MAX_H / 64 + 1] = {};
+    if (!attr_done[backward ? 1 : 0][d.H / 64]) {
+        const cudaError_t ea = cudaFuncSetAttribute(gt_kernel_for(d.H, backward != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)(backward ? gt_smem_bwd(d.H) : gt_smem_fwd(d.H)));
         if (ea != cudaSuccess) {
             set_error("gru_tc: shared memory attribute (%zu bytes): %s", backward ? gt_smem_bwd(d.H) : gt_smem_fwd(d.H),
@@ -731,10 +756,8 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
             cudaGetLastError();
             return A2CB_ERR_CUDA;
         }
-        attr_h[backward ? 1 : 0] = d.H;
+        attr_done[backward ? 1 : 0][d.H / 64] = true;
     }
-    static int swap = -1;                                                  // probe knob: exchange LBO / SBO of the MN-major operand
-    if (swap < 0) { const char* e = getenv("A2CB_GRU_TC_SWAP"); swap = (e && e[0] == '1') ? 1 : 0; }
     const int ug = d.H / GT_UB;
     const int ngrp = (d.N + GT_RW - 1) / GT_RW;
     int gy = gt_sms() / ug;
@@ -752,15 +775,11 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
     if (dbg < 0) { const char* e = getenv("A2CB_GRU_TC_DEBUG"); dbg = (e && e[0] == '1') ? 1 : 0; }
     GruDesc dd = d;
     float* ws = d.dcarry;
-    int sw = swap;
     void* args_f[] = {(void*)&dd, (void*)&Whh, (void*)&bhh, (void*)&dbg};
-    void* args_b[] = {(void*)&dd, (void*)&Whh, (void*)&ws, (void*)&sw, (void*)&dbg};
+    void* args_b[] = {(void*)&dd, (void*)&Whh, (void*)&ws, (void*)&dbg};
     dim3 grid((unsigned)ug, (unsigned)gy);
-    const bool ta = gt_tmem_weights();
-    const void* kf = ta ? (const void*)gru_tc_fwd_kernel<true> : (const void*)gru_tc_fwd_kernel<false>;
-    const void* kb = ta ? (const void*)gru_tc_bwd_kernel<true> : (const void*)gru_tc_bwd_kernel<false>;
-    cudaError_t e = backward ? cudaLaunchCooperativeKernel(kb, grid, dim3(GT_NT), args_b, gt_smem_bwd(d.H), st)
-                             : cudaLaunchCooperativeKernel(kf, grid, dim3(GT_NT), args_f, gt_smem_fwd(d.H), st);
+    cudaError_t e = cudaLaunchCooperativeKernel(gt_kernel_for(d.H, backward != 0), grid, dim3(GT_NT), backward ? args_b : args_f,
+                                                backward ? gt_smem_bwd(d.H) : gt_smem_fwd(d.H), st);
     if (e != cudaSuccess) {
         set_error("gru_tc: cooperative launch failed: %s", cudaGetErrorString(e));
         cudaGetLastError();

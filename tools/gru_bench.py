@@ -80,6 +80,11 @@ def main():
             ok = slice(2, 14)
             print(json.dumps({"stamps": name, "phase_cycles_median": np.median(d[ok], axis=0).round(0).tolist(),
                               "step_cycles_median": float(np.median(np.abs(np.diff(st[:, 0]))[ok]))}))
+            # extra stamps (slots n..15), relative to the step's first stamp: forward 11..13 = arrival of state chunks 1..3,
+            # 10 = chunk 0's instructions issued
+            ex = buf[direction, :, n:].astype(np.float64) - buf[direction, :, :1].astype(np.float64)
+            print(json.dumps({"stamps": name + "_extra_since_stamp0", "slots": list(range(n, 16)),
+                              "cycles_median": np.median(ex[ok], axis=0).round(0).tolist()}))
     for cs in (16, 8, 4, 2):
         print(json.dumps({"cluster_size": cs, "max_active_clusters_217KB": int(lib.a2cb_gru_cluster_probe(cs, 217 * 1024)),
                           "max_active_clusters_100KB": int(lib.a2cb_gru_cluster_probe(cs, 100 * 1024))}))
