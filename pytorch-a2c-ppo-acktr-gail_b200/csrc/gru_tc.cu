@@ -82,6 +82,9 @@ __device__ __forceinline__ void gt_mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     }
 }
+__device__ __forceinline__ void gt_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gt_smem(bar)) : "memory");
+}
 __device__ __forceinline__ void gt_expect(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gt_smem(bar)), "r"(bytes) : "memory");
 }
@@ -133,15 +136,6 @@ __device__ __forceinline__ bool gt_elect() {
         : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void gt_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
 // 16 accumulator columns of this thread's row; the wait "touches" the registers so that their uses stay behind it
 __device__ __forceinline__ void gt_ld16_issue(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -189,7 +183,9 @@ __device__ __forceinline__ float gt_pow2_scale(float amax, int e) {
 // Converts the CTA's weight slice (rows g * H + ub + u, g < 3, u < 32, all H columns) into the two fp16 planes of the
 // UMMA image at `img` (plane stride = (H / 64) * GT_WBLK); returns the scale (w * scale = hi + lo).
 // `planes`: 3 = both planes (plane 1 behind plane 0), 2 = the lo plane only (at img), 0 = none (scale only).
-__device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, int H, int ub, float* red, int planes = 3) {
+// `k_first`: the image starts at reduction index k_first (a multiple of 64): only columns k >= k_first are written.
+__device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, int H, int ub, float* red, int planes = 3,
+                                  int k_first = 0) {
     const int tid = threadIdx.x;
     float amax = 0.f;
     for (int e = tid; e < GT_ROWS * H; e += GT_NT) {
@@ -208,8 +204,9 @@ __device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, i
     if (planes)
         for (int e = tid; e < GT_ROWS * H; e += GT_NT) {
             const int row = e / H, k = e - row * H;
+            if (k < k_first) continue;
             const uint32_t p = gt_split(Whh[(long)((row >> 5) * H + ub + (row & 31)) * H + k] * sw);
-            const uint32_t off = gt_swz(row, k, GT_WBLK);
+            const uint32_t off = gt_swz(row, k - k_first, GT_WBLK);
             if (planes == 3) {
                 *reinterpret_cast<unsigned short*>(img + off) = (unsigned short)(p & 0xffffu);
                 *reinterpret_cast<unsigned short*>(img + plane + off) = (unsigned short)(p >> 16);
@@ -242,9 +239,15 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
     constexpr int SPC = NKB * 4 / NCH;                                      // 16-element reduction steps per chunk
     constexpr uint32_t ST_PLANE = (uint32_t)NKB * 1024u;                    // one plane of the state image: [NKB][8 rows x 128 B]
     constexpr uint32_t ST_BYTES = 2u * ST_PLANE;
-    constexpr uint32_t W_PLANE = (uint32_t)NKB * GT_WBLK;
+    constexpr uint32_t W_PLANE = (uint32_t)(NKB - (4 * NKB < 56 - 4 * NKB ? NKB : (56 - 4 * NKB) / 4)) * GT_WBLK;   // lo k-blocks kept in shared memory
     constexpr uint32_t CH_BYTES = (uint32_t)(NKB / NCH) * 1024u;            // per plane and chunk
-    constexpr uint32_t TCOLS = gt_tmem_cols(GT_ACC_COLS + H / 2);
+    // the lo weight plane goes to tensor memory too as far as the 512 columns reach (H = 512: 24 of its 32 reduction
+    // steps); only the remaining k-blocks stay in shared memory and cost an instruction with a shared-memory A operand
+    constexpr int LO_TS = (4 * NKB < 56 - 4 * NKB) ? 4 * NKB : 56 - 4 * NKB;   // reduction steps of the lo plane in tensor memory
+    constexpr int LO_KB0 = LO_TS / 4;                                       // first k-block of the shared-memory lo image
+    constexpr uint32_t HI_COL0 = GT_ACC_COLS, LO_COL0 = GT_ACC_COLS + (uint32_t)H / 2;
+    constexpr uint32_t TCOLS = gt_tmem_cols(LO_COL0 + 8u * LO_TS);
+    static_assert(LO_TS % 4 == 0 && LO_COL0 + 8u * LO_TS <= 512u, "gru_tc_fwd: tensor-memory budget");
     static_assert(NCH * 16 <= (int)GT_ACC_COLS && 2 * SPC <= 24, "gru_tc_fwd: accumulator chains");
     extern __shared__ uint8_t gt_dyn[];
     __shared__ uint64_t bar_state[4], bar_acc;
@@ -261,7 +264,7 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
     const bool single = ngrp <= (int)gridDim.y;
 
     if (tid == 0) {
-        for (int c = 0; c < 4; ++c) gt_mbar_init(&bar_state[c], 1);
+        for (int c = 0; c < 4; ++c) gt_mbar_init(&bar_state[c], GT_GW / NCH);
         gt_mbar_init(&bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -269,30 +272,32 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gt_smem(&tmem_slot)), "r"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    const float sw = gt_build_weights(sm + ST_BYTES, Whh, H, ub, red, 2);  // lo plane -> shared memory
+    const float sw = gt_build_weights(sm + ST_BYTES, Whh, H, ub, red, LO_KB0 < NKB ? 2 : 0, LO_KB0 * 64);   // rest of the lo plane
     const float inv_scale = 1.f / (sw * GT_SX);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // weight image: generic stores -> tensor-core reads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
-    // hi plane -> tensor memory: thread (warp w < 4, lane) owns row 32 w + lane (rows >= 96: zero); column
-    // GT_ACC_COLS + c holds reduction elements 2 c, 2 c + 1 of that row
+    // weight planes -> tensor memory: thread (warp w < 4, lane) owns row 32 w + lane (rows >= 96: zero); column
+    // HI_COL0 + c (LO_COL0 + c) holds the hi (lo) parts of reduction elements 2 c, 2 c + 1 of that row
     if (warp < 4) {
         const int row = 32 * warp + lane;
         const float* wr = Whh + (long)((row >> 5) * H + ub + (row & 31)) * H;       // rows >= 96 never dereferenced
         for (int c0 = 0; c0 < H / 2; c0 += 8) {
-            uint32_t r[8];
+            uint32_t rh[8], rl[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                uint32_t lo16 = 0u, hi16 = 0u;
+                uint32_t pa = 0u, pb = 0u;
                 if (row < GT_ROWS) {
-                    lo16 = gt_split(wr[2 * (c0 + j)] * sw) & 0xffffu;
-                    hi16 = gt_split(wr[2 * (c0 + j) + 1] * sw) & 0xffffu;
+                    pa = gt_split(wr[2 * (c0 + j)] * sw);
+                    pb = gt_split(wr[2 * (c0 + j) + 1] * sw);
                 }
-                r[j] = lo16 | (hi16 << 16);
+                rh[j] = (pa & 0xffffu) | (pb << 16);
+                rl[j] = (pa >> 16) | (pb & 0xffff0000u);
             }
-            gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + GT_ACC_COLS + (uint32_t)c0, r);
+            gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + HI_COL0 + (uint32_t)c0, rh);
+            if (c0 < 8 * LO_TS) gt_st8(tmem + ((uint32_t)(32 * warp) << 16) + LO_COL0 + (uint32_t)c0, rl);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     }
@@ -336,38 +341,22 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
     }
 
     if (warp == GT_CTRL) {
-        // ===== control warp: per (step, group) wait for the group's state, fetch it, issue the step's instructions.
-        // It never meets the gate warps at a CTA barrier: the accumulators and the state image of step t + 1 cannot be
-        // touched before this CTA's own gate warps have released step t + 1, which they do after draining step t. =====
+        // ===== control warp: per (step, group) wait for the chunks of the group's state that the gate warps fetch into
+        // shared memory, issue the step's instructions.  It never meets the gate warps at a CTA barrier: they fetch the
+        // state of the next (step, group) only after their second gate barrier, i.e. after the accumulators of this one
+        // have been drained (and therefore after its instructions have read the state image). =====
         // instruction descriptor: D fp32, A / B fp16, both K-major, N = 16, M = 128
         const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         // B: 16 rows = the 8 environments' hi parts (first 8-row atom) and their lo parts (second atom, one plane further)
         const uint64_t b0 = gt_desc(s_state, 16, ST_PLANE);
-        const uint64_t a0 = gt_desc(s_w, 16, 1024);                        // lo weight plane: 96 (128) rows, K-major
+        const uint64_t a0 = gt_desc(s_w, 16, 1024);                        // lo weight plane, k-blocks >= LO_KB0: 96 (128) rows, K-major
         uint32_t it = 0;                                                   // (step, pass) counter: barrier parities
         for (int t = 0; t < d.T; ++t) {
             for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y, ++it) {
-                if (lane == 0) {
-                    GT_STAMP(0, t, 0);
-                    const unsigned target = (unsigned)UG * (unsigned)(t + 1);
-                    while (gt_ld_acquire(&gt_flags[0][grp]) < target) {}
-                    GT_STAMP(0, t, 1);
-                }
-                __syncwarp();
-                if (gt_elect()) {
-                    asm volatile("fence.proxy.async;" ::: "memory");     // other CTAs' generic stores -> these bulk copies
-                    const uint8_t* src = image_of(grp, t & 1);
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        gt_expect(&bar_state[c], 2 * CH_BYTES);
-                        gt_bulk_g2s(s_state + c * CH_BYTES, src + c * CH_BYTES, CH_BYTES, &bar_state[c]);
-                        gt_bulk_g2s(s_state + ST_PLANE + c * CH_BYTES, src + ST_PLANE + c * CH_BYTES, CH_BYTES, &bar_state[c]);
-                    }
-                }
-                __syncwarp();
+                if (lane == 0) GT_STAMP(0, t, 0);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
-                    gt_mbar_wait(&bar_state[c], it & 1u);
+                    gt_mbar_wait(&bar_state[c], it & 1u);                            // chunk c of the state image is in shared memory
                     if (lane == 0) { if (c == 0) GT_STAMP(0, t, 2); else GT_STAMP(0, t, 10 + c); }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (gt_elect()) {
@@ -375,11 +364,15 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
 #pragma unroll
                         for (int j = 0; j < SPC; ++j) {
                             const int s = c * SPC + j;                                     // compile-time after unrolling
-                            const uint32_t o = (uint32_t)(s >> 2) * GT_WBLK + (uint32_t)(s & 3) * 32u;
                             const uint32_t ob = (uint32_t)(s >> 2) * 1024u + (uint32_t)(s & 3) * 32u;
                             const uint64_t b = b0 + (uint64_t)(ob >> 4);
-                            gt_mma(dcol, a0 + (uint64_t)(o >> 4), b, idesc, j == 0 ? 0u : 1u);   // W_lo [x_hi | x_lo]
-                            gt_mma_ts(dcol, tmem + GT_ACC_COLS + 8u * (uint32_t)s, b, idesc, 1u); // W_hi [x_hi | x_lo]
+                            if (s < LO_TS) {                                               // W_lo [x_hi | x_lo]
+                                gt_mma_ts(dcol, tmem + LO_COL0 + 8u * (uint32_t)s, b, idesc, j == 0 ? 0u : 1u);
+                            } else {
+                                const uint32_t o = (uint32_t)((s >> 2) - LO_KB0) * GT_WBLK + (uint32_t)(s & 3) * 32u;
+                                gt_mma(dcol, a0 + (uint64_t)(o >> 4), b, idesc, j == 0 ? 0u : 1u);
+                            }
+                            gt_mma_ts(dcol, tmem + HI_COL0 + 8u * (uint32_t)s, b, idesc, 1u);  // W_hi [x_hi | x_lo]
                         }
                         if (c == NCH - 1) gt_commit(&bar_acc);
                     }
@@ -410,6 +403,36 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                 const long row = (long)t * d.N + my;
                 const GateIn q = single ? pre : load_gi(t, my);
                 const float hprev = single ? hm_cur : (live ? d.hm[row * H + ku] : 0.f);
+                // ---- fetch: every gate warp waits for the group's flag and copies its share of the state image with
+                //      16-byte cp.async (generic proxy, L2 only): warps c * GT_GW / NCH .. share chunk c of both planes.
+                //      (One bulk copy per chunk needs a cross-proxy fence between the other CTAs' generic stores and the
+                //      async-proxy reads -- fence.proxy.async measured 1,400 cycles here; one warp issuing all the
+                //      cp.async copies takes 3,800.) ----
+                {
+                    if (lane == 0) {
+                        const unsigned target = (unsigned)UG * (unsigned)(t + 1);
+                        while (gt_ld_acquire(&gt_flags[0][grp]) < target) {}
+                    }
+                    __syncwarp();
+                    if (tid == 0) GT_STAMP(0, t, 14);
+                    constexpr int WPC = GT_GW / NCH;                                 // warps per chunk
+                    constexpr int PER = 4 * NKB / NCH / WPC;                         // copies per lane
+                    constexpr int HALF16 = (int)(CH_BYTES / 16);                     // 16-byte pieces of one plane's share
+                    const int c = warp / WPC, wq = warp % WPC;
+                    const uint8_t* src = image_of(grp, t & 1);
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) {
+                        const int o16 = (wq * PER + i) * 32 + lane;
+                        const uint32_t o = (o16 >= HALF16 ? ST_PLANE + (uint32_t)(o16 - HALF16) * 16u : (uint32_t)o16 * 16u) + (uint32_t)c * CH_BYTES;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_state + o), "l"(src + o) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // these generic writes -> tensor-core reads
+                    __syncwarp();
+                    if (lane == 0) gt_mbar_arrive(&bar_state[c]);
+                    if (tid == 0) GT_STAMP(0, t, 15);
+                }
                 if (warp < 3) {
                     // ===== drain: gate `warp`, row = lane: NCH accumulators x (8 environments hi | 8 lo) =====
                     gt_mbar_wait(&bar_acc, it & 1u);
@@ -681,7 +704,13 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static size_t gt_smem_fwd(int H) { return (size_t)2 * (H / 64) * 1024 + (size_t)(H / 64) * GT_WBLK + 4096 + 1024; }
+// state image + the lo k-blocks that do not fit tensor memory + exchange tail; at least 120 KiB: one CTA per SM (each
+// allocates up to 512 tensor-memory columns)
+static size_t gt_smem_fwd(int H) {
+    const int nkb = H / 64, lo_ts = 4 * nkb < 56 - 4 * nkb ? 4 * nkb : 56 - 4 * nkb;
+    const size_t need = (size_t)2 * nkb * 1024 + (size_t)(nkb - lo_ts / 4) * GT_WBLK + 4096 + 1024;
+    return need > 120 * 1024 ? need : 120 * 1024;
+}
 // the backward kernel needs 5 KiB; it asks for more than half an SM's shared memory so that two CTAs (512 tensor-memory
 // columns each) can never be placed on one SM
 static size_t gt_smem_bwd(int) { return 120 * 1024; }

@@ -213,6 +213,29 @@ __global__ void __launch_bounds__(256, 1) xchg_probe(const uint4* src, uint4* ds
     }
 }
 
+// ---- 128 CTAs fetch 16 KiB each at the same moment (8 bulk copies of 2 KiB, as the GRU forward kernel does):
+//      mode 0 = every CTA its own 16 KiB, mode 1 = the 16 CTAs of a group read the SAME 16 KiB (all-gather image) ----
+__global__ void __launch_bounds__(32, 1) fetch_probe(const uint8_t* src, unsigned* counter, long long* out, int mode, int round) {
+    __shared__ __align__(1024) uint8_t buf[16384];
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint8_t* s = src + (size_t)(mode ? (blockIdx.x / 16) : blockIdx.x) * 16384 + (size_t)round * (4u << 20);
+        atomicAdd(counter, 1u);
+        while (*(volatile unsigned*)counter < gridDim.x) {}
+        const long long t0 = clock64();
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(16384u) : "memory");
+        for (int c = 0; c < 8; ++c)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(buf) + c * 2048u),
+                         "l"(s + c * 2048), "r"(2048u), "r"(smem_u32(&bar))
+                         : "memory");
+        mbar_wait(&bar, 0);
+        out[blockIdx.x] = clock64() - t0;
+    }
+}
+
 __global__ void fill(uint4* p, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = make_uint4(i, i, i, i);
 }
@@ -257,5 +280,24 @@ int main() {
            "\"fence_plus_red\": %lld, \"ld_acquire\": %lld, \"ld_relaxed\": %lld, \"ld_volatile\": %lld, \"ld_relaxed_v4\": %lld, "
            "\"red_relaxed_issue\": %lld}\n",
            ho[0], ho[1], ho[2], ho[3], ho[4], ho[5], ho[6], ho[7], ho[8], ho[9]);
+    // fetch probe: warm L2 with the source (fill wrote it), 2 modes x 2 rounds
+    unsigned* counters;
+    cudaMalloc(&counters, 64);
+    cudaMemset(counters, 0, 64);
+    uint8_t* big;
+    cudaMalloc(&big, 16u << 20);
+    fill<<<256, 256>>>(reinterpret_cast<uint4*>(big), (16 << 20) / 16);
+    cudaDeviceSynchronize();
+    for (int k = 0; k < 4; ++k) {
+        const int mode = k & 1;
+        fetch_probe<<<128, 32>>>(big, counters + k, out, mode, k);
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("fetch_probe failed: %s\n", cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(ho, out, sizeof(long long) * 128, cudaMemcpyDeviceToHost);
+        long long mx = 0, mn = 1ll << 60, sum = 0;
+        for (int i = 0; i < 128; ++i) { mx = ho[i] > mx ? ho[i] : mx; mn = ho[i] < mn ? ho[i] : mn; sum += ho[i]; }
+        printf("{\"probe\": \"fetch16k_x128\", \"same_image_per_16_ctas\": %d, \"round\": %d, \"min\": %lld, \"mean\": %lld, \"max\": %lld}\n",
+               mode, k, mn, sum / 128, mx);
+    }
     return 0;
 }
