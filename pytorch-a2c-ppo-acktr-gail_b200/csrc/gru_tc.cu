@@ -220,6 +220,21 @@ __device__ float gt_build_weights(uint8_t* img, const float* __restrict__ Whh, i
 
 }  // namespace
 
+// Episode masks of the CTA's environments for every step and pass -> shared memory, once.  The per-step lookup is a
+// DEPENDENT pair of loads (minibatch row list -> flat mask array) that sat at the end of every step, in front of the
+// next step's wait: 11 % (forward) / 14 % (backward) of all warp-stall samples (profiles/r02n_gru_full.txt).
+__device__ __forceinline__ void gt_fill_masks(float* msk, const GruDesc& d, int use_msk, int ngrp) {
+    if (use_msk) {
+        const int npass = (ngrp - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+        for (int i = threadIdx.x; i < npass * d.T * GT_RW; i += GT_NT) {
+            const int e = i % GT_RW, t = (i / GT_RW) % d.T, p = i / (GT_RW * d.T);
+            const int my = ((int)blockIdx.y + p * (int)gridDim.y) * GT_RW + e;
+            msk[i] = my < d.N ? gt_mask(d, t, my) : 0.f;
+        }
+    }
+    __syncthreads();
+}
+
 // tensor-memory columns to allocate: a power of two >= 32
 __host__ __device__ constexpr uint32_t gt_tmem_cols(uint32_t need) {
     return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
@@ -233,7 +248,7 @@ __host__ __device__ constexpr uint32_t gt_tmem_cols(uint32_t need) {
 // ---------------------------------------------------------------------------------------------------------------
 template <int NKB>
 __global__ void __launch_bounds__(GT_NT, 1)
-gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh, const int dbg) {
+gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh, const int use_msk, const int dbg) {
     constexpr int H = NKB * 64, UG = H / 32;
     constexpr int NCH = (NKB % 4 == 0) ? 4 : 2;                             // chunks of the state fetch = accumulators
     constexpr int SPC = NKB * 4 / NCH;                                      // 16-element reduction steps per chunk
@@ -257,11 +272,15 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
     uint8_t* sm = gt_dyn + (base - gt_smem(gt_dyn));
     const uint32_t s_state = base, s_w = base + ST_BYTES;
     float* xchg = reinterpret_cast<float*>(sm + ST_BYTES + W_PLANE);        // [3 gates][8 environments][32 units]
+    float* msk = xchg + 3 * GT_RW * GT_UB;                                  // [passes][T][8 environments] episode masks
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool gate = warp < GT_GW;
     const int ub = blockIdx.x * GT_UB, ku = ub + lane;
     const int ngrp = (d.N + GT_RW - 1) / GT_RW;
     const bool single = ngrp <= (int)gridDim.y;
+    gt_fill_masks(msk, d, use_msk, ngrp);
+    // mask of (pass p, step t, this warp's environment): from the table, or the dependent idx -> masks lookup
+    auto mask_of = [&](int p, int t, int my) { return use_msk ? msk[(p * d.T + t) * GT_RW + warp] : gt_mask(d, t, my); };
 
     if (tid == 0) {
         for (int c = 0; c < 4; ++c) gt_mbar_init(&bar_state[c], GT_GW / NCH);
@@ -325,12 +344,12 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
 
     // ---- image of step 0: hm_0 = h0 * mask_0 ----
     float hm_cur = 0.f;                                                    // this thread's hm_t (single pass: kept in a register)
-    for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+    for (int grp = blockIdx.y, ps = 0; grp < ngrp; grp += gridDim.y, ++ps) {
         const int my = grp * GT_RW + warp;
         if (gate) {
             float v = 0.f;
             if (my < d.N) {
-                v = d.h0[(long)my * H + ku] * gt_mask(d, 0, my);
+                v = d.h0[(long)my * H + ku] * mask_of(ps, 0, my);
                 d.hm[(long)my * H + ku] = v;
             }
             put_state(image_of(grp, 0), v);
@@ -385,23 +404,23 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
     } else {
         const float bias = warp < 3 ? bhh[warp * H + ku] : 0.f;           // drain warp g adds b_hh of gate g
         struct GateIn { float r, z, n, mnext; };
-        auto load_gi = [&](int t, int my) {
+        auto load_gi = [&](int ps, int t, int my) {
             GateIn q = {0.f, 0.f, 0.f, 0.f};
             if (my < d.N) {
                 const float* gi = d.gi + ((long)t * d.N + my) * 3 * H;
                 q.r = __ldg(gi + ku); q.z = __ldg(gi + H + ku); q.n = __ldg(gi + 2 * H + ku);
-                q.mnext = (t + 1 < d.T) ? gt_mask(d, t + 1, my) : 0.f;
+                q.mnext = (t + 1 < d.T) ? mask_of(ps, t + 1, my) : 0.f;
             }
             return q;
         };
-        GateIn pre = load_gi(0, blockIdx.y * GT_RW + warp);
+        GateIn pre = load_gi(0, 0, blockIdx.y * GT_RW + warp);
         uint32_t it = 0;
         for (int t = 0; t < d.T; ++t) {
-            for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y, ++it) {
+            for (int grp = blockIdx.y, ps = 0; grp < ngrp; grp += gridDim.y, ++it, ++ps) {
                 const int my = grp * GT_RW + warp;
                 const bool live = my < d.N;
                 const long row = (long)t * d.N + my;
-                const GateIn q = single ? pre : load_gi(t, my);
+                const GateIn q = single ? pre : load_gi(ps, t, my);
                 const float hprev = single ? hm_cur : (live ? d.hm[row * H + ku] : 0.f);
                 // ---- fetch: every gate warp waits for the group's flag and copies its share of the state image with
                 //      16-byte cp.async (generic proxy, L2 only): warps c * GT_GW / NCH .. share chunk c of both planes.
@@ -470,7 +489,7 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                 if (tid == 0 && t + 1 < d.T) gt_release_add(&gt_flags[0][grp]);
                 if (tid == 0) GT_STAMP(0, t, 9);
                 // everything below is consumed by later kernels only
-                if (single && t + 1 < d.T) pre = load_gi(t + 1, my);
+                if (single && t + 1 < d.T) pre = load_gi(0, t + 1, my);
                 if (live) {
                     d.out[row * H + ku] = h;
                     if (d.r) {
@@ -498,7 +517,7 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
 // ---------------------------------------------------------------------------------------------------------------
 template <int NKB>
 __global__ void __launch_bounds__(GT_NT, 1)
-gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws, const int dbg) {
+gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restrict__ carry_ws, const int use_msk, const int dbg) {
     constexpr int H = NKB * 64, UG = H / 32, NMB = H / 128;
     constexpr uint32_t TCOLS = gt_tmem_cols(GT_ACC_COLS + (uint32_t)NMB * 96u);
     constexpr uint32_t G_BYTES = 2 * 2048;                                 // [2 blocks of 64 gate rows][16 rows x 128 B]
@@ -509,10 +528,13 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
     const uint32_t base = (gt_smem(gt_dyn) + 1023u) & ~1023u;
     uint8_t* gop = gt_dyn + (base - gt_smem(gt_dyn));
     const uint32_t s_g = base;
+    float* msk = reinterpret_cast<float*>(gop + G_BYTES);                  // [passes][T][8 environments] episode masks
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool gate = warp < GT_GW;
     const int ub = blockIdx.x * GT_UB, ku = ub + lane;
     const int ngrp = (d.N + GT_RW - 1) / GT_RW;
+    gt_fill_masks(msk, d, use_msk, ngrp);
+    auto mask_of = [&](int p, int t, int my) { return use_msk ? msk[(p * d.T + t) * GT_RW + warp] : gt_mask(d, t, my); };
 
     if (tid == 0) {
         gt_mbar_init(&bar_acc, 1);
@@ -559,7 +581,7 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
     const uint64_t b0 = gt_desc(s_g, 16, 1024);                            // rows 8..15 (the lo parts): the next 8-row atom
 
     struct PhaseA { float dout, r, z, n, hm, ghn, mnext; };
-    auto load_a = [&](int t, int my) {
+    auto load_a = [&](int ps, int t, int my) {
         PhaseA a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (gate && my < d.N) {
             const long row = (long)t * d.N + my;
@@ -567,23 +589,23 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
             a.r = d.r[row * H + ku]; a.z = d.z[row * H + ku]; a.n = d.n[row * H + ku];
             a.hm = d.hm[row * H + ku];
             a.ghn = d.gh[row * 3 * H + 2 * H + ku];
-            a.mnext = (t + 1 < d.T) ? gt_mask(d, t + 1, my) : 0.f;
+            a.mnext = (t + 1 < d.T) ? mask_of(ps, t + 1, my) : 0.f;
         }
         return a;
     };
     auto part_of = [&](int grp, int buf) { return gt_part + ((size_t)grp * 2 + buf) * GT_PART_FLOATS; };
     const int my0 = blockIdx.y * GT_RW + warp;
-    PhaseA pre = load_a(d.T - 1, my0);
+    PhaseA pre = load_a(0, d.T - 1, my0);
     float carry0 = 0.f;                                                    // dh_{t+1} z_{t+1} of the first pass's (environment, unit)
     uint32_t it = 0;
 
     for (int t = d.T - 1; t >= 0; --t) {
-        for (int grp = blockIdx.y; grp < ngrp; grp += gridDim.y) {
+        for (int grp = blockIdx.y, ps = 0; grp < ngrp; grp += gridDim.y, ++ps) {
             const int my = grp * GT_RW + warp;
             const bool live = gate && my < d.N;
             const bool first = grp == (int)blockIdx.y;
             const long row = (long)t * d.N + my;
-            const PhaseA a = first ? pre : load_a(t, my);
+            const PhaseA a = first ? pre : load_a(ps, t, my);
             // ---- carry of step t + 1: own dh z + the unit groups' partial products, summed in a fixed order ----
             float dh = a.dout;
             if (t + 1 < d.T) {
@@ -692,7 +714,7 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                 dgi[ku] = dr_pre; dgi[H + ku] = dz_pre; dgi[2 * H + ku] = dn_pre;
                 dgh[ku] = dr_pre; dgh[H + ku] = dz_pre; dgh[2 * H + ku] = dn_pre * a.r;
             }
-            if (first && t > 0) pre = load_a(t - 1, my);
+            if (first && t > 0) pre = load_a(0, t - 1, my);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -706,14 +728,15 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
 // ---------------------------------------------------------------------------------------------------------------
 // state image + the lo k-blocks that do not fit tensor memory + exchange tail; at least 120 KiB: one CTA per SM (each
 // allocates up to 512 tensor-memory columns)
-static size_t gt_smem_fwd(int H) {
+constexpr size_t GT_MSK_MAX = 64 * 1024;      // largest mask table ([passes][T][8] floats) kept in shared memory
+static size_t gt_smem_fwd(int H, size_t msk_bytes) {
     const int nkb = H / 64, lo_ts = 4 * nkb < 56 - 4 * nkb ? 4 * nkb : 56 - 4 * nkb;
-    const size_t need = (size_t)2 * nkb * 1024 + (size_t)(nkb - lo_ts / 4) * GT_WBLK + 4096 + 1024;
+    const size_t need = (size_t)2 * nkb * 1024 + (size_t)(nkb - lo_ts / 4) * GT_WBLK + 4096 + 1024 + msk_bytes;
     return need > 120 * 1024 ? need : 120 * 1024;
 }
 // the backward kernel needs 5 KiB; it asks for more than half an SM's shared memory so that two CTAs (512 tensor-memory
 // columns each) can never be placed on one SM
-static size_t gt_smem_bwd(int) { return 120 * 1024; }
+static size_t gt_smem_bwd(int, size_t msk_bytes) { return 120 * 1024 > 8192 + msk_bytes ? 120 * 1024 : 8192 + msk_bytes; }
 
 template <int NKB>
 static const void* gt_kernel(bool backward) {
@@ -765,7 +788,7 @@ int gru_tc_debug_stamps(long long* out) {
 bool gru_tc_supported(int N, int H) {
     if (gru_mode() != 2 || N <= 0 || H % 128 != 0 || H > GT_MAX_H) return false;
     if ((N + GT_RW - 1) / GT_RW > GT_MAX_GROUPS) return false;
-    if (gt_smem_fwd(H) > 226 * 1024 || gt_smem_bwd(H) > 226 * 1024) return false;
+    if (gt_smem_fwd(H, GT_MSK_MAX) > 226 * 1024 || gt_smem_bwd(H, GT_MSK_MAX) > 226 * 1024) return false;
     return H / GT_UB <= gt_sms();
 }
 
@@ -774,14 +797,12 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
     A2CB_REQUIRE(Whh && d.hm && d.masks, "gru_tc: null pointer");
     A2CB_REQUIRE(backward || (bhh && d.h0 && d.gi && d.out), "gru_tc: forward pointers");
     A2CB_REQUIRE(!backward || (d.r && d.z && d.n && d.gh && d.dout && d.dgi && d.dgh), "gru_tc: backward pointers");
-    // dynamic shared memory: exactly what this H needs (the device limit of 227 KiB includes the kernels' few static bytes)
     static bool attr_done[2][GT_MAX_H / 64 + 1] = {};
     if (!attr_done[backward ? 1 : 0][d.H / 64]) {
-        const cudaError_t ea = cudaFuncSetAttribute(gt_kernel_for(d.H, backward != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)(backward ? gt_smem_bwd(d.H) : gt_smem_fwd(d.H)));
+        const size_t most = backward ? gt_smem_bwd(d.H, GT_MSK_MAX) : gt_smem_fwd(d.H, GT_MSK_MAX);
+        const cudaError_t ea = cudaFuncSetAttribute(gt_kernel_for(d.H, backward != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
         if (ea != cudaSuccess) {
-            set_error("gru_tc: shared memory attribute (%zu bytes): %s", backward ? gt_smem_bwd(d.H) : gt_smem_fwd(d.H),
-                      cudaGetErrorString(ea));
+            set_error("gru_tc: shared memory attribute (%zu bytes): %s", most, cudaGetErrorString(ea));
             cudaGetLastError();
             return A2CB_ERR_CUDA;
         }
@@ -804,11 +825,15 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
     if (dbg < 0) { const char* e = getenv("A2CB_GRU_TC_DEBUG"); dbg = (e && e[0] == '1') ? 1 : 0; }
     GruDesc dd = d;
     float* ws = d.dcarry;
-    void* args_f[] = {(void*)&dd, (void*)&Whh, (void*)&bhh, (void*)&dbg};
-    void* args_b[] = {(void*)&dd, (void*)&Whh, (void*)&ws, (void*)&dbg};
+    // episode-mask table in shared memory when it fits: [passes per CTA][T][8 environments]
+    size_t msk_bytes = (size_t)((ngrp + gy - 1) / gy) * (size_t)d.T * GT_RW * sizeof(float);
+    int use_msk = msk_bytes <= GT_MSK_MAX ? 1 : 0;
+    if (!use_msk) msk_bytes = 0;
+    void* args_f[] = {(void*)&dd, (void*)&Whh, (void*)&bhh, (void*)&use_msk, (void*)&dbg};
+    void* args_b[] = {(void*)&dd, (void*)&Whh, (void*)&ws, (void*)&use_msk, (void*)&dbg};
     dim3 grid((unsigned)ug, (unsigned)gy);
     cudaError_t e = cudaLaunchCooperativeKernel(gt_kernel_for(d.H, backward != 0), grid, dim3(GT_NT), backward ? args_b : args_f,
-                                                backward ? gt_smem_bwd(d.H) : gt_smem_fwd(d.H), st);
+                                                backward ? gt_smem_bwd(d.H, msk_bytes) : gt_smem_fwd(d.H, msk_bytes), st);
     if (e != cudaSuccess) {
         set_error("gru_tc: cooperative launch failed: %s", cudaGetErrorString(e));
         cudaGetLastError();

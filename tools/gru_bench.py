@@ -1,6 +1,6 @@
 """Times the persistent GRU recurrence kernels (a2cb_gru_seq) per kernel family and checks them against each other.
 
-    python tools/gru_bench.py [T N H]
+    python tools/gru_bench.py [T N H [family]]
 
 Prints one JSON line per family: ms per forward / backward launch (CUDA events, L2 flushed between launches) and the
 rel-L2 distance of its outputs from the fp32 SIMT kernels.
@@ -33,7 +33,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lib = _native.lib()
     ref = None
+    only = sys.argv[4] if len(sys.argv) >= 5 else None            # e.g. "tc": time this family only (ncu captures)
     for mode, code in (("simt", 0), ("mma", 1), ("tc", 2)):
+        if only and mode != only:
+            continue
         _native.set_gru_mode(code)
         if _native.gru_seq_variant(N, H) != mode:
             print(json.dumps({"mode": mode, "skipped": "shape runs %s" % _native.gru_seq_variant(N, H)}))
