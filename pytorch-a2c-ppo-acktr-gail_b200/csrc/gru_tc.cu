@@ -51,11 +51,11 @@ constexpr int GT_CTRL = GT_GW;                // control warp: polls, issues the
 constexpr uint32_t GT_ACC_COLS = 64;          // tensor-memory columns of the accumulators (4 x 16)
 constexpr float GT_SX = 16.f;                 // power-of-two scale of the forward state planes
 
-__device__ unsigned gt_flags[2][GT_MAX_GROUPS];
 __device__ long long gt_dbg[2][16][16];            // A2CB_GRU_TC_DEBUG=1: clock64 stamps of CTA (0, 0), steps 16..31, per phase
 #define GT_STAMP(dir, t, i) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && (t) >= 16 && (t) < 32) gt_dbg[dir][(t) - 16][i] = clock64(); } while (0)
 __device__ uint4 gt_img[(size_t)GT_MAX_GROUPS * 2 * GT_IMG_BYTES / 16];
-__device__ float gt_part[(size_t)GT_MAX_GROUPS * 2 * GT_PART_FLOATS];
+// backward exchange: [GT_MAX_GROUPS arrival counters][group][2 buffers][partial carries] -- one memset resets both
+__device__ float gt_part_all[GT_MAX_GROUPS + (size_t)GT_MAX_GROUPS * 2 * GT_PART_FLOATS];
 
 __device__ __forceinline__ uint32_t gt_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float gt_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
@@ -153,14 +153,19 @@ __device__ __forceinline__ void gt_ld_wait16(uint32_t* v) {
                  : "memory");
 }
 __device__ __forceinline__ void gt_gate_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * GT_GW) : "memory"); }
-__device__ __forceinline__ unsigned gt_ld_acquire(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// strong (L1-bypassing) 16-byte / 4-byte loads of words other CTAs are writing right now
+__device__ __forceinline__ uint4 gt_ld_relaxed16(const void* p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void gt_release_add(unsigned* p) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+__device__ __forceinline__ uint32_t gt_ld_relaxed4(const void* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
+// 2-bit validity tag of exchange step t (the buffer t & 1 held step t -+ 2 before: the other tag; 0 = never written)
+__device__ __forceinline__ uint32_t gt_tag(int t) { return 1u + (uint32_t)((t >> 1) & 1); }
 // x * s = hi + lo, both fp16 (hi the nearest fp16, lo the nearest fp16 of the exact remainder): packed {lo:hi}
 __device__ __forceinline__ uint32_t gt_split(float xs) {
     const __half hi = __float2half_rn(xs);
@@ -324,18 +329,22 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // writes this thread's masked state v of (environment `warp`, unit `lane`) into the group's image `img`
-    auto put_state = [&](uint8_t* img, float v) {
-        const uint32_t p = gt_split(v * GT_SX);
-        const uint32_t q = __shfl_xor_sync(0xffffffffu, p, 1);
-        // even lane: hi-plane word {hi(u), hi(u + 1)}; odd lane: lo-plane word {lo(u - 1), lo(u)}
-        const uint32_t w0 = (lane & 1) ? ((q >> 16) | (p & 0xffff0000u)) : ((p & 0xffffu) | (q << 16));
-        const uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 2), w2 = __shfl_down_sync(0xffffffffu, w0, 4),
-                       w3 = __shfl_down_sync(0xffffffffu, w0, 6);
-        if ((lane & 7) < 2) {                                             // lane 8 j: hi chunk of units 8 j .. 8 j + 7; 8 j + 1: lo chunk
-            const int k = ub + (lane & ~7);
-            const uint32_t off = (uint32_t)(lane & 1) * ST_PLANE + gt_swz(warp, k, 1024);
-            *reinterpret_cast<uint4*>(img + off) = make_uint4(w0, w1, w2, w3);
+    // Writes this thread's masked state v of (environment `warp`, unit `lane`) into the group's exchange image for
+    // step t.  Global layout: [8 environments][H / 4 pieces] x 16 bytes, piece (e, j) = {hi parts of units 4 j .. 4 j + 3,
+    // their lo parts}; the two low mantissa bits of the piece's first two lo parts carry the step's validity tag, so a
+    // consumer that finds the tag knows the whole 16-byte store has landed -- no flag, no fence, no barrier.
+    auto put_state = [&](uint8_t* img, float v, int t) {
+        const uint32_t p = gt_split(v * GT_SX);                            // {lo : hi}
+        const uint32_t p1 = __shfl_down_sync(0xffffffffu, p, 1), p2 = __shfl_down_sync(0xffffffffu, p, 2),
+                       p3 = __shfl_down_sync(0xffffffffu, p, 3);
+        if ((lane & 3) == 0) {
+            const uint32_t tag = gt_tag(t);
+            uint4 w;
+            w.x = (p & 0xffffu) | (p1 << 16);
+            w.y = (p2 & 0xffffu) | (p3 << 16);
+            w.z = (((p >> 16) | (p1 & 0xffff0000u)) & 0xfffefffeu) | (tag & 1u) | ((tag >> 1) << 16);
+            w.w = (p2 >> 16) | (p3 & 0xffff0000u);
+            *reinterpret_cast<uint4*>(img + ((size_t)warp * (H / 4) + (ub >> 2) + (lane >> 2)) * 16) = w;
         }
     };
     auto image_of = [&](int grp, int buf) {
@@ -352,11 +361,9 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                 v = d.h0[(long)my * H + ku] * mask_of(ps, 0, my);
                 d.hm[(long)my * H + ku] = v;
             }
-            put_state(image_of(grp, 0), v);
+            put_state(image_of(grp, 0), v, 0);
             hm_cur = v;
         }
-        __syncthreads();
-        if (tid == 0) gt_release_add(&gt_flags[0][grp]);
     }
 
     if (warp == GT_CTRL) {
@@ -421,32 +428,37 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                 const bool live = my < d.N;
                 const long row = (long)t * d.N + my;
                 const GateIn q = single ? pre : load_gi(ps, t, my);
+                if (single && t + 1 < d.T) pre = load_gi(0, t + 1, my);          // a whole step ahead of its use
                 const float hprev = single ? hm_cur : (live ? d.hm[row * H + ku] : 0.f);
-                // ---- fetch: every gate warp waits for the group's flag and copies its share of the state image with
-                //      16-byte cp.async (generic proxy, L2 only): warps c * GT_GW / NCH .. share chunk c of both planes.
-                //      (One bulk copy per chunk needs a cross-proxy fence between the other CTAs' generic stores and the
-                //      async-proxy reads -- fence.proxy.async measured 1,400 cycles here; one warp issuing all the
-                //      cp.async copies takes 3,800.) ----
+                // ---- fetch: every gate warp loads its share of the group's exchange image (strong 16-byte loads), waits
+                //      until every piece carries this step's tag, scatters hi / lo parts into the shared-memory operand and
+                //      arrives on its chunk's barrier: warps c * GT_GW / NCH .. share chunk c (a k-range) of both planes.
+                //      (Round-trip history of this exchange: counter flag + bulk copies needed a cross-proxy fence --
+                //      fence.proxy.async measured 1,400 cycles -- and a red.release.gpu of ~1,000 cycles per step.) ----
                 {
-                    if (lane == 0) {
-                        const unsigned target = (unsigned)UG * (unsigned)(t + 1);
-                        while (gt_ld_acquire(&gt_flags[0][grp]) < target) {}
-                    }
-                    __syncwarp();
-                    if (tid == 0) GT_STAMP(0, t, 14);
                     constexpr int WPC = GT_GW / NCH;                                 // warps per chunk
-                    constexpr int PER = 4 * NKB / NCH / WPC;                         // copies per lane
-                    constexpr int HALF16 = (int)(CH_BYTES / 16);                     // 16-byte pieces of one plane's share
+                    constexpr int JPC = H / 4 / NCH;                                 // pieces per environment and chunk
+                    constexpr int PER = GT_RW * JPC / (32 * WPC);                    // pieces per lane
                     const int c = warp / WPC, wq = warp % WPC;
                     const uint8_t* src = image_of(grp, t & 1);
+                    const uint32_t tag = gt_tag(t);
+                    const uint4* ptr[PER];
+                    uint32_t dst[PER];
+                    uint4 w[PER];
 #pragma unroll
                     for (int i = 0; i < PER; ++i) {
-                        const int o16 = (wq * PER + i) * 32 + lane;
-                        const uint32_t o = (o16 >= HALF16 ? ST_PLANE + (uint32_t)(o16 - HALF16) * 16u : (uint32_t)o16 * 16u) + (uint32_t)c * CH_BYTES;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_state + o), "l"(src + o) : "memory");
+                        const int o = (wq * PER + i) * 32 + lane;                    // piece of the chunk: (environment, j)
+                        const int e = o / JPC, j = c * JPC + (o - e * JPC);
+                        ptr[i] = reinterpret_cast<const uint4*>(src + ((size_t)e * (H / 4) + j) * 16);
+                        dst[i] = gt_swz(e, 4 * j, 1024);
+                        w[i] = gt_ld_relaxed16(ptr[i]);
                     }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) {
+                        while (((w[i].z & 1u) | ((w[i].z >> 15) & 2u)) != tag) w[i] = gt_ld_relaxed16(ptr[i]);
+                        *reinterpret_cast<uint2*>(sm + dst[i]) = make_uint2(w[i].x, w[i].y);
+                        *reinterpret_cast<uint2*>(sm + ST_PLANE + dst[i]) = make_uint2(w[i].z, w[i].w);
+                    }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // these generic writes -> tensor-core reads
                     __syncwarp();
                     if (lane == 0) gt_mbar_arrive(&bar_state[c]);
@@ -481,15 +493,15 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                 const float nn = tanhf(q.n + rr * ghn);
                 const float h = (1.f - zz) * nn + zz * hprev;
                 const float hm_next = live ? h * q.mnext : 0.f;
-                if (t + 1 < d.T) put_state(image_of(grp, (t + 1) & 1), hm_next);    // what the other CTAs wait for
+                if (t + 1 < d.T) put_state(image_of(grp, (t + 1) & 1), hm_next, t + 1);   // what the other CTAs wait for
                 hm_cur = hm_next;
                 if (tid == 0) GT_STAMP(0, t, 7);
-                gt_gate_barrier();
+                // several groups per CTA: the next pass's drain must not overwrite xchg while this pass still reads it
+                // (one group per CTA: the next drain needs every CTA's new state, this one's slowest warp included)
+                if (!single) gt_gate_barrier();
                 if (tid == 0) GT_STAMP(0, t, 8);
-                if (tid == 0 && t + 1 < d.T) gt_release_add(&gt_flags[0][grp]);
                 if (tid == 0) GT_STAMP(0, t, 9);
                 // everything below is consumed by later kernels only
-                if (single && t + 1 < d.T) pre = load_gi(0, t + 1, my);
                 if (live) {
                     d.out[row * H + ku] = h;
                     if (d.r) {
@@ -593,7 +605,8 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
         }
         return a;
     };
-    auto part_of = [&](int grp, int buf) { return gt_part + ((size_t)grp * 2 + buf) * GT_PART_FLOATS; };
+    auto part_of = [&](int grp, int buf) { return gt_part_all + GT_MAX_GROUPS + ((size_t)grp * 2 + buf) * GT_PART_FLOATS; };
+    unsigned* arrived = reinterpret_cast<unsigned*>(gt_part_all);        // per group: partial slabs stored so far (a HINT)
     const int my0 = blockIdx.y * GT_RW + warp;
     PhaseA pre = load_a(0, d.T - 1, my0);
     float carry0 = 0.f;                                                    // dh_{t+1} z_{t+1} of the first pass's (environment, unit)
@@ -606,25 +619,38 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
             const bool first = grp == (int)blockIdx.y;
             const long row = (long)t * d.N + my;
             const PhaseA a = first ? pre : load_a(ps, t, my);
+            // next step's operands of the first pass: issued NOW, a whole step ahead of their use (they come from HBM:
+            // issued at the end of the step, their latency sat in front of the next step -- 15 % of all stall samples)
+            if (first && t > 0) pre = load_a(0, t - 1, my);
             // ---- carry of step t + 1: own dh z + the unit groups' partial products, summed in a fixed order ----
             float dh = a.dout;
             if (t + 1 < d.T) {
+                // The arrival counter is bumped WITHOUT a release fence (a red.release.gpu cost ~1,100 cycles per step): it
+                // only tells when polling the data is worth while -- one thread polls one word instead of 256 threads
+                // polling 16 each, which slowed the producers' stores down.  Validity comes from the tags below.
                 if (tid == 0) {
                     GT_STAMP(1, t, 0);
                     const unsigned target = (unsigned)UG * (unsigned)(d.T - 1 - t);
-                    while (gt_ld_acquire(&gt_flags[1][grp]) < target) {}
+                    while (gt_ld_relaxed4(arrived + grp) < target) {}
                     GT_STAMP(1, t, 1);
                 }
                 __syncthreads();
                 if (gate) {
+                    // the 16 partial products of step t + 1 for this (environment, unit), one per unit group: strong loads,
+                    // repeated until every word carries that step's tag in its two low mantissa bits
                     const float* p = part_of(grp, (t + 1) & 1) + (((size_t)blockIdx.x * UG) * GT_RW + warp) * GT_UB + lane;
+                    const uint32_t tag = gt_tag(t + 1);
+                    uint32_t w[UG];
+#pragma unroll
+                    for (int src = 0; src < UG; ++src) w[src] = gt_ld_relaxed4(p + (size_t)src * GT_RW * GT_UB);
+#pragma unroll
+                    for (int src = 0; src < UG; ++src)
+                        while ((w[src] & 3u) != tag) w[src] = gt_ld_relaxed4(p + (size_t)src * GT_RW * GT_UB);
                     float sum = 0.f;
 #pragma unroll
-                    for (int src = 0; src < UG; src += 4) {
-                        const float v0 = __ldcg(p + (size_t)(src + 0) * GT_RW * GT_UB), v1 = __ldcg(p + (size_t)(src + 1) * GT_RW * GT_UB),
-                                    v2 = __ldcg(p + (size_t)(src + 2) * GT_RW * GT_UB), v3 = __ldcg(p + (size_t)(src + 3) * GT_RW * GT_UB);
-                        sum += (v0 + v1) + (v2 + v3);
-                    }
+                    for (int src = 0; src < UG; src += 4)
+                        sum += (__uint_as_float(w[src] & ~3u) + __uint_as_float(w[src + 1] & ~3u)) +
+                               (__uint_as_float(w[src + 2] & ~3u) + __uint_as_float(w[src + 3] & ~3u));
                     const float c = (first ? carry0 : (live ? carry_ws[(long)my * H + ku] : 0.f)) + sum;
                     dh += c * a.mnext;
                 }
@@ -685,6 +711,7 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                     if (tid == 0) GT_STAMP(1, t, 5);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const float unscale = 1.f / (sw * sg);
+                    const uint32_t tag = gt_tag(t);
                     float* pbase = part_of(grp, t & 1);
                     uint32_t v[NMB][16];
 #pragma unroll
@@ -695,8 +722,10 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                     for (int mb = 0; mb < NMB; ++mb) {
                         float* p = pbase + ((size_t)((4 * mb + warp) * UG + blockIdx.x) * GT_RW) * GT_UB + lane;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            __stcg(p + e * GT_UB, (__uint_as_float(v[mb][e]) + __uint_as_float(v[mb][e + 8])) * unscale);
+                        for (int e = 0; e < 8; ++e) {
+                            const float val = (__uint_as_float(v[mb][e]) + __uint_as_float(v[mb][e + 8])) * unscale;
+                            __stcg(reinterpret_cast<uint32_t*>(p) + e * GT_UB, (__float_as_uint(val) & ~3u) | tag);
+                        }
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (tid == 0) GT_STAMP(1, t, 6);
@@ -704,7 +733,7 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                 ++it;
                 __syncthreads();
                 if (tid == 0) GT_STAMP(1, t, 7);
-                if (tid == 0) gt_release_add(&gt_flags[1][grp]);
+                if (tid == 0) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(arrived + grp) : "memory");
                 if (tid == 0) GT_STAMP(1, t, 8);
             }
             // ---- consumed by the weight-gradient products after this kernel ----
@@ -714,7 +743,6 @@ gru_tc_bwd_kernel(const GruDesc d, const float* __restrict__ Whh, float* __restr
                 dgi[ku] = dr_pre; dgi[H + ku] = dz_pre; dgi[2 * H + ku] = dn_pre;
                 dgh[ku] = dr_pre; dgh[H + ku] = dz_pre; dgh[2 * H + ku] = dn_pre * a.r;
             }
-            if (first && t > 0) pre = load_a(0, t - 1, my);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -814,12 +842,12 @@ int gru_tc(int backward, const GruDesc& d, const float* Whh, const float* bhh, c
     gy = gy < 1 ? 1 : (gy > ngrp ? ngrp : gy);
     A2CB_REQUIRE(!backward || ngrp <= gy || d.dcarry, "gru_tc: dcarry workspace [N, H] needed for N > %d", gy * GT_RW);
     {
-        void* fptr = nullptr;
-        cudaError_t e0 = cudaGetSymbolAddress(&fptr, gt_flags);
-        if (e0 == cudaSuccess)
-            e0 = cudaMemsetAsync(reinterpret_cast<unsigned*>(fptr) + (backward ? GT_MAX_GROUPS : 0), 0,
-                                 GT_MAX_GROUPS * sizeof(unsigned), st);
-        if (e0 != cudaSuccess) { set_error("gru_tc: flag reset: %s", cudaGetErrorString(e0)); return A2CB_ERR_CUDA; }
+        // exchange buffers of the launch's groups: tag 0 = "never written" (the kernels validate every word they read)
+        void* ptr = nullptr;
+        cudaError_t e0 = backward ? cudaGetSymbolAddress(&ptr, gt_part_all) : cudaGetSymbolAddress(&ptr, gt_img);
+        const size_t bytes = backward ? (GT_MAX_GROUPS + (size_t)ngrp * 2 * GT_PART_FLOATS) * sizeof(float) : (size_t)ngrp * 2 * GT_IMG_BYTES;
+        if (e0 == cudaSuccess) e0 = cudaMemsetAsync(ptr, 0, bytes, st);
+        if (e0 != cudaSuccess) { set_error("gru_tc: exchange buffer reset: %s", cudaGetErrorString(e0)); return A2CB_ERR_CUDA; }
     }
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("A2CB_GRU_TC_DEBUG"); dbg = (e && e[0] == '1') ? 1 : 0; }
