@@ -85,14 +85,6 @@ __device__ __forceinline__ void gt_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void gt_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gt_smem(bar)) : "memory");
 }
-__device__ __forceinline__ void gt_expect(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gt_smem(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void gt_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(gt_smem(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void gt_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gt_smem(bar)) : "memory");
 }
@@ -254,13 +246,12 @@ __host__ __device__ constexpr uint32_t gt_tmem_cols(uint32_t need) {
 template <int NKB>
 __global__ void __launch_bounds__(GT_NT, 1)
 gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* __restrict__ bhh, const int use_msk, const int dbg) {
-    constexpr int H = NKB * 64, UG = H / 32;
+    constexpr int H = NKB * 64;
     constexpr int NCH = (NKB % 4 == 0) ? 4 : 2;                             // chunks of the state fetch = accumulators
     constexpr int SPC = NKB * 4 / NCH;                                      // 16-element reduction steps per chunk
     constexpr uint32_t ST_PLANE = (uint32_t)NKB * 1024u;                    // one plane of the state image: [NKB][8 rows x 128 B]
     constexpr uint32_t ST_BYTES = 2u * ST_PLANE;
     constexpr uint32_t W_PLANE = (uint32_t)(NKB - (4 * NKB < 56 - 4 * NKB ? NKB : (56 - 4 * NKB) / 4)) * GT_WBLK;   // lo k-blocks kept in shared memory
-    constexpr uint32_t CH_BYTES = (uint32_t)(NKB / NCH) * 1024u;            // per plane and chunk
     // the lo weight plane goes to tensor memory too as far as the 512 columns reach (H = 512: 24 of its 32 reduction
     // steps); only the remaining k-blocks stay in shared memory and cost an instruction with a shared-memory A operand
     constexpr int LO_TS = (4 * NKB < 56 - 4 * NKB) ? 4 * NKB : 56 - 4 * NKB;   // reduction steps of the lo plane in tensor memory
@@ -433,8 +424,9 @@ gru_tc_fwd_kernel(const GruDesc d, const float* __restrict__ Whh, const float* _
                 // ---- fetch: every gate warp loads its share of the group's exchange image (strong 16-byte loads), waits
                 //      until every piece carries this step's tag, scatters hi / lo parts into the shared-memory operand and
                 //      arrives on its chunk's barrier: warps c * GT_GW / NCH .. share chunk c (a k-range) of both planes.
-                //      (Round-trip history of this exchange: counter flag + bulk copies needed a cross-proxy fence --
-                //      fence.proxy.async measured 1,400 cycles -- and a red.release.gpu of ~1,000 cycles per step.) ----
+                //      (History of this exchange: a counter flag + bulk copies needed a cross-proxy fence -- fence.proxy.async
+                //      measured 1,400 cycles -- and a red.release.gpu of ~1,000 cycles per step; an unfenced arrival counter
+                //      in front of these loads, as the backward kernel uses, made this direction 7 % slower.) ----
                 {
                     constexpr int WPC = GT_GW / NCH;                                 // warps per chunk
                     constexpr int JPC = H / 4 / NCH;                                 // pieces per environment and chunk
