@@ -179,9 +179,20 @@ __global__ void __launch_bounds__(TX_NT, 1)
 tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ TcxFwd p, const int stages,
-               const int patch_base_offset, const int stagesB) {
+               const int patch_base_offset, const int stagesB, const int merge_on) {
     constexpr int B_BYTES = BN * TX_ROWB;
     constexpr int HALF = BN / 2;
+    // MERGE (<= 64 output channels): the weight planes of a stage are contiguous in shared memory, so ONE instruction
+    // A x [B_hi | B_lo] (N = 2 BN; bf16: [b1 | b2 | b3], N = 3 BN) replaces two (three): an instruction with its A operand
+    // in shared memory costs >= 46 cycles whatever N is (the 4 KiB A read, tools/mma_probe.cu), and A is read once per
+    // plane instead of once per product.  The products land in NPL column blocks of the accumulator; the drain adds them.
+    constexpr bool MERGE_T = BN <= 64;
+    // A2CB_TCX_MERGE (A / B knob, default 7): bit 0 = bf16 instances, bit 1 = 32-channel TF32, bit 2 = 64-channel TF32
+    const bool MERGE = MERGE_T && ((merge_on >> (BF16 ? 0 : (BN == 32 ? 1 : 2))) & 1) != 0;
+    constexpr int NPL = MERGE_T ? (BF16 ? 3 : 2) : 1;              // column blocks per accumulator
+    constexpr int W = NPL * BN;                                  // accumulator width in tensor-memory columns
+    constexpr uint32_t TCOLS = (2 * MB * W <= 32) ? 32 : (2 * MB * W <= 64) ? 64 : (2 * MB * W <= 128) ? 128 : (2 * MB * W <= 256) ? 256 : 512;
+    static_assert(2 * MB * W <= 512, "tcx_fwd: accumulators exceed tensor memory");
     extern __shared__ uint8_t tx_dyn[];
     __shared__ TxBars bars;
     // one plane of the A tile: the R rows TMA writes, rounded up to a swizzle atom (8 rows).  The last M block's MMAs
@@ -217,7 +228,7 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tx_smem(&bars.tmem_base)),
-                     "r"((uint32_t)(2 * MB * BN)));
+                     "r"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -315,6 +326,7 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // D fp32, A/B tf32 (format 2) or bf16 (format 1), both K-major, N = BN, M = 128
         constexpr uint32_t fmt = BF16 ? 1u : 2u;
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idescW = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(W >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = W
         int s = 0, cc = 0;
         uint32_t ph = 0;                                   // parity of full[s] to wait for
         if constexpr (PATCH && !BF16) {
@@ -340,20 +352,20 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t sb = dynB + (uint32_t)(sB * NB * B_BYTES);
 #pragma unroll
                         for (int mb = 0; mb < MB; ++mb) {
-                            const uint32_t d = tmem + (uint32_t)(buf * MB * BN + mb * BN);
+                            const uint32_t d = tmem + (uint32_t)(buf * MB * W + mb * W);
                             const uint32_t ah = sa + (uint32_t)(mb * 128 * TX_ROWB);
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint32_t o = ks * 32;
                                 const uint64_t dah = tx_desc_k(ah + o), dbh = tx_desc_k(sb + o), dbl = tx_desc_k(sb + B_BYTES + o);
-                                if (ks == 0) {
-                                    const uint32_t acc0 = first ? 0u : 1u;
-                                    if (has_lo) { tx_mma(d, tx_desc_k(ah + A_BYTES + o), dbh, idesc, acc0); tx_mma(d, dah, dbl, idesc, 1u); }
-                                    else tx_mma(d, dah, dbl, idesc, acc0);
-                                } else {
+                                const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
+                                if (MERGE) {
+                                    tx_mma(d, dah, dbh, idescW, acc0);                       // A_hi x [B_hi | B_lo]
                                     if (has_lo) tx_mma(d, tx_desc_k(ah + A_BYTES + o), dbh, idesc, 1u);
-                                    tx_mma(d, dah, dbl, idesc, 1u);
+                                    continue;
                                 }
+                                if (has_lo) { tx_mma(d, tx_desc_k(ah + A_BYTES + o), dbh, idesc, acc0); tx_mma(d, dah, dbl, idesc, 1u); }
+                                else tx_mma(d, dah, dbl, idesc, acc0);
                                 tx_mma(d, dah, dbh, idesc, 1u);
                             }
                         }
@@ -389,13 +401,17 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t sb = dynB + (uint32_t)(kb * NB * B_BYTES);
 #pragma unroll
                         for (int mb = 0; mb < MB; ++mb) {
-                            const uint32_t d = tmem + (uint32_t)(buf * MB * BN + mb * BN);
+                            const uint32_t d = tmem + (uint32_t)(buf * MB * W + mb * W);
                             const uint32_t ah = sa + (uint32_t)(mb * 128 * TX_ROWB);
                             const uint64_t bo = patch_base_offset ? ((uint64_t)((ah >> 7) & 7u) << 49) : 0ull;
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint32_t o = ks * 32;
                                 const uint64_t dah = tx_desc_k(ah + o) | bo;
+                                if (MERGE) {                                                 // A x [b1 | b2 | b3]
+                                    tx_mma_f16(d, dah, tx_desc_k(sb + o), idescW, (first && ks == 0) ? 0u : 1u);
+                                    continue;
+                                }
                                 tx_mma_f16(d, dah, tx_desc_k(sb + 2 * B_BYTES + o), idesc, (first && ks == 0) ? 0u : 1u);
                                 tx_mma_f16(d, dah, tx_desc_k(sb + B_BYTES + o), idesc, 1u);
                                 tx_mma_f16(d, dah, tx_desc_k(sb + o), idesc, 1u);
@@ -425,12 +441,19 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sb = sa + (uint32_t)(A_BYTES * (has_lo ? 2 : 1));
 #pragma unroll
                     for (int mb = 0; mb < MB; ++mb) {
-                        const uint32_t d = tmem + (uint32_t)(buf * MB * BN + mb * BN);
+                        const uint32_t d = tmem + (uint32_t)(buf * MB * W + mb * W);
                         const uint32_t ah = sa + (uint32_t)(mb * 128 * TX_ROWB);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t o = ks * 32;                  // 8 tf32 or 16 bf16 reduction elements = 32 bytes
                             const uint64_t dah = tx_desc_k(ah + o), dbh = tx_desc_k(sb + o), dbl = tx_desc_k(sb + B_BYTES + o);
+                            if (MERGE) {
+                                const uint32_t acc0 = (first && ks == 0) ? 0u : 1u;
+                                if (BF16) { tx_mma_f16(d, dah, dbh, idescW, acc0); continue; }   // A x [b1 | b2 | b3]
+                                tx_mma(d, dah, dbh, idescW, acc0);                                // A_hi x [B_hi | B_lo]
+                                if (has_lo) tx_mma(d, tx_desc_k(ah + A_BYTES + o), dbh, idesc, 1u);
+                                continue;
+                            }
                             if (BF16) {
                                 // exact bf16 operand x (b1 + b2 + b3): smallest term first
                                 tx_mma_f16(d, dah, tx_desc_k(sb + 2 * B_BYTES + o), idesc, (first && ks == 0) ? 0u : 1u);
@@ -550,7 +573,8 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tx_mbar_wait(&bars.acc_full[buf], (uint32_t)((cc >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // two 16-column loads in flight per wait (the pair is the two M blocks when a thread owns 16 columns)
-                constexpr int NLD = MB * (HALF / 16);
+                // (load l = ((mb * HALF / 16 + c0 / 16) * NPL + column block): the NPL blocks of a product are summed here)
+                constexpr int NLD = MB * (HALF / 16) * NPL;
                 static_assert(NLD % 2 == 0 || NLD == 1, "tcx_fwd: loads are drained in pairs");
 #pragma unroll
                 for (int l0 = 0; l0 < NLD; l0 += 2) {
@@ -559,8 +583,10 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 2; ++j) {
                         const int l = l0 + j;
                         if (l < NLD) {
-                            const int mb = l / (HALF / 16), c0 = (l % (HALF / 16)) * 16;
-                            tx_ld16_issue(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * MB * BN + mb * BN + hf * HALF + c0), v[j]);
+                            const int pl = l % NPL, r = l / NPL;
+                            const int mb = r / (HALF / 16), c0 = (r % (HALF / 16)) * 16;
+                            if (pl > 0 && !MERGE) continue;
+                            tx_ld16_issue(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * MB * W + mb * W + pl * BN + hf * HALF + c0), v[j]);
                         }
                     }
                     tx_ld_wait16(v[0]);
@@ -568,8 +594,9 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const int l = l0 + j;
-                        if (l < NLD) {
-                            const int mb = l / (HALF / 16), c0 = (l % (HALF / 16)) * 16;
+                        if (l < NLD && (l % NPL == 0 || MERGE)) {
+                            const int r = l / NPL;
+                            const int mb = r / (HALF / 16), c0 = (r % (HALF / 16)) * 16;
 #pragma unroll
                             for (int n = 0; n < 16; ++n) acc[mb][c0 + n] += __uint_as_float(v[j][n]);
                         }
@@ -658,7 +685,7 @@ tcx_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(2 * MB * BN)));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS));
     }
     if (p.colsum_part && threadIdx.x < BN && (int)threadIdx.x < p.N) {
         // column n lives in column half n / HALF: sum its four quadrant warps (fixed order) -> one partial row per CTA
@@ -960,7 +987,9 @@ int launch_fwd(const TcxFwd& p, const CUtensorMap* m, cudaStream_t st) {
     if (base_offset < 0) { const char* e = getenv("A2CB_TCX_PATCH_BO"); base_offset = (e && e[0] == '1') ? 1 : 0; }
     const long n_work = (long)p.tiles.n_tiles * ((p.N + BN - 1) / BN);
     dim3 grid((unsigned)(n_work < kNumSM ? n_work : kNumSM));
-    tcx_fwd_kernel<BN, MB, BF16, PATCH><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], p, stages, base_offset, stagesB);
+    static int merge_on = -1;
+    if (merge_on < 0) { const char* e = getenv("A2CB_TCX_MERGE"); merge_on = (e && e[0] >= '0' && e[0] <= '7') ? e[0] - '0' : 7; }
+    tcx_fwd_kernel<BN, MB, BF16, PATCH><<<grid, TX_NT, smem, st>>>(m[0], m[1], m[2], m[3], m[4], p, stages, base_offset, stagesB, merge_on);
     return check_launch("tcx_fwd");
 }
 

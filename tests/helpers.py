@@ -108,3 +108,30 @@ def assert_summary_close(got, want, rtol, atol, what="", elem_frac=0.0):
     assert abs(got[1] - want[1]) <= rtol * scale + atol, "%s: norm %r vs %r" % (what, got[1], want[1])
     assert abs(got[0] - want[0]) <= ((rtol + elem_frac) * scale + atol) * np.sqrt(n), "%s: sum %r vs %r" % (what, got[0], want[0])
     np.testing.assert_allclose(got[3:], want[3:], rtol=rtol, atol=atol + (rtol + elem_frac) * scale / np.sqrt(n), err_msg=what)
+
+
+def relu_knife_edge(case, cfg, obs_uint8, rel=3e-6):
+    """Smallest |pre-activation| / layer RMS of the CNN trunk's LAST ReLU layer (Linear 1568 -> 512, reference
+    model.py:176-188) on the case's update batch, computed with the fp32 CPU oracle parameters, and whether it is
+    below `rel`.
+
+    A unit whose pre-activation is that close to zero relative to the layer's scale has an UNDETERMINED sign at fp32
+    accuracy: the reference's own rounding, the exact-fp32 engine and the 3xTF32 tensor-core engine may each put it on
+    either side, and its relu' bit then switches a whole row-gradient entry of the 512-wide feature layer on or off
+    (every layer below inherits it).  The small goldens sit at >= 1.7e-4 (80 x 512 units: nothing near zero) -- except
+    update_C2, whose unit [72, 188] has 8.0e-7 against an RMS of 0.55 (1.5e-6); the full-size C3 case has 1.1e-6.  Update
+    goldens with such a unit cannot be held to the 1e-4 vector bound on the parameters after the step (losses are)."""
+    import torch.nn.functional as F
+    from oracle import policy as o_pol
+    if len(cfg["obs_shape"]) != 3:
+        return 1.0, False
+    ro = rollout_from_case(case, cfg, obs_uint8=obs_uint8)
+    spec = o_pol.Spec(cfg["obs_shape"], cfg["action"], cfg["recurrent"])
+    p = o_pol.init_params(spec, seed=1)
+    a = ro["obs"][:-1].reshape(-1, *cfg["obs_shape"]).float() / 255.0
+    with torch.no_grad():
+        for i, stride in ((0, 4), (2, 2), (4, 1)):
+            a = F.conv2d(a, p["base.main.%d.weight" % i], p["base.main.%d.bias" % i], stride=stride).relu()
+        z = F.linear(a.reshape(a.shape[0], -1), p["base.main.7.weight"], p["base.main.7.bias"])
+        worst = float(z.abs().min() / (z ** 2).mean().sqrt())
+    return worst, worst < rel

