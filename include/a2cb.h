@@ -132,7 +132,9 @@ typedef struct {
     int32_t tc_chunk;   /* tensor-core engine: k-blocks (32 reduction indices each) accumulated in TMEM before
                            the partial sum is drained into fp32 registers (the tensor core's accumulator
                            truncates; short chains keep long, cancelling reductions exact enough).  0 = 8 */
-    int32_t pad_;
+    int32_t sym;        /* 1: the product is symmetric (M == N, B is A transposed through the maps: KFAC's a^T a and
+                           g^T g, reference kfac.py:29-64): tiles strictly below the diagonal are skipped and the tiles
+                           above it also store their mirror image C[rowC(j) + colC(i)] (SIMT engine only) */
     const float* B_image; /* optional image of B produced by a2cb_gemm_prep_b (weights: once per optimiser step);
                              the tensor-core engine then loads B with one TMA bulk copy per k-block */
 } a2cb_gemm_t;

@@ -265,6 +265,7 @@ def resolve(plan, arena):
     g.splits, g.split_stride = plan.splits, plan.split_stride
     g.vecA, g.vecB, g.tile = plan.vecA, plan.vecB, plan.tile
     g.tc_chunk = plan.tc_chunk
+    g.sym = plan.sym
     g.B_image = arena.ptr(plan.b_image)
     return g
 

@@ -42,7 +42,7 @@ class GemmDesc(ctypes.Structure):
         ("alpha", c_f32), ("batch", c_i32),
         ("batch_offA", c_i64 * 4), ("batch_offB", c_i64 * 4), ("batch_offC", c_i64 * 4), ("batch_offM", c_i64 * 4),
         ("splits", c_i32), ("vecA", c_i32), ("split_stride", c_i64), ("vecB", c_i32), ("tile", c_i32),
-        ("tc_chunk", c_i32), ("pad_", c_i32), ("B_image", c_vp),
+        ("tc_chunk", c_i32), ("sym", c_i32), ("B_image", c_vp),
     ]
 
 
@@ -109,6 +109,7 @@ class Plan(object):
         self.accumulate = kw.pop("accumulate", 0)
         self.tile = kw.pop("tile", 0)
         self.tc_chunk = kw.pop("tc_chunk", 0)
+        self.sym = kw.pop("sym", 0)                 # symmetric product: the engine computes the upper tiles only
         self.b_image = kw.pop("b_image", None)      # (buffer, offset) of the pre-tiled hi/lo image of B
         self.flops = 2 * self.M * self.N * self.K * self.batch
         assert not kw, kw

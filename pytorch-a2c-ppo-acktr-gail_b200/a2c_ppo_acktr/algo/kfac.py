@@ -102,7 +102,7 @@ class KFACOptimizer(object):
             part = buf("part_" + name, splits * n * n)
             p = P.Plan("kfac." + name, Asrc, Bsrc, ("kfac_part_" + name, 0), n, n, K, rowA, redA, redB, colB, rowC, colC,
                        splits=splits, split_stride=n * n, split_dst=("kfac_m_" + name, 0, n * n), accumulate=1,
-                       vecA=vecA, vecB=vecB, alpha=scale, tile=1001)
+                       vecA=vecA, vecB=vecB, alpha=scale, tile=1001, sym=1)
             p.base_scale = scale
             return p
 

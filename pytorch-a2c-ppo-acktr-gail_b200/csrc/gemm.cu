@@ -78,6 +78,9 @@ gemm_kernel(const GemmDesc g) {
     const int tid = threadIdx.x;
     const int batch = blockIdx.z / g.splits, split = blockIdx.z % g.splits;
     const long i0 = (long)blockIdx.y * BM, j0 = (long)blockIdx.x * BN;
+    // symmetric product (KFAC factors): a tile that lies strictly below the diagonal is produced, transposed, by the
+    // tile above it -- half the flops of the full product (reference kfac.py:42,60 computes the full a^T a / g^T g)
+    if (g.sym && i0 > j0 + BN - 1) return;
     const long ktiles = (g.K + kBK - 1) / kBK;
     const long tps = (ktiles + g.splits - 1) / g.splits;
     const long kbeg = (long)split * tps * kBK;
@@ -91,7 +94,9 @@ gemm_kernel(const GemmDesc g) {
         if (i < g.M) {
             rA[t] = affine_eval(g.rowA, i, g.gather_row);
             rC[t] = affine_eval(g.rowC, i, nullptr);
-            rM[t] = g.mask_mode ? affine_eval(g.rowM, i, nullptr) : 0;
+            // (symmetric products carry no mask: the mask tables hold the maps of the mirror image instead --
+            //  colC of this tile's rows here, rowC of its columns below)
+            rM[t] = g.mask_mode ? affine_eval(g.rowM, i, nullptr) : (g.sym ? affine_eval(g.colC, i, nullptr) : 0);
             rflag[t] = 0;
         } else {
             rA[t] = rC[t] = rM[t] = 0;
@@ -103,7 +108,7 @@ gemm_kernel(const GemmDesc g) {
         if (j < g.N) {
             cB[t] = affine_eval(g.colB, j, nullptr);
             cC[t] = affine_eval(g.colC, j, nullptr);
-            cM[t] = g.mask_mode ? affine_eval(g.colM, j, nullptr) : 0;
+            cM[t] = g.mask_mode ? affine_eval(g.colM, j, nullptr) : (g.sym ? affine_eval(g.rowC, j, nullptr) : 0);
             cvalid[t] = 1;
         } else {
             cB[t] = cC[t] = cM[t] = 0;
@@ -300,6 +305,11 @@ gemm_kernel(const GemmDesc g) {
                 if (g.accumulate) v += *dst;
             }
             *dst = v;
+            if (g.sym) {
+                // mirror image of an element above the diagonal, when the tile that would hold it was skipped
+                const long gi = i0 + il, gj = j0 + jl;
+                if (gi < gj && (gj / BM) * BM > (gi / BN) * BN + BN - 1) Cb[cM[jl] + rM[il]] = v;
+            }
         }
     }
 }
@@ -351,6 +361,8 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
     A2CB_REQUIRE(g.vecA != 2 || g.M % 4 == 0, "gemm: vecA=2 needs M %% 4 == 0");
     A2CB_REQUIRE(g.vecB != 1 || g.N % 4 == 0, "gemm: vecB=1 needs N %% 4 == 0");
     A2CB_REQUIRE(g.vecB != 2 || g.K % 4 == 0, "gemm: vecB=2 needs K %% 4 == 0");
+    A2CB_REQUIRE(!g.sym || (g.M == g.N && !g.ones_row && !g.bias_mode && !g.act && !g.mask_mode && !g.accumulate && g.tile == 1001),
+                 "gemm: sym needs a square product without epilogue on the SIMT engine (tile 1001)");
     if (g.M + g.ones_row == 0 || g.N == 0) return A2CB_OK;
     if (g.tile != 1001 && gemm_tc_supported(g)) {
         const int mode = gemm_mode();

@@ -39,7 +39,7 @@ struct GemmDesc {
     int32_t vecB;         // 0 scalar, 1 four consecutive columns contiguous & aligned
     int32_t tile;         // 0 auto, else preferred BN (32 / 64 / 128)
     int32_t tc_chunk;     // tensor-core engine: k-blocks (of 32) per TMEM accumulation chain, 0 = default 8
-    int32_t pad_;
+    int32_t sym;          // symmetric product (SYRK): lower tiles skipped, upper tiles also store their mirror image
     const float* B_image; // optional: B pre-split (hi | lo) and pre-tiled in the UMMA smem layout by
                           // gemm_prep_b(); the tensor-core engine then fetches it with one TMA bulk copy
                           // per k-block instead of gathering + splitting it in every CTA
