@@ -411,13 +411,13 @@ def golden_parity_check(cfg, obs_np, dev):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the C5 shard
-# (profiles/r01f_tcx_gru_full_c5.txt); only meaningful for that workload
-NCU_DRAM_SOURCE = "profiles/r01f_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
+# (profiles/r02y_tcx_gru_full_c5.txt); only meaningful for that workload
+NCU_DRAM_SOURCE = "profiles/r02y_tcx_gru_full_c5.txt (ncu --set full, C5 shard)"
 NCU_DRAM_BYTES = {
-    "conv1.fwd": 0.464279e9 + 783.700e6, "conv2.fwd": 0.840722e9 + 310.317e6, "conv3.fwd": 0.340063e9 + 82.415e6,
-    "conv2.dgrad": 0.759710e9 + 793.716e6, "conv3.dgrad": 0.272854e9 + 291.207e6,
-    "conv1.wgrad": 1.764638e9 + 3.536e6, "conv2.wgrad": 1.184132e9 + 8.677e6, "conv3.wgrad": 0.442583e9 + 4.129e6,
-    "gru.seq_fwd": 0.053970e9 + 47.836e6, "gru.seq_bwd": 0.104082e9 + 59.566e6,
+    "conv1.fwd": 0.463882e9 + 784.483e6, "conv2.fwd": 0.841301e9 + 310.626e6, "conv3.fwd": 0.340044e9 + 82.657e6,
+    "conv2.dgrad": 0.759749e9 + 794.737e6, "conv3.dgrad": 0.272990e9 + 291.951e6,
+    "conv1.wgrad": 1.764634e9 + 3.855e6, "conv2.wgrad": 1.182154e9 + 7.643e6, "conv3.wgrad": 0.444832e9 + 9.184e6,
+    "gru.seq_fwd": 0.053998e9 + 47.039e6, "gru.seq_bwd": 0.104061e9 + 62.479e6,
 }
 
 
