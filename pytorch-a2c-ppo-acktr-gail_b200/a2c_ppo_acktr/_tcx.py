@@ -555,7 +555,7 @@ class CnnNet(object):
         R = 32
         ot_a, ot_b = -(-K // 128), -(-N // 256)
         n_rt = -(-B // R)
-        splits, per = split_rows(n_rt, max(1, 160 // (ot_a * ot_b)))
+        splits, per = split_rows(n_rt, max(1, 148 // (ot_a * ot_b)))      # one wave of CTAs (fc: 26 tiles x 5 splits, not 6)
         part = self.nb.buf("wpart_" + name, splits * N * K)
         row_off = []
         for f in range(ot_a * 128):

@@ -327,16 +327,20 @@ class Policy(nn.Module):
         return value, action, logp, hout
 
     use_cuda_graph = True      # act_into: one CUDA graph per (rollout slot, mode), captured on its second use
+    MAX_ACT_GRAPHS = 512       # per batch size: a rollout has num_steps slots (2048 for the MuJoCo recipe runs uncaptured
+                               # beyond this); the least recently used entry is dropped when a new slot shows up
 
     def _act_graphed(self, plan, key, launch):
         """A slot's actor step is the same launch sequence with the same pointers every iteration (the sampling
         stream advances on the device), so from its second use on it is replayed as a CUDA graph: the host cost
         of a step drops from ~10 launches + their TMA descriptor encodes to one replay."""
         graphs = plan.graphs
-        g = graphs.get(key)
-        if not self.use_cuda_graph or (g is None and len(graphs) >= 4096):
+        g = graphs.pop(key, None)                             # re-inserted below: dict order = recency
+        if not self.use_cuda_graph:
             return launch()
         if g is None:
+            while len(graphs) >= self.MAX_ACT_GRAPHS:
+                graphs.pop(next(iter(graphs)))
             graphs[key] = "seen"
             return launch()
         if g == "seen":
@@ -348,7 +352,8 @@ class Policy(nn.Module):
                 launch()
             n = _native.launch_count() - n0
             _native.lib().a2cb_add_launches(-n)               # capture recorded, did not run, them
-            g = graphs[key] = (graph, n)
+            g = (graph, n)
+        graphs[key] = g
         g[0].replay()
         _native.lib().a2cb_add_launches(g[1])
 

@@ -102,6 +102,52 @@ def test_gemm_split_k_and_reduce():
     assert np.all(got["G"][:5] == 3.0)
 
 
+@pytest.mark.parametrize("n,K,perm", [(1, 300, False), (96, 700, False), (257, 3000, True), (576, 2100, True)])
+def test_gemm_symmetric_product_upper_tiles_and_mirror(n, K, perm):
+    """KFAC factor products (reference kfac.py:29-64: a^T a, g^T g) as SYMMETRIC products: `sym` makes the engine skip the
+    tiles strictly below the diagonal and lets the tiles above store their mirror image through the transposed output maps
+    (a2cb_gemm_t.sym).  The folded result must equal the full product -- here with split-K, a running average folded in
+    (beta * old + sum) and, for `perm`, the digit-reversing output permutation the conv factors use (engine K order
+    (ky, kx, c) -> reference patch order (c, ky, kx))."""
+    rng = np.random.default_rng(n + K)
+    splits = 3 if K > 100 else 1
+    X = rng.standard_normal((K, n)).astype(np.float32)
+    old = rng.standard_normal(n * n).astype(np.float32)
+    old = (old.reshape(n, n) + old.reshape(n, n).T).reshape(-1).copy()
+    bufs = {"X": X.reshape(-1).copy(), "part": np.full(splits * n * n, 7.0, np.float32), "m": old.copy()}
+    if perm and n % 9 == 0:         # n = c * 9: (tap, c) -> (c, tap)
+        c = n // 9
+        rowC, colC = P.aff(c, 1, n, 9 * n, 0), P.aff(c, 1, 1, 9, 0)
+        order = np.array([(i % c) * 9 + i // c for i in range(n)])
+    else:
+        rowC, colC = P.plain(n), P.plain(1)
+        order = np.arange(n)
+    plan = P.Plan("sym", ("X", 0), ("X", 0), ("part", 0), n, n, K, P.plain(1), P.plain(n), P.plain(n), P.plain(1), rowC, colC,
+                  splits=splits, split_stride=n * n, split_dst=("m", 0, n * n), accumulate=1, split_beta=0.5, alpha=0.25,
+                  tile=1001, sym=1, vecA=2 if n % 4 == 0 else 0, vecB=1 if n % 4 == 0 else 0)
+    got = run_plan(plan, bufs)
+    full = 0.25 * (X.astype(np.float64).T @ X.astype(np.float64))
+    want = np.zeros((n, n))
+    want[np.ix_(order, order)] = full
+    want = 0.5 * old.reshape(n, n) + want
+    np.testing.assert_allclose(got["m"].reshape(n, n), want, rtol=2e-5, atol=2e-4)
+    assert np.array_equal(got["m"].reshape(n, n), got["m"].reshape(n, n).T), "the mirror image is a copy: exactly symmetric"
+
+
+def test_gru_tc_consecutive_launches_with_changing_group_counts():
+    """The tcgen05 recurrence validates every exchanged word by a 2-bit step tag and relies on a memset of the exchange
+    buffers in front of each launch (csrc/gru_tc.cu): launches with more, fewer and again more environment groups, odd
+    and even step counts, must not see each other's leftovers."""
+    _native.set_gru_mode(2)
+    try:
+        for T, N, H in ((6, 150, 512), (5, 8, 512), (7, 64, 512), (3, 150, 512), (2, 24, 256), (9, 64, 512)):
+            if _native.gru_seq_variant(N, H) != "tc":
+                pytest.skip("tcgen05 recurrence not available for this shape")
+            _run_gru_case(T, N, H, 0.2)
+    finally:
+        _native.set_gru_mode(-1)
+
+
 @pytest.mark.parametrize("B", [4, 37])
 def test_cnn_forward_backward_conv3_patch_mode(B, monkeypatch):
     """The opt-in TF32 patch mode of conv3's forward (A2CB_TCX_PATCH3=1: one 9 x 9 patch per tile and channel half,
