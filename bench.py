@@ -320,6 +320,19 @@ def run_ours(args):
     clocks = sampler.stop(t0, t1)
     timed(1, True)
     e2e_ms, _ = timed(args.steps, True)
+    # N > 1, recurrent PPO: the default draws the reference's ONE global randperm, so every rank's share of a minibatch is
+    # hypergeometric and a step lasts as long as the fullest rank.  The balanced opt-in scheme (NOT the reference's
+    # minibatch composition) is timed next to it, a few steps, to separate that imbalance from the cost of the exchange.
+    strat = None
+    if world > 1 and cfg.get("recurrent") and getattr(agent, "recurrent_sharding", "") == "global":
+        agent.recurrent_sharding = "stratified"
+        timed(2, False)
+        k = max(3, min(args.steps, 5))
+        s_ms, _ = timed(k, False)
+        agent.recurrent_sharding = "global"
+        strat = {"value": T * Nloc * world / (s_ms / k / 1e3), "unit": "transitions/s", "ms_per_step": s_ms / k, "steps": k,
+                 "note": "recurrent_sharding='stratified': balanced per-rank permutations, not the reference's minibatch "
+                         "composition; shown to separate load imbalance from exchange cost"}
 
     transitions = T * Nloc * world
     ms_per_step = total_ms / args.steps
@@ -349,6 +362,8 @@ def run_ours(args):
             "clocks": clocks,
             "losses": [float(x) for x in losses],
         }
+        if strat:
+            out["stratified_sharding"] = strat
         if roof:
             out["roofline"] = roof
             out["kernels"] = kernels
