@@ -305,6 +305,8 @@ def run_ours(args):
             if world > 1:
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             total_ms += ms.item()
+            if rank == 0 and os.environ.get("A2CB_BENCH_VERBOSE") == "1":
+                sys.stderr.write("step %d (%s): %.3f ms\n" % (i, "e2e" if e2e else "resident", ms.item()))
         return total_ms, losses
 
     timed(args.warmup, False)
@@ -320,16 +322,17 @@ def run_ours(args):
     clocks = sampler.stop(t0, t1)
     timed(1, True)
     e2e_ms, _ = timed(args.steps, True)
-    # N > 1, recurrent PPO: the default draws the reference's ONE global randperm, so every rank's share of a minibatch is
-    # hypergeometric and a step lasts as long as the fullest rank.  The balanced opt-in scheme (NOT the reference's
-    # minibatch composition) is timed next to it, a few steps, to separate that imbalance from the cost of the exchange.
+    # N > 1, recurrent PPO: the default forms the reference's minibatches (ONE global randperm per epoch) and migrates the
+    # surplus environments of a minibatch between ranks.  The stratified opt-in scheme (balanced by construction, NOT the
+    # reference's minibatch composition, no migration) is timed next to it, a few steps, as the no-migration bound.
     strat = None
-    if world > 1 and cfg.get("recurrent") and getattr(agent, "recurrent_sharding", "") == "global":
+    if world > 1 and cfg.get("recurrent") and getattr(agent, "recurrent_sharding", "") in ("global", "balanced"):
+        default_mode = agent.recurrent_sharding
         agent.recurrent_sharding = "stratified"
         timed(2, False)
         k = max(3, min(args.steps, 5))
         s_ms, _ = timed(k, False)
-        agent.recurrent_sharding = "global"
+        agent.recurrent_sharding = default_mode
         strat = {"value": T * Nloc * world / (s_ms / k / 1e3), "unit": "transitions/s", "ms_per_step": s_ms / k, "steps": k,
                  "note": "recurrent_sharding='stratified': balanced per-rank permutations, not the reference's minibatch "
                          "composition; shown to separate load imbalance from exchange cost"}
@@ -728,8 +731,9 @@ def main():
     ap.add_argument("--stacked-frames", action="store_true",
                     help="Atari workloads: store / upload full 4-frame stacks (reference layout) instead of the frame ring")
     ap.add_argument("--envs", type=int, default=0, help="override the number of environments per GPU")
-    ap.add_argument("--recurrent-sharding", default="", choices=["", "global", "stratified"],
-                    help="N > 1, recurrent PPO: 'global' (default) = the reference's one randperm(N_total); "
+    ap.add_argument("--recurrent-sharding", default="", choices=["", "global", "balanced", "stratified"],
+                    help="N > 1, recurrent PPO: 'global' / 'balanced' = the reference's one randperm(N_total), every rank "
+                         "processing the environments it owns / exactly E / world of them after migrating the surplus; "
                          "'stratified' = balanced per-rank permutations (not the reference's minibatch composition)")
     args = ap.parse_args()
     global ENVS_OVERRIDE

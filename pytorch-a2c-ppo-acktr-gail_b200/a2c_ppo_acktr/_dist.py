@@ -92,6 +92,86 @@ def shard_env_chunks(perm, E_global, n_mb, shard):
     return out
 
 
+def balance_update_plan(perms, E_global, n_mb, world, n_local):
+    """Reference-identical minibatches, balanced: who processes which environment of every global recurrent minibatch.
+
+    `perms`: the `randperm(N_total)` of every epoch of one update (reference storage.py:152), identical on every rank;
+    global minibatch (e, k) is perms[e][k E : (k + 1) E].  Its environments are spread over their owner ranks
+    hypergeometrically; every rank keeps the first E / world of ITS environments (in chunk order), the rest are moved to
+    the ranks that own fewer, donors and receivers matched in rank order -- the minimum number of moves, a pure function
+    of the permutations, so every rank computes the same plan.  A moved environment lands in the next free GUEST slot of
+    its receiver (column n_local + slot of the receiver's shadow rollout).
+
+    Returns a list over ranks of dict(envs=[epoch][minibatch] -> int64 columns (E / world of them),
+    send=[dst] -> local columns in transfer order, recv=[src] -> guest slots in the same order, n_guests)."""
+    assert E_global % world == 0, "the global recurrent minibatch must split evenly over the ranks"
+    target = E_global // world
+    out = [dict(envs=[[None] * n_mb for _ in perms], send=[[] for _ in range(world)], recv=[[] for _ in range(world)],
+                n_guests=0) for _ in range(world)]
+    for e, perm in enumerate(perms):
+        perm = np.asarray(perm, dtype=np.int64)
+        for k in range(n_mb):
+            chunk = perm[k * E_global:(k + 1) * E_global]
+            owner = chunk // n_local
+            order = np.argsort(owner, kind="stable")             # chunk order inside every owner
+            counts = np.bincount(owner, minlength=world)
+            starts = np.concatenate([[0], np.cumsum(counts)])
+            local = chunk[order] - owner[order] * n_local
+            keep, sur_src, sur_col = [], [], []
+            for r in range(world):
+                mine = local[starts[r]:starts[r + 1]]
+                keep.append(mine[:target])
+                if len(mine) > target:
+                    sur_col.append(mine[target:])
+                    sur_src.append(np.full(len(mine) - target, r, np.int64))
+            sur_col = np.concatenate(sur_col) if sur_col else np.zeros(0, np.int64)
+            sur_src = np.concatenate(sur_src) if sur_src else np.zeros(0, np.int64)
+            si = 0
+            for r in range(world):
+                need = target - len(keep[r])
+                if need > 0:
+                    slots = np.arange(out[r]["n_guests"], out[r]["n_guests"] + need, dtype=np.int64)
+                    out[r]["n_guests"] += need
+                    for j in range(need):
+                        src = int(sur_src[si + j])
+                        out[src]["send"][r].append(int(sur_col[si + j]))
+                        out[r]["recv"][src].append(int(slots[j]))
+                    si += need
+                    keep[r] = np.concatenate([keep[r], n_local + slots])
+                out[r]["envs"][e][k] = np.asarray(keep[r], dtype=np.int64)
+            assert si == len(sur_col)
+    for o in out:
+        o["send"] = [np.asarray(x, dtype=np.int64) for x in o["send"]]
+        o["recv"] = [np.asarray(x, dtype=np.int64) for x in o["recv"]]
+    return out
+
+
+class Exchange(object):
+    """A variable all-to-all of fixed-size byte records (rows of `send` / `recv`, uint8 [n, record_bytes]): block d of
+    `send` (send_counts[d] rows) goes to rank d, block s of `recv` arrives from rank s.  Yielded by the sharded update
+    generators next to the tensors they want summed; `run` is the torch.distributed (NCCL) call, `emulate` performs
+    the same movement between the objects of several emulated ranks in one process (tests)."""
+
+    def __init__(self, send, send_counts, recv, recv_counts):
+        self.send, self.recv = send, recv
+        self.send_counts, self.recv_counts = [int(c) for c in send_counts], [int(c) for c in recv_counts]
+
+    def run(self):
+        import torch.distributed as dist
+        dist.all_to_all_single(self.recv, self.send, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts)
+
+    @staticmethod
+    def emulate(items):
+        so = [np.concatenate([[0], np.cumsum(x.send_counts)]) for x in items]
+        ro = [np.concatenate([[0], np.cumsum(x.recv_counts)]) for x in items]
+        for d, dst in enumerate(items):
+            for s, src in enumerate(items):
+                n = src.send_counts[d]
+                assert n == dst.recv_counts[s]
+                if n:
+                    dst.recv[int(ro[d][s]):int(ro[d][s]) + n].copy_(src.send[int(so[s][d]):int(so[s][d]) + n])
+
+
 def env_capacity(E_global, shard, gran):
     """Environments per recurrent minibatch a shard must be able to hold: the hypergeometric expectation plus a
     6-sigma margin, rounded up to the program granularity and capped by what the shard owns."""

@@ -12,6 +12,7 @@ Minibatch order: one `torch.randperm(T*N)` per epoch from the global CPU generat
 into consecutive chunks with the remainder dropped -- the sampler semantics of
 reference storage.py:122-125 -- so identical seeds give identical minibatches.
 """
+import numpy as np
 import torch
 
 from .. import _dist, _native
@@ -56,7 +57,13 @@ class PPO():
     GRAPH_SLOTS = 4            # epochs whose index / scalar uploads may be in flight at once (_epoch_graph)
     ENV_GRANULARITY = 4        # sharded recurrent minibatches: local environment count rounded up to this many slots
     native_exchange = True     # sharded: exchange gradients inside the op list through liba2cb's NCCL communicator
-    recurrent_sharding = "global"      # "global": the reference's one randperm(N_total); "stratified": balanced opt-in
+    # sharded recurrent PPO.  "balanced" (default) and "global" both form the reference's minibatches -- the ONE
+    # randperm(N_total) per epoch of storage.py:152.  "global": every rank processes the environments of a minibatch it
+    # owns (hypergeometric counts: a step lasts as long as the fullest rank).  "balanced": the surplus environments of a
+    # minibatch migrate to the ranks that own fewer (one all-to-all of rollout columns per update), so every rank runs
+    # exactly E / world environments; it needs equal contiguous shards and E divisible by world, else "global" runs.
+    # "stratified" = balanced per-rank permutations, NOT the reference's minibatch composition (round 1)
+    recurrent_sharding = "balanced"
 
     def __init__(self,
                  actor_critic,
@@ -335,7 +342,11 @@ class PPO():
     def _drive(gen):
         try:
             while True:
-                _dist.all_reduce_sum(next(gen))
+                item = next(gen)
+                if isinstance(item, _dist.Exchange):
+                    item.run()
+                else:
+                    _dist.all_reduce_sum(item)
         except StopIteration as done:
             return done.value
 
@@ -344,6 +355,11 @@ class PPO():
         `recurrent_sharding` selects how the global minibatches are formed (see the two methods)."""
         if self.recurrent_sharding == "stratified":
             return self._sharded_recurrent_stratified(rt, rollouts)
+        sh = self.shard
+        nmb = self.num_mini_batch
+        if (self.recurrent_sharding == "balanced" and sh.world > 1 and sh.n_local * sh.world == sh.n_total
+                and sh.lo == sh.rank * sh.n_local and sh.n_total % (nmb * sh.world) == 0):
+            return self._sharded_recurrent_balanced(rt, rollouts)
         return self._sharded_recurrent_global(rt, rollouts)
 
     def _sized_recurrent_program(self, rt, rollouts, E_p, adv, accum, inv_B):
@@ -444,6 +460,146 @@ class PPO():
                     self.step_hook(self.optimizer.step_count)
             if epoch == 0:
                 finish()
+        self.last_launches = _native.launch_count() - launches0
+        yield accum
+        num_updates = self.ppo_epoch * self.num_mini_batch
+        sums = accum[:3].cpu()
+        return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
+
+    # ---- reference-identical minibatches, balanced by migrating environments -------------------------------------
+    _MIGRATED = ("masks", "value_preds", "returns", "action_log_probs", "actions")
+
+    def _shadow_rollout(self, rt, rollouts, n_guests):
+        """The rollout this rank trains on in balanced mode: its own environments (columns 0 .. n_local - 1, copied
+        from `rollouts` at the start of every update) followed by guest columns for migrated environments."""
+        from ..storage import RolloutStorage
+        T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+        cap = getattr(self, "_shadow_cap", 0)
+        if n_guests > cap or getattr(self, "_shadow_src", None) != (rollouts.rewards.data_ptr(), T, n_loc):
+            cap = max(cap, 96, (int(n_guests * 1.25) + 31) // 32 * 32)
+            ring = bool(getattr(rollouts, "frame_ring", False))
+            obs_shape = tuple(rollouts.obs.shape[2:])
+
+            # (the storage duck-types its action space by class name, like the reference: storage.py:19,24)
+            space = type("Discrete" if rollouts.actions.dtype == torch.int64 else "Box", (object,),
+                         {"shape": (rollouts.actions.shape[-1],), "n": 0})()
+            # (+ 1: a dummy guest column that the fixed-shape scatter of unused message rows writes to)
+            sh = RolloutStorage(T, n_loc + cap + 1, obs_shape, space, rollouts.recurrent_hidden_states.shape[-1],
+                                obs_dtype=torch.uint8 if ring else rollouts.obs.dtype, frame_ring=ring)
+            sh.to(rt.dev)
+            self._shadow, self._shadow_cap = sh, cap
+            self._shadow_src = (rollouts.rewards.data_ptr(), T, n_loc)
+        return self._shadow
+
+    def _migration_fields(self, st):
+        """(tensor, leading rows) of everything an update reads per environment (dimension 1 = environment)."""
+        f = [(st.frames, None), (st.stack_valid, None)] if getattr(st, "frame_ring", False) else [(st.obs, None)]
+        f += [(getattr(st, k), None) for k in self._MIGRATED]
+        f.append((st.recurrent_hidden_states, 1))              # only the initial state is read (storage.py:160-161)
+        return f
+
+    def _sharded_recurrent_balanced(self, rt, rollouts):
+        """Reference-identical minibatches (the ONE `randperm(N_total)` per epoch of reference storage.py:152) with every
+        rank processing exactly E / world environments of each: `_dist.balance_update_plan` moves the surplus
+        environments of a minibatch to the ranks that own fewer.  All permutations of the update are drawn first (the
+        same RNG sequence as drawing one per epoch), the rollout columns of every environment that has to move travel in
+        ONE all-to-all per update (~0.9 MB per environment in frame-ring format, a few dozen per rank), and the update
+        then runs on a shadow rollout [own environments | guests] with a single program size."""
+        sh = self.shard
+        self._update_serial = getattr(self, "_update_serial", 0) + 1
+        T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
+        assert n_loc == sh.n_local, "rollouts hold %d environments, the shard declares %d" % (n_loc, sh.n_local)
+        nmb = self.num_mini_batch
+        E_g = sh.n_total // nmb
+        E = E_g // sh.world
+        perms = [torch.randperm(sh.n_total).numpy() for _ in range(self.ppo_epoch)]
+        plans = _dist.balance_update_plan(perms, E_g, nmb, sh.world, n_loc)
+        mine = plans[sh.rank]
+        moments = _adv_moments(rt, rollouts)
+        yield moments
+        _wait_staged(rollouts)                                  # migration reads the frames: the upload has to be complete
+        shadow = self._shadow_rollout(rt, rollouts, max(p["n_guests"] for p in plans))
+        Nv = shadow.rewards.shape[1]
+        dev = rt.dev
+        # ---- own columns, then the guests ----
+        src_f, dst_f = self._migration_fields(rollouts), self._migration_fields(shadow)
+        for (a, rows), (b, _) in zip(src_f, dst_f):
+            if rows is None:
+                b[:, :n_loc].copy_(a)
+            else:
+                b[:rows, :n_loc].copy_(a[:rows])
+        # Every shape below is the CAPACITY of the shadow rollout, not this update's count: the gather / scatter
+        # temporaries and the message buffers then have the same sizes in every update (no allocator growth, no new
+        # NCCL message sizes in the middle of a run); unused rows point at a dummy guest column (the last one).
+        cap = Nv - n_loc - 1
+        n_send, n_recv = sum(len(x) for x in mine["send"]), sum(len(x) for x in mine["recv"])
+        assert n_send <= cap and n_recv <= cap
+        send_np, recv_np = np.zeros(cap, np.int64), np.full(cap, cap, np.int64)
+        send_np[:n_send] = np.concatenate(mine["send"])
+        recv_np[:n_recv] = np.concatenate(mine["recv"])
+        send_cols, recv_cols = torch.from_numpy(send_np).to(dev), torch.from_numpy(recv_np).to(dev) + n_loc
+        widths = [(x if rows is None else x[:rows])[:, 0].numel() * x.element_size() for x, rows in src_f]
+        rec_bytes = sum(widths)
+        bufs = getattr(self, "_xchg_bufs", None)
+        if bufs is None or bufs[0].shape != (cap, rec_bytes) or bufs[0].device != dev:
+            bufs = self._xchg_bufs = (torch.zeros(cap, rec_bytes, dtype=torch.uint8, device=dev),
+                                      torch.zeros(cap, rec_bytes, dtype=torch.uint8, device=dev))
+        send, recv = bufs
+        off = 0
+        for (a, rows), w in zip(src_f, widths):
+            x = a if rows is None else a[:rows]
+            send[:, off:off + w].copy_(x.index_select(1, send_cols).transpose(0, 1).reshape(cap, -1).contiguous().view(torch.uint8))
+            off += w
+        yield _dist.Exchange(send[:n_send], [len(x) for x in mine["send"]], recv[:n_recv], [len(x) for x in mine["recv"]])
+        off = 0
+        for (b, rows), w in zip(dst_f, widths):
+            x = b if rows is None else b[:rows]
+            piece = recv[:, off:off + w].reshape(-1).clone().view(cap, w).view(x.dtype).view((cap, x.shape[0]) + tuple(x.shape[2:]))
+            x.index_copy_(1, recv_cols, piece.transpose(0, 1))
+            off += w
+        adv = _adv_apply(rt, shadow, moments)
+        accum = rt.arena.ensure("loss_accum", 4)
+        accum.zero_()
+        inv_B = 1.0 / (T * E_g)
+        prog, opt = self._sized_recurrent_program(rt, shadow, E, adv, accum, inv_B)
+        H = rt.spec.hidden
+        h0 = shadow.recurrent_hidden_states[0]
+        t_off = (torch.arange(T, device=dev, dtype=torch.int64) * Nv).view(T, 1)
+        grads = rt.arena.bufs["G"]
+        launches0 = _native.launch_count()
+        chunked = getattr(prog, "prologue_chunk", None) is not None
+        if not chunked and getattr(prog, "prologue", None) is not None:
+            prog.prologue.run()
+        envs = [[torch.from_numpy(x).to(dev) for x in ep] for ep in mine["envs"]]
+        if chunked and self.ppo_epoch > 1:
+            # columns first used after the first epoch (own environments that the first epoch sent away, guests of later
+            # epochs): their frames are re-laid out now, E columns at a time (the re-layout program has that size)
+            first = np.unique(np.concatenate(mine["envs"][0]))
+            later = np.setdiff1d(np.unique(np.concatenate([x for ep in mine["envs"][1:] for x in ep])), first)
+            for i in range(0, len(later), E):
+                part = later[i:i + E]
+                part = np.concatenate([part, np.full(E - len(part), part[0], np.int64)])
+                env = torch.from_numpy(part).to(dev)
+                prog.prologue_chunk.run((t_off + env.view(1, E)).reshape(-1).contiguous())
+        for epoch in range(self.ppo_epoch):
+            for k in range(nmb):
+                env = envs[epoch][k]
+                rows = (t_off + env.view(1, E)).reshape(-1).contiguous()
+                if epoch == 0 and chunked:
+                    prog.prologue_chunk.run(rows)
+                hxs_mb = rt.arena.bufs["hxs_mb"][:E * H].view(E, H)
+                _native.gather_rows([(h0, hxs_mb)], env, E)
+                prog.loss_desc.n_valid = E
+                if getattr(prog, "fused_exchange", False):
+                    self.optimizer.configure(prog.optim_desc)
+                    prog.run(rows)
+                else:
+                    prog.run(rows)
+                    yield grads
+                    self.optimizer.configure(opt.optim_desc)
+                    opt.run()
+                if self.step_hook is not None:
+                    self.step_hook(self.optimizer.step_count)
         self.last_launches = _native.launch_count() - launches0
         yield accum
         num_updates = self.ppo_epoch * self.num_mini_batch

@@ -104,3 +104,40 @@ def test_world2_gloo_moments_and_partition():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert out[0] and out[1]
+
+
+def test_balance_update_plan_moves_the_minimum_and_keeps_the_reference_composition():
+    """`_dist.balance_update_plan`: every rank gets exactly E / world environments of every global minibatch, kept
+    environments stay where they are, the union over ranks is the reference's chunk perm[k E : (k + 1) E], the number of
+    moves is the sum of the surpluses (the minimum), and both ends of every transfer agree on counts and order."""
+    import numpy as np
+    import torch
+    from a2c_ppo_acktr import _dist
+    for world, n_total, nmb, epochs in ((2, 512, 4, 4), (8, 2048, 4, 4), (4, 64, 2, 3)):
+        n_local = n_total // world
+        g = torch.Generator().manual_seed(world)
+        perms = [torch.randperm(n_total, generator=g).numpy() for _ in range(epochs)]
+        E_g = n_total // nmb
+        plans = _dist.balance_update_plan(perms, E_g, nmb, world, n_local)
+        # what every guest slot holds: replay the transfers
+        guest = [dict() for _ in range(world)]
+        for s in range(world):
+            for d in range(world):
+                assert len(plans[s]["send"][d]) == len(plans[d]["recv"][s])
+                for col, slot in zip(plans[s]["send"][d], plans[d]["recv"][s]):
+                    guest[d][int(slot)] = int(col) + s * n_local
+        for r in range(world):
+            assert sorted(guest[r]) == list(range(plans[r]["n_guests"]))
+        moves = 0
+        for e in range(epochs):
+            for k in range(nmb):
+                chunk = perms[e][k * E_g:(k + 1) * E_g]
+                got = []
+                for r in range(world):
+                    cols = plans[r]["envs"][e][k]
+                    assert len(cols) == E_g // world
+                    got += [int(c) + r * n_local if c < n_local else guest[r][int(c) - n_local] for c in cols]
+                assert sorted(got) == sorted(int(x) for x in chunk)
+                owner = chunk // n_local
+                moves += sum(max(int((owner == r).sum()) - E_g // world, 0) for r in range(world))
+        assert moves == sum(p["n_guests"] for p in plans)

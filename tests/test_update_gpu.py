@@ -11,7 +11,7 @@ from test_oracle_golden import POLICY_CASES, policy_inputs
 
 pytestmark = pytest.mark.gpu
 
-from a2c_ppo_acktr import algo  # noqa: E402
+from a2c_ppo_acktr import _dist, algo  # noqa: E402
 from a2c_ppo_acktr.model import Policy  # noqa: E402
 from a2c_ppo_acktr.storage import RolloutStorage  # noqa: E402
 
@@ -407,6 +407,9 @@ def _lockstep(ranks):
             r["rng"] = torch.get_rng_state()
         if pend:
             assert len(pend) == len(ranks)
+            if isinstance(pend[0], _dist.Exchange):             # environment migration: a variable all-to-all
+                _dist.Exchange.emulate(pend)
+                continue
             total = torch.stack([t.clone() for t in pend]).sum(0)
             for t in pend:
                 t.copy_(total)
@@ -450,11 +453,15 @@ def test_sharded_acktr_equals_single_device(name, world, gemm_engine):
     assert rl2 <= (2e-3 if edge else 1e-4), rl2
 
 
-@pytest.mark.parametrize("name,world", [("C5s", 2), ("C5s", 4), ("C5m", 4)])
-def test_sharded_recurrent_ppo_vs_reference_golden(name, world, gemm_engine):
-    """Default sharded recurrent PPO (`recurrent_sharding = "global"`): every rank draws the reference's ONE
-    randperm(N_total) and processes the environments of each global chunk that it owns (count rounded up to the
-    program granularity, padding slots masked out).  `world` emulated ranks in lock-step on one GPU must reproduce
+@pytest.mark.parametrize("name,world,sharding", [("C5s", 2, "global"), ("C5s", 4, "global"), ("C5m", 4, "global"),
+                                                 ("C5s", 2, "balanced"), ("C5m", 4, "balanced")])
+def test_sharded_recurrent_ppo_vs_reference_golden(name, world, sharding, gemm_engine):
+    """Sharded recurrent PPO with the reference's minibatch composition.  "global" (default): every rank draws the
+    reference's ONE randperm(N_total) and processes the environments of each global chunk that it owns (count rounded
+    up to the program granularity, padding slots masked out).  "balanced": the same chunks, but the surplus environments
+    of a chunk migrate to the ranks that own fewer (`_dist.balance_update_plan`, one all-to-all of rollout columns per
+    update -- emulated here by `_dist.Exchange.emulate`), so every rank runs exactly E / world environments.
+    `world` emulated ranks in lock-step on one GPU must reproduce
     the REFERENCE golden of the single-device update: same minibatch composition, losses and parameters 1e-4."""
     if name == "C5m" and gemm_engine != "tcgen05":
         pytest.skip("benchmarked shape: default engine only")
@@ -481,7 +488,8 @@ def test_sharded_recurrent_ppo_vs_reference_golden(name, world, gemm_engine):
         agent = algo.PPO(pol, cfg["clip_param"], cfg["ppo_epoch"], cfg["num_mini_batch"], cfg["value_loss_coef"],
                          cfg["entropy_coef"], lr=cfg["lr"], eps=cfg["eps"], max_grad_norm=cfg["max_grad_norm"])
         agent.set_distributed(world, r, (lo, hi), N)
-        assert agent.recurrent_sharding == "global"
+        assert agent.recurrent_sharding == "balanced"          # the default; ("C5s", 4): E = 2 < world -> runs "global"
+        agent.recurrent_sharding = sharding
         torch.manual_seed(7)
         ranks.append(dict(pol=pol, st=st, agent=agent, rng=torch.get_rng_state(),
                           gen=agent.sharded_recurrent_steps(pol.runtime(), st)))
@@ -494,6 +502,58 @@ def test_sharded_recurrent_ppo_vs_reference_golden(name, world, gemm_engine):
             assert torch.equal(p, p0[k]), k
     rl2 = helpers.rel_l2(case, "finaldense_", p0)
     assert rl2 <= 1e-4, rl2
+
+
+@pytest.mark.parametrize("world,N,nmb", [(2, 8, 2), (4, 16, 2)])
+def test_sharded_balanced_equals_global_on_a_ring_rollout(world, N, nmb, gemm_engine):
+    """Frame-ring rollouts under the balanced scheme: the migrated columns are ring frames + stack counters.  The same
+    minibatch composition as the default scheme, other ranks doing the work: losses and parameters must agree to
+    summation-order noise."""
+    if gemm_engine != "tcgen05":
+        pytest.skip("the frame ring is read by the TMA-fed engine")
+    T, C, per = 6, 4, N // world
+    g = torch.Generator().manual_seed(13)
+    frames = torch.randint(0, 256, (T + C, N, 84, 84), generator=g, dtype=torch.uint8)
+    masks = (torch.rand(T + 1, N, 1, generator=g) > 0.2).float()
+    valid = torch.zeros(T + 1, N, dtype=torch.uint8)
+    valid[0] = C
+    for t in range(T):
+        valid[t + 1] = torch.where(masks[t + 1, :, 0] == 0, torch.ones(N, dtype=torch.int64),
+                                   torch.clamp(valid[t].long() + 1, max=C)).to(torch.uint8)
+    narrow = dict(rewards=torch.randn(T, N, 1, generator=g), value_preds=torch.randn(T + 1, N, 1, generator=g),
+                  action_log_probs=-torch.rand(T, N, 1, generator=g) - 1.0,
+                  actions=torch.randint(0, 6, (T, N, 1), generator=g), masks=masks, bad_masks=torch.ones(T + 1, N, 1),
+                  recurrent_hidden_states=torch.randn(T + 1, N, 512, generator=g) * 0.1)
+    nv = torch.randn(N, 1, generator=g)
+    out = {}
+    for sharding in ("global", "balanced"):
+        ranks = []
+        for r in range(world):
+            lo, hi = r * per, (r + 1) * per
+            torch.manual_seed(1)
+            pol = Policy((C, 84, 84), Discrete(6), base_kwargs={"recurrent": True}).to(DEV)
+            st = RolloutStorage(T, per, (C, 84, 84), Discrete(6), 512, obs_dtype=torch.uint8, frame_ring=True)
+            for k, v in narrow.items():
+                getattr(st, k).copy_(v[:, lo:hi])
+            st.frames.copy_(frames[:, lo:hi])
+            st.stack_valid.copy_(valid[:, lo:hi])
+            st.to(DEV)
+            st.compute_returns(nv[lo:hi].to(DEV), True, 0.99, 0.95, False)
+            agent = algo.PPO(pol, 0.1, 3, nmb, 0.5, 0.01, lr=2.5e-4, eps=1e-5, max_grad_norm=0.5)
+            agent.set_distributed(world, r, (lo, hi), N)
+            agent.recurrent_sharding = sharding
+            torch.manual_seed(7)
+            ranks.append(dict(pol=pol, st=st, agent=agent, rng=torch.get_rng_state(),
+                              gen=agent.sharded_recurrent_steps(pol.runtime(), st)))
+        res = _lockstep(ranks)
+        out[sharding] = (res[0], {k: p.detach().clone() for k, p in ranks[0]["pol"].named_parameters()})
+        for r in ranks[1:]:
+            for k, p in r["pol"].named_parameters():
+                assert torch.equal(p, out[sharding][1][k]), k
+    np.testing.assert_allclose(np.array(out["balanced"][0]), np.array(out["global"][0]), rtol=1e-5, atol=2e-6)
+    for k, p in out["global"][1].items():
+        d = (out["balanced"][1][k] - p).double().norm() / p.double().norm().clamp_min(1e-30)
+        assert d <= 2e-5, (k, d.item())
 
 
 def test_sharded_recurrent_ppo_equals_single_device(gemm_engine, monkeypatch):
