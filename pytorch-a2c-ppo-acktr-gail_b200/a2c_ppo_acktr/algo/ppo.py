@@ -517,17 +517,37 @@ class PPO():
         mine = plans[sh.rank]
         moments = _adv_moments(rt, rollouts)
         yield moments
-        _wait_staged(rollouts)                                  # migration reads the frames: the upload has to be complete
         shadow = self._shadow_rollout(rt, rollouts, max(p["n_guests"] for p in plans))
         Nv = shadow.rewards.shape[1]
         dev = rt.dev
-        # ---- own columns, then the guests ----
+        cur = torch.cuda.current_stream(dev)
         src_f, dst_f = self._migration_fields(rollouts), self._migration_fields(shadow)
-        for (a, rows), (b, _) in zip(src_f, dst_f):
+        # ---- frames staged on the host (`stage_host`): uploaded in the order they are needed -- the environments that
+        #      migrate first, then the first epoch's minibatches -- and copied into the shadow rollout chunk by chunk, so
+        #      that only the first ~40 columns are waited for before the exchange; the rest overlaps the compute ----
+        sent = np.unique(np.concatenate(mine["send"] + [np.zeros(0, np.int64)]))
+        first_cols = [x[x < n_loc] for x in mine["envs"][0]]
+        events = None
+        if getattr(rollouts, "_staged_obs", None) is not None:
+            events = rollouts._upload_staged([torch.from_numpy(sent)] +
+                                             [torch.from_numpy(np.setdiff1d(c, sent)) for c in first_cols])
+        big_src, big_dst = src_f[0][0], dst_f[0][0]              # frames (ring) / obs: everything else is narrow
+
+        def frames_to_shadow(cols, event):
+            if event is not None:
+                cur.wait_event(event)
+            if len(cols):
+                c = torch.from_numpy(np.ascontiguousarray(cols)).to(dev)
+                big_dst.index_copy_(1, c, big_src.index_select(1, c))
+        for (a, rows), (b, _) in zip(src_f[1:], dst_f[1:]):
             if rows is None:
                 b[:, :n_loc].copy_(a)
             else:
                 b[:rows, :n_loc].copy_(a[:rows])
+        if events is None:
+            big_dst[:, :n_loc].copy_(big_src)
+        else:
+            frames_to_shadow(sent, events[0])
         # Every shape below is the CAPACITY of the shadow rollout, not this update's count: the gather / scatter
         # temporaries and the message buffers then have the same sizes in every update (no allocator growth, no new
         # NCCL message sizes in the middle of a run); unused rows point at a dummy guest column (the last one).
@@ -585,6 +605,11 @@ class PPO():
             for k in range(nmb):
                 env = envs[epoch][k]
                 rows = (t_off + env.view(1, E)).reshape(-1).contiguous()
+                if epoch == 0 and events is not None:
+                    frames_to_shadow(np.setdiff1d(first_cols[k], sent), events[1 + k])
+                    if k == nmb - 1:                            # columns outside the first epoch's minibatches: none are
+                        for ev in events[1 + nmb:]:             # left by construction, the events only close the upload
+                            cur.wait_event(ev)
                 if epoch == 0 and chunked:
                     prog.prologue_chunk.run(rows)
                 hxs_mb = rt.arena.bufs["hxs_mb"][:E * H].view(E, H)

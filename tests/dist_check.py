@@ -47,6 +47,10 @@ def main():
                 "bad_masks"):
         getattr(st, nme).copy_(ro[nme][:, lo:hi])
     st.to(dev)
+    if os.environ.get("A2CB_DIST_STAGED", "0") == "1":          # frames ingested from pinned host memory (bench.py's e2e arm)
+        host = st.obs.detach().cpu().clone().pin_memory()
+        st.obs.fill_(3)
+        st.stage_host({"obs": host})
     st.compute_returns(ro["next_value"][lo:hi].to(dev), cfg["use_gae"], cfg["gamma"], cfg["gae_lambda"],
                        cfg["use_proper_time_limits"], schedule=1)
     if cfg["algo"] == "acktr":

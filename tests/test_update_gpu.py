@@ -504,11 +504,13 @@ def test_sharded_recurrent_ppo_vs_reference_golden(name, world, sharding, gemm_e
     assert rl2 <= 1e-4, rl2
 
 
-@pytest.mark.parametrize("world,N,nmb", [(2, 8, 2), (4, 16, 2)])
-def test_sharded_balanced_equals_global_on_a_ring_rollout(world, N, nmb, gemm_engine):
+@pytest.mark.parametrize("world,N,nmb,staged", [(2, 8, 2, False), (4, 16, 2, False), (2, 8, 2, True), (4, 16, 4, True)])
+def test_sharded_balanced_equals_global_on_a_ring_rollout(world, N, nmb, staged, gemm_engine):
     """Frame-ring rollouts under the balanced scheme: the migrated columns are ring frames + stack counters.  The same
     minibatch composition as the default scheme, other ranks doing the work: losses and parameters must agree to
-    summation-order noise."""
+    summation-order noise.  `staged`: the balanced ranks ingest their frames through `stage_host` (the end-to-end arm of
+    bench.py at N > 1): the upload is ordered migrating environments first, then minibatch by minibatch, and the shadow
+    rollout is filled chunk by chunk behind it."""
     if gemm_engine != "tcgen05":
         pytest.skip("the frame ring is read by the TMA-fed engine")
     T, C, per = 6, 4, N // world
@@ -538,6 +540,9 @@ def test_sharded_balanced_equals_global_on_a_ring_rollout(world, N, nmb, gemm_en
             st.frames.copy_(frames[:, lo:hi])
             st.stack_valid.copy_(valid[:, lo:hi])
             st.to(DEV)
+            if staged and sharding == "balanced":
+                st.frames.fill_(3)
+                st.stage_host({"frames": frames[:, lo:hi].contiguous().pin_memory()})
             st.compute_returns(nv[lo:hi].to(DEV), True, 0.99, 0.95, False)
             agent = algo.PPO(pol, 0.1, 3, nmb, 0.5, 0.01, lr=2.5e-4, eps=1e-5, max_grad_norm=0.5)
             agent.set_distributed(world, r, (lo, hi), N)

@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 for c in C3 C5s C5m; do
   A2CB_DIST_CASE=$c timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py > gpurun_out/r02z_dist_check_$c.log 2>&1; echo "dist_check $c rc=$?"; tail -1 gpurun_out/r02z_dist_check_$c.log
 done
+A2CB_DIST_STAGED=1 A2CB_DIST_CASE=C5m timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py > gpurun_out/r02z_dist_check_C5m_staged.log 2>&1; echo "dist_check C5m staged rc=$?"; tail -1 gpurun_out/r02z_dist_check_C5m_staged.log
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02z_bench_C5_n2.json 2> gpurun_out/r02z_bench_C5_n2.err; echo "C5 n2 rc=$?"
 python - <<'PY'
 import json
