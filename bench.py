@@ -356,6 +356,9 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: %s" % (cfg["name"], describe(cfg)), "envs_per_gpu": Nloc, "num_steps": T,
                        "recurrent_sharding": (getattr(agent, "recurrent_sharding", None) if (world > 1 and cfg.get("recurrent")) else None),
+                       "exchange": (None if world == 1 else
+                                    "peer-memory all-reduce over NVLink mappings (csrc/p2p.cu)" if getattr(getattr(agent, "_comm", None), "p2p", None) is not None
+                                    else "ncclAllReduce on a side stream" if getattr(agent, "_comm", None) is not None else "torch.distributed"),
                        "obs": ("uint8 frame ring (each 84x84 frame stored once, 4-stacks assembled on the device)" if ring
                                else "uint8 4x84x84 stacks" if obs_dtype == torch.uint8 else "fp32"), "l2": "flushed between steps (256 MiB write)",
                        "step": "compute_returns + update + after_update"},

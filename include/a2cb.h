@@ -541,6 +541,28 @@ int a2cb_comm_ctx_destroy(a2cb_comm_ctx_t ctx);
 int a2cb_comm_fork_allreduce(a2cb_comm_ctx_t ctx, float* buf, int64_t count, a2cb_stream_t stream);
 int a2cb_comm_join(a2cb_comm_ctx_t ctx, a2cb_stream_t stream);
 
+/* Peer-memory all-reduce (csrc/p2p.cu): the same sum over NVLink peer mappings instead of NCCL.  The update's kernels
+ * are persistent and own (nearly) all of every SM's shared memory, so an NCCL kernel on the side stream cannot become
+ * resident next to them and serialises with them; this exchange is three short copy / sum kernels without shared memory
+ * (scatter slices into the owners' inboxes, sum in rank order and broadcast, copy back) whose two cross-GPU hand-shakes
+ * are stream memory operations (no SM held while a rank waits).  One rank sums each element: results are bit-identical
+ * on every rank.  a2cb_p2p_create allocates [inbox | result | counters] on the current device for segments of up to
+ * capacity_floats; the 64-byte CUDA IPC handles are passed around by the host side (world * 64 bytes, in rank order) and
+ * mapped by a2cb_p2p_open_ipc -- or the caller hands over its own mappings (a2cb_p2p_set_peers: one base pointer per
+ * rank, from a2cb_p2p_local_base; same-process tests, symmetric-memory allocators).  Every rank must issue the same
+ * sequence of a2cb_p2p_allreduce_sum_f32 calls (buf 16-byte aligned, in place).  a2cb_comm_ctx_set_p2p makes
+ * A2CB_OP_COMM_FORK use it for every segment that fits (larger ones still go through NCCL). */
+typedef void* a2cb_p2p_t;
+int a2cb_p2p_create(a2cb_p2p_t* p2p, int32_t world, int32_t rank, int64_t capacity_floats);
+int a2cb_p2p_ipc_handle(a2cb_p2p_t p2p, void* out64);
+int a2cb_p2p_open_ipc(a2cb_p2p_t p2p, const void* handles);
+int a2cb_p2p_set_peers(a2cb_p2p_t p2p, void* const* bases);
+int a2cb_p2p_local_base(a2cb_p2p_t p2p, void** base);
+int64_t a2cb_p2p_capacity(a2cb_p2p_t p2p);
+int a2cb_p2p_allreduce_sum_f32(a2cb_p2p_t p2p, float* buf, int64_t count, a2cb_stream_t stream);
+int a2cb_p2p_destroy(a2cb_p2p_t p2p);
+int a2cb_comm_ctx_set_p2p(a2cb_comm_ctx_t ctx, a2cb_p2p_t p2p);
+
 /* ---------------------------------------------------------------------------
  * GAIL discriminator                      a2c_ppo_acktr/algo/gail.py:11-110, main.py:141-155
  * trunk = Linear(D, H) - Tanh - Linear(H, H) - Tanh - Linear(H, 1), D = Ds + Da <= 128, H <= 128, flat parameters

@@ -37,6 +37,15 @@ _native.register({
     "a2cb_comm_ctx_destroy": (c_i32, [c_vp]),
     "a2cb_comm_fork_allreduce": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "a2cb_comm_join": (c_i32, [c_vp, c_vp]),
+    "a2cb_comm_ctx_set_p2p": (c_i32, [c_vp, c_vp]),
+    "a2cb_p2p_create": (c_i32, [ctypes.POINTER(c_vp), c_i32, c_i32, c_i64]),
+    "a2cb_p2p_ipc_handle": (c_i32, [c_vp, c_vp]),
+    "a2cb_p2p_open_ipc": (c_i32, [c_vp, c_vp]),
+    "a2cb_p2p_set_peers": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),
+    "a2cb_p2p_local_base": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),
+    "a2cb_p2p_capacity": (c_i64, [c_vp]),
+    "a2cb_p2p_allreduce_sum_f32": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    "a2cb_p2p_destroy": (c_i32, [c_vp]),
 })
 
 
@@ -188,6 +197,64 @@ def round_up_envs(count, gran):
     return max(gran, (int(count) + gran - 1) // gran * gran)
 
 
+class PeerExchange(object):
+    """The peer-memory all-reduce of csrc/p2p.cu (a2cb_p2p_*): one exchange buffer per rank, mapped into the peers.
+    `connect_ipc()` passes the CUDA IPC handles around through the default torch.distributed group (ranks = processes on
+    one NVLink / NVSwitch node); `connect_local(group)` wires several instances living in ONE process (tests)."""
+
+    def __init__(self, device, world, rank, capacity_floats):
+        self.device = torch.device(device)
+        self.world, self.rank = int(world), int(rank)
+        h = c_vp()
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().a2cb_p2p_create(ctypes.byref(h), self.world, self.rank, int(capacity_floats)),
+                          "a2cb_p2p_create")
+        self.handle = h
+        self.capacity = int(_native.lib().a2cb_p2p_capacity(h))
+
+    def connect_ipc(self):
+        import torch.distributed as dist
+        lib = _native.lib()
+        mine = torch.zeros(64, dtype=torch.uint8)
+        _native.check(lib.a2cb_p2p_ipc_handle(self.handle, c_vp(mine.data_ptr())), "a2cb_p2p_ipc_handle")
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, bytes(mine.numpy().tobytes()))
+        blob = torch.frombuffer(bytearray(b"".join(everyone)), dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            rc = lib.a2cb_p2p_open_ipc(self.handle, c_vp(blob.data_ptr()))
+        # all ranks or none: a rank that cannot map its peers must not leave the others waiting for its arrivals
+        ok = torch.tensor([1 if rc == 0 else 0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            raise _native.NativeError("a2cb_p2p_open_ipc: %s" % (_native.lib().a2cb_last_error().decode() if rc != 0 else "a peer could not map the buffers"))
+        return self
+
+    @staticmethod
+    def connect_local(group):
+        lib = _native.lib()
+        bases = (c_vp * len(group))()
+        for i, g in enumerate(group):
+            b = c_vp()
+            _native.check(lib.a2cb_p2p_local_base(g.handle, ctypes.byref(b)), "a2cb_p2p_local_base")
+            bases[i] = b.value
+        for g in group:
+            _native.check(lib.a2cb_p2p_set_peers(g.handle, bases), "a2cb_p2p_set_peers")
+
+    def all_reduce_sum(self, t, stream=None):
+        """In-place fp32 sum of a flat, 16-byte aligned tensor on `stream` (default: the current stream)."""
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+        sp = _native.stream_ptr(self.device) if stream is None else c_vp(stream.cuda_stream)
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().a2cb_p2p_allreduce_sum_f32(self.handle, t.data_ptr(), t.numel(), sp),
+                          "a2cb_p2p_allreduce_sum_f32")
+        return t
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _native.lib().a2cb_p2p_destroy(self.handle)
+            self.handle = None
+
+
 class NativeComm(object):
     """An NCCL communicator owned by liba2cb (a2cb_nccl_* / a2cb_comm_* in include/a2cb.h) next to the default
     torch.distributed group: the 128-byte unique id is made on rank 0 and broadcast through the existing group, every
@@ -232,6 +299,29 @@ class NativeComm(object):
                                                                     _native.stream_ptr(self.device)), "a2cb_nccl_allreduce_sum_f32")
         return t
 
+    def enable_peer_exchange(self, capacity_floats):
+        """Routes the forked segments through the peer-memory all-reduce (csrc/p2p.cu) instead of ncclAllReduce.
+        Collective: every rank calls it at the same point (it is called while the op lists are built).  Falls back to
+        NCCL -- on every rank -- when the buffers cannot be mapped; `A2CB_EXCHANGE=nccl` keeps NCCL."""
+        import os
+        import warnings
+        if getattr(self, "p2p", None) is not None and self.p2p.capacity >= capacity_floats:
+            return True
+        if os.environ.get("A2CB_EXCHANGE", "p2p") == "nccl" or getattr(self, "_p2p_failed", False):
+            return False
+        try:
+            p2p = PeerExchange(self.device, self.world, self.rank, capacity_floats).connect_ipc()
+        except Exception as e:
+            self._p2p_failed = True
+            warnings.warn("peer-memory gradient exchange unavailable (%s): using ncclAllReduce" % e)
+            return False
+        old, self.p2p = getattr(self, "p2p", None), p2p
+        _native.check(_native.lib().a2cb_comm_ctx_set_p2p(self.ctx, p2p.handle), "a2cb_comm_ctx_set_p2p")
+        if old is not None:
+            torch.cuda.synchronize(self.device)
+            old.close()
+        return True
+
     def fork_op(self, tensor, lo, hi):
         """Descriptor of an OP_COMM_FORK on tensor[lo:hi] (fp32, flat)."""
         d = CommOpDesc()
@@ -248,6 +338,9 @@ class NativeComm(object):
         if getattr(self, "ctx", None):
             lib.a2cb_comm_ctx_destroy(self.ctx)
             self.ctx = None
+        if getattr(self, "p2p", None) is not None:
+            self.p2p.close()
+            self.p2p = None
         if getattr(self, "comm", None):
             lib.a2cb_nccl_comm_destroy(self.comm)
             self.comm = None

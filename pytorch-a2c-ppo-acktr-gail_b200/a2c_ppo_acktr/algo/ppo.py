@@ -123,6 +123,8 @@ class PPO():
         OP_COMM_JOIN, then grad-norm clip + Adam."""
         from .. import _engine
         G = rt.arena.bufs["G"]
+        if hasattr(comm, "enable_peer_exchange"):
+            comm.enable_peer_exchange(rt.L.total)                  # NVLink peer mappings instead of ncclAllReduce (csrc/p2p.cu)
         for lo, hi, before in _dist.gradient_buckets(rt.L):
             at = prog.index_of(before) if before is not None else None
             if at is None:

@@ -199,6 +199,19 @@ int a2cb_comm_fork_allreduce(a2cb_comm_ctx_t ctx, float* buf, int64_t count, a2c
     return comm_fork_allreduce(ctx, buf, (long)count, (cudaStream_t)stream);
 }
 int a2cb_comm_join(a2cb_comm_ctx_t ctx, a2cb_stream_t stream) { return comm_join(ctx, (cudaStream_t)stream); }
+int a2cb_comm_ctx_set_p2p(a2cb_comm_ctx_t ctx, a2cb_p2p_t p2p) { return comm_ctx_set_p2p(ctx, p2p); }
+int a2cb_p2p_create(a2cb_p2p_t* p2p, int32_t world, int32_t rank, int64_t capacity_floats) {
+    return p2p_create(p2p, world, rank, (long)capacity_floats);
+}
+int a2cb_p2p_ipc_handle(a2cb_p2p_t p2p, void* out64) { return p2p_ipc_handle(p2p, out64); }
+int a2cb_p2p_open_ipc(a2cb_p2p_t p2p, const void* handles) { return p2p_open_ipc(p2p, handles); }
+int a2cb_p2p_set_peers(a2cb_p2p_t p2p, void* const* bases) { return p2p_set_peers(p2p, bases); }
+int a2cb_p2p_local_base(a2cb_p2p_t p2p, void** base) { return p2p_local_base(p2p, base); }
+int64_t a2cb_p2p_capacity(a2cb_p2p_t p2p) { return (int64_t)p2p_capacity(p2p); }
+int a2cb_p2p_allreduce_sum_f32(a2cb_p2p_t p2p, float* buf, int64_t count, a2cb_stream_t stream) {
+    return p2p_allreduce_sum_f32(p2p, buf, (long)count, (cudaStream_t)stream);
+}
+int a2cb_p2p_destroy(a2cb_p2p_t p2p) { return p2p_destroy(p2p); }
 
 int a2cb_gail_disc(int32_t reward, const a2cb_gail_t* desc, a2cb_stream_t stream) {
     A2CB_REQUIRE(desc, "gail_disc: null descriptor");

@@ -68,6 +68,16 @@ int comm_ctx_create(void** ctx, void* comm);
 int comm_ctx_destroy(void* ctx);
 int comm_fork_allreduce(void* ctx, float* buf, long count, cudaStream_t st);
 int comm_join(void* ctx, cudaStream_t st);
+int comm_ctx_set_p2p(void* ctx, void* p2p);
+// p2p.cu
+int p2p_create(void** out, int world, int rank, long capacity_floats);
+int p2p_ipc_handle(void* ctx, void* out64);
+int p2p_open_ipc(void* ctx, const void* handles);
+int p2p_set_peers(void* ctx, void* const* bases);
+int p2p_local_base(void* ctx, void** base);
+long p2p_capacity(void* ctx);
+int p2p_allreduce_sum_f32(void* ctx, float* buf, long count, cudaStream_t st);
+int p2p_destroy(void* ctx);
 // gail.cu
 int gail_slab_floats(int D, int H);
 int gail_ctas(int B);

@@ -63,6 +63,7 @@ int nccl_fail(const char* what, int rc) {
 // exchange context: the communicator + a side stream + the events that order it against the launching stream
 struct CommCtx {
     void* comm;
+    void* p2p;                     // peer-memory exchange (p2p.cu): takes the forked segments it has room for
     cudaStream_t side;
     cudaEvent_t ready[8], done[8];
     int pending;                   // forks since the last join
@@ -117,6 +118,13 @@ int comm_ctx_create(void** ctx, void* comm) {
     return A2CB_OK;
 }
 
+int comm_ctx_set_p2p(void* ctx, void* p2p) {
+    CommCtx* c = (CommCtx*)ctx;
+    A2CB_REQUIRE(c, "comm_ctx_set_p2p: null context");
+    c->p2p = p2p;
+    return A2CB_OK;
+}
+
 int comm_ctx_destroy(void* ctx) {
     CommCtx* c = (CommCtx*)ctx;
     if (!c) return A2CB_OK;
@@ -134,7 +142,8 @@ int comm_fork_allreduce(void* ctx, float* buf, long count, cudaStream_t st) {
     cudaError_t e = cudaEventRecord(c->ready[i], st);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(c->side, c->ready[i], 0);
     if (e != cudaSuccess) { set_error("comm_fork_allreduce: %s", cudaGetErrorString(e)); return A2CB_ERR_CUDA; }
-    const int rc = nccl_allreduce_sum_f32(c->comm, buf, count, c->side);
+    const int rc = (c->p2p && count <= p2p_capacity(c->p2p)) ? p2p_allreduce_sum_f32(c->p2p, buf, count, c->side)
+                                                             : nccl_allreduce_sum_f32(c->comm, buf, count, c->side);
     if (rc != A2CB_OK) return rc;
     e = cudaEventRecord(c->done[i], c->side);
     if (e != cudaSuccess) { set_error("comm_fork_allreduce: %s", cudaGetErrorString(e)); return A2CB_ERR_CUDA; }

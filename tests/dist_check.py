@@ -76,7 +76,9 @@ def main():
     assert helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters())) <= (1e-4 if cfg["recurrent"] else 2e-3)
     dist.barrier()
     if rank == 0:
-        print("dist_check ok: case=%s world=%d losses=%s" % (name, world, losses))
+        comm = getattr(agent, "_comm", None)
+        how = "none" if comm is None else ("p2p" if getattr(comm, "p2p", None) is not None else "nccl")
+        print("dist_check ok: case=%s world=%d exchange=%s losses=%s" % (name, world, how, losses))
     dist.destroy_process_group()
 
 
