@@ -12,7 +12,10 @@
 //   gather    result -> buf                                       (local)
 //
 // and the two cross-GPU hand-shakes between them are STREAM memory operations (cuStreamWaitValue32 on a counter in local
-// memory that the last CTA of the peers' previous phase bumps with red.release.sys): a waiting rank occupies no SM at all.
+// memory that the last CTA of the peers' previous phase bumps with red.release.sys): a waiting rank occupies no SM at all
+// (A2CB_P2P_WAIT=spin: one polling warp instead).  Either way nothing may be launched for the FIRST time behind a pending
+// hand-shake -- lazy module loading synchronises the context (tools/stream_probe.cu) -- so the kernels are loaded when the
+// context is created.
 // Every element is summed once, by one rank, in rank order: results are bit-identical on all ranks and independent of the
 // grid.  The buffers ([inbox | result | counters], one cudaMalloc per rank) are mapped into the peers through CUDA IPC
 // handles that the host side passes around (a2cb_p2p_ipc_handle / a2cb_p2p_open_ipc), or handed over as plain pointers by
@@ -45,7 +48,7 @@ struct P2P {
     bool opened[kMaxWorld];
     bool connected;
     unsigned seq;                           // all-reduces issued so far (identical on every rank: same program order)
-    int wait_mode;                          // 0: stream memory operation, 1: one-CTA polling kernel
+    int wait_mode;                          // 0: stream memory operation (default), 1: one polling warp
 };
 
 typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) p2p_gather_kernel(Peers P, float* __
     }
 }
 
-// fallback hand-shake (A2CB_P2P_WAIT=spin, or no cuStreamWaitValue32): ONE resident CTA polls the local counter
+// the hand-shake without stream memory operations: ONE resident warp polls the local counter
 __global__ void p2p_wait_kernel(const unsigned* counter, unsigned target) {
     if (threadIdx.x == 0) {
         unsigned v;
@@ -190,6 +193,15 @@ int p2p_create(void** out, int world, int rank, long capacity_floats) {
     c->wait_mode = (w && !strcmp(w, "spin")) || !wait_value_fn() ? 1 : 0;
     c->peers.base[0] = c->local;
     c->peers.base[1 + rank] = c->local;
+    // CUDA loads kernels lazily, and a first launch may need a context-wide synchronisation: behind a pending hand-shake
+    // that would stall the launching thread until the peers arrive (and dead-lock emulated ranks sharing a process).  Load
+    // everything now: one empty launch of each kernel (world = 0: nobody is signalled).
+    p2p_scatter_kernel<<<1, kThreads>>>(c->peers, nullptr, 0, 4, 0, rank, c->cap);
+    p2p_reduce_kernel<<<1, kThreads>>>(c->peers, 0, 4, 0, rank, c->cap);
+    p2p_gather_kernel<<<1, kThreads>>>(c->peers, nullptr, 0, c->cap);
+    p2p_wait_kernel<<<1, 32>>>(reinterpret_cast<unsigned*>(c->local + (size_t)c->cap * 8), 0);
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("p2p_create: warm-up launches: %s", cudaGetErrorString(e)); cudaFree(c->local); free(c); return A2CB_ERR_CUDA; }
     *out = c;
     return A2CB_OK;
 }

@@ -1,6 +1,6 @@
 """Peer-memory all-reduce (csrc/p2p.cu, a2cb_p2p_*) on ONE GPU: `world` exchange contexts live in this process, wired
 to each other with a2cb_p2p_set_peers, every emulated rank on its own stream -- the hand-shakes (a counter bumped by the
-peers' last CTA, awaited by a stream memory operation) are the ones the real multi-process runs use.  The cross-process
+peers' last CTA, awaited by a stream memory operation or one polling warp) are the ones the real multi-process runs use.  The cross-process
 mapping (CUDA IPC) is covered by tests/dist_check.py under torchrun on 2+ GPUs."""
 import numpy as np
 import pytest
@@ -19,7 +19,7 @@ def _group(world, cap):
     return g
 
 
-@pytest.mark.timeout(180, method="thread")
+@pytest.mark.timeout(60, method="thread")
 @pytest.mark.parametrize("world,count,wait", [(2, 1 << 20, "memop"), (2, 1027, "memop"), (3, 77777, "memop"), (4, 4, "memop"),
                                               (8, 3, "memop"), (8, 866_310, "memop"), (2, 1 << 20, "spin"), (4, 77777, "spin")])
 def test_allreduce_matches_rank_ordered_sum(world, count, wait, monkeypatch):
@@ -46,7 +46,7 @@ def test_allreduce_matches_rank_ordered_sum(world, count, wait, monkeypatch):
         x.close()
 
 
-@pytest.mark.timeout(180, method="thread")
+@pytest.mark.timeout(60, method="thread")
 def test_untouched_tail_and_argument_checks():
     world, count = 2, 1001
     g = _group(world, count)
@@ -69,7 +69,7 @@ def test_untouched_tail_and_argument_checks():
         x.close()
 
 
-@pytest.mark.timeout(180, method="thread")
+@pytest.mark.timeout(60, method="thread")
 def test_overlaps_with_a_kernel_that_fills_the_gpu():
     """The exchange must make progress next to work that keeps every SM busy on another stream (its kernels use no
     shared memory, its waits no SM): here a long matmul chain on the default stream."""
