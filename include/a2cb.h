@@ -541,6 +541,21 @@ int a2cb_comm_ctx_destroy(a2cb_comm_ctx_t ctx);
 int a2cb_comm_fork_allreduce(a2cb_comm_ctx_t ctx, float* buf, int64_t count, a2cb_stream_t stream);
 int a2cb_comm_join(a2cb_comm_ctx_t ctx, a2cb_stream_t stream);
 
+/* Column copies between rollout-shaped tensors (csrc/colcopy.cu): dst[dst_col(j)][t] = src[src_col(j)][t] for j < n_cols,
+ * t < rows, every field with its own byte strides per column (cs) and per row (rs) and w bytes per element; dst_cols /
+ * src_cols are device arrays of n_cols indices or NULL (column j).  Used by the balanced sharded recurrent update to pack
+ * the rollout columns of migrating environments into records (storage.py:10-30 layout, time-major -> environment-major),
+ * to unpack received records into guest columns and to copy uploaded columns into the shadow rollout: one launch for all
+ * fields.  Elements of >= 256 bytes with 16-byte aligned pointers / strides move as 16-byte words. */
+typedef struct {
+    void* dst; const void* src;
+    int64_t dst_cs, dst_rs, src_cs, src_rs;
+    int64_t w;
+    int32_t rows; int32_t reserved_;
+} a2cb_colcopy_t;
+int a2cb_copy_columns(const a2cb_colcopy_t* fields, int32_t n_fields, const int64_t* dst_cols, const int64_t* src_cols,
+                      int32_t n_cols, a2cb_stream_t stream);
+
 /* Peer-memory all-reduce (csrc/p2p.cu): the same sum over NVLink peer mappings instead of NCCL.  The update's kernels
  * are persistent and own (nearly) all of every SM's shared memory, so an NCCL kernel on the side stream cannot become
  * resident next to them and serialises with them; this exchange is three short copy / sum kernels without shared memory

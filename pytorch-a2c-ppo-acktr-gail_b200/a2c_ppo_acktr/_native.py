@@ -27,8 +27,15 @@ class GatherField(ctypes.Structure):
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("row_bytes", c_i64)]
 
 
+class ColCopyField(ctypes.Structure):
+    """Mirror of a2cb_colcopy_t."""
+    _fields_ = [("dst", c_void_p), ("src", c_void_p), ("dst_cs", c_i64), ("dst_rs", c_i64), ("src_cs", c_i64),
+                ("src_rs", c_i64), ("w", c_i64), ("rows", c_int), ("reserved_", c_int)]
+
+
 _SIGNATURES = {
     "a2cb_abi_version": (c_int, []),
+    "a2cb_copy_columns": (c_int, [ctypes.POINTER(ColCopyField), c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "a2cb_last_error": (ctypes.c_char_p, []),
     "a2cb_launch_count": (c_i64, []),
     "a2cb_add_launches": (None, [c_i64]),
@@ -155,6 +162,36 @@ def gather_rows(pairs, idx, n_out_rows, mode=0, E=0, N=0):
         rc = lib().a2cb_gather_rows(arr, len(pairs), idx_p, int(n_out_rows),
                                     int(mode), int(E), int(N), stream_ptr(dev))
     check(rc, "a2cb_gather_rows")
+
+
+def copy_columns(pairs, dst_cols, src_cols, n_cols):
+    """dst[:, dst_cols[j]] = src[:, src_cols[j]] for j < n_cols, for every (dst, src) pair of [rows, columns, ...] device
+    tensors (same rows and trailing shape byte for byte; any strides over the first two dimensions, trailing dimensions
+    dense) in ONE launch on the current stream.  `dst_cols` / `src_cols`: device int64 tensors with at least n_cols
+    entries, or None for column j."""
+    if n_cols <= 0 or not pairs:
+        return
+    arr = (ColCopyField * len(pairs))()
+    dev = pairs[0][0].device
+    for f, (d, s) in zip(arr, pairs):
+        if not (d.is_cuda and s.is_cuda) or d.shape[0] != s.shape[0] or d.dim() < 2 or s.dim() < 2:
+            raise NativeError("copy_columns: pairs of CUDA tensors [rows, columns, ...] with the same number of rows")
+        wd = d[0, 0].numel() * d.element_size()
+        ws = s[0, 0].numel() * s.element_size()
+        if wd != ws or not d[0, 0].is_contiguous() or not s[0, 0].is_contiguous():
+            raise NativeError("copy_columns: elements must be dense and of the same size (%d vs %d bytes)" % (wd, ws))
+        f.dst, f.src = d.data_ptr(), s.data_ptr()
+        f.dst_rs, f.dst_cs = d.stride(0) * d.element_size(), d.stride(1) * d.element_size()
+        f.src_rs, f.src_cs = s.stride(0) * s.element_size(), s.stride(1) * s.element_size()
+        f.w, f.rows = wd, d.shape[0]
+    for c in (dst_cols, src_cols):
+        if c is not None and (c.dtype != torch.int64 or not c.is_cuda or not c.is_contiguous() or c.numel() < n_cols):
+            raise NativeError("copy_columns: column lists are contiguous int64 CUDA tensors with >= n_cols entries")
+    with torch.cuda.device(dev):
+        rc = lib().a2cb_copy_columns(arr, len(pairs), c_void_p(dst_cols.data_ptr()) if dst_cols is not None else None,
+                                     c_void_p(src_cols.data_ptr()) if src_cols is not None else None, int(n_cols),
+                                     stream_ptr(dev))
+    check(rc, "a2cb_copy_columns")
 
 
 def upload_env_columns(dst, src_host, envs, stream):

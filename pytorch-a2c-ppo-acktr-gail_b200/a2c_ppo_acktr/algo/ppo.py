@@ -43,6 +43,37 @@ def _adv_apply(rt, rollouts, moments):
     return adv
 
 
+class _Phases(object):
+    """A2CB_PHASE_TIMING=1: CUDA events and host clocks at named points of a sharded update; rank 0 prints, per phase, the
+    device time since the previous mark and how far ahead of the device the host was when it enqueued the mark
+    (negative lead = the device was waiting for the host)."""
+
+    def __init__(self, dev, rank):
+        import os
+        self.on = os.environ.get("A2CB_PHASE_TIMING") == "1" and rank == 0
+        self.dev, self.items = dev, []
+
+    def mark(self, name):
+        if self.on:
+            import time
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.dev))
+            self.items.append((name, ev, time.perf_counter()))
+
+    def report(self):
+        if not self.on or len(self.items) < 2:
+            return
+        import sys
+        torch.cuda.synchronize(self.dev)
+        n0, e0, h0 = self.items[0]
+        prev = e0
+        out = []
+        for name, ev, h in self.items[1:]:
+            out.append("%s %.3f (dev %.3f host %.3f)" % (name, prev.elapsed_time(ev), e0.elapsed_time(ev), (h - h0) * 1e3))
+            prev = ev
+        sys.stderr.write("phases [ms since previous mark (device clock, host clock since start)]: " + " | ".join(out) + "\n")
+
+
 def _wait_staged(rollouts):
     f = getattr(rollouts, "wait_staged", None)
     if f is not None:
@@ -306,7 +337,10 @@ class PPO():
             "to be greater than or equal to the number of "
             "PPO mini batches ({}).".format(N, self.num_mini_batch))
         E = N // self.num_mini_batch
+        ph = _Phases(rt.dev, 0)
+        ph.mark("start")
         adv = _adv_normalize(rt, rollouts)
+        ph.mark("adv")
         accum = rt.arena.ensure("loss_accum", 4)
         accum.zero_()
         prog, _ = self._program(rt, rollouts, T * E, adv, accum, seq=(T, E), chunked=True)
@@ -330,11 +364,14 @@ class PPO():
                 prog.run(rows)
                 if self.step_hook is not None:
                     self.step_hook(self.optimizer.step_count)
+                ph.mark("mb%d.%d" % (epoch, k))
             if epoch == 0:
                 finish()
         self.last_launches = _native.launch_count() - launches0
         num_updates = self.ppo_epoch * self.num_mini_batch
         sums = accum[:3].cpu()
+        ph.mark("losses")
+        ph.report()
         return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
 
     def _update_sharded(self, rt, rollouts):
@@ -514,23 +551,43 @@ class PPO():
         nmb = self.num_mini_batch
         E_g = sh.n_total // nmb
         E = E_g // sh.world
+        ph = _Phases(rt.dev, sh.rank)
+        ph.mark("start")
+        dev = rt.dev
+        cur = torch.cuda.current_stream(dev)
+        moments = _adv_moments(rt, rollouts)                    # (device work first: the host-side planning overlaps it)
+        staged = getattr(rollouts, "_staged_obs", None) is not None
+        src_f = self._migration_fields(rollouts)
+
+        def own_columns(shadow):
+            """The rank's own environments -> columns [0, n_loc) of the shadow rollout (frames staged on the host follow
+            their upload, chunk by chunk)."""
+            for (a, rows), (b, _) in zip(src_f[1 if staged else 0:], self._migration_fields(shadow)[1 if staged else 0:]):
+                if rows is None:
+                    b[:, :n_loc].copy_(a)
+                else:
+                    b[:rows, :n_loc].copy_(a[:rows])
+        early = getattr(self, "_shadow", None) if getattr(self, "_shadow_src", None) == (rollouts.rewards.data_ptr(), T, n_loc) else None
+        if early is not None:
+            own_columns(early)
         perms = [torch.randperm(sh.n_total).numpy() for _ in range(self.ppo_epoch)]
         plans = _dist.balance_update_plan(perms, E_g, nmb, sh.world, n_loc)
         mine = plans[sh.rank]
-        moments = _adv_moments(rt, rollouts)
+        ph.mark("plan")
         yield moments
+        ph.mark("moments")
         shadow = self._shadow_rollout(rt, rollouts, max(p["n_guests"] for p in plans))
+        if shadow is not early:
+            own_columns(shadow)
         Nv = shadow.rewards.shape[1]
-        dev = rt.dev
-        cur = torch.cuda.current_stream(dev)
-        src_f, dst_f = self._migration_fields(rollouts), self._migration_fields(shadow)
+        dst_f = self._migration_fields(shadow)
         # ---- frames staged on the host (`stage_host`): uploaded in the order they are needed -- the environments that
         #      migrate first, then the first epoch's minibatches -- and copied into the shadow rollout chunk by chunk, so
         #      that only the first ~40 columns are waited for before the exchange; the rest overlaps the compute ----
         sent = np.unique(np.concatenate(mine["send"] + [np.zeros(0, np.int64)]))
         first_cols = [x[x < n_loc] for x in mine["envs"][0]]
         events = None
-        if getattr(rollouts, "_staged_obs", None) is not None:
+        if staged:
             events = rollouts._upload_staged([torch.from_numpy(sent)] +
                                              [torch.from_numpy(np.setdiff1d(c, sent)) for c in first_cols])
         big_src, big_dst = src_f[0][0], dst_f[0][0]              # frames (ring) / obs: everything else is narrow
@@ -540,46 +597,46 @@ class PPO():
                 cur.wait_event(event)
             if len(cols):
                 c = torch.from_numpy(np.ascontiguousarray(cols)).to(dev)
-                big_dst.index_copy_(1, c, big_src.index_select(1, c))
-        for (a, rows), (b, _) in zip(src_f[1:], dst_f[1:]):
-            if rows is None:
-                b[:, :n_loc].copy_(a)
-            else:
-                b[:rows, :n_loc].copy_(a[:rows])
-        if events is None:
-            big_dst[:, :n_loc].copy_(big_src)
-        else:
+                _native.copy_columns([(big_dst, big_src)], c, c, len(cols))
+        if events is not None:
             frames_to_shadow(sent, events[0])
-        # Every shape below is the CAPACITY of the shadow rollout, not this update's count: the gather / scatter
-        # temporaries and the message buffers then have the same sizes in every update (no allocator growth, no new
-        # NCCL message sizes in the middle of a run); unused rows point at a dummy guest column (the last one).
+        # ---- migration: the travelling environments' columns packed into records (one record = every field of one
+        #      environment, environment-major), ONE all-to-all, records unpacked into the guest columns.  The record
+        #      buffers have the CAPACITY of the shadow rollout (no allocator growth, one registration), the kernels and
+        #      the messages carry this update's counts. ----
         cap = Nv - n_loc - 1
         n_send, n_recv = sum(len(x) for x in mine["send"]), sum(len(x) for x in mine["recv"])
         assert n_send <= cap and n_recv <= cap
-        send_np, recv_np = np.zeros(cap, np.int64), np.full(cap, cap, np.int64)
-        send_np[:n_send] = np.concatenate(mine["send"])
-        recv_np[:n_recv] = np.concatenate(mine["recv"])
-        send_cols, recv_cols = torch.from_numpy(send_np).to(dev), torch.from_numpy(recv_np).to(dev) + n_loc
-        widths = [(x if rows is None else x[:rows])[:, 0].numel() * x.element_size() for x, rows in src_f]
+        cols_np = np.zeros(2 * cap, np.int64)
+        cols_np[:n_send] = np.concatenate(mine["send"] + [np.zeros(0, np.int64)])
+        cols_np[cap:cap + n_recv] = np.concatenate(mine["recv"] + [np.zeros(0, np.int64)]) + n_loc
+        cols_dev = torch.from_numpy(cols_np).to(dev)
+        send_cols, recv_cols = cols_dev[:cap], cols_dev[cap:]
+        views = [(x if rows is None else x[:rows]) for x, rows in src_f]
+        widths = [(v[:, 0].numel() * v.element_size() + 15) // 16 * 16 for v in views]      # fields start 16-byte aligned
         rec_bytes = sum(widths)
         bufs = getattr(self, "_xchg_bufs", None)
         if bufs is None or bufs[0].shape != (cap, rec_bytes) or bufs[0].device != dev:
             bufs = self._xchg_bufs = (torch.zeros(cap, rec_bytes, dtype=torch.uint8, device=dev),
                                       torch.zeros(cap, rec_bytes, dtype=torch.uint8, device=dev))
         send, recv = bufs
-        off = 0
-        for (a, rows), w in zip(src_f, widths):
-            x = a if rows is None else a[:rows]
-            send[:, off:off + w].copy_(x.index_select(1, send_cols).transpose(0, 1).reshape(cap, -1).contiguous().view(torch.uint8))
-            off += w
+
+        def record_views(buf, like):
+            """The fields of `like` (tensors [rows, columns, ...]) as [rows, record, bytes] views of the record buffer."""
+            out, off = [], 0
+            for v, w in zip(like, widths):
+                rows, wb = v.shape[0], v[0, 0].numel() * v.element_size()
+                out.append(buf[:, off:off + rows * wb].view(cap, rows, wb).transpose(0, 1))
+                off += w
+            return out
+        _native.copy_columns(list(zip(record_views(send, views), views)), None, send_cols, n_send)
+        ph.mark("shadow+pack")
         yield _dist.Exchange(send[:n_send], [len(x) for x in mine["send"]], recv[:n_recv], [len(x) for x in mine["recv"]])
-        off = 0
-        for (b, rows), w in zip(dst_f, widths):
-            x = b if rows is None else b[:rows]
-            piece = recv[:, off:off + w].reshape(-1).clone().view(cap, w).view(x.dtype).view((cap, x.shape[0]) + tuple(x.shape[2:]))
-            x.index_copy_(1, recv_cols, piece.transpose(0, 1))
-            off += w
+        ph.mark("exchange")
+        dviews = [(x if rows is None else x[:rows]) for x, rows in dst_f]
+        _native.copy_columns(list(zip(dviews, record_views(recv, dviews))), recv_cols, None, n_recv)
         adv = _adv_apply(rt, shadow, moments)
+        ph.mark("unpack+adv")
         accum = rt.arena.ensure("loss_accum", 4)
         accum.zero_()
         inv_B = 1.0 / (T * E_g)
@@ -595,14 +652,21 @@ class PPO():
         envs = [[torch.from_numpy(x).to(dev) for x in ep] for ep in mine["envs"]]
         if chunked and self.ppo_epoch > 1:
             # columns first used after the first epoch (own environments that the first epoch sent away, guests of later
-            # epochs): their frames are re-laid out now, E columns at a time (the re-layout program has that size)
+            # epochs): their frames are re-laid out now, at most E columns per launch (the size the re-layout op was
+            # built for; its image count is a field of the descriptor)
             first = np.unique(np.concatenate(mine["envs"][0]))
             later = np.setdiff1d(np.unique(np.concatenate([x for ep in mine["envs"][1:] for x in ep])), first)
+            s2d = prog.prologue_chunk.entries[0][2]
+            full = s2d.B
+            assert len(prog.prologue_chunk.entries) == 1 and full == T * E
             for i in range(0, len(later), E):
-                part = later[i:i + E]
-                part = np.concatenate([part, np.full(E - len(part), part[0], np.int64)])
-                env = torch.from_numpy(part).to(dev)
-                prog.prologue_chunk.run((t_off + env.view(1, E)).reshape(-1).contiguous())
+                env = torch.from_numpy(later[i:i + E]).to(dev)
+                s2d.B = T * env.numel()
+                try:
+                    prog.prologue_chunk.run((t_off + env.view(1, -1)).reshape(-1).contiguous())
+                finally:
+                    s2d.B = full
+        ph.mark("relayout-later")
         for epoch in range(self.ppo_epoch):
             for k in range(nmb):
                 env = envs[epoch][k]
@@ -627,10 +691,13 @@ class PPO():
                     opt.run()
                 if self.step_hook is not None:
                     self.step_hook(self.optimizer.step_count)
+                ph.mark("mb%d.%d" % (epoch, k))
         self.last_launches = _native.launch_count() - launches0
         yield accum
         num_updates = self.ppo_epoch * self.num_mini_batch
         sums = accum[:3].cpu()
+        ph.mark("losses")
+        ph.report()
         return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)
 
     def _sharded_recurrent_stratified(self, rt, rollouts):
@@ -644,9 +711,12 @@ class PPO():
         assert n_loc == sh.n_local and n_loc >= self.num_mini_batch
         E = n_loc // self.num_mini_batch
         E_global = E * sh.world
+        ph = _Phases(rt.dev, sh.rank)
+        ph.mark("start")
         moments = _adv_moments(rt, rollouts)
         yield moments
         adv = _adv_apply(rt, rollouts, moments)
+        ph.mark("moments+adv")
         accum = rt.arena.ensure("loss_accum", 4)
         accum.zero_()
         prog, opt = self._program(rt, rollouts, T * E, adv, accum, inv_B=1.0 / (T * E_global), seq=(T, E), chunked=True)
@@ -675,10 +745,13 @@ class PPO():
                     opt.run()
                 if self.step_hook is not None:
                     self.step_hook(self.optimizer.step_count)
+                ph.mark("mb%d.%d" % (epoch, k))
             if epoch == 0:
                 finish()
         self.last_launches = _native.launch_count() - launches0
         yield accum
+        ph.mark("accum")
+        ph.report()
         num_updates = self.ppo_epoch * self.num_mini_batch
         sums = accum[:3].cpu()
         return (sums[0].item() / num_updates, sums[1].item() / num_updates, sums[2].item() / num_updates)

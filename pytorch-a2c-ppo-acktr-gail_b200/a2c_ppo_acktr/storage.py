@@ -136,6 +136,8 @@ class RolloutStorage(object):
         self._idx_cache = None
         self._staged_obs = None          # pinned host frames whose upload has not been started yet
         self._copy_stream = None
+        self._staged_tail = None         # (device, pinned host) tensors whose rows [1:] follow the frames on the copy stream
+        self._tail_event = None
 
     # -- frame ring --------------------------------------------------------
     def __getattr__(self, name):
@@ -176,7 +178,8 @@ class RolloutStorage(object):
     # -- host ingest (extension; the device-side half of envs.py:167-190 `VecPyTorch`) ------------
     def stage_host(self, host):
         """`host`: dict attribute name -> PINNED host tensor of the attribute's shape and dtype (any subset of the
-        buffer's tensors).  Everything except `obs` is copied now, asynchronously on the current stream.  The frames
+        buffer's tensors).  Everything except `obs` is copied now, asynchronously on the current stream (of a wide
+        `recurrent_hidden_states` only row 0, the one an update reads; rows [1:] follow the frames).  The frames
         are only registered: the next `update()` (or `wait_staged()`, which every other reader of `obs` in this
         package calls) uploads them on a side stream.  The host tensors must stay untouched until then."""
         dev = self.rewards.device
@@ -192,6 +195,12 @@ class RolloutStorage(object):
                 if not src.is_pinned() or not src.is_contiguous():
                     raise _native.NativeError("stage_host: %s must be a contiguous pinned host tensor" % name)
                 self._staged_obs = src
+            elif (name == "recurrent_hidden_states" and src.is_pinned() and dst.shape[0] > 1
+                  and dst[1:].numel() * dst.element_size() >= (1 << 20)):
+                # an update reads only the initial state (reference storage.py:160-161); the other T rows (tens of MB for
+                # a GRU) follow the frames on the copy stream instead of holding up the launching stream
+                dst[0].copy_(src[0], non_blocking=True)
+                self._staged_tail = (dst, src)
             else:
                 dst.copy_(src, non_blocking=True)
 
@@ -199,7 +208,8 @@ class RolloutStorage(object):
         """Starts the upload of the registered frames on the copy stream, one strided copy set per chunk of
         environments (default: everything at once).  Returns one event per chunk, or None if nothing is staged."""
         host, self._staged_obs = self._staged_obs, None
-        if host is None:
+        tail, self._staged_tail = self._staged_tail, None
+        if host is None and tail is None:
             return None
         frames = self.frames if self.frame_ring else self.obs
         dev = frames.device
@@ -207,6 +217,9 @@ class RolloutStorage(object):
             self._copy_stream = torch.cuda.Stream(dev)
         cs = self._copy_stream
         cs.wait_stream(torch.cuda.current_stream(dev))      # earlier readers / writers of obs are done
+        if host is None:
+            self._upload_tail(tail, cs)
+            return None
         N = frames.shape[1]
         if env_chunks is None:
             env_chunks = [torch.arange(N)]
@@ -225,7 +238,23 @@ class RolloutStorage(object):
             ev.record(cs)
             events.append(ev)
         self._staged_keepalive = host                       # until the next stage / upload replaces it
+        self._upload_tail(tail, cs)
         return events
+
+    def _upload_tail(self, tail, cs):
+        if tail is None:
+            return
+        dst, src = tail
+        with torch.cuda.stream(cs):
+            dst[1:].copy_(src[1:], non_blocking=True)
+        self._tail_event = torch.cuda.Event()
+        self._tail_event.record(cs)
+        self._tail_keepalive = src
+
+    def _wait_tail(self):
+        ev, self._tail_event = self._tail_event, None
+        if ev is not None:
+            torch.cuda.current_stream(self.rewards.device).wait_event(ev)
 
     def wait_staged(self):
         """Makes the current stream wait for the staged frames (no-op when nothing is staged)."""
@@ -234,6 +263,7 @@ class RolloutStorage(object):
             cur = torch.cuda.current_stream(self.rewards.device)
             for ev in events:
                 cur.wait_event(ev)
+        self._wait_tail()
 
     # -- actor-side writes (reference storage.py:46-64) --------------------------
     def insert(self, obs, recurrent_hidden_states, actions, action_log_probs,

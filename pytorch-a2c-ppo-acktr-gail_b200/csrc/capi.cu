@@ -212,6 +212,12 @@ int a2cb_p2p_allreduce_sum_f32(a2cb_p2p_t p2p, float* buf, int64_t count, a2cb_s
     return p2p_allreduce_sum_f32(p2p, buf, (long)count, (cudaStream_t)stream);
 }
 int a2cb_p2p_destroy(a2cb_p2p_t p2p) { return p2p_destroy(p2p); }
+int a2cb_copy_columns(const a2cb_colcopy_t* fields, int32_t n_fields, const int64_t* dst_cols, const int64_t* src_cols,
+                      int32_t n_cols, a2cb_stream_t stream) {
+    static_assert(sizeof(a2cb_colcopy_t) == sizeof(ColCopyField), "a2cb_colcopy_t mirrors ColCopyField");
+    return copy_columns(reinterpret_cast<const ColCopyField*>(fields), n_fields, reinterpret_cast<const long*>(dst_cols),
+                        reinterpret_cast<const long*>(src_cols), n_cols, (cudaStream_t)stream);
+}
 
 int a2cb_gail_disc(int32_t reward, const a2cb_gail_t* desc, a2cb_stream_t stream) {
     A2CB_REQUIRE(desc, "gail_disc: null descriptor");

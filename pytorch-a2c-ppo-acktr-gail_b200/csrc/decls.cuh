@@ -69,6 +69,16 @@ int comm_ctx_destroy(void* ctx);
 int comm_fork_allreduce(void* ctx, float* buf, long count, cudaStream_t st);
 int comm_join(void* ctx, cudaStream_t st);
 int comm_ctx_set_p2p(void* ctx, void* p2p);
+// colcopy.cu
+struct ColCopyField {
+    char* dst;
+    const char* src;
+    long dst_cs, dst_rs, src_cs, src_rs;   // byte strides per column / per row
+    long w;                                // bytes per (column, row) element
+    int rows;
+    int wide;                              // set by copy_columns
+};
+int copy_columns(const ColCopyField* fields, int n_fields, const long* dst_cols, const long* src_cols, int n_cols, cudaStream_t st);
 // p2p.cu
 int p2p_create(void** out, int world, int rank, long capacity_floats);
 int p2p_ipc_handle(void* ctx, void* out64);

@@ -225,6 +225,7 @@ def test_update_at_benchmarked_size_vs_reference_golden(staged, gemm_engine):
                 ("obs", "rewards", "masks", "bad_masks", "actions", "action_log_probs", "value_preds",
                  "recurrent_hidden_states")}
         st.obs.fill_(9)
+        st.recurrent_hidden_states[1:].fill_(5)               # rows [1:] follow the frames on the copy stream
         st.stage_host(host)
     first = {}
 
@@ -244,6 +245,9 @@ def test_update_at_benchmarked_size_vs_reference_golden(staged, gemm_engine):
     rl2 = helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters()))
     assert rl2 <= 1e-4, rl2
     st.after_update()
+    if staged:
+        assert torch.equal(st.recurrent_hidden_states[1:].cpu(), host["recurrent_hidden_states"][1:])
+        assert torch.equal(st.recurrent_hidden_states[0].cpu(), host["recurrent_hidden_states"][-1])
     torch.manual_seed(8)
     got2 = agent.update(st)
     np.testing.assert_allclose(np.array(got2), case["losses2"], rtol=5e-4, atol=5e-6)
@@ -385,6 +389,9 @@ def test_acktr_update_vs_reference_golden(name, obs_uint8, gemm_engine):
     rl2 = helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters()))
     assert rl2 <= 1e-4, rl2
     st.after_update()
+    if staged:
+        assert torch.equal(st.recurrent_hidden_states[1:].cpu(), host["recurrent_hidden_states"][1:])
+        assert torch.equal(st.recurrent_hidden_states[0].cpu(), host["recurrent_hidden_states"][-1])
     torch.manual_seed(8)
     got2 = agent.update(st)
     np.testing.assert_allclose(np.array(got2), case["losses2"], rtol=5e-4, atol=5e-6)
