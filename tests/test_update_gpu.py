@@ -389,9 +389,6 @@ def test_acktr_update_vs_reference_golden(name, obs_uint8, gemm_engine):
     rl2 = helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters()))
     assert rl2 <= 1e-4, rl2
     st.after_update()
-    if staged:
-        assert torch.equal(st.recurrent_hidden_states[1:].cpu(), host["recurrent_hidden_states"][1:])
-        assert torch.equal(st.recurrent_hidden_states[0].cpu(), host["recurrent_hidden_states"][-1])
     torch.manual_seed(8)
     got2 = agent.update(st)
     np.testing.assert_allclose(np.array(got2), case["losses2"], rtol=5e-4, atol=5e-6)
