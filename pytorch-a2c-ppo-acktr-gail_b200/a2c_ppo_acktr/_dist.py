@@ -114,44 +114,47 @@ def balance_update_plan(perms, E_global, n_mb, world, n_local):
     Returns a list over ranks of dict(envs=[epoch][minibatch] -> int64 columns (E / world of them),
     send=[dst] -> local columns in transfer order, recv=[src] -> guest slots in the same order, n_guests)."""
     assert E_global % world == 0, "the global recurrent minibatch must split evenly over the ranks"
-    target = E_global // world
-    out = [dict(envs=[[None] * n_mb for _ in perms], send=[[] for _ in range(world)], recv=[[] for _ in range(world)],
-                n_guests=0) for _ in range(world)]
-    for e, perm in enumerate(perms):
-        perm = np.asarray(perm, dtype=np.int64)
-        for k in range(n_mb):
-            chunk = perm[k * E_global:(k + 1) * E_global]
-            owner = chunk // n_local
-            order = np.argsort(owner, kind="stable")             # chunk order inside every owner
-            counts = np.bincount(owner, minlength=world)
-            starts = np.concatenate([[0], np.cumsum(counts)])
-            local = chunk[order] - owner[order] * n_local
-            keep, sur_src, sur_col = [], [], []
-            for r in range(world):
-                mine = local[starts[r]:starts[r + 1]]
-                keep.append(mine[:target])
-                if len(mine) > target:
-                    sur_col.append(mine[target:])
-                    sur_src.append(np.full(len(mine) - target, r, np.int64))
-            sur_col = np.concatenate(sur_col) if sur_col else np.zeros(0, np.int64)
-            sur_src = np.concatenate(sur_src) if sur_src else np.zeros(0, np.int64)
-            si = 0
-            for r in range(world):
-                need = target - len(keep[r])
-                if need > 0:
-                    slots = np.arange(out[r]["n_guests"], out[r]["n_guests"] + need, dtype=np.int64)
-                    out[r]["n_guests"] += need
-                    for j in range(need):
-                        src = int(sur_src[si + j])
-                        out[src]["send"][r].append(int(sur_col[si + j]))
-                        out[r]["recv"][src].append(int(slots[j]))
-                    si += need
-                    keep[r] = np.concatenate([keep[r], n_local + slots])
-                out[r]["envs"][e][k] = np.asarray(keep[r], dtype=np.int64)
-            assert si == len(sur_col)
-    for o in out:
-        o["send"] = [np.asarray(x, dtype=np.int64) for x in o["send"]]
-        o["recv"] = [np.asarray(x, dtype=np.int64) for x in o["recv"]]
+    # Vectorised over all minibatches of the update (the plan is made on the host while the device waits for it: ~0.15 ms
+    # whatever the number of ranks; a loop over minibatches x ranks took 0.5 ms at 2 ranks, 2 ms at 8).
+    target, E, n_ep = E_global // world, E_global, len(perms)
+    M = n_ep * n_mb
+    chunks = np.stack([np.asarray(p, dtype=np.int64)[:n_mb * E].reshape(n_mb, E) for p in perms]).reshape(M, E)
+    owner = chunks // n_local
+    order = np.argsort(owner.astype(np.uint8 if world <= 256 else np.int64), axis=1, kind="stable")   # (radix sort)
+    order += np.arange(M)[:, None] * E                            # flat indices: chunk order inside every owner
+    owner_s = owner.ravel()[order]
+    local_s = chunks.ravel()[order] - owner_s * n_local
+    counts = np.bincount((owner + np.arange(M)[:, None] * world).ravel(), minlength=M * world).reshape(M, world)
+    starts = np.cumsum(counts, 1) - counts
+    pos = np.arange(E)[None, :] - starts.ravel()[owner_s + np.arange(M)[:, None] * world]    # index inside the owner's group
+    keep = pos < target
+    need = np.maximum(target - counts, 0)                         # guests rank r takes in minibatch m
+    base = np.cumsum(need, 0) - need                              # guest slots rank r has filled before minibatch m
+    n_guests = need.sum(0)
+    # surplus environments (minibatch-major, rank order inside a minibatch) pair up with the receivers' free places
+    # (minibatch-major, rank order): donors and receivers matched in rank order
+    s_m, s_p = np.nonzero(~keep)
+    s_src, s_col = owner_s[s_m, s_p], local_s[s_m, s_p]
+    r_m, r_rank = np.nonzero(need)
+    reps = need[r_m, r_rank]
+    s_dst = np.repeat(r_rank, reps)
+    within = np.arange(int(reps.sum())) - np.repeat(np.cumsum(reps) - reps, reps)
+    s_slot = np.repeat(base[r_m, r_rank], reps) + within
+    assert len(s_dst) == len(s_src) and np.array_equal(np.repeat(r_m, reps), s_m)
+    by_pair = np.argsort(s_src * world + s_dst, kind="stable")    # transfer order inside every (source, destination) pair
+    pair_n = np.bincount(s_src * world + s_dst, minlength=world * world)
+    cuts = np.concatenate([[0], np.cumsum(pair_n)]).tolist()      # pair (src, dst) = items cuts[src * world + dst] ...
+    cols_by_pair, slots_by_pair = s_col[by_pair], s_slot[by_pair]
+    envs = np.empty((world, M, target), np.int64)
+    k_m, k_p = np.nonzero(keep)
+    envs[owner_s[k_m, k_p], k_m, pos[k_m, k_p]] = local_s[k_m, k_p]          # kept environments, in chunk order
+    envs[s_dst, s_m, np.minimum(counts[s_m, s_dst], target) + within] = n_local + s_slot
+    out = []
+    for r in range(world):
+        out.append(dict(envs=[[envs[r, e * n_mb + k] for k in range(n_mb)] for e in range(n_ep)],
+                        send=[cols_by_pair[cuts[r * world + d]:cuts[r * world + d + 1]] for d in range(world)],
+                        recv=[slots_by_pair[cuts[s * world + r]:cuts[s * world + r + 1]] for s in range(world)],
+                        n_guests=int(n_guests[r])))
     return out
 
 

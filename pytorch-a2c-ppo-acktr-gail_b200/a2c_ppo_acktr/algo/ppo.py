@@ -530,6 +530,25 @@ class PPO():
             self._shadow_src = (rollouts.rewards.data_ptr(), T, n_loc)
         return self._shadow
 
+    @staticmethod
+    def _relayout_columns(prog, cols, T, E, n_columns, dev):
+        """Frame re-layout (`prologue_chunk`, built for E columns = T * E images) of the rollout columns `cols` (host
+        int64), at most E per launch; the image count is a field of the op's descriptor."""
+        if len(cols) == 0:
+            return
+        s2d = prog.prologue_chunk.entries[0][2]
+        full = s2d.B
+        assert len(prog.prologue_chunk.entries) == 1 and full == T * E
+        c = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int64)).to(dev)
+        rows = (torch.arange(T, device=dev, dtype=torch.int64).view(T, 1) * n_columns + c.view(1, -1))
+        try:
+            for i in range(0, len(cols), E):
+                part = rows[:, i:i + E].reshape(-1).contiguous()
+                s2d.B = part.numel()
+                prog.prologue_chunk.run(part)
+        finally:
+            s2d.B = full
+
     def _migration_fields(self, st):
         """(tensor, leading rows) of everything an update reads per environment (dimension 1 = environment)."""
         f = [(st.frames, None), (st.stack_valid, None)] if getattr(st, "frame_ring", False) else [(st.obs, None)]
@@ -568,8 +587,17 @@ class PPO():
                 else:
                     b[:rows, :n_loc].copy_(a[:rows])
         early = getattr(self, "_shadow", None) if getattr(self, "_shadow_src", None) == (rollouts.rewards.data_ptr(), T, n_loc) else None
+        pre = None
         if early is not None:
             own_columns(early)
+            bp = getattr(self, "_bal_prog", None)
+            if (not staged and bp is not None and bp[0] is early and getattr(bp[1], "prologue_chunk", None) is not None
+                    and self.ppo_epoch > 1):
+                # resident frames: every own environment is used by this update (locally or as somebody's guest), so
+                # all own columns are re-laid out NOW -- device work that does not depend on the plan the host is about
+                # to make -- and the first epoch's minibatches find their frames ready
+                self._relayout_columns(bp[1], np.arange(n_loc, dtype=np.int64), T, E, early.rewards.shape[1], dev)
+                pre = bp[1]
         perms = [torch.randperm(sh.n_total).numpy() for _ in range(self.ppo_epoch)]
         plans = _dist.balance_update_plan(perms, E_g, nmb, sh.world, n_loc)
         mine = plans[sh.rank]
@@ -649,34 +677,28 @@ class PPO():
         chunked = getattr(prog, "prologue_chunk", None) is not None
         if not chunked and getattr(prog, "prologue", None) is not None:
             prog.prologue.run()
-        envs = [[torch.from_numpy(x).to(dev) for x in ep] for ep in mine["envs"]]
-        if chunked and self.ppo_epoch > 1:
+        self._bal_prog = (shadow, prog)
+        pre_laid = chunked and pre is prog                      # (a rebuilt program re-lays everything out below)
+        envs = torch.from_numpy(np.concatenate([x for ep in mine["envs"] for x in ep])).to(dev).view(self.ppo_epoch, nmb, E)
+        rows_all = (t_off.view(1, 1, T, 1) + envs.view(self.ppo_epoch, nmb, 1, E)).reshape(self.ppo_epoch, nmb, T * E)
+        if pre_laid:
+            self._relayout_columns(prog, n_loc + np.arange(n_recv, dtype=np.int64), T, E, Nv, dev)      # the guests
+        elif chunked and self.ppo_epoch > 1:
             # columns first used after the first epoch (own environments that the first epoch sent away, guests of later
-            # epochs): their frames are re-laid out now, at most E columns per launch (the size the re-layout op was
-            # built for; its image count is a field of the descriptor)
+            # epochs): their frames are re-laid out now
             first = np.unique(np.concatenate(mine["envs"][0]))
             later = np.setdiff1d(np.unique(np.concatenate([x for ep in mine["envs"][1:] for x in ep])), first)
-            s2d = prog.prologue_chunk.entries[0][2]
-            full = s2d.B
-            assert len(prog.prologue_chunk.entries) == 1 and full == T * E
-            for i in range(0, len(later), E):
-                env = torch.from_numpy(later[i:i + E]).to(dev)
-                s2d.B = T * env.numel()
-                try:
-                    prog.prologue_chunk.run((t_off + env.view(1, -1)).reshape(-1).contiguous())
-                finally:
-                    s2d.B = full
+            self._relayout_columns(prog, later, T, E, Nv, dev)
         ph.mark("relayout-later")
         for epoch in range(self.ppo_epoch):
             for k in range(nmb):
-                env = envs[epoch][k]
-                rows = (t_off + env.view(1, E)).reshape(-1).contiguous()
+                env, rows = envs[epoch, k], rows_all[epoch, k]
                 if epoch == 0 and events is not None:
                     frames_to_shadow(np.setdiff1d(first_cols[k], sent), events[1 + k])
                     if k == nmb - 1:                            # columns outside the first epoch's minibatches: none are
                         for ev in events[1 + nmb:]:             # left by construction, the events only close the upload
                             cur.wait_event(ev)
-                if epoch == 0 and chunked:
+                if epoch == 0 and chunked and not pre_laid:
                     prog.prologue_chunk.run(rows)
                 hxs_mb = rt.arena.bufs["hxs_mb"][:E * H].view(E, H)
                 _native.gather_rows([(h0, hxs_mb)], env, E)

@@ -74,11 +74,22 @@ def main():
     for k, p in pol.named_parameters():
         helpers.assert_summary_close(helpers.summary(p), case["final_" + k], rtol=1e-2, atol=1e-6, what=k, elem_frac=0.1)
     assert helpers.rel_l2(case, "finaldense_", dict(pol.named_parameters())) <= (1e-4 if cfg["recurrent"] else 2e-3)
+    # second update (the balanced recurrent scheme re-uses its shadow rollout and re-lays resident frames out early)
+    losses2 = None
+    if "losses2" in case and cfg["algo"] == "ppo" and cfg["recurrent"]:
+        st.after_update()
+        torch.manual_seed(8)
+        losses2 = agent.update(st)
+        np.testing.assert_allclose(np.array(losses2), case["losses2"], rtol=5e-4, atol=5e-6)
+        flat = pol._flat.clone()
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(flat, ref), "parameters diverged across ranks (second update)"
     dist.barrier()
     if rank == 0:
         comm = getattr(agent, "_comm", None)
         how = "none" if comm is None else ("p2p" if getattr(comm, "p2p", None) is not None else "nccl")
-        print("dist_check ok: case=%s world=%d exchange=%s losses=%s" % (name, world, how, losses))
+        print("dist_check ok: case=%s world=%d exchange=%s losses=%s second=%s" % (name, world, how, losses, losses2))
     dist.destroy_process_group()
 
 

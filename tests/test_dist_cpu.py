@@ -106,6 +106,56 @@ def test_world2_gloo_moments_and_partition():
     assert out[0] and out[1]
 
 
+def _plan_loop(perms, E_global, n_mb, world, n_local):
+    """The plan of `_dist.balance_update_plan` written as the plain loop over minibatches and ranks (the definition the
+    vectorised implementation must reproduce entry for entry)."""
+    import numpy as np
+    target = E_global // world
+    out = [dict(envs=[[None] * n_mb for _ in perms], send=[[] for _ in range(world)], recv=[[] for _ in range(world)],
+                n_guests=0) for _ in range(world)]
+    for e, perm in enumerate(perms):
+        for k in range(n_mb):
+            chunk = np.asarray(perm, dtype=np.int64)[k * E_global:(k + 1) * E_global]
+            keep, surplus = [], []
+            for r in range(world):
+                mine = [int(c) - r * n_local for c in chunk if c // n_local == r]
+                keep.append(mine[:target])
+                surplus += [(r, c) for c in mine[target:]]
+            for r in range(world):
+                while len(keep[r]) < target:
+                    src, col = surplus.pop(0)
+                    slot = out[r]["n_guests"]
+                    out[r]["n_guests"] += 1
+                    out[src]["send"][r].append(col)
+                    out[r]["recv"][src].append(slot)
+                    keep[r].append(n_local + slot)
+                out[r]["envs"][e][k] = keep[r]
+            assert not surplus
+    return out
+
+
+def test_balance_update_plan_equals_its_definition():
+    import numpy as np
+    import torch
+    from a2c_ppo_acktr import _dist
+    for world, n_total, nmb, epochs in ((2, 512, 4, 4), (8, 2048, 4, 4), (4, 64, 2, 3), (2, 8, 2, 3), (4, 16, 4, 2), (16, 4096, 4, 4)):
+        n_local = n_total // world
+        g = torch.Generator().manual_seed(17 + world)
+        perms = [torch.randperm(n_total, generator=g).numpy() for _ in range(epochs)]
+        E_g = n_total // nmb
+        got = _dist.balance_update_plan(perms, E_g, nmb, world, n_local)
+        want = _plan_loop(perms, E_g, nmb, world, n_local)
+        for r in range(world):
+            assert got[r]["n_guests"] == want[r]["n_guests"]
+            for d in range(world):
+                assert list(got[r]["send"][d]) == want[r]["send"][d], (r, d)
+                assert list(got[r]["recv"][d]) == want[r]["recv"][d], (r, d)
+            for e in range(epochs):
+                for k in range(nmb):
+                    assert got[r]["envs"][e][k].dtype == np.int64
+                    assert list(got[r]["envs"][e][k]) == want[r]["envs"][e][k], (r, e, k)
+
+
 def test_balance_update_plan_moves_the_minimum_and_keeps_the_reference_composition():
     """`_dist.balance_update_plan`: every rank gets exactly E / world environments of every global minibatch, kept
     environments stay where they are, the union over ranks is the reference's chunk perm[k E : (k + 1) E], the number of

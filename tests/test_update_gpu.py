@@ -555,7 +555,18 @@ def test_sharded_balanced_equals_global_on_a_ring_rollout(world, N, nmb, staged,
             ranks.append(dict(pol=pol, st=st, agent=agent, rng=torch.get_rng_state(),
                               gen=agent.sharded_recurrent_steps(pol.runtime(), st)))
         res = _lockstep(ranks)
-        out[sharding] = (res[0], {k: p.detach().clone() for k, p in ranks[0]["pol"].named_parameters()})
+        # a second update on the same rollout: the balanced scheme now re-lays its own columns out before it plans
+        # (resident frames), on the shadow rollout and program of the first update
+        for r, rk in enumerate(ranks):
+            if staged and sharding == "balanced":
+                lo, hi = r * per, (r + 1) * per
+                rk["st"].frames.fill_(3)
+                rk["st"].stage_host({"frames": frames[:, lo:hi].contiguous().pin_memory()})
+            torch.manual_seed(8)
+            rk["rng"] = torch.get_rng_state()
+            rk["gen"] = rk["agent"].sharded_recurrent_steps(rk["pol"].runtime(), rk["st"])
+        res2 = _lockstep(ranks)
+        out[sharding] = (tuple(res[0]) + tuple(res2[0]), {k: p.detach().clone() for k, p in ranks[0]["pol"].named_parameters()})
         for r in ranks[1:]:
             for k, p in r["pol"].named_parameters():
                 assert torch.equal(p, out[sharding][1][k]), k
