@@ -581,11 +581,9 @@ class PPO():
         def own_columns(shadow):
             """The rank's own environments -> columns [0, n_loc) of the shadow rollout (frames staged on the host follow
             their upload, chunk by chunk)."""
-            for (a, rows), (b, _) in zip(src_f[1 if staged else 0:], self._migration_fields(shadow)[1 if staged else 0:]):
-                if rows is None:
-                    b[:, :n_loc].copy_(a)
-                else:
-                    b[:rows, :n_loc].copy_(a[:rows])
+            pairs = [((b if rows is None else b[:rows])[:, :n_loc], a if rows is None else a[:rows])
+                     for (a, rows), (b, _) in zip(src_f[1 if staged else 0:], self._migration_fields(shadow)[1 if staged else 0:])]
+            _native.copy_columns(pairs, None, None, n_loc)          # one launch (a strided uint8 copy_ per field is slow)
         early = getattr(self, "_shadow", None) if getattr(self, "_shadow_src", None) == (rollouts.rewards.data_ptr(), T, n_loc) else None
         pre = None
         if early is not None:
