@@ -179,6 +179,10 @@ def run_ours(args):
             raise SystemExit("--gpus %d needs a torchrun launch with %d ranks" % (args.gpus, args.gpus))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    from a2c_ppo_acktr import utils as a2c_utils
+    # N > 1: every rank pins itself to its GPU's NUMA node before the pinned rollout is allocated.  (Not at N = 1: the
+    # same process later times the CPU baseline on ALL host cores, and worker threads inherit the mask.)
+    bound = None if (args.no_numa_bind or world == 1) else a2c_utils.bind_host_to_device_node(local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -361,7 +365,8 @@ def run_ours(args):
                                     else "ncclAllReduce on a side stream" if getattr(agent, "_comm", None) is not None else "torch.distributed"),
                        "obs": ("uint8 frame ring (each 84x84 frame stored once, 4-stacks assembled on the device)" if ring
                                else "uint8 4x84x84 stacks" if obs_dtype == torch.uint8 else "fp32"), "l2": "flushed between steps (256 MiB write)",
-                       "step": "compute_returns + update + after_update"},
+                       "step": "compute_returns + update + after_update",
+                       "host_cpus": ("%d cores of the GPU's NUMA node" % len(bound)) if bound else "unbound"},
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 12},
             "gpu_launches": int(launches),
@@ -730,6 +735,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C5", choices=sorted(synthetic.CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not pin the process to the CPU cores of the GPU's NUMA node before the pinned rollout is allocated")
     ap.add_argument("--no-parity", action="store_true", help="skip the first-update check against the reference golden (C5)")
     ap.add_argument("--stacked-frames", action="store_true",
                     help="Atari workloads: store / upload full 4-frame stacks (reference layout) instead of the frame ring")

@@ -32,3 +32,33 @@ def init(module, weight_init, bias_init, gain=1):
     weight_init(module.weight.data, gain=gain)
     bias_init(module.bias.data)
     return module
+
+
+def bind_host_to_device_node(device_index):
+    """Host-side half of the rollout ingest (`RolloutStorage.stage_host`): pins the calling process to the CPU cores of
+    the NUMA node the GPU hangs off, so that pinned rollout buffers allocated afterwards are local to the GPU's PCIe root
+    (first-touch placement) -- with one rank per GPU every rank then pulls from its own memory controller instead of all
+    of them from the node the launcher happened to start on.  Returns the CPU list it bound to, or None when the
+    platform does not say (single-node hosts report numa_node = -1) or the container does not allow it."""
+    import os
+    import torch
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        with open(base + "/numa_node") as f:
+            if int(f.read().strip()) < 0:
+                return None
+        with open(base + "/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
