@@ -112,7 +112,8 @@ def balance_update_plan(perms, E_global, n_mb, world, n_local):
     its receiver (column n_local + slot of the receiver's shadow rollout).
 
     Returns a list over ranks of dict(envs=[epoch][minibatch] -> int64 columns (E / world of them),
-    send=[dst] -> local columns in transfer order, recv=[src] -> guest slots in the same order, n_guests)."""
+    send=[dst] -> local columns in transfer order, recv=[src] -> guest slots in the same order, n_guests,
+    first_send=[dst] / first_recv=[src] -> how many leading entries of send / recv belong to the FIRST epoch)."""
     assert E_global % world == 0, "the global recurrent minibatch must split evenly over the ranks"
     # Vectorised over all minibatches of the update (the plan is made on the host while the device waits for it: ~0.15 ms
     # whatever the number of ranks; a loop over minibatches x ranks took 0.5 ms at 2 ranks, 2 ms at 8).
@@ -143,6 +144,7 @@ def balance_update_plan(perms, E_global, n_mb, world, n_local):
     assert len(s_dst) == len(s_src) and np.array_equal(np.repeat(r_m, reps), s_m)
     by_pair = np.argsort(s_src * world + s_dst, kind="stable")    # transfer order inside every (source, destination) pair
     pair_n = np.bincount(s_src * world + s_dst, minlength=world * world)
+    first_n = np.bincount((s_src * world + s_dst)[s_m < n_mb], minlength=world * world)   # (stable order: they lead)
     cuts = np.concatenate([[0], np.cumsum(pair_n)]).tolist()      # pair (src, dst) = items cuts[src * world + dst] ...
     cols_by_pair, slots_by_pair = s_col[by_pair], s_slot[by_pair]
     envs = np.empty((world, M, target), np.int64)
@@ -154,7 +156,9 @@ def balance_update_plan(perms, E_global, n_mb, world, n_local):
         out.append(dict(envs=[[envs[r, e * n_mb + k] for k in range(n_mb)] for e in range(n_ep)],
                         send=[cols_by_pair[cuts[r * world + d]:cuts[r * world + d + 1]] for d in range(world)],
                         recv=[slots_by_pair[cuts[s * world + r]:cuts[s * world + r + 1]] for s in range(world)],
-                        n_guests=int(n_guests[r])))
+                        n_guests=int(n_guests[r]),
+                        first_send=[int(first_n[r * world + d]) for d in range(world)],
+                        first_recv=[int(first_n[s * world + r]) for s in range(world)]))
     return out
 
 

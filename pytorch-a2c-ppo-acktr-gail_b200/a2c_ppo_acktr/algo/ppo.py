@@ -562,12 +562,18 @@ class PPO():
         environments of a minibatch to the ranks that own fewer.  All permutations of the update are drawn first (the
         same RNG sequence as drawing one per epoch), the rollout columns of every environment that has to move travel in
         ONE all-to-all per update (~0.9 MB per environment in frame-ring format, a few dozen per rank), and the update
-        then runs on a shadow rollout [own environments | guests] with a single program size."""
+        then runs on a shadow rollout [own environments | guests] with a single program size.
+
+        Frames staged on the host (`stage_host`) arrive in the order they are needed -- the rank's environments of the
+        first global minibatch (started before the plan is made: they are needed first whoever processes them), the other
+        environments the first epoch sends away, then minibatch by minibatch -- and the migration runs in TWO all-to-alls:
+        what the first epoch needs before it, the later epochs' guests after it (by then every column is on the device),
+        so the first minibatch waits for ~70 columns instead of ~95."""
         sh = self.shard
         self._update_serial = getattr(self, "_update_serial", 0) + 1
         T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
         assert n_loc == sh.n_local, "rollouts hold %d environments, the shard declares %d" % (n_loc, sh.n_local)
-        nmb = self.num_mini_batch
+        nmb, n_ep = self.num_mini_batch, self.ppo_epoch
         E_g = sh.n_total // nmb
         E = E_g // sh.world
         ph = _Phases(rt.dev, sh.rank)
@@ -575,7 +581,8 @@ class PPO():
         dev = rt.dev
         cur = torch.cuda.current_stream(dev)
         moments = _adv_moments(rt, rollouts)                    # (device work first: the host-side planning overlaps it)
-        staged = getattr(rollouts, "_staged_obs", None) is not None
+        upload = rollouts._staged_upload() if hasattr(rollouts, "_staged_upload") else None
+        staged = upload is not None
         src_f = self._migration_fields(rollouts)
 
         def own_columns(shadow):
@@ -590,13 +597,18 @@ class PPO():
             own_columns(early)
             bp = getattr(self, "_bal_prog", None)
             if (not staged and bp is not None and bp[0] is early and getattr(bp[1], "prologue_chunk", None) is not None
-                    and self.ppo_epoch > 1):
+                    and n_ep > 1):
                 # resident frames: every own environment is used by this update (locally or as somebody's guest), so
                 # all own columns are re-laid out NOW -- device work that does not depend on the plan the host is about
                 # to make -- and the first epoch's minibatches find their frames ready
                 self._relayout_columns(bp[1], np.arange(n_loc, dtype=np.int64), T, E, early.rewards.shape[1], dev)
                 pre = bp[1]
-        perms = [torch.randperm(sh.n_total).numpy() for _ in range(self.ppo_epoch)]
+        perms = [torch.randperm(sh.n_total).numpy() for _ in range(n_ep)]
+        events = {}
+        if staged:
+            c0 = np.asarray(perms[0][:E_g], dtype=np.int64)
+            own0 = np.sort(c0[c0 // n_loc == sh.rank] - sh.rank * n_loc)
+            events["own0"] = upload.columns(own0)               # the copy engine starts while the host plans
         plans = _dist.balance_update_plan(perms, E_g, nmb, sh.world, n_loc)
         mine = plans[sh.rank]
         ph.mark("plan")
@@ -607,38 +619,54 @@ class PPO():
             own_columns(shadow)
         Nv = shadow.rewards.shape[1]
         dst_f = self._migration_fields(shadow)
-        # ---- frames staged on the host (`stage_host`): uploaded in the order they are needed -- the environments that
-        #      migrate first, then the first epoch's minibatches -- and copied into the shadow rollout chunk by chunk, so
-        #      that only the first ~40 columns are waited for before the exchange; the rest overlaps the compute ----
-        sent = np.unique(np.concatenate(mine["send"] + [np.zeros(0, np.int64)]))
-        first_cols = [x[x < n_loc] for x in mine["envs"][0]]
-        events = None
-        if staged:
-            events = rollouts._upload_staged([torch.from_numpy(sent)] +
-                                             [torch.from_numpy(np.setdiff1d(c, sent)) for c in first_cols])
         big_src, big_dst = src_f[0][0], dst_f[0][0]              # frames (ring) / obs: everything else is narrow
+        # two migration phases for staged frames (first epoch / later epochs), one otherwise
+        two = staged and n_ep > 1
+        cutS = [int(c) for c in mine["first_send"]] if two else [len(x) for x in mine["send"]]
+        cutR = [int(c) for c in mine["first_recv"]] if two else [len(x) for x in mine["recv"]]
+        parts = [([x[:c] for x, c in zip(mine["send"], cutS)], [x[:c] for x, c in zip(mine["recv"], cutR)])]
+        if two:
+            parts.append(([x[c:] for x, c in zip(mine["send"], cutS)], [x[c:] for x, c in zip(mine["recv"], cutR)]))
+        moves_all = sum(len(x) for p in plans for x in p["send"])
+        moves_first = sum(sum(p["first_send"]) for p in plans) if two else moves_all
+        moves = [moves_first, moves_all - moves_first]          # over ALL ranks: a phase nobody takes part in is skipped
+        first_cols = [x[x < n_loc] for x in mine["envs"][0]]
+        if staged:
+            sentA = np.unique(np.concatenate(parts[0][0] + [np.zeros(0, np.int64)]))
+            done = own0
+            events["sentA"] = upload.columns(np.setdiff1d(sentA, done))
+            done = np.union1d(done, sentA)
+            for k in range(nmb):
+                events[k] = upload.columns(np.setdiff1d(first_cols[k], done))
+                done = np.union1d(done, first_cols[k])
+            events["rest"] = upload.finish()                    # none are left by construction; closes the upload (+ tail)
 
         def frames_to_shadow(cols, event):
-            if event is not None:
-                cur.wait_event(event)
+            cur.wait_event(event)
             if len(cols):
                 c = torch.from_numpy(np.ascontiguousarray(cols)).to(dev)
                 _native.copy_columns([(big_dst, big_src)], c, c, len(cols))
-        if events is not None:
-            frames_to_shadow(sent, events[0])
+        if staged:
+            frames_to_shadow(own0, events["own0"])
+            frames_to_shadow(np.setdiff1d(sentA, own0), events["sentA"])
         # ---- migration: the travelling environments' columns packed into records (one record = every field of one
-        #      environment, environment-major), ONE all-to-all, records unpacked into the guest columns.  The record
+        #      environment, environment-major), an all-to-all, records unpacked into the guest columns.  The record
         #      buffers have the CAPACITY of the shadow rollout (no allocator growth, one registration), the kernels and
         #      the messages carry this update's counts. ----
         cap = Nv - n_loc - 1
         n_send, n_recv = sum(len(x) for x in mine["send"]), sum(len(x) for x in mine["recv"])
         assert n_send <= cap and n_recv <= cap
         cols_np = np.zeros(2 * cap, np.int64)
-        cols_np[:n_send] = np.concatenate(mine["send"] + [np.zeros(0, np.int64)])
-        cols_np[cap:cap + n_recv] = np.concatenate(mine["recv"] + [np.zeros(0, np.int64)]) + n_loc
+        so, ro, bounds = 0, 0, []
+        for snd, rcv in parts:                                  # phase-major, destination / source rank order inside
+            a, b = np.concatenate(snd + [np.zeros(0, np.int64)]), np.concatenate(rcv + [np.zeros(0, np.int64)])
+            cols_np[so:so + len(a)] = a
+            cols_np[cap + ro:cap + ro + len(b)] = b + n_loc
+            bounds.append((so, so + len(a), ro, ro + len(b)))
+            so, ro = so + len(a), ro + len(b)
         cols_dev = torch.from_numpy(cols_np).to(dev)
-        send_cols, recv_cols = cols_dev[:cap], cols_dev[cap:]
         views = [(x if rows is None else x[:rows]) for x, rows in src_f]
+        dviews = [(x if rows is None else x[:rows]) for x, rows in dst_f]
         widths = [(v[:, 0].numel() * v.element_size() + 15) // 16 * 16 for v in views]      # fields start 16-byte aligned
         rec_bytes = sum(widths)
         bufs = getattr(self, "_xchg_bufs", None)
@@ -652,15 +680,22 @@ class PPO():
             out, off = [], 0
             for v, w in zip(like, widths):
                 rows, wb = v.shape[0], v[0, 0].numel() * v.element_size()
-                out.append(buf[:, off:off + rows * wb].view(cap, rows, wb).transpose(0, 1))
+                out.append(buf.narrow(1, off, rows * wb).unflatten(1, (rows, wb)).transpose(0, 1))
                 off += w
             return out
-        _native.copy_columns(list(zip(record_views(send, views), views)), None, send_cols, n_send)
-        ph.mark("shadow+pack")
-        yield _dist.Exchange(send[:n_send], [len(x) for x in mine["send"]], recv[:n_recv], [len(x) for x in mine["recv"]])
-        ph.mark("exchange")
-        dviews = [(x if rows is None else x[:rows]) for x, rows in dst_f]
-        _native.copy_columns(list(zip(dviews, record_views(recv, dviews))), recv_cols, None, n_recv)
+
+        def migrate(i):
+            """Phase i of the migration (a generator: the all-to-all is performed by whoever drives the update)."""
+            s0, s1, r0, r1 = bounds[i]
+            snd, rcv = parts[i]
+            if moves[i] == 0:
+                return
+            _native.copy_columns(list(zip(record_views(send[s0:s1], views), views)), None, cols_dev[s0:], s1 - s0)
+            ph.mark("pack%d" % i)
+            yield _dist.Exchange(send[s0:s1], [len(x) for x in snd], recv[r0:r1], [len(x) for x in rcv])
+            ph.mark("exchange%d" % i)
+            _native.copy_columns(list(zip(dviews, record_views(recv[r0:r1], dviews))), cols_dev[cap + r0:], None, r1 - r0)
+        yield from migrate(0)
         adv = _adv_apply(rt, shadow, moments)
         ph.mark("unpack+adv")
         accum = rt.arena.ensure("loss_accum", 4)
@@ -674,28 +709,35 @@ class PPO():
         launches0 = _native.launch_count()
         chunked = getattr(prog, "prologue_chunk", None) is not None
         if not chunked and getattr(prog, "prologue", None) is not None:
+            assert not two, "staged frames need the per-chunk re-layout"
             prog.prologue.run()
         self._bal_prog = (shadow, prog)
         pre_laid = chunked and pre is prog                      # (a rebuilt program re-lays everything out below)
-        envs = torch.from_numpy(np.concatenate([x for ep in mine["envs"] for x in ep])).to(dev).view(self.ppo_epoch, nmb, E)
-        rows_all = (t_off.view(1, 1, T, 1) + envs.view(self.ppo_epoch, nmb, 1, E)).reshape(self.ppo_epoch, nmb, T * E)
+        envs = torch.from_numpy(np.concatenate([x for ep in mine["envs"] for x in ep])).to(dev).view(n_ep, nmb, E)
+        rows_all = (t_off.view(1, 1, T, 1) + envs.view(n_ep, nmb, 1, E)).reshape(n_ep, nmb, T * E)
+        later_guests = np.zeros(0, np.int64)
         if pre_laid:
             self._relayout_columns(prog, n_loc + np.arange(n_recv, dtype=np.int64), T, E, Nv, dev)      # the guests
-        elif chunked and self.ppo_epoch > 1:
+        elif chunked and n_ep > 1:
             # columns first used after the first epoch (own environments that the first epoch sent away, guests of later
-            # epochs): their frames are re-laid out now
+            # epochs): their frames are re-laid out now -- the guests of a second migration phase once they have arrived
             first = np.unique(np.concatenate(mine["envs"][0]))
             later = np.setdiff1d(np.unique(np.concatenate([x for ep in mine["envs"][1:] for x in ep])), first)
+            if two:
+                later, later_guests = later[later < n_loc], later[later >= n_loc]
             self._relayout_columns(prog, later, T, E, Nv, dev)
         ph.mark("relayout-later")
-        for epoch in range(self.ppo_epoch):
+        for epoch in range(n_ep):
+            if epoch == 1 and two:
+                yield from migrate(1)
+                self._relayout_columns(prog, later_guests, T, E, Nv, dev)
+                ph.mark("migrate1")
             for k in range(nmb):
                 env, rows = envs[epoch, k], rows_all[epoch, k]
-                if epoch == 0 and events is not None:
-                    frames_to_shadow(np.setdiff1d(first_cols[k], sent), events[1 + k])
-                    if k == nmb - 1:                            # columns outside the first epoch's minibatches: none are
-                        for ev in events[1 + nmb:]:             # left by construction, the events only close the upload
-                            cur.wait_event(ev)
+                if epoch == 0 and staged:
+                    frames_to_shadow(np.setdiff1d(first_cols[k], np.union1d(own0, sentA)), events[k])
+                    if k == nmb - 1:
+                        cur.wait_event(events["rest"])
                 if epoch == 0 and chunked and not pre_laid:
                     prog.prologue_chunk.run(rows)
                 hxs_mb = rt.arena.bufs["hxs_mb"][:E * H].view(E, H)
@@ -714,7 +756,7 @@ class PPO():
                 ph.mark("mb%d.%d" % (epoch, k))
         self.last_launches = _native.launch_count() - launches0
         yield accum
-        num_updates = self.ppo_epoch * self.num_mini_batch
+        num_updates = n_ep * self.num_mini_batch
         sums = accum[:3].cpu()
         ph.mark("losses")
         ph.report()

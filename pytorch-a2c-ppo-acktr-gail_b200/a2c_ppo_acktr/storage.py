@@ -204,41 +204,58 @@ class RolloutStorage(object):
             else:
                 dst.copy_(src, non_blocking=True)
 
-    def _upload_staged(self, env_chunks=None):
-        """Starts the upload of the registered frames on the copy stream, one strided copy set per chunk of
-        environments (default: everything at once).  Returns one event per chunk, or None if nothing is staged."""
+    def _staged_upload(self):
+        """Begins the upload of the registered frames on the copy stream.  Returns None when no frames are staged, else an
+        object with `columns(envs)` -- enqueues the strided copies of those environments (host int64 array, may be
+        empty) and returns an event -- and `finish()` -- uploads every environment not asked for yet, then the deferred
+        rows of the hidden states, and returns the closing event."""
         host, self._staged_obs = self._staged_obs, None
-        tail, self._staged_tail = self._staged_tail, None
-        if host is None and tail is None:
+        if host is None:
             return None
+        tail, self._staged_tail = self._staged_tail, None
         frames = self.frames if self.frame_ring else self.obs
         dev = frames.device
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         cs = self._copy_stream
         cs.wait_stream(torch.cuda.current_stream(dev))      # earlier readers / writers of obs are done
-        if host is None:
-            self._upload_tail(tail, cs)
+        storage = self
+        seen = torch.zeros(frames.shape[1], dtype=torch.bool)
+
+        class Upload(object):
+            def columns(self, envs):
+                envs = torch.as_tensor(envs, dtype=torch.int64)
+                if envs.numel():
+                    _native.upload_env_columns(frames, host, envs, cs)
+                    seen[envs] = True
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                return ev
+
+            def finish(self):
+                ev = self.columns((~seen).nonzero().view(-1))
+                storage._staged_keepalive = host            # until the next stage / upload replaces it
+                if tail is not None:
+                    storage._upload_tail(tail, cs)
+                return ev
+        return Upload()
+
+    def _upload_staged(self, env_chunks=None):
+        """Starts the upload of the registered frames on the copy stream, one strided copy set per chunk of
+        environments (default: everything at once).  Returns one event per chunk (+ one for the environments no chunk
+        named), or None if nothing is staged."""
+        up = self._staged_upload()
+        if up is None:
+            tail, self._staged_tail = self._staged_tail, None
+            if tail is not None:
+                dev = self.rewards.device
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(dev)
+                self._copy_stream.wait_stream(torch.cuda.current_stream(dev))
+                self._upload_tail(tail, self._copy_stream)
             return None
-        N = frames.shape[1]
-        if env_chunks is None:
-            env_chunks = [torch.arange(N)]
-        else:
-            seen = torch.zeros(N, dtype=torch.bool)
-            for c in env_chunks:
-                seen[c] = True
-            rest = (~seen).nonzero().view(-1)
-            if rest.numel():
-                env_chunks = list(env_chunks) + [rest]
-        events = []
-        for envs in env_chunks:
-            if len(envs):
-                _native.upload_env_columns(frames, host, envs, cs)
-            ev = torch.cuda.Event()
-            ev.record(cs)
-            events.append(ev)
-        self._staged_keepalive = host                       # until the next stage / upload replaces it
-        self._upload_tail(tail, cs)
+        events = [up.columns(c) for c in (env_chunks if env_chunks is not None else [])]
+        events.append(up.finish())
         return events
 
     def _upload_tail(self, tail, cs):

@@ -112,7 +112,7 @@ def _plan_loop(perms, E_global, n_mb, world, n_local):
     import numpy as np
     target = E_global // world
     out = [dict(envs=[[None] * n_mb for _ in perms], send=[[] for _ in range(world)], recv=[[] for _ in range(world)],
-                n_guests=0) for _ in range(world)]
+                n_guests=0, first_send=[0] * world, first_recv=[0] * world) for _ in range(world)]
     for e, perm in enumerate(perms):
         for k in range(n_mb):
             chunk = np.asarray(perm, dtype=np.int64)[k * E_global:(k + 1) * E_global]
@@ -128,6 +128,9 @@ def _plan_loop(perms, E_global, n_mb, world, n_local):
                     out[r]["n_guests"] += 1
                     out[src]["send"][r].append(col)
                     out[r]["recv"][src].append(slot)
+                    if e == 0:
+                        out[src]["first_send"][r] += 1
+                        out[r]["first_recv"][src] += 1
                     keep[r].append(n_local + slot)
                 out[r]["envs"][e][k] = keep[r]
             assert not surplus
@@ -147,6 +150,7 @@ def test_balance_update_plan_equals_its_definition():
         want = _plan_loop(perms, E_g, nmb, world, n_local)
         for r in range(world):
             assert got[r]["n_guests"] == want[r]["n_guests"]
+            assert got[r]["first_send"] == want[r]["first_send"] and got[r]["first_recv"] == want[r]["first_recv"]
             for d in range(world):
                 assert list(got[r]["send"][d]) == want[r]["send"][d], (r, d)
                 assert list(got[r]["recv"][d]) == want[r]["recv"][d], (r, d)
