@@ -564,11 +564,11 @@ class PPO():
         ONE all-to-all per update (~0.9 MB per environment in frame-ring format, a few dozen per rank), and the update
         then runs on a shadow rollout [own environments | guests] with a single program size.
 
-        Frames staged on the host (`stage_host`) arrive in the order they are needed -- the rank's environments of the
-        first global minibatch (started before the plan is made: they are needed first whoever processes them), the other
-        environments the first epoch sends away, then minibatch by minibatch -- and the migration runs in TWO all-to-alls:
-        what the first epoch needs before it, the later epochs' guests after it (by then every column is on the device),
-        so the first minibatch waits for ~70 columns instead of ~95."""
+        Frames staged on the host (`stage_host`) arrive in the order they are needed -- the environments the first epoch
+        sends away, the ones its first minibatch keeps (both known from the first permutation, so the copy engine starts
+        before the plan is made), then minibatch by minibatch -- and the migration runs in TWO all-to-alls: what the first
+        epoch needs before it (while the first minibatch's own columns are still arriving), the later epochs' guests after
+        it (by then every column is on the device)."""
         sh = self.shard
         self._update_serial = getattr(self, "_update_serial", 0) + 1
         T, n_loc = rollouts.rewards.shape[0], rollouts.rewards.shape[1]
@@ -606,9 +606,16 @@ class PPO():
         perms = [torch.randperm(sh.n_total).numpy() for _ in range(n_ep)]
         events = {}
         if staged:
-            c0 = np.asarray(perms[0][:E_g], dtype=np.int64)
-            own0 = np.sort(c0[c0 // n_loc == sh.rank] - sh.rank * n_loc)
-            events["own0"] = upload.columns(own0)               # the copy engine starts while the host plans
+            # what the first epoch sends away and what its first minibatch keeps follow from the first permutation
+            # alone (a rank keeps the first E of its environments of a chunk, in chunk order): the copy engine gets
+            # them -- in that order: the all-to-all can then run while the kept columns are still arriving -- before
+            # the host makes the full plan
+            p0 = np.asarray(perms[0], dtype=np.int64)
+            own_k = [c[c // n_loc == sh.rank] - sh.rank * n_loc for c in (p0[k * E_g:(k + 1) * E_g] for k in range(nmb))]
+            sentA = np.unique(np.concatenate([c[E:] for c in own_k]))
+            kept0 = np.sort(own_k[0][:E])
+            events["sentA"] = upload.columns(sentA)
+            events["kept0"] = upload.columns(kept0)
         plans = _dist.balance_update_plan(perms, E_g, nmb, sh.world, n_loc)
         mine = plans[sh.rank]
         ph.mark("plan")
@@ -632,13 +639,11 @@ class PPO():
         moves = [moves_first, moves_all - moves_first]          # over ALL ranks: a phase nobody takes part in is skipped
         first_cols = [x[x < n_loc] for x in mine["envs"][0]]
         if staged:
-            sentA = np.unique(np.concatenate(parts[0][0] + [np.zeros(0, np.int64)]))
-            done = own0
-            events["sentA"] = upload.columns(np.setdiff1d(sentA, done))
-            done = np.union1d(done, sentA)
-            for k in range(nmb):
-                events[k] = upload.columns(np.setdiff1d(first_cols[k], done))
-                done = np.union1d(done, first_cols[k])
+            assert np.array_equal(sentA, np.unique(np.concatenate(
+                [x[:c] for x, c in zip(mine["send"], mine["first_send"])] + [np.zeros(0, np.int64)])))
+            assert np.array_equal(kept0, np.sort(first_cols[0]))
+            for k in range(1, nmb):
+                events[k] = upload.columns(first_cols[k])
             events["rest"] = upload.finish()                    # none are left by construction; closes the upload (+ tail)
 
         def frames_to_shadow(cols, event):
@@ -647,8 +652,7 @@ class PPO():
                 c = torch.from_numpy(np.ascontiguousarray(cols)).to(dev)
                 _native.copy_columns([(big_dst, big_src)], c, c, len(cols))
         if staged:
-            frames_to_shadow(own0, events["own0"])
-            frames_to_shadow(np.setdiff1d(sentA, own0), events["sentA"])
+            frames_to_shadow(sentA, events["sentA"])
         # ---- migration: the travelling environments' columns packed into records (one record = every field of one
         #      environment, environment-major), an all-to-all, records unpacked into the guest columns.  The record
         #      buffers have the CAPACITY of the shadow rollout (no allocator growth, one registration), the kernels and
@@ -730,12 +734,13 @@ class PPO():
         for epoch in range(n_ep):
             if epoch == 1 and two:
                 yield from migrate(1)
+                assert _adv_apply(rt, shadow, moments).data_ptr() == adv.data_ptr()     # the new guests' advantages
                 self._relayout_columns(prog, later_guests, T, E, Nv, dev)
                 ph.mark("migrate1")
             for k in range(nmb):
                 env, rows = envs[epoch, k], rows_all[epoch, k]
                 if epoch == 0 and staged:
-                    frames_to_shadow(np.setdiff1d(first_cols[k], np.union1d(own0, sentA)), events[k])
+                    frames_to_shadow(first_cols[k], events["kept0" if k == 0 else k])
                     if k == nmb - 1:
                         cur.wait_event(events["rest"])
                 if epoch == 0 and chunked and not pre_laid:
