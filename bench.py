@@ -341,6 +341,19 @@ def run_ours(args):
                  "note": "recurrent_sharding='stratified': balanced per-rank permutations, not the reference's minibatch "
                          "composition; shown to separate load imbalance from exchange cost"}
 
+    # N > 1: after all those sharded updates every rank must hold bit-identical parameters (one rank sums each gradient
+    # element, the clip + Adam step is redundant and identical) -- a cheap end-to-end check of the exchange at this N
+    identical = None
+    if world > 1:
+        flat = policy._flat.detach().clone()
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        ok = torch.tensor([1 if (torch.equal(flat, ref) and bool(torch.isfinite(flat).all())) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        identical = bool(ok.item())
+        if not identical:
+            raise SystemExit("bench: parameters diverged across ranks (or are not finite) after the sharded updates")
+
     transitions = T * Nloc * world
     ms_per_step = total_ms / args.steps
     value = transitions / (ms_per_step / 1e3)
@@ -375,6 +388,8 @@ def run_ours(args):
         }
         if strat:
             out["stratified_sharding"] = strat
+        if identical is not None:
+            out["ranks_bit_identical"] = identical
         if roof:
             out["roofline"] = roof
             out["kernels"] = kernels

@@ -4,8 +4,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T=${TAG:-r02zb}
 G=${GPUS:-2}
-for c in C5s C5m; do
-A2CB_DIST_STAGED=1 A2CB_DIST_CASE=$c timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py > gpurun_out/${T}_dist_check_$c.log 2>&1; echo "dist_check $c rc=$?"; tail -1 gpurun_out/${T}_dist_check_$c.log | cut -c1-200
+for c in ${CASES:-C5s C5m}; do
+A2CB_DIST_STAGED=1 A2CB_DIST_CASE=$c timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${CHECK_GPUS:-2} --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py > gpurun_out/${T}_dist_check_$c.log 2>&1; echo "dist_check $c rc=$?"; tail -1 gpurun_out/${T}_dist_check_$c.log | cut -c1-200
 done
 if [ "${SKIP_N1:-0}" != "1" ]; then
 A2CB_PHASE_TIMING=1 timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-parity > gpurun_out/${T}_phases_n1.json 2> gpurun_out/${T}_phases_n1.err; echo "n1 rc=$?"
