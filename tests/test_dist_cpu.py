@@ -195,3 +195,55 @@ def test_balance_update_plan_moves_the_minimum_and_keeps_the_reference_compositi
                 owner = chunk // n_local
                 moves += sum(max(int((owner == r).sum()) - E_g // world, 0) for r in range(world))
         assert moves == sum(p["n_guests"] for p in plans)
+
+
+def _migration_worker(rank, world, port, out):
+    """The environment migration of the balanced scheme over a real process group (gloo): every rank plans from the same
+    permutations, packs one record per travelling environment, and the two all-to-alls (first epoch / later epochs) must
+    leave every guest slot holding the record of the environment the plan put there."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_local, nmb, epochs, width = 16, 2, 3, 24
+    n_total = n_local * world
+    g = torch.Generator().manual_seed(5)                       # same seed everywhere: same permutations, same plan
+    perms = [torch.randperm(n_total, generator=g).numpy() for _ in range(epochs)]
+    plans = _dist.balance_update_plan(perms, n_total // nmb, nmb, world, n_local)
+    mine = plans[rank]
+    # record of global environment e: [e, e + 1, ...] as bytes
+    def record(e):
+        return (torch.arange(width, dtype=torch.int64) + int(e)).to(torch.uint8)
+    guests = torch.zeros(max(p["n_guests"] for p in plans) + 1, width, dtype=torch.uint8)
+    for phase in (0, 1):
+        cut_s, cut_r = mine["first_send"], mine["first_recv"]
+        snd = [x[:c] if phase == 0 else x[c:] for x, c in zip(mine["send"], cut_s)]
+        rcv = [x[:c] if phase == 0 else x[c:] for x, c in zip(mine["recv"], cut_r)]
+        cols = np.concatenate(snd + [np.zeros(0, np.int64)])
+        send = torch.stack([record(rank * n_local + c) for c in cols]) if len(cols) else torch.zeros(0, width, dtype=torch.uint8)
+        recv = torch.zeros(sum(len(x) for x in rcv), width, dtype=torch.uint8)
+        _dist.Exchange(send, [len(x) for x in snd], recv, [len(x) for x in rcv]).run()
+        slots = np.concatenate(rcv + [np.zeros(0, np.int64)])
+        if len(slots):
+            guests[torch.from_numpy(slots)] = recv
+    # what every guest slot must hold, replayed from the senders' side of the plan
+    ok = True
+    for s in range(world):
+        for col, slot in zip(plans[s]["send"][rank], mine["recv"][s]):
+            ok = ok and torch.equal(guests[int(slot)], record(s * n_local + int(col)))
+    # and every minibatch of this rank is E / world environments of the reference's chunk
+    E_g = n_total // nmb
+    slot_env = {int(slot): s * n_local + int(col) for s in range(world) for col, slot in zip(plans[s]["send"][rank], mine["recv"][s])}
+    for e in range(epochs):
+        for k in range(nmb):
+            envs = [rank * n_local + int(c) if c < n_local else slot_env[int(c) - n_local] for c in mine["envs"][e][k]]
+            ok = ok and len(envs) == E_g // world and set(envs) <= set(int(x) for x in perms[e][k * E_g:(k + 1) * E_g])
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_environment_migration_in_two_phases():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_migration_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] and out[1]
