@@ -101,44 +101,61 @@ template <typename T>
 __global__ void __launch_bounds__(352)
 tcx_s2d_atari_kernel(float4* __restrict__ out, float4* __restrict__ out_lo, uint2* __restrict__ out_b16,
                      const T* __restrict__ frames, const int64_t* __restrict__ idx, int scatter,
-                     const uint8_t* __restrict__ valid, int ring_n) {
-    __shared__ float4 tile[16][21];
-    const int b = blockIdx.x / 21, by = blockIdx.x % 21;
+                     const uint8_t* __restrict__ valid, int ring_n, int by_per) {
+    // One CTA = `by_per` of the 21 block rows of one image (a block row: 16 source rows of 84 pixels -> 21 output pixels
+    // of 64 channels = 5.4 KB of fp32 + 2.7 KB of bf16).  One block row per CTA (172,032 CTAs for a 64-environment chunk)
+    // left the kernel bound by CTA turnover at 3.3 TB/s of writes; the tile is double-buffered so that a block row costs
+    // one barrier.
+    __shared__ float4 tile[2][16][21];
+    const int groups = 21 / by_per;
+    const int b = blockIdx.x / groups, by0 = (blockIdx.x % groups) * by_per;
     const long row = idx ? (long)idx[b] : b;
     const long slot = scatter ? row : b;                                 // scatter: image slot = source row
     const int i = threadIdx.x;
-    if (i < 336) {
-        const int r = i / 21, bx = i % 21;                       // r = c * 4 + dy
-        long src = ((row * 4 + (r >> 2)) * 84 + (by * 4 + (r & 3))) * 84 + bx * 4;
-        float4 v;
-        if (sizeof(T) == 1 && valid != nullptr) {
-            const int c = r >> 2;
-            const long t = row / ring_n, n = row - t * ring_n;
-            src = (((t + c) * ring_n + n) * 84 + (by * 4 + (r & 3))) * 84 + bx * 4;
-            uchar4 u = make_uchar4(0, 0, 0, 0);
-            if (c >= 4 - (int)valid[row]) u = *reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(frames) + src);
-            v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
-        } else if (sizeof(T) == 1) {
-            const uchar4 u = *reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(frames) + src);
-            v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
-        } else {
-            v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(frames) + src);
-        }
-        tile[r][bx] = v;
+    const int r = i / 21, bx = i % 21;                                   // load role: r = c * 4 + dy
+    const int sbx = i >> 4, sr = i & 15;                                 // store role
+    const bool ring = sizeof(T) == 1 && valid != nullptr;
+    long t = 0, n = 0;
+    int first_real = 0;
+    if (ring) {
+        t = row / ring_n;
+        n = row - t * ring_n;
+        first_real = 4 - (int)valid[row];
     }
-    __syncthreads();
-    if (i < 336) {
-        const int bx = i >> 4, r = i & 15;
-        const float4 v = tile[r][bx];
-        const long o = ((slot * 21 + by) * 21 + bx) * 16 + r;
-        out[o] = v;
-        if (out_lo) out_lo[o] = make_float4(ax_lo(v.x), ax_lo(v.y), ax_lo(v.z), ax_lo(v.w));
-        if (out_b16) {
-            const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
-            uint2 u;
-            u.x = *reinterpret_cast<const uint32_t*>(&p0);
-            u.y = *reinterpret_cast<const uint32_t*>(&p1);
-            out_b16[o] = u;
+    for (int k = 0; k < by_per; ++k) {
+        const int by = by0 + k;
+        if (i < 336) {
+            float4 v;
+            if (ring) {
+                const int c = r >> 2;
+                const long src = (((t + c) * ring_n + n) * 84 + (by * 4 + (r & 3))) * 84 + bx * 4;
+                uchar4 u = make_uchar4(0, 0, 0, 0);
+                if (c >= first_real) u = *reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(frames) + src);
+                v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+            } else {
+                const long src = ((row * 4 + (r >> 2)) * 84 + (by * 4 + (r & 3))) * 84 + bx * 4;
+                if (sizeof(T) == 1) {
+                    const uchar4 u = *reinterpret_cast<const uchar4*>(reinterpret_cast<const uint8_t*>(frames) + src);
+                    v = make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+                } else {
+                    v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(frames) + src);
+                }
+            }
+            tile[k & 1][r][bx] = v;
+        }
+        __syncthreads();
+        if (i < 336) {
+            const float4 v = tile[k & 1][sr][sbx];
+            const long o = ((slot * 21 + by) * 21 + sbx) * 16 + sr;
+            out[o] = v;
+            if (out_lo) out_lo[o] = make_float4(ax_lo(v.x), ax_lo(v.y), ax_lo(v.z), ax_lo(v.w));
+            if (out_b16) {
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+                uint2 u;
+                u.x = *reinterpret_cast<const uint32_t*>(&p0);
+                u.y = *reinterpret_cast<const uint32_t*>(&p1);
+                out_b16[o] = u;
+            }
         }
     }
 }
@@ -315,16 +332,23 @@ int tcx_s2d(float* out, float* out_lo, void* out_b16, const void* frames, int sr
     A2CB_REQUIRE(!valid || (src_is_u8 && C == 4 && H == 84 && W == 84 && S == 4 && ring_n > 0),
                  "tcx_s2d: the frame ring holds uint8 84 x 84 frames stacked 4 deep");
     if (C == 4 && H == 84 && W == 84 && S == 4) {
+        static int by_per = 0;                                   // block rows per CTA: 1, 3, 7 or 21 (A2CB_S2D_BY)
+        if (by_per == 0) {
+            const char* e = getenv("A2CB_S2D_BY");
+            const int v = e ? atoi(e) : 3;
+            by_per = (v == 1 || v == 3 || v == 7 || v == 21) ? v : 3;
+        }
+        const unsigned grid = (unsigned)((long)B * (21 / by_per));
         if (src_is_u8)
-            tcx_s2d_atari_kernel<uint8_t><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
-                                                                               reinterpret_cast<uint2*>(out_b16),
-                                                                               reinterpret_cast<const uint8_t*>(frames), idx, scatter,
-                                                                               valid, ring_n);
+            tcx_s2d_atari_kernel<uint8_t><<<grid, 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
+                                                                 reinterpret_cast<uint2*>(out_b16),
+                                                                 reinterpret_cast<const uint8_t*>(frames), idx, scatter,
+                                                                 valid, ring_n, by_per);
         else
-            tcx_s2d_atari_kernel<float><<<(unsigned)(B * 21), 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
-                                                                             reinterpret_cast<uint2*>(out_b16),
-                                                                             reinterpret_cast<const float*>(frames), idx, scatter,
-                                                                             nullptr, 0);
+            tcx_s2d_atari_kernel<float><<<grid, 352, 0, st>>>(reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(out_lo),
+                                                               reinterpret_cast<uint2*>(out_b16),
+                                                               reinterpret_cast<const float*>(frames), idx, scatter,
+                                                               nullptr, 0, by_per);
         return check_launch("tcx_s2d");
     }
     A2CB_REQUIRE(!out_b16, "tcx_s2d: the bf16 copy is only produced for the Atari geometry");
